@@ -1,0 +1,57 @@
+# Builds everything in-tree (the .so files travel to the GPU box with the gpurun snapshot):
+#   vulkanhybridraytracer_b200/lib/libvkp.so       CUDA kernels + C-ABI (include/vkp.h), sm_100a only
+#   vulkanhybridraytracer_b200/lib/libvkp_host.so  host C++ mirror of the reference API + C shim
+#   vulkanhybridraytracer_b200/bin/vkpinut         headless CLI (replaces src/main.cpp + window.cpp)
+#   oracle/liboracle*.so                           CPU oracle (test infrastructure)
+ROOT   := $(dir $(abspath $(lastword $(MAKEFILE_LIST))))
+PKG    := $(ROOT)vulkanhybridraytracer_b200
+CSRC   := $(PKG)/csrc
+HOST   := $(PKG)/host
+LIBDIR := $(PKG)/lib
+BINDIR := $(PKG)/bin
+OBJDIR := $(ROOT)build
+
+NVCC   ?= /usr/local/cuda/bin/nvcc
+CXX    := $(shell if [ -x /usr/bin/g++ ]; then echo /usr/bin/g++; else echo g++; fi)
+ARCH   := -gencode arch=compute_100a,code=sm_100a
+# -fmad=false: the numerics contract (bit-identical to the scalar fp32 evaluation); explicit __fmaf_rn where safe
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-fvisibility=hidden -ccbin $(CXX) --cudart static \
+           -Xptxas -v -diag-suppress 20012
+CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-unused-variable
+
+CU_SRCS := $(CSRC)/vkp_api.cu $(CSRC)/bvh_build.cu $(CSRC)/kernels_frame.cu
+CU_OBJS := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
+CU_HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard $(ROOT)include/*.h)
+HOST_SRCS := $(HOST)/scene_model.cpp $(HOST)/procedural.cpp $(HOST)/renderer.cpp $(HOST)/output.cpp $(HOST)/host_capi.cpp
+HOST_HDRS := $(wildcard $(HOST)/*.h) $(wildcard $(ROOT)include/*.h)
+
+all: libvkp host oracle
+libvkp: $(LIBDIR)/libvkp.so
+host: $(LIBDIR)/libvkp_host.so $(BINDIR)/vkpinut
+oracle:
+	$(MAKE) -C $(ROOT)oracle
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(CU_HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
+
+$(LIBDIR)/libvkp.so: $(CU_OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared --cudart static -ccbin $(CXX) -o $@ $(CU_OBJS) -lpthread -ldl -lrt
+
+$(LIBDIR)/libvkp_host.so: $(HOST_SRCS) $(HOST_HDRS) $(LIBDIR)/libvkp.so
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) -L$(LIBDIR) -lvkp -lz -Wl,-rpath,'$$ORIGIN'
+
+$(BINDIR)/vkpinut: $(HOST)/main.cpp $(LIBDIR)/libvkp_host.so
+	@mkdir -p $(BINDIR)
+	$(CXX) $(CXXFLAGS) -o $@ $(HOST)/main.cpp -L$(LIBDIR) -lvkp_host -lvkp -Wl,-rpath,'$$ORIGIN/../lib'
+
+sass: $(LIBDIR)/libvkp.so
+	@mkdir -p $(ROOT)profiles
+	/usr/local/cuda/bin/cuobjdump -sass $(LIBDIR)/libvkp.so > $(ROOT)profiles/libvkp.sass
+
+clean:
+	rm -rf $(OBJDIR) $(LIBDIR) $(BINDIR)
+	$(MAKE) -C $(ROOT)oracle clean
+
+.PHONY: all libvkp host oracle clean sass

@@ -1,0 +1,119 @@
+/*
+ * vkp.h -- C-ABI of the B200 hybrid ray-tracing hot path (libvkp.so).
+ *
+ * The reference has no FFI; its de-facto boundary is class Renderer and the buffers it binds
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface it replaces.
+ * Conventions: every call returns 0 on success and a negative vkp_status on failure (the reference
+ * aborts through VK_CHECK, vk_engine.h:15-24; a library must not), vkp_last_error() gives the text,
+ * one context == one GPU == one host thread at a time (the reference is single-threaded, single
+ * queue).  Host pointers are borrowed for the duration of the call only; device memory is owned
+ * by the context.  There is no CPU fallback: without a usable CUDA device vkp_create fails.
+ */
+#ifndef VKP_H
+#define VKP_H
+
+#include "vkp_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define VKP_API
+#else
+#define VKP_API __attribute__((visibility("default")))
+#endif
+
+enum vkp_status {
+    VKP_OK = 0,
+    VKP_ERR_INVALID = -1,   /* bad argument / call order            */
+    VKP_ERR_CUDA = -2,      /* CUDA runtime error (text in last_error) */
+    VKP_ERR_NO_DEVICE = -3, /* no usable sm_100 device              */
+    VKP_ERR_OOM = -4
+};
+
+typedef struct vkp_ctx vkp_ctx;
+
+/* library ------------------------------------------------------------------------------------ */
+VKP_API int         vkp_abi_version(void);
+VKP_API const char* vkp_last_error(const vkp_ctx* ctx);          /* ctx may be NULL: last create error */
+
+/* VulkanEngine::init_vulkan + new Renderer (vk_engine.cpp:236, :50): one context per GPU */
+VKP_API int  vkp_create(vkp_ctx** out, int device_ordinal);
+VKP_API void vkp_destroy(vkp_ctx* ctx);                           /* VulkanEngine::cleanup */
+
+/* geometry & resources --------------------------------------------------------------------- */
+/* Mesh::upload (vk_mesh.cpp:265-359): vertex + index buffers; returns the mesh handle */
+VKP_API int vkp_upload_mesh(vkp_ctx* ctx, const vkp_vertex* vertices, uint32_t n_vertices,
+                            const uint32_t* indices, uint32_t n_indices, int* mesh_id);
+/* vkutil::load_image_from_file (vk_textures.cpp:11-103): R8G8B8A8_UNORM, no mips, NEAREST/REPEAT */
+VKP_API int vkp_upload_texture_rgba8(vkp_ctx* ctx, const uint8_t* rgba, int width, int height, int* tex_id);
+/* hybrid descriptor binding 10, environmentTexture[0] = sky, [1] = irradiance (renderer.cpp:3073-3074) */
+VKP_API int vkp_set_env(vkp_ctx* ctx, int sky_tex_id, int irradiance_tex_id);
+/* binding 9 _matBuffer (renderer.cpp:1488-1499) */
+VKP_API int vkp_set_materials(vkp_ctx* ctx, const vkp_material* materials, int n);
+/* binding 4 _lightBuffer, rewritten every frame by VulkanEngine::update (vk_engine.cpp:146-164) */
+VKP_API int vkp_set_lights(vkp_ctx* ctx, const vkp_light* lights, int n);
+/* Renderer::_tlas + id buffer + matrices buffer (vk_engine.cpp:172-185, vk_mesh.cpp:506-533) */
+VKP_API int vkp_set_instances(vkp_ctx* ctx, const vkp_instance* instances, int n);
+
+/* acceleration structures ------------------------------------------------------------------- */
+/* Renderer::create_bottom_acceleration_structure + buildBlas (renderer.cpp:1643-1753):
+ * one BLAS per distinct (mesh, first_index, index_count) referenced by the instances */
+VKP_API int vkp_build_blas(vkp_ctx* ctx);
+/* Renderer::buildTlas(instances, flags, update) (renderer.cpp:1757-1865); update=1 == MODE_UPDATE refit */
+VKP_API int vkp_build_tlas(vkp_ctx* ctx, int update);
+
+/* per-frame state --------------------------------------------------------------------------- */
+/* VulkanEngine::updateCameraMatrices (vk_engine.cpp:688-741) */
+VKP_API int vkp_set_camera(vkp_ctx* ctx, const vkp_camera* camera);
+VKP_API int vkp_set_params(vkp_ctx* ctx, const vkp_params* params);
+/* multi-GPU: this context renders only tiles t with (t mod world) == rank; world=1 = all */
+VKP_API int vkp_set_tiling(vkp_ctx* ctx, int rank, int world, int tile_w, int tile_h);
+
+/* frame --------------------------------------------------------------------------------------- */
+/* Renderer::render / raytrace / rasterize_hybrid by params.mode (renderer.cpp:403, :465, :530).
+ * Asynchronous on the context stream. */
+VKP_API int vkp_render(vkp_ctx* ctx);
+/* a single pass of the frame, for stage-isolated parity tests */
+VKP_API int vkp_run_stage(vkp_ctx* ctx, int stage);
+VKP_API int vkp_sync(vkp_ctx* ctx);                                /* vkQueueWaitIdle */
+/* VulkanEngine::resetFrame (vk_engine.cpp:683): zero the denoise / accumulation history */
+VKP_API int vkp_reset_history(vkp_ctx* ctx);
+
+/* results ------------------------------------------------------------------------------------- */
+VKP_API int vkp_plane_bytes(const vkp_ctx* ctx, int plane, size_t* bytes);
+VKP_API int vkp_readback(vkp_ctx* ctx, int plane, void* dst, size_t bytes);       /* syncs */
+VKP_API int vkp_upload_plane(vkp_ctx* ctx, int plane, const void* src, size_t bytes);
+VKP_API int vkp_plane_device_ptr(vkp_ctx* ctx, int plane, void** device_ptr, size_t* bytes);
+VKP_API int vkp_get_counters(vkp_ctx* ctx, vkp_counters* out);                    /* syncs */
+VKP_API int vkp_set_profiling(vkp_ctx* ctx, int on);            /* per-stage CUDA events on/off */
+
+/* traceRayEXT made explicit: trace n rays against the current TLAS (host buffers). any_hit != 0
+ * == gl_RayFlagsTerminateOnFirstHitEXT|SkipClosestHitShaderEXT: only hit.t >= 0 / < 0 is defined */
+VKP_API int vkp_trace_rays(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, vkp_hit* hits);
+
+/* BVH introspection (tests): copy out the nodes and the leaf-ordered primitive ids of one BLAS
+ * (index = order of first use in vkp_set_instances) or of the TLAS (blas_index = -1) */
+VKP_API int vkp_bvh_info(vkp_ctx* ctx, int blas_index, uint32_t* n_nodes, uint32_t* n_prims);
+VKP_API int vkp_bvh_download(vkp_ctx* ctx, int blas_index, vkp_bvh_node* nodes, uint32_t* prim_ids);
+
+/* device-side timing on the context stream (CUDA events) */
+VKP_API int vkp_timer_begin(vkp_ctx* ctx);
+VKP_API int vkp_timer_end(vkp_ctx* ctx, float* elapsed_ms);                       /* syncs */
+/* write > L2-size bytes so the next timed frame starts with a cold L2 */
+VKP_API int vkp_flush_l2(vkp_ctx* ctx);
+
+/* multi-GPU composite: gather this rank's tiles of a plane into a dense buffer
+ * (pack) and scatter packed tiles of rank r of `world` into the full-frame plane (unpack).
+ * Buffers are DEVICE pointers so they can be handed to NCCL / peer copies without staging. */
+VKP_API int vkp_tiles_packed_bytes(const vkp_ctx* ctx, int plane, int rank, int world, size_t* bytes);
+VKP_API int vkp_tiles_pack(vkp_ctx* ctx, int plane, void* device_dst, size_t bytes);
+VKP_API int vkp_tiles_unpack(vkp_ctx* ctx, int plane, int rank, int world, const void* device_src, size_t bytes);
+/* run subsequent work on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
+VKP_API int vkp_set_stream(vkp_ctx* ctx, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VKP_H */

@@ -1,0 +1,150 @@
+/*
+ * vkp_types.h -- plain-old-data layouts crossing the C-ABI.
+ *
+ * Every struct mirrors a buffer the reference binds in its hybrid / shadow
+ * descriptor sets (renderer.cpp:2932-2958, :1932-1949); byte layouts follow the
+ * reference structs so a maintainer can memcpy the same host data.
+ * Matrices are column-major float[16] (GLM convention, m[col*4+row]).
+ */
+#ifndef VKP_TYPES_H
+#define VKP_TYPES_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* src/vk_mesh.h:21-27  Vertex {vec3 position, normal, color; vec2 uv} = 44 B */
+typedef struct vkp_vertex {
+    float position[3];
+    float normal[3];
+    float color[3];
+    float uv[2];
+} vkp_vertex;
+
+/* src/material.h:5-10 GPUMaterial, packed by Material::materialToShader (material.cpp:19-26):
+ * diffuse = (r,g,b, ior); textures = (diffuse, normal, emissive, metallicRoughness; -1 = none);
+ * shadingMetallicRoughness = (shadingModel, metallic, roughness, materialIndex). 48 B */
+typedef struct vkp_material {
+    float diffuse[4];
+    float textures[4];
+    float shadingMetallicRoughness[4];
+} vkp_material;
+
+/* src/vk_engine.h:76-80 uboLight (std140 Light, helpers.glsl:18-22). 48 B
+ * position.w = maxDistance (point) or -1 (directional); color.w = intensity. */
+typedef struct vkp_light {
+    float position[4];
+    float color[4];
+    float radius;
+    float _pad[3];
+} vkp_light;
+
+/* One TLAS instance == one primitive (vk_mesh.cpp:472-492, renderer.cpp:1895-1916) plus the
+ * id record (instanceID, materialID, transformID, firstIndex) of vk_mesh.cpp:521-533 and the
+ * model / inverse pair the reference pushes as constants (vk_mesh.h:55-58 ModelMatrices). */
+typedef struct vkp_instance {
+    int32_t  mesh_id;       /* handle returned by vkp_upload_mesh                      */
+    uint32_t first_index;   /* Primitive::firstIndex                                   */
+    uint32_t index_count;   /* Primitive::indexCount (3 * triangles)                   */
+    int32_t  material_id;   /* Primitive::materialID                                   */
+    float    model[16];     /* obj->m_matrix * node global matrix                      */
+    float    inv_model[16]; /* inverse(model), computed by the host (glm::inverse)     */
+} vkp_instance;
+
+/* GPUCameraData (vk_engine.h:48-54, 256 B) + RTCameraData (vk_engine.h:56-62) */
+typedef struct vkp_camera {
+    float view[16];
+    float proj[16];        /* already with proj[1][1] *= -1 (vk_engine.cpp:695) */
+    float prev_view[16];
+    float prev_proj[16];
+    float inv_view[16];
+    float inv_proj[16];
+    float position[4];     /* _cameraPositionBuffer (vk_engine.cpp:699-702) */
+} vkp_camera;
+
+/* src/vk_engine.h:42-46 */
+enum vkp_render_mode { VKP_MODE_DEFERRED = 0, VKP_MODE_RAYTRACING = 1, VKP_MODE_HYBRID = 2 };
+
+typedef struct vkp_params {
+    int32_t width, height;
+    int32_t mode;                    /* vkp_render_mode                                            */
+    int32_t spp;                     /* NSAMPLES (helpers.glsl:6) made runtime; raytraced mode     */
+    int32_t shadow_samples;          /* VulkanEngine::_samples, 1..64 (renderer.cpp:656)           */
+    int32_t max_bounces;             /* MAX_RECURSION (helpers.glsl:8) = 8                         */
+    int32_t frame;                   /* RTCameraData.frame = _denoise ? _denoise_frame : 0         */
+    int32_t denoise_frame;           /* blur.comp frameBuffer.frame = _denoise_frame (always)      */
+    int32_t faithful_rng;            /* 1: sampleDisk gets the seed by value (helpers.glsl:82)     */
+    int32_t denoise_cover_remainder; /* 0: dispatch W/16 x H/16 groups exactly (renderer.cpp:2672) */
+    int32_t debug_target;            /* deferred.frag debug.target 0..6                            */
+    int32_t reserved[5];
+} vkp_params;
+
+/* Planes readable with vkp_readback / writable with vkp_upload_plane.  Layouts are row-major,
+ * pixel (x,y) at index y*W+x, formats follow renderer.cpp:255-261 and :1535-1538. */
+enum vkp_plane {
+    VKP_PLANE_POSITION   = 0,  /* 4 x fp16 : world pos xyz, materialIdx              (8 B/px) */
+    VKP_PLANE_NORMAL     = 1,  /* 4 x fp16 : N*0.5+0.5, 1   (background: 0,0,0,0)    (8 B/px) */
+    VKP_PLANE_ALBEDO     = 2,  /* 4 x u8   : albedo rgb, 255                         (4 B/px) */
+    VKP_PLANE_MOTION     = 3,  /* 2 x fp16 : motion*0.5+0.5                          (4 B/px) */
+    VKP_PLANE_MATERIAL   = 4,  /* 4 x u8   : (0, roughness, metallic, 255)           (4 B/px) */
+    VKP_PLANE_EMISSIVE   = 5,  /* 4 x u8   : emissive rgb, 255                       (4 B/px) */
+    VKP_PLANE_HIT_IDS    = 6,  /* 2 x i32  : primary hit (instance, primitive), -1 = miss (debug, 8 B/px) */
+    VKP_PLANE_FINAL_F32  = 7,  /* 4 x f32  : linear radiance before the 8-bit store (16 B/px) */
+    VKP_PLANE_FINAL_SRGB8= 8,  /* 4 x u8   : RGBA after unorm8 store + postFragment.frag gamma */
+    VKP_PLANE_SHADOW0    = 16, /* + light index: 1 x u8 R8_UNORM shadowImage[i]       (1 B/px) */
+    VKP_PLANE_DENOISED0  = 48  /* + light index: 1 x u8 R8_UNORM _denoisedImages[i]   (1 B/px) */
+};
+#define VKP_MAX_LIGHTS 32
+
+/* Pipeline stages, for stage-isolated parity tests (vkp_run_stage) */
+enum vkp_stage {
+    VKP_STAGE_GBUFFER  = 0,  /* a3: basic.vert + geometry_shader.frag + skybox.frag        */
+    VKP_STAGE_SHADOW   = 1,  /* a4: shadowRaygen.rgen + shadow.rmiss                        */
+    VKP_STAGE_DENOISE  = 2,  /* a5: blur.comp                                               */
+    VKP_STAGE_RESOLVE  = 3,  /* a6+a7+a8: hybridRaygen.rgen + hybridHit.rchit + miss.rmiss  */
+    VKP_STAGE_POST     = 4,  /* a10: postFragment.frag                                      */
+    VKP_STAGE_RAYTRACE = 5,  /* a11: raygen.rgen + closesthit.rchit                         */
+    VKP_STAGE_DEFERRED = 6   /* a12: deferred.frag                                          */
+};
+
+/* Ray / hit records for vkp_trace_rays (the traceRayEXT contract made explicit) */
+typedef struct vkp_ray {
+    float origin[3]; float tmin;
+    float dir[3];    float tmax;
+} vkp_ray;
+
+typedef struct vkp_hit {
+    float   t;          /* gl_HitTEXT, or -1 on miss                         */
+    float   u, v;       /* hitAttributeEXT attribs.xy                        */
+    int32_t instance;   /* gl_InstanceCustomIndexEXT, -1 on miss             */
+    int32_t primitive;  /* gl_PrimitiveID, -1 on miss                        */
+} vkp_hit;
+
+typedef struct vkp_counters {
+    uint64_t rays_primary;          /* our G-buffer visibility rays (reported separately)  */
+    uint64_t rays_shadow;           /* shadowRaygen.rgen:78                                */
+    uint64_t rays_reflect;          /* hybridRaygen.rgen:158 / raygen.rgen:49              */
+    uint64_t rays_secondary_shadow; /* hybridHit.rchit:123 / closesthit.rchit:111          */
+    float    ms_stage[8];           /* per vkp_stage, valid when profiling is on           */
+    float    ms_tlas;
+    float    ms_frame;
+    uint32_t kernel_launches;       /* kernels launched by the last vkp_render             */
+    uint32_t _pad;
+} vkp_counters;
+
+/* 32-byte BVH node (both BLAS and TLAS).  ref: bit31 = leaf; leaf: bits[30:3] = first item,
+ * bits[2:0] = count-1 ... see DESIGN.md "BVH layout". */
+typedef struct vkp_bvh_node {
+    float    bmin[3];
+    uint32_t ref;
+    float    bmax[3];
+    uint32_t aux;
+} vkp_bvh_node;
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VKP_TYPES_H */

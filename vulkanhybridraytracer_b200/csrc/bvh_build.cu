@@ -1,0 +1,381 @@
+// bvh_build.cu -- acceleration-structure build on the GPU: what vkCmdBuildAccelerationStructuresKHR does for the
+// reference (renderer.cpp:1747 buildBlas, :1853 buildTlas / MODE_UPDATE refit).
+//
+// Morton-code LBVH (Karras 2012): primitive boxes -> centroid bounds -> 30-bit Morton keys -> radix sort ->
+// binary radix tree (one thread per internal node) -> bottom-up AABB fit with atomic arrival flags ->
+// collapse sub-trees of <= leaf_max primitives into leaves and emit the 32-byte sibling-pair node array
+// described in vkp_bvh.cuh.  Refit re-runs only fit + emit on the stored topology.
+#include "vkp_internal.h"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <math_constants.h>
+
+namespace {
+
+__device__ __forceinline__ int float_to_ordered(float f)
+{
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// ---- primitive boxes -----------------------------------------------------------------------------------------
+// BLAS input of Node::node_to_geometry (vk_mesh.cpp:424-470): R32G32B32 positions at stride sizeof(Vertex) = 44,
+// uint32 indices starting at firstIndex
+__global__ void k_triangle_boxes(const vkp_vertex* __restrict__ verts, const uint32_t* __restrict__ indices, uint32_t n, float* __restrict__ boxes)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t i0 = indices[3 * i], i1 = indices[3 * i + 1], i2 = indices[3 * i + 2];
+    const float* a = verts[i0].position; const float* b = verts[i1].position; const float* c = verts[i2].position;
+    float* o = boxes + 6 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        o[k] = fminf(fminf(a[k], b[k]), c[k]);
+        o[3 + k] = fmaxf(fmaxf(a[k], b[k]), c[k]);
+    }
+}
+
+// TLAS input of Renderer::object_to_instance (renderer.cpp:1895-1916): world box of the instance = box of the 8
+// transformed corners of its BLAS root, padded by 1e-5 relative (the object-space hit is exact inside the
+// object box, the world box only to rounding)
+__global__ void k_instance_boxes(const DInstance* __restrict__ inst, uint32_t n, float* __restrict__ boxes)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DInstance& I = inst[i];
+    const float4* root = reinterpret_cast<const float4*>(I.nodes);
+    float4 lo = root[0], hi = root[1];
+    float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (int c = 0; c < 8; c++) {
+        float3 p = make_float3((c & 1) ? hi.x : lo.x, (c & 2) ? hi.y : lo.y, (c & 4) ? hi.z : lo.z);
+        float3 w = xform_point(I.model, p);
+        mn[0] = fminf(mn[0], w.x); mn[1] = fminf(mn[1], w.y); mn[2] = fminf(mn[2], w.z);
+        mx[0] = fmaxf(mx[0], w.x); mx[1] = fmaxf(mx[1], w.y); mx[2] = fmaxf(mx[2], w.z);
+    }
+    float* o = boxes + 6 * (size_t)i;
+    for (int k = 0; k < 3; k++) {
+        float e = 1e-5f * fmaxf(fmaxf(fabsf(mn[k]), fabsf(mx[k])), 1e-3f);
+        o[k] = mn[k] - e; o[3 + k] = mx[k] + e;
+    }
+}
+
+// ---- centroid bounds + Morton keys ------------------------------------------------------------------------
+__global__ void k_init_bounds(int* b)
+{
+    if (threadIdx.x < 3) b[threadIdx.x] = 0x7fffffff;
+    else if (threadIdx.x < 6) b[threadIdx.x] = (int)0x80000000;
+}
+
+__global__ void k_centroid_bounds(const float* __restrict__ boxes, uint32_t n, int* __restrict__ bounds)
+{
+    float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* b = boxes + 6 * (size_t)i;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { float c = 0.5f * (b[k] + b[3 + k]); mn[k] = fminf(mn[k], c); mx[k] = fmaxf(mx[k], c); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        for (int off = 16; off; off >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], off));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], off));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { atomicMin(&bounds[k], float_to_ordered(mn[k])); atomicMax(&bounds[3 + k], float_to_ordered(mx[k])); }
+    }
+}
+
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v)
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void k_morton(const float* __restrict__ boxes, uint32_t n, const int* __restrict__ bounds, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* b = boxes + 6 * (size_t)i;
+    uint32_t q[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float lo = ordered_to_float(bounds[k]), hi = ordered_to_float(bounds[3 + k]);
+        float c = 0.5f * (b[k] + b[3 + k]);
+        float ext = hi - lo;
+        float t = ext > 0.0f ? (c - lo) / ext : 0.0f;
+        t = fminf(fmaxf(t * 1024.0f, 0.0f), 1023.0f);
+        q[k] = (uint32_t)t;
+    }
+    keys[i] = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
+    vals[i] = i;
+}
+
+// ---- Karras binary radix tree -------------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const uint32_t* __restrict__ keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = keys[i], b = keys[j];
+    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);   // tie-break on the index: balanced split of duplicates
+    return __clz(a ^ b);
+}
+
+__global__ void k_hierarchy(const uint32_t* __restrict__ keys, int n, int2* __restrict__ child, int* __restrict__ parent, int2* __restrict__ range)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int first = min(i, j), last = max(i, j);
+    int left = (first == gamma) ? ~gamma : gamma;
+    int right = (last == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    child[i] = make_int2(left, right);
+    range[i] = make_int2(first, last);
+    // parents: internals in [0, n-1), leaves in [n-1, 2n-1)
+    if (left >= 0) parent[left] = i; else parent[(n - 1) + (~left)] = i;
+    if (right >= 0) parent[right] = i; else parent[(n - 1) + (~right)] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+// ---- bottom-up fit ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_box(const float* __restrict__ boxes, const uint32_t* __restrict__ items, const float4* ibox,
+                                         int c, float4& lo, float4& hi)
+{
+    if (c < 0) {
+        const float* b = boxes + 6 * (size_t)items[~c];
+        lo = make_float4(b[0], b[1], b[2], 0.f); hi = make_float4(b[3], b[4], b[5], 0.f);
+    } else {
+        lo = __ldcg(&ibox[2 * (size_t)c]); hi = __ldcg(&ibox[2 * (size_t)c + 1]);
+    }
+}
+
+__global__ void k_fit(const float* __restrict__ boxes, const uint32_t* __restrict__ items, int n, const int2* __restrict__ child,
+                      const int* __restrict__ parent, float4* ibox, int* flags, int* height_out)
+{
+    int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n) return;
+    int p = parent[(n - 1) + leaf];
+    int h = 1;
+    while (p >= 0) {
+        __threadfence();
+        int old = atomicAdd(&flags[p], 1);
+        if (old == 0) return;                // the sibling sub-tree is not finished yet
+        int2 c = child[p];
+        float4 l0, h0, l1, h1;
+        load_box(boxes, items, ibox, c.x, l0, h0);
+        load_box(boxes, items, ibox, c.y, l1, h1);
+        // heights ride in the w components
+        float hl = c.x < 0 ? 0.f : l0.w, hr = c.y < 0 ? 0.f : l1.w;
+        float hh = fmaxf(hl, hr) + 1.0f;
+        float4 lo = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), hh);
+        float4 hi = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
+        __stcg(&ibox[2 * (size_t)p], lo); __stcg(&ibox[2 * (size_t)p + 1], hi);
+        h = (int)hh;
+        if (p == 0) *height_out = h;
+        p = parent[p];
+    }
+}
+
+// ---- collapse + emit ----------------------------------------------------------------------------------------
+__global__ void k_mark_keep(const int2* __restrict__ range, int n_internal, int leaf_max, uint32_t* __restrict__ keep)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal) return;
+    int2 r = range[i];
+    keep[i] = (r.y - r.x + 1) > leaf_max ? 1u : 0u;
+}
+
+__global__ void k_emit_nodes(const float* __restrict__ boxes, const uint32_t* __restrict__ items, int n, const int2* __restrict__ child,
+                             const int2* __restrict__ range, const float4* __restrict__ ibox, const uint32_t* __restrict__ keep,
+                             const uint32_t* __restrict__ rank, vkp_bvh_node* __restrict__ nodes)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n - 1) return;
+    if (k == 0) {
+        // root
+        float4 lo = ibox[0], hi = ibox[1];
+        vkp_bvh_node r;
+        r.bmin[0] = lo.x; r.bmin[1] = lo.y; r.bmin[2] = lo.z; r.bmax[0] = hi.x; r.bmax[1] = hi.y; r.bmax[2] = hi.z;
+        r.ref = keep[0] ? 1u : (0x80000000u | ((uint32_t)range[0].x << 3) | (uint32_t)(range[0].y - range[0].x));
+        r.aux = (uint32_t)(range[0].y - range[0].x + 1);
+        nodes[0] = r;
+    }
+    if (!keep[k]) return;
+    uint32_t slot = 1u + 2u * rank[k];
+    int2 c = child[k];
+    int cc[2] = {c.x, c.y};
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        vkp_bvh_node nd;
+        int ci = cc[s];
+        if (ci < 0) {
+            int pos = ~ci;
+            const float* b = boxes + 6 * (size_t)items[pos];
+            nd.bmin[0] = b[0]; nd.bmin[1] = b[1]; nd.bmin[2] = b[2]; nd.bmax[0] = b[3]; nd.bmax[1] = b[4]; nd.bmax[2] = b[5];
+            nd.ref = 0x80000000u | ((uint32_t)pos << 3);
+            nd.aux = 1u;
+        } else {
+            float4 lo = ibox[2 * (size_t)ci], hi = ibox[2 * (size_t)ci + 1];
+            nd.bmin[0] = lo.x; nd.bmin[1] = lo.y; nd.bmin[2] = lo.z; nd.bmax[0] = hi.x; nd.bmax[1] = hi.y; nd.bmax[2] = hi.z;
+            int2 r = range[ci];
+            nd.ref = keep[ci] ? (1u + 2u * rank[ci]) : (0x80000000u | ((uint32_t)r.x << 3) | (uint32_t)(r.y - r.x));
+            nd.aux = (uint32_t)(r.y - r.x + 1);
+        }
+        nodes[slot + s] = nd;
+    }
+}
+
+__global__ void k_emit_single(const float* __restrict__ boxes, int n, vkp_bvh_node* __restrict__ nodes)
+{
+    vkp_bvh_node r;
+    if (n == 1) {
+        for (int k = 0; k < 3; k++) { r.bmin[k] = boxes[k]; r.bmax[k] = boxes[3 + k]; }
+        r.ref = 0x80000000u; r.aux = 1u;
+    } else {
+        for (int k = 0; k < 3; k++) { r.bmin[k] = CUDART_INF_F; r.bmax[k] = -CUDART_INF_F; }
+        r.ref = 0x80000000u; r.aux = 0u;
+    }
+    nodes[0] = r;
+}
+
+__global__ void k_emit_triangles(const vkp_vertex* __restrict__ verts, const uint32_t* __restrict__ indices, const uint32_t* __restrict__ items,
+                                 uint32_t n, float4* __restrict__ tris)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t prim = items[i];
+    uint32_t i0 = indices[3 * prim], i1 = indices[3 * prim + 1], i2 = indices[3 * prim + 2];
+    const float* a = verts[i0].position; const float* b = verts[i1].position; const float* c = verts[i2].position;
+    tris[3 * (size_t)i + 0] = make_float4(a[0], a[1], a[2], __int_as_float((int)prim));
+    tris[3 * (size_t)i + 1] = make_float4(b[0], b[1], b[2], 0.f);
+    tris[3 * (size_t)i + 2] = make_float4(c[0], c[1], c[2], 0.f);
+}
+
+inline unsigned blocks_for(uint32_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+cudaError_t fit_and_emit(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches)
+{
+    const uint32_t n = B.n_prims;
+    cudaError_t e;
+    if (n <= 1) {
+        k_emit_single<<<1, 1, 0, s>>>(sc.boxes.as<float>(), (int)n, B.nodes.as<vkp_bvh_node>());
+        if (launches) *launches += 1;
+        B.n_nodes = 1; B.height = 0;
+        return cudaGetLastError();
+    }
+    if ((e = cudaMemsetAsync(B.flags.p, 0, sizeof(int) * (n - 1), s)) != cudaSuccess) return e;
+    int* height_dev = sc.misc.as<int>();
+    if ((e = cudaMemsetAsync(height_dev, 0, sizeof(int), s)) != cudaSuccess) return e;
+    k_fit<<<blocks_for(n, 256), 256, 0, s>>>(sc.boxes.as<float>(), B.items.as<uint32_t>(), (int)n, B.child.as<int2>(), B.parent.as<int>(),
+                                             B.ibox.as<float4>(), B.flags.as<int>(), height_dev);
+    k_emit_nodes<<<blocks_for(n - 1, 256), 256, 0, s>>>(sc.boxes.as<float>(), B.items.as<uint32_t>(), (int)n, B.child.as<int2>(), B.range.as<int2>(),
+                                                        B.ibox.as<float4>(), B.keep.as<uint32_t>(), B.rank.as<uint32_t>(), B.nodes.as<vkp_bvh_node>());
+    if (launches) *launches += 2;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return cudaMemcpyAsync(&B.height, height_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
+}
+
+} // namespace
+
+cudaError_t bvh_triangle_boxes(cudaStream_t s, const vkp_vertex* verts, const uint32_t* indices, uint32_t n_tris, float* boxes)
+{
+    if (n_tris == 0) return cudaSuccess;
+    k_triangle_boxes<<<blocks_for(n_tris, 256), 256, 0, s>>>(verts, indices, n_tris, boxes);
+    return cudaGetLastError();
+}
+
+cudaError_t bvh_instance_boxes(cudaStream_t s, const DInstance* inst, uint32_t n, float* boxes)
+{
+    if (n == 0) return cudaSuccess;
+    k_instance_boxes<<<blocks_for(n, 128), 128, 0, s>>>(inst, n, boxes);
+    return cudaGetLastError();
+}
+
+cudaError_t bvh_build(cudaStream_t s, BuildScratch& sc, uint32_t n, int leaf_max, Bvh& B, int* launches)
+{
+    cudaError_t e;
+    B.n_prims = n; B.leaf_max = leaf_max;
+    const uint32_t ni = n > 1 ? n - 1 : 0;
+    if ((e = B.nodes.ensure(sizeof(vkp_bvh_node) * (2 * (size_t)ni + 1))) != cudaSuccess) return e;
+    if ((e = B.items.ensure(sizeof(uint32_t) * (size_t)(n ? n : 1))) != cudaSuccess) return e;
+    if ((e = sc.misc.ensure(256)) != cudaSuccess) return e;
+    if (n <= 1) {
+        if (n == 1 && (e = cudaMemsetAsync(B.items.p, 0, sizeof(uint32_t), s)) != cudaSuccess) return e;
+        return fit_and_emit(s, sc, B, launches);
+    }
+    if ((e = B.child.ensure(sizeof(int2) * ni)) != cudaSuccess) return e;
+    if ((e = B.range.ensure(sizeof(int2) * ni)) != cudaSuccess) return e;
+    if ((e = B.parent.ensure(sizeof(int) * (ni + (size_t)n))) != cudaSuccess) return e;
+    if ((e = B.ibox.ensure(sizeof(float4) * 2 * ni)) != cudaSuccess) return e;
+    if ((e = B.flags.ensure(sizeof(int) * ni)) != cudaSuccess) return e;
+    if ((e = B.rank.ensure(sizeof(uint32_t) * ni)) != cudaSuccess) return e;
+    if ((e = B.keep.ensure(sizeof(uint32_t) * ni)) != cudaSuccess) return e;
+    if ((e = sc.keys.ensure(sizeof(uint32_t) * (size_t)n)) != cudaSuccess) return e;
+    if ((e = sc.keys_alt.ensure(sizeof(uint32_t) * (size_t)n)) != cudaSuccess) return e;
+    if ((e = sc.vals.ensure(sizeof(uint32_t) * (size_t)n)) != cudaSuccess) return e;
+    if ((e = sc.bounds.ensure(64)) != cudaSuccess) return e;
+
+    k_init_bounds<<<1, 32, 0, s>>>(sc.bounds.as<int>());
+    unsigned rb = blocks_for(n, 256); if (rb > 592) rb = 592;
+    k_centroid_bounds<<<rb, 256, 0, s>>>(sc.boxes.as<float>(), n, sc.bounds.as<int>());
+    k_morton<<<blocks_for(n, 256), 256, 0, s>>>(sc.boxes.as<float>(), n, sc.bounds.as<int>(), sc.keys.as<uint32_t>(), sc.vals.as<uint32_t>());
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, sc.keys.as<uint32_t>(), sc.keys_alt.as<uint32_t>(), sc.vals.as<uint32_t>(), B.items.as<uint32_t>(), (int)n, 0, 30, s);
+    size_t tmp2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, B.keep.as<uint32_t>(), B.rank.as<uint32_t>(), (int)ni, s);
+    if (tmp2 > tmp) tmp = tmp2;
+    if ((e = sc.cub_tmp.ensure(tmp)) != cudaSuccess) return e;
+    size_t tbytes = sc.cub_tmp.bytes;
+    if ((e = cub::DeviceRadixSort::SortPairs(sc.cub_tmp.p, tbytes, sc.keys.as<uint32_t>(), sc.keys_alt.as<uint32_t>(), sc.vals.as<uint32_t>(),
+                                             B.items.as<uint32_t>(), (int)n, 0, 30, s)) != cudaSuccess) return e;
+    k_hierarchy<<<blocks_for(ni, 256), 256, 0, s>>>(sc.keys_alt.as<uint32_t>(), (int)n, B.child.as<int2>(), B.parent.as<int>(), B.range.as<int2>());
+    k_mark_keep<<<blocks_for(ni, 256), 256, 0, s>>>(B.range.as<int2>(), (int)ni, leaf_max, B.keep.as<uint32_t>());
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    tbytes = sc.cub_tmp.bytes;
+    if ((e = cub::DeviceScan::ExclusiveSum(sc.cub_tmp.p, tbytes, B.keep.as<uint32_t>(), B.rank.as<uint32_t>(), (int)ni, s)) != cudaSuccess) return e;
+    if (launches) *launches += 8;   // own kernels + the sort / scan passes
+    // number of emitted nodes = 1 + 2 * (#kept internals)
+    uint32_t last_rank = 0, last_keep = 0;
+    if ((e = cudaMemcpyAsync(&last_rank, B.rank.as<uint32_t>() + (ni - 1), 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(&last_keep, B.keep.as<uint32_t>() + (ni - 1), 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    if ((e = fit_and_emit(s, sc, B, launches)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    B.n_nodes = 1u + 2u * (last_rank + last_keep);
+    return cudaSuccess;
+}
+
+cudaError_t bvh_refit(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches)
+{
+    return fit_and_emit(s, sc, B, launches);
+}
+
+cudaError_t bvh_emit_triangles(cudaStream_t s, const vkp_vertex* verts, const uint32_t* indices, Bvh& B)
+{
+    cudaError_t e;
+    if ((e = B.tris.ensure(sizeof(float4) * 3 * (size_t)(B.n_prims ? B.n_prims : 1))) != cudaSuccess) return e;
+    if (B.n_prims == 0) return cudaSuccess;
+    k_emit_triangles<<<blocks_for(B.n_prims, 256), 256, 0, s>>>(verts, indices, B.items.as<uint32_t>(), B.n_prims, B.tris.as<float4>());
+    return cudaGetLastError();
+}

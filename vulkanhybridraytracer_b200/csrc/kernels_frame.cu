@@ -1,0 +1,699 @@
+// kernels_frame.cu -- the frame kernels of the Hybrid / Raytraced / Deferred pipelines, one per reference GPU
+// program (SURVEY.md section 7 kernel plan):
+//   k_gbuffer   basic.vert + geometry_shader.frag + skybox.frag (G-buffer content, ray-cast primary visibility)
+//   k_shadow    shadowRaygen.rgen + shadow.rmiss (any-hit shadow rays seeded from the G-buffer)
+//   k_denoise   blur.comp
+//   k_resolve   hybridRaygen.rgen + hybridHit.rchit + miss.rmiss (+ postFragment.frag fused into the store)
+//   k_raytrace  raygen.rgen + closesthit.rchit + miss.rmiss
+//   k_deferred  deferred.frag
+//   k_post      postFragment.frag (stand-alone, for stage tests and the non-fused modes)
+// Thread mapping: one thread per pixel; a warp covers an 8x4 pixel patch (coherent rays, 64-byte row segments
+// for the fp16x4 planes), a 128-thread CTA covers a 16x8 block; CTAs enumerate only the screen tiles this
+// rank owns (tile t belongs to rank t % world).
+#include "vkp_internal.h"
+#include "vkp_bvh.cuh"
+
+namespace {
+
+struct Pixel { int x, y; bool valid; };
+
+__device__ __forceinline__ Pixel pixel_of_thread(const DFrame& F)
+{
+    const int bpt_x = F.tile_w >> 4, bpt_y = F.tile_h >> 3;
+    const int bpt = bpt_x * bpt_y;
+    const int own_tile = blockIdx.x / bpt, sub = blockIdx.x - own_tile * bpt;
+    const int tile = F.rank + own_tile * F.world;
+    const int tx = tile % F.tiles_x, ty = tile / F.tiles_x;
+    const int sbx = sub % bpt_x, sby = sub / bpt_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Pixel p;
+    p.x = tx * F.tile_w + sbx * 16 + (warp & 1) * 8 + (lane & 7);
+    p.y = ty * F.tile_h + sby * 8 + (warp >> 1) * 4 + (lane >> 3);
+    p.valid = p.x < F.p.width && p.y < F.p.height;
+    return p;
+}
+
+__device__ __forceinline__ void add_counter(unsigned long long* counters, int slot, unsigned int n)
+{
+    for (int off = 16; off; off >>= 1) n += __shfl_xor_sync(0xffffffffu, n, off);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&counters[slot], (unsigned long long)n);
+}
+
+// image store into the B8G8R8A8_UNORM target (renderer.cpp:1535) followed by postFragment.frag:9-21
+__device__ __forceinline__ uchar4 post_pixel(float4 c)
+{
+    float r = (float)vkp_unorm8(c.x) / 255.0f, g = (float)vkp_unorm8(c.y) / 255.0f, b = (float)vkp_unorm8(c.z) / 255.0f;
+    const float gamma = 1.0f / 2.2f;
+    r = vkp_powf(fmaxf(r, 0.001f), gamma); g = vkp_powf(fmaxf(g, 0.001f), gamma); b = vkp_powf(fmaxf(b, 0.001f), gamma);
+    return make_uchar4(vkp_unorm8(r), vkp_unorm8(g), vkp_unorm8(b), vkp_unorm8(c.w));
+}
+
+struct Payload { float3 color; float dist; float3 direction; float scatter; float3 origin; uint32_t seed; };
+
+// miss.rmiss:13-19
+__device__ __forceinline__ void shade_miss(const DScene& S, float3 rayDir, Payload& prd)
+{
+    float3 dir = normalize3(rayDir);
+    float2 uv = equirect_uv(dir, VKP_PI_MISS);
+    prd.color = pow3(xyz(tex_nearest(S.textures[S.sky_tex], uv.x, uv.y)), 2.2f);
+    prd.dist = -1.0f;
+}
+
+// hybridHit.rchit:24-184 (RT == false) / closesthit.rchit:26-186 (RT == true)
+template <bool RT>
+__device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, float3 rayD, const HitRec& h, Payload& prd,
+                          unsigned int& n_secondary)
+{
+    const DInstance& I = S.instances[h.inst];
+    const float b0 = 1.0f - h.u - h.v, b1 = h.u, b2 = h.v;
+    const uint32_t* ind = I.indices + 3u * (uint32_t)h.prim;
+    const vkp_vertex& v0 = I.vertices[__ldg(ind)]; const vkp_vertex& v1 = I.vertices[__ldg(ind + 1)]; const vkp_vertex& v2 = I.vertices[__ldg(ind + 2)];
+    const float3 normal = f3(v0.normal[0], v0.normal[1], v0.normal[2]) * b0 + f3(v1.normal[0], v1.normal[1], v1.normal[2]) * b1 +
+                          f3(v2.normal[0], v2.normal[1], v2.normal[2]) * b2;
+    const float uvx = v0.uv[0] * b0 + v1.uv[0] * b1 + v2.uv[0] * b2;
+    const float uvy = v0.uv[1] * b0 + v1.uv[1] * b1 + v2.uv[1] * b2;
+    const float3 N = normalize3(xform_normal_by_inverse(I.inv_model, normal));
+    const float3 V = normalize3(-rayD);
+    const float NdotV = clamp01(dot3(N, V));
+    const float3 worldPos = rayO + rayD * h.t;
+
+    float3 Lo = f3s(0.0f);
+    float attenuation = 1.0f;
+
+    const vkp_material& mat = S.materials[max(0, min(I.material_id, S.n_materials - 1))];
+    const int shadingMode = (int)mat.shadingMetallicRoughness[0];
+    float3 albedo = mat.textures[0] > -1 ? xyz(tex_nearest(S.textures[(int)mat.textures[0]], uvx, uvy)) : f3(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2]);
+    const float3 emissive = mat.textures[2] > -1 ? xyz(tex_nearest(S.textures[(int)mat.textures[2]], uvx, uvy)) : f3s(0.0f);
+    const float3 roughnessMetallic = mat.textures[3] > -1 ? xyz(tex_nearest(S.textures[(int)mat.textures[3]], uvx, uvy))
+                                                          : f3(0.0f, mat.shadingMetallicRoughness[2], mat.shadingMetallicRoughness[1]);
+    albedo = pow3(albedo, 2.2f);
+    const float roughness = roughnessMetallic.y, metallic = roughnessMetallic.z;
+    const float3 F0 = mix3(f3s(0.04f), albedo, metallic);
+
+    const float2 envUV = equirect_uv(N, VKP_PI);
+    const float3 irradiance = xyz(tex_nearest(S.textures[S.irr_tex], envUV.x, envUV.y));
+
+    float3 direction = f3(1.0f, 1.0f, 1.0f);
+    float scatter = 0.0f;
+    const bool advance = P.faithful_rng == 0;
+
+    for (int i = 0; i < S.n_lights; i++) {
+        const vkp_light light = S.lights[i];
+        const float3 lpos = f3(light.position[0], light.position[1], light.position[2]);
+        const float3 lcol = f3(light.color[0], light.color[1], light.color[2]);
+        const bool isDirectional = light.position[3] < 0.0f;
+        float3 L = isDirectional ? lpos : (lpos - worldPos);
+        const float light_max_distance = light.position[3];
+        const float light_distance = length3(L);
+        L = normalize3(L);
+        const float light_intensity = isDirectional ? 1.0f : (light.color[3] / (light_distance * light_distance));
+        const float3 H = normalize3(V + L);
+        const float NdotL = clamp01(dot3(N, L));
+        const float NdotH = clamp01(dot3(N, H));
+        float shadowFactor = RT ? 0.0f : 1.0f;
+
+        if (RT) {
+            if (NdotL > 0.0f) {
+                for (int a = 0; a < P.shadow_samples; a++) {
+                    bool shadowed = true;
+                    if (light_distance < light_max_distance) {
+                        float3 dir = sample_disk(light, worldPos, L, prd.seed, advance);
+                        HitRec sh; n_secondary++;
+                        shadowed = trace_ray<true>(S, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh);
+                    }
+                    if (!shadowed) shadowFactor += 1.0f;
+                }
+                shadowFactor /= (float)P.shadow_samples;
+            }
+            if (light_intensity == 0.0f) attenuation = 0.0f;
+            else {
+                attenuation = light_max_distance - light_distance;
+                attenuation /= light_max_distance;
+                attenuation = fmaxf(attenuation, 0.0f);
+                attenuation = attenuation * attenuation;
+            }
+        } else {
+            if (light_intensity == 0.0f) attenuation = 0.0f;
+            else {
+                attenuation = light_max_distance - light_distance;
+                attenuation /= light_max_distance;
+                attenuation = fmaxf(attenuation, 0.0f);
+                attenuation = isDirectional ? 0.3f : attenuation * attenuation;
+            }
+        }
+
+        if (shadingMode == 0) {
+            if (!RT) {
+                if (NdotL > 0.0f) {
+                    bool shadowed = true;
+                    if (light_distance < light_max_distance) {
+                        float3 dir = sample_disk(light, worldPos, L, prd.seed, advance);
+                        HitRec sh; n_secondary++;
+                        shadowed = trace_ray<true>(S, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh);
+                    }
+                    if (!shadowed) shadowFactor += 1.0f;
+                }
+            }
+            float3 radiance = light_intensity * lcol * attenuation * shadowFactor;
+            float3 F = fresnel_schlick(NdotH, F0);
+            float D = distribution_ggx(N, H, roughness);
+            float G = geometry_smith(N, V, L, roughness);
+            float3 numerator = (D * G) * F;
+            float denominator = fmaxf(4.0f * clamp01(dot3(N, V)) * NdotL, 0.000001f);
+            float3 specular = numerator / denominator;
+            float3 kD = (f3s(1.0f) - F) * (1.0f - metallic);
+            Lo = Lo + (kD * albedo / VKP_PI + specular) * radiance * NdotL;
+            direction = f3(1.0f, 1.0f, 1.0f); scatter = 0.0f;
+        } else if (shadingMode == 3) {
+            const float3 reflected = reflect3(normalize3(rayD), N);
+            const bool isScattered = dot3(reflected, N) > 0.0f;
+            float3 add;
+            if (NdotL > 0.0f && light_intensity > 0.0f)
+                add = RT ? light_intensity * lcol * attenuation * shadowFactor * metallic * albedo
+                         : light_intensity * lcol * attenuation * albedo * metallic;
+            else
+                add = irradiance * albedo * metallic;
+            Lo = Lo + add;
+            direction = reflected; scatter = isScattered ? 1.0f : 0.0f;
+        } else if (shadingMode == 4) {
+            const float ior = mat.diffuse[3];
+            const float NdotVg = dot3(N, normalize3(rayD));
+            const float3 refrNormal = NdotVg > 0.0f ? -N : N;
+            const float refrEta = NdotVg > 0.0f ? 1.0f / ior : ior;
+            Lo = Lo + ((light_intensity > 0.0f) ? light_intensity * lcol * attenuation * albedo * metallic : irradiance * albedo * metallic);
+            float radicand = 1.0f + vkp_powf(refrEta, 2.0f) * (NdotVg * NdotVg - 1.0f);
+            if (radicand < 0.0f) direction = reflect3(rayD, N);
+            else direction = RT ? refract3(rayD, refrNormal, refrEta) : refract3(normalize3(rayD), refrNormal, refrEta);
+            scatter = 1.0f;
+        }
+    }
+
+    float3 F = fresnel_schlick(NdotV, F0);
+    float3 kD = (1.0f - F) * (1.0f - metallic);
+    float3 diffuse = kD * albedo * irradiance;
+    prd.color = Lo + diffuse + emissive;
+    prd.dist = h.t; prd.direction = direction; prd.scatter = scatter; prd.origin = worldPos;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_gbuffer(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    const Pixel px = pixel_of_thread(F);
+    unsigned int nrays = 0;
+    if (px.valid) {
+        const int W = F.p.width, H = F.p.height;
+        const size_t i = (size_t)px.y * W + px.x;
+        float3 o, d; camera_ray(F.cam, px.x, px.y, 0.5f, 0.5f, W, H, o, d);
+        HitRec h; nrays = 1;
+        bool hit = trace_ray<false>(S, o + d * 1e-2f, d, 0.001f, 10000.0f, h);
+        F.hit_ids[i] = make_int2(h.inst, h.prim);
+        if (!hit) {
+            // skybox.frag:16-21
+            F.position[i] = make_uint2(0u, 0u); F.normal[i] = make_uint2(0u, 0u);
+            F.material[i] = make_uchar4(0, 0, 0, 0); F.emissive[i] = make_uchar4(0, 0, 0, 0);
+            F.motion[i] = 0u;
+            float2 uv = equirect_uv(normalize3(d), VKP_PI_MISS);
+            float4 sky = tex_nearest(S.textures[S.sky_tex], uv.x, uv.y);
+            F.albedo[i] = pack_unorm4(sky.x, sky.y, sky.z, sky.w);
+        } else {
+            const DInstance& I = S.instances[h.inst];
+            const uint32_t* ind = I.indices + 3u * (uint32_t)h.prim;
+            const vkp_vertex& v0 = I.vertices[__ldg(ind)]; const vkp_vertex& v1 = I.vertices[__ldg(ind + 1)]; const vkp_vertex& v2 = I.vertices[__ldg(ind + 2)];
+            const float b0 = 1.0f - h.u - h.v, b1 = h.u, b2 = h.v;
+            float3 P0 = xform_point(I.model, f3(v0.position[0], v0.position[1], v0.position[2]));
+            float3 P1 = xform_point(I.model, f3(v1.position[0], v1.position[1], v1.position[2]));
+            float3 P2 = xform_point(I.model, f3(v2.position[0], v2.position[1], v2.position[2]));
+            float3 worldPos = P0 * b0 + P1 * b1 + P2 * b2;
+            float3 n = f3(v0.normal[0], v0.normal[1], v0.normal[2]) * b0 + f3(v1.normal[0], v1.normal[1], v1.normal[2]) * b1 +
+                       f3(v2.normal[0], v2.normal[1], v2.normal[2]) * b2;
+            float3 inNormal = xform_normal_by_inverse(I.inv_model, n);
+            float3 inColor = f3(v0.color[0], v0.color[1], v0.color[2]) * b0 + f3(v1.color[0], v1.color[1], v1.color[2]) * b1 +
+                             f3(v2.color[0], v2.color[1], v2.color[2]) * b2;
+            float uvx = v0.uv[0] * b0 + v1.uv[0] * b1 + v2.uv[0] * b2, uvy = v0.uv[1] * b0 + v1.uv[1] * b1 + v2.uv[1] * b2;
+            const vkp_material& mat = S.materials[max(0, min(I.material_id, S.n_materials - 1))];
+            float3 color = mat.textures[0] > -1 ? xyz(tex_nearest(S.textures[(int)mat.textures[0]], uvx, uvy)) * inColor : f3(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2]);
+            float3 N = normalize3(inNormal);
+            float3 emissive = mat.textures[2] > -1 ? xyz(tex_nearest(S.textures[(int)mat.textures[2]], uvx, uvy)) : f3s(0.0f);
+            float3 material = mat.textures[3] > -1 ? xyz(tex_nearest(S.textures[(int)mat.textures[3]], uvx, uvy))
+                                                   : f3(0.0f, mat.shadingMetallicRoughness[2], mat.shadingMetallicRoughness[1]);
+            float materialIdx = mat.shadingMetallicRoughness[3];
+            F.position[i] = pack_half4(worldPos.x, worldPos.y, worldPos.z, materialIdx);
+            float3 nn = N * 0.5f + f3s(0.5f);
+            F.normal[i] = pack_half4(nn.x, nn.y, nn.z, 1.0f);
+            uchar4 a = pack_unorm4(color.x, color.y, color.z, 1.0f); F.albedo[i] = a;
+            F.material[i] = pack_unorm4(material.x, material.y, material.z, 1.0f);
+            F.emissive[i] = pack_unorm4(emissive.x, emissive.y, emissive.z, 1.0f);
+            float4 wp = make_float4(worldPos.x, worldPos.y, worldPos.z, 1.0f);
+            float4 clip = xform_vec4(F.cam.proj, xform_vec4(F.cam.view, wp));
+            float4 clipPrev = xform_vec4(F.cam.prev_proj, xform_vec4(F.cam.prev_view, wp));
+            float mx = clip.x / clip.w - clipPrev.x / clipPrev.w;
+            float my = clip.y / clip.w - clipPrev.y / clipPrev.w;
+            F.motion[i] = (uint32_t)vkp_f32_to_f16(mx * 0.5f + 0.5f) | ((uint32_t)vkp_f32_to_f16(my * 0.5f + 0.5f) << 16);
+        }
+    }
+    add_counter(F.counters, 0, nrays);
+}
+
+// shadowRaygen.rgen:28-117
+__global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    const Pixel px = pixel_of_thread(F);
+    unsigned int nrays = 0;
+    if (px.valid) {
+        const int W = F.p.width, H = F.p.height;
+        const size_t i = (size_t)px.y * W + px.x;
+        const size_t plane = (size_t)W * H;
+        uint32_t seed = tea16((uint32_t)px.y * (uint32_t)W + (uint32_t)px.x, (uint32_t)F.p.frame);
+        float4 pos4 = unpack_half4(F.position[i]);
+        float4 nrm4 = unpack_half4(F.normal[i]);
+        float3 position = xyz(pos4);
+        float3 normal = xyz(nrm4) * 2.0f - f3s(1.0f);
+        int mode = (int)material_by_float_index(S, pos4.w).shadingMetallicRoughness[0];
+        float3 N = normalize3(normal);
+        if (mode == 4) {
+            for (int l = 0; l < S.n_lights; l++) F.shadow[l * plane + i] = 255;
+        } else {
+            for (int l = 0; l < S.n_lights; l++) {
+                const vkp_light light = S.lights[l];
+                const float3 lpos = f3(light.position[0], light.position[1], light.position[2]);
+                const bool isDirectional = light.position[3] < 0.0f;
+                float3 L = isDirectional ? lpos : (lpos - position);
+                const float light_max_distance = light.position[3];
+                const float light_distance = length3(L);
+                L = normalize3(L);
+                const float NdotL = clamp01(dot3(N, L));
+                float shadowFactor = 0.0f;
+                const int shadowSamples = F.p.shadow_samples;
+                if (NdotL > 0.0f) {
+                    for (int s = 0; s < shadowSamples; s++) {
+                        bool shadowed;
+                        if (light_distance < light_max_distance) {
+                            const float3 dir = sample_disk(light, position, L, seed, F.p.faithful_rng == 0);
+                            HitRec h; nrays++;
+                            shadowed = trace_ray<true>(S, position + dir * 1e-1f, dir, 0.001f, light_distance + 1.0f, h);
+                        } else {
+                            shadowed = false;
+                        }
+                        if (!shadowed) shadowFactor += 1.0f;
+                    }
+                    shadowFactor /= (float)shadowSamples;
+                }
+                F.shadow[l * plane + i] = vkp_unorm8(shadowFactor);
+            }
+        }
+    }
+    add_counter(F.counters, 1, nrays);
+}
+
+// blur.comp:35-82 with runtime W/H/NLIGHTS and an integer motion fetch
+__global__ void __launch_bounds__(128) k_denoise(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    const Pixel px = pixel_of_thread(F);
+    if (!px.valid) return;
+    const int W = F.p.width, H = F.p.height;
+    const size_t i = (size_t)px.y * W + px.x;
+    const size_t plane = (size_t)W * H;
+    const int frame = F.p.denoise_frame;
+    const int Wc = F.p.denoise_cover_remainder ? W : (W / 16) * 16;
+    const int Hc = F.p.denoise_cover_remainder ? H : (H / 16) * 16;
+    const bool covered = px.x < Wc && px.y < Hc;
+    for (int l = 0; l < S.n_lights; l++) {
+        const uint8_t* in = F.shadow + l * plane;
+        const uint8_t* hist = F.denoised + l * plane;
+        uint8_t* out = F.denoised_next + l * plane;
+        if (!covered) { out[i] = hist[i]; continue; }
+        float pixelColor;
+        if (frame > 0) {
+            float center = (float)in[i] / 255.0f;
+            float old = (float)hist[i] / 255.0f;
+            float a = 1.0f / (float)((float)frame + 1.0f);
+            pixelColor = mix1(old, center, a);
+        } else {
+            uint32_t m = F.motion[i];
+            float rx = vkp_f16_to_f32((uint16_t)(m & 0xffffu)) * 2.0f - 1.0f;
+            float lastx = (float)px.x + rx * (float)W, lasty = (float)px.y + rx * (float)H;   // blur.comp:53 (r.x twice)
+            float center = (float)in[i] / 255.0f;
+            float minColor = center, maxColor = center;
+#pragma unroll
+            for (int yy = -1; yy <= 1; yy++)
+#pragma unroll
+                for (int xx = -1; xx <= 1; xx++) {
+                    if (xx == 0 && yy == 0) continue;
+                    int qx = px.x + xx, qy = px.y + yy;
+                    float c = (qx < 0 || qy < 0 || qx >= W || qy >= H) ? 0.0f : (float)in[(size_t)qy * W + qx] / 255.0f;
+                    minColor = fminf(minColor, c); maxColor = fmaxf(maxColor, c);
+                }
+            float cx = fminf(fmaxf(lastx, -2147483000.0f), 2147483000.0f), cy = fminf(fmaxf(lasty, -2147483000.0f), 2147483000.0f);
+            if (cx != cx) cx = -1.0f;
+            if (cy != cy) cy = -1.0f;
+            int ix = (int)cx, iy = (int)cy;
+            float old = (ix < 0 || iy < 0 || ix >= W || iy >= H) ? 0.0f : (float)hist[(size_t)iy * W + ix] / 255.0f;
+            old = fmaxf(minColor, old);
+            old = fminf(maxColor, old);
+            pixelColor = mix1(old, center, 0.4f);
+        }
+        out[i] = vkp_unorm8(pixelColor);
+    }
+}
+
+// hybridRaygen.rgen:27-186
+__global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    const Pixel px = pixel_of_thread(F);
+    unsigned int n_refl = 0, n_sec = 0;
+    if (px.valid) {
+        const int W = F.p.width, H = F.p.height;
+        const size_t i = (size_t)px.y * W + px.x;
+        const size_t plane = (size_t)W * H;
+        Payload prd;
+        prd.seed = tea16((uint32_t)px.y * (uint32_t)W + (uint32_t)px.x, (uint32_t)F.p.frame);
+        float4 pos4 = unpack_half4(F.position[i]);
+        float4 nrm4 = unpack_half4(F.normal[i]);
+        const vkp_material& mat = material_by_float_index(S, pos4.w);
+        const int shadingMode = (int)mat.shadingMetallicRoughness[0];
+        float3 position = xyz(pos4);
+        float3 normal = xyz(nrm4) * 2.0f - f3s(1.0f);
+        float3 albedo = pow3(unorm3(F.albedo[i]), 2.2f);
+        float3 material = unorm3(F.material[i]);
+        float3 emissive = unorm3(F.emissive[i]);
+        const bool background = pos4.w == 0.0f && nrm4.w == 0.0f;
+        const float roughness = material.y, metallic = material.z;
+        const float3 F0 = mix3(f3s(0.04f), albedo, metallic);
+        const float3 camPosition = f3(F.cam.inv_view[12], F.cam.inv_view[13], F.cam.inv_view[14]);
+        const float3 V = normalize3(camPosition - position);
+        const float3 N = normalize3(normal);
+        const float NdotV = clamp01(dot3(N, V));
+        const float2 envUV = equirect_uv(N, VKP_PI);
+        const float3 irradiance = xyz(tex_nearest(S.textures[S.irr_tex], envUV.x, envUV.y));
+
+        const float tmin = 0.001f, tmax = 1000.0f;
+        float3 origin = f3s(0.0f), direction = f3s(0.0f);
+        float attenuation = 1.0f;   // declared outside the light loop upstream: stale across lights (App. A #8)
+        float3 rayColor = f3s(0.0f);
+        for (int l = 0; l < S.n_lights; l++) {
+            const vkp_light light = S.lights[l];
+            const float3 lpos = f3(light.position[0], light.position[1], light.position[2]);
+            const float3 lcol = f3(light.color[0], light.color[1], light.color[2]);
+            const bool isDirectional = light.position[3] < 0.0f;
+            float3 L = isDirectional ? lpos : (lpos - position);
+            const float light_max_distance = light.position[3];
+            const float light_distance = length3(L);
+            const float light_intensity = isDirectional ? 1.0f : (light.color[3] / (light_distance * light_distance));
+            L = normalize3(L);
+            const float NdotL = clamp01(dot3(N, L));
+            const float shadowFactor = (float)F.denoised[l * plane + i] / 255.0f;
+            if (NdotL > 0.0f) {
+                if (light_intensity == 0.0f) attenuation = 0.0f;
+                else {
+                    attenuation = light_max_distance - light_distance;
+                    attenuation /= light_max_distance;
+                    attenuation = fmaxf(attenuation, 0.0f);
+                    attenuation = isDirectional ? 0.3f : (attenuation * attenuation);
+                }
+            }
+            if (shadingMode == 0) {
+                float3 radiance = lcol * light_intensity * attenuation * shadowFactor;
+                const float3 Hh = normalize3(V + L);
+                float D = distribution_ggx(N, Hh, roughness);
+                float G = geometry_smith(N, V, L, roughness);
+                float3 Fr = fresnel_schlick(fmaxf(dot3(Hh, V), 0.0f), F0);
+                float3 kD = f3s(1.0f) - Fr;
+                kD = kD * (1.0f - metallic);
+                float3 numerator = (D * G) * Fr;
+                float denominator = 4.0f * NdotV * NdotL;
+                float3 specular = numerator / fmaxf(denominator, 0.001f);
+                rayColor = rayColor + (kD * albedo / VKP_PI + specular) * radiance * NdotL;
+            }
+            if (shadingMode == 3) {
+                direction = reflect3(normalize3(-V), N);
+                origin = position;
+                rayColor = rayColor + ((NdotL > 0.0f && light_intensity > 0.0f) ? lcol * light_intensity * attenuation * shadowFactor * albedo * metallic
+                                                                                : irradiance * albedo * metallic);
+            }
+            if (shadingMode == 4) {
+                const float ior = mat.diffuse[3];
+                origin = position;
+                const float cosAlpha = dot3(N, V);
+                const float3 Iv = -V;
+                const float NdotI = dot3(N, Iv);
+                const float3 refrNormal = NdotI > 0.0f ? -N : N;
+                const float refrEta = NdotI > 0.0f ? 1.0f / ior : ior;
+                const float radicand = 1.0f + vkp_powf(refrEta, 2.0f) * (cosAlpha * cosAlpha - 1.0f);
+                direction = radicand < 0.0f ? reflect3(Iv, N) : refract3(Iv, refrNormal, refrEta);
+                rayColor = rayColor + ((light_intensity > 0.0f) ? light_intensity * lcol * attenuation * albedo * metallic
+                                                                : irradiance * albedo * metallic);
+            }
+        }
+        // hybridRaygen.rgen:153-170
+        if (shadingMode != 0) {
+            for (int depth = 0; depth < F.p.max_bounces; depth++) {
+                float3 ro = origin + direction * 1e-2f;
+                HitRec h; n_refl++;
+                bool hit = trace_ray<false>(S, ro, direction, tmin, tmax, h);
+                if (hit) shade_hit<false>(S, F.p, ro, direction, h, prd, n_sec); else shade_miss(S, direction, prd);
+                rayColor = rayColor * prd.color;
+                if (!hit || !(prd.scatter > 0.0f)) break;
+                origin = prd.origin; direction = prd.direction;
+            }
+        }
+        float3 finalColor = rayColor;
+        float3 Fa = fresnel_schlick(NdotV, F0);
+        float3 kDa = (1.0f - Fa) * (1.0f - metallic);
+        float3 diffuse = kDa * albedo * irradiance;
+        finalColor = finalColor + (diffuse + emissive);
+        if (background) finalColor = albedo;
+        float4 outc = make_float4(finalColor.x, finalColor.y, finalColor.z, 1.0f);
+        F.final_f32[i] = outc;
+        F.final_srgb8[i] = post_pixel(outc);
+    }
+    add_counter(F.counters, 2, n_refl);
+    add_counter(F.counters, 3, n_sec);
+}
+
+__global__ void __launch_bounds__(128) k_post(const __grid_constant__ DFrame F)
+{
+    const Pixel px = pixel_of_thread(F);
+    if (!px.valid) return;
+    const size_t i = (size_t)px.y * F.p.width + px.x;
+    F.final_srgb8[i] = post_pixel(F.final_f32[i]);
+}
+
+// raygen.rgen:20-81 with NSAMPLES = params.spp; the accumulation target is kept in fp32
+__global__ void __launch_bounds__(128) k_raytrace(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    const Pixel px = pixel_of_thread(F);
+    unsigned int n_refl = 0, n_sec = 0;
+    if (px.valid) {
+        const int W = F.p.width, H = F.p.height;
+        const size_t i = (size_t)px.y * W + px.x;
+        const int frame = F.p.frame;
+        Payload prd;
+        prd.seed = tea16((uint32_t)px.y * (uint32_t)W + (uint32_t)px.x, (uint32_t)frame);
+        float3 finalColor = f3s(0.0f);
+        for (int nS = 0; nS < F.p.spp; nS++) {
+            float r1 = rnd01(prd.seed);
+            float r2 = rnd01(prd.seed);
+            float ox = nS == 0 ? 0.5f : r1, oy = nS == 0 ? 0.5f : r2;
+            float3 origin, direction; camera_ray(F.cam, px.x, px.y, ox, oy, W, H, origin, direction);
+            float3 rayColor = f3s(1.0f);
+            for (int b = 0; b < F.p.max_bounces; b++) {
+                float3 ro = origin + direction * 1e-2f;
+                HitRec h; n_refl++;
+                bool hit = trace_ray<false>(S, ro, direction, 0.001f, 10000.0f, h);
+                if (hit) shade_hit<true>(S, F.p, ro, direction, h, prd, n_sec); else shade_miss(S, direction, prd);
+                rayColor = rayColor * prd.color;
+                if (!hit || !(prd.scatter > 0.0f)) break;
+                origin = prd.origin; direction = prd.direction;
+            }
+            finalColor = finalColor + rayColor;
+        }
+        finalColor = finalColor / (float)F.p.spp;
+        if (frame >= 0) {
+            float a = 1.0f / (float)(1.0f + (float)frame);
+            float4 last = F.final_f32[i];
+            finalColor = mix3(f3(last.x, last.y, last.z), finalColor, a);
+        }
+        float4 outc = make_float4(finalColor.x, finalColor.y, finalColor.z, 1.0f);
+        F.final_f32[i] = outc;
+        F.final_srgb8[i] = post_pixel(outc);
+    }
+    add_counter(F.counters, 2, n_refl);
+    add_counter(F.counters, 3, n_sec);
+}
+
+// deferred.frag:30-133 (no gamma pass in DEFERRED mode upstream; the sRGB8 plane gets the plain 8-bit store)
+__global__ void __launch_bounds__(128) k_deferred(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    const Pixel px = pixel_of_thread(F);
+    if (!px.valid) return;
+    const int W = F.p.width;
+    const size_t i = (size_t)px.y * W + px.x;
+    float4 pos4 = unpack_half4(F.position[i]);
+    float4 nrm4 = unpack_half4(F.normal[i]);
+    float3 position = xyz(pos4);
+    float3 normal = xyz(nrm4) * 2.0f - f3s(1.0f);
+    float3 albedo = unorm3(F.albedo[i]);
+    uint32_t m = F.motion[i];
+    float3 motion = f3(vkp_f16_to_f32((uint16_t)(m & 0xffffu)) * 2.0f - 1.0f, vkp_f16_to_f32((uint16_t)(m >> 16)) * 2.0f - 1.0f, 0.0f * 2.0f - 1.0f);
+    float3 material = unorm3(F.material[i]);
+    float3 emissive = unorm3(F.emissive[i]);
+    const bool background = pos4.w == 0.0f && nrm4.w == 0.0f;
+    const float metallic = material.z, roughness = material.y;
+    float3 N = normalize3(normal);
+    float3 V = normalize3(f3(F.cam.position[0], F.cam.position[1], F.cam.position[2]) - position);
+    float NdotV = fmaxf(dot3(N, V), 0.0f);
+    float3 F0 = mix3(f3s(0.04f), pow3(albedo, 2.2f), metallic);
+    float2 envUV = equirect_uv(N, VKP_PI);
+    float3 irradiance = xyz(tex_nearest(S.textures[S.irr_tex], envUV.x, envUV.y));
+    float3 color = f3s(1.0f);
+    float alpha = 1.0f;
+    if (F.p.debug_target > 0) {
+        switch (F.p.debug_target) {
+        case 1: color = position; alpha = 1.0f; break;
+        case 2: color = normal; alpha = 0.0f; break;
+        case 3: color = albedo; break;
+        case 4: color = motion; break;
+        case 5: color = material; break;
+        case 6: color = emissive; break;
+        default: color = f3s(0.0f); alpha = 0.0f; break;
+        }
+    } else {
+        float3 Lo = f3s(0.0f);
+        for (int l = 0; l < S.n_lights; l++) {
+            const vkp_light light = S.lights[l];
+            const float3 lpos = f3(light.position[0], light.position[1], light.position[2]);
+            const float3 lcol = f3(light.color[0], light.color[1], light.color[2]);
+            const bool isDirectional = light.position[3] < 0.0f;
+            float3 L = isDirectional ? lpos : (lpos - position);
+            float3 Hh = normalize3(V + normalize3(L));
+            float NdotL = fmaxf(dot3(N, normalize3(L)), 0.0f);
+            if (isDirectional) {
+                Lo = Lo + (NdotL * lcol);
+            } else {
+                float light_max_distance = light.position[3];
+                float light_distance = length3(L);
+                float light_intensity = light.color[3] / (light_distance * light_distance);
+                float attenuation = light_max_distance - light_distance;
+                attenuation /= light_max_distance;
+                attenuation = fmaxf(attenuation, 0.0f);
+                attenuation = attenuation * attenuation;
+                float3 radiance = lcol * light_intensity * attenuation;
+                float NDF = distribution_ggx(N, Hh, roughness);
+                float G = geometry_smith(N, V, L, roughness);     // un-normalised L (deferred.frag:104)
+                float3 Fr = fresnel_schlick(fmaxf(dot3(Hh, V), 0.0f), F0);
+                float3 kD = f3s(1.0f) - Fr;
+                kD = kD * (1.0f - metallic);
+                float3 numerator = (NDF * G) * Fr;
+                float denominator = 4.0f * NdotV * fmaxf(dot3(N, L), 0.0f);
+                float3 specular = numerator / fmaxf(denominator, 0.001f);
+                Lo = Lo + (kD * pow3(albedo, 2.2f) / VKP_PI + specular) * radiance * NdotL;
+            }
+        }
+        if (!background) {
+            float3 Fa = fresnel_schlick(NdotV, F0);
+            float3 kD = (1.0f - Fa) * (1.0f - metallic);
+            float3 diffuse = kD * albedo * irradiance;
+            color = Lo + diffuse;
+            color = color + emissive;
+        } else {
+            color = albedo;
+        }
+    }
+    float4 outc = make_float4(color.x, color.y, color.z, alpha);
+    F.final_f32[i] = outc;
+    F.final_srgb8[i] = pack_unorm4(outc.x, outc.y, outc.z, outc.w);
+}
+
+// traceRayEXT over an explicit ray list (vkp_trace_rays)
+template <bool ANY>
+__global__ void __launch_bounds__(128) k_trace_list(const __grid_constant__ DScene S, const vkp_ray* __restrict__ rays, uint32_t n, vkp_hit* __restrict__ hits)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vkp_ray r = rays[i];
+    HitRec h;
+    bool hit = trace_ray<ANY>(S, f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax, h);
+    vkp_hit o; o.t = hit ? h.t : -1.0f; o.u = h.u; o.v = h.v; o.instance = h.inst; o.primitive = h.prim;
+    hits[i] = o;
+}
+
+// ---- multi-GPU tile pack / unpack (SURVEY 8e composite) -------------------------------------------------------
+__global__ void k_tiles_copy(uint8_t* __restrict__ plane, uint8_t* __restrict__ packed, int elem_bytes, int W, int H, int tile_w, int tile_h,
+                             int tiles_x, int rank, int world, int to_plane)
+{
+    const int own_tile = blockIdx.x;
+    const int tile = rank + own_tile * world;
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    const int row_bytes = tile_w * elem_bytes;
+    for (int r = threadIdx.y; r < tile_h; r += blockDim.y) {
+        const int y = ty * tile_h + r;
+        if (y >= H) continue;
+        for (int b = threadIdx.x * 4; b < row_bytes; b += blockDim.x * 4) {
+            const int x = tx * tile_w + b / elem_bytes;
+            if (x >= W) continue;
+            uint32_t* pp = reinterpret_cast<uint32_t*>(plane + ((size_t)y * W) * elem_bytes + (size_t)tx * row_bytes + b);
+            uint32_t* qq = reinterpret_cast<uint32_t*>(packed + ((size_t)own_tile * tile_h + r) * row_bytes + b);
+            if (to_plane) *pp = *qq; else *qq = *pp;
+        }
+    }
+}
+
+__global__ void k_l2_flush(uint4* buf, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) buf[i] = make_uint4((unsigned)i, 1u, 2u, 3u);
+}
+
+inline dim3 frame_grid(const FrameLaunch& L)
+{
+    const int bpt = (L.frame.tile_w >> 4) * (L.frame.tile_h >> 3);
+    return dim3((unsigned)(L.n_own_tiles * bpt));
+}
+
+} // namespace
+
+cudaError_t launch_gbuffer(const FrameLaunch& L) { k_gbuffer<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
+cudaError_t launch_shadow(const FrameLaunch& L) { k_shadow<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
+cudaError_t launch_denoise(const FrameLaunch& L) { k_denoise<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
+cudaError_t launch_resolve(const FrameLaunch& L) { k_resolve<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
+cudaError_t launch_post(const FrameLaunch& L) { k_post<<<frame_grid(L), 128, 0, L.stream>>>(L.frame); return cudaGetLastError(); }
+cudaError_t launch_raytrace(const FrameLaunch& L) { k_raytrace<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
+cudaError_t launch_deferred(const FrameLaunch& L) { k_deferred<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
+
+cudaError_t launch_trace_rays(cudaStream_t s, const DScene& scene, const vkp_ray* rays, uint32_t n, int any_hit, vkp_hit* hits)
+{
+    if (n == 0) return cudaSuccess;
+    unsigned blocks = (n + 127u) / 128u;
+    if (any_hit) k_trace_list<true><<<blocks, 128, 0, s>>>(scene, rays, n, hits);
+    else k_trace_list<false><<<blocks, 128, 0, s>>>(scene, rays, n, hits);
+    return cudaGetLastError();
+}
+
+static int own_tiles(int W, int H, int tw, int th, int rank, int world, int* tiles_x_out)
+{
+    int tiles_x = (W + tw - 1) / tw, tiles_y = (H + th - 1) / th;
+    if (tiles_x_out) *tiles_x_out = tiles_x;
+    int total = tiles_x * tiles_y;
+    return total > rank ? (total - rank + world - 1) / world : 0;
+}
+
+cudaError_t launch_tiles_pack(cudaStream_t s, const void* plane, void* dst, int elem_bytes, int W, int H, int tw, int th, int rank, int world)
+{
+    int tiles_x; int n = own_tiles(W, H, tw, th, rank, world, &tiles_x);
+    if (n == 0) return cudaSuccess;
+    k_tiles_copy<<<n, dim3(32, 8), 0, s>>>((uint8_t*)plane, (uint8_t*)dst, elem_bytes, W, H, tw, th, tiles_x, rank, world, 0);
+    return cudaGetLastError();
+}
+cudaError_t launch_tiles_unpack(cudaStream_t s, void* plane, const void* src, int elem_bytes, int W, int H, int tw, int th, int rank, int world)
+{
+    int tiles_x; int n = own_tiles(W, H, tw, th, rank, world, &tiles_x);
+    if (n == 0) return cudaSuccess;
+    k_tiles_copy<<<n, dim3(32, 8), 0, s>>>((uint8_t*)plane, (uint8_t*)src, elem_bytes, W, H, tw, th, tiles_x, rank, world, 1);
+    return cudaGetLastError();
+}
+cudaError_t launch_l2_flush(cudaStream_t s, void* buf, size_t bytes)
+{
+    k_l2_flush<<<1184, 256, 0, s>>>((uint4*)buf, bytes / 16);
+    return cudaGetLastError();
+}

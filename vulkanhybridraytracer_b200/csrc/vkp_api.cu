@@ -1,0 +1,690 @@
+// vkp_api.cu -- the extern "C" boundary of libvkp (include/vkp.h): context, device memory, streams, frame graph.
+// No CPU fallback lives here: every entry point that computes launches CUDA kernels, and vkp_create fails
+// loudly when no sm_100-class device is usable.
+#include "vkp_internal.h"
+#include "vkp_bvh.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+namespace {
+
+struct MeshRec { DevBuf verts, idx; uint32_t nv = 0, ni = 0; };
+struct TexRec { DevBuf texels; int w = 0, h = 0; };
+struct BlasRec { int mesh; uint32_t first, count; Bvh bvh; };
+
+std::string g_create_error;
+
+} // namespace
+
+struct vkp_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+
+    std::vector<std::unique_ptr<MeshRec>> meshes;
+    std::vector<std::unique_ptr<TexRec>> textures;
+    int sky = -1, irr = -1;
+    std::vector<vkp_material> materials;
+    std::vector<vkp_light> lights;
+    std::vector<vkp_instance> instances;
+    std::vector<int> inst_blas;
+    std::vector<std::unique_ptr<BlasRec>> blas;
+    DevBuf d_materials, d_lights, d_instances, d_textures;
+    Bvh tlas;
+    BuildScratch scratch, tlas_scratch;
+    bool blas_built = false, tlas_built = false, textures_dirty = true;
+
+    vkp_camera cam{};
+    vkp_params params{};
+    bool have_cam = false, have_params = false;
+    int rank = 0, world = 1, tile_w = 16, tile_h = 8;
+
+    DevBuf position, normal, albedo, motion, material, emissive, hit_ids, final_f32, final_srgb8, shadow, denoised[2];
+    int denoised_cur = 0;
+    int plane_w = 0, plane_h = 0, plane_lights = 0;
+    DevBuf counters, io_tmp, io_tmp2, flush;
+
+    bool profiling = false;
+    cudaEvent_t ev[12]{};
+    int ev_stage[12]{};
+    int n_ev = 0;
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    uint32_t last_launches = 0;
+    int build_launches = 0;
+};
+
+namespace {
+
+int fail(vkp_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(vkp_ctx* c, cudaError_t e, const char* what)
+{
+    return fail(c, e == cudaErrorMemoryAllocation ? VKP_ERR_OOM : VKP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call);   \
+    } while (0)
+
+size_t plane_elem_bytes(int plane)
+{
+    switch (plane) {
+    case VKP_PLANE_POSITION: case VKP_PLANE_NORMAL: case VKP_PLANE_HIT_IDS: return 8;
+    case VKP_PLANE_ALBEDO: case VKP_PLANE_MOTION: case VKP_PLANE_MATERIAL: case VKP_PLANE_EMISSIVE: case VKP_PLANE_FINAL_SRGB8: return 4;
+    case VKP_PLANE_FINAL_F32: return 16;
+    default: break;
+    }
+    if (plane >= VKP_PLANE_SHADOW0 && plane < VKP_PLANE_SHADOW0 + VKP_MAX_LIGHTS) return 1;
+    if (plane >= VKP_PLANE_DENOISED0 && plane < VKP_PLANE_DENOISED0 + VKP_MAX_LIGHTS) return 1;
+    return 0;
+}
+
+void* plane_ptr(vkp_ctx* c, int plane)
+{
+    const size_t px = (size_t)c->plane_w * c->plane_h;
+    switch (plane) {
+    case VKP_PLANE_POSITION: return c->position.p;
+    case VKP_PLANE_NORMAL: return c->normal.p;
+    case VKP_PLANE_ALBEDO: return c->albedo.p;
+    case VKP_PLANE_MOTION: return c->motion.p;
+    case VKP_PLANE_MATERIAL: return c->material.p;
+    case VKP_PLANE_EMISSIVE: return c->emissive.p;
+    case VKP_PLANE_HIT_IDS: return c->hit_ids.p;
+    case VKP_PLANE_FINAL_F32: return c->final_f32.p;
+    case VKP_PLANE_FINAL_SRGB8: return c->final_srgb8.p;
+    default: break;
+    }
+    if (plane >= VKP_PLANE_SHADOW0 && plane < VKP_PLANE_SHADOW0 + c->plane_lights) return c->shadow.as<uint8_t>() + px * (plane - VKP_PLANE_SHADOW0);
+    if (plane >= VKP_PLANE_DENOISED0 && plane < VKP_PLANE_DENOISED0 + c->plane_lights)
+        return c->denoised[c->denoised_cur].as<uint8_t>() + px * (plane - VKP_PLANE_DENOISED0);
+    return nullptr;
+}
+
+int ensure_planes(vkp_ctx* ctx)
+{
+    if (!ctx->have_params) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params has not been called");
+    const int W = ctx->params.width, H = ctx->params.height, L = (int)ctx->lights.size() > 0 ? (int)ctx->lights.size() : 1;
+    if (W == ctx->plane_w && H == ctx->plane_h && L == ctx->plane_lights) return VKP_OK;
+    const size_t px = (size_t)W * H;
+    CK(ctx->position.ensure(px * 8)); CK(ctx->normal.ensure(px * 8)); CK(ctx->albedo.ensure(px * 4)); CK(ctx->motion.ensure(px * 4));
+    CK(ctx->material.ensure(px * 4)); CK(ctx->emissive.ensure(px * 4)); CK(ctx->hit_ids.ensure(px * 8));
+    CK(ctx->final_f32.ensure(px * 16)); CK(ctx->final_srgb8.ensure(px * 4));
+    CK(ctx->shadow.ensure(px * L)); CK(ctx->denoised[0].ensure(px * L)); CK(ctx->denoised[1].ensure(px * L));
+    CK(ctx->counters.ensure(64));
+    ctx->plane_w = W; ctx->plane_h = H; ctx->plane_lights = L;
+    // defined initial state: history and accumulation start at zero (blur.comp:73 reads uninitialised memory upstream)
+    CK(cudaMemsetAsync(ctx->position.p, 0, px * 8, ctx->stream)); CK(cudaMemsetAsync(ctx->normal.p, 0, px * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->albedo.p, 0, px * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->motion.p, 0, px * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->material.p, 0, px * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->emissive.p, 0, px * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->hit_ids.p, 0xff, px * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->final_f32.p, 0, px * 16, ctx->stream)); CK(cudaMemsetAsync(ctx->final_srgb8.p, 0, px * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->shadow.p, 0, px * L, ctx->stream));
+    CK(cudaMemsetAsync(ctx->denoised[0].p, 0, px * L, ctx->stream)); CK(cudaMemsetAsync(ctx->denoised[1].p, 0, px * L, ctx->stream));
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
+    ctx->denoised_cur = 0;
+    return VKP_OK;
+}
+
+int upload_textures(vkp_ctx* ctx)
+{
+    if (!ctx->textures_dirty) return VKP_OK;
+    std::vector<DTexture> t(ctx->textures.size() ? ctx->textures.size() : 1);
+    for (size_t i = 0; i < ctx->textures.size(); i++) { t[i].texels = ctx->textures[i]->texels.as<uchar4>(); t[i].w = ctx->textures[i]->w; t[i].h = ctx->textures[i]->h; }
+    CK(ctx->d_textures.ensure(sizeof(DTexture) * t.size()));
+    CK(cudaMemcpyAsync(ctx->d_textures.p, t.data(), sizeof(DTexture) * t.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->textures_dirty = false;
+    return VKP_OK;
+}
+
+int make_scene(vkp_ctx* ctx, DScene& S)
+{
+    if (!ctx->tlas_built) return fail(ctx, VKP_ERR_INVALID, "acceleration structures are not built (vkp_build_blas / vkp_build_tlas)");
+    if (ctx->sky < 0 || ctx->irr < 0) return fail(ctx, VKP_ERR_INVALID, "vkp_set_env has not been called");
+    if (ctx->materials.empty()) return fail(ctx, VKP_ERR_INVALID, "vkp_set_materials has not been called");
+    int r = upload_textures(ctx);
+    if (r != VKP_OK) return r;
+    S.tlas_nodes = ctx->tlas.nodes.as<vkp_bvh_node>();
+    S.tlas_items = ctx->tlas.items.as<uint32_t>();
+    S.instances = ctx->d_instances.as<DInstance>();
+    S.materials = ctx->d_materials.as<vkp_material>();
+    S.lights = ctx->d_lights.as<vkp_light>();
+    S.textures = ctx->d_textures.as<DTexture>();
+    S.n_instances = (int)ctx->instances.size(); S.n_materials = (int)ctx->materials.size();
+    S.n_lights = (int)ctx->lights.size(); S.n_textures = (int)ctx->textures.size();
+    S.sky_tex = ctx->sky; S.irr_tex = ctx->irr;
+    return VKP_OK;
+}
+
+int make_launch(vkp_ctx* ctx, FrameLaunch& L)
+{
+    int r = ensure_planes(ctx);
+    if (r != VKP_OK) return r;
+    if ((r = make_scene(ctx, L.scene)) != VKP_OK) return r;
+    if (!ctx->have_cam) return fail(ctx, VKP_ERR_INVALID, "vkp_set_camera has not been called");
+    DFrame& F = L.frame;
+    F.cam = ctx->cam; F.p = ctx->params;
+    F.tile_w = ctx->tile_w; F.tile_h = ctx->tile_h;
+    F.tiles_x = (F.p.width + F.tile_w - 1) / F.tile_w; F.tiles_y = (F.p.height + F.tile_h - 1) / F.tile_h;
+    F.rank = ctx->rank; F.world = ctx->world;
+    F.position = ctx->position.as<uint2>(); F.normal = ctx->normal.as<uint2>(); F.albedo = ctx->albedo.as<uchar4>();
+    F.motion = ctx->motion.as<uint32_t>(); F.material = ctx->material.as<uchar4>(); F.emissive = ctx->emissive.as<uchar4>();
+    F.hit_ids = ctx->hit_ids.as<int2>(); F.final_f32 = ctx->final_f32.as<float4>(); F.final_srgb8 = ctx->final_srgb8.as<uchar4>();
+    F.shadow = ctx->shadow.as<uint8_t>();
+    F.denoised = ctx->denoised[ctx->denoised_cur].as<uint8_t>();
+    F.denoised_next = ctx->denoised[ctx->denoised_cur ^ 1].as<uint8_t>();
+    F.counters = ctx->counters.as<unsigned long long>();
+    const int total = F.tiles_x * F.tiles_y;
+    L.n_own_tiles = total > F.rank ? (total - F.rank + F.world - 1) / F.world : 0;
+    L.stream = ctx->stream;
+    L.frame_dev = nullptr;
+    return VKP_OK;
+}
+
+int stage_event(vkp_ctx* ctx, int stage)
+{
+    if (!ctx->profiling || ctx->n_ev >= 12) return VKP_OK;
+    if (!ctx->ev[ctx->n_ev]) CK(cudaEventCreate(&ctx->ev[ctx->n_ev]));
+    CK(cudaEventRecord(ctx->ev[ctx->n_ev], ctx->stream));
+    ctx->ev_stage[ctx->n_ev] = stage;
+    ctx->n_ev++;
+    return VKP_OK;
+}
+
+int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
+{
+    int r = stage_event(ctx, stage);
+    if (r != VKP_OK) return r;
+    if (L.n_own_tiles == 0) return VKP_OK;
+    switch (stage) {
+    case VKP_STAGE_GBUFFER: CK(launch_gbuffer(L)); break;
+    case VKP_STAGE_SHADOW: CK(launch_shadow(L)); break;
+    case VKP_STAGE_DENOISE:
+        CK(launch_denoise(L));
+        ctx->denoised_cur ^= 1;
+        L.frame.denoised = ctx->denoised[ctx->denoised_cur].as<uint8_t>();
+        L.frame.denoised_next = ctx->denoised[ctx->denoised_cur ^ 1].as<uint8_t>();
+        break;
+    case VKP_STAGE_RESOLVE: CK(launch_resolve(L)); break;
+    case VKP_STAGE_POST: CK(launch_post(L)); break;
+    case VKP_STAGE_RAYTRACE: CK(launch_raytrace(L)); break;
+    case VKP_STAGE_DEFERRED: CK(launch_deferred(L)); break;
+    default: return fail(ctx, VKP_ERR_INVALID, "unknown stage");
+    }
+    ctx->last_launches++;
+    return VKP_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int vkp_abi_version(void) { return 1; }
+
+const char* vkp_last_error(const vkp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int vkp_create(vkp_ctx** out, int device_ordinal)
+{
+    vkp_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, VKP_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, VKP_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                                    " (libvkp has no CPU fallback)");
+    if (device_ordinal < 0 || device_ordinal >= n) return fail(nullptr, VKP_ERR_INVALID, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_ordinal)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10) {
+        char b[160]; snprintf(b, sizeof b, "device %d is sm_%d%d; libvkp is built for sm_100a only", device_ordinal, prop.major, prop.minor);
+        return fail(nullptr, VKP_ERR_NO_DEVICE, b);
+    }
+    if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    ctx = new vkp_ctx();
+    ctx->device = device_ordinal;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+    ctx->stream = ctx->own_stream;
+    cudaEventCreate(&ctx->timer0); cudaEventCreate(&ctx->timer1);
+    *out = ctx;
+    return VKP_OK;
+}
+
+void vkp_destroy(vkp_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& m : ctx->meshes) { m->verts.release(); m->idx.release(); }
+    for (auto& t : ctx->textures) t->texels.release();
+    for (auto& b : ctx->blas) b->bvh.release();
+    ctx->tlas.release(); ctx->scratch.release(); ctx->tlas_scratch.release();
+    DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_lights, &ctx->d_instances, &ctx->d_textures, &ctx->position, &ctx->normal, &ctx->albedo, &ctx->motion,
+                      &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
+                      &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->timer0) cudaEventDestroy(ctx->timer0);
+    if (ctx->timer1) cudaEventDestroy(ctx->timer1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int vkp_set_stream(vkp_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return VKP_OK;
+}
+
+int vkp_upload_mesh(vkp_ctx* ctx, const vkp_vertex* vertices, uint32_t nv, const uint32_t* indices, uint32_t ni, int* mesh_id)
+{
+    if (!ctx || !vertices || !indices || !mesh_id) return fail(ctx, VKP_ERR_INVALID, "vkp_upload_mesh: NULL argument");
+    if (ni % 3u) return fail(ctx, VKP_ERR_INVALID, "vkp_upload_mesh: index count is not a multiple of 3");
+    for (uint32_t i = 0; i < ni; i++) if (indices[i] >= nv) return fail(ctx, VKP_ERR_INVALID, "vkp_upload_mesh: index out of range");
+    CK(cudaSetDevice(ctx->device));
+    std::unique_ptr<MeshRec> m(new MeshRec());
+    m->nv = nv; m->ni = ni;
+    CK(m->verts.ensure(sizeof(vkp_vertex) * (size_t)(nv ? nv : 1)));
+    CK(m->idx.ensure(sizeof(uint32_t) * (size_t)(ni ? ni : 1)));
+    CK(cudaMemcpyAsync(m->verts.p, vertices, sizeof(vkp_vertex) * (size_t)nv, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(m->idx.p, indices, sizeof(uint32_t) * (size_t)ni, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->meshes.push_back(std::move(m));
+    *mesh_id = (int)ctx->meshes.size() - 1;
+    return VKP_OK;
+}
+
+int vkp_upload_texture_rgba8(vkp_ctx* ctx, const uint8_t* rgba, int w, int h, int* tex_id)
+{
+    if (!ctx || !rgba || !tex_id || w <= 0 || h <= 0) return fail(ctx, VKP_ERR_INVALID, "vkp_upload_texture_rgba8: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    std::unique_ptr<TexRec> t(new TexRec());
+    t->w = w; t->h = h;
+    CK(t->texels.ensure((size_t)w * h * 4));
+    CK(cudaMemcpyAsync(t->texels.p, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->textures.push_back(std::move(t));
+    ctx->textures_dirty = true;
+    *tex_id = (int)ctx->textures.size() - 1;
+    return VKP_OK;
+}
+
+int vkp_set_env(vkp_ctx* ctx, int sky, int irr)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    if (sky < 0 || irr < 0 || sky >= (int)ctx->textures.size() || irr >= (int)ctx->textures.size()) return fail(ctx, VKP_ERR_INVALID, "vkp_set_env: texture id out of range");
+    ctx->sky = sky; ctx->irr = irr;
+    return VKP_OK;
+}
+
+int vkp_set_materials(vkp_ctx* ctx, const vkp_material* m, int n)
+{
+    if (!ctx || !m || n <= 0) return fail(ctx, VKP_ERR_INVALID, "vkp_set_materials: bad argument");
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 4; k++)
+            if (m[i].textures[k] > -1 && (int)m[i].textures[k] >= (int)ctx->textures.size()) return fail(ctx, VKP_ERR_INVALID, "vkp_set_materials: texture id out of range");
+    CK(cudaSetDevice(ctx->device));
+    ctx->materials.assign(m, m + n);
+    CK(ctx->d_materials.ensure(sizeof(vkp_material) * n));
+    CK(cudaMemcpyAsync(ctx->d_materials.p, ctx->materials.data(), sizeof(vkp_material) * n, cudaMemcpyHostToDevice, ctx->stream));
+    return VKP_OK;
+}
+
+int vkp_set_lights(vkp_ctx* ctx, const vkp_light* l, int n)
+{
+    if (!ctx || (n > 0 && !l) || n < 0 || n > VKP_MAX_LIGHTS) return fail(ctx, VKP_ERR_INVALID, "vkp_set_lights: bad argument (0..32 lights)");
+    CK(cudaSetDevice(ctx->device));
+    // the previous frame may still be reading the staging vector through an async copy: order on the stream
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->lights.assign(l, l + n);
+    CK(ctx->d_lights.ensure(sizeof(vkp_light) * (n ? n : 1)));
+    if (n) CK(cudaMemcpyAsync(ctx->d_lights.p, ctx->lights.data(), sizeof(vkp_light) * n, cudaMemcpyHostToDevice, ctx->stream));
+    return VKP_OK;
+}
+
+int vkp_set_instances(vkp_ctx* ctx, const vkp_instance* inst, int n)
+{
+    if (!ctx || (n > 0 && !inst) || n < 0) return fail(ctx, VKP_ERR_INVALID, "vkp_set_instances: bad argument");
+    for (int i = 0; i < n; i++) {
+        if (inst[i].mesh_id < 0 || inst[i].mesh_id >= (int)ctx->meshes.size()) return fail(ctx, VKP_ERR_INVALID, "vkp_set_instances: mesh id out of range");
+        const MeshRec& m = *ctx->meshes[inst[i].mesh_id];
+        if (inst[i].index_count % 3u || (uint64_t)inst[i].first_index + inst[i].index_count > m.ni) return fail(ctx, VKP_ERR_INVALID, "vkp_set_instances: index range out of the mesh");
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->instances.assign(inst, inst + n);
+    ctx->tlas_built = false;
+    return VKP_OK;
+}
+
+int vkp_build_blas(vkp_ctx* ctx)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    ctx->build_launches = 0;
+    for (const vkp_instance& I : ctx->instances) {
+        bool found = false;
+        for (auto& b : ctx->blas) if (b->mesh == I.mesh_id && b->first == I.first_index && b->count == I.index_count) { found = true; break; }
+        if (found) continue;
+        std::unique_ptr<BlasRec> b(new BlasRec());
+        b->mesh = I.mesh_id; b->first = I.first_index; b->count = I.index_count;
+        const MeshRec& m = *ctx->meshes[I.mesh_id];
+        const uint32_t ntri = I.index_count / 3u;
+        CK(ctx->scratch.boxes.ensure(sizeof(float) * 6 * (size_t)(ntri ? ntri : 1)));
+        const uint32_t* idx = m.idx.as<uint32_t>() + I.first_index;
+        CK(bvh_triangle_boxes(ctx->stream, m.verts.as<vkp_vertex>(), idx, ntri, ctx->scratch.boxes.as<float>()));
+        CK(bvh_build(ctx->stream, ctx->scratch, ntri, 4, b->bvh, &ctx->build_launches));
+        CK(bvh_emit_triangles(ctx->stream, m.verts.as<vkp_vertex>(), idx, b->bvh));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (b->bvh.height + 8 > VKP_TRAV_STACK - 8) {
+            char msg[160]; snprintf(msg, sizeof msg, "BLAS height %d exceeds the traversal stack budget", b->bvh.height);
+            return fail(ctx, VKP_ERR_INVALID, msg);
+        }
+        ctx->blas.push_back(std::move(b));
+    }
+    ctx->blas_built = true;
+    return VKP_OK;
+}
+
+int vkp_build_tlas(vkp_ctx* ctx, int update)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    if (!ctx->blas_built) return fail(ctx, VKP_ERR_INVALID, "vkp_build_tlas: call vkp_build_blas first");
+    CK(cudaSetDevice(ctx->device));
+    const int n = (int)ctx->instances.size();
+    std::vector<DInstance> d(n ? n : 1);
+    for (int i = 0; i < n; i++) {
+        const vkp_instance& I = ctx->instances[i];
+        BlasRec* rec = nullptr;
+        for (auto& b : ctx->blas) if (b->mesh == I.mesh_id && b->first == I.first_index && b->count == I.index_count) { rec = b.get(); break; }
+        if (!rec) return fail(ctx, VKP_ERR_INVALID, "vkp_build_tlas: an instance references geometry without a BLAS; call vkp_build_blas");
+        const MeshRec& m = *ctx->meshes[I.mesh_id];
+        memcpy(d[i].model, I.model, 64); memcpy(d[i].inv_model, I.inv_model, 64);
+        d[i].nodes = rec->bvh.nodes.as<vkp_bvh_node>(); d[i].tris = rec->bvh.tris.as<float4>();
+        d[i].vertices = m.verts.as<vkp_vertex>(); d[i].indices = m.idx.as<uint32_t>() + I.first_index;
+        d[i].material_id = I.material_id;
+    }
+    CK(ctx->d_instances.ensure(sizeof(DInstance) * d.size()));
+    CK(cudaMemcpyAsync(ctx->d_instances.p, d.data(), sizeof(DInstance) * d.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->tlas_scratch.boxes.ensure(sizeof(float) * 6 * (size_t)(n ? n : 1)));
+    CK(bvh_instance_boxes(ctx->stream, ctx->d_instances.as<DInstance>(), (uint32_t)n, ctx->tlas_scratch.boxes.as<float>()));
+    int launches = 0;
+    if (update && ctx->tlas.n_prims == (uint32_t)n && ctx->tlas.n_nodes > 0) CK(bvh_refit(ctx->stream, ctx->tlas_scratch, ctx->tlas, &launches));
+    else CK(bvh_build(ctx->stream, ctx->tlas_scratch, (uint32_t)n, 1, ctx->tlas, &launches));
+    CK(cudaStreamSynchronize(ctx->stream));   // `d` is a stack vector the async copy reads
+    ctx->tlas_built = true;
+    return VKP_OK;
+}
+
+int vkp_set_camera(vkp_ctx* ctx, const vkp_camera* cam)
+{
+    if (!ctx || !cam) return fail(ctx, VKP_ERR_INVALID, "vkp_set_camera: NULL");
+    ctx->cam = *cam; ctx->have_cam = true;
+    return VKP_OK;
+}
+
+int vkp_set_params(vkp_ctx* ctx, const vkp_params* p)
+{
+    if (!ctx || !p) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: NULL");
+    if (p->width <= 0 || p->height <= 0 || p->width > 16384 || p->height > 16384) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: bad image size");
+    if (p->mode < 0 || p->mode > 2) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: bad mode");
+    if (p->spp < 1 || p->shadow_samples < 1 || p->max_bounces < 0) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: spp / shadow_samples must be >= 1");
+    ctx->params = *p; ctx->have_params = true;
+    return VKP_OK;
+}
+
+int vkp_set_tiling(vkp_ctx* ctx, int rank, int world, int tile_w, int tile_h)
+{
+    if (!ctx || world < 1 || rank < 0 || rank >= world) return fail(ctx, VKP_ERR_INVALID, "vkp_set_tiling: bad rank / world");
+    if (tile_w < 16 || tile_h < 8 || tile_w % 16 || tile_h % 8) return fail(ctx, VKP_ERR_INVALID, "vkp_set_tiling: tiles must be multiples of 16 x 8 pixels");
+    ctx->rank = rank; ctx->world = world; ctx->tile_w = tile_w; ctx->tile_h = tile_h;
+    return VKP_OK;
+}
+
+int vkp_render(vkp_ctx* ctx)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    FrameLaunch L;
+    int r = make_launch(ctx, L);
+    if (r != VKP_OK) return r;
+    ctx->n_ev = 0; ctx->last_launches = 0;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
+    static const int hybrid[] = {VKP_STAGE_GBUFFER, VKP_STAGE_SHADOW, VKP_STAGE_DENOISE, VKP_STAGE_RESOLVE};
+    static const int rt[] = {VKP_STAGE_RAYTRACE};
+    static const int deferred[] = {VKP_STAGE_GBUFFER, VKP_STAGE_DEFERRED};
+    const int* seq = hybrid; int n = 4;
+    if (ctx->params.mode == VKP_MODE_RAYTRACING) { seq = rt; n = 1; }
+    else if (ctx->params.mode == VKP_MODE_DEFERRED) { seq = deferred; n = 2; }
+    for (int i = 0; i < n; i++) if ((r = run_one(ctx, L, seq[i])) != VKP_OK) return r;
+    return stage_event(ctx, -1);
+}
+
+int vkp_run_stage(vkp_ctx* ctx, int stage)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    FrameLaunch L;
+    int r = make_launch(ctx, L);
+    if (r != VKP_OK) return r;
+    ctx->n_ev = 0; ctx->last_launches = 0;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
+    if ((r = run_one(ctx, L, stage)) != VKP_OK) return r;
+    return stage_event(ctx, -1);
+}
+
+int vkp_sync(vkp_ctx* ctx)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VKP_OK;
+}
+
+int vkp_reset_history(vkp_ctx* ctx)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    const size_t px = (size_t)ctx->plane_w * ctx->plane_h;
+    if (!px) return VKP_OK;
+    CK(cudaMemsetAsync(ctx->denoised[0].p, 0, px * ctx->plane_lights, ctx->stream));
+    CK(cudaMemsetAsync(ctx->denoised[1].p, 0, px * ctx->plane_lights, ctx->stream));
+    CK(cudaMemsetAsync(ctx->final_f32.p, 0, px * 16, ctx->stream));
+    return VKP_OK;
+}
+
+int vkp_plane_bytes(const vkp_ctx* ctx, int plane, size_t* bytes)
+{
+    if (!ctx || !bytes || !ctx->have_params) return VKP_ERR_INVALID;
+    size_t e = plane_elem_bytes(plane);
+    if (!e) return VKP_ERR_INVALID;
+    *bytes = e * (size_t)ctx->params.width * ctx->params.height;
+    return VKP_OK;
+}
+
+int vkp_readback(vkp_ctx* ctx, int plane, void* dst, size_t bytes)
+{
+    if (!ctx || !dst) return fail(ctx, VKP_ERR_INVALID, "vkp_readback: NULL");
+    int r = ensure_planes(ctx);
+    if (r != VKP_OK) return r;
+    void* p = plane_ptr(ctx, plane);
+    size_t need = plane_elem_bytes(plane) * (size_t)ctx->plane_w * ctx->plane_h;
+    if (!p || !need) return fail(ctx, VKP_ERR_INVALID, "vkp_readback: unknown plane");
+    if (bytes < need) return fail(ctx, VKP_ERR_INVALID, "vkp_readback: destination too small");
+    CK(cudaMemcpyAsync(dst, p, need, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VKP_OK;
+}
+
+int vkp_upload_plane(vkp_ctx* ctx, int plane, const void* src, size_t bytes)
+{
+    if (!ctx || !src) return fail(ctx, VKP_ERR_INVALID, "vkp_upload_plane: NULL");
+    int r = ensure_planes(ctx);
+    if (r != VKP_OK) return r;
+    void* p = plane_ptr(ctx, plane);
+    size_t need = plane_elem_bytes(plane) * (size_t)ctx->plane_w * ctx->plane_h;
+    if (!p || !need) return fail(ctx, VKP_ERR_INVALID, "vkp_upload_plane: unknown plane");
+    if (bytes < need) return fail(ctx, VKP_ERR_INVALID, "vkp_upload_plane: source too small");
+    CK(cudaMemcpyAsync(p, src, need, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VKP_OK;
+}
+
+int vkp_plane_device_ptr(vkp_ctx* ctx, int plane, void** device_ptr, size_t* bytes)
+{
+    if (!ctx || !device_ptr) return VKP_ERR_INVALID;
+    int r = ensure_planes(ctx);
+    if (r != VKP_OK) return r;
+    void* p = plane_ptr(ctx, plane);
+    if (!p) return fail(ctx, VKP_ERR_INVALID, "vkp_plane_device_ptr: unknown plane");
+    *device_ptr = p;
+    if (bytes) *bytes = plane_elem_bytes(plane) * (size_t)ctx->plane_w * ctx->plane_h;
+    return VKP_OK;
+}
+
+int vkp_get_counters(vkp_ctx* ctx, vkp_counters* out)
+{
+    if (!ctx || !out) return VKP_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->counters.p) {
+        unsigned long long c[4];
+        CK(cudaMemcpy(c, ctx->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+        out->rays_primary = c[0]; out->rays_shadow = c[1]; out->rays_reflect = c[2]; out->rays_secondary_shadow = c[3];
+    }
+    if (ctx->profiling && ctx->n_ev >= 2) {
+        for (int i = 0; i + 1 < ctx->n_ev; i++) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
+            if (ctx->ev_stage[i] >= 0 && ctx->ev_stage[i] < 8) out->ms_stage[ctx->ev_stage[i]] += ms;
+        }
+        CK(cudaEventElapsedTime(&out->ms_frame, ctx->ev[0], ctx->ev[ctx->n_ev - 1]));
+    }
+    out->kernel_launches = ctx->last_launches;
+    return VKP_OK;
+}
+
+int vkp_set_profiling(vkp_ctx* ctx, int on)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    ctx->profiling = on != 0;
+    return VKP_OK;
+}
+
+int vkp_trace_rays(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, vkp_hit* hits)
+{
+    if (!ctx || (n && (!rays || !hits))) return fail(ctx, VKP_ERR_INVALID, "vkp_trace_rays: NULL");
+    CK(cudaSetDevice(ctx->device));
+    DScene S;
+    // tracing needs only geometry: tolerate a missing environment / materials
+    if (!ctx->tlas_built) return fail(ctx, VKP_ERR_INVALID, "vkp_trace_rays: acceleration structures are not built");
+    memset(&S, 0, sizeof(S));
+    S.tlas_nodes = ctx->tlas.nodes.as<vkp_bvh_node>(); S.tlas_items = ctx->tlas.items.as<uint32_t>();
+    S.instances = ctx->d_instances.as<DInstance>(); S.n_instances = (int)ctx->instances.size();
+    if (n == 0) return VKP_OK;
+    CK(ctx->io_tmp.ensure(sizeof(vkp_ray) * (size_t)n));
+    CK(ctx->io_tmp2.ensure(sizeof(vkp_hit) * (size_t)n));
+    CK(cudaMemcpyAsync(ctx->io_tmp.p, rays, sizeof(vkp_ray) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_trace_rays(ctx->stream, S, ctx->io_tmp.as<vkp_ray>(), n, any_hit, ctx->io_tmp2.as<vkp_hit>()));
+    CK(cudaMemcpyAsync(hits, ctx->io_tmp2.p, sizeof(vkp_hit) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VKP_OK;
+}
+
+static Bvh* pick_bvh(vkp_ctx* ctx, int blas_index)
+{
+    if (blas_index < 0) return ctx->tlas_built ? &ctx->tlas : nullptr;
+    if (blas_index >= (int)ctx->blas.size()) return nullptr;
+    return &ctx->blas[blas_index]->bvh;
+}
+
+int vkp_bvh_info(vkp_ctx* ctx, int blas_index, uint32_t* n_nodes, uint32_t* n_prims)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    Bvh* b = pick_bvh(ctx, blas_index);
+    if (!b) return fail(ctx, VKP_ERR_INVALID, "vkp_bvh_info: no such BVH");
+    if (n_nodes) *n_nodes = b->n_nodes;
+    if (n_prims) *n_prims = b->n_prims;
+    return VKP_OK;
+}
+
+int vkp_bvh_download(vkp_ctx* ctx, int blas_index, vkp_bvh_node* nodes, uint32_t* prim_ids)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    Bvh* b = pick_bvh(ctx, blas_index);
+    if (!b) return fail(ctx, VKP_ERR_INVALID, "vkp_bvh_download: no such BVH");
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (nodes) CK(cudaMemcpy(nodes, b->nodes.p, sizeof(vkp_bvh_node) * (size_t)b->n_nodes, cudaMemcpyDeviceToHost));
+    if (prim_ids && b->n_prims) CK(cudaMemcpy(prim_ids, b->items.p, sizeof(uint32_t) * (size_t)b->n_prims, cudaMemcpyDeviceToHost));
+    return VKP_OK;
+}
+
+int vkp_timer_begin(vkp_ctx* ctx)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    CK(cudaEventRecord(ctx->timer0, ctx->stream));
+    return VKP_OK;
+}
+
+int vkp_timer_end(vkp_ctx* ctx, float* ms)
+{
+    if (!ctx || !ms) return VKP_ERR_INVALID;
+    CK(cudaEventRecord(ctx->timer1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->timer1));
+    CK(cudaEventElapsedTime(ms, ctx->timer0, ctx->timer1));
+    return VKP_OK;
+}
+
+int vkp_flush_l2(vkp_ctx* ctx)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    const size_t bytes = (size_t)256 << 20;   // 2x the 126 MB L2
+    CK(ctx->flush.ensure(bytes));
+    CK(launch_l2_flush(ctx->stream, ctx->flush.p, bytes));
+    return VKP_OK;
+}
+
+int vkp_tiles_packed_bytes(const vkp_ctx* ctx, int plane, int rank, int world, size_t* bytes)
+{
+    if (!ctx || !bytes || !ctx->have_params || world < 1) return VKP_ERR_INVALID;
+    size_t e = plane_elem_bytes(plane);
+    if (!e) return VKP_ERR_INVALID;
+    int tiles_x = (ctx->params.width + ctx->tile_w - 1) / ctx->tile_w, tiles_y = (ctx->params.height + ctx->tile_h - 1) / ctx->tile_h;
+    int total = tiles_x * tiles_y;
+    int own = total > rank ? (total - rank + world - 1) / world : 0;
+    *bytes = (size_t)own * ctx->tile_w * ctx->tile_h * e;
+    return VKP_OK;
+}
+
+int vkp_tiles_pack(vkp_ctx* ctx, int plane, void* device_dst, size_t bytes)
+{
+    if (!ctx || !device_dst) return VKP_ERR_INVALID;
+    size_t need = 0;
+    if (vkp_tiles_packed_bytes(ctx, plane, ctx->rank, ctx->world, &need) != VKP_OK || bytes < need) return fail(ctx, VKP_ERR_INVALID, "vkp_tiles_pack: bad plane / size");
+    void* p = plane_ptr(ctx, plane);
+    if (!p) return fail(ctx, VKP_ERR_INVALID, "vkp_tiles_pack: unknown plane");
+    CK(launch_tiles_pack(ctx->stream, p, device_dst, (int)plane_elem_bytes(plane), ctx->plane_w, ctx->plane_h, ctx->tile_w, ctx->tile_h, ctx->rank, ctx->world));
+    ctx->last_launches++;
+    return VKP_OK;
+}
+
+int vkp_tiles_unpack(vkp_ctx* ctx, int plane, int rank, int world, const void* device_src, size_t bytes)
+{
+    if (!ctx || !device_src) return VKP_ERR_INVALID;
+    size_t need = 0;
+    if (vkp_tiles_packed_bytes(ctx, plane, rank, world, &need) != VKP_OK || bytes < need) return fail(ctx, VKP_ERR_INVALID, "vkp_tiles_unpack: bad plane / size");
+    int r = ensure_planes(ctx);
+    if (r != VKP_OK) return r;
+    void* p = plane_ptr(ctx, plane);
+    if (!p) return fail(ctx, VKP_ERR_INVALID, "vkp_tiles_unpack: unknown plane");
+    CK(launch_tiles_unpack(ctx->stream, p, device_src, (int)plane_elem_bytes(plane), ctx->plane_w, ctx->plane_h, ctx->tile_w, ctx->tile_h, rank, world));
+    ctx->last_launches++;
+    return VKP_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,168 @@
+// vkp_bvh.cuh -- two-level BVH traversal (what the Vulkan driver + RT cores do behind traceRayEXT:
+// shadowRaygen.rgen:78, hybridRaygen.rgen:158, hybridHit.rchit:123, raygen.rgen:49, closesthit.rchit:111).
+//
+// Layout (DESIGN.md "BVH layout"): 32-byte nodes {bmin, ref, bmax, aux}.  Node 0 is the root.  An internal
+// node's `ref` is the index of its left child; the right child is ref+1, so one 64-byte aligned fetch brings
+// both children.  A leaf's ref has bit 31 set: bits[30:3] = first item, bits[2:0] = count-1.  BLAS items are
+// triangles stored as 3 x float4 in leaf order (v0 | primitive id, v1, v2); TLAS items are instance ids.
+//
+// Intersection contract: Moeller-Trumbore in object space, no culling, tmin < t < tmax, u >= 0, v >= 0,
+// u + v <= 1; closest hit = min t, then lower instance id, then lower primitive id.  The arithmetic order
+// of tri_test() is the contract -- do not re-associate it.
+#pragma once
+#include "vkp_device.cuh"
+
+#define VKP_LEAF_BIT 0x80000000u
+#define VKP_STACK_SENTINEL 0xffffffffu
+#define VKP_STACK_RETURN 0xfffffffeu
+#define VKP_TRAV_STACK 64
+
+struct HitRec {
+    float t, u, v;
+    int inst, prim;
+};
+
+VKP_D float3 safe_inv_dir(float3 d)
+{
+    // a zero component would give inf and 0*inf = NaN in the slab test; a huge finite reciprocal keeps the
+    // test conservative (inside the slab -> unbounded interval, outside -> empty)
+    const float big = 1e30f;
+    float3 r;
+    r.x = (fabsf(d.x) > 1e-30f) ? 1.0f / d.x : copysignf(big, d.x);
+    r.y = (fabsf(d.y) > 1e-30f) ? 1.0f / d.y : copysignf(big, d.y);
+    r.z = (fabsf(d.z) > 1e-30f) ? 1.0f / d.z : copysignf(big, d.z);
+    return r;
+}
+
+// conservative slab test in (b - o) * inv form (relative error only) with an 8-ulp slack on the far side
+VKP_D bool box_test(const float4 lo, const float4 hi, float3 o, float3 inv, float tmin, float tmax, float& tnear)
+{
+    float x0 = (lo.x - o.x) * inv.x, x1 = (hi.x - o.x) * inv.x;
+    float y0 = (lo.y - o.y) * inv.y, y1 = (hi.y - o.y) * inv.y;
+    float z0 = (lo.z - o.z) * inv.z, z1 = (hi.z - o.z) * inv.z;
+    float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    tnear = tn;
+    return tn * 0.999999f <= tf * 1.000001f;
+}
+
+// the intersection contract
+VKP_D bool tri_test(float3 o, float3 d, float3 v0, float3 v1, float3 v2, float tmin, float tmax, float& t, float& u, float& v)
+{
+    float3 e1 = v1 - v0, e2 = v2 - v0;
+    float3 p = cross3(d, e2);
+    float det = dot3(e1, p);
+    if (det == 0.0f) return false;
+    float inv = 1.0f / det;
+    float3 s = o - v0;
+    u = dot3(s, p) * inv;
+    if (!(u >= 0.0f) || u > 1.0f) return false;
+    float3 q = cross3(s, e1);
+    v = dot3(d, q) * inv;
+    if (!(v >= 0.0f) || u + v > 1.0f) return false;
+    t = dot3(e2, q) * inv;
+    return t > tmin && t < tmax;
+}
+
+VKP_D bool hit_better(float t, int inst, int prim, const HitRec& h)
+{
+    if (h.inst < 0) return true;
+    if (t < h.t) return true;
+    if (t > h.t) return false;
+    if (inst != h.inst) return inst < h.inst;
+    return prim < h.prim;
+}
+
+// ANY == true: gl_RayFlagsTerminateOnFirstHitEXT | SkipClosestHitShaderEXT (shadow rays): returns on the first hit
+template <bool ANY>
+VKP_D bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax, HitRec& best)
+{
+    best.t = -1.0f; best.u = 0.0f; best.v = 0.0f; best.inst = -1; best.prim = -1;
+    float limit = tmax;                       // current far bound (closest so far)
+
+    uint32_t stack[VKP_TRAV_STACK];
+    int sp = 0;
+    stack[sp++] = VKP_STACK_SENTINEL;
+
+    float3 ro = o, rd = d;
+    float3 inv = safe_inv_dir(rd);
+    const float4* nodes = reinterpret_cast<const float4*>(S.tlas_nodes);
+    const float4* tris = nullptr;
+    int inst = -1;
+
+    uint32_t cur;
+    {
+        float4 lo = __ldg(&nodes[0]), hi = __ldg(&nodes[1]);
+        float tn;
+        if (!box_test(lo, hi, ro, inv, tmin, limit, tn)) return false;
+        cur = __float_as_uint(lo.w);
+    }
+
+    while (true) {
+        if (!(cur & VKP_LEAF_BIT)) {
+            // internal: fetch both children (64 contiguous bytes)
+            const float4* c = nodes + 2u * (size_t)cur;
+            float4 lo0 = __ldg(c + 0), hi0 = __ldg(c + 1), lo1 = __ldg(c + 2), hi1 = __ldg(c + 3);
+            float t0, t1;
+            bool h0 = box_test(lo0, hi0, ro, inv, tmin, limit, t0);
+            bool h1 = box_test(lo1, hi1, ro, inv, tmin, limit, t1);
+            uint32_t r0 = __float_as_uint(lo0.w), r1 = __float_as_uint(lo1.w);
+            if (h0 && h1) {
+                bool swap = t1 < t0;
+                stack[sp++] = swap ? r0 : r1;
+                cur = swap ? r1 : r0;
+                continue;
+            }
+            if (h0) { cur = r0; continue; }
+            if (h1) { cur = r1; continue; }
+        } else if (inst < 0) {
+            // TLAS leaf: one instance (the TLAS is built with leaf size 1)
+            uint32_t first = (cur & 0x7fffffffu) >> 3;
+            inst = (int)__ldg(&S.tlas_items[first]);
+            const DInstance& I = S.instances[inst];
+            ro = xform_point(I.inv_model, o);
+            rd = xform_dir(I.inv_model, d);
+            inv = safe_inv_dir(rd);
+            nodes = reinterpret_cast<const float4*>(I.nodes);
+            tris = I.tris;
+            float4 lo = __ldg(&nodes[0]), hi = __ldg(&nodes[1]);
+            float tn;
+            if (box_test(lo, hi, ro, inv, tmin, limit, tn)) {
+                stack[sp++] = VKP_STACK_RETURN;
+                cur = __float_as_uint(lo.w);
+                continue;
+            }
+            // missed the object-space root: fall through to pop, but first leave the instance
+            inst = -1; ro = o; rd = d; inv = safe_inv_dir(rd);
+            nodes = reinterpret_cast<const float4*>(S.tlas_nodes);
+        } else {
+            // BLAS leaf: triangles
+            uint32_t first = (cur & 0x7fffffffu) >> 3, count = (cur & 7u) + 1u;
+            for (uint32_t k = 0; k < count; k++) {
+                const float4* tp = tris + 3u * (size_t)(first + k);
+                float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                float t, u, v;
+                if (tri_test(ro, rd, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), tmin, tmax, t, u, v)) {
+                    int prim = __float_as_int(a.w);
+                    if (ANY) { best.t = t; best.u = u; best.v = v; best.inst = inst; best.prim = prim; return true; }
+                    if (hit_better(t, inst, prim, best)) {
+                        best.t = t; best.u = u; best.v = v; best.inst = inst; best.prim = prim;
+                        limit = t;
+                    }
+                }
+            }
+        }
+        // pop
+        while (true) {
+            cur = stack[--sp];
+            if (cur == VKP_STACK_RETURN) {
+                inst = -1; ro = o; rd = d; inv = safe_inv_dir(rd);
+                nodes = reinterpret_cast<const float4*>(S.tlas_nodes);
+                continue;
+            }
+            break;
+        }
+        if (cur == VKP_STACK_SENTINEL) break;
+    }
+    return best.inst >= 0;
+}

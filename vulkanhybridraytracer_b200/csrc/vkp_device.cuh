@@ -1,0 +1,243 @@
+// vkp_device.cuh -- device-side math and shading helpers shared by every kernel of libvkp.
+//
+// Numerics contract (DESIGN.md "Numerics"): all translation units are compiled with -fmad=false, IEEE
+// div/sqrt (nvcc defaults), and every expression below keeps the left-to-right order of the GLSL source
+// it implements, so results are bit-identical to a scalar fp32 evaluation of the same shader.  FMA is
+// only used explicitly (__fmaf_rn) where the result cannot change an output (conservative box tests).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/vkp_types.h"
+#include "../../include/vkp_detmath.h"
+
+#define VKP_D __device__ __forceinline__
+
+// ---- float3 in contract order -------------------------------------------------------------------------
+VKP_D float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+VKP_D float3 f3s(float s) { return make_float3(s, s, s); }
+VKP_D float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+VKP_D float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+VKP_D float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+VKP_D float3 operator/(float3 a, float3 b) { return f3(a.x / b.x, a.y / b.y, a.z / b.z); }
+VKP_D float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+VKP_D float3 operator*(float s, float3 a) { return f3(s * a.x, s * a.y, s * a.z); }
+VKP_D float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+VKP_D float3 operator+(float3 a, float s) { return f3(a.x + s, a.y + s, a.z + s); }
+VKP_D float3 operator-(float s, float3 a) { return f3(s - a.x, s - a.y, s - a.z); }
+VKP_D float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+VKP_D float dot3(float3 a, float3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+VKP_D float3 cross3(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+VKP_D float length3(float3 a) { return sqrtf(dot3(a, a)); }
+VKP_D float3 normalize3(float3 a) { float inv = 1.0f / sqrtf(dot3(a, a)); return a * inv; }
+VKP_D float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+VKP_D float mix1(float x, float y, float a) { return x * (1.0f - a) + y * a; }
+VKP_D float3 mix3(float3 x, float3 y, float a) { return x * (1.0f - a) + y * a; }
+VKP_D float3 pow3(float3 a, float e) { return f3(vkp_powf(a.x, e), vkp_powf(a.y, e), vkp_powf(a.z, e)); }
+VKP_D float3 reflect3(float3 I, float3 N) { return I - N * (2.0f * dot3(N, I)); }
+VKP_D float3 refract3(float3 I, float3 N, float eta)
+{
+    float d = dot3(N, I);
+    float k = 1.0f - (eta * eta) * (1.0f - d * d);
+    if (k < 0.0f) return f3s(0.0f);
+    return I * eta - N * (eta * d + sqrtf(k));
+}
+
+// column-major 4x4 (m[c*4+r]) applied to points / directions; same association as the oracle
+VKP_D float3 xform_point(const float* __restrict__ m, float3 p)
+{
+    return f3(((m[0] * p.x + m[4] * p.y) + m[8] * p.z) + m[12],
+              ((m[1] * p.x + m[5] * p.y) + m[9] * p.z) + m[13],
+              ((m[2] * p.x + m[6] * p.y) + m[10] * p.z) + m[14]);
+}
+VKP_D float3 xform_dir(const float* __restrict__ m, float3 d)
+{
+    return f3((m[0] * d.x + m[4] * d.y) + m[8] * d.z,
+              (m[1] * d.x + m[5] * d.y) + m[9] * d.z,
+              (m[2] * d.x + m[6] * d.y) + m[10] * d.z);
+}
+VKP_D float4 xform_vec4(const float* __restrict__ m, float4 v)
+{
+    float4 r;
+    r.x = ((m[0] * v.x + m[4] * v.y) + m[8] * v.z) + m[12] * v.w;
+    r.y = ((m[1] * v.x + m[5] * v.y) + m[9] * v.z) + m[13] * v.w;
+    r.z = ((m[2] * v.x + m[6] * v.y) + m[10] * v.z) + m[14] * v.w;
+    r.w = ((m[3] * v.x + m[7] * v.y) + m[11] * v.z) + m[15] * v.w;
+    return r;
+}
+// mat3(transpose(M)) * n
+VKP_D float3 xform_normal_by_inverse(const float* __restrict__ inv, float3 n)
+{
+    return f3((inv[0] * n.x + inv[1] * n.y) + inv[2] * n.z,
+              (inv[4] * n.x + inv[5] * n.y) + inv[6] * n.z,
+              (inv[8] * n.x + inv[9] * n.y) + inv[10] * n.z);
+}
+
+// ---- RNG: random.glsl:3-33 ---------------------------------------------------------------------------------
+VKP_D uint32_t tea16(uint32_t val0, uint32_t val1)
+{
+    uint32_t v0 = val0, v1 = val1, s0 = 0u;
+#pragma unroll
+    for (int n = 0; n < 16; n++) {
+        s0 += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    return v0;
+}
+VKP_D float rnd01(uint32_t& state)
+{
+    state = 1664525u * state + 1013904223u;
+    return (float)(state & 0x00ffffffu) / 16777216.0f;
+}
+
+// ---- device scene ---------------------------------------------------------------------------------------------
+struct DTexture { const uchar4* texels; int w, h; };
+
+struct DInstance {
+    float model[16];
+    float inv_model[16];
+    const vkp_bvh_node* nodes;   // BLAS nodes
+    const float4* tris;          // 3 x float4 per leaf-ordered triangle: (v0, prim id bits), (v1, 0), (v2, 0)
+    const vkp_vertex* vertices;  // mesh vertex buffer
+    const uint32_t* indices;     // mesh index buffer + first_index
+    int32_t material_id;
+    int32_t _pad[3];
+};
+
+struct DScene {
+    const vkp_bvh_node* tlas_nodes;
+    const uint32_t* tlas_items;      // leaf-ordered instance ids
+    const DInstance* instances;
+    const vkp_material* materials;
+    const vkp_light* lights;
+    const DTexture* textures;
+    int n_instances, n_materials, n_lights, n_textures;
+    int sky_tex, irr_tex;
+};
+
+struct DFrame {
+    vkp_camera cam;
+    vkp_params p;
+    // multi-GPU tiling: this context renders tiles t with t % world == rank
+    int tile_w, tile_h, tiles_x, tiles_y, rank, world;
+    // planes
+    uint2* position;      // 4 x fp16
+    uint2* normal;        // 4 x fp16
+    uchar4* albedo;
+    uint32_t* motion;     // 2 x fp16
+    uchar4* material;
+    uchar4* emissive;
+    int2* hit_ids;
+    float4* final_f32;
+    uchar4* final_srgb8;
+    uint8_t* shadow;      // n_lights planes
+    uint8_t* denoised;    // n_lights planes (history, updated in place through denoised_next)
+    uint8_t* denoised_next;
+    unsigned long long* counters;   // [4] rays by type
+};
+
+// ---- texture / env -----------------------------------------------------------------------------------------
+// texture(): VK_FILTER_NEAREST + REPEAT on R8G8B8A8_UNORM (vk_textures.cpp:15,26; vk_initializers.h:86)
+VKP_D float4 tex_nearest(const DTexture& T, float u, float v)
+{
+    float fx = u * (float)T.w, fy = v * (float)T.h;
+    int ix = (fx == fx) ? (int)floorf(fx) : 0, iy = (fy == fy) ? (int)floorf(fy) : 0;
+    ix %= T.w; if (ix < 0) ix += T.w;
+    iy %= T.h; if (iy < 0) iy += T.h;
+    uchar4 t = __ldg(&T.texels[(size_t)iy * T.w + ix]);
+    return make_float4((float)t.x / 255.0f, (float)t.y / 255.0f, (float)t.z / 255.0f, (float)t.w / 255.0f);
+}
+VKP_D float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
+
+#define VKP_PI 3.14159265359f        /* helpers.glsl:5 */
+#define VKP_PI_MISS 3.141592f        /* miss.rmiss:11  */
+
+// miss.rmiss:16, hybridRaygen.rgen:59
+VKP_D float2 equirect_uv(float3 d, float pi)
+{
+    float2 uv;
+    uv.x = 0.5f + vkp_atan2f(d.x, d.z) / (2.0f * pi);
+    uv.y = 0.5f - vkp_asinf(d.y) / pi;
+    return uv;
+}
+
+// ---- BRDF: helpers.glsl:33-93 ------------------------------------------------------------------------------
+VKP_D float distribution_ggx(float3 N, float3 H, float roughness)
+{
+    float a = roughness * roughness;
+    float a2 = a * a;
+    float NdotH = fmaxf(dot3(N, H), 0.0f);
+    float NdotH2 = NdotH * NdotH;
+    float denom = (NdotH2 * (a2 - 1.0f) + 1.0f);
+    denom = VKP_PI * denom * denom;
+    return a2 / denom;
+}
+VKP_D float geometry_schlick_ggx(float NdotV, float roughness)
+{
+    float r = roughness + 1.0f;
+    float k = (r * r) / 8.0f;
+    float denom = NdotV * (1.0f - k) + k;
+    return NdotV / denom;
+}
+VKP_D float geometry_smith(float3 N, float3 V, float3 L, float roughness)
+{
+    float NdotV = fmaxf(dot3(N, V), 0.0f);
+    float NdotL = fmaxf(dot3(N, L), 0.0f);
+    return geometry_schlick_ggx(NdotV, roughness) * geometry_schlick_ggx(NdotL, roughness);
+}
+VKP_D float3 fresnel_schlick(float cosTheta, float3 F0)
+{
+    return F0 + (1.0f - F0) * vkp_powf(1.0f - cosTheta, 5.0f);
+}
+// helpers.glsl:82-93; the reference passes `seed` by value (faithful); advance=true writes it back
+VKP_D float3 sample_disk(const vkp_light& light, float3 position, float3 L, uint32_t& seed_io, bool advance)
+{
+    uint32_t seed = seed_io;
+    float radius = light.radius * sqrtf(rnd01(seed));
+    float angle = rnd01(seed) * 2.0f * VKP_PI;
+    float sa, ca; vkp_sincosf(angle, &sa, &ca);
+    float px = radius * ca, py = radius * sa;
+    float3 tangent = normalize3(cross3(L, f3(0.0f, 1.0f, 0.0f)));
+    if (L.x == 0.0f && L.y == 1.0f && L.z == 0.0f) tangent = f3(0.0f, 0.0f, 1.0f);
+    float3 bitangent = normalize3(cross3(tangent, L));
+    float3 target = position + L + px * tangent + py * bitangent;
+    if (advance) seed_io = seed;
+    return normalize3(target - position);
+}
+
+// ---- storage formats ---------------------------------------------------------------------------------------
+VKP_D uint2 pack_half4(float x, float y, float z, float w)
+{
+    return make_uint2((uint32_t)vkp_f32_to_f16(x) | ((uint32_t)vkp_f32_to_f16(y) << 16),
+                      (uint32_t)vkp_f32_to_f16(z) | ((uint32_t)vkp_f32_to_f16(w) << 16));
+}
+VKP_D float4 unpack_half4(uint2 v)
+{
+    return make_float4(vkp_f16_to_f32((uint16_t)(v.x & 0xffffu)), vkp_f16_to_f32((uint16_t)(v.x >> 16)),
+                       vkp_f16_to_f32((uint16_t)(v.y & 0xffffu)), vkp_f16_to_f32((uint16_t)(v.y >> 16)));
+}
+VKP_D uchar4 pack_unorm4(float x, float y, float z, float w)
+{
+    return make_uchar4(vkp_unorm8(x), vkp_unorm8(y), vkp_unorm8(z), vkp_unorm8(w));
+}
+VKP_D float3 unorm3(uchar4 c) { return f3((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f); }
+
+// camera ray of raygen.rgen:32-40
+VKP_D void camera_ray(const vkp_camera& cam, int x, int y, float ox, float oy, int W, int H, float3& origin, float3& dir)
+{
+    float pcx = (float)x + ox, pcy = (float)y + oy;
+    float u = pcx / (float)W, v = pcy / (float)H;
+    float dx = u * 2.0f - 1.0f, dy = v * 2.0f - 1.0f;
+    origin = f3(cam.inv_view[12], cam.inv_view[13], cam.inv_view[14]);
+    float4 target = xform_vec4(cam.inv_proj, make_float4(dx, dy, 1.0f, 1.0f));
+    float3 tn = normalize3(xyz(target));
+    dir = xform_dir(cam.inv_view, tn);
+}
+
+VKP_D const vkp_material& material_by_float_index(const DScene& S, float matIdx)
+{
+    int i = (int)matIdx;
+    i = max(0, min(i, S.n_materials - 1));
+    return S.materials[i];
+}

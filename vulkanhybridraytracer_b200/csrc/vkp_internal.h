@@ -1,0 +1,81 @@
+// vkp_internal.h -- host-side declarations shared by the translation units of libvkp
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/vkp.h"
+#include "vkp_device.cuh"
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// One bounding volume hierarchy (BLAS over triangles or TLAS over instance boxes)
+struct Bvh {
+    uint32_t n_prims = 0;
+    uint32_t n_nodes = 0;
+    int leaf_max = 4;
+    int height = 0;
+    DevBuf nodes;        // vkp_bvh_node[n_nodes]
+    DevBuf items;        // uint32_t[n_prims]: leaf-ordered primitive ids
+    DevBuf tris;         // BLAS only: float4[3*n_prims]
+    // topology kept for refit (Karras radix tree)
+    DevBuf child;        // int2[n_prims-1]   (>=0 internal index, <0: ~leaf position)
+    DevBuf parent;       // int[n_prims-1 + n_prims]: parents of internals then of leaves
+    DevBuf ibox;         // float4[2*(n_prims-1)]
+    DevBuf flags;        // int[n_prims-1]
+    DevBuf rank;         // uint32_t[n_prims-1]: exclusive rank among emitted internals
+    DevBuf keep;         // uint32_t[n_prims-1]
+    DevBuf range;        // int2[n_prims-1]
+    void release()
+    {
+        nodes.release(); items.release(); tris.release(); child.release(); parent.release(); ibox.release();
+        flags.release(); rank.release(); keep.release(); range.release();
+    }
+};
+
+struct BuildScratch {
+    DevBuf boxes;       // float[6*n] primitive boxes
+    DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, bounds, misc;
+    void release() { boxes.release(); keys.release(); keys_alt.release(); vals.release(); vals_alt.release(); cub_tmp.release(); bounds.release(); misc.release(); }
+};
+
+// bvh_build.cu
+cudaError_t bvh_triangle_boxes(cudaStream_t s, const vkp_vertex* verts, const uint32_t* indices, uint32_t n_tris, float* boxes);
+cudaError_t bvh_instance_boxes(cudaStream_t s, const DInstance* inst, uint32_t n, float* boxes);
+cudaError_t bvh_build(cudaStream_t s, BuildScratch& scratch, uint32_t n_prims, int leaf_max, Bvh& out, int* launches);
+cudaError_t bvh_refit(cudaStream_t s, BuildScratch& scratch, Bvh& bvh, int* launches);
+cudaError_t bvh_emit_triangles(cudaStream_t s, const vkp_vertex* verts, const uint32_t* indices, Bvh& bvh);
+
+// kernels_frame.cu
+struct FrameLaunch {
+    cudaStream_t stream;
+    DScene scene;
+    const DFrame* frame_dev;   // device copy of DFrame
+    DFrame frame;              // host copy (for grid sizing)
+    int n_own_tiles;
+};
+cudaError_t launch_gbuffer(const FrameLaunch& L);
+cudaError_t launch_shadow(const FrameLaunch& L);
+cudaError_t launch_denoise(const FrameLaunch& L);
+cudaError_t launch_resolve(const FrameLaunch& L);
+cudaError_t launch_post(const FrameLaunch& L);
+cudaError_t launch_raytrace(const FrameLaunch& L);
+cudaError_t launch_deferred(const FrameLaunch& L);
+cudaError_t launch_trace_rays(cudaStream_t s, const DScene& scene, const vkp_ray* rays, uint32_t n, int any_hit, vkp_hit* hits);
+cudaError_t launch_tiles_pack(cudaStream_t s, const void* plane, void* dst, int elem_bytes, int W, int H, int tile_w, int tile_h, int rank, int world);
+cudaError_t launch_tiles_unpack(cudaStream_t s, void* plane, const void* src, int elem_bytes, int W, int H, int tile_w, int tile_h, int rank, int world);
+cudaError_t launch_l2_flush(cudaStream_t s, void* buf, size_t bytes);

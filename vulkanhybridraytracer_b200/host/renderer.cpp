@@ -1,0 +1,203 @@
+// renderer.cpp -- Renderer and VulkanEngine of the reference (src/renderer.cpp, src/vk_engine.cpp) re-hosted on
+// the C-ABI of include/vkp.h.  The 5 vkQueueSubmit + vkQueueWaitIdle pairs of Renderer::rasterize_hybrid
+// (renderer.cpp:544-588) collapse into one asynchronous vkp_render on the context stream.
+#include "vkpinut.h"
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#define VKP_CHECK(x)                                                                                              \
+    do {                                                                                                          \
+        int _e = (x);                                                                                             \
+        if (_e != VKP_OK) throw std::runtime_error(std::string(#x) + ": " + vkp_last_error(_ctx));                \
+    } while (0)
+
+// ---- Renderer ---------------------------------------------------------------------------------------------
+Renderer::Renderer(Scene* scene) : _scene(scene)
+{
+    VulkanEngine* e = VulkanEngine::engine;
+    _width = e ? e->_width : 1700; _height = e ? e->_height : 900;
+    int dev = e ? e->_device : 0;
+    if (vkp_create(&_ctx, dev) != VKP_OK) throw std::runtime_error(std::string("vkp_create: ") + vkp_last_error(nullptr));
+    load_data_to_gpu();
+    create_bottom_acceleration_structure();
+    create_top_acceleration_structure();
+}
+
+Renderer::~Renderer() { if (_ctx) vkp_destroy(_ctx); }
+
+// renderer.cpp:1477-1530 (lights, materials, matrices) + create_hybrid_descriptors (:2917-3129: vertex /
+// index / id / texture / environment bindings)
+void Renderer::load_data_to_gpu()
+{
+    SceneBuffers B = build_scene_buffers(_scene);
+    for (Mesh* m : B.meshes) m->_deviceMeshId = -1;
+    for (size_t i = 0; i < B.meshes.size(); i++) {
+        B.meshes[i]->upload(_ctx);
+        if (B.meshes[i]->_deviceMeshId != (int)i) throw std::runtime_error("mesh upload order");
+    }
+    for (Texture* t : B.textures) {
+        int id = -1;
+        VKP_CHECK(vkp_upload_texture_rgba8(_ctx, t->_rgba.data(), t->_width, t->_height, &id));
+    }
+    VKP_CHECK(vkp_set_env(_ctx, B.sky_tex, B.irradiance_tex));
+    VKP_CHECK(vkp_set_materials(_ctx, B.materials.data(), (int)B.materials.size()));
+    VKP_CHECK(vkp_set_lights(_ctx, B.lights.data(), (int)B.lights.size()));
+    _instances = B.instances;
+    VKP_CHECK(vkp_set_instances(_ctx, _instances.data(), (int)_instances.size()));
+    _tlas.clear();
+    for (size_t i = 0; i < _instances.size(); i++) {
+        TlasInstance t; t.blasId = t.instanceId = (uint32_t)i;
+        std::memcpy(t.transform.data(), _instances[i].model, 64);
+        _tlas.push_back(t);
+    }
+}
+
+void Renderer::create_bottom_acceleration_structure() { VKP_CHECK(vkp_build_blas(_ctx)); }
+void Renderer::create_top_acceleration_structure() { VKP_CHECK(vkp_build_tlas(_ctx, 0)); }
+
+// Renderer::buildTlas(input, flags, update) (renderer.cpp:1757-1865)
+void Renderer::buildTlas(const std::vector<TlasInstance>& input, bool update)
+{
+    if (input.size() != _instances.size()) throw std::runtime_error("buildTlas: instance count changed; rebuild the renderer");
+    bool changed = false;
+    for (size_t i = 0; i < input.size(); i++) {
+        if (std::memcmp(_instances[i].model, input[i].transform.data(), 64) != 0) {
+            glm::mat4 inv = glm::inverse(input[i].transform);
+            std::memcpy(_instances[i].model, input[i].transform.data(), 64);
+            std::memcpy(_instances[i].inv_model, inv.data(), 64);
+            changed = true;
+        }
+    }
+    if (!changed && update) return;   // the reference refits every frame regardless (vk_engine.cpp:187); identical result
+    VKP_CHECK(vkp_set_instances(_ctx, _instances.data(), (int)_instances.size()));
+    VKP_CHECK(vkp_build_tlas(_ctx, update ? 1 : 0));
+}
+
+void Renderer::recreate_renderer()
+{
+    VulkanEngine* e = VulkanEngine::engine;
+    if (e) { _width = e->_width; _height = e->_height; }
+    VKP_CHECK(vkp_reset_history(_ctx));
+}
+
+void Renderer::submit(renderMode mode)
+{
+    VulkanEngine* e = VulkanEngine::engine;
+    vkp_params p = e->current_params();
+    p.mode = (int)mode;
+    VKP_CHECK(vkp_set_params(_ctx, &p));
+    VKP_CHECK(vkp_set_camera(_ctx, &e->_cameraData));
+    VKP_CHECK(vkp_render(_ctx));
+}
+
+void Renderer::render() { submit(DEFERRED); }
+void Renderer::raytrace() { submit(RAYTRACING); }
+void Renderer::rasterize_hybrid() { submit(HYBRID); }
+
+std::vector<uint8_t> Renderer::read_final_srgb8()
+{
+    std::vector<uint8_t> out((size_t)_width * _height * 4);
+    VKP_CHECK(vkp_readback(_ctx, VKP_PLANE_FINAL_SRGB8, out.data(), out.size()));
+    return out;
+}
+std::vector<float> Renderer::read_final_linear()
+{
+    std::vector<float> out((size_t)_width * _height * 4);
+    VKP_CHECK(vkp_readback(_ctx, VKP_PLANE_FINAL_F32, out.data(), out.size() * sizeof(float)));
+    return out;
+}
+vkp_counters Renderer::counters()
+{
+    vkp_counters c{};
+    VKP_CHECK(vkp_get_counters(_ctx, &c));
+    return c;
+}
+
+// ---- VulkanEngine (headless) ---------------------------------------------------------------------------
+VulkanEngine* VulkanEngine::engine = nullptr;
+
+// vk_engine.cpp:23-61 minus window / swapchain / ImGui
+void VulkanEngine::init()
+{
+    engine = this;
+    Scene::reset_registries();
+    _scene = new Scene();
+    _scene->create_scene(_sceneIndex);
+    renderer = new Renderer(_scene);
+    _denoise_frame = 0; _frameNumber = 0; _havePrev = false;
+    _refMatrix = glm::mat4(0.0f);
+}
+
+vkp_params VulkanEngine::current_params() const
+{
+    vkp_params p{};
+    p.width = _width; p.height = _height; p.mode = (int)_mode;
+    p.spp = _spp; p.shadow_samples = _samples; p.max_bounces = _maxBounces;
+    p.frame = _denoise ? _denoise_frame : 0;             // vk_engine.cpp:733
+    p.denoise_frame = _denoise_frame;                    // vk_engine.cpp:720-723
+    p.faithful_rng = _faithfulRng ? 1 : 0;
+    p.denoise_cover_remainder = 1;
+    p.debug_target = debugTarget;
+    return p;
+}
+
+// vk_engine.cpp:669-686
+void VulkanEngine::updateFrame()
+{
+    const glm::mat4 m = _scene->_camera->getView();
+    if (m != _refMatrix) { resetFrame(); _refMatrix = m; }
+    _denoise_frame++;
+}
+void VulkanEngine::resetFrame() { _denoise_frame = -1; }
+
+// vk_engine.cpp:688-741
+void VulkanEngine::updateCameraMatrices()
+{
+    float ratio = (float)_width / (float)_height;
+    glm::mat4 view = _scene->_camera->getView();
+    glm::mat4 projection = _scene->_camera->getProjection(ratio);
+    projection[1][1] *= -1;
+    if (!_havePrev) { _prevView = view; _prevProj = projection; _havePrev = true; }   // App. A #17: defined static-camera motion
+    if (_prevView != view || _prevProj != projection) {
+        _cameraData = build_camera(_scene->_camera, ratio, &_prevView, &_prevProj);
+        _prevView = view; _prevProj = projection;
+    } else {
+        _cameraData = build_camera(_scene->_camera, ratio, nullptr, nullptr);
+    }
+}
+
+// vk_engine.cpp:130-188
+void VulkanEngine::update(const float)
+{
+    updateFrame();
+    updateCameraMatrices();
+    std::vector<vkp_light> lights = build_lights(_scene);
+    if (vkp_set_lights(renderer->_ctx, lights.data(), (int)lights.size()) != VKP_OK) throw std::runtime_error(vkp_last_error(renderer->_ctx));
+    int instanceIndex = 0;
+    renderer->_tlas.clear();
+    for (Object* obj : _scene->_entities)
+        if (!obj->prefab->_root.empty())
+            for (Node* root : obj->prefab->_root) root->node_to_instance(renderer->_tlas, instanceIndex, obj->m_matrix);
+    renderer->buildTlas(renderer->_tlas, true);
+}
+
+// vk_engine.cpp:91-128 for a fixed number of frames
+void VulkanEngine::run(int frames)
+{
+    for (int f = 0; f < frames; f++) {
+        update(16.6f);
+        if (_mode == DEFERRED) renderer->render();
+        else if (_mode == RAYTRACING) renderer->raytrace();
+        else if (_mode == HYBRID) renderer->rasterize_hybrid();
+        _frameNumber++;
+    }
+}
+
+void VulkanEngine::cleanup()
+{
+    delete renderer; renderer = nullptr;
+    delete _scene; _scene = nullptr;
+    if (engine == this) engine = nullptr;
+}
