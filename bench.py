@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s and ms/frame of the Hybrid pipeline hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4]
+
+One "step" = one frame of the hot path (Renderer::rasterize_hybrid: G-buffer -> shadow rays -> denoise -> resolve +
+reflection rays) on the default scene at 1920x1080 with a static camera, frame index advancing (temporal accumulation),
+i.e. BASELINE.json configs[1].  Rays counted are the traceRayEXT calls the reference would issue (shadow + reflection +
+secondary shadow); our own primary-visibility rays are reported separately and NOT counted.
+
+N > 1 (torchrun, one rank per GPU): the frame is tile-sharded over a replicated BVH (tile t -> rank t % N) and the
+finished sRGB8 tiles are gathered to rank 0 over NCCL -- the only collective; "scaling": "strong".
+
+Prints ONE JSON line (rank 0) with the contract keys plus "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches".
+The CPU oracle (oracle/) is used only for the cpu_baseline leg and for --impl reference; it is never on the GPU path.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (scene index, width, height, mode, spp, shadow samples, faithful_rng, description)
+    "cfg2": (0, 1920, 1080, 2, 1, 1, 1, "default scene, Hybrid 1920x1080, 1 shadow ray/light/pixel + reflection rays, static camera"),
+    "cfg1": (0, 1280, 720, 2, 1, 1, 1, "default scene, Hybrid 1280x720 (oracle-sized case)"),
+    "cfg3": (0, 1920, 1080, 1, 64, 64, 0, "default scene, Raytraced 1920x1080, 64 spp x 64 shadow samples, advancing RNG"),
+    "cfg4": (2, 3840, 2160, 2, 1, 1, 1, "instanced stress scene (~10M instanced triangles), Hybrid 3840x2160"),
+    "cfg5": (3, 3840, 2160, 2, 1, 16, 0, "default scene, 16 ring lights x 16 shadow samples, Hybrid 3840x2160"),
+}
+
+
+def b_ray(T):
+    """algorithmic bytes per traced ray for a BVH over T triangles."""
+    return 32 + 16 + 32 * (1 + 2 * math.ceil(math.log2(max(T, 4) / 4))) + 4 * 36
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_leg(scene, W, H, mode, spp, samples, faithful, budget_s, steps, warmup, grow_steps=False):
+    """Times the CPU oracle (the reference's shader math on host cores) on a bounded row sample of the workload."""
+    import vulkanhybridraytracer_b200 as vk
+    from oracle.oracle_py import Oracle
+    o = Oracle(scene)
+    cores = o.threads()
+    cam = scene.camera(W, H)
+
+    def one(frame, stride):
+        o.set_row_sampling(stride, stride // 2)
+        o.reset_counters()
+        p = vk.make_params(W, H, mode=mode, spp=spp, shadow_samples=samples, faithful_rng=faithful, frame=frame)
+        t0 = time.perf_counter()
+        if mode == 2:
+            o.hybrid_frame(cam, p)
+        else:
+            o.raytrace(cam, p)
+        dt = time.perf_counter() - t0
+        c = list(o.counters.rays)
+        return dt, c[1] + c[2] + c[3], c[0]
+
+    # calibrate on a sparse sample, then pick the row stride so that (steps + warmup) samples fit the budget
+    stride = 64 if mode == 2 else 270
+    dt, _, _ = one(1, stride)
+    per_row = dt / max(1, H // stride)
+    rows = max(8, min(H, int(budget_s / max(1, steps + warmup) / max(per_row, 1e-9))))
+    stride = max(1, H // rows)
+    if grow_steps and stride == 1:
+        # fast host: whole frames fit the budget -- spend it on more frames so the sample is 10-30 s of CPU work
+        steps = int(min(200, max(steps, budget_s / max(per_row * H, 1e-9) - warmup)))
+    for w in range(warmup):
+        one(1 + w, stride)
+    tot_t, tot_rays = 0.0, 0
+    for k in range(steps):
+        dt, rays, _ = one(1 + warmup + k, stride)
+        tot_t += dt; tot_rays += rays
+    o.set_row_sampling(1, 0)
+    o.close()
+    rows = len(range(stride // 2, H, stride))
+    return {"mrays_s": tot_rays / tot_t / 1e6, "ms_per_frame_est": tot_t / steps * 1e3 * (H / rows), "cores": cores,
+            "sample": f"{steps} steps x every {stride}th row ({rows} of {H} rows) of the {W}x{H} frame, {tot_t:.1f} s of CPU time", "seconds": tot_t}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    scene_idx, W, H, mode, spp, samples, faithful, desc = WORKLOADS[args.workload]
+    peak, peak_src = measured_peak()
+
+    import vulkanhybridraytracer_b200 as vk
+
+    # ---------------------------------------------------------------------------------------- reference arm ----
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        scene = vk.HostScene(scene_idx)
+        leg = oracle_leg(scene, W, H, mode, spp, samples, faithful, budget_s=90.0, steps=args.steps, warmup=args.warmup)
+        line = {
+            "impl": "reference", "metric": "Mrays/s (Hybrid 1080p hot path: shadow + reflection + secondary-shadow rays per second)", "value": leg["mrays_s"],
+            "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_frame_est"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "triangles": scene.n_triangles, "note": "the reference (Vulkan RT, MSVC) cannot be built or run here; "
+                       "this arm times the CPU oracle = scalar port of its shaders + a binned-SAH BVH, OpenMP over rows, all host cores; ms_per_step is the "
+                       "full-frame estimate from the row sample"},
+            "cpu_baseline": {"value": leg["mrays_s"], "unit": "Mrays/s", "cores": leg["cores"], "kind": "port", "sample": leg["sample"]},
+            "e2e": {"value": leg["mrays_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------ ours ----
+    import torch
+    import torch.distributed as dist
+    from vulkanhybridraytracer_b200 import PLANE, tiling
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = local if world > 1 else 0
+    scene = vk.HostScene(scene_idx)
+    T = scene.n_triangles
+    ctx = vk.Context(dev)
+    ctx.upload_scene(scene)
+    cam = scene.camera(W, H)
+    ctx.set_camera(cam)
+    TW, TH = (32, 16)
+    ctx.set_tiling(rank, world, TW, TH)
+    L = len(scene.lights)
+
+    def params(frame):
+        return vk.make_params(W, H, mode=mode, spp=spp, shadow_samples=samples, faithful_rng=faithful, frame=frame)
+
+    # composite buffers (N > 1): packed sRGB8 tiles of every rank -> rank 0
+    sizes = [tiling.packed_bytes(W, H, r, world, 4, TW, TH) for r in range(world)]
+    packed = torch.empty(max(sizes), dtype=torch.uint8, device=f"cuda:{dev}") if world > 1 else None
+    gathered = [torch.empty(max(sizes), dtype=torch.uint8, device=f"cuda:{dev}") for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def composite():
+        ctx.tiles_pack(PLANE.FINAL_SRGB8, packed.data_ptr(), sizes[rank])
+        ctx.sync()
+        dist.gather(packed, gathered, dst=0)
+        if rank == 0:
+            torch.cuda.current_stream().synchronize()
+            for r in range(1, world):
+                ctx.tiles_unpack(PLANE.FINAL_SRGB8, r, world, gathered[r].data_ptr(), sizes[r])
+        return 2 + (world - 1 if rank == 0 else 0)
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx.set_params(params(0)); ctx.reset_history()
+    frame = 0
+    for _ in range(args.warmup):                      # warm-up: frame 0 (reset frame) .. W-1
+        ctx.set_params(params(frame)); ctx.render()
+        if world > 1:
+            composite()
+        frame += 1
+    ctx.sync()
+
+    # -- timed region 1: device time, inputs resident, K frames, L2 flushed between frames ---------------------------------------
+    ctx.set_profiling(True)
+    stage_ms = np.zeros(8)
+    rays = np.zeros(4, dtype=np.int64)
+    launches = 0
+    sampler = ClockSampler(dev); sampler.start()
+    barrier()
+    total_ms = 0.0
+    for k in range(args.steps):
+        if not args.no_flush:
+            ctx.flush_l2()
+        ctx.set_params(params(frame))
+        if world > 1:
+            dist.barrier()
+        ctx.timer_begin()
+        ctx.render()
+        n_launch = 0
+        if world > 1:
+            n_launch = composite()
+        total_ms += ctx.timer_end()
+        c = ctx.counters()
+        stage_ms += np.array(list(c.ms_stage))
+        rays += np.array([c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow], dtype=np.int64)
+        launches += c.kernel_launches + n_launch
+        frame += 1
+    barrier()
+    clocks = sampler.stop()
+    ctx.set_profiling(False)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{dev}")
+    r = torch.tensor(rays, dtype=torch.int64, device=f"cuda:{dev}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)            # max over ranks
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)            # whole-job rays
+    total_ms = float(t.item()); rays_all = r.cpu().numpy()
+    ms_per_step = total_ms / args.steps
+    counted = int(rays_all[1] + rays_all[2] + rays_all[3])
+    value = counted / args.steps / (ms_per_step * 1e-3) / 1e6
+
+    # -- timed region 2: end to end through the reference-facing host API (VulkanEngine::update + rasterize_hybrid + read-back) ---
+    e2e = None
+    if world == 1 and mode == 2 and scene_idx == 0:
+        ctx.close()
+        eng = vk.HostEngine(scene_idx, W, H, dev)
+        pinned = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+        for _ in range(args.warmup):
+            eng.frames(1)
+            eng._H.vkph_engine_read(eng._h, 0, pinned.data_ptr(), pinned.numel())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e_rays = 0
+        for k in range(args.steps):
+            eng.frames(1)          # update(): lights + instance matrices H2D, TLAS refit; then the 4 frame kernels
+            eng._H.vkph_engine_read(eng._h, 0, pinned.data_ptr(), pinned.numel())      # D2H of the presented image into pinned memory
+        dt = time.perf_counter() - t0
+        c = eng.counters()
+        e_rays = (c.rays_shadow + c.rays_reflect + c.rays_secondary_shadow)
+        e2e = {"value": e_rays / (dt / args.steps) / 1e6, "unit": "Mrays/s", "ms_per_step": dt / args.steps * 1e3,
+               "h2d_bytes_per_step": 48 * L + 144 * len(scene.instances) + 400 + 64, "d2h_bytes_per_step": W * H * 4,
+               "api": "VulkanEngine::update + Renderer::rasterize_hybrid + read-back of the sRGB8 image (host C++ over the C-ABI), wall clock"}
+        eng.close()
+    else:
+        # tile-sharded / other workloads: same loop through the C-ABI with per-frame host inputs and a read-back on rank 0
+        pinned = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            ctx.set_lights(scene.lights); ctx.set_camera(cam); ctx.set_params(params(frame + k))
+            ctx.render()
+            if world > 1:
+                composite()
+            if rank == 0:
+                ctx.L.vkp_readback(ctx.h, PLANE.FINAL_SRGB8, pinned.data_ptr(), pinned.numel())
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{dev}")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": counted / args.steps / (dt / args.steps) / 1e6, "unit": "Mrays/s", "ms_per_step": dt / args.steps * 1e3,
+               "h2d_bytes_per_step": 48 * L + 400 + 64, "d2h_bytes_per_step": W * H * 4,
+               "api": "vkp_set_lights/camera/params + vkp_render (+ NCCL tile gather) + vkp_readback(FINAL_SRGB8) on rank 0, wall clock"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return 0
+
+    # -- roofline of the dominant kernel (SURVEY 8d algorithmic bytes / CUDA-event duration) ------------------------------------------
+    P = W * H
+    names = ["k_gbuffer", "k_shadow", "k_denoise", "k_resolve", "k_post", "k_raytrace", "k_deferred"]
+    per_frame = rays_all / args.steps / world          # this rank's share (tiles are balanced)
+    Pr = P / world
+    BR = b_ray(T)
+    kbytes = {
+        "k_gbuffer": Pr * 32 + per_frame[0] * BR,
+        "k_shadow": Pr * (16 + L) + per_frame[1] * BR,
+        "k_denoise": Pr * (2 * L + 4 + L),
+        "k_resolve": Pr * (32 + L + 16) + (per_frame[2] + per_frame[3]) * BR,
+        "k_raytrace": Pr * 32 + (per_frame[2] + per_frame[3]) * BR,
+    }
+    ms = stage_ms / args.steps
+    dom = int(np.argmax(ms))
+    dname = names[dom]
+    achieved = kbytes.get(dname, 0.0) / (ms[dom] * 1e-3) / 1e9 if ms[dom] > 0 else 0.0
+    frame_bytes = sum(kbytes[n] for n in (("k_gbuffer", "k_shadow", "k_denoise", "k_resolve") if mode == 2 else ("k_raytrace",)))
+    roofline = {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": kbytes.get(dname, 0.0), "kernel_ms": float(ms[dom]),
+                "kernel_share_of_step": float(ms[dom] / max(ms.sum(), 1e-9)),
+                "stage_ms": {names[i]: float(ms[i]) for i in range(7) if ms[i] > 0},
+                "frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_bytes * world / (ms_per_step * 1e-3) / 1e9, "frac": frame_bytes * world / (ms_per_step * 1e-3) / 1e9 / (peak * world)},
+                "note": "algorithmic bytes = P*B_px(stage) + rays*B_ray(T) (SURVEY 8d, B_ray=%d B at T=%d); traversal is latency/L2 bound, measured DRAM traffic is far below this" % (BR, T)}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get(dname)
+        except Exception:
+            pass
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        leg = oracle_leg(scene, W, H, mode, spp, samples, faithful, budget_s=15.0, steps=2, warmup=1, grow_steps=True)
+        cpu = {"value": leg["mrays_s"], "unit": "Mrays/s", "cores": leg["cores"], "kind": "port", "sample": leg["sample"],
+               "ms_per_frame_est": leg["ms_per_frame_est"]}
+
+    line = {
+        "metric": "Mrays/s (Hybrid 1080p hot path: shadow + reflection + secondary-shadow rays per second)", "value": value, "unit": "Mrays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "triangles": T, "lights": L, "pixels": P,
+                   "rays_per_frame": {"shadow": int(rays_all[1] // args.steps), "reflect": int(rays_all[2] // args.steps),
+                                      "secondary_shadow": int(rays_all[3] // args.steps), "primary_not_counted": int(rays_all[0] // args.steps)},
+                   "mrays_s_incl_primary": float(rays_all.sum()) / args.steps / (ms_per_step * 1e-3) / 1e6,
+                   "nominal_2P_mrays_s": 2 * P / (ms_per_step * 1e-3) / 1e6,
+                   "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
+                   "parallelism": f"tiles {TW}x{TH} interleaved over {world} GPU(s), replicated BVH, NCCL gather of sRGB8 tiles" if world > 1 else "1 GPU",
+                   "timing": "CUDA events on the context stream around each frame, summed over K frames, max over ranks"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

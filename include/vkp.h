@@ -110,6 +110,9 @@ VKP_API int vkp_flush_l2(vkp_ctx* ctx);
 VKP_API int vkp_tiles_packed_bytes(const vkp_ctx* ctx, int plane, int rank, int world, size_t* bytes);
 VKP_API int vkp_tiles_pack(vkp_ctx* ctx, int plane, void* device_dst, size_t bytes);
 VKP_API int vkp_tiles_unpack(vkp_ctx* ctx, int plane, int rank, int world, const void* device_src, size_t bytes);
+/* numerics-contract probe (tests): evaluate one vkp_detmath.h function on the DEVICE over host arrays.
+ * func: 0 sin, 1 cos, 2 atan2(x,y), 3 asin, 4 pow(x,y), 5 log2, 6 exp2, 7 f32->f16->f32, 8 unorm8 */
+VKP_API int vkp_eval_math(vkp_ctx* ctx, int func, const float* x, const float* y, uint32_t n, float* out);
 /* run subsequent work on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
 VKP_API int vkp_set_stream(vkp_ctx* ctx, void* cuda_stream);
 

@@ -22,6 +22,9 @@
 
 using namespace orc;
 
+/* timing aid for bench.py: process only rows y with y % stride == offset (a representative sample of the frame) */
+static int g_row_stride = 1, g_row_offset = 0;
+
 /* ------------------------------------------------------------------------------------------------
  * scene storage + a simple binned-SAH BVH per (mesh, firstIndex, indexCount) range (the reference
  * builds one BLAS per primitive: renderer.cpp:1643-1666, vk_mesh.cpp:424-470)
@@ -541,6 +544,7 @@ void shade_hit(const orc_scene& S, const vkp_params& P, bool rt_mode, vec3 rayO,
 extern "C" {
 
 int orc_abi_version(void) { return 1; }
+void orc_set_row_sampling(int stride, int offset) { g_row_stride = stride > 0 ? stride : 1; g_row_offset = offset; }
 int orc_num_threads(void)
 {
 #ifdef _OPENMP
@@ -614,6 +618,7 @@ void orc_gbuffer_pass(const orc_scene* sp, const vkp_camera* cam, const vkp_para
     uint64_t nrays = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : nrays)
     for (int y = 0; y < H; y++) {
+        if (g_row_stride > 1 && y % g_row_stride != g_row_offset) continue;
         for (int x = 0; x < W; x++) {
             const size_t px = (size_t)y * W + x;
             vec3 o, d; camera_ray(*cam, x, y, 0.5f, 0.5f, W, H, o, d);
@@ -684,6 +689,7 @@ void orc_shadow_pass(const orc_scene* sp, const vkp_camera* cam, const vkp_param
     uint64_t nrays = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : nrays)
     for (int y = 0; y < H; y++) {
+        if (g_row_stride > 1 && y % g_row_stride != g_row_offset) continue;
         for (int x = 0; x < W; x++) {
             const size_t px = (size_t)y * W + x;
             const int frame = p->frame;
@@ -752,6 +758,7 @@ void orc_denoise_pass(const vkp_params* p, int n_lights, const orc_gbuffer* g, c
     };
 #pragma omp parallel for schedule(static)
     for (int y = 0; y < Hc; y++) {
+        if (g_row_stride > 1 && y % g_row_stride != g_row_offset) continue;
         for (int x = 0; x < Wc; x++) {
             const size_t px = (size_t)y * W + x;
             for (int l = 0; l < n_lights; l++) {
@@ -798,6 +805,7 @@ void orc_resolve_pass(const orc_scene* sp, const vkp_camera* cam, const vkp_para
     uint64_t r_refl = 0, r_sec = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : r_refl, r_sec)
     for (int y = 0; y < H; y++) {
+        if (g_row_stride > 1 && y % g_row_stride != g_row_offset) continue;
         for (int x = 0; x < W; x++) {
             const size_t px = (size_t)y * W + x;
             orc_counters lc; memset(&lc, 0, sizeof(lc));
@@ -935,6 +943,7 @@ void orc_raytrace_pass(const orc_scene* sp, const vkp_camera* cam, const vkp_par
     uint64_t r_refl = 0, r_sec = 0;
 #pragma omp parallel for schedule(dynamic, 2) reduction(+ : r_refl, r_sec)
     for (int y = 0; y < H; y++) {
+        if (g_row_stride > 1 && y % g_row_stride != g_row_offset) continue;
         for (int x = 0; x < W; x++) {
             const size_t px = (size_t)y * W + x;
             orc_counters lc; memset(&lc, 0, sizeof(lc));
@@ -982,6 +991,7 @@ void orc_deferred_pass(const orc_scene* sp, const vkp_camera* cam, const vkp_par
     const int W = p->width, H = p->height;
 #pragma omp parallel for schedule(static)
     for (int y = 0; y < H; y++) {
+        if (g_row_stride > 1 && y % g_row_stride != g_row_offset) continue;
         for (int x = 0; x < W; x++) {
             const size_t px = (size_t)y * W + x;
             vec4 pos4 = load_half4(g->position, px);

@@ -56,6 +56,8 @@ int  orc_abi_version(void);
 int  orc_num_threads(void);
 void orc_set_num_threads(int n);
 int  orc_uses_libm(void);
+/* bench timing aid: passes only process rows y % stride == offset (results of skipped rows are left untouched) */
+void orc_set_row_sampling(int stride, int offset);
 
 orc_scene* orc_scene_create(const orc_scene_desc* desc);   /* deep-copies everything, builds BVHs */
 void orc_scene_destroy(orc_scene* s);

@@ -53,6 +53,7 @@ def load(libm=False):
     L.orc_num_threads.restype = i
     L.orc_set_num_threads.argtypes = [i]
     L.orc_uses_libm.restype = i
+    L.orc_set_row_sampling.argtypes = [i, i]
     L.orc_scene_create.restype = vp; L.orc_scene_create.argtypes = [P(OrcSceneDesc)]
     L.orc_scene_destroy.argtypes = [vp]
     L.orc_scene_set_lights.argtypes = [vp, vp, i]
@@ -148,6 +149,10 @@ class Oracle:
     def set_instances(self, inst):
         inst = np.ascontiguousarray(inst, dtype=T.instance_dtype)
         self.L.orc_scene_set_instances(self.h, inst.ctypes.data, len(inst))
+
+    def set_row_sampling(self, stride, offset=0):
+        """bench timing aid: only rows y % stride == offset are processed (1 = every row)."""
+        self.L.orc_set_row_sampling(stride, offset)
 
     def reset_counters(self):
         self.counters = OrcCounters()

@@ -97,6 +97,7 @@ def load_vkp():
         "vkp_tiles_pack": (i, [vp, i, vp, sz]),
         "vkp_tiles_unpack": (i, [vp, i, i, i, vp, sz]),
         "vkp_set_stream": (i, [vp, vp]),
+        "vkp_eval_math": (i, [vp, i, vp, vp, u32, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -386,6 +387,13 @@ class Context:
         prims = np.empty(npr.value, dtype=np.uint32)
         self._ck(self.L.vkp_bvh_download(self.h, blas_index, nodes.ctypes.data, prims.ctypes.data if npr.value else None), "vkp_bvh_download")
         return nodes, prims
+
+    def eval_math(self, func, x, y=None):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.zeros_like(x) if y is None else np.ascontiguousarray(y, dtype=np.float32)
+        out = np.empty_like(x)
+        self._ck(self.L.vkp_eval_math(self.h, func, x.ctypes.data, y.ctypes.data, x.size, out.ctypes.data), "vkp_eval_math")
+        return out
 
     def timer_begin(self):
         self._ck(self.L.vkp_timer_begin(self.h), "vkp_timer_begin")

@@ -375,7 +375,7 @@ cudaError_t bvh_emit_triangles(cudaStream_t s, const vkp_vertex* verts, const ui
 {
     cudaError_t e;
     if ((e = B.tris.ensure(sizeof(float4) * 3 * (size_t)(B.n_prims ? B.n_prims : 1))) != cudaSuccess) return e;
-    if (B.n_prims == 0) return cudaSuccess;
+    if (B.n_prims == 0) return cudaMemsetAsync(B.tris.p, 0, sizeof(float4) * 3, s);   // one degenerate triangle: det == 0, never hit
     k_emit_triangles<<<blocks_for(B.n_prims, 256), 256, 0, s>>>(verts, indices, B.items.as<uint32_t>(), B.n_prims, B.tris.as<float4>());
     return cudaGetLastError();
 }

@@ -618,23 +618,20 @@ __global__ void __launch_bounds__(128) k_trace_list(const __grid_constant__ DSce
 }
 
 // ---- multi-GPU tile pack / unpack (SURVEY 8e composite) -------------------------------------------------------
-__global__ void k_tiles_copy(uint8_t* __restrict__ plane, uint8_t* __restrict__ packed, int elem_bytes, int W, int H, int tile_w, int tile_h,
-                             int tiles_x, int rank, int world, int to_plane)
+template <typename E>
+__global__ void k_tiles_copy(E* __restrict__ plane, E* __restrict__ packed, int W, int H, int tile_w, int tile_h, int tiles_x, int rank, int world, int to_plane)
 {
+    // one CTA per owned tile, one element (pixel) per thread iteration; rows of a tile are contiguous in both layouts
     const int own_tile = blockIdx.x;
     const int tile = rank + own_tile * world;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
-    const int row_bytes = tile_w * elem_bytes;
-    for (int r = threadIdx.y; r < tile_h; r += blockDim.y) {
-        const int y = ty * tile_h + r;
-        if (y >= H) continue;
-        for (int b = threadIdx.x * 4; b < row_bytes; b += blockDim.x * 4) {
-            const int x = tx * tile_w + b / elem_bytes;
-            if (x >= W) continue;
-            uint32_t* pp = reinterpret_cast<uint32_t*>(plane + ((size_t)y * W) * elem_bytes + (size_t)tx * row_bytes + b);
-            uint32_t* qq = reinterpret_cast<uint32_t*>(packed + ((size_t)own_tile * tile_h + r) * row_bytes + b);
-            if (to_plane) *pp = *qq; else *qq = *pp;
-        }
+    for (int e = threadIdx.x; e < tile_w * tile_h; e += blockDim.x) {
+        const int r = e / tile_w, c = e - r * tile_w;
+        const int x = tx * tile_w + c, y = ty * tile_h + r;
+        if (x >= W || y >= H) continue;
+        E* pp = plane + (size_t)y * W + x;
+        E* qq = packed + (size_t)own_tile * tile_w * tile_h + e;
+        if (to_plane) *pp = *qq; else *qq = *pp;
     }
 }
 
@@ -643,6 +640,25 @@ __global__ void k_l2_flush(uint4* buf, size_t n)
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) buf[i] = make_uint4((unsigned)i, 1u, 2u, 3u);
+}
+
+__global__ void k_eval_math(int func, const float* __restrict__ x, const float* __restrict__ y, uint32_t n, float* __restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float r;
+    switch (func) {
+    case 0: r = vkp_sinf(x[i]); break;
+    case 1: r = vkp_cosf(x[i]); break;
+    case 2: r = vkp_atan2f(x[i], y[i]); break;
+    case 3: r = vkp_asinf(x[i]); break;
+    case 4: r = vkp_powf(x[i], y[i]); break;
+    case 5: r = vkp_log2f(x[i]); break;
+    case 6: r = vkp_exp2f(x[i]); break;
+    case 7: r = vkp_f16_to_f32(vkp_f32_to_f16(x[i])); break;
+    default: r = (float)vkp_unorm8(x[i]); break;
+    }
+    out[i] = r;
 }
 
 inline dim3 frame_grid(const FrameLaunch& L)
@@ -678,18 +694,31 @@ static int own_tiles(int W, int H, int tw, int th, int rank, int world, int* til
     return total > rank ? (total - rank + world - 1) / world : 0;
 }
 
-cudaError_t launch_tiles_pack(cudaStream_t s, const void* plane, void* dst, int elem_bytes, int W, int H, int tw, int th, int rank, int world)
+static cudaError_t tiles_copy(cudaStream_t s, void* plane, void* packed, int elem_bytes, int W, int H, int tw, int th, int rank, int world, int to_plane)
 {
     int tiles_x; int n = own_tiles(W, H, tw, th, rank, world, &tiles_x);
     if (n == 0) return cudaSuccess;
-    k_tiles_copy<<<n, dim3(32, 8), 0, s>>>((uint8_t*)plane, (uint8_t*)dst, elem_bytes, W, H, tw, th, tiles_x, rank, world, 0);
+    switch (elem_bytes) {
+    case 1: k_tiles_copy<uint8_t><<<n, 128, 0, s>>>((uint8_t*)plane, (uint8_t*)packed, W, H, tw, th, tiles_x, rank, world, to_plane); break;
+    case 4: k_tiles_copy<uint32_t><<<n, 128, 0, s>>>((uint32_t*)plane, (uint32_t*)packed, W, H, tw, th, tiles_x, rank, world, to_plane); break;
+    case 8: k_tiles_copy<uint2><<<n, 128, 0, s>>>((uint2*)plane, (uint2*)packed, W, H, tw, th, tiles_x, rank, world, to_plane); break;
+    case 16: k_tiles_copy<uint4><<<n, 128, 0, s>>>((uint4*)plane, (uint4*)packed, W, H, tw, th, tiles_x, rank, world, to_plane); break;
+    default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
+}
+cudaError_t launch_tiles_pack(cudaStream_t s, const void* plane, void* dst, int elem_bytes, int W, int H, int tw, int th, int rank, int world)
+{
+    return tiles_copy(s, const_cast<void*>(plane), dst, elem_bytes, W, H, tw, th, rank, world, 0);
 }
 cudaError_t launch_tiles_unpack(cudaStream_t s, void* plane, const void* src, int elem_bytes, int W, int H, int tw, int th, int rank, int world)
 {
-    int tiles_x; int n = own_tiles(W, H, tw, th, rank, world, &tiles_x);
+    return tiles_copy(s, plane, const_cast<void*>(src), elem_bytes, W, H, tw, th, rank, world, 1);
+}
+cudaError_t launch_eval_math(cudaStream_t s, int func, const float* x, const float* y, uint32_t n, float* out)
+{
     if (n == 0) return cudaSuccess;
-    k_tiles_copy<<<n, dim3(32, 8), 0, s>>>((uint8_t*)plane, (uint8_t*)src, elem_bytes, W, H, tw, th, tiles_x, rank, world, 1);
+    k_eval_math<<<(n + 255u) / 256u, 256, 0, s>>>(func, x, y, n, out);
     return cudaGetLastError();
 }
 cudaError_t launch_l2_flush(cudaStream_t s, void* buf, size_t bytes)

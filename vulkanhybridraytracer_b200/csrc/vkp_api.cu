@@ -596,6 +596,22 @@ int vkp_trace_rays(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, v
     return VKP_OK;
 }
 
+int vkp_eval_math(vkp_ctx* ctx, int func, const float* x, const float* y, uint32_t n, float* out)
+{
+    if (!ctx || (n && (!x || !y || !out))) return fail(ctx, VKP_ERR_INVALID, "vkp_eval_math: NULL");
+    if (n == 0) return VKP_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->io_tmp.ensure(sizeof(float) * 2 * (size_t)n));
+    CK(ctx->io_tmp2.ensure(sizeof(float) * (size_t)n));
+    float* dx = ctx->io_tmp.as<float>(); float* dy = dx + n;
+    CK(cudaMemcpyAsync(dx, x, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dy, y, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_eval_math(ctx->stream, func, dx, dy, n, ctx->io_tmp2.as<float>()));
+    CK(cudaMemcpyAsync(out, ctx->io_tmp2.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VKP_OK;
+}
+
 static Bvh* pick_bvh(vkp_ctx* ctx, int blas_index)
 {
     if (blas_index < 0) return ctx->tlas_built ? &ctx->tlas : nullptr;

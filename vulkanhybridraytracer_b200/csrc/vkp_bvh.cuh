@@ -34,16 +34,30 @@ VKP_D float3 safe_inv_dir(float3 d)
     return r;
 }
 
-// conservative slab test in (b - o) * inv form (relative error only) with an 8-ulp slack on the far side
-VKP_D bool box_test(const float4 lo, const float4 hi, float3 o, float3 inv, float tmin, float tmax, float& tnear)
+// conservative slab test in (b - o) * inv form (relative error only) with slack on both ends.  PAR == true is the
+// rare path for rays with a (near-)zero direction component: such a ray is inside a slab for all t or for none,
+// including when it lies exactly in a face plane of the box (0 * inf in exact arithmetic).
+template <bool PAR>
+VKP_D bool box_test(const float4 lo, const float4 hi, float3 o, float3 d, float3 inv, float tmin, float tmax, float& tnear)
 {
     float x0 = (lo.x - o.x) * inv.x, x1 = (hi.x - o.x) * inv.x;
     float y0 = (lo.y - o.y) * inv.y, y1 = (hi.y - o.y) * inv.y;
     float z0 = (lo.z - o.z) * inv.z, z1 = (hi.z - o.z) * inv.z;
+    if (PAR) {
+        const float inf = __int_as_float(0x7f800000);
+        if (fabsf(d.x) <= 1e-30f) { bool in = lo.x <= o.x && o.x <= hi.x; x0 = in ? -inf : inf; x1 = in ? inf : -inf; }
+        if (fabsf(d.y) <= 1e-30f) { bool in = lo.y <= o.y && o.y <= hi.y; y0 = in ? -inf : inf; y1 = in ? inf : -inf; }
+        if (fabsf(d.z) <= 1e-30f) { bool in = lo.z <= o.z && o.z <= hi.z; z0 = in ? -inf : inf; z1 = in ? inf : -inf; }
+    }
     float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
     float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
     tnear = tn;
     return tn * 0.999999f <= tf * 1.000001f;
+}
+VKP_D bool has_parallel_axis(float3 d) { return fabsf(d.x) <= 1e-30f || fabsf(d.y) <= 1e-30f || fabsf(d.z) <= 1e-30f; }
+VKP_D bool box_test(const float4 lo, const float4 hi, float3 o, float3 d, float3 inv, bool par, float tmin, float tmax, float& tnear)
+{
+    return par ? box_test<true>(lo, hi, o, d, inv, tmin, tmax, tnear) : box_test<false>(lo, hi, o, d, inv, tmin, tmax, tnear);
 }
 
 // the intersection contract
@@ -78,6 +92,7 @@ template <bool ANY>
 VKP_D bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax, HitRec& best)
 {
     best.t = -1.0f; best.u = 0.0f; best.v = 0.0f; best.inst = -1; best.prim = -1;
+    if (S.n_instances == 0) return false;     // empty TLAS: its root box is inverted, which a slab test cannot reject
     float limit = tmax;                       // current far bound (closest so far)
 
     uint32_t stack[VKP_TRAV_STACK];
@@ -86,6 +101,8 @@ VKP_D bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax
 
     float3 ro = o, rd = d;
     float3 inv = safe_inv_dir(rd);
+    const bool wpar = has_parallel_axis(d);
+    bool par = wpar;
     const float4* nodes = reinterpret_cast<const float4*>(S.tlas_nodes);
     const float4* tris = nullptr;
     int inst = -1;
@@ -94,7 +111,7 @@ VKP_D bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax
     {
         float4 lo = __ldg(&nodes[0]), hi = __ldg(&nodes[1]);
         float tn;
-        if (!box_test(lo, hi, ro, inv, tmin, limit, tn)) return false;
+        if (!box_test(lo, hi, ro, rd, inv, par, tmin, limit, tn)) return false;
         cur = __float_as_uint(lo.w);
     }
 
@@ -104,8 +121,8 @@ VKP_D bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax
             const float4* c = nodes + 2u * (size_t)cur;
             float4 lo0 = __ldg(c + 0), hi0 = __ldg(c + 1), lo1 = __ldg(c + 2), hi1 = __ldg(c + 3);
             float t0, t1;
-            bool h0 = box_test(lo0, hi0, ro, inv, tmin, limit, t0);
-            bool h1 = box_test(lo1, hi1, ro, inv, tmin, limit, t1);
+            bool h0 = box_test(lo0, hi0, ro, rd, inv, par, tmin, limit, t0);
+            bool h1 = box_test(lo1, hi1, ro, rd, inv, par, tmin, limit, t1);
             uint32_t r0 = __float_as_uint(lo0.w), r1 = __float_as_uint(lo1.w);
             if (h0 && h1) {
                 bool swap = t1 < t0;
@@ -123,17 +140,18 @@ VKP_D bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax
             ro = xform_point(I.inv_model, o);
             rd = xform_dir(I.inv_model, d);
             inv = safe_inv_dir(rd);
+            par = has_parallel_axis(rd);
             nodes = reinterpret_cast<const float4*>(I.nodes);
             tris = I.tris;
             float4 lo = __ldg(&nodes[0]), hi = __ldg(&nodes[1]);
             float tn;
-            if (box_test(lo, hi, ro, inv, tmin, limit, tn)) {
+            if (box_test(lo, hi, ro, rd, inv, par, tmin, limit, tn)) {
                 stack[sp++] = VKP_STACK_RETURN;
                 cur = __float_as_uint(lo.w);
                 continue;
             }
             // missed the object-space root: fall through to pop, but first leave the instance
-            inst = -1; ro = o; rd = d; inv = safe_inv_dir(rd);
+            inst = -1; ro = o; rd = d; inv = safe_inv_dir(rd); par = wpar;
             nodes = reinterpret_cast<const float4*>(S.tlas_nodes);
         } else {
             // BLAS leaf: triangles
@@ -156,7 +174,7 @@ VKP_D bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax
         while (true) {
             cur = stack[--sp];
             if (cur == VKP_STACK_RETURN) {
-                inst = -1; ro = o; rd = d; inv = safe_inv_dir(rd);
+                inst = -1; ro = o; rd = d; inv = safe_inv_dir(rd); par = wpar;
                 nodes = reinterpret_cast<const float4*>(S.tlas_nodes);
                 continue;
             }

@@ -141,8 +141,9 @@ VKPH_API int vkph_engine_read(void* p, int linear, void* dst, size_t bytes)
 {
     VulkanEngine* e = (VulkanEngine*)p;
     try {
-        if (linear) { auto v = e->renderer->read_final_linear(); if (bytes < v.size() * 4) return -1; std::memcpy(dst, v.data(), v.size() * 4); }
-        else { auto v = e->renderer->read_final_srgb8(); if (bytes < v.size()) return -1; std::memcpy(dst, v.data(), v.size()); }
+        size_t need = (size_t)e->_width * e->_height * (linear ? 16 : 4);
+        if (bytes < need) { g_err = "vkph_engine_read: destination too small"; return -1; }
+        e->renderer->read_into(linear ? VKP_PLANE_FINAL_F32 : VKP_PLANE_FINAL_SRGB8, dst, need);
         return 0;
     } catch (const std::exception& ex) { g_err = ex.what(); return -1; }
 }

@@ -70,8 +70,8 @@ void Renderer::buildTlas(const std::vector<TlasInstance>& input, bool update)
             changed = true;
         }
     }
-    if (!changed && update) return;   // the reference refits every frame regardless (vk_engine.cpp:187); identical result
-    VKP_CHECK(vkp_set_instances(_ctx, _instances.data(), (int)_instances.size()));
+    // the reference refits every frame whether or not anything moved (vk_engine.cpp:172-187): so do we
+    if (changed || !update) VKP_CHECK(vkp_set_instances(_ctx, _instances.data(), (int)_instances.size()));
     VKP_CHECK(vkp_build_tlas(_ctx, update ? 1 : 0));
 }
 
@@ -95,6 +95,8 @@ void Renderer::submit(renderMode mode)
 void Renderer::render() { submit(DEFERRED); }
 void Renderer::raytrace() { submit(RAYTRACING); }
 void Renderer::rasterize_hybrid() { submit(HYBRID); }
+
+void Renderer::read_into(int plane, void* dst, size_t bytes) { VKP_CHECK(vkp_readback(_ctx, plane, dst, bytes)); }
 
 std::vector<uint8_t> Renderer::read_final_srgb8()
 {

@@ -243,6 +243,7 @@ public:
     // headless outputs
     std::vector<uint8_t> read_final_srgb8();
     std::vector<float> read_final_linear();
+    void read_into(int plane, void* dst, size_t bytes);   // straight into caller (e.g. pinned) memory
     vkp_counters counters();
 
 private:
