@@ -189,12 +189,15 @@ VKP_HD float vkp_exp2f(float x)
     return p * vkp_u2f((uint32_t)e << 23);
 }
 
-/* GLSL pow(x, y) for x >= 0.  pow(0, y>0) = 0, pow(x, 0) = 1. */
+/* GLSL pow(x, y) for x >= 0.  pow(0, y>0) = 0, pow(x, 0) = 1.  The two small integer exponents the shaders use
+ * (helpers.glsl:71 pow(1-cos, 5.0); hybridRaygen.rgen:143 pow(eta, 2.0)) are plain products. */
 VKP_HD float vkp_powf(float x, float y)
 {
     if (y == 0.0f) return 1.0f;
     if (!(x > 0.0f)) return 0.0f;
     if (x == 1.0f) return 1.0f;
+    if (y == 2.0f) return x * x;
+    if (y == 5.0f) { float x2 = x * x; return (x2 * x2) * x; }
     return vkp_exp2f(y * vkp_log2f(x));
 }
 

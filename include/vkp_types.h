@@ -79,7 +79,9 @@ typedef struct vkp_params {
     int32_t faithful_rng;            /* 1: sampleDisk gets the seed by value (helpers.glsl:82)     */
     int32_t denoise_cover_remainder; /* 0: dispatch W/16 x H/16 groups exactly (renderer.cpp:2672) */
     int32_t debug_target;            /* deferred.frag debug.target 0..6                            */
-    int32_t reserved[5];
+    int32_t wavefront;               /* reflection chain (hybridRaygen.rgen:153-170): 0 = inline in the resolve kernel,
+                                        1 = wavefront path queues with ray compaction, one launch per bounce        */
+    int32_t reserved[4];
 } vkp_params;
 
 /* Planes readable with vkp_readback / writable with vkp_upload_plane.  Layouts are row-major,

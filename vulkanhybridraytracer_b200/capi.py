@@ -155,12 +155,13 @@ def load_host():
 
 
 def make_params(width, height, mode=MODE_HYBRID, spp=1, shadow_samples=1, max_bounces=8, frame=0, denoise_frame=None,
-                faithful_rng=1, denoise_cover_remainder=1, debug_target=0):
+                faithful_rng=1, denoise_cover_remainder=1, debug_target=0, wavefront=0):
     p = T.Params()
     p.width, p.height, p.mode, p.spp, p.shadow_samples, p.max_bounces = width, height, mode, spp, shadow_samples, max_bounces
     p.frame = frame
     p.denoise_frame = frame if denoise_frame is None else denoise_frame
     p.faithful_rng, p.denoise_cover_remainder, p.debug_target = faithful_rng, denoise_cover_remainder, debug_target
+    p.wavefront = wavefront
     return p
 
 

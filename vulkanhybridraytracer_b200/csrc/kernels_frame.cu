@@ -40,12 +40,30 @@ __device__ __forceinline__ void add_counter(unsigned long long* counters, int sl
 }
 
 // image store into the B8G8R8A8_UNORM target (renderer.cpp:1535) followed by postFragment.frag:9-21
-__device__ __forceinline__ uchar4 post_pixel(float4 c)
+// (the 8-bit store leaves 256 possible inputs per channel: the gamma curve is a table built on the device by k_build_luts)
+__device__ __forceinline__ uchar4 post_pixel(const uint8_t* __restrict__ lut_post, float4 c)
 {
-    float r = (float)vkp_unorm8(c.x) / 255.0f, g = (float)vkp_unorm8(c.y) / 255.0f, b = (float)vkp_unorm8(c.z) / 255.0f;
-    const float gamma = 1.0f / 2.2f;
-    r = vkp_powf(fmaxf(r, 0.001f), gamma); g = vkp_powf(fmaxf(g, 0.001f), gamma); b = vkp_powf(fmaxf(b, 0.001f), gamma);
-    return make_uchar4(vkp_unorm8(r), vkp_unorm8(g), vkp_unorm8(b), vkp_unorm8(c.w));
+    return make_uchar4(__ldg(&lut_post[vkp_unorm8(c.x)]), __ldg(&lut_post[vkp_unorm8(c.y)]), __ldg(&lut_post[vkp_unorm8(c.z)]), vkp_unorm8(c.w));
+}
+
+__global__ void k_build_luts(float* lut_pow22, uint8_t* lut_post)
+{
+    const int k = threadIdx.x;
+    const float x = (float)k / 255.0f;
+    lut_pow22[k] = vkp_powf(x, 2.2f);
+    lut_post[k] = vkp_unorm8(vkp_powf(fmaxf(x, 0.001f), 1.0f / 2.2f));
+}
+
+// warp-aggregated queue append: one atomic per warp, slots assigned with ballot + popc prefix (ray compaction)
+__device__ __forceinline__ void path_push(PathItem* q, unsigned int* count, bool want, const PathItem& item)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == (__ffs(mask) - 1)) base = atomicAdd(count, (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+    if (want) q[base + __popc(mask & ((1u << lane) - 1u))] = item;
 }
 
 struct Payload { float3 color; float dist; float3 direction; float scatter; float3 origin; uint32_t seed; };
@@ -55,7 +73,7 @@ __device__ __forceinline__ void shade_miss(const DScene& S, float3 rayDir, Paylo
 {
     float3 dir = normalize3(rayDir);
     float2 uv = equirect_uv(dir, VKP_PI_MISS);
-    prd.color = pow3(xyz(tex_nearest(S.textures[S.sky_tex], uv.x, uv.y)), 2.2f);
+    prd.color = lut3(S.lut_pow22, tex_nearest_raw(S.textures[S.sky_tex], uv.x, uv.y));
     prd.dist = -1.0f;
 }
 
@@ -82,11 +100,11 @@ __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, flo
 
     const vkp_material& mat = S.materials[max(0, min(I.material_id, S.n_materials - 1))];
     const int shadingMode = (int)mat.shadingMetallicRoughness[0];
-    float3 albedo = mat.textures[0] > -1 ? xyz(tex_nearest(S.textures[(int)mat.textures[0]], uvx, uvy)) : f3(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2]);
+    float3 albedo = mat.textures[0] > -1 ? lut3(S.lut_pow22, tex_nearest_raw(S.textures[(int)mat.textures[0]], uvx, uvy))
+                                         : pow3(f3(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2]), 2.2f);
     const float3 emissive = mat.textures[2] > -1 ? xyz(tex_nearest(S.textures[(int)mat.textures[2]], uvx, uvy)) : f3s(0.0f);
     const float3 roughnessMetallic = mat.textures[3] > -1 ? xyz(tex_nearest(S.textures[(int)mat.textures[3]], uvx, uvy))
                                                           : f3(0.0f, mat.shadingMetallicRoughness[2], mat.shadingMetallicRoughness[1]);
-    albedo = pow3(albedo, 2.2f);
     const float roughness = roughnessMetallic.y, metallic = roughnessMetallic.z;
     const float3 F0 = mix3(f3s(0.04f), albedo, metallic);
 
@@ -357,10 +375,15 @@ __global__ void __launch_bounds__(128) k_denoise(const __grid_constant__ DScene 
 }
 
 // hybridRaygen.rgen:27-186
+// WAVEFRONT == false: the bounce chain runs inline in this kernel (its latency hides behind the other pixels' shading);
+// WAVEFRONT == true: mirror / glass pixels are compacted into a path queue consumed by k_bounce, one launch per bounce.
+template <bool WAVEFRONT>
 __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     const Pixel px = pixel_of_thread(F);
+    bool wants_path = false;
     unsigned int n_refl = 0, n_sec = 0;
+    PathItem item;
     if (px.valid) {
         const int W = F.p.width, H = F.p.height;
         const size_t i = (size_t)px.y * W + px.x;
@@ -373,7 +396,7 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DScene 
         const int shadingMode = (int)mat.shadingMetallicRoughness[0];
         float3 position = xyz(pos4);
         float3 normal = xyz(nrm4) * 2.0f - f3s(1.0f);
-        float3 albedo = pow3(unorm3(F.albedo[i]), 2.2f);
+        float3 albedo = lut3(F.lut_pow22, F.albedo[i]);
         float3 material = unorm3(F.material[i]);
         float3 emissive = unorm3(F.emissive[i]);
         const bool background = pos4.w == 0.0f && nrm4.w == 0.0f;
@@ -386,7 +409,6 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DScene 
         const float2 envUV = equirect_uv(N, VKP_PI);
         const float3 irradiance = xyz(tex_nearest(S.textures[S.irr_tex], envUV.x, envUV.y));
 
-        const float tmin = 0.001f, tmax = 1000.0f;
         float3 origin = f3s(0.0f), direction = f3s(0.0f);
         float attenuation = 1.0f;   // declared outside the light loop upstream: stale across lights (App. A #8)
         float3 rayColor = f3s(0.0f);
@@ -444,27 +466,82 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DScene 
                                                                 : irradiance * albedo * metallic);
             }
         }
-        // hybridRaygen.rgen:153-170
-        if (shadingMode != 0) {
+        // hybridRaygen.rgen:172-183: ambient + emissive tail; for background pixels the result is the sky albedo
+        float3 Fa = fresnel_schlick(NdotV, F0);
+        float3 kDa = (1.0f - Fa) * (1.0f - metallic);
+        float3 diffuse = kDa * albedo * irradiance;
+        float3 tail = diffuse + emissive;
+        wants_path = shadingMode != 0 && F.p.max_bounces > 0;
+        if (!WAVEFRONT && wants_path) {
+            // hybridRaygen.rgen:153-170
             for (int depth = 0; depth < F.p.max_bounces; depth++) {
                 float3 ro = origin + direction * 1e-2f;
                 HitRec h; n_refl++;
-                bool hit = trace_ray<false>(S, ro, direction, tmin, tmax, h);
+                bool hit = trace_ray<false>(S, ro, direction, 0.001f, 1000.0f, h);
                 if (hit) shade_hit<false>(S, F.p, ro, direction, h, prd, n_sec); else shade_miss(S, direction, prd);
                 rayColor = rayColor * prd.color;
                 if (!hit || !(prd.scatter > 0.0f)) break;
                 origin = prd.origin; direction = prd.direction;
             }
         }
-        float3 finalColor = rayColor;
-        float3 Fa = fresnel_schlick(NdotV, F0);
-        float3 kDa = (1.0f - Fa) * (1.0f - metallic);
-        float3 diffuse = kDa * albedo * irradiance;
-        finalColor = finalColor + (diffuse + emissive);
-        if (background) finalColor = albedo;
-        float4 outc = make_float4(finalColor.x, finalColor.y, finalColor.z, 1.0f);
-        F.final_f32[i] = outc;
-        F.final_srgb8[i] = post_pixel(outc);
+        if (!WAVEFRONT || !wants_path) {
+            float3 finalColor = rayColor + tail;
+            if (background) finalColor = albedo;
+            float4 outc = make_float4(finalColor.x, finalColor.y, finalColor.z, 1.0f);
+            F.final_f32[i] = outc;
+            F.final_srgb8[i] = post_pixel(F.lut_post, outc);
+        } else {
+            // hybridRaygen.rgen:153-170 becomes the wavefront below: queue the first reflection / refraction ray
+            item.a = make_float4(origin.x, origin.y, origin.z, __uint_as_float((uint32_t)i | (background ? 0x80000000u : 0u)));
+            item.b = make_float4(direction.x, direction.y, direction.z, __uint_as_float(prd.seed));
+            item.c = make_float4(rayColor.x, rayColor.y, rayColor.z, 0.0f);
+            item.d = background ? make_float4(albedo.x, albedo.y, albedo.z, 0.0f) : make_float4(tail.x, tail.y, tail.z, 0.0f);
+        }
+    }
+    if (WAVEFRONT) path_push(F.path_q[0], &F.path_count[0], wants_path, item);
+    else { add_counter(F.counters, 2, n_refl); add_counter(F.counters, 3, n_sec); }
+}
+
+// One bounce of the reflection / refraction chain of hybridRaygen.rgen:153-170 for every queued path: closest-hit
+// traversal, hit shading (hybridHit.rchit, with its per-light secondary shadow rays) or sky (miss.rmiss), throughput
+// update, then either re-queue (compacted with warp ballot + prefix) or finish the pixel.
+__global__ void __launch_bounds__(128) k_bounce(const __grid_constant__ DScene S, const __grid_constant__ DFrame F, int depth)
+{
+    const uint32_t n_in = F.path_count[depth];
+    const PathItem* __restrict__ qin = F.path_q[depth & 1];
+    PathItem* qout = F.path_q[(depth + 1) & 1];
+    unsigned int n_refl = 0, n_sec = 0;
+    const uint32_t n_round = (n_in + 31u) & ~31u;       // whole warps stay in the loop so that the ballots are convergent
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
+        bool again = false;
+        PathItem item;
+        if (k < n_in) {
+            item = qin[k];
+            const uint32_t tag = __float_as_uint(item.a.w);
+            const uint32_t i = tag & 0x7fffffffu;
+            const bool background = (tag & 0x80000000u) != 0;
+            float3 origin = f3(item.a.x, item.a.y, item.a.z), direction = f3(item.b.x, item.b.y, item.b.z);
+            float3 rayColor = f3(item.c.x, item.c.y, item.c.z);
+            Payload prd; prd.seed = __float_as_uint(item.b.w);
+            float3 ro = origin + direction * 1e-2f;
+            HitRec h; n_refl++;
+            bool hit = trace_ray<false>(S, ro, direction, 0.001f, 1000.0f, h);
+            if (hit) shade_hit<false>(S, F.p, ro, direction, h, prd, n_sec); else shade_miss(S, direction, prd);
+            rayColor = rayColor * prd.color;
+            again = hit && (prd.scatter > 0.0f) && (depth + 1 < F.p.max_bounces);
+            if (again) {
+                item.a = make_float4(prd.origin.x, prd.origin.y, prd.origin.z, item.a.w);
+                item.b = make_float4(prd.direction.x, prd.direction.y, prd.direction.z, __uint_as_float(prd.seed));
+                item.c = make_float4(rayColor.x, rayColor.y, rayColor.z, 0.0f);
+            } else {
+                float3 tail = f3(item.d.x, item.d.y, item.d.z);
+                float3 finalColor = background ? tail : rayColor + tail;
+                float4 outc = make_float4(finalColor.x, finalColor.y, finalColor.z, 1.0f);
+                F.final_f32[i] = outc;
+                F.final_srgb8[i] = post_pixel(F.lut_post, outc);
+            }
+        }
+        path_push(qout, &F.path_count[depth + 1], again, item);
     }
     add_counter(F.counters, 2, n_refl);
     add_counter(F.counters, 3, n_sec);
@@ -475,7 +552,7 @@ __global__ void __launch_bounds__(128) k_post(const __grid_constant__ DFrame F)
     const Pixel px = pixel_of_thread(F);
     if (!px.valid) return;
     const size_t i = (size_t)px.y * F.p.width + px.x;
-    F.final_srgb8[i] = post_pixel(F.final_f32[i]);
+    F.final_srgb8[i] = post_pixel(F.lut_post, F.final_f32[i]);
 }
 
 // raygen.rgen:20-81 with NSAMPLES = params.spp; the accumulation target is kept in fp32
@@ -515,7 +592,7 @@ __global__ void __launch_bounds__(128) k_raytrace(const __grid_constant__ DScene
         }
         float4 outc = make_float4(finalColor.x, finalColor.y, finalColor.z, 1.0f);
         F.final_f32[i] = outc;
-        F.final_srgb8[i] = post_pixel(outc);
+        F.final_srgb8[i] = post_pixel(F.lut_post, outc);
     }
     add_counter(F.counters, 2, n_refl);
     add_counter(F.counters, 3, n_sec);
@@ -542,7 +619,8 @@ __global__ void __launch_bounds__(128) k_deferred(const __grid_constant__ DScene
     float3 N = normalize3(normal);
     float3 V = normalize3(f3(F.cam.position[0], F.cam.position[1], F.cam.position[2]) - position);
     float NdotV = fmaxf(dot3(N, V), 0.0f);
-    float3 F0 = mix3(f3s(0.04f), pow3(albedo, 2.2f), metallic);
+    const float3 albedo_lin = lut3(F.lut_pow22, F.albedo[i]);
+    float3 F0 = mix3(f3s(0.04f), albedo_lin, metallic);
     float2 envUV = equirect_uv(N, VKP_PI);
     float3 irradiance = xyz(tex_nearest(S.textures[S.irr_tex], envUV.x, envUV.y));
     float3 color = f3s(1.0f);
@@ -586,7 +664,7 @@ __global__ void __launch_bounds__(128) k_deferred(const __grid_constant__ DScene
                 float3 numerator = (NDF * G) * Fr;
                 float denominator = 4.0f * NdotV * fmaxf(dot3(N, L), 0.0f);
                 float3 specular = numerator / fmaxf(denominator, 0.001f);
-                Lo = Lo + (kD * pow3(albedo, 2.2f) / VKP_PI + specular) * radiance * NdotL;
+                Lo = Lo + (kD * albedo_lin / VKP_PI + specular) * radiance * NdotL;
             }
         }
         if (!background) {
@@ -672,7 +750,25 @@ inline dim3 frame_grid(const FrameLaunch& L)
 cudaError_t launch_gbuffer(const FrameLaunch& L) { k_gbuffer<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
 cudaError_t launch_shadow(const FrameLaunch& L) { k_shadow<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
 cudaError_t launch_denoise(const FrameLaunch& L) { k_denoise<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
-cudaError_t launch_resolve(const FrameLaunch& L) { k_resolve<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
+cudaError_t launch_resolve(const FrameLaunch& L, int* launches)
+{
+    if (!L.frame.p.wavefront) {
+        k_resolve<false><<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaMemsetAsync(L.frame.path_count, 0, sizeof(unsigned int) * (VKP_MAX_BOUNCES + 2), L.stream);
+    if (e != cudaSuccess) return e;
+    k_resolve<true><<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);
+    if (launches) *launches += 1;
+    // the queue lengths live on the device: every bounce is a fixed-size grid-stride launch, no host round trip
+    const int bounces = L.frame.p.max_bounces < VKP_MAX_BOUNCES ? L.frame.p.max_bounces : VKP_MAX_BOUNCES;
+    for (int d = 0; d < bounces; d++) {
+        k_bounce<<<148 * 8, 128, 0, L.stream>>>(L.scene, L.frame, d);
+        if (launches) *launches += 1;
+    }
+    return cudaGetLastError();
+}
 cudaError_t launch_post(const FrameLaunch& L) { k_post<<<frame_grid(L), 128, 0, L.stream>>>(L.frame); return cudaGetLastError(); }
 cudaError_t launch_raytrace(const FrameLaunch& L) { k_raytrace<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
 cudaError_t launch_deferred(const FrameLaunch& L) { k_deferred<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
@@ -714,6 +810,11 @@ cudaError_t launch_tiles_pack(cudaStream_t s, const void* plane, void* dst, int 
 cudaError_t launch_tiles_unpack(cudaStream_t s, void* plane, const void* src, int elem_bytes, int W, int H, int tw, int th, int rank, int world)
 {
     return tiles_copy(s, plane, const_cast<void*>(src), elem_bytes, W, H, tw, th, rank, world, 1);
+}
+cudaError_t launch_build_luts(cudaStream_t s, float* lut_pow22, uint8_t* lut_post)
+{
+    k_build_luts<<<1, 256, 0, s>>>(lut_pow22, lut_post);
+    return cudaGetLastError();
 }
 cudaError_t launch_eval_math(cudaStream_t s, int func, const float* x, const float* y, uint32_t n, float* out)
 {

@@ -44,7 +44,7 @@ struct vkp_ctx {
     DevBuf position, normal, albedo, motion, material, emissive, hit_ids, final_f32, final_srgb8, shadow, denoised[2];
     int denoised_cur = 0;
     int plane_w = 0, plane_h = 0, plane_lights = 0;
-    DevBuf counters, io_tmp, io_tmp2, flush;
+    DevBuf counters, io_tmp, io_tmp2, flush, path_q[2], path_count, luts;
 
     bool profiling = false;
     cudaEvent_t ev[12]{};
@@ -117,6 +117,8 @@ int ensure_planes(vkp_ctx* ctx)
     CK(ctx->final_f32.ensure(px * 16)); CK(ctx->final_srgb8.ensure(px * 4));
     CK(ctx->shadow.ensure(px * L)); CK(ctx->denoised[0].ensure(px * L)); CK(ctx->denoised[1].ensure(px * L));
     CK(ctx->counters.ensure(64));
+    CK(ctx->path_q[0].ensure(px * sizeof(PathItem))); CK(ctx->path_q[1].ensure(px * sizeof(PathItem)));
+    CK(ctx->path_count.ensure(sizeof(unsigned int) * (VKP_MAX_BOUNCES + 2)));
     ctx->plane_w = W; ctx->plane_h = H; ctx->plane_lights = L;
     // defined initial state: history and accumulation start at zero (blur.comp:73 reads uninitialised memory upstream)
     CK(cudaMemsetAsync(ctx->position.p, 0, px * 8, ctx->stream)); CK(cudaMemsetAsync(ctx->normal.p, 0, px * 8, ctx->stream));
@@ -150,6 +152,7 @@ int make_scene(vkp_ctx* ctx, DScene& S)
     if (ctx->materials.empty()) return fail(ctx, VKP_ERR_INVALID, "vkp_set_materials has not been called");
     int r = upload_textures(ctx);
     if (r != VKP_OK) return r;
+    S.lut_pow22 = ctx->luts.as<float>();
     S.tlas_nodes = ctx->tlas.nodes.as<vkp_bvh_node>();
     S.tlas_items = ctx->tlas.items.as<uint32_t>();
     S.instances = ctx->d_instances.as<DInstance>();
@@ -180,6 +183,9 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.denoised = ctx->denoised[ctx->denoised_cur].as<uint8_t>();
     F.denoised_next = ctx->denoised[ctx->denoised_cur ^ 1].as<uint8_t>();
     F.counters = ctx->counters.as<unsigned long long>();
+    F.path_q[0] = ctx->path_q[0].as<PathItem>(); F.path_q[1] = ctx->path_q[1].as<PathItem>();
+    F.path_count = ctx->path_count.as<unsigned int>();
+    F.lut_pow22 = ctx->luts.as<float>(); F.lut_post = ctx->luts.as<uint8_t>() + 1024;
     const int total = F.tiles_x * F.tiles_y;
     L.n_own_tiles = total > F.rank ? (total - F.rank + F.world - 1) / F.world : 0;
     L.stream = ctx->stream;
@@ -211,7 +217,7 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
         L.frame.denoised = ctx->denoised[ctx->denoised_cur].as<uint8_t>();
         L.frame.denoised_next = ctx->denoised[ctx->denoised_cur ^ 1].as<uint8_t>();
         break;
-    case VKP_STAGE_RESOLVE: CK(launch_resolve(L)); break;
+    case VKP_STAGE_RESOLVE: { int n = 0; CK(launch_resolve(L, &n)); ctx->last_launches += (uint32_t)n - 1u; break; }
     case VKP_STAGE_POST: CK(launch_post(L)); break;
     case VKP_STAGE_RAYTRACE: CK(launch_raytrace(L)); break;
     case VKP_STAGE_DEFERRED: CK(launch_deferred(L)); break;
@@ -252,6 +258,13 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
     ctx->stream = ctx->own_stream;
     cudaEventCreate(&ctx->timer0); cudaEventCreate(&ctx->timer1);
+    // decode / gamma tables, computed on the device with the contract's own vkp_powf so they are bit-identical to the call
+    if ((e = ctx->luts.ensure(2048)) != cudaSuccess || (e = launch_build_luts(ctx->stream, ctx->luts.as<float>(), ctx->luts.as<uint8_t>() + 1024)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+        std::string msg = std::string("LUT kernel launch failed (is this an sm_100 device?): ") + cudaGetErrorString(e);
+        vkp_destroy(ctx);
+        return fail(nullptr, VKP_ERR_CUDA, msg);
+    }
     *out = ctx;
     return VKP_OK;
 }
@@ -267,7 +280,7 @@ void vkp_destroy(vkp_ctx* ctx)
     ctx->tlas.release(); ctx->scratch.release(); ctx->tlas_scratch.release();
     DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_lights, &ctx->d_instances, &ctx->d_textures, &ctx->position, &ctx->normal, &ctx->albedo, &ctx->motion,
                       &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
-                      &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush};
+                      &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->timer0) cudaEventDestroy(ctx->timer0);
@@ -435,6 +448,7 @@ int vkp_set_params(vkp_ctx* ctx, const vkp_params* p)
     if (!ctx || !p) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: NULL");
     if (p->width <= 0 || p->height <= 0 || p->width > 16384 || p->height > 16384) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: bad image size");
     if (p->mode < 0 || p->mode > 2) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: bad mode");
+    if (p->max_bounces > VKP_MAX_BOUNCES) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: max_bounces > 64");
     if (p->spp < 1 || p->shadow_samples < 1 || p->max_bounces < 0) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: spp / shadow_samples must be >= 1");
     ctx->params = *p; ctx->have_params = true;
     return VKP_OK;

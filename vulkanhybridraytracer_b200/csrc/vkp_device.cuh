@@ -106,6 +106,7 @@ struct DInstance {
 };
 
 struct DScene {
+    const float* lut_pow22;          // same table as DFrame::lut_pow22 (hit / miss shading has only the scene)
     const vkp_bvh_node* tlas_nodes;
     const uint32_t* tlas_items;      // leaf-ordered instance ids
     const DInstance* instances;
@@ -115,6 +116,15 @@ struct DScene {
     int n_instances, n_materials, n_lights, n_textures;
     int sky_tex, irr_tex;
 };
+
+// one in-flight reflection / refraction path of the wavefront (64 bytes)
+struct PathItem {
+    float4 a;   // origin.xyz, pixel index | background flag (bit 31)
+    float4 b;   // direction.xyz, RNG seed bits
+    float4 c;   // throughput (rayColor)
+    float4 d;   // ambient + emissive tail (or the sky albedo for background pixels)
+};
+#define VKP_MAX_BOUNCES 64
 
 struct DFrame {
     vkp_camera cam;
@@ -135,6 +145,10 @@ struct DFrame {
     uint8_t* denoised;    // n_lights planes (history, updated in place through denoised_next)
     uint8_t* denoised_next;
     unsigned long long* counters;   // [4] rays by type
+    const float* lut_pow22;         // [256] vkp_powf(k/255, 2.2): decode of 8-bit albedo / sky texels (bit-identical to the call)
+    const uint8_t* lut_post;        // [256] postFragment.frag on an 8-bit input: unorm8(pow(max(k/255, 0.001), 1/2.2))
+    PathItem* path_q[2];            // ping-pong path queues of the reflection wavefront
+    unsigned int* path_count;       // [VKP_MAX_BOUNCES + 2] queue length per bounce
 };
 
 // ---- texture / env -----------------------------------------------------------------------------------------
@@ -147,6 +161,14 @@ VKP_D float4 tex_nearest(const DTexture& T, float u, float v)
     iy %= T.h; if (iy < 0) iy += T.h;
     uchar4 t = __ldg(&T.texels[(size_t)iy * T.w + ix]);
     return make_float4((float)t.x / 255.0f, (float)t.y / 255.0f, (float)t.z / 255.0f, (float)t.w / 255.0f);
+}
+VKP_D uchar4 tex_nearest_raw(const DTexture& T, float u, float v)
+{
+    float fx = u * (float)T.w, fy = v * (float)T.h;
+    int ix = (fx == fx) ? (int)floorf(fx) : 0, iy = (fy == fy) ? (int)floorf(fy) : 0;
+    ix %= T.w; if (ix < 0) ix += T.w;
+    iy %= T.h; if (iy < 0) iy += T.h;
+    return __ldg(&T.texels[(size_t)iy * T.w + ix]);
 }
 VKP_D float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
 
@@ -221,6 +243,7 @@ VKP_D uchar4 pack_unorm4(float x, float y, float z, float w)
 {
     return make_uchar4(vkp_unorm8(x), vkp_unorm8(y), vkp_unorm8(z), vkp_unorm8(w));
 }
+VKP_D float3 lut3(const float* __restrict__ lut, uchar4 c) { return f3(__ldg(&lut[c.x]), __ldg(&lut[c.y]), __ldg(&lut[c.z])); }
 VKP_D float3 unorm3(uchar4 c) { return f3((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f); }
 
 // camera ray of raygen.rgen:32-40

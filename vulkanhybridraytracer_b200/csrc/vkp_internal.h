@@ -71,12 +71,13 @@ struct FrameLaunch {
 cudaError_t launch_gbuffer(const FrameLaunch& L);
 cudaError_t launch_shadow(const FrameLaunch& L);
 cudaError_t launch_denoise(const FrameLaunch& L);
-cudaError_t launch_resolve(const FrameLaunch& L);
+cudaError_t launch_resolve(const FrameLaunch& L, int* launches);
 cudaError_t launch_post(const FrameLaunch& L);
 cudaError_t launch_raytrace(const FrameLaunch& L);
 cudaError_t launch_deferred(const FrameLaunch& L);
 cudaError_t launch_trace_rays(cudaStream_t s, const DScene& scene, const vkp_ray* rays, uint32_t n, int any_hit, vkp_hit* hits);
 cudaError_t launch_tiles_pack(cudaStream_t s, const void* plane, void* dst, int elem_bytes, int W, int H, int tile_w, int tile_h, int rank, int world);
 cudaError_t launch_tiles_unpack(cudaStream_t s, void* plane, const void* src, int elem_bytes, int W, int H, int tile_w, int tile_h, int rank, int world);
+cudaError_t launch_build_luts(cudaStream_t s, float* lut_pow22, uint8_t* lut_post);
 cudaError_t launch_eval_math(cudaStream_t s, int func, const float* x, const float* y, uint32_t n, float* out);
 cudaError_t launch_l2_flush(cudaStream_t s, void* buf, size_t bytes);
