@@ -139,6 +139,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
+    ap.add_argument("--chain", type=int, default=2, choices=[0, 1, 2],
+                    help="reflection-chain schedule: 0 inline in k_resolve, 1 wavefront queues, 2 k_chain overlapped with the shadow pass (default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -187,7 +189,7 @@ def main():
     L = len(scene.lights)
 
     def params(frame):
-        return vk.make_params(W, H, mode=mode, spp=spp, shadow_samples=samples, faithful_rng=faithful, frame=frame)
+        return vk.make_params(W, H, mode=mode, spp=spp, shadow_samples=samples, faithful_rng=faithful, frame=frame, wavefront=args.chain)
 
     # composite buffers (N > 1): packed sRGB8 tiles of every rank -> rank 0
     sizes = [tiling.packed_bytes(W, H, r, world, 4, TW, TH) for r in range(world)]
@@ -262,6 +264,7 @@ def main():
     if world == 1 and mode == 2 and scene_idx == 0:
         ctx.close()
         eng = vk.HostEngine(scene_idx, W, H, dev)
+        eng.set("chain", args.chain)
         pinned = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
         for _ in range(args.warmup):
             eng.frames(1)
@@ -352,6 +355,7 @@ def main():
                                       "secondary_shadow": int(rays_all[3] // args.steps), "primary_not_counted": int(rays_all[0] // args.steps)},
                    "mrays_s_incl_primary": float(rays_all.sum()) / args.steps / (ms_per_step * 1e-3) / 1e6,
                    "nominal_2P_mrays_s": 2 * P / (ms_per_step * 1e-3) / 1e6,
+                   "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain on a second stream overlapping k_shadow + k_denoise"}[args.chain],
                    "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
                    "parallelism": f"tiles {TW}x{TH} interleaved over {world} GPU(s), replicated BVH, NCCL gather of sRGB8 tiles" if world > 1 else "1 GPU",
                    "timing": "CUDA events on the context stream around each frame, summed over K frames, max over ranks"},

@@ -61,6 +61,8 @@ VKP_API int vkp_set_instances(vkp_ctx* ctx, const vkp_instance* instances, int n
 /* Renderer::create_bottom_acceleration_structure + buildBlas (renderer.cpp:1643-1753):
  * one BLAS per distinct (mesh, first_index, index_count) referenced by the instances */
 VKP_API int vkp_build_blas(vkp_ctx* ctx);
+/* BLAS hierarchy builder for subsequent vkp_build_blas calls: 0 = Morton LBVH (Karras radix tree), 1 = PLOC (default) */
+VKP_API int vkp_set_builder(vkp_ctx* ctx, int builder);
 /* Renderer::buildTlas(instances, flags, update) (renderer.cpp:1757-1865); update=1 == MODE_UPDATE refit */
 VKP_API int vkp_build_tlas(vkp_ctx* ctx, int update);
 
@@ -92,6 +94,9 @@ VKP_API int vkp_set_profiling(vkp_ctx* ctx, int on);            /* per-stage CUD
 /* traceRayEXT made explicit: trace n rays against the current TLAS (host buffers). any_hit != 0
  * == gl_RayFlagsTerminateOnFirstHitEXT|SkipClosestHitShaderEXT: only hit.t >= 0 / < 0 is defined */
 VKP_API int vkp_trace_rays(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, vkp_hit* hits);
+
+/* instrumented traversal: per ray {node pairs fetched, triangles tested} (2 x uint32 per ray), for build-quality studies */
+VKP_API int vkp_trace_stats(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, uint32_t* steps_and_tris);
 
 /* BVH introspection (tests): copy out the nodes and the leaf-ordered primitive ids of one BLAS
  * (index = order of first use in vkp_set_instances) or of the TLAS (blas_index = -1) */

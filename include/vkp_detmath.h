@@ -214,6 +214,10 @@ VKP_HD float vkp_from_unorm8(uint8_t b) { return (float)b / 255.0f; }
 /* float -> IEEE binary16 bits, round-to-nearest-even (matches __float2half_rn) */
 VKP_HD uint16_t vkp_f32_to_f16(float f)
 {
+#if defined(__CUDA_ARCH__)
+    /* cvt.rn.f16.f32: the same round-to-nearest-even conversion in one instruction (checked bit for bit by the GPU tests) */
+    { unsigned short hw; asm("{ .reg .b16 t; cvt.rn.f16.f32 t, %1; mov.b16 %0, t; }" : "=h"(hw) : "f"(f)); return (uint16_t)hw; }
+#endif
     uint32_t x = vkp_f2u(f);
     uint32_t sign = (x >> 16) & 0x8000u;
     uint32_t ax = x & 0x7fffffffu;
@@ -242,6 +246,9 @@ VKP_HD uint16_t vkp_f32_to_f16(float f)
 
 VKP_HD float vkp_f16_to_f32(uint16_t h)
 {
+#if defined(__CUDA_ARCH__)
+    { float r; asm("{ .reg .b16 t; mov.b16 t, %1; cvt.f32.f16 %0, t; }" : "=f"(r) : "h"((unsigned short)h)); return r; }
+#endif
     uint32_t sign = ((uint32_t)h & 0x8000u) << 16;
     uint32_t e = (h >> 10) & 0x1fu;
     uint32_t m = h & 0x3ffu;

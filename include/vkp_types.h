@@ -80,7 +80,8 @@ typedef struct vkp_params {
     int32_t denoise_cover_remainder; /* 0: dispatch W/16 x H/16 groups exactly (renderer.cpp:2672) */
     int32_t debug_target;            /* deferred.frag debug.target 0..6                            */
     int32_t wavefront;               /* reflection chain (hybridRaygen.rgen:153-170): 0 = inline in the resolve kernel,
-                                        1 = wavefront path queues with ray compaction, one launch per bounce        */
+                                        1 = wavefront path queues with ray compaction, one launch per bounce,
+                                        2 = compacted chain kernel on a second stream, overlapping shadow + denoise  */
     int32_t reserved[4];
 } vkp_params;
 

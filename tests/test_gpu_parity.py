@@ -94,7 +94,7 @@ def test_trace_edge_cases(gpu_ctx, small_scene, small_oracle):
     assert got["instance"][0] == -1 and got["instance"][1] == 0 and abs(got["t"][1] - 5.0) < 1e-5 and got["instance"][2] == -1 and got["instance"][3] == -1
 
 
-@pytest.mark.parametrize("w,h,wavefront", [(320, 184, 0), (250, 130, 0), (320, 184, 1), (250, 130, 1)])
+@pytest.mark.parametrize("w,h,wavefront", [(320, 184, 0), (250, 130, 0), (320, 184, 1), (250, 130, 1), (320, 184, 2), (250, 130, 2)])
 def test_hybrid_frames_stage_by_stage(gpu_ctx, small_scene, small_oracle, w, h, wavefront):
     ctx, sc, o = gpu_ctx, small_scene, small_oracle
     cam = sc.camera(w, h)
@@ -118,7 +118,7 @@ def test_hybrid_frames_stage_by_stage(gpu_ctx, small_scene, small_oracle, w, h, 
         assert np.array_equal(final.view(np.uint32), ref["final"].view(np.uint32))          # stronger than the bar: same bits
         assert np.array_equal(ctx.readback(PLANE.FINAL_SRGB8), o.post(p, ref["final"]))
         assert [c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow] == list(o.counters.rays)
-        assert c.kernel_launches == (4 + 8 if wavefront else 4)     # + one k_bounce per bounce (max_bounces = 8) in wavefront mode
+        assert c.kernel_launches == {0: 4, 1: 4 + 8, 2: 5}[wavefront]     # 1: + one k_bounce per bounce (8); 2: + k_chain
 
 
 def test_stage_isolation(gpu_ctx, small_scene, small_oracle):

@@ -42,8 +42,10 @@ def walk_bvh(nodes, n_prims, leaf_max):
     return seen, max_depth
 
 
-def test_blas_invariants(gpu_ctx, small_scene):
+@pytest.mark.parametrize("builder", [0, 1])          # 0 = Karras LBVH, 1 = PLOC
+def test_blas_invariants(small_scene, small_oracle, builder):
     sc = small_scene
+    gpu_ctx = vk.Context(0); gpu_ctx.set_builder(builder); gpu_ctx.upload_scene(sc)
     keys = []
     for inst in sc.instances:
         k = (int(inst["mesh_id"]), int(inst["first_index"]), int(inst["index_count"]))
@@ -65,6 +67,14 @@ def test_blas_invariants(gpu_ctx, small_scene):
                 f, c = (ref & 0x7FFFFFFF) >> 3, (ref & 7) + 1
                 t = tri[prims[f:f + c]].reshape(-1, 3)
                 assert (t.min(0) >= n["bmin"]).all() and (t.max(0) <= n["bmax"]).all()
+    # both builders answer every query identically (results do not depend on the tree)
+    rays = random_rays(sc, 8000, seed=21)
+    ref = small_oracle.trace_rays(rays, brute_force=True)
+    got = gpu_ctx.trace_rays(rays)
+    assert np.array_equal(got["instance"], ref["instance"]) and np.array_equal(got["primitive"], ref["primitive"])
+    assert np.array_equal(got["t"].view(np.uint32), ref["t"].view(np.uint32))
+    assert np.array_equal(gpu_ctx.trace_rays(rays, any_hit=True)["t"] >= 0, ref["t"] >= 0)
+    gpu_ctx.close()
 
 
 def test_tlas_build_refit_and_moving_instance(small_scene, small_oracle):

@@ -55,7 +55,7 @@ def load_vkp():
     global _vkp
     if _vkp is not None:
         return _vkp
-    path = os.path.join(lib_dir(), "libvkp.so")
+    path = os.environ.get("VKP_LIB") or os.path.join(lib_dir(), "libvkp.so")      # VKP_LIB: tuning builds (scripts/variants.sh)
     if not os.path.exists(path):
         raise VkpError(f"{path} is missing: run `make` (or __graft_entry__.build()); there is no fallback path")
     L = C.CDLL(path, mode=C.RTLD_GLOBAL)
@@ -73,6 +73,7 @@ def load_vkp():
         "vkp_set_lights": (i, [vp, vp, i]),
         "vkp_set_instances": (i, [vp, vp, i]),
         "vkp_build_blas": (i, [vp]),
+        "vkp_set_builder": (i, [vp, i]),
         "vkp_build_tlas": (i, [vp, i]),
         "vkp_set_camera": (i, [vp, P(T.Camera)]),
         "vkp_set_params": (i, [vp, P(T.Params)]),
@@ -98,6 +99,7 @@ def load_vkp():
         "vkp_tiles_unpack": (i, [vp, i, i, i, vp, sz]),
         "vkp_set_stream": (i, [vp, vp]),
         "vkp_eval_math": (i, [vp, i, vp, vp, u32, vp]),
+        "vkp_trace_stats": (i, [vp, vp, u32, i, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -303,6 +305,9 @@ class Context:
         inst = np.ascontiguousarray(inst, dtype=T.instance_dtype)
         self._ck(self.L.vkp_set_instances(self.h, inst.ctypes.data if len(inst) else None, len(inst)), "vkp_set_instances")
 
+    def set_builder(self, builder):
+        self._ck(self.L.vkp_set_builder(self.h, builder), "vkp_set_builder")
+
     def build_blas(self):
         self._ck(self.L.vkp_build_blas(self.h), "vkp_build_blas")
 
@@ -380,6 +385,12 @@ class Context:
         self._ck(self.L.vkp_trace_rays(self.h, rays.ctypes.data if len(rays) else None, len(rays), 1 if any_hit else 0,
                                        hits.ctypes.data if len(rays) else None), "vkp_trace_rays")
         return hits
+
+    def trace_stats(self, rays, any_hit=False):
+        rays = np.ascontiguousarray(rays, dtype=T.ray_dtype)
+        out = np.zeros((len(rays), 2), dtype=np.uint32)
+        self._ck(self.L.vkp_trace_stats(self.h, rays.ctypes.data, len(rays), 1 if any_hit else 0, out.ctypes.data), "vkp_trace_stats")
+        return out
 
     def bvh(self, blas_index):
         nn, npr = C.c_uint32(), C.c_uint32()

@@ -13,6 +13,17 @@
 #include "vkp_internal.h"
 #include "vkp_bvh.cuh"
 
+// occupancy knobs (min resident CTAs per SM -> register cap), tuned by measurement
+#ifndef VKP_LB_GBUFFER
+#define VKP_LB_GBUFFER 8
+#endif
+#ifndef VKP_LB_SHADOW
+#define VKP_LB_SHADOW 6
+#endif
+#ifndef VKP_LB_RESOLVE
+#define VKP_LB_RESOLVE 4
+#endif
+
 namespace {
 
 struct Pixel { int x, y; bool valid; };
@@ -214,7 +225,7 @@ __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, flo
 }
 
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_gbuffer(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+__global__ void __launch_bounds__(128, VKP_LB_GBUFFER) k_gbuffer(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     const Pixel px = pixel_of_thread(F);
     unsigned int nrays = 0;
@@ -261,63 +272,87 @@ __global__ void __launch_bounds__(128) k_gbuffer(const __grid_constant__ DScene 
             uchar4 a = pack_unorm4(color.x, color.y, color.z, 1.0f); F.albedo[i] = a;
             F.material[i] = pack_unorm4(material.x, material.y, material.z, 1.0f);
             F.emissive[i] = pack_unorm4(emissive.x, emissive.y, emissive.z, 1.0f);
-            float4 wp = make_float4(worldPos.x, worldPos.y, worldPos.z, 1.0f);
-            float4 clip = xform_vec4(F.cam.proj, xform_vec4(F.cam.view, wp));
-            float4 clipPrev = xform_vec4(F.cam.prev_proj, xform_vec4(F.cam.prev_view, wp));
-            float mx = clip.x / clip.w - clipPrev.x / clipPrev.w;
-            float my = clip.y / clip.w - clipPrev.y / clipPrev.w;
-            F.motion[i] = (uint32_t)vkp_f32_to_f16(mx * 0.5f + 0.5f) | ((uint32_t)vkp_f32_to_f16(my * 0.5f + 0.5f) << 16);
+            if (F.static_camera) {
+                // identical matrices give ndc - ndcPrev == 0 exactly (a hit in front of the camera has clip.w != 0): 0.5 in both halves
+                F.motion[i] = 0x38003800u;
+            } else {
+                float4 wp = make_float4(worldPos.x, worldPos.y, worldPos.z, 1.0f);
+                float4 clip = xform_vec4(F.cam.proj, xform_vec4(F.cam.view, wp));
+                float4 clipPrev = xform_vec4(F.cam.prev_proj, xform_vec4(F.cam.prev_view, wp));
+                float mx = clip.x / clip.w - clipPrev.x / clipPrev.w;
+                float my = clip.y / clip.w - clipPrev.y / clipPrev.w;
+                F.motion[i] = (uint32_t)vkp_f32_to_f16(mx * 0.5f + 0.5f) | ((uint32_t)vkp_f32_to_f16(my * 0.5f + 0.5f) << 16);
+            }
         }
     }
     add_counter(F.counters, 0, nrays);
 }
 
-// shadowRaygen.rgen:28-117
-__global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+// per-light pieces of shadowRaygen.rgen:55-61 that decide whether rays are traced (and hence how far the RNG advances)
+struct LightGeom { float3 L; float dist, maxd, NdotL; };
+__device__ __forceinline__ LightGeom light_geom(const vkp_light& light, float3 position, float3 N)
+{
+    LightGeom g;
+    const float3 lpos = f3(light.position[0], light.position[1], light.position[2]);
+    const bool isDirectional = light.position[3] < 0.0f;
+    float3 L = isDirectional ? lpos : (lpos - position);
+    g.maxd = light.position[3];
+    g.dist = length3(L);
+    g.L = normalize3(L);
+    g.NdotL = clamp01(dot3(N, g.L));
+    return g;
+}
+
+// shadowRaygen.rgen:28-117.  One thread per (pixel, light) -- blockIdx.y is the light -- so the longest any-hit
+// traversal of a pixel is not serialised behind the other lights' (the kernel's duration is set by its slowest
+// thread: DESIGN.md section 4).  With the non-faithful RNG the seed a light starts from is replayed from the
+// cheap per-light conditions of the lights before it.
+__global__ void __launch_bounds__(128, VKP_LB_SHADOW) k_shadow(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     const Pixel px = pixel_of_thread(F);
+    const int l = blockIdx.y;
     unsigned int nrays = 0;
     if (px.valid) {
         const int W = F.p.width, H = F.p.height;
         const size_t i = (size_t)px.y * W + px.x;
         const size_t plane = (size_t)W * H;
-        uint32_t seed = tea16((uint32_t)px.y * (uint32_t)W + (uint32_t)px.x, (uint32_t)F.p.frame);
         float4 pos4 = unpack_half4(F.position[i]);
         float4 nrm4 = unpack_half4(F.normal[i]);
         float3 position = xyz(pos4);
         float3 normal = xyz(nrm4) * 2.0f - f3s(1.0f);
         int mode = (int)material_by_float_index(S, pos4.w).shadingMetallicRoughness[0];
-        float3 N = normalize3(normal);
         if (mode == 4) {
-            for (int l = 0; l < S.n_lights; l++) F.shadow[l * plane + i] = 255;
+            F.shadow[l * plane + i] = 255;
         } else {
-            for (int l = 0; l < S.n_lights; l++) {
-                const vkp_light light = S.lights[l];
-                const float3 lpos = f3(light.position[0], light.position[1], light.position[2]);
-                const bool isDirectional = light.position[3] < 0.0f;
-                float3 L = isDirectional ? lpos : (lpos - position);
-                const float light_max_distance = light.position[3];
-                const float light_distance = length3(L);
-                L = normalize3(L);
-                const float NdotL = clamp01(dot3(N, L));
-                float shadowFactor = 0.0f;
-                const int shadowSamples = F.p.shadow_samples;
-                if (NdotL > 0.0f) {
-                    for (int s = 0; s < shadowSamples; s++) {
-                        bool shadowed;
-                        if (light_distance < light_max_distance) {
-                            const float3 dir = sample_disk(light, position, L, seed, F.p.faithful_rng == 0);
-                            HitRec h; nrays++;
-                            shadowed = trace_ray<true>(S, position + dir * 1e-1f, dir, 0.001f, light_distance + 1.0f, h);
-                        } else {
-                            shadowed = false;
-                        }
-                        if (!shadowed) shadowFactor += 1.0f;
-                    }
-                    shadowFactor /= (float)shadowSamples;
+            float3 N = normalize3(normal);
+            const int shadowSamples = F.p.shadow_samples;
+            const bool advance = F.p.faithful_rng == 0;
+            uint32_t seed = tea16((uint32_t)px.y * (uint32_t)W + (uint32_t)px.x, (uint32_t)F.p.frame);
+            if (advance) {
+                for (int k = 0; k < l; k++) {
+                    const LightGeom g = light_geom(S.lights[k], position, N);
+                    if (g.NdotL > 0.0f && g.dist < g.maxd)
+                        for (int r = 0; r < 2 * shadowSamples; r++) seed = 1664525u * seed + 1013904223u;   // two rnd() per sampleDisk
                 }
-                F.shadow[l * plane + i] = vkp_unorm8(shadowFactor);
             }
+            const vkp_light light = S.lights[l];
+            const LightGeom g = light_geom(light, position, N);
+            float shadowFactor = 0.0f;
+            if (g.NdotL > 0.0f) {
+                for (int s = 0; s < shadowSamples; s++) {
+                    bool shadowed;
+                    if (g.dist < g.maxd) {
+                        const float3 dir = sample_disk(light, position, g.L, seed, advance);
+                        HitRec h; nrays++;
+                        shadowed = trace_ray<true>(S, position + dir * 1e-1f, dir, 0.001f, g.dist + 1.0f, h);
+                    } else {
+                        shadowed = false;
+                    }
+                    if (!shadowed) shadowFactor += 1.0f;
+                }
+                shadowFactor /= (float)shadowSamples;
+            }
+            F.shadow[l * plane + i] = vkp_unorm8(shadowFactor);
         }
     }
     add_counter(F.counters, 1, nrays);
@@ -375,10 +410,85 @@ __global__ void __launch_bounds__(128) k_denoise(const __grid_constant__ DScene 
 }
 
 // hybridRaygen.rgen:27-186
-// WAVEFRONT == false: the bounce chain runs inline in this kernel (its latency hides behind the other pixels' shading);
-// WAVEFRONT == true: mirror / glass pixels are compacted into a path queue consumed by k_bounce, one launch per bounce.
-template <bool WAVEFRONT>
-__global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+// first reflection / refraction ray of a mirror / glass pixel (hybridRaygen.rgen:123-148): depends on the G-buffer only
+__device__ __forceinline__ void first_bounce(int shadingMode, const vkp_material& mat, float3 position, float3 N, float3 V, float3& origin, float3& direction)
+{
+    if (shadingMode == 3) {
+        direction = reflect3(normalize3(-V), N);
+        origin = position;
+    }
+    if (shadingMode == 4) {
+        const float ior = mat.diffuse[3];
+        origin = position;
+        const float cosAlpha = dot3(N, V);
+        const float3 Iv = -V;
+        const float NdotI = dot3(N, Iv);
+        const float3 refrNormal = NdotI > 0.0f ? -N : N;
+        const float refrEta = NdotI > 0.0f ? 1.0f / ior : ior;
+        const float radicand = 1.0f + vkp_powf(refrEta, 2.0f) * (cosAlpha * cosAlpha - 1.0f);
+        direction = radicand < 0.0f ? reflect3(Iv, N) : refract3(Iv, refrNormal, refrEta);
+    }
+}
+
+// The bounce chain of hybridRaygen.rgen:153-170 depends only on the G-buffer, not on the shadow / denoise passes, so in
+// chain mode 2 it runs in this kernel on a second, high-priority stream CONCURRENTLY with k_shadow + k_denoise; the
+// per-bounce colours are stored (<= 8 per path) and k_resolve<2> multiplies them into rayColor in the reference's order.
+__global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_chain(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    const Pixel px = pixel_of_thread(F);
+    unsigned int n_refl = 0, n_sec = 0;
+    bool path = false;
+    size_t i = 0;
+    float4 pos4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (px.valid) {
+        i = (size_t)px.y * F.p.width + px.x;
+        pos4 = unpack_half4(F.position[i]);
+        path = (int)material_by_float_index(S, pos4.w).shadingMetallicRoughness[0] != 0 && F.p.max_bounces > 0;
+    }
+    // compaction: one atomic per warp, slots by ballot + popc prefix
+    const unsigned mask = __ballot_sync(0xffffffffu, path);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&F.path_count[0], (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (path) {
+        const unsigned slot = base + __popc(mask & ((1u << lane) - 1u));
+        F.chain_slot[i] = (int)slot;
+        float4* rec = F.chain_buf + (size_t)slot * VKP_CHAIN_MAX;
+        const vkp_material& mat = material_by_float_index(S, pos4.w);
+        const int shadingMode = (int)mat.shadingMetallicRoughness[0];
+        float4 nrm4 = unpack_half4(F.normal[i]);
+        const float3 position = xyz(pos4);
+        const float3 N = normalize3(xyz(nrm4) * 2.0f - f3s(1.0f));
+        const float3 camPosition = f3(F.cam.inv_view[12], F.cam.inv_view[13], F.cam.inv_view[14]);
+        const float3 V = normalize3(camPosition - position);
+        float3 origin = f3s(0.0f), direction = f3s(0.0f);
+        if (S.n_lights > 0) first_bounce(shadingMode, mat, position, N, V, origin, direction);   // upstream sets them inside the light loop
+        Payload prd;
+        prd.seed = tea16((uint32_t)px.y * (uint32_t)F.p.width + (uint32_t)px.x, (uint32_t)F.p.frame);
+        int n = 0;
+        for (int depth = 0; depth < F.p.max_bounces; depth++) {
+            float3 ro = origin + direction * 1e-2f;
+            HitRec h; n_refl++;
+            bool hit = trace_ray<false>(S, ro, direction, 0.001f, 1000.0f, h);
+            if (hit) shade_hit<false>(S, F.p, ro, direction, h, prd, n_sec); else shade_miss(S, direction, prd);
+            rec[n] = make_float4(prd.color.x, prd.color.y, prd.color.z, 0.0f);
+            n++;
+            if (!hit || !(prd.scatter > 0.0f)) break;
+            origin = prd.origin; direction = prd.direction;
+        }
+        F.chain_len[slot] = n;
+    }
+    add_counter(F.counters, 2, n_refl);
+    add_counter(F.counters, 3, n_sec);
+}
+
+// CHAIN == 0: the bounce chain runs inline in this kernel (its latency hides behind the other pixels' shading);
+// CHAIN == 1: mirror / glass pixels are compacted into a path queue consumed by k_bounce, one launch per bounce;
+// CHAIN == 2: the chain was traced by k_chain concurrently with the shadow pass; multiply its stored colours in.
+template <int CHAIN>
+__global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_resolve(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     const Pixel px = pixel_of_thread(F);
     bool wants_path = false;
@@ -472,7 +582,13 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DScene 
         float3 diffuse = kDa * albedo * irradiance;
         float3 tail = diffuse + emissive;
         wants_path = shadingMode != 0 && F.p.max_bounces > 0;
-        if (!WAVEFRONT && wants_path) {
+        if (CHAIN == 2 && wants_path) {
+            const int slot = F.chain_slot[i];
+            const float4* rec = F.chain_buf + (size_t)slot * VKP_CHAIN_MAX;
+            const int n = F.chain_len[slot];
+            for (int k = 0; k < n; k++) { float4 c = rec[k]; rayColor = rayColor * f3(c.x, c.y, c.z); }
+        }
+        if (CHAIN == 0 && wants_path) {
             // hybridRaygen.rgen:153-170
             for (int depth = 0; depth < F.p.max_bounces; depth++) {
                 float3 ro = origin + direction * 1e-2f;
@@ -484,7 +600,7 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DScene 
                 origin = prd.origin; direction = prd.direction;
             }
         }
-        if (!WAVEFRONT || !wants_path) {
+        if (CHAIN != 1 || !wants_path) {
             float3 finalColor = rayColor + tail;
             if (background) finalColor = albedo;
             float4 outc = make_float4(finalColor.x, finalColor.y, finalColor.z, 1.0f);
@@ -498,8 +614,8 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DScene 
             item.d = background ? make_float4(albedo.x, albedo.y, albedo.z, 0.0f) : make_float4(tail.x, tail.y, tail.z, 0.0f);
         }
     }
-    if (WAVEFRONT) path_push(F.path_q[0], &F.path_count[0], wants_path, item);
-    else { add_counter(F.counters, 2, n_refl); add_counter(F.counters, 3, n_sec); }
+    if (CHAIN == 1) path_push(F.path_q[0], &F.path_count[0], wants_path, item);
+    if (CHAIN == 0) { add_counter(F.counters, 2, n_refl); add_counter(F.counters, 3, n_sec); }
 }
 
 // One bounce of the reflection / refraction chain of hybridRaygen.rgen:153-170 for every queued path: closest-hit
@@ -695,6 +811,19 @@ __global__ void __launch_bounds__(128) k_trace_list(const __grid_constant__ DSce
     hits[i] = o;
 }
 
+// instrumented traversal (vkp_trace_stats): node-pair fetches and triangle tests per ray, for build-quality studies
+template <bool ANY>
+__global__ void __launch_bounds__(128) k_trace_stats(const __grid_constant__ DScene S, const vkp_ray* __restrict__ rays, uint32_t n, uint32_t* __restrict__ stats)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vkp_ray r = rays[i];
+    HitRec h;
+    uint32_t st[2] = {0u, 0u};
+    trace_ray<ANY, true>(S, f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax, h, st);
+    stats[2 * (size_t)i] = st[0]; stats[2 * (size_t)i + 1] = st[1];
+}
+
 // ---- multi-GPU tile pack / unpack (SURVEY 8e composite) -------------------------------------------------------
 template <typename E>
 __global__ void k_tiles_copy(E* __restrict__ plane, E* __restrict__ packed, int W, int H, int tile_w, int tile_h, int tiles_x, int rank, int world, int to_plane)
@@ -748,18 +877,29 @@ inline dim3 frame_grid(const FrameLaunch& L)
 } // namespace
 
 cudaError_t launch_gbuffer(const FrameLaunch& L) { k_gbuffer<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
-cudaError_t launch_shadow(const FrameLaunch& L) { k_shadow<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
+cudaError_t launch_shadow(const FrameLaunch& L)
+{
+    if (L.scene.n_lights == 0) return cudaSuccess;
+    dim3 g = frame_grid(L); g.y = (unsigned)L.scene.n_lights;
+    k_shadow<<<g, 128, 0, L.stream>>>(L.scene, L.frame);
+    return cudaGetLastError();
+}
 cudaError_t launch_denoise(const FrameLaunch& L) { k_denoise<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
 cudaError_t launch_resolve(const FrameLaunch& L, int* launches)
 {
-    if (!L.frame.p.wavefront) {
-        k_resolve<false><<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);
+    if (L.frame.p.wavefront == 0 || (L.frame.p.wavefront == 2 && L.frame.p.max_bounces > VKP_CHAIN_MAX)) {
+        k_resolve<0><<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
+    if (L.frame.p.wavefront == 2) {
+        k_resolve<2><<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);     // launch_chain has run (and been waited for) before
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
     cudaError_t e = cudaMemsetAsync(L.frame.path_count, 0, sizeof(unsigned int) * (VKP_MAX_BOUNCES + 2), L.stream);
     if (e != cudaSuccess) return e;
-    k_resolve<true><<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);
+    k_resolve<1><<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);
     if (launches) *launches += 1;
     // the queue lengths live on the device: every bounce is a fixed-size grid-stride launch, no host round trip
     const int bounces = L.frame.p.max_bounces < VKP_MAX_BOUNCES ? L.frame.p.max_bounces : VKP_MAX_BOUNCES;
@@ -767,6 +907,13 @@ cudaError_t launch_resolve(const FrameLaunch& L, int* launches)
         k_bounce<<<148 * 8, 128, 0, L.stream>>>(L.scene, L.frame, d);
         if (launches) *launches += 1;
     }
+    return cudaGetLastError();
+}
+cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(L.frame.path_count, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    k_chain<<<frame_grid(L), 128, 0, stream>>>(L.scene, L.frame);
     return cudaGetLastError();
 }
 cudaError_t launch_post(const FrameLaunch& L) { k_post<<<frame_grid(L), 128, 0, L.stream>>>(L.frame); return cudaGetLastError(); }
@@ -779,6 +926,15 @@ cudaError_t launch_trace_rays(cudaStream_t s, const DScene& scene, const vkp_ray
     unsigned blocks = (n + 127u) / 128u;
     if (any_hit) k_trace_list<true><<<blocks, 128, 0, s>>>(scene, rays, n, hits);
     else k_trace_list<false><<<blocks, 128, 0, s>>>(scene, rays, n, hits);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_stats(cudaStream_t s, const DScene& scene, const vkp_ray* rays, uint32_t n, int any_hit, uint32_t* stats)
+{
+    if (n == 0) return cudaSuccess;
+    unsigned blocks = (n + 127u) / 128u;
+    if (any_hit) k_trace_stats<true><<<blocks, 128, 0, s>>>(scene, rays, n, stats);
+    else k_trace_stats<false><<<blocks, 128, 0, s>>>(scene, rays, n, stats);
     return cudaGetLastError();
 }
 

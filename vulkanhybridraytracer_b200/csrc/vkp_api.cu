@@ -5,6 +5,7 @@
 #include "vkp_bvh.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -44,7 +45,10 @@ struct vkp_ctx {
     DevBuf position, normal, albedo, motion, material, emissive, hit_ids, final_f32, final_srgb8, shadow, denoised[2];
     int denoised_cur = 0;
     int plane_w = 0, plane_h = 0, plane_lights = 0;
-    DevBuf counters, io_tmp, io_tmp2, flush, path_q[2], path_count, luts;
+    DevBuf counters, io_tmp, io_tmp2, flush, path_q[2], path_count, luts, chain_buf, chain_len, chain_slot;
+    cudaStream_t chain_stream = nullptr;
+    cudaEvent_t ev_gbuffer = nullptr, ev_chain = nullptr;
+    bool chain_in_flight = false;
 
     bool profiling = false;
     cudaEvent_t ev[12]{};
@@ -53,6 +57,7 @@ struct vkp_ctx {
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     uint32_t last_launches = 0;
     int build_launches = 0;
+    int builder = 1;      // BLAS hierarchy: 0 = Karras LBVH, 1 = PLOC (default; VKP_BLAS_BUILDER=lbvh|ploc or vkp_set_builder)
 };
 
 namespace {
@@ -119,6 +124,7 @@ int ensure_planes(vkp_ctx* ctx)
     CK(ctx->counters.ensure(64));
     CK(ctx->path_q[0].ensure(px * sizeof(PathItem))); CK(ctx->path_q[1].ensure(px * sizeof(PathItem)));
     CK(ctx->path_count.ensure(sizeof(unsigned int) * (VKP_MAX_BOUNCES + 2)));
+    CK(ctx->chain_buf.ensure(px * sizeof(float4) * VKP_CHAIN_MAX)); CK(ctx->chain_len.ensure(px * sizeof(int))); CK(ctx->chain_slot.ensure(px * sizeof(int)));
     ctx->plane_w = W; ctx->plane_h = H; ctx->plane_lights = L;
     // defined initial state: history and accumulation start at zero (blur.comp:73 reads uninitialised memory upstream)
     CK(cudaMemsetAsync(ctx->position.p, 0, px * 8, ctx->stream)); CK(cudaMemsetAsync(ctx->normal.p, 0, px * 8, ctx->stream));
@@ -176,6 +182,7 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.tile_w = ctx->tile_w; F.tile_h = ctx->tile_h;
     F.tiles_x = (F.p.width + F.tile_w - 1) / F.tile_w; F.tiles_y = (F.p.height + F.tile_h - 1) / F.tile_h;
     F.rank = ctx->rank; F.world = ctx->world;
+    F.static_camera = memcmp(F.cam.view, F.cam.prev_view, 64) == 0 && memcmp(F.cam.proj, F.cam.prev_proj, 64) == 0;
     F.position = ctx->position.as<uint2>(); F.normal = ctx->normal.as<uint2>(); F.albedo = ctx->albedo.as<uchar4>();
     F.motion = ctx->motion.as<uint32_t>(); F.material = ctx->material.as<uchar4>(); F.emissive = ctx->emissive.as<uchar4>();
     F.hit_ids = ctx->hit_ids.as<int2>(); F.final_f32 = ctx->final_f32.as<float4>(); F.final_srgb8 = ctx->final_srgb8.as<uchar4>();
@@ -186,6 +193,7 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.path_q[0] = ctx->path_q[0].as<PathItem>(); F.path_q[1] = ctx->path_q[1].as<PathItem>();
     F.path_count = ctx->path_count.as<unsigned int>();
     F.lut_pow22 = ctx->luts.as<float>(); F.lut_post = ctx->luts.as<uint8_t>() + 1024;
+    F.chain_buf = ctx->chain_buf.as<float4>(); F.chain_len = ctx->chain_len.as<int>(); F.chain_slot = ctx->chain_slot.as<int>();
     const int total = F.tiles_x * F.tiles_y;
     L.n_own_tiles = total > F.rank ? (total - F.rank + F.world - 1) / F.world : 0;
     L.stream = ctx->stream;
@@ -217,7 +225,14 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
         L.frame.denoised = ctx->denoised[ctx->denoised_cur].as<uint8_t>();
         L.frame.denoised_next = ctx->denoised[ctx->denoised_cur ^ 1].as<uint8_t>();
         break;
-    case VKP_STAGE_RESOLVE: { int n = 0; CK(launch_resolve(L, &n)); ctx->last_launches += (uint32_t)n - 1u; break; }
+    case VKP_STAGE_RESOLVE: {
+        int n = 0;
+        const bool chain2 = L.frame.p.wavefront == 2 && L.frame.p.max_bounces <= VKP_CHAIN_MAX;
+        if (chain2 && !ctx->chain_in_flight) { CK(launch_chain(L, ctx->stream)); ctx->last_launches++; }      // stand-alone stage: serial
+        if (chain2 && ctx->chain_in_flight) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0)); ctx->chain_in_flight = false; }
+        CK(launch_resolve(L, &n)); ctx->last_launches += (uint32_t)n - 1u;
+        break;
+    }
     case VKP_STAGE_POST: CK(launch_post(L)); break;
     case VKP_STAGE_RAYTRACE: CK(launch_raytrace(L)); break;
     case VKP_STAGE_DEFERRED: CK(launch_deferred(L)); break;
@@ -257,6 +272,14 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
     ctx->device = device_ordinal;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
     ctx->stream = ctx->own_stream;
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);               // hi = greatest priority (numerically lowest)
+        cudaStreamCreateWithPriority(&ctx->chain_stream, cudaStreamNonBlocking, hi);
+        cudaEventCreateWithFlags(&ctx->ev_gbuffer, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
+    }
+    if (const char* b = getenv("VKP_BLAS_BUILDER")) ctx->builder = (strcmp(b, "lbvh") == 0) ? 0 : 1;
     cudaEventCreate(&ctx->timer0); cudaEventCreate(&ctx->timer1);
     // decode / gamma tables, computed on the device with the contract's own vkp_powf so they are bit-identical to the call
     if ((e = ctx->luts.ensure(2048)) != cudaSuccess || (e = launch_build_luts(ctx->stream, ctx->luts.as<float>(), ctx->luts.as<uint8_t>() + 1024)) != cudaSuccess ||
@@ -280,11 +303,14 @@ void vkp_destroy(vkp_ctx* ctx)
     ctx->tlas.release(); ctx->scratch.release(); ctx->tlas_scratch.release();
     DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_lights, &ctx->d_instances, &ctx->d_textures, &ctx->position, &ctx->normal, &ctx->albedo, &ctx->motion,
                       &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
-                      &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts};
+                      &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->timer0) cudaEventDestroy(ctx->timer0);
     if (ctx->timer1) cudaEventDestroy(ctx->timer1);
+    if (ctx->chain_stream) cudaStreamDestroy(ctx->chain_stream);
+    if (ctx->ev_gbuffer) cudaEventDestroy(ctx->ev_gbuffer);
+    if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -377,6 +403,13 @@ int vkp_set_instances(vkp_ctx* ctx, const vkp_instance* inst, int n)
     return VKP_OK;
 }
 
+int vkp_set_builder(vkp_ctx* ctx, int builder)
+{
+    if (!ctx || builder < 0 || builder > 1) return fail(ctx, VKP_ERR_INVALID, "vkp_set_builder: 0 = LBVH, 1 = PLOC");
+    ctx->builder = builder;
+    return VKP_OK;
+}
+
 int vkp_build_blas(vkp_ctx* ctx)
 {
     if (!ctx) return VKP_ERR_INVALID;
@@ -393,7 +426,7 @@ int vkp_build_blas(vkp_ctx* ctx)
         CK(ctx->scratch.boxes.ensure(sizeof(float) * 6 * (size_t)(ntri ? ntri : 1)));
         const uint32_t* idx = m.idx.as<uint32_t>() + I.first_index;
         CK(bvh_triangle_boxes(ctx->stream, m.verts.as<vkp_vertex>(), idx, ntri, ctx->scratch.boxes.as<float>()));
-        CK(bvh_build(ctx->stream, ctx->scratch, ntri, 4, b->bvh, &ctx->build_launches));
+        CK(bvh_build(ctx->stream, ctx->scratch, ntri, 4, b->bvh, &ctx->build_launches, ctx->builder));
         CK(bvh_emit_triangles(ctx->stream, m.verts.as<vkp_vertex>(), idx, b->bvh));
         CK(cudaStreamSynchronize(ctx->stream));
         if (b->bvh.height + 8 > VKP_TRAV_STACK - 8) {
@@ -430,7 +463,7 @@ int vkp_build_tlas(vkp_ctx* ctx, int update)
     CK(bvh_instance_boxes(ctx->stream, ctx->d_instances.as<DInstance>(), (uint32_t)n, ctx->tlas_scratch.boxes.as<float>()));
     int launches = 0;
     if (update && ctx->tlas.n_prims == (uint32_t)n && ctx->tlas.n_nodes > 0) CK(bvh_refit(ctx->stream, ctx->tlas_scratch, ctx->tlas, &launches));
-    else CK(bvh_build(ctx->stream, ctx->tlas_scratch, (uint32_t)n, 1, ctx->tlas, &launches));
+    else CK(bvh_build(ctx->stream, ctx->tlas_scratch, (uint32_t)n, 1, ctx->tlas, &launches, 0));
     CK(cudaStreamSynchronize(ctx->stream));   // `d` is a stack vector the async copy reads
     ctx->tlas_built = true;
     return VKP_OK;
@@ -477,7 +510,19 @@ int vkp_render(vkp_ctx* ctx)
     const int* seq = hybrid; int n = 4;
     if (ctx->params.mode == VKP_MODE_RAYTRACING) { seq = rt; n = 1; }
     else if (ctx->params.mode == VKP_MODE_DEFERRED) { seq = deferred; n = 2; }
-    for (int i = 0; i < n; i++) if ((r = run_one(ctx, L, seq[i])) != VKP_OK) return r;
+    for (int i = 0; i < n; i++) {
+        if ((r = run_one(ctx, L, seq[i])) != VKP_OK) return r;
+        if (seq[i] == VKP_STAGE_GBUFFER && ctx->params.mode == VKP_MODE_HYBRID && ctx->params.wavefront == 2 &&
+            ctx->params.max_bounces <= VKP_CHAIN_MAX && L.n_own_tiles > 0) {
+            // fork: the reflection chain needs only the G-buffer; it overlaps the shadow + denoise passes on its own stream
+            CK(cudaEventRecord(ctx->ev_gbuffer, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->chain_stream, ctx->ev_gbuffer, 0));
+            CK(launch_chain(L, ctx->chain_stream));
+            CK(cudaEventRecord(ctx->ev_chain, ctx->chain_stream));
+            ctx->chain_in_flight = true;
+            ctx->last_launches++;
+        }
+    }
     return stage_event(ctx, -1);
 }
 
@@ -606,6 +651,24 @@ int vkp_trace_rays(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, v
     CK(cudaMemcpyAsync(ctx->io_tmp.p, rays, sizeof(vkp_ray) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(launch_trace_rays(ctx->stream, S, ctx->io_tmp.as<vkp_ray>(), n, any_hit, ctx->io_tmp2.as<vkp_hit>()));
     CK(cudaMemcpyAsync(hits, ctx->io_tmp2.p, sizeof(vkp_hit) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VKP_OK;
+}
+
+int vkp_trace_stats(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, uint32_t* steps_and_tris)
+{
+    if (!ctx || (n && (!rays || !steps_and_tris))) return fail(ctx, VKP_ERR_INVALID, "vkp_trace_stats: NULL");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->tlas_built) return fail(ctx, VKP_ERR_INVALID, "vkp_trace_stats: acceleration structures are not built");
+    DScene S; memset(&S, 0, sizeof(S));
+    S.tlas_nodes = ctx->tlas.nodes.as<vkp_bvh_node>(); S.tlas_items = ctx->tlas.items.as<uint32_t>();
+    S.instances = ctx->d_instances.as<DInstance>(); S.n_instances = (int)ctx->instances.size();
+    if (n == 0) return VKP_OK;
+    CK(ctx->io_tmp.ensure(sizeof(vkp_ray) * (size_t)n));
+    CK(ctx->io_tmp2.ensure(sizeof(uint32_t) * 2 * (size_t)n));
+    CK(cudaMemcpyAsync(ctx->io_tmp.p, rays, sizeof(vkp_ray) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_trace_stats(ctx->stream, S, ctx->io_tmp.as<vkp_ray>(), n, any_hit, ctx->io_tmp2.as<uint32_t>()));
+    CK(cudaMemcpyAsync(steps_and_tris, ctx->io_tmp2.p, sizeof(uint32_t) * 2 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return VKP_OK;
 }

@@ -88,9 +88,15 @@ VKP_D bool hit_better(float t, int inst, int prim, const HitRec& h)
 }
 
 // ANY == true: gl_RayFlagsTerminateOnFirstHitEXT | SkipClosestHitShaderEXT (shadow rays): returns on the first hit
-template <bool ANY>
-VKP_D bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax, HitRec& best)
+#ifdef VKP_NOINLINE_TRACE
+#define VKP_TRACE_FN __device__ __noinline__
+#else
+#define VKP_TRACE_FN __device__ __forceinline__
+#endif
+template <bool ANY, bool STATS = false>
+VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax, HitRec& best, uint32_t* stats = nullptr)
 {
+    uint32_t n_steps = 0, n_tris = 0;      // STATS: node pairs fetched, triangles tested
     best.t = -1.0f; best.u = 0.0f; best.v = 0.0f; best.inst = -1; best.prim = -1;
     if (S.n_instances == 0) return false;     // empty TLAS: its root box is inverted, which a slab test cannot reject
     float limit = tmax;                       // current far bound (closest so far)
@@ -119,6 +125,7 @@ VKP_D bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax
         if (!(cur & VKP_LEAF_BIT)) {
             // internal: fetch both children (64 contiguous bytes)
             const float4* c = nodes + 2u * (size_t)cur;
+            if (STATS) n_steps++;
             float4 lo0 = __ldg(c + 0), hi0 = __ldg(c + 1), lo1 = __ldg(c + 2), hi1 = __ldg(c + 3);
             float t0, t1;
             bool h0 = box_test(lo0, hi0, ro, rd, inv, par, tmin, limit, t0);
@@ -159,10 +166,11 @@ VKP_D bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax
             for (uint32_t k = 0; k < count; k++) {
                 const float4* tp = tris + 3u * (size_t)(first + k);
                 float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                if (STATS) n_tris++;
                 float t, u, v;
                 if (tri_test(ro, rd, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), tmin, tmax, t, u, v)) {
                     int prim = __float_as_int(a.w);
-                    if (ANY) { best.t = t; best.u = u; best.v = v; best.inst = inst; best.prim = prim; return true; }
+                    if (ANY) { best.t = t; best.u = u; best.v = v; best.inst = inst; best.prim = prim; if (STATS) { stats[0] = n_steps; stats[1] = n_tris; } return true; }
                     if (hit_better(t, inst, prim, best)) {
                         best.t = t; best.u = u; best.v = v; best.inst = inst; best.prim = prim;
                         limit = t;
@@ -182,5 +190,6 @@ VKP_D bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax
         }
         if (cur == VKP_STACK_SENTINEL) break;
     }
+    if (STATS) { stats[0] = n_steps; stats[1] = n_tris; }
     return best.inst >= 0;
 }

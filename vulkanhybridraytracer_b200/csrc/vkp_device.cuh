@@ -125,12 +125,14 @@ struct PathItem {
     float4 d;   // ambient + emissive tail (or the sky albedo for background pixels)
 };
 #define VKP_MAX_BOUNCES 64
+#define VKP_CHAIN_MAX 8          /* stored per-bounce colours per path in chain mode 2 (MAX_RECURSION, helpers.glsl:8) */
 
 struct DFrame {
     vkp_camera cam;
     vkp_params p;
     // multi-GPU tiling: this context renders tiles t with t % world == rank
     int tile_w, tile_h, tiles_x, tiles_y, rank, world;
+    int static_camera;    // prev_view/prev_proj are bit-identical to view/proj: motion vectors are exactly 0
     // planes
     uint2* position;      // 4 x fp16
     uint2* normal;        // 4 x fp16
@@ -149,6 +151,9 @@ struct DFrame {
     const uint8_t* lut_post;        // [256] postFragment.frag on an 8-bit input: unorm8(pow(max(k/255, 0.001), 1/2.2))
     PathItem* path_q[2];            // ping-pong path queues of the reflection wavefront
     unsigned int* path_count;       // [VKP_MAX_BOUNCES + 2] queue length per bounce
+    float4* chain_buf;              // chain mode 2: VKP_CHAIN_MAX colours per compacted path
+    int* chain_len;                 // chain mode 2: number of bounces traced per path
+    int* chain_slot;                // chain mode 2: per-pixel path slot (written for mirror / glass pixels only)
 };
 
 // ---- texture / env -----------------------------------------------------------------------------------------

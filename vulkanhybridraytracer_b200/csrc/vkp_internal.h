@@ -29,6 +29,7 @@ struct Bvh {
     uint32_t n_nodes = 0;
     int leaf_max = 4;
     int height = 0;
+    int root = 0;        // index of the root among the internal nodes (0 for the Karras tree)
     DevBuf nodes;        // vkp_bvh_node[n_nodes]
     DevBuf items;        // uint32_t[n_prims]: leaf-ordered primitive ids
     DevBuf tris;         // BLAS only: float4[3*n_prims]
@@ -50,13 +51,19 @@ struct Bvh {
 struct BuildScratch {
     DevBuf boxes;       // float[6*n] primitive boxes
     DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, bounds, misc;
-    void release() { boxes.release(); keys.release(); keys_alt.release(); vals.release(); vals_alt.release(); cub_tmp.release(); bounds.release(); misc.release(); }
+    DevBuf ploc_cid[2], ploc_box[2], ploc_cnt[2], ploc_nn, ploc_flags, ploc_scan, ploc_icnt, ploc_parent;
+    void release()
+    {
+        DevBuf* all[] = {&boxes, &keys, &keys_alt, &vals, &vals_alt, &cub_tmp, &bounds, &misc, &ploc_cid[0], &ploc_cid[1], &ploc_box[0], &ploc_box[1],
+                         &ploc_cnt[0], &ploc_cnt[1], &ploc_nn, &ploc_flags, &ploc_scan, &ploc_icnt, &ploc_parent};
+        for (DevBuf* b : all) b->release();
+    }
 };
 
 // bvh_build.cu
 cudaError_t bvh_triangle_boxes(cudaStream_t s, const vkp_vertex* verts, const uint32_t* indices, uint32_t n_tris, float* boxes);
 cudaError_t bvh_instance_boxes(cudaStream_t s, const DInstance* inst, uint32_t n, float* boxes);
-cudaError_t bvh_build(cudaStream_t s, BuildScratch& scratch, uint32_t n_prims, int leaf_max, Bvh& out, int* launches);
+cudaError_t bvh_build(cudaStream_t s, BuildScratch& scratch, uint32_t n_prims, int leaf_max, Bvh& out, int* launches, int builder /*0 LBVH (Karras), 1 PLOC*/);
 cudaError_t bvh_refit(cudaStream_t s, BuildScratch& scratch, Bvh& bvh, int* launches);
 cudaError_t bvh_emit_triangles(cudaStream_t s, const vkp_vertex* verts, const uint32_t* indices, Bvh& bvh);
 
@@ -72,10 +79,12 @@ cudaError_t launch_gbuffer(const FrameLaunch& L);
 cudaError_t launch_shadow(const FrameLaunch& L);
 cudaError_t launch_denoise(const FrameLaunch& L);
 cudaError_t launch_resolve(const FrameLaunch& L, int* launches);
+cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream);
 cudaError_t launch_post(const FrameLaunch& L);
 cudaError_t launch_raytrace(const FrameLaunch& L);
 cudaError_t launch_deferred(const FrameLaunch& L);
 cudaError_t launch_trace_rays(cudaStream_t s, const DScene& scene, const vkp_ray* rays, uint32_t n, int any_hit, vkp_hit* hits);
+cudaError_t launch_trace_stats(cudaStream_t s, const DScene& scene, const vkp_ray* rays, uint32_t n, int any_hit, uint32_t* stats);
 cudaError_t launch_tiles_pack(cudaStream_t s, const void* plane, void* dst, int elem_bytes, int W, int H, int tile_w, int tile_h, int rank, int world);
 cudaError_t launch_tiles_unpack(cudaStream_t s, void* plane, const void* src, int elem_bytes, int W, int H, int tile_w, int tile_h, int rank, int world);
 cudaError_t launch_build_luts(cudaStream_t s, float* lut_pow22, uint8_t* lut_post);

@@ -125,6 +125,7 @@ VKPH_API int vkph_engine_set(void* p, const char* key, int value)
     else if (k == "max_bounces") e->_maxBounces = value;
     else if (k == "faithful_rng") e->_faithfulRng = value != 0;
     else if (k == "debug_target") e->debugTarget = value;
+    else if (k == "chain") e->_chainMode = value;
     else return -1;
     return 0;
 }

@@ -142,6 +142,7 @@ vkp_params VulkanEngine::current_params() const
     p.faithful_rng = _faithfulRng ? 1 : 0;
     p.denoise_cover_remainder = 1;
     p.debug_target = debugTarget;
+    p.wavefront = _chainMode;
     return p;
 }
 

@@ -274,6 +274,7 @@ public:
     int _spp{1};
     int _maxBounces{8};
     bool _faithfulRng{true};
+    int _chainMode{2};                  // vkp_params.wavefront: how the reflection chain is scheduled (0 inline, 1 wavefront, 2 overlapped)
 
     void init();
     void run(int frames = 1);
