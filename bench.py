@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
+    ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-identity check of the composite against a 1-GPU render")
     ap.add_argument("--chain", type=int, default=2, choices=[0, 1, 2],
                     help="reflection-chain schedule: 0 inline in k_resolve, 1 wavefront queues, 2 k_chain overlapped with the shadow pass (default)")
     args = ap.parse_args()
@@ -175,6 +176,7 @@ def main():
     import torch.distributed as dist
     from vulkanhybridraytracer_b200 import PLANE, tiling
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: the contract is ONE JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = local if world > 1 else 0
@@ -191,20 +193,11 @@ def main():
     def params(frame):
         return vk.make_params(W, H, mode=mode, spp=spp, shadow_samples=samples, faithful_rng=faithful, frame=frame, wavefront=args.chain)
 
-    # composite buffers (N > 1): packed sRGB8 tiles of every rank -> rank 0
-    sizes = [tiling.packed_bytes(W, H, r, world, 4, TW, TH) for r in range(world)]
-    packed = torch.empty(max(sizes), dtype=torch.uint8, device=f"cuda:{dev}") if world > 1 else None
-    gathered = [torch.empty(max(sizes), dtype=torch.uint8, device=f"cuda:{dev}") for _ in range(world)] if (world > 1 and rank == 0) else None
+    from vulkanhybridraytracer_b200.multigpu import TiledRenderer
+    tr = TiledRenderer(ctx, rank, world, L, tile=(TW, TH), backend="nccl", device=torch.device("cuda", dev), stream_ordered=world > 1)
 
     def composite():
-        ctx.tiles_pack(PLANE.FINAL_SRGB8, packed.data_ptr(), sizes[rank])
-        ctx.sync()
-        dist.gather(packed, gathered, dst=0)
-        if rank == 0:
-            torch.cuda.current_stream().synchronize()
-            for r in range(1, world):
-                ctx.tiles_unpack(PLANE.FINAL_SRGB8, r, world, gathered[r].data_ptr(), sizes[r])
-        return 2 + (world - 1 if rank == 0 else 0)
+        return tr.composite(PLANE.FINAL_SRGB8)
 
     def barrier():
         ctx.sync()
@@ -214,8 +207,8 @@ def main():
 
     ctx.set_params(params(0)); ctx.reset_history()
     frame = 0
-    for _ in range(args.warmup):                      # warm-up: frame 0 (reset frame) .. W-1
-        ctx.set_params(params(frame)); ctx.render()
+    for _ in range(args.warmup):                      # warm-up: frame 0 (reset frame, with its halo exchange for N > 1) .. W-1
+        tr.render(params(frame))
         if world > 1:
             composite()
         frame += 1
@@ -232,11 +225,11 @@ def main():
     for k in range(args.steps):
         if not args.no_flush:
             ctx.flush_l2()
-        ctx.set_params(params(frame))
+        p_k = params(frame)
         if world > 1:
             dist.barrier()
         ctx.timer_begin()
-        ctx.render()
+        tr.render(p_k)
         n_launch = 0
         if world > 1:
             n_launch = composite()
@@ -258,6 +251,18 @@ def main():
     ms_per_step = total_ms / args.steps
     counted = int(rays_all[1] + rays_all[2] + rays_all[3])
     value = counted / args.steps / (ms_per_step * 1e-3) / 1e6
+
+    # -- N > 1: the composited image must be bit-identical to the same frame sequence rendered on one GPU ---------------------------
+    composite_ok = None
+    if world > 1 and not args.no_verify:
+        if rank == 0:
+            got = ctx.readback(PLANE.FINAL_SRGB8).copy()
+            solo = vk.Context(dev); solo.upload_scene(scene); solo.set_camera(cam)
+            for f in range(frame):
+                solo.set_params(params(f)); solo.render()
+            composite_ok = bool(np.array_equal(got, solo.readback(PLANE.FINAL_SRGB8)))
+            solo.close()
+        dist.barrier()
 
     # -- timed region 2: end to end through the reference-facing host API (VulkanEngine::update + rasterize_hybrid + read-back) ---
     e2e = None
@@ -288,8 +293,8 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for k in range(args.steps):
-            ctx.set_lights(scene.lights); ctx.set_camera(cam); ctx.set_params(params(frame + k))
-            ctx.render()
+            ctx.set_lights(scene.lights); ctx.set_camera(cam)
+            tr.render(params(frame + k))
             if world > 1:
                 composite()
             if rank == 0:
@@ -358,6 +363,7 @@ def main():
                    "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain on a second stream overlapping k_shadow + k_denoise"}[args.chain],
                    "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
                    "parallelism": f"tiles {TW}x{TH} interleaved over {world} GPU(s), replicated BVH, NCCL gather of sRGB8 tiles" if world > 1 else "1 GPU",
+                   "composite_bit_identical_to_1gpu": composite_ok,
                    "timing": "CUDA events on the context stream around each frame, summed over K frames, max over ranks"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
     }

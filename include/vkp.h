@@ -95,7 +95,8 @@ VKP_API int vkp_set_profiling(vkp_ctx* ctx, int on);            /* per-stage CUD
  * == gl_RayFlagsTerminateOnFirstHitEXT|SkipClosestHitShaderEXT: only hit.t >= 0 / < 0 is defined */
 VKP_API int vkp_trace_rays(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, vkp_hit* hits);
 
-/* instrumented traversal: per ray {node pairs fetched, triangles tested} (2 x uint32 per ray), for build-quality studies */
+/* instrumented traversal: per ray {node pairs fetched, triangles tested, SM cycles} (3 x uint32 per ray), for build-quality
+ * and latency studies */
 VKP_API int vkp_trace_stats(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, uint32_t* steps_and_tris);
 
 /* BVH introspection (tests): copy out the nodes and the leaf-ordered primitive ids of one BLAS

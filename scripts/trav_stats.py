@@ -18,6 +18,11 @@ rays["origin"] = iv[:3, 3] + dirs * 1e-2; rays["dir"] = dirs; rays["tmin"] = 0.0
 st = ctx.trace_stats(rays)
 hits = ctx.trace_rays(rays)
 print("primary rays %d: steps mean %.1f p50 %d p99 %d max %d | tris mean %.1f p99 %d max %d" % (len(rays), st[:, 0].mean(), np.median(st[:, 0]), np.percentile(st[:, 0], 99), st[:, 0].max(), st[:, 1].mean(), np.percentile(st[:, 1], 99), st[:, 1].max()))
+it = st[:, 0] + st[:, 1]
+slow = np.argsort(-st[:, 2].astype(np.int64))[:8]
+print("cycles: mean %.0f p50 %d p99 %d max %d | cycles per iteration (steps+tris): mean %.0f ; slowest rays: %s" % (st[:, 2].mean(), np.median(st[:, 2]), np.percentile(st[:, 2], 99), st[:, 2].max(), (st[:, 2] / np.maximum(it, 1)).mean(), [(int(st[k, 0]), int(st[k, 1]), int(st[k, 2])) for k in slow]))
+heavy = it > 40
+print("rays with > 40 iterations: %d, cycles/iteration %.0f" % (heavy.sum(), (st[heavy, 2] / it[heavy]).mean()))
 for inst in range(len(sc.instances)):
     m = hits["instance"] == inst
     if m.any(): print("  hit instance %d (%d tris): rays %d steps mean %.1f tris mean %.1f" % (inst, sc.instances["index_count"][inst] // 3, m.sum(), st[m, 0].mean(), st[m, 1].mean()))

@@ -388,7 +388,7 @@ class Context:
 
     def trace_stats(self, rays, any_hit=False):
         rays = np.ascontiguousarray(rays, dtype=T.ray_dtype)
-        out = np.zeros((len(rays), 2), dtype=np.uint32)
+        out = np.zeros((len(rays), 3), dtype=np.uint32)
         self._ck(self.L.vkp_trace_stats(self.h, rays.ctypes.data, len(rays), 1 if any_hit else 0, out.ctypes.data), "vkp_trace_stats")
         return out
 

@@ -207,7 +207,7 @@ __global__ void k_mark_keep(const int2* __restrict__ range, int n_internal, int 
 
 __global__ void k_emit_nodes(const float* __restrict__ boxes, const uint32_t* __restrict__ items, int n, const int2* __restrict__ child,
                              const int2* __restrict__ range, const float4* __restrict__ ibox, const uint32_t* __restrict__ keep,
-                             const uint32_t* __restrict__ rank, vkp_bvh_node* __restrict__ nodes, int root)
+                             const uint32_t* __restrict__ rank, vkp_bvh_node* __restrict__ nodes, int root, int ref_items)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n - 1) return;
@@ -231,7 +231,8 @@ __global__ void k_emit_nodes(const float* __restrict__ boxes, const uint32_t* __
             int pos = ~ci;
             const float* b = boxes + 6 * (size_t)items[pos];
             nd.bmin[0] = b[0]; nd.bmin[1] = b[1]; nd.bmin[2] = b[2]; nd.bmax[0] = b[3]; nd.bmax[1] = b[4]; nd.bmax[2] = b[5];
-            nd.ref = 0x80000000u | ((uint32_t)pos << 3);
+            // TLAS (ref_items): a single-instance leaf names the instance itself, saving traversal one dependent load
+            nd.ref = 0x80000000u | ((ref_items ? items[pos] : (uint32_t)pos) << 3);
             nd.aux = 1u;
         } else {
             float4 lo = ibox[2 * (size_t)ci], hi = ibox[2 * (size_t)ci + 1];
@@ -426,7 +427,7 @@ cudaError_t fit_and_emit(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches
     k_fit<<<blocks_for(n, 256), 256, 0, s>>>(sc.boxes.as<float>(), B.items.as<uint32_t>(), (int)n, B.child.as<int2>(), B.parent.as<int>(),
                                              B.ibox.as<float4>(), B.flags.as<int>(), height_dev, B.root);
     k_emit_nodes<<<blocks_for(n - 1, 256), 256, 0, s>>>(sc.boxes.as<float>(), B.items.as<uint32_t>(), (int)n, B.child.as<int2>(), B.range.as<int2>(),
-                                                        B.ibox.as<float4>(), B.keep.as<uint32_t>(), B.rank.as<uint32_t>(), B.nodes.as<vkp_bvh_node>(), B.root);
+                                                        B.ibox.as<float4>(), B.keep.as<uint32_t>(), B.rank.as<uint32_t>(), B.nodes.as<vkp_bvh_node>(), B.root, B.leaf_max == 1 ? 1 : 0);
     if (launches) *launches += 2;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return cudaMemcpyAsync(&B.height, height_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
@@ -519,6 +520,7 @@ cudaError_t bvh_build(cudaStream_t s, BuildScratch& sc, uint32_t n, int leaf_max
     if ((e = sc.misc.ensure(256)) != cudaSuccess) return e;
     if (n <= 1) {
         if (n == 1 && (e = cudaMemsetAsync(B.items.p, 0, sizeof(uint32_t), s)) != cudaSuccess) return e;
+        B.root_ref = 0x80000000u;     // a single leaf: first item 0, one item (an empty BLAS holds one degenerate triangle)
         return fit_and_emit(s, sc, B, launches);
     }
     if ((e = B.child.ensure(sizeof(int2) * ni)) != cudaSuccess) return e;
@@ -567,6 +569,7 @@ cudaError_t bvh_build(cudaStream_t s, BuildScratch& sc, uint32_t n, int leaf_max
     if ((e = cudaMemcpyAsync(&last_keep, B.keep.as<uint32_t>() + (ni - 1), 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     (void)fitted;   // PLOC already knows every box, but the shared fit pass is cheap and keeps one code path (also used by refit)
     if ((e = fit_and_emit(s, sc, B, launches)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(&B.root_ref, &B.nodes.as<vkp_bvh_node>()[0].ref, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
     B.n_nodes = 1u + 2u * (last_rank + last_keep);
     return cudaSuccess;

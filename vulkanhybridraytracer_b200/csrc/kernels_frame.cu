@@ -327,28 +327,27 @@ __global__ void __launch_bounds__(128, VKP_LB_SHADOW) k_shadow(const __grid_cons
             float3 N = normalize3(normal);
             const int shadowSamples = F.p.shadow_samples;
             const bool advance = F.p.faithful_rng == 0;
-            uint32_t seed = tea16((uint32_t)px.y * (uint32_t)W + (uint32_t)px.x, (uint32_t)F.p.frame);
-            if (advance) {
-                for (int k = 0; k < l; k++) {
-                    const LightGeom g = light_geom(S.lights[k], position, N);
-                    if (g.NdotL > 0.0f && g.dist < g.maxd)
-                        for (int r = 0; r < 2 * shadowSamples; r++) seed = 1664525u * seed + 1013904223u;   // two rnd() per sampleDisk
-                }
-            }
             const vkp_light light = S.lights[l];
             const LightGeom g = light_geom(light, position, N);
             float shadowFactor = 0.0f;
             if (g.NdotL > 0.0f) {
-                for (int s = 0; s < shadowSamples; s++) {
-                    bool shadowed;
-                    if (g.dist < g.maxd) {
+                if (g.dist < g.maxd) {
+                    // the RNG is only needed when rays are traced: TEA (16 rounds) is the most expensive part of an unlit pixel
+                    uint32_t seed = tea16((uint32_t)px.y * (uint32_t)W + (uint32_t)px.x, (uint32_t)F.p.frame);
+                    if (advance) {
+                        for (int k = 0; k < l; k++) {
+                            const LightGeom gk = light_geom(S.lights[k], position, N);
+                            if (gk.NdotL > 0.0f && gk.dist < gk.maxd)
+                                for (int r = 0; r < 2 * shadowSamples; r++) seed = 1664525u * seed + 1013904223u;   // two rnd() per sampleDisk
+                        }
+                    }
+                    for (int s = 0; s < shadowSamples; s++) {
                         const float3 dir = sample_disk(light, position, g.L, seed, advance);
                         HitRec h; nrays++;
-                        shadowed = trace_ray<true>(S, position + dir * 1e-1f, dir, 0.001f, g.dist + 1.0f, h);
-                    } else {
-                        shadowed = false;
+                        if (!trace_ray<true>(S, position + dir * 1e-1f, dir, 0.001f, g.dist + 1.0f, h)) shadowFactor += 1.0f;
                     }
-                    if (!shadowed) shadowFactor += 1.0f;
+                } else {
+                    for (int s = 0; s < shadowSamples; s++) shadowFactor += 1.0f;      // beyond maxDistance: unshadowed (shadowRaygen.rgen:81-83)
                 }
                 shadowFactor /= (float)shadowSamples;
             }
@@ -522,7 +521,9 @@ __global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_resolve(const __grid_co
         float3 origin = f3s(0.0f), direction = f3s(0.0f);
         float attenuation = 1.0f;   // declared outside the light loop upstream: stale across lights (App. A #8)
         float3 rayColor = f3s(0.0f);
-        for (int l = 0; l < S.n_lights; l++) {
+        // a background pixel with a diffuse material 0 traces nothing and ends as `albedo` (hybridRaygen.rgen:182-183): its light loop is dead code
+        const int n_lights_eff = (background && shadingMode == 0) ? 0 : S.n_lights;
+        for (int l = 0; l < n_lights_eff; l++) {
             const vkp_light light = S.lights[l];
             const float3 lpos = f3(light.position[0], light.position[1], light.position[2]);
             const float3 lcol = f3(light.color[0], light.color[1], light.color[2]);
@@ -820,8 +821,10 @@ __global__ void __launch_bounds__(128) k_trace_stats(const __grid_constant__ DSc
     vkp_ray r = rays[i];
     HitRec h;
     uint32_t st[2] = {0u, 0u};
+    const long long t0 = clock64();
     trace_ray<ANY, true>(S, f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax, h, st);
-    stats[2 * (size_t)i] = st[0]; stats[2 * (size_t)i + 1] = st[1];
+    const long long t1 = clock64();
+    stats[3 * (size_t)i] = st[0]; stats[3 * (size_t)i + 1] = st[1]; stats[3 * (size_t)i + 2] = (uint32_t)(t1 - t0);   // SM cycles for this ray's traversal
 }
 
 // ---- multi-GPU tile pack / unpack (SURVEY 8e composite) -------------------------------------------------------

@@ -32,7 +32,7 @@ struct vkp_ctx {
     std::vector<vkp_instance> instances;
     std::vector<int> inst_blas;
     std::vector<std::unique_ptr<BlasRec>> blas;
-    DevBuf d_materials, d_lights, d_instances, d_textures;
+    DevBuf d_materials, d_lights, d_instances, d_textures, d_inst_trav;
     Bvh tlas;
     BuildScratch scratch, tlas_scratch;
     bool blas_built = false, tlas_built = false, textures_dirty = true;
@@ -162,6 +162,7 @@ int make_scene(vkp_ctx* ctx, DScene& S)
     S.tlas_nodes = ctx->tlas.nodes.as<vkp_bvh_node>();
     S.tlas_items = ctx->tlas.items.as<uint32_t>();
     S.instances = ctx->d_instances.as<DInstance>();
+    S.inst_trav = ctx->d_inst_trav.as<DInstTrav>();
     S.materials = ctx->d_materials.as<vkp_material>();
     S.lights = ctx->d_lights.as<vkp_light>();
     S.textures = ctx->d_textures.as<DTexture>();
@@ -301,7 +302,7 @@ void vkp_destroy(vkp_ctx* ctx)
     for (auto& t : ctx->textures) t->texels.release();
     for (auto& b : ctx->blas) b->bvh.release();
     ctx->tlas.release(); ctx->scratch.release(); ctx->tlas_scratch.release();
-    DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_lights, &ctx->d_instances, &ctx->d_textures, &ctx->position, &ctx->normal, &ctx->albedo, &ctx->motion,
+    DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_lights, &ctx->d_instances, &ctx->d_textures, &ctx->d_inst_trav, &ctx->position, &ctx->normal, &ctx->albedo, &ctx->motion,
                       &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
                       &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot};
     for (DevBuf* b : bufs) b->release();
@@ -446,6 +447,7 @@ int vkp_build_tlas(vkp_ctx* ctx, int update)
     CK(cudaSetDevice(ctx->device));
     const int n = (int)ctx->instances.size();
     std::vector<DInstance> d(n ? n : 1);
+    std::vector<DInstTrav> tv(n ? n : 1);
     for (int i = 0; i < n; i++) {
         const vkp_instance& I = ctx->instances[i];
         BlasRec* rec = nullptr;
@@ -456,7 +458,12 @@ int vkp_build_tlas(vkp_ctx* ctx, int update)
         d[i].nodes = rec->bvh.nodes.as<vkp_bvh_node>(); d[i].tris = rec->bvh.tris.as<float4>();
         d[i].vertices = m.verts.as<vkp_vertex>(); d[i].indices = m.idx.as<uint32_t>() + I.first_index;
         d[i].material_id = I.material_id;
+        const float* im = I.inv_model;
+        tv[i].r0 = make_float4(im[0], im[4], im[8], im[12]); tv[i].r1 = make_float4(im[1], im[5], im[9], im[13]); tv[i].r2 = make_float4(im[2], im[6], im[10], im[14]);
+        tv[i].nodes = rec->bvh.nodes.as<float4>(); tv[i].tris = rec->bvh.tris.as<float4>(); tv[i].root_ref = rec->bvh.root_ref;
     }
+    CK(ctx->d_inst_trav.ensure(sizeof(DInstTrav) * tv.size()));
+    CK(cudaMemcpyAsync(ctx->d_inst_trav.p, tv.data(), sizeof(DInstTrav) * tv.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx->d_instances.ensure(sizeof(DInstance) * d.size()));
     CK(cudaMemcpyAsync(ctx->d_instances.p, d.data(), sizeof(DInstance) * d.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx->tlas_scratch.boxes.ensure(sizeof(float) * 6 * (size_t)(n ? n : 1)));
@@ -645,6 +652,7 @@ int vkp_trace_rays(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, v
     memset(&S, 0, sizeof(S));
     S.tlas_nodes = ctx->tlas.nodes.as<vkp_bvh_node>(); S.tlas_items = ctx->tlas.items.as<uint32_t>();
     S.instances = ctx->d_instances.as<DInstance>(); S.n_instances = (int)ctx->instances.size();
+    S.inst_trav = ctx->d_inst_trav.as<DInstTrav>();
     if (n == 0) return VKP_OK;
     CK(ctx->io_tmp.ensure(sizeof(vkp_ray) * (size_t)n));
     CK(ctx->io_tmp2.ensure(sizeof(vkp_hit) * (size_t)n));
@@ -663,12 +671,13 @@ int vkp_trace_stats(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, 
     DScene S; memset(&S, 0, sizeof(S));
     S.tlas_nodes = ctx->tlas.nodes.as<vkp_bvh_node>(); S.tlas_items = ctx->tlas.items.as<uint32_t>();
     S.instances = ctx->d_instances.as<DInstance>(); S.n_instances = (int)ctx->instances.size();
+    S.inst_trav = ctx->d_inst_trav.as<DInstTrav>();
     if (n == 0) return VKP_OK;
     CK(ctx->io_tmp.ensure(sizeof(vkp_ray) * (size_t)n));
-    CK(ctx->io_tmp2.ensure(sizeof(uint32_t) * 2 * (size_t)n));
+    CK(ctx->io_tmp2.ensure(sizeof(uint32_t) * 3 * (size_t)n));
     CK(cudaMemcpyAsync(ctx->io_tmp.p, rays, sizeof(vkp_ray) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(launch_trace_stats(ctx->stream, S, ctx->io_tmp.as<vkp_ray>(), n, any_hit, ctx->io_tmp2.as<uint32_t>()));
-    CK(cudaMemcpyAsync(steps_and_tris, ctx->io_tmp2.p, sizeof(uint32_t) * 2 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(steps_and_tris, ctx->io_tmp2.p, sizeof(uint32_t) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return VKP_OK;
 }

@@ -105,8 +105,18 @@ struct DInstance {
     int32_t _pad[3];
 };
 
+// what traversal needs to enter an instance, in one 80-byte record (5 independent 16-byte loads = one memory round trip):
+// the rows of inverse(model) 3x4 in xform_point()'s association, the BLAS arrays and the BLAS root reference
+struct DInstTrav {
+    float4 r0, r1, r2;
+    const float4* nodes;
+    const float4* tris;
+    uint32_t root_ref, _pad[3];
+};
+
 struct DScene {
-    const float* lut_pow22;          // same table as DFrame::lut_pow22 (hit / miss shading has only the scene)
+    const float* lut_pow22;
+    const DInstTrav* inst_trav;          // same table as DFrame::lut_pow22 (hit / miss shading has only the scene)
     const vkp_bvh_node* tlas_nodes;
     const uint32_t* tlas_items;      // leaf-ordered instance ids
     const DInstance* instances;

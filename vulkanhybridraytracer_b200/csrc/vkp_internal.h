@@ -30,6 +30,7 @@ struct Bvh {
     int leaf_max = 4;
     int height = 0;
     int root = 0;        // index of the root among the internal nodes (0 for the Karras tree)
+    uint32_t root_ref = 0x80000000u;   // nodes[0].ref: what traversal continues with after entering this BVH
     DevBuf nodes;        // vkp_bvh_node[n_nodes]
     DevBuf items;        // uint32_t[n_prims]: leaf-ordered primitive ids
     DevBuf tris;         // BLAS only: float4[3*n_prims]
