@@ -201,6 +201,15 @@ def test_raytraced_mode(gpu_ctx, small_scene, small_oracle):
         assert np.array_equal(got.view(np.uint32), acc.view(np.uint32))
         c = ctx.counters()
         assert [c.rays_reflect, c.rays_secondary_shadow] == list(o.counters.rays)[2:]
+    # many shadow samples: the one-warp-per-pixel kernel (lanes split the samples), advancing and faithful RNG, 40 > 32 samples
+    for faithful in (0, 1):
+        p = vk.make_params(w, h, mode=vk.MODE_RAYTRACING, spp=2, shadow_samples=40, faithful_rng=faithful, frame=0)
+        ctx.set_params(p); ctx.reset_history(); ctx.render()
+        o.reset_counters()
+        ref = o.raytrace(cam, p)
+        assert np.array_equal(ctx.readback(PLANE.FINAL_F32).view(np.uint32), ref.view(np.uint32)), faithful
+        c = ctx.counters()
+        assert [c.rays_reflect, c.rays_secondary_shadow] == list(o.counters.rays)[2:]
     # faithful variant (seed by value, closesthit.rchit:107)
     p = vk.make_params(w, h, mode=vk.MODE_RAYTRACING, spp=1, shadow_samples=4, faithful_rng=1, frame=0)
     ctx.set_params(p); ctx.reset_history(); ctx.render()

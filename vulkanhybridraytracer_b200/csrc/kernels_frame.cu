@@ -20,6 +20,9 @@
 #ifndef VKP_LB_SHADOW
 #define VKP_LB_SHADOW 6
 #endif
+#ifndef VKP_LB_RT
+#define VKP_LB_RT 4
+#endif
 #ifndef VKP_LB_RESOLVE
 #define VKP_LB_RESOLVE 4
 #endif
@@ -89,7 +92,9 @@ __device__ __forceinline__ void shade_miss(const DScene& S, float3 rayDir, Paylo
 }
 
 // hybridHit.rchit:24-184 (RT == false) / closesthit.rchit:26-186 (RT == true)
-template <bool RT>
+// WARP == true (k_raytrace_warp): the 32 lanes of the warp hold the SAME path; everything is computed redundantly
+// (one SIMT instruction stream, broadcast loads) except the per-light shadow samples, which are spread over the lanes.
+template <bool RT, bool WARP = false>
 __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, float3 rayD, const HitRec& h, Payload& prd,
                           unsigned int& n_secondary)
 {
@@ -141,7 +146,39 @@ __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, flo
         const float NdotH = clamp01(dot3(N, H));
         float shadowFactor = RT ? 0.0f : 1.0f;
 
-        if (RT) {
+        if (RT && WARP) {
+            // closesthit.rchit:99-120 with the samples of this light traced by different lanes.  Every traced sample
+            // advances the RNG by exactly two LCG steps whatever it hits, so sample a starts from LCG^(2a)(seed); the
+            // unshadowed count is an integer, so the sum does not depend on the order.
+            if (NdotL > 0.0f) {
+                unsigned lit = 0;
+                if (light_distance < light_max_distance) {
+                    const int lane = threadIdx.x & 31;
+                    for (int a0 = 0; a0 < P.shadow_samples; a0 += 32) {
+                        const int a = a0 + lane;
+                        bool unshadowed = false;
+                        if (a < P.shadow_samples) {
+                            uint32_t sd = prd.seed;
+                            if (advance) for (int r = 0; r < 2 * a; r++) sd = 1664525u * sd + 1013904223u;
+                            float3 dir = sample_disk(light, worldPos, L, sd, false);
+                            HitRec sh; n_secondary++;
+                            unshadowed = !trace_ray<true>(S, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh);
+                        }
+                        lit += (unsigned)__popc(__ballot_sync(0xffffffffu, unshadowed));
+                    }
+                    if (advance) for (int r = 0; r < 2 * P.shadow_samples; r++) prd.seed = 1664525u * prd.seed + 1013904223u;
+                }
+                shadowFactor = (float)lit;            // == lit times "+= 1.0f"
+                shadowFactor /= (float)P.shadow_samples;
+            }
+            if (light_intensity == 0.0f) attenuation = 0.0f;
+            else {
+                attenuation = light_max_distance - light_distance;
+                attenuation /= light_max_distance;
+                attenuation = fmaxf(attenuation, 0.0f);
+                attenuation = attenuation * attenuation;
+            }
+        } else if (RT) {
             if (NdotL > 0.0f) {
                 for (int a = 0; a < P.shadow_samples; a++) {
                     bool shadowed = true;
@@ -673,7 +710,7 @@ __global__ void __launch_bounds__(128) k_post(const __grid_constant__ DFrame F)
 }
 
 // raygen.rgen:20-81 with NSAMPLES = params.spp; the accumulation target is kept in fp32
-__global__ void __launch_bounds__(128) k_raytrace(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+__global__ void __launch_bounds__(128, VKP_LB_RT) k_raytrace(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     const Pixel px = pixel_of_thread(F);
     unsigned int n_refl = 0, n_sec = 0;
@@ -710,6 +747,60 @@ __global__ void __launch_bounds__(128) k_raytrace(const __grid_constant__ DScene
         float4 outc = make_float4(finalColor.x, finalColor.y, finalColor.z, 1.0f);
         F.final_f32[i] = outc;
         F.final_srgb8[i] = post_pixel(F.lut_post, outc);
+    }
+    add_counter(F.counters, 2, n_refl);
+    add_counter(F.counters, 3, n_sec);
+}
+
+// raygen.rgen with ONE WARP PER PIXEL, for many shadow samples per hit (BASELINE configs[2]: 64 spp x 64 samples): a pixel
+// is ~12 000 rays, so one thread per pixel leaves a tile-sharded GPU with less than one wave of threads and a ~100 ms
+// critical path per pixel.  Here the lanes share the path and split each light's shadow samples (shade_hit<true, true>).
+__global__ void __launch_bounds__(128, VKP_LB_RT) k_raytrace_warp(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    const int tpp = F.tile_w * F.tile_h;
+    const long long gw = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int own_tile = (int)(gw / tpp), within = (int)(gw - (long long)own_tile * tpp);
+    const int tile = F.rank + own_tile * F.world;
+    const int tx = tile % F.tiles_x, ty = tile / F.tiles_x;
+    const int x = tx * F.tile_w + within % F.tile_w, y = ty * F.tile_h + within / F.tile_w;
+    unsigned int n_refl = 0, n_sec = 0;
+    if (ty < F.tiles_y && x < F.p.width && y < F.p.height) {           // warp-uniform
+        const int W = F.p.width, H = F.p.height;
+        const size_t i = (size_t)y * W + x;
+        const int frame = F.p.frame;
+        Payload prd;
+        prd.seed = tea16((uint32_t)y * (uint32_t)W + (uint32_t)x, (uint32_t)frame);
+        float3 finalColor = f3s(0.0f);
+        for (int nS = 0; nS < F.p.spp; nS++) {
+            float r1 = rnd01(prd.seed);
+            float r2 = rnd01(prd.seed);
+            float ox = nS == 0 ? 0.5f : r1, oy = nS == 0 ? 0.5f : r2;
+            float3 origin, direction; camera_ray(F.cam, x, y, ox, oy, W, H, origin, direction);
+            float3 rayColor = f3s(1.0f);
+            for (int b = 0; b < F.p.max_bounces; b++) {
+                float3 ro = origin + direction * 1e-2f;
+                HitRec h; n_refl++;
+                bool hit = trace_ray<false>(S, ro, direction, 0.001f, 10000.0f, h);
+                if (hit) shade_hit<true, true>(S, F.p, ro, direction, h, prd, n_sec); else shade_miss(S, direction, prd);
+                rayColor = rayColor * prd.color;
+                if (!hit || !(prd.scatter > 0.0f)) break;
+                origin = prd.origin; direction = prd.direction;
+            }
+            finalColor = finalColor + rayColor;
+        }
+        finalColor = finalColor / (float)F.p.spp;
+        if (frame >= 0) {
+            float a = 1.0f / (float)(1.0f + (float)frame);
+            float4 last = F.final_f32[i];
+            finalColor = mix3(f3(last.x, last.y, last.z), finalColor, a);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            float4 outc = make_float4(finalColor.x, finalColor.y, finalColor.z, 1.0f);
+            F.final_f32[i] = outc;
+            F.final_srgb8[i] = post_pixel(F.lut_post, outc);
+        } else {
+            n_refl = 0;                       // the closest-hit rays are the warp's, count them once
+        }
     }
     add_counter(F.counters, 2, n_refl);
     add_counter(F.counters, 3, n_sec);
@@ -920,7 +1011,17 @@ cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream)
     return cudaGetLastError();
 }
 cudaError_t launch_post(const FrameLaunch& L) { k_post<<<frame_grid(L), 128, 0, L.stream>>>(L.frame); return cudaGetLastError(); }
-cudaError_t launch_raytrace(const FrameLaunch& L) { k_raytrace<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
+cudaError_t launch_raytrace(const FrameLaunch& L)
+{
+    if (L.frame.p.shadow_samples >= 8) {
+        // many shadow samples per hit: one warp per pixel, lanes split the samples
+        const long long warps = (long long)L.n_own_tiles * L.frame.tile_w * L.frame.tile_h;
+        k_raytrace_warp<<<(unsigned)((warps + 3) / 4), 128, 0, L.stream>>>(L.scene, L.frame);
+    } else {
+        k_raytrace<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);
+    }
+    return cudaGetLastError();
+}
 cudaError_t launch_deferred(const FrameLaunch& L) { k_deferred<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
 
 cudaError_t launch_trace_rays(cudaStream_t s, const DScene& scene, const vkp_ray* rays, uint32_t n, int any_hit, vkp_hit* hits)
