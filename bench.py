@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
+    ap.add_argument("--no-peer", action="store_true", help="N > 1: composite with pack + NCCL gather + unpack instead of NVLink peer stores")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-identity check of the composite against a 1-GPU render")
     ap.add_argument("--chain", type=int, default=2, choices=[0, 1, 2],
                     help="reflection-chain schedule: 0 inline in k_resolve, 1 wavefront queues, 2 k_chain overlapped with the shadow pass (default)")
@@ -195,6 +196,11 @@ def main():
 
     from vulkanhybridraytracer_b200.multigpu import TiledRenderer
     tr = TiledRenderer(ctx, rank, world, L, tile=(TW, TH), backend="nccl", device=torch.device("cuda", dev), stream_ordered=world > 1)
+
+    peer = False
+    if world > 1 and not args.no_peer:
+        ctx.set_params(params(0))
+        peer = tr.enable_peer_output()
 
     def composite():
         return tr.composite(PLANE.FINAL_SRGB8)
@@ -362,7 +368,9 @@ def main():
                    "nominal_2P_mrays_s": 2 * P / (ms_per_step * 1e-3) / 1e6,
                    "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain on a second stream overlapping k_shadow + k_denoise"}[args.chain],
                    "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
-                   "parallelism": f"tiles {TW}x{TH} interleaved over {world} GPU(s), replicated BVH, NCCL gather of sRGB8 tiles" if world > 1 else "1 GPU",
+                   "parallelism": (f"tiles {TW}x{TH} interleaved over {world} GPU(s), replicated BVH, " +
+                                   ("resolve kernels store sRGB8 pixels straight into rank 0's image over NVLink peer memory (CUDA IPC) + 4-byte all-reduce as the frame barrier"
+                                    if peer else "pack + NCCL gather of sRGB8 tiles + unpack")) if world > 1 else "1 GPU",
                    "composite_bit_identical_to_1gpu": composite_ok,
                    "timing": "CUDA events on the context stream around each frame, summed over K frames, max over ranks"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),

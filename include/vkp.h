@@ -116,6 +116,12 @@ VKP_API int vkp_flush_l2(vkp_ctx* ctx);
 VKP_API int vkp_tiles_packed_bytes(const vkp_ctx* ctx, int plane, int rank, int world, size_t* bytes);
 VKP_API int vkp_tiles_pack(vkp_ctx* ctx, int plane, void* device_dst, size_t bytes);
 VKP_API int vkp_tiles_unpack(vkp_ctx* ctx, int plane, int rank, int world, const void* device_src, size_t bytes);
+/* multi-GPU composite without a gather: rank 0 exports its FINAL_SRGB8 plane (64-byte CUDA IPC handle), the other ranks
+ * open it and redirect their own FINAL_SRGB8 stores to it, so the resolve kernels write finished pixels straight into
+ * rank 0's image over NVLink; the only per-frame collective left is a barrier.  NULL restores the local plane. */
+VKP_API int vkp_ipc_export_plane(vkp_ctx* ctx, int plane, void* handle64);
+VKP_API int vkp_ipc_open(vkp_ctx* ctx, const void* handle64, void** device_ptr);
+VKP_API int vkp_set_output_redirect(vkp_ctx* ctx, void* peer_final_srgb8);
 /* numerics-contract probe (tests): evaluate one vkp_detmath.h function on the DEVICE over host arrays.
  * func: 0 sin, 1 cos, 2 atan2(x,y), 3 asin, 4 pow(x,y), 5 log2, 6 exp2, 7 f32->f16->f32, 8 unorm8 */
 VKP_API int vkp_eval_math(vkp_ctx* ctx, int func, const float* x, const float* y, uint32_t n, float* out);

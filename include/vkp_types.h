@@ -82,7 +82,8 @@ typedef struct vkp_params {
     int32_t wavefront;               /* reflection chain (hybridRaygen.rgen:153-170): 0 = inline in the resolve kernel,
                                         1 = wavefront path queues with ray compaction, one launch per bounce,
                                         2 = compacted chain kernel on a second stream, overlapping shadow + denoise  */
-    int32_t reserved[4];
+    int32_t fuse_denoise;            /* vkp_render (Hybrid): run blur.comp inside the resolve kernel instead of as its own pass */
+    int32_t reserved[3];
 } vkp_params;
 
 /* Planes readable with vkp_readback / writable with vkp_upload_plane.  Layouts are row-major,

@@ -94,15 +94,15 @@ def test_trace_edge_cases(gpu_ctx, small_scene, small_oracle):
     assert got["instance"][0] == -1 and got["instance"][1] == 0 and abs(got["t"][1] - 5.0) < 1e-5 and got["instance"][2] == -1 and got["instance"][3] == -1
 
 
-@pytest.mark.parametrize("w,h,wavefront", [(320, 184, 0), (250, 130, 0), (320, 184, 1), (250, 130, 1), (320, 184, 2), (250, 130, 2)])
-def test_hybrid_frames_stage_by_stage(gpu_ctx, small_scene, small_oracle, w, h, wavefront):
+@pytest.mark.parametrize("w,h,wavefront,fuse", [(320, 184, 0, 1), (250, 130, 0, 0), (320, 184, 1, 1), (250, 130, 1, 0), (320, 184, 2, 0), (250, 130, 2, 1)])
+def test_hybrid_frames_stage_by_stage(gpu_ctx, small_scene, small_oracle, w, h, wavefront, fuse):
     ctx, sc, o = gpu_ctx, small_scene, small_oracle
     cam = sc.camera(w, h)
     ctx.set_camera(cam)
     ctx.set_params(vk.make_params(w, h)); ctx.reset_history()
     hist = None
     for frame in range(3):
-        p = vk.make_params(w, h, frame=frame, wavefront=wavefront)
+        p = vk.make_params(w, h, frame=frame, wavefront=wavefront, fuse_denoise=fuse)
         ctx.set_params(p)
         o.reset_counters()
         ref = o.hybrid_frame(cam, p, history=hist)
@@ -118,7 +118,8 @@ def test_hybrid_frames_stage_by_stage(gpu_ctx, small_scene, small_oracle, w, h, 
         assert np.array_equal(final.view(np.uint32), ref["final"].view(np.uint32))          # stronger than the bar: same bits
         assert np.array_equal(ctx.readback(PLANE.FINAL_SRGB8), o.post(p, ref["final"]))
         assert [c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow] == list(o.counters.rays)
-        assert c.kernel_launches == {0: 4, 1: 4 + 8, 2: 5}[wavefront]     # 1: + one k_bounce per bounce (8); 2: + k_chain
+        # gbuffer, shadow, [denoise], resolve; 1: + one k_bounce per bounce (8), never fused; 2: + k_chain
+        assert c.kernel_launches == {0: 4, 1: 4 + 8, 2: 5}[wavefront] - (1 if fuse and wavefront != 1 else 0)
 
 
 def test_stage_isolation(gpu_ctx, small_scene, small_oracle):

@@ -283,3 +283,26 @@ def test_error_behaviour():
     with pytest.raises(vk.VkpError):
         vk.Context(99)
     ctx.close()
+
+
+@pytest.mark.parametrize("scene_index,w,h,samples,faithful", [(1, 160, 96, 1, 1), (2, 192, 108, 1, 1), (3, 128, 72, 4, 0)])
+def test_other_scenes_match_the_oracle(scene_index, w, h, samples, faithful):
+    """Cornell scene (scene.cpp:162-272), the instanced stress scene (BASELINE configs[3], rotated / scaled instances, all
+    three shading models) and the 16-ring-light scene (configs[4]) at reduced detail: two Hybrid frames, bit for bit."""
+    sc = vk.HostScene(scene_index, detail=(4, 3, 4, 9))
+    ctx = vk.Context(0); ctx.upload_scene(sc)
+    o = Oracle(sc)
+    cam = sc.camera(w, h); ctx.set_camera(cam)
+    hist = None
+    for f in range(2):
+        p = vk.make_params(w, h, frame=f, shadow_samples=samples, faithful_rng=faithful)
+        ctx.set_params(p); ctx.render()
+        o.reset_counters()
+        ref = o.hybrid_frame(cam, p, history=hist); hist = ref["denoised"]
+        assert np.array_equal(ctx.readback(PLANE.HIT_IDS), ref["g"].hit_ids)
+        for l in range(len(sc.lights)):
+            assert np.array_equal(ctx.readback(PLANE.DENOISED0 + l), ref["denoised"][l]), (f, l)
+        assert np.array_equal(ctx.readback(PLANE.FINAL_F32).view(np.uint32), ref["final"].view(np.uint32)), f
+        c = ctx.counters()
+        assert [c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow] == list(o.counters.rays)
+    ctx.close(); sc.close(); o.close()

@@ -100,6 +100,9 @@ def load_vkp():
         "vkp_set_stream": (i, [vp, vp]),
         "vkp_eval_math": (i, [vp, i, vp, vp, u32, vp]),
         "vkp_trace_stats": (i, [vp, vp, u32, i, vp]),
+        "vkp_ipc_export_plane": (i, [vp, i, vp]),
+        "vkp_ipc_open": (i, [vp, vp, P(vp)]),
+        "vkp_set_output_redirect": (i, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -157,13 +160,14 @@ def load_host():
 
 
 def make_params(width, height, mode=MODE_HYBRID, spp=1, shadow_samples=1, max_bounces=8, frame=0, denoise_frame=None,
-                faithful_rng=1, denoise_cover_remainder=1, debug_target=0, wavefront=0):
+                faithful_rng=1, denoise_cover_remainder=1, debug_target=0, wavefront=0, fuse_denoise=0):
     p = T.Params()
     p.width, p.height, p.mode, p.spp, p.shadow_samples, p.max_bounces = width, height, mode, spp, shadow_samples, max_bounces
     p.frame = frame
     p.denoise_frame = frame if denoise_frame is None else denoise_frame
     p.faithful_rng, p.denoise_cover_remainder, p.debug_target = faithful_rng, denoise_cover_remainder, debug_target
     p.wavefront = wavefront
+    p.fuse_denoise = fuse_denoise
     return p
 
 
@@ -385,6 +389,20 @@ class Context:
         self._ck(self.L.vkp_trace_rays(self.h, rays.ctypes.data if len(rays) else None, len(rays), 1 if any_hit else 0,
                                        hits.ctypes.data if len(rays) else None), "vkp_trace_rays")
         return hits
+
+    def ipc_export_plane(self, plane):
+        h = (C.c_ubyte * 64)()
+        self._ck(self.L.vkp_ipc_export_plane(self.h, plane, h), "vkp_ipc_export_plane")
+        return bytes(h)
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._ck(self.L.vkp_ipc_open(self.h, buf, C.byref(p)), "vkp_ipc_open")
+        return p.value
+
+    def set_output_redirect(self, ptr):
+        self._ck(self.L.vkp_set_output_redirect(self.h, C.c_void_p(ptr) if ptr else None), "vkp_set_output_redirect")
 
     def trace_stats(self, rays, any_hit=False):
         rays = np.ascontiguousarray(rays, dtype=T.ray_dtype)

@@ -394,55 +394,57 @@ __global__ void __launch_bounds__(128, VKP_LB_SHADOW) k_shadow(const __grid_cons
     add_counter(F.counters, 1, nrays);
 }
 
-// blur.comp:35-82 with runtime W/H/NLIGHTS and an integer motion fetch
+// blur.comp:35-82 for one pixel and one light, with runtime W/H/NLIGHTS and an integer motion fetch; returns the new
+// R8 history value (pixels outside the faithful dispatch area keep their history)
+__device__ __forceinline__ uint8_t denoise_pixel(const DFrame& F, int l, int x, int y, size_t i, size_t plane)
+{
+    const int W = F.p.width, H = F.p.height;
+    const int frame = F.p.denoise_frame;
+    const int Wc = F.p.denoise_cover_remainder ? W : (W / 16) * 16;
+    const int Hc = F.p.denoise_cover_remainder ? H : (H / 16) * 16;
+    const uint8_t* in = F.shadow + l * plane;
+    const uint8_t* hist = F.denoised + l * plane;
+    if (!(x < Wc && y < Hc)) return hist[i];
+    float pixelColor;
+    if (frame > 0) {
+        float center = (float)in[i] / 255.0f;
+        float old = (float)hist[i] / 255.0f;
+        float a = 1.0f / (float)((float)frame + 1.0f);
+        pixelColor = mix1(old, center, a);
+    } else {
+        uint32_t m = F.motion[i];
+        float rx = vkp_f16_to_f32((uint16_t)(m & 0xffffu)) * 2.0f - 1.0f;
+        float lastx = (float)x + rx * (float)W, lasty = (float)y + rx * (float)H;   // blur.comp:53 (r.x twice)
+        float center = (float)in[i] / 255.0f;
+        float minColor = center, maxColor = center;
+#pragma unroll
+        for (int yy = -1; yy <= 1; yy++)
+#pragma unroll
+            for (int xx = -1; xx <= 1; xx++) {
+                if (xx == 0 && yy == 0) continue;
+                int qx = x + xx, qy = y + yy;
+                float c = (qx < 0 || qy < 0 || qx >= W || qy >= H) ? 0.0f : (float)in[(size_t)qy * W + qx] / 255.0f;
+                minColor = fminf(minColor, c); maxColor = fmaxf(maxColor, c);
+            }
+        float cx = fminf(fmaxf(lastx, -2147483000.0f), 2147483000.0f), cy = fminf(fmaxf(lasty, -2147483000.0f), 2147483000.0f);
+        if (cx != cx) cx = -1.0f;
+        if (cy != cy) cy = -1.0f;
+        int ix = (int)cx, iy = (int)cy;
+        float old = (ix < 0 || iy < 0 || ix >= W || iy >= H) ? 0.0f : (float)hist[(size_t)iy * W + ix] / 255.0f;
+        old = fmaxf(minColor, old);
+        old = fminf(maxColor, old);
+        pixelColor = mix1(old, center, 0.4f);
+    }
+    return vkp_unorm8(pixelColor);
+}
+
 __global__ void __launch_bounds__(128) k_denoise(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     const Pixel px = pixel_of_thread(F);
     if (!px.valid) return;
-    const int W = F.p.width, H = F.p.height;
-    const size_t i = (size_t)px.y * W + px.x;
-    const size_t plane = (size_t)W * H;
-    const int frame = F.p.denoise_frame;
-    const int Wc = F.p.denoise_cover_remainder ? W : (W / 16) * 16;
-    const int Hc = F.p.denoise_cover_remainder ? H : (H / 16) * 16;
-    const bool covered = px.x < Wc && px.y < Hc;
-    for (int l = 0; l < S.n_lights; l++) {
-        const uint8_t* in = F.shadow + l * plane;
-        const uint8_t* hist = F.denoised + l * plane;
-        uint8_t* out = F.denoised_next + l * plane;
-        if (!covered) { out[i] = hist[i]; continue; }
-        float pixelColor;
-        if (frame > 0) {
-            float center = (float)in[i] / 255.0f;
-            float old = (float)hist[i] / 255.0f;
-            float a = 1.0f / (float)((float)frame + 1.0f);
-            pixelColor = mix1(old, center, a);
-        } else {
-            uint32_t m = F.motion[i];
-            float rx = vkp_f16_to_f32((uint16_t)(m & 0xffffu)) * 2.0f - 1.0f;
-            float lastx = (float)px.x + rx * (float)W, lasty = (float)px.y + rx * (float)H;   // blur.comp:53 (r.x twice)
-            float center = (float)in[i] / 255.0f;
-            float minColor = center, maxColor = center;
-#pragma unroll
-            for (int yy = -1; yy <= 1; yy++)
-#pragma unroll
-                for (int xx = -1; xx <= 1; xx++) {
-                    if (xx == 0 && yy == 0) continue;
-                    int qx = px.x + xx, qy = px.y + yy;
-                    float c = (qx < 0 || qy < 0 || qx >= W || qy >= H) ? 0.0f : (float)in[(size_t)qy * W + qx] / 255.0f;
-                    minColor = fminf(minColor, c); maxColor = fmaxf(maxColor, c);
-                }
-            float cx = fminf(fmaxf(lastx, -2147483000.0f), 2147483000.0f), cy = fminf(fmaxf(lasty, -2147483000.0f), 2147483000.0f);
-            if (cx != cx) cx = -1.0f;
-            if (cy != cy) cy = -1.0f;
-            int ix = (int)cx, iy = (int)cy;
-            float old = (ix < 0 || iy < 0 || ix >= W || iy >= H) ? 0.0f : (float)hist[(size_t)iy * W + ix] / 255.0f;
-            old = fmaxf(minColor, old);
-            old = fminf(maxColor, old);
-            pixelColor = mix1(old, center, 0.4f);
-        }
-        out[i] = vkp_unorm8(pixelColor);
-    }
+    const size_t i = (size_t)px.y * F.p.width + px.x;
+    const size_t plane = (size_t)F.p.width * F.p.height;
+    for (int l = 0; l < S.n_lights; l++) F.denoised_next[l * plane + i] = denoise_pixel(F, l, px.x, px.y, i, plane);
 }
 
 // hybridRaygen.rgen:27-186
@@ -560,7 +562,13 @@ __global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_resolve(const __grid_co
         float3 rayColor = f3s(0.0f);
         // a background pixel with a diffuse material 0 traces nothing and ends as `albedo` (hybridRaygen.rgen:182-183): its light loop is dead code
         const int n_lights_eff = (background && shadingMode == 0) ? 0 : S.n_lights;
-        for (int l = 0; l < n_lights_eff; l++) {
+        // F.fused: the shadow filter (blur.comp) runs here, per light, instead of in its own pass over the frame; the new
+        // history goes to the other ping-pong buffer, so reprojected reads of the old history by other pixels stay valid
+        for (int l = 0; l < (F.fused ? S.n_lights : n_lights_eff); l++) {
+            uint8_t dq;
+            if (F.fused) { dq = denoise_pixel(F, l, px.x, px.y, i, plane); F.denoised_next[l * plane + i] = dq; }
+            else dq = F.denoised[l * plane + i];
+            if (l >= n_lights_eff) continue;
             const vkp_light light = S.lights[l];
             const float3 lpos = f3(light.position[0], light.position[1], light.position[2]);
             const float3 lcol = f3(light.color[0], light.color[1], light.color[2]);
@@ -571,7 +579,7 @@ __global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_resolve(const __grid_co
             const float light_intensity = isDirectional ? 1.0f : (light.color[3] / (light_distance * light_distance));
             L = normalize3(L);
             const float NdotL = clamp01(dot3(N, L));
-            const float shadowFactor = (float)F.denoised[l * plane + i] / 255.0f;
+            const float shadowFactor = (float)dq / 255.0f;
             if (NdotL > 0.0f) {
                 if (light_intensity == 0.0f) attenuation = 0.0f;
                 else {

@@ -49,6 +49,8 @@ struct vkp_ctx {
     cudaStream_t chain_stream = nullptr;
     cudaEvent_t ev_gbuffer = nullptr, ev_chain = nullptr;
     bool chain_in_flight = false;
+    void* peer_srgb8 = nullptr;          // multi-GPU: FINAL_SRGB8 is written straight into rank 0's image over NVLink (vkp_set_output_redirect)
+    std::vector<void*> ipc_opened;
 
     bool profiling = false;
     cudaEvent_t ev[12]{};
@@ -183,10 +185,12 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.tile_w = ctx->tile_w; F.tile_h = ctx->tile_h;
     F.tiles_x = (F.p.width + F.tile_w - 1) / F.tile_w; F.tiles_y = (F.p.height + F.tile_h - 1) / F.tile_h;
     F.rank = ctx->rank; F.world = ctx->world;
+    F.fused = 0;
     F.static_camera = memcmp(F.cam.view, F.cam.prev_view, 64) == 0 && memcmp(F.cam.proj, F.cam.prev_proj, 64) == 0;
     F.position = ctx->position.as<uint2>(); F.normal = ctx->normal.as<uint2>(); F.albedo = ctx->albedo.as<uchar4>();
     F.motion = ctx->motion.as<uint32_t>(); F.material = ctx->material.as<uchar4>(); F.emissive = ctx->emissive.as<uchar4>();
-    F.hit_ids = ctx->hit_ids.as<int2>(); F.final_f32 = ctx->final_f32.as<float4>(); F.final_srgb8 = ctx->final_srgb8.as<uchar4>();
+    F.hit_ids = ctx->hit_ids.as<int2>(); F.final_f32 = ctx->final_f32.as<float4>();
+    F.final_srgb8 = ctx->peer_srgb8 ? reinterpret_cast<uchar4*>(ctx->peer_srgb8) : ctx->final_srgb8.as<uchar4>();
     F.shadow = ctx->shadow.as<uint8_t>();
     F.denoised = ctx->denoised[ctx->denoised_cur].as<uint8_t>();
     F.denoised_next = ctx->denoised[ctx->denoised_cur ^ 1].as<uint8_t>();
@@ -231,7 +235,12 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
         const bool chain2 = L.frame.p.wavefront == 2 && L.frame.p.max_bounces <= VKP_CHAIN_MAX;
         if (chain2 && !ctx->chain_in_flight) { CK(launch_chain(L, ctx->stream)); ctx->last_launches++; }      // stand-alone stage: serial
         if (chain2 && ctx->chain_in_flight) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0)); ctx->chain_in_flight = false; }
-        CK(launch_resolve(L, &n)); ctx->last_launches += (uint32_t)n - 1u;
+        CK(launch_resolve(L, &n));
+        if (L.frame.fused) {
+            ctx->denoised_cur ^= 1;             // the fused filter wrote the other ping-pong buffer
+            L.frame.denoised = ctx->denoised[ctx->denoised_cur].as<uint8_t>();
+            L.frame.denoised_next = ctx->denoised[ctx->denoised_cur ^ 1].as<uint8_t>();
+        } ctx->last_launches += (uint32_t)n - 1u;
         break;
     }
     case VKP_STAGE_POST: CK(launch_post(L)); break;
@@ -298,6 +307,7 @@ void vkp_destroy(vkp_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
     for (auto& m : ctx->meshes) { m->verts.release(); m->idx.release(); }
     for (auto& t : ctx->textures) t->texels.release();
     for (auto& b : ctx->blas) b->bvh.release();
@@ -512,9 +522,13 @@ int vkp_render(vkp_ctx* ctx)
     ctx->n_ev = 0; ctx->last_launches = 0;
     CK(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
     static const int hybrid[] = {VKP_STAGE_GBUFFER, VKP_STAGE_SHADOW, VKP_STAGE_DENOISE, VKP_STAGE_RESOLVE};
+    static const int hybrid_fused[] = {VKP_STAGE_GBUFFER, VKP_STAGE_SHADOW, VKP_STAGE_RESOLVE};
     static const int rt[] = {VKP_STAGE_RAYTRACE};
     static const int deferred[] = {VKP_STAGE_GBUFFER, VKP_STAGE_DEFERRED};
     const int* seq = hybrid; int n = 4;
+    // the wavefront variant re-reads the resolve inputs per bounce; it keeps the stand-alone filter pass
+    const bool fused = ctx->params.mode == VKP_MODE_HYBRID && ctx->params.fuse_denoise != 0 && ctx->params.wavefront != 1;
+    if (fused) { seq = hybrid_fused; n = 3; L.frame.fused = 1; }
     if (ctx->params.mode == VKP_MODE_RAYTRACING) { seq = rt; n = 1; }
     else if (ctx->params.mode == VKP_MODE_DEFERRED) { seq = deferred; n = 2; }
     for (int i = 0; i < n; i++) {
@@ -610,6 +624,37 @@ int vkp_plane_device_ptr(vkp_ctx* ctx, int plane, void** device_ptr, size_t* byt
     if (!p) return fail(ctx, VKP_ERR_INVALID, "vkp_plane_device_ptr: unknown plane");
     *device_ptr = p;
     if (bytes) *bytes = plane_elem_bytes(plane) * (size_t)ctx->plane_w * ctx->plane_h;
+    return VKP_OK;
+}
+
+int vkp_ipc_export_plane(vkp_ctx* ctx, int plane, void* handle64)
+{
+    if (!ctx || !handle64) return VKP_ERR_INVALID;
+    int r = ensure_planes(ctx);
+    if (r != VKP_OK) return r;
+    void* p = plane_ptr(ctx, plane);
+    if (!p) return fail(ctx, VKP_ERR_INVALID, "vkp_ipc_export_plane: unknown plane");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), p));
+    return VKP_OK;
+}
+
+int vkp_ipc_open(vkp_ctx* ctx, const void* handle64, void** device_ptr)
+{
+    if (!ctx || !handle64 || !device_ptr) return VKP_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    CK(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->ipc_opened.push_back(*device_ptr);
+    return VKP_OK;
+}
+
+int vkp_set_output_redirect(vkp_ctx* ctx, void* peer_final_srgb8)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->peer_srgb8 = peer_final_srgb8;
     return VKP_OK;
 }
 

@@ -38,6 +38,21 @@ class TiledRenderer:
             ctx.set_stream(self.stream.cuda_stream)
         self._bufs = {}
         self.collectives = 0
+        self.peer_output = False
+
+    def enable_peer_output(self):
+        """Composite of FINAL_SRGB8 without a gather: every rank's resolve kernel stores its pixels straight into rank 0's
+        image over NVLink peer memory (CUDA IPC); a frame then only needs a barrier.  NCCL backend, one GPU per rank."""
+        import torch.distributed as dist
+        if self.world == 1 or self.backend != "nccl":
+            return False
+        box = [self.ctx.ipc_export_plane(PLANE.FINAL_SRGB8) if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=self.group)
+        if self.rank != 0:
+            self.ctx.set_output_redirect(self.ctx.ipc_open(box[0]))
+        self._flag = self.torch.zeros(1, dtype=self.torch.int32, device=self.device)
+        self.peer_output = True
+        return True
 
     # ---- helpers -------------------------------------------------------------------------------------------
     def _sizes(self, plane):
@@ -101,6 +116,17 @@ class TiledRenderer:
         kernels launched on this rank."""
         import torch.distributed as dist
         if self.world == 1:
+            return 0
+        if self.peer_output and plane == PLANE.FINAL_SRGB8:
+            # the pixels are already in rank 0's image; a 4-byte all-reduce is the completion barrier (stream-ordered)
+            if self.stream_ordered:
+                with self.torch.cuda.stream(self.stream):
+                    dist.all_reduce(self._flag, group=self.group)
+            else:
+                self.ctx.sync()
+                dist.all_reduce(self._flag, group=self.group)
+                self.torch.cuda.synchronize(self.device)
+            self.collectives += 1
             return 0
         sizes = self._sizes(plane)
         pad = max(sizes)
