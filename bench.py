@@ -347,7 +347,9 @@ def main():
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get(dname)
+            tj = json.load(open(prof))
+            roofline["traffic"] = tj.get(dname, tj.get(dname + "<2>"))
+            roofline["traffic_source"] = tj.get("_source")
         except Exception:
             pass
 

@@ -122,6 +122,9 @@ VKP_API int vkp_tiles_unpack(vkp_ctx* ctx, int plane, int rank, int world, const
 VKP_API int vkp_ipc_export_plane(vkp_ctx* ctx, int plane, void* handle64);
 VKP_API int vkp_ipc_open(vkp_ctx* ctx, const void* handle64, void** device_ptr);
 VKP_API int vkp_set_output_redirect(vkp_ctx* ctx, void* peer_final_srgb8);
+/* build-primitive probe (tests): stable radix sort of (keys[i], i) on bits [0, end_bit) and an exclusive 64-bit prefix sum of
+ * ((keys[i] & 1) << 32 | (keys[i] & 3)) with the BVH builder's own kernels (bvh_sort.cuh) */
+VKP_API int vkp_selftest_sort(vkp_ctx* ctx, const uint32_t* keys, uint32_t n, int end_bit, uint32_t* sorted_keys, uint32_t* sorted_vals, uint64_t* scan);
 /* numerics-contract probe (tests): evaluate one vkp_detmath.h function on the DEVICE over host arrays.
  * func: 0 sin, 1 cos, 2 atan2(x,y), 3 asin, 4 pow(x,y), 5 log2, 6 exp2, 7 f32->f16->f32, 8 unorm8 */
 VKP_API int vkp_eval_math(vkp_ctx* ctx, int func, const float* x, const float* y, uint32_t n, float* out);

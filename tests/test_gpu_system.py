@@ -306,3 +306,18 @@ def test_other_scenes_match_the_oracle(scene_index, w, h, samples, faithful):
         c = ctx.counters()
         assert [c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow] == list(o.counters.rays)
     ctx.close(); sc.close(); o.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 2048, 2049, 100003, 1 << 20])
+def test_build_primitives_sort_and_scan(n):
+    """The BVH builder's own radix sort (stable, warp-level ranking) and prefix sum against numpy."""
+    ctx = vk.Context(0)
+    rng = np.random.default_rng(n)
+    for keys, bits in ((rng.integers(0, 1 << 30, size=n, dtype=np.uint32), 30), (rng.integers(0, 7, size=n, dtype=np.uint32), 30),
+                       (rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32), 32)):
+        sk, sv, sc = ctx.selftest_sort(keys, bits)
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(sk, keys[order]) and np.array_equal(sv, order.astype(np.uint32))
+        wide = ((keys.astype(np.uint64) & 1) << np.uint64(32)) | (keys.astype(np.uint64) & 3)
+        assert np.array_equal(sc, np.concatenate([[0], np.cumsum(wide)[:-1]]).astype(np.uint64))
+    ctx.close()

@@ -100,6 +100,7 @@ def load_vkp():
         "vkp_set_stream": (i, [vp, vp]),
         "vkp_eval_math": (i, [vp, i, vp, vp, u32, vp]),
         "vkp_trace_stats": (i, [vp, vp, u32, i, vp]),
+        "vkp_selftest_sort": (i, [vp, vp, u32, i, vp, vp, vp]),
         "vkp_ipc_export_plane": (i, [vp, i, vp]),
         "vkp_ipc_open": (i, [vp, vp, P(vp)]),
         "vkp_set_output_redirect": (i, [vp, vp]),
@@ -389,6 +390,12 @@ class Context:
         self._ck(self.L.vkp_trace_rays(self.h, rays.ctypes.data if len(rays) else None, len(rays), 1 if any_hit else 0,
                                        hits.ctypes.data if len(rays) else None), "vkp_trace_rays")
         return hits
+
+    def selftest_sort(self, keys, end_bit=32):
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        sk = np.empty_like(keys); sv = np.empty_like(keys); sc = np.empty(len(keys), dtype=np.uint64)
+        self._ck(self.L.vkp_selftest_sort(self.h, keys.ctypes.data, len(keys), end_bit, sk.ctypes.data, sv.ctypes.data, sc.ctypes.data), "vkp_selftest_sort")
+        return sk, sv, sc
 
     def ipc_export_plane(self, plane):
         h = (C.c_ubyte * 64)()

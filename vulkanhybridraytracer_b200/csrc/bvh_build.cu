@@ -1,14 +1,14 @@
 // bvh_build.cu -- acceleration-structure build on the GPU: what vkCmdBuildAccelerationStructuresKHR does for the
 // reference (renderer.cpp:1747 buildBlas, :1853 buildTlas / MODE_UPDATE refit).
 //
-// Morton-code LBVH (Karras 2012): primitive boxes -> centroid bounds -> 30-bit Morton keys -> radix sort ->
+// Morton-code LBVH (Karras 2012): primitive boxes -> centroid bounds -> 30-bit Morton keys -> radix sort (own warp-level
+// LSD sort, bvh_sort.cuh) ->
 // binary radix tree (one thread per internal node) -> bottom-up AABB fit with atomic arrival flags ->
 // collapse sub-trees of <= leaf_max primitives into leaves and emit the 32-byte sibling-pair node array
 // described in vkp_bvh.cuh.  Refit re-runs only fit + emit on the stored topology.
 #include "vkp_internal.h"
 
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include "bvh_sort.cuh"
 #include <math_constants.h>
 
 namespace {
@@ -466,9 +466,7 @@ static cudaError_t ploc_hierarchy(cudaStream_t s, BuildScratch& sc, Bvh& B, int*
     if ((e = sc.ploc_icnt.ensure(sizeof(uint32_t) * (size_t)n)) != cudaSuccess) return e;
     if ((e = sc.vals_alt.ensure(sizeof(uint32_t) * (size_t)n)) != cudaSuccess) return e;
     if ((e = sc.ploc_parent.ensure(sizeof(int) * (2 * (size_t)n))) != cudaSuccess) return e;
-    size_t tmp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp, sc.ploc_flags.as<unsigned long long>(), sc.ploc_scan.as<unsigned long long>(), n, s);
-    if ((e = sc.cub_tmp.ensure(tmp)) != cudaSuccess) return e;
+    if ((e = sc.cub_tmp.ensure(vkpsort::scan_scratch_bytes((uint32_t)n, sizeof(unsigned long long)))) != cudaSuccess) return e;
 
     k_ploc_init<<<blocks_for(n, 256), 256, 0, s>>>(sc.boxes.as<float>(), B.items.as<uint32_t>(), n, sc.ploc_cid[0].as<int>(), sc.ploc_box[0].as<float4>(), sc.ploc_cnt[0].as<uint32_t>());
     int cur = 0, n_cur = n, node_base = 0, iters = 0;
@@ -476,8 +474,8 @@ static cudaError_t ploc_hierarchy(cudaStream_t s, BuildScratch& sc, Bvh& B, int*
         const int nxt = cur ^ 1;
         k_ploc_nn<<<blocks_for(n_cur, PLOC_BS), PLOC_BS, 0, s>>>(sc.ploc_box[cur].as<float4>(), n_cur, sc.ploc_nn.as<int>());
         k_ploc_mark<<<blocks_for(n_cur, 256), 256, 0, s>>>(sc.ploc_nn.as<int>(), n_cur, sc.ploc_flags.as<unsigned long long>());
-        size_t tb = sc.cub_tmp.bytes;
-        if ((e = cub::DeviceScan::ExclusiveSum(sc.cub_tmp.p, tb, sc.ploc_flags.as<unsigned long long>(), sc.ploc_scan.as<unsigned long long>(), n_cur, s)) != cudaSuccess) return e;
+        if ((e = vkpsort::exclusive_scan<unsigned long long>(s, sc.ploc_flags.as<unsigned long long>(), sc.ploc_scan.as<unsigned long long>(), (uint32_t)n_cur,
+                                                             sc.cub_tmp.p, launches)) != cudaSuccess) return e;
         k_ploc_merge<<<blocks_for(n_cur, 256), 256, 0, s>>>(sc.ploc_nn.as<int>(), sc.ploc_flags.as<unsigned long long>(), sc.ploc_scan.as<unsigned long long>(), n_cur, node_base,
                                                          sc.ploc_cid[cur].as<int>(), sc.ploc_box[cur].as<float4>(), sc.ploc_cnt[cur].as<uint32_t>(),
                                                          sc.ploc_cid[nxt].as<int>(), sc.ploc_box[nxt].as<float4>(), sc.ploc_cnt[nxt].as<uint32_t>(), n,
@@ -490,7 +488,7 @@ static cudaError_t ploc_hierarchy(cudaStream_t s, BuildScratch& sc, Bvh& B, int*
         const int merges = (int)(tot >> 32), survivors = (int)(tot & 0xffffffffull);
         if (merges <= 0) return cudaErrorUnknown;              // cannot happen: the globally closest pair is always mutual
         node_base += merges; n_cur = survivors; cur = nxt;
-        if (launches) *launches += 4;
+        if (launches) *launches += 3;
         if (++iters > 4096) return cudaErrorUnknown;
     }
     // root = the single remaining cluster (an internal node because n >= 2)
@@ -541,15 +539,12 @@ cudaError_t bvh_build(cudaStream_t s, BuildScratch& sc, uint32_t n, int leaf_max
     k_morton<<<blocks_for(n, 256), 256, 0, s>>>(sc.boxes.as<float>(), n, sc.bounds.as<int>(), sc.keys.as<uint32_t>(), sc.vals.as<uint32_t>());
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, sc.keys.as<uint32_t>(), sc.keys_alt.as<uint32_t>(), sc.vals.as<uint32_t>(), B.items.as<uint32_t>(), (int)n, 0, 30, s);
-    size_t tmp2 = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, B.keep.as<uint32_t>(), B.rank.as<uint32_t>(), (int)ni, s);
-    if (tmp2 > tmp) tmp = tmp2;
-    if ((e = sc.cub_tmp.ensure(tmp)) != cudaSuccess) return e;
-    size_t tbytes = sc.cub_tmp.bytes;
-    if ((e = cub::DeviceRadixSort::SortPairs(sc.cub_tmp.p, tbytes, sc.keys.as<uint32_t>(), sc.keys_alt.as<uint32_t>(), sc.vals.as<uint32_t>(),
-                                             B.items.as<uint32_t>(), (int)n, 0, 30, s)) != cudaSuccess) return e;
+    {
+        size_t need = vkpsort::sort_scratch_bytes(n), need2 = vkpsort::scan_scratch_bytes(n, sizeof(unsigned long long));
+        if ((e = sc.cub_tmp.ensure(need > need2 ? need : need2)) != cudaSuccess) return e;
+    }
+    if ((e = vkpsort::sort_pairs(s, sc.keys.as<uint32_t>(), sc.vals.as<uint32_t>(), sc.keys_alt.as<uint32_t>(), B.items.as<uint32_t>(), n, 30, sc.cub_tmp.p,
+                                 launches)) != cudaSuccess) return e;
     B.root = 0;
     bool fitted = false;
     if (builder == 1) {
@@ -560,9 +555,8 @@ cudaError_t bvh_build(cudaStream_t s, BuildScratch& sc, uint32_t n, int leaf_max
     }
     k_mark_keep<<<blocks_for(ni, 256), 256, 0, s>>>(B.range.as<int2>(), (int)ni, leaf_max, B.keep.as<uint32_t>());
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    tbytes = sc.cub_tmp.bytes;
-    if ((e = cub::DeviceScan::ExclusiveSum(sc.cub_tmp.p, tbytes, B.keep.as<uint32_t>(), B.rank.as<uint32_t>(), (int)ni, s)) != cudaSuccess) return e;
-    if (launches) *launches += 8;   // own kernels + the sort / scan passes
+    if ((e = vkpsort::exclusive_scan<uint32_t>(s, B.keep.as<uint32_t>(), B.rank.as<uint32_t>(), ni, sc.cub_tmp.p, launches)) != cudaSuccess) return e;
+    if (launches) *launches += 5;
     // number of emitted nodes = 1 + 2 * (#kept internals)
     uint32_t last_rank = 0, last_keep = 0;
     if ((e = cudaMemcpyAsync(&last_rank, B.rank.as<uint32_t>() + (ni - 1), 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
@@ -587,4 +581,32 @@ cudaError_t bvh_emit_triangles(cudaStream_t s, const vkp_vertex* verts, const ui
     if (B.n_prims == 0) return cudaMemsetAsync(B.tris.p, 0, sizeof(float4) * 3, s);   // one degenerate triangle: det == 0, never hit
     k_emit_triangles<<<blocks_for(B.n_prims, 256), 256, 0, s>>>(verts, indices, B.items.as<uint32_t>(), B.n_prims, B.tris.as<float4>());
     return cudaGetLastError();
+}
+
+// test hook (vkp_selftest_sort): sort host keys with the build's own radix sort and scan them with its own prefix sum
+cudaError_t bvh_selftest_sort(cudaStream_t s, const uint32_t* keys_host, uint32_t n, int end_bit, uint32_t* keys_sorted_host, uint32_t* vals_sorted_host,
+                              unsigned long long* scan_host)
+{
+    if (n == 0) return cudaSuccess;
+    DevBuf k0, v0, k1, v1, tmp, in64, out64;
+    cudaError_t e;
+    std::vector<uint32_t> iota(n);
+    for (uint32_t i = 0; i < n; i++) iota[i] = i;
+    std::vector<unsigned long long> wide(n);
+    for (uint32_t i = 0; i < n; i++) wide[i] = ((unsigned long long)(keys_host[i] & 1u) << 32) | (unsigned long long)(keys_host[i] & 3u);
+    size_t need = vkpsort::sort_scratch_bytes(n), need2 = vkpsort::scan_scratch_bytes(n, 8);
+    if ((e = k0.ensure(4 * (size_t)n)) != cudaSuccess || (e = v0.ensure(4 * (size_t)n)) != cudaSuccess || (e = k1.ensure(4 * (size_t)n)) != cudaSuccess ||
+        (e = v1.ensure(4 * (size_t)n)) != cudaSuccess || (e = tmp.ensure(need > need2 ? need : need2)) != cudaSuccess || (e = in64.ensure(8 * (size_t)n)) != cudaSuccess ||
+        (e = out64.ensure(8 * (size_t)n)) != cudaSuccess) return e;
+    cudaMemcpyAsync(k0.p, keys_host, 4 * (size_t)n, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(v0.p, iota.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(in64.p, wide.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, s);
+    if ((e = vkpsort::sort_pairs(s, k0.as<uint32_t>(), v0.as<uint32_t>(), k1.as<uint32_t>(), v1.as<uint32_t>(), n, end_bit, tmp.p, nullptr)) != cudaSuccess) return e;
+    cudaMemcpyAsync(keys_sorted_host, k1.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(vals_sorted_host, v1.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, s);
+    if ((e = vkpsort::exclusive_scan<unsigned long long>(s, in64.as<unsigned long long>(), out64.as<unsigned long long>(), n, tmp.p, nullptr)) != cudaSuccess) return e;
+    cudaMemcpyAsync(scan_host, out64.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, s);
+    e = cudaStreamSynchronize(s);
+    k0.release(); v0.release(); k1.release(); v1.release(); tmp.release(); in64.release(); out64.release();
+    return e;
 }

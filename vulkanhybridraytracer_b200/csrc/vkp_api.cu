@@ -727,6 +727,14 @@ int vkp_trace_stats(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, 
     return VKP_OK;
 }
 
+int vkp_selftest_sort(vkp_ctx* ctx, const uint32_t* keys, uint32_t n, int end_bit, uint32_t* sorted_keys, uint32_t* sorted_vals, uint64_t* scan)
+{
+    if (!ctx || (n && (!keys || !sorted_keys || !sorted_vals || !scan))) return fail(ctx, VKP_ERR_INVALID, "vkp_selftest_sort: NULL");
+    CK(cudaSetDevice(ctx->device));
+    CK(bvh_selftest_sort(ctx->stream, keys, n, end_bit, sorted_keys, sorted_vals, reinterpret_cast<unsigned long long*>(scan)));
+    return VKP_OK;
+}
+
 int vkp_eval_math(vkp_ctx* ctx, int func, const float* x, const float* y, uint32_t n, float* out)
 {
     if (!ctx || (n && (!x || !y || !out))) return fail(ctx, VKP_ERR_INVALID, "vkp_eval_math: NULL");

@@ -66,6 +66,8 @@ cudaError_t bvh_triangle_boxes(cudaStream_t s, const vkp_vertex* verts, const ui
 cudaError_t bvh_instance_boxes(cudaStream_t s, const DInstance* inst, uint32_t n, float* boxes);
 cudaError_t bvh_build(cudaStream_t s, BuildScratch& scratch, uint32_t n_prims, int leaf_max, Bvh& out, int* launches, int builder /*0 LBVH (Karras), 1 PLOC*/);
 cudaError_t bvh_refit(cudaStream_t s, BuildScratch& scratch, Bvh& bvh, int* launches);
+cudaError_t bvh_selftest_sort(cudaStream_t s, const uint32_t* keys_host, uint32_t n, int end_bit, uint32_t* keys_sorted_host, uint32_t* vals_sorted_host,
+                              unsigned long long* scan_host);
 cudaError_t bvh_emit_triangles(cudaStream_t s, const vkp_vertex* verts, const uint32_t* indices, Bvh& bvh);
 
 // kernels_frame.cu
