@@ -109,7 +109,8 @@ def oracle_leg(scene, W, H, mode, spp, samples, faithful, budget_s, steps, warmu
         return dt, c[1] + c[2] + c[3], c[0]
 
     # calibrate on a sparse sample, then pick the row stride so that (steps + warmup) samples fit the budget
-    stride = 64 if mode == 2 else 270
+    stride = 16 if mode == 2 else 270
+    one(1, stride)                                  # first touch (page faults, OpenMP team start-up)
     dt, _, _ = one(1, stride)
     per_row = dt / max(1, H // stride)
     rows = max(8, min(H, int(budget_s / max(1, steps + warmup) / max(per_row, 1e-9))))

@@ -118,10 +118,13 @@ VKP_API int vkp_tiles_pack(vkp_ctx* ctx, int plane, void* device_dst, size_t byt
 VKP_API int vkp_tiles_unpack(vkp_ctx* ctx, int plane, int rank, int world, const void* device_src, size_t bytes);
 /* multi-GPU composite without a gather: rank 0 exports its FINAL_SRGB8 plane (64-byte CUDA IPC handle), the other ranks
  * open it and redirect their own FINAL_SRGB8 stores to it, so the resolve kernels write finished pixels straight into
- * rank 0's image over NVLink; the only per-frame collective left is a barrier.  NULL restores the local plane. */
+ * rank 0's image over NVLink; the only per-frame collective left is a barrier.  NULL restores the local planes. */
 VKP_API int vkp_ipc_export_plane(vkp_ctx* ctx, int plane, void* handle64);
 VKP_API int vkp_ipc_open(vkp_ctx* ctx, const void* handle64, void** device_ptr);
-VKP_API int vkp_set_output_redirect(vkp_ctx* ctx, void* peer_final_srgb8);
+VKP_API int vkp_set_output_redirect(vkp_ctx* ctx, void* peer_buffer0, void* peer_buffer1);
+/* FINAL_SRGB8 is double-buffered: select which buffer (0 / 1) the next frame writes and vkp_readback / export read.  With peer
+ * stores, alternating per frame lets rank 0 consume frame k while the peers already write frame k+1 (one barrier per frame). */
+VKP_API int vkp_set_output_buffer(vkp_ctx* ctx, int which);
 /* build-primitive probe (tests): stable radix sort of (keys[i], i) on bits [0, end_bit) and an exclusive 64-bit prefix sum of
  * ((keys[i] & 1) << 32 | (keys[i] & 3)) with the BVH builder's own kernels (bvh_sort.cuh) */
 VKP_API int vkp_selftest_sort(vkp_ctx* ctx, const uint32_t* keys, uint32_t n, int end_bit, uint32_t* sorted_keys, uint32_t* sorted_vals, uint64_t* scan);

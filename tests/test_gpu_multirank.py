@@ -38,13 +38,16 @@ def _worker(rank, world, port, q):
     ctx = vk.Context(0); ctx.upload_scene(sc)
     tr = TiledRenderer(ctx, rank, world, len(sc.lights), tile=(16, 8), backend="gloo", device=torch.device("cuda", 0))
     outs = []
+    ctx.set_params(vk.make_params(W, H))
+    assert tr.enable_peer_output()          # sRGB8 pixels go straight into rank 0's plane through CUDA IPC peer memory
     for cam, p in frame_sequence(vk, sc):
         ctx.set_camera(cam)
         tr.render(p)
-        tr.composite(PLANE.FINAL_F32)
+        tr.composite(PLANE.FINAL_F32)       # pack + gather + unpack
         tr.composite(PLANE.DENOISED0 + 1)
+        tr.composite(PLANE.FINAL_SRGB8)     # barrier only
         if rank == 0:
-            outs.append((ctx.readback(PLANE.FINAL_F32).copy(), ctx.readback(PLANE.DENOISED0 + 1).copy()))
+            outs.append((ctx.readback(PLANE.FINAL_F32).copy(), ctx.readback(PLANE.DENOISED0 + 1).copy(), ctx.readback(PLANE.FINAL_SRGB8).copy()))
     if rank == 0:
         q.put(outs)
     dist.barrier()
@@ -62,7 +65,7 @@ def test_multirank_frames_are_bit_identical_to_one_gpu(world):
     ref = []
     for cam, p in frame_sequence(vk, sc):
         ctx.set_camera(cam); ctx.set_params(p); ctx.render()
-        ref.append((ctx.readback(PLANE.FINAL_F32).copy(), ctx.readback(PLANE.DENOISED0 + 1).copy()))
+        ref.append((ctx.readback(PLANE.FINAL_F32).copy(), ctx.readback(PLANE.DENOISED0 + 1).copy(), ctx.readback(PLANE.FINAL_SRGB8).copy()))
     ctx.close(); sc.close()
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
@@ -75,6 +78,7 @@ def test_multirank_frames_are_bit_identical_to_one_gpu(world):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert len(outs) == len(ref)
-    for k, ((f, d), (rf, rd)) in enumerate(zip(outs, ref)):
+    for k, ((f, d, g), (rf, rd, rg)) in enumerate(zip(outs, ref)):
         assert np.array_equal(d, rd), f"denoised plane differs on frame {k}"
         assert np.array_equal(f.view(np.uint32), rf.view(np.uint32)), f"final image differs on frame {k}"
+        assert np.array_equal(g, rg), f"peer-written sRGB8 image differs on frame {k}"

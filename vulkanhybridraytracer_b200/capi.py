@@ -103,7 +103,8 @@ def load_vkp():
         "vkp_selftest_sort": (i, [vp, vp, u32, i, vp, vp, vp]),
         "vkp_ipc_export_plane": (i, [vp, i, vp]),
         "vkp_ipc_open": (i, [vp, vp, P(vp)]),
-        "vkp_set_output_redirect": (i, [vp, vp]),
+        "vkp_set_output_redirect": (i, [vp, vp, vp]),
+        "vkp_set_output_buffer": (i, [vp, i]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -408,8 +409,11 @@ class Context:
         self._ck(self.L.vkp_ipc_open(self.h, buf, C.byref(p)), "vkp_ipc_open")
         return p.value
 
-    def set_output_redirect(self, ptr):
-        self._ck(self.L.vkp_set_output_redirect(self.h, C.c_void_p(ptr) if ptr else None), "vkp_set_output_redirect")
+    def set_output_redirect(self, ptr0, ptr1):
+        self._ck(self.L.vkp_set_output_redirect(self.h, C.c_void_p(ptr0) if ptr0 else None, C.c_void_p(ptr1) if ptr1 else None), "vkp_set_output_redirect")
+
+    def set_output_buffer(self, which):
+        self._ck(self.L.vkp_set_output_buffer(self.h, which), "vkp_set_output_buffer")
 
     def trace_stats(self, rays, any_hit=False):
         rays = np.ascontiguousarray(rays, dtype=T.ray_dtype)

@@ -49,7 +49,11 @@ struct vkp_ctx {
     cudaStream_t chain_stream = nullptr;
     cudaEvent_t ev_gbuffer = nullptr, ev_chain = nullptr;
     bool chain_in_flight = false;
-    void* peer_srgb8 = nullptr;          // multi-GPU: FINAL_SRGB8 is written straight into rank 0's image over NVLink (vkp_set_output_redirect)
+    // multi-GPU: FINAL_SRGB8 is double-buffered (vkp_set_output_buffer) and may be redirected into rank 0's two buffers over NVLink
+    // (vkp_set_output_redirect): frame k+1 is written to the other buffer while rank 0 still consumes frame k
+    void* peer_srgb8[2] = {nullptr, nullptr};
+    DevBuf final_srgb8_alt;
+    int out_sel = 0;
     std::vector<void*> ipc_opened;
 
     bool profiling = false;
@@ -104,7 +108,7 @@ void* plane_ptr(vkp_ctx* c, int plane)
     case VKP_PLANE_EMISSIVE: return c->emissive.p;
     case VKP_PLANE_HIT_IDS: return c->hit_ids.p;
     case VKP_PLANE_FINAL_F32: return c->final_f32.p;
-    case VKP_PLANE_FINAL_SRGB8: return c->final_srgb8.p;
+    case VKP_PLANE_FINAL_SRGB8: return c->out_sel ? c->final_srgb8_alt.p : c->final_srgb8.p;
     default: break;
     }
     if (plane >= VKP_PLANE_SHADOW0 && plane < VKP_PLANE_SHADOW0 + c->plane_lights) return c->shadow.as<uint8_t>() + px * (plane - VKP_PLANE_SHADOW0);
@@ -121,7 +125,7 @@ int ensure_planes(vkp_ctx* ctx)
     const size_t px = (size_t)W * H;
     CK(ctx->position.ensure(px * 8)); CK(ctx->normal.ensure(px * 8)); CK(ctx->albedo.ensure(px * 4)); CK(ctx->motion.ensure(px * 4));
     CK(ctx->material.ensure(px * 4)); CK(ctx->emissive.ensure(px * 4)); CK(ctx->hit_ids.ensure(px * 8));
-    CK(ctx->final_f32.ensure(px * 16)); CK(ctx->final_srgb8.ensure(px * 4));
+    CK(ctx->final_f32.ensure(px * 16)); CK(ctx->final_srgb8.ensure(px * 4)); CK(ctx->final_srgb8_alt.ensure(px * 4));
     CK(ctx->shadow.ensure(px * L)); CK(ctx->denoised[0].ensure(px * L)); CK(ctx->denoised[1].ensure(px * L));
     CK(ctx->counters.ensure(64));
     CK(ctx->path_q[0].ensure(px * sizeof(PathItem))); CK(ctx->path_q[1].ensure(px * sizeof(PathItem)));
@@ -134,6 +138,7 @@ int ensure_planes(vkp_ctx* ctx)
     CK(cudaMemsetAsync(ctx->material.p, 0, px * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->emissive.p, 0, px * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->hit_ids.p, 0xff, px * 8, ctx->stream));
     CK(cudaMemsetAsync(ctx->final_f32.p, 0, px * 16, ctx->stream)); CK(cudaMemsetAsync(ctx->final_srgb8.p, 0, px * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->final_srgb8_alt.p, 0, px * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->shadow.p, 0, px * L, ctx->stream));
     CK(cudaMemsetAsync(ctx->denoised[0].p, 0, px * L, ctx->stream)); CK(cudaMemsetAsync(ctx->denoised[1].p, 0, px * L, ctx->stream));
     CK(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
@@ -161,8 +166,7 @@ int make_scene(vkp_ctx* ctx, DScene& S)
     int r = upload_textures(ctx);
     if (r != VKP_OK) return r;
     S.lut_pow22 = ctx->luts.as<float>();
-    S.tlas_nodes = ctx->tlas.nodes.as<vkp_bvh_node>();
-    S.tlas_items = ctx->tlas.items.as<uint32_t>();
+    S.tlas_nodes4 = ctx->tlas.nodes4.as<float4>(); S.tlas_root_ref = ctx->tlas.root_ref4;
     S.instances = ctx->d_instances.as<DInstance>();
     S.inst_trav = ctx->d_inst_trav.as<DInstTrav>();
     S.materials = ctx->d_materials.as<vkp_material>();
@@ -190,7 +194,8 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.position = ctx->position.as<uint2>(); F.normal = ctx->normal.as<uint2>(); F.albedo = ctx->albedo.as<uchar4>();
     F.motion = ctx->motion.as<uint32_t>(); F.material = ctx->material.as<uchar4>(); F.emissive = ctx->emissive.as<uchar4>();
     F.hit_ids = ctx->hit_ids.as<int2>(); F.final_f32 = ctx->final_f32.as<float4>();
-    F.final_srgb8 = ctx->peer_srgb8 ? reinterpret_cast<uchar4*>(ctx->peer_srgb8) : ctx->final_srgb8.as<uchar4>();
+    F.final_srgb8 = ctx->peer_srgb8[ctx->out_sel] ? reinterpret_cast<uchar4*>(ctx->peer_srgb8[ctx->out_sel])
+                                                  : (ctx->out_sel ? ctx->final_srgb8_alt.as<uchar4>() : ctx->final_srgb8.as<uchar4>());
     F.shadow = ctx->shadow.as<uint8_t>();
     F.denoised = ctx->denoised[ctx->denoised_cur].as<uint8_t>();
     F.denoised_next = ctx->denoised[ctx->denoised_cur ^ 1].as<uint8_t>();
@@ -314,7 +319,7 @@ void vkp_destroy(vkp_ctx* ctx)
     ctx->tlas.release(); ctx->scratch.release(); ctx->tlas_scratch.release();
     DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_lights, &ctx->d_instances, &ctx->d_textures, &ctx->d_inst_trav, &ctx->position, &ctx->normal, &ctx->albedo, &ctx->motion,
                       &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
-                      &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot};
+                      &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->final_srgb8_alt};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->timer0) cudaEventDestroy(ctx->timer0);
@@ -440,7 +445,7 @@ int vkp_build_blas(vkp_ctx* ctx)
         CK(bvh_build(ctx->stream, ctx->scratch, ntri, 4, b->bvh, &ctx->build_launches, ctx->builder));
         CK(bvh_emit_triangles(ctx->stream, m.verts.as<vkp_vertex>(), idx, b->bvh));
         CK(cudaStreamSynchronize(ctx->stream));
-        if (b->bvh.height + 8 > VKP_TRAV_STACK - 8) {
+        if (3 * ((b->bvh.height + 1) / 2 + 1) + 16 > VKP_TRAV_STACK) {      // up to 3 pushes per wide level + the TLAS part
             char msg[160]; snprintf(msg, sizeof msg, "BLAS height %d exceeds the traversal stack budget", b->bvh.height);
             return fail(ctx, VKP_ERR_INVALID, msg);
         }
@@ -470,7 +475,7 @@ int vkp_build_tlas(vkp_ctx* ctx, int update)
         d[i].material_id = I.material_id;
         const float* im = I.inv_model;
         tv[i].r0 = make_float4(im[0], im[4], im[8], im[12]); tv[i].r1 = make_float4(im[1], im[5], im[9], im[13]); tv[i].r2 = make_float4(im[2], im[6], im[10], im[14]);
-        tv[i].nodes = rec->bvh.nodes.as<float4>(); tv[i].tris = rec->bvh.tris.as<float4>(); tv[i].root_ref = rec->bvh.root_ref;
+        tv[i].nodes = rec->bvh.nodes4.as<float4>(); tv[i].tris = rec->bvh.tris.as<float4>(); tv[i].root_ref = rec->bvh.root_ref4;
     }
     CK(ctx->d_inst_trav.ensure(sizeof(DInstTrav) * tv.size()));
     CK(cudaMemcpyAsync(ctx->d_inst_trav.p, tv.data(), sizeof(DInstTrav) * tv.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -650,11 +655,18 @@ int vkp_ipc_open(vkp_ctx* ctx, const void* handle64, void** device_ptr)
     return VKP_OK;
 }
 
-int vkp_set_output_redirect(vkp_ctx* ctx, void* peer_final_srgb8)
+int vkp_set_output_redirect(vkp_ctx* ctx, void* peer_buffer0, void* peer_buffer1)
 {
     if (!ctx) return VKP_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->peer_srgb8 = peer_final_srgb8;
+    ctx->peer_srgb8[0] = peer_buffer0; ctx->peer_srgb8[1] = peer_buffer1;
+    return VKP_OK;
+}
+
+int vkp_set_output_buffer(vkp_ctx* ctx, int which)
+{
+    if (!ctx || which < 0 || which > 1) return VKP_ERR_INVALID;
+    ctx->out_sel = which;
     return VKP_OK;
 }
 
@@ -695,7 +707,7 @@ int vkp_trace_rays(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, v
     // tracing needs only geometry: tolerate a missing environment / materials
     if (!ctx->tlas_built) return fail(ctx, VKP_ERR_INVALID, "vkp_trace_rays: acceleration structures are not built");
     memset(&S, 0, sizeof(S));
-    S.tlas_nodes = ctx->tlas.nodes.as<vkp_bvh_node>(); S.tlas_items = ctx->tlas.items.as<uint32_t>();
+    S.tlas_nodes4 = ctx->tlas.nodes4.as<float4>(); S.tlas_root_ref = ctx->tlas.root_ref4;
     S.instances = ctx->d_instances.as<DInstance>(); S.n_instances = (int)ctx->instances.size();
     S.inst_trav = ctx->d_inst_trav.as<DInstTrav>();
     if (n == 0) return VKP_OK;
@@ -714,7 +726,7 @@ int vkp_trace_stats(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, 
     CK(cudaSetDevice(ctx->device));
     if (!ctx->tlas_built) return fail(ctx, VKP_ERR_INVALID, "vkp_trace_stats: acceleration structures are not built");
     DScene S; memset(&S, 0, sizeof(S));
-    S.tlas_nodes = ctx->tlas.nodes.as<vkp_bvh_node>(); S.tlas_items = ctx->tlas.items.as<uint32_t>();
+    S.tlas_nodes4 = ctx->tlas.nodes4.as<float4>(); S.tlas_root_ref = ctx->tlas.root_ref4;
     S.instances = ctx->d_instances.as<DInstance>(); S.n_instances = (int)ctx->instances.size();
     S.inst_trav = ctx->d_inst_trav.as<DInstTrav>();
     if (n == 0) return VKP_OK;

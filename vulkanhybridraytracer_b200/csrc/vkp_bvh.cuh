@@ -15,7 +15,8 @@
 #define VKP_LEAF_BIT 0x80000000u
 #define VKP_STACK_SENTINEL 0xffffffffu
 #define VKP_STACK_RETURN 0xfffffffeu
-#define VKP_TRAV_STACK 64
+#define VKP_TRAV_STACK 128
+#define VKP_W_EMPTY_REF 0xfffffffdu
 
 struct HitRec {
     float t, u, v;
@@ -110,43 +111,42 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
     float3 inv = winv;
     const bool wpar = has_parallel_axis(d);
     bool par = wpar;
-    const float4* nodes = reinterpret_cast<const float4*>(S.tlas_nodes);
+    const float4* nodes = S.tlas_nodes4;
     const float4* tris = nullptr;
     int inst = -1;
 
-    uint32_t cur;
-    {
-        float4 lo = __ldg(&nodes[0]), hi = __ldg(&nodes[1]);
-        float tn;
-        if (!box_test(lo, hi, ro, rd, inv, par, tmin, limit, tn)) return false;
-        cur = __float_as_uint(lo.w);
-    }
+    uint32_t cur = S.tlas_root_ref;
 
-    // "while-while" traversal (Aila & Laine): all lanes of a warp walk internal nodes together and only then process
-    // their leaves together, instead of serialising a node body and a leaf body in every trip of one loop.  Measured on
-    // the default scene: the if-if form cost ~2000 SM cycles per trip under load.
+    // "while-while" traversal (Aila & Laine) over 4-wide nodes: all lanes of a warp walk internal nodes together and only
+    // then process their leaves together.  One trip = one 128-byte node fetch and four slab tests; the hit children other
+    // than the nearest go on the stack, farthest first.
     while (true) {
-        // ---- internal nodes: descend until this lane holds a leaf / marker --------------------------------------------------
         while (!(cur & VKP_LEAF_BIT)) {
-            const float4* c = nodes + 2u * (size_t)cur;      // both children: 64 contiguous bytes
+            const float4* c = nodes + 8u * (size_t)cur;
             if (STATS) n_steps++;
-            float4 lo0 = __ldg(c + 0), hi0 = __ldg(c + 1), lo1 = __ldg(c + 2), hi1 = __ldg(c + 3);
-            float t0, t1;
-            bool h0 = box_test(lo0, hi0, ro, rd, inv, par, tmin, limit, t0);
-            bool h1 = box_test(lo1, hi1, ro, rd, inv, par, tmin, limit, t1);
-            uint32_t r0 = __float_as_uint(lo0.w), r1 = __float_as_uint(lo1.w);
-            if (h0 && h1) {
-                bool swap = t1 < t0;
-                stack[sp++] = swap ? r0 : r1;
-                cur = swap ? r1 : r0;
-            } else if (h0) cur = r0;
-            else if (h1) cur = r1;
-            else cur = stack[--sp];
+            const float4 lox = __ldg(c + 0), loy = __ldg(c + 1), loz = __ldg(c + 2), hix = __ldg(c + 3), hiy = __ldg(c + 4), hiz = __ldg(c + 5), rf = __ldg(c + 6);
+            const float inf = __int_as_float(0x7f800000);
+            float t0, t1, t2, t3;
+            const uint32_t r0 = __float_as_uint(rf.x), r1 = __float_as_uint(rf.y), r2 = __float_as_uint(rf.z), r3 = __float_as_uint(rf.w);
+            bool h0 = box_test(make_float4(lox.x, loy.x, loz.x, 0.f), make_float4(hix.x, hiy.x, hiz.x, 0.f), ro, rd, inv, par, tmin, limit, t0);
+            bool h1 = box_test(make_float4(lox.y, loy.y, loz.y, 0.f), make_float4(hix.y, hiy.y, hiz.y, 0.f), ro, rd, inv, par, tmin, limit, t1);
+            bool h2 = box_test(make_float4(lox.z, loy.z, loz.z, 0.f), make_float4(hix.z, hiy.z, hiz.z, 0.f), ro, rd, inv, par, tmin, limit, t2) && r2 != VKP_W_EMPTY_REF;
+            bool h3 = box_test(make_float4(lox.w, loy.w, loz.w, 0.f), make_float4(hix.w, hiy.w, hiz.w, 0.f), ro, rd, inv, par, tmin, limit, t3) && r3 != VKP_W_EMPTY_REF;
+            // sort the (distance, ref) pairs ascending with a 5-comparator network; misses sink to the end as +inf
+            float d0 = h0 ? t0 : inf, d1 = h1 ? t1 : inf, d2 = h2 ? t2 : inf, d3 = h3 ? t3 : inf;
+            uint32_t q0 = r0, q1 = r1, q2 = r2, q3 = r3;
+#define VKP_CSWAP(da, qa, db, qb) { if (db < da) { float td = da; da = db; db = td; uint32_t tq = qa; qa = qb; qb = tq; } }
+            VKP_CSWAP(d0, q0, d1, q1) VKP_CSWAP(d2, q2, d3, q3) VKP_CSWAP(d0, q0, d2, q2) VKP_CSWAP(d1, q1, d3, q3) VKP_CSWAP(d1, q1, d2, q2)
+#undef VKP_CSWAP
+            if (d3 < inf) stack[sp++] = q3;
+            if (d2 < inf) stack[sp++] = q2;
+            if (d1 < inf) stack[sp++] = q1;
+            cur = (d0 < inf) ? q0 : stack[--sp];
         }
         if (cur == VKP_STACK_SENTINEL) break;
         if (cur == VKP_STACK_RETURN) {
             inst = -1; ro = o; rd = d; inv = winv; par = wpar;
-            nodes = reinterpret_cast<const float4*>(S.tlas_nodes);
+            nodes = S.tlas_nodes4;
             cur = stack[--sp];
             continue;
         }

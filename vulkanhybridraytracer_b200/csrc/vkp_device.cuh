@@ -117,8 +117,9 @@ struct DInstTrav {
 struct DScene {
     const float* lut_pow22;
     const DInstTrav* inst_trav;          // same table as DFrame::lut_pow22 (hit / miss shading has only the scene)
-    const vkp_bvh_node* tlas_nodes;
-    const uint32_t* tlas_items;      // leaf-ordered instance ids
+    const float4* tlas_nodes4;       // 4-wide TLAS nodes (8 x float4 each)
+    uint32_t tlas_root_ref;          // wide node index or leaf reference (single instance)
+    uint32_t _pad0;
     const DInstance* instances;
     const vkp_material* materials;
     const vkp_light* lights;

@@ -30,7 +30,10 @@ struct Bvh {
     int leaf_max = 4;
     int height = 0;
     int root = 0;        // index of the root among the internal nodes (0 for the Karras tree)
-    uint32_t root_ref = 0x80000000u;   // nodes[0].ref: what traversal continues with after entering this BVH
+    uint32_t root_ref = 0x80000000u;   // nodes[0].ref of the binary layout
+    uint32_t n_nodes4 = 0;             // 4-wide layout (what traversal uses): 128-byte nodes
+    uint32_t root_ref4 = 0x80000000u;  // reference traversal starts from: wide node index, or a leaf reference
+    DevBuf nodes4, is4, rank4;
     DevBuf nodes;        // vkp_bvh_node[n_nodes]
     DevBuf items;        // uint32_t[n_prims]: leaf-ordered primitive ids
     DevBuf tris;         // BLAS only: float4[3*n_prims]
@@ -45,7 +48,7 @@ struct Bvh {
     void release()
     {
         nodes.release(); items.release(); tris.release(); child.release(); parent.release(); ibox.release();
-        flags.release(); rank.release(); keep.release(); range.release();
+        flags.release(); rank.release(); keep.release(); range.release(); nodes4.release(); is4.release(); rank4.release();
     }
 };
 

@@ -44,13 +44,20 @@ class TiledRenderer:
         """Composite of FINAL_SRGB8 without a gather: every rank's resolve kernel stores its pixels straight into rank 0's
         image over NVLink peer memory (CUDA IPC); a frame then only needs a barrier.  NCCL backend, one GPU per rank."""
         import torch.distributed as dist
-        if self.world == 1 or self.backend != "nccl":
+        if self.world == 1:
             return False
-        box = [self.ctx.ipc_export_plane(PLANE.FINAL_SRGB8) if self.rank == 0 else None]
+        # two buffers: frame k+1 goes to the other one, so rank 0 may still be consuming frame k when the peers start writing
+        box = [None, None]
+        if self.rank == 0:
+            for which in (0, 1):
+                self.ctx.set_output_buffer(which)
+                box[which] = self.ctx.ipc_export_plane(PLANE.FINAL_SRGB8)
+            self.ctx.set_output_buffer(0)
         dist.broadcast_object_list(box, src=0, group=self.group)
         if self.rank != 0:
-            self.ctx.set_output_redirect(self.ctx.ipc_open(box[0]))
-        self._flag = self.torch.zeros(1, dtype=self.torch.int32, device=self.device)
+            self.ctx.set_output_redirect(self.ctx.ipc_open(box[0]), self.ctx.ipc_open(box[1]))
+        self._frame_no = 0
+        self._flag = self.torch.zeros(1, dtype=self.torch.int32, device=self.device if self.backend == "nccl" else "cpu")
         self.peer_output = True
         return True
 
@@ -99,6 +106,9 @@ class TiledRenderer:
         """One frame of params.mode on this rank's tiles; exact w.r.t. the single-GPU image."""
         ctx = self.ctx
         ctx.set_params(params)
+        if self.peer_output:
+            self._frame_no += 1
+            ctx.set_output_buffer(self._frame_no & 1)
         if self.world == 1 or params.mode != MODE_HYBRID or params.denoise_frame > 0:
             ctx.render()
             return
