@@ -167,6 +167,7 @@ int make_scene(vkp_ctx* ctx, DScene& S)
     if (r != VKP_OK) return r;
     S.lut_pow22 = ctx->luts.as<float>();
     S.tlas_nodes4 = ctx->tlas.nodes4.as<float4>(); S.tlas_root_ref = ctx->tlas.root_ref4;
+    S.tlas_nodes2 = ctx->tlas.nodes.as<float4>(); S.tlas_root_ref2 = ctx->tlas.root_ref;
     S.instances = ctx->d_instances.as<DInstance>();
     S.inst_trav = ctx->d_inst_trav.as<DInstTrav>();
     S.materials = ctx->d_materials.as<vkp_material>();
@@ -445,7 +446,7 @@ int vkp_build_blas(vkp_ctx* ctx)
         CK(bvh_build(ctx->stream, ctx->scratch, ntri, 4, b->bvh, &ctx->build_launches, ctx->builder));
         CK(bvh_emit_triangles(ctx->stream, m.verts.as<vkp_vertex>(), idx, b->bvh));
         CK(cudaStreamSynchronize(ctx->stream));
-        if (3 * ((b->bvh.height + 1) / 2 + 1) + 16 > VKP_TRAV_STACK) {      // up to 3 pushes per wide level + the TLAS part
+        if ((VKP_WIDE ? 3 * ((b->bvh.height + 1) / 2 + 1) + 16 : b->bvh.height + 16) > VKP_TRAV_STACK) {     // pushes per level + the TLAS part
             char msg[160]; snprintf(msg, sizeof msg, "BLAS height %d exceeds the traversal stack budget", b->bvh.height);
             return fail(ctx, VKP_ERR_INVALID, msg);
         }
@@ -476,6 +477,7 @@ int vkp_build_tlas(vkp_ctx* ctx, int update)
         const float* im = I.inv_model;
         tv[i].r0 = make_float4(im[0], im[4], im[8], im[12]); tv[i].r1 = make_float4(im[1], im[5], im[9], im[13]); tv[i].r2 = make_float4(im[2], im[6], im[10], im[14]);
         tv[i].nodes = rec->bvh.nodes4.as<float4>(); tv[i].tris = rec->bvh.tris.as<float4>(); tv[i].root_ref = rec->bvh.root_ref4;
+        tv[i].nodes2 = rec->bvh.nodes.as<float4>(); tv[i].root_ref2 = rec->bvh.root_ref;
     }
     CK(ctx->d_inst_trav.ensure(sizeof(DInstTrav) * tv.size()));
     CK(cudaMemcpyAsync(ctx->d_inst_trav.p, tv.data(), sizeof(DInstTrav) * tv.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -708,6 +710,7 @@ int vkp_trace_rays(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, v
     if (!ctx->tlas_built) return fail(ctx, VKP_ERR_INVALID, "vkp_trace_rays: acceleration structures are not built");
     memset(&S, 0, sizeof(S));
     S.tlas_nodes4 = ctx->tlas.nodes4.as<float4>(); S.tlas_root_ref = ctx->tlas.root_ref4;
+    S.tlas_nodes2 = ctx->tlas.nodes.as<float4>(); S.tlas_root_ref2 = ctx->tlas.root_ref;
     S.instances = ctx->d_instances.as<DInstance>(); S.n_instances = (int)ctx->instances.size();
     S.inst_trav = ctx->d_inst_trav.as<DInstTrav>();
     if (n == 0) return VKP_OK;
@@ -727,6 +730,7 @@ int vkp_trace_stats(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, 
     if (!ctx->tlas_built) return fail(ctx, VKP_ERR_INVALID, "vkp_trace_stats: acceleration structures are not built");
     DScene S; memset(&S, 0, sizeof(S));
     S.tlas_nodes4 = ctx->tlas.nodes4.as<float4>(); S.tlas_root_ref = ctx->tlas.root_ref4;
+    S.tlas_nodes2 = ctx->tlas.nodes.as<float4>(); S.tlas_root_ref2 = ctx->tlas.root_ref;
     S.instances = ctx->d_instances.as<DInstance>(); S.n_instances = (int)ctx->instances.size();
     S.inst_trav = ctx->d_inst_trav.as<DInstTrav>();
     if (n == 0) return VKP_OK;

@@ -15,7 +15,17 @@
 #define VKP_LEAF_BIT 0x80000000u
 #define VKP_STACK_SENTINEL 0xffffffffu
 #define VKP_STACK_RETURN 0xfffffffeu
+// VKP_WIDE: 0 = binary nodes (default), 1 = 4-wide nodes.  Measured on B200: the wide layout halves the node
+// fetches per ray but costs more slab tests and registers; it is neutral on the latency-bound 1080p Hybrid frame and
+// 10-26 % slower on the throughput-bound workloads (cfg3 / cfg4 / cfg5), so the binary layout stays the default.
+#ifndef VKP_WIDE
+#define VKP_WIDE 0
+#endif
+#if VKP_WIDE
 #define VKP_TRAV_STACK 128
+#else
+#define VKP_TRAV_STACK 64
+#endif
 #define VKP_W_EMPTY_REF 0xfffffffdu
 
 struct HitRec {
@@ -111,16 +121,38 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
     float3 inv = winv;
     const bool wpar = has_parallel_axis(d);
     bool par = wpar;
+#if VKP_WIDE
     const float4* nodes = S.tlas_nodes4;
+    uint32_t cur = S.tlas_root_ref;
+#else
+    const float4* nodes = S.tlas_nodes2;
+    uint32_t cur = S.tlas_root_ref2;
+#endif
     const float4* tris = nullptr;
     int inst = -1;
-
-    uint32_t cur = S.tlas_root_ref;
 
     // "while-while" traversal (Aila & Laine) over 4-wide nodes: all lanes of a warp walk internal nodes together and only
     // then process their leaves together.  One trip = one 128-byte node fetch and four slab tests; the hit children other
     // than the nearest go on the stack, farthest first.
     while (true) {
+#if !VKP_WIDE
+        while (!(cur & VKP_LEAF_BIT)) {
+            const float4* c = nodes + 2u * (size_t)cur;      // both children: 64 contiguous bytes
+            if (STATS) n_steps++;
+            float4 lo0 = __ldg(c + 0), hi0 = __ldg(c + 1), lo1 = __ldg(c + 2), hi1 = __ldg(c + 3);
+            float t0, t1;
+            bool h0 = box_test(lo0, hi0, ro, rd, inv, par, tmin, limit, t0);
+            bool h1 = box_test(lo1, hi1, ro, rd, inv, par, tmin, limit, t1);
+            uint32_t r0 = __float_as_uint(lo0.w), r1 = __float_as_uint(lo1.w);
+            if (h0 && h1) {
+                bool swap = t1 < t0;
+                stack[sp++] = swap ? r0 : r1;
+                cur = swap ? r1 : r0;
+            } else if (h0) cur = r0;
+            else if (h1) cur = r1;
+            else cur = stack[--sp];
+        }
+#else
         while (!(cur & VKP_LEAF_BIT)) {
             const float4* c = nodes + 8u * (size_t)cur;
             if (STATS) n_steps++;
@@ -143,10 +175,15 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
             if (d1 < inf) stack[sp++] = q1;
             cur = (d0 < inf) ? q0 : stack[--sp];
         }
+#endif
         if (cur == VKP_STACK_SENTINEL) break;
         if (cur == VKP_STACK_RETURN) {
             inst = -1; ro = o; rd = d; inv = winv; par = wpar;
+#if VKP_WIDE
             nodes = S.tlas_nodes4;
+#else
+            nodes = S.tlas_nodes2;
+#endif
             cur = stack[--sp];
             continue;
         }
@@ -160,11 +197,16 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
             rd = f3((r0.x * d.x + r0.y * d.y) + r0.z * d.z, (r1.x * d.x + r1.y * d.y) + r1.z * d.z, (r2.x * d.x + r2.y * d.y) + r2.z * d.z);
             inv = safe_inv_dir(rd);
             par = has_parallel_axis(rd);
-            nodes = reinterpret_cast<const float4*>(((unsigned long long)__float_as_uint(pp.y) << 32) | (unsigned long long)__float_as_uint(pp.x));
             tris = reinterpret_cast<const float4*>(((unsigned long long)__float_as_uint(pp.w) << 32) | (unsigned long long)__float_as_uint(pp.z));
             // the TLAS leaf box is the world box of this instance: go straight to the BLAS root's content
             stack[sp++] = VKP_STACK_RETURN;
+#if VKP_WIDE
+            nodes = reinterpret_cast<const float4*>(((unsigned long long)__float_as_uint(pp.y) << 32) | (unsigned long long)__float_as_uint(pp.x));
             cur = __float_as_uint(rr.x);
+#else
+            nodes = reinterpret_cast<const float4*>(((unsigned long long)__float_as_uint(rr.w) << 32) | (unsigned long long)__float_as_uint(rr.z));
+            cur = __float_as_uint(rr.y);
+#endif
             continue;
         }
         // ---- BLAS leaf: <= 4 triangles; issue all loads first so that their latency overlaps ----------------------------------

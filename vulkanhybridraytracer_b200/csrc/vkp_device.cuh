@@ -109,17 +109,20 @@ struct DInstance {
 // the rows of inverse(model) 3x4 in xform_point()'s association, the BLAS arrays and the BLAS root reference
 struct DInstTrav {
     float4 r0, r1, r2;
-    const float4* nodes;
+    const float4* nodes;        // 4-wide nodes
     const float4* tris;
-    uint32_t root_ref, _pad[3];
+    uint32_t root_ref;          // wide root reference
+    uint32_t root_ref2;         // binary root reference
+    const float4* nodes2;       // binary nodes (32 B each)
 };
 
 struct DScene {
     const float* lut_pow22;
     const DInstTrav* inst_trav;          // same table as DFrame::lut_pow22 (hit / miss shading has only the scene)
     const float4* tlas_nodes4;       // 4-wide TLAS nodes (8 x float4 each)
-    uint32_t tlas_root_ref;          // wide node index or leaf reference (single instance)
-    uint32_t _pad0;
+    const float4* tlas_nodes2;       // binary TLAS nodes (2 x float4 each)
+    uint32_t tlas_root_ref;          // wide: node index or leaf reference (single instance)
+    uint32_t tlas_root_ref2;         // binary: nodes[0].ref
     const DInstance* instances;
     const vkp_material* materials;
     const vkp_light* lights;
