@@ -225,6 +225,7 @@ def main():
     ctx.set_profiling(True)
     stage_ms = np.zeros(8)
     rays = np.zeros(4, dtype=np.int64)
+    trav = np.zeros(3, dtype=np.int64)
     launches = 0
     sampler = ClockSampler(dev); sampler.start()
     barrier()
@@ -248,6 +249,14 @@ def main():
         frame += 1
     barrier()
     clocks = sampler.stop()
+    # one extra, untimed frame with traversal accounting on: what the rays actually requested from memory
+    ctx.set_profiling(2)
+    tr.render(params(frame))
+    c = ctx.counters()
+    trav = np.array([c.node_fetches, c.triangle_tests, c.instance_entries], dtype=np.int64) * args.steps
+    if world > 1:
+        composite()
+    frame += 1
     ctx.set_profiling(False)
     t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{dev}")
     r = torch.tensor(rays, dtype=torch.int64, device=f"cuda:{dev}")
@@ -344,6 +353,12 @@ def main():
                 "kernel_share_of_step": float(ms[dom] / max(ms.sum(), 1e-9)),
                 "stage_ms": {names[i]: float(ms[i]) for i in range(7) if ms[i] > 0},
                 "frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_bytes * world / (ms_per_step * 1e-3) / 1e9, "frac": frame_bytes * world / (ms_per_step * 1e-3) / 1e9 / (peak * world)},
+                "requested": {"note": "bytes the traversal actually asked the memory system for on this rank (device counters): 64 B per child-pair fetch, 48 B per "
+                                      "triangle, 80 B per instance entry, + the per-pixel plane traffic of SURVEY 8d",
+                              "node_fetches_per_frame": int(trav[0] // args.steps), "triangle_tests_per_frame": int(trav[1] // args.steps),
+                              "instance_entries_per_frame": int(trav[2] // args.steps),
+                              "bytes_per_frame": float((64 * trav[0] + 48 * trav[1] + 80 * trav[2]) / args.steps + Pr * (100 + 5 * L)),
+                              "GBps": float(((64 * trav[0] + 48 * trav[1] + 80 * trav[2]) / args.steps + Pr * (100 + 5 * L)) / (ms_per_step * 1e-3) / 1e9)},
                 "note": "algorithmic bytes = P*B_px(stage) + rays*B_ray(T) (SURVEY 8d, B_ray=%d B at T=%d); traversal is latency/L2 bound, measured DRAM traffic is far below this" % (BR, T)}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):

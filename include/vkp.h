@@ -89,7 +89,7 @@ VKP_API int vkp_readback(vkp_ctx* ctx, int plane, void* dst, size_t bytes);     
 VKP_API int vkp_upload_plane(vkp_ctx* ctx, int plane, const void* src, size_t bytes);
 VKP_API int vkp_plane_device_ptr(vkp_ctx* ctx, int plane, void** device_ptr, size_t* bytes);
 VKP_API int vkp_get_counters(vkp_ctx* ctx, vkp_counters* out);                    /* syncs */
-VKP_API int vkp_set_profiling(vkp_ctx* ctx, int on);            /* per-stage CUDA events on/off */
+VKP_API int vkp_set_profiling(vkp_ctx* ctx, int on);            /* 0 off, 1 per-stage CUDA events, 2 also count traversal fetches (slower) */
 
 /* traceRayEXT made explicit: trace n rays against the current TLAS (host buffers). any_hit != 0
  * == gl_RayFlagsTerminateOnFirstHitEXT|SkipClosestHitShaderEXT: only hit.t >= 0 / < 0 is defined */

@@ -137,6 +137,9 @@ typedef struct vkp_counters {
     float    ms_frame;
     uint32_t kernel_launches;       /* kernels launched by the last vkp_render             */
     uint32_t _pad;
+    uint64_t node_fetches;          /* traversal: child-pair fetches (64 B each)            */
+    uint64_t triangle_tests;        /* traversal: leaf triangles fetched + tested (48 B)    */
+    uint64_t instance_entries;      /* traversal: TLAS leaves entered (80 B record each)    */
 } vkp_counters;
 
 /* 32-byte BVH node (both BLAS and TLAS).  ref: bit31 = leaf; leaf: bits[30:3] = first item,

@@ -357,7 +357,7 @@ class Context:
         self._ck(self.L.vkp_reset_history(self.h), "vkp_reset_history")
 
     def set_profiling(self, on):
-        self._ck(self.L.vkp_set_profiling(self.h, 1 if on else 0), "vkp_set_profiling")
+        self._ck(self.L.vkp_set_profiling(self.h, int(on)), "vkp_set_profiling")
 
     def set_stream(self, stream_ptr):
         self._ck(self.L.vkp_set_stream(self.h, C.c_void_p(stream_ptr)), "vkp_set_stream")

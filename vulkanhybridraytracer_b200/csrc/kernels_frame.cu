@@ -53,6 +53,11 @@ __device__ __forceinline__ void add_counter(unsigned long long* counters, int sl
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(&counters[slot], (unsigned long long)n);
 }
 
+__device__ __forceinline__ void add_trav(unsigned long long* counters, const TravCount& tc)
+{
+    add_counter(counters, 4, tc.nodes); add_counter(counters, 5, tc.tris); add_counter(counters, 6, tc.entries);
+}
+
 // image store into the B8G8R8A8_UNORM target (renderer.cpp:1535) followed by postFragment.frag:9-21
 // (the 8-bit store leaves 256 possible inputs per channel: the gamma curve is a table built on the device by k_build_luts)
 __device__ __forceinline__ uchar4 post_pixel(const uint8_t* __restrict__ lut_post, float4 c)
@@ -96,7 +101,7 @@ __device__ __forceinline__ void shade_miss(const DScene& S, float3 rayDir, Paylo
 // (one SIMT instruction stream, broadcast loads) except the per-light shadow samples, which are spread over the lanes.
 template <bool RT, bool WARP = false>
 __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, float3 rayD, const HitRec& h, Payload& prd,
-                          unsigned int& n_secondary)
+                          unsigned int& n_secondary, TravCount* tcp)
 {
     const DInstance& I = S.instances[h.inst];
     const float b0 = 1.0f - h.u - h.v, b1 = h.u, b2 = h.v;
@@ -162,7 +167,7 @@ __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, flo
                             if (advance) for (int r = 0; r < 2 * a; r++) sd = 1664525u * sd + 1013904223u;
                             float3 dir = sample_disk(light, worldPos, L, sd, false);
                             HitRec sh; n_secondary++;
-                            unshadowed = !trace_ray<true>(S, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh);
+                            unshadowed = !trace_ray<true>(S, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, nullptr, tcp);
                         }
                         lit += (unsigned)__popc(__ballot_sync(0xffffffffu, unshadowed));
                     }
@@ -185,7 +190,7 @@ __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, flo
                     if (light_distance < light_max_distance) {
                         float3 dir = sample_disk(light, worldPos, L, prd.seed, advance);
                         HitRec sh; n_secondary++;
-                        shadowed = trace_ray<true>(S, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh);
+                        shadowed = trace_ray<true>(S, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, nullptr, tcp);
                     }
                     if (!shadowed) shadowFactor += 1.0f;
                 }
@@ -215,7 +220,7 @@ __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, flo
                     if (light_distance < light_max_distance) {
                         float3 dir = sample_disk(light, worldPos, L, prd.seed, advance);
                         HitRec sh; n_secondary++;
-                        shadowed = trace_ray<true>(S, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh);
+                        shadowed = trace_ray<true>(S, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, nullptr, tcp);
                     }
                     if (!shadowed) shadowFactor += 1.0f;
                 }
@@ -266,12 +271,14 @@ __global__ void __launch_bounds__(128, VKP_LB_GBUFFER) k_gbuffer(const __grid_co
 {
     const Pixel px = pixel_of_thread(F);
     unsigned int nrays = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
     if (px.valid) {
         const int W = F.p.width, H = F.p.height;
         const size_t i = (size_t)px.y * W + px.x;
         float3 o, d; camera_ray(F.cam, px.x, px.y, 0.5f, 0.5f, W, H, o, d);
         HitRec h; nrays = 1;
-        bool hit = trace_ray<false>(S, o + d * 1e-2f, d, 0.001f, 10000.0f, h);
+        bool hit = trace_ray<false>(S, o + d * 1e-2f, d, 0.001f, 10000.0f, h, nullptr, tcp);
         F.hit_ids[i] = make_int2(h.inst, h.prim);
         if (!hit) {
             // skybox.frag:16-21
@@ -323,6 +330,7 @@ __global__ void __launch_bounds__(128, VKP_LB_GBUFFER) k_gbuffer(const __grid_co
         }
     }
     add_counter(F.counters, 0, nrays);
+    if (F.count_trav) add_trav(F.counters, tc);
 }
 
 // per-light pieces of shadowRaygen.rgen:55-61 that decide whether rays are traced (and hence how far the RNG advances)
@@ -349,6 +357,8 @@ __global__ void __launch_bounds__(128, VKP_LB_SHADOW) k_shadow(const __grid_cons
     const Pixel px = pixel_of_thread(F);
     const int l = blockIdx.y;
     unsigned int nrays = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
     if (px.valid) {
         const int W = F.p.width, H = F.p.height;
         const size_t i = (size_t)px.y * W + px.x;
@@ -381,7 +391,7 @@ __global__ void __launch_bounds__(128, VKP_LB_SHADOW) k_shadow(const __grid_cons
                     for (int s = 0; s < shadowSamples; s++) {
                         const float3 dir = sample_disk(light, position, g.L, seed, advance);
                         HitRec h; nrays++;
-                        if (!trace_ray<true>(S, position + dir * 1e-1f, dir, 0.001f, g.dist + 1.0f, h)) shadowFactor += 1.0f;
+                        if (!trace_ray<true>(S, position + dir * 1e-1f, dir, 0.001f, g.dist + 1.0f, h, nullptr, tcp)) shadowFactor += 1.0f;
                     }
                 } else {
                     for (int s = 0; s < shadowSamples; s++) shadowFactor += 1.0f;      // beyond maxDistance: unshadowed (shadowRaygen.rgen:81-83)
@@ -392,6 +402,7 @@ __global__ void __launch_bounds__(128, VKP_LB_SHADOW) k_shadow(const __grid_cons
         }
     }
     add_counter(F.counters, 1, nrays);
+    if (F.count_trav) add_trav(F.counters, tc);
 }
 
 // blur.comp:35-82 for one pixel and one light, with runtime W/H/NLIGHTS and an integer motion fetch; returns the new
@@ -475,6 +486,8 @@ __global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_chain(const __grid_cons
 {
     const Pixel px = pixel_of_thread(F);
     unsigned int n_refl = 0, n_sec = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
     bool path = false;
     size_t i = 0;
     float4 pos4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -509,8 +522,8 @@ __global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_chain(const __grid_cons
         for (int depth = 0; depth < F.p.max_bounces; depth++) {
             float3 ro = origin + direction * 1e-2f;
             HitRec h; n_refl++;
-            bool hit = trace_ray<false>(S, ro, direction, 0.001f, 1000.0f, h);
-            if (hit) shade_hit<false>(S, F.p, ro, direction, h, prd, n_sec); else shade_miss(S, direction, prd);
+            bool hit = trace_ray<false>(S, ro, direction, 0.001f, 1000.0f, h, nullptr, tcp);
+            if (hit) shade_hit<false>(S, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
             rec[n] = make_float4(prd.color.x, prd.color.y, prd.color.z, 0.0f);
             n++;
             if (!hit || !(prd.scatter > 0.0f)) break;
@@ -520,6 +533,7 @@ __global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_chain(const __grid_cons
     }
     add_counter(F.counters, 2, n_refl);
     add_counter(F.counters, 3, n_sec);
+    if (F.count_trav) add_trav(F.counters, tc);
 }
 
 // CHAIN == 0: the bounce chain runs inline in this kernel (its latency hides behind the other pixels' shading);
@@ -531,6 +545,8 @@ __global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_resolve(const __grid_co
     const Pixel px = pixel_of_thread(F);
     bool wants_path = false;
     unsigned int n_refl = 0, n_sec = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
     PathItem item;
     if (px.valid) {
         const int W = F.p.width, H = F.p.height;
@@ -639,8 +655,8 @@ __global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_resolve(const __grid_co
             for (int depth = 0; depth < F.p.max_bounces; depth++) {
                 float3 ro = origin + direction * 1e-2f;
                 HitRec h; n_refl++;
-                bool hit = trace_ray<false>(S, ro, direction, 0.001f, 1000.0f, h);
-                if (hit) shade_hit<false>(S, F.p, ro, direction, h, prd, n_sec); else shade_miss(S, direction, prd);
+                bool hit = trace_ray<false>(S, ro, direction, 0.001f, 1000.0f, h, nullptr, tcp);
+                if (hit) shade_hit<false>(S, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
                 rayColor = rayColor * prd.color;
                 if (!hit || !(prd.scatter > 0.0f)) break;
                 origin = prd.origin; direction = prd.direction;
@@ -673,6 +689,8 @@ __global__ void __launch_bounds__(128) k_bounce(const __grid_constant__ DScene S
     const PathItem* __restrict__ qin = F.path_q[depth & 1];
     PathItem* qout = F.path_q[(depth + 1) & 1];
     unsigned int n_refl = 0, n_sec = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
     const uint32_t n_round = (n_in + 31u) & ~31u;       // whole warps stay in the loop so that the ballots are convergent
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
         bool again = false;
@@ -687,8 +705,8 @@ __global__ void __launch_bounds__(128) k_bounce(const __grid_constant__ DScene S
             Payload prd; prd.seed = __float_as_uint(item.b.w);
             float3 ro = origin + direction * 1e-2f;
             HitRec h; n_refl++;
-            bool hit = trace_ray<false>(S, ro, direction, 0.001f, 1000.0f, h);
-            if (hit) shade_hit<false>(S, F.p, ro, direction, h, prd, n_sec); else shade_miss(S, direction, prd);
+            bool hit = trace_ray<false>(S, ro, direction, 0.001f, 1000.0f, h, nullptr, tcp);
+            if (hit) shade_hit<false>(S, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
             rayColor = rayColor * prd.color;
             again = hit && (prd.scatter > 0.0f) && (depth + 1 < F.p.max_bounces);
             if (again) {
@@ -707,6 +725,7 @@ __global__ void __launch_bounds__(128) k_bounce(const __grid_constant__ DScene S
     }
     add_counter(F.counters, 2, n_refl);
     add_counter(F.counters, 3, n_sec);
+    if (F.count_trav) add_trav(F.counters, tc);
 }
 
 __global__ void __launch_bounds__(128) k_post(const __grid_constant__ DFrame F)
@@ -722,6 +741,8 @@ __global__ void __launch_bounds__(128, VKP_LB_RT) k_raytrace(const __grid_consta
 {
     const Pixel px = pixel_of_thread(F);
     unsigned int n_refl = 0, n_sec = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
     if (px.valid) {
         const int W = F.p.width, H = F.p.height;
         const size_t i = (size_t)px.y * W + px.x;
@@ -738,8 +759,8 @@ __global__ void __launch_bounds__(128, VKP_LB_RT) k_raytrace(const __grid_consta
             for (int b = 0; b < F.p.max_bounces; b++) {
                 float3 ro = origin + direction * 1e-2f;
                 HitRec h; n_refl++;
-                bool hit = trace_ray<false>(S, ro, direction, 0.001f, 10000.0f, h);
-                if (hit) shade_hit<true>(S, F.p, ro, direction, h, prd, n_sec); else shade_miss(S, direction, prd);
+                bool hit = trace_ray<false>(S, ro, direction, 0.001f, 10000.0f, h, nullptr, tcp);
+                if (hit) shade_hit<true>(S, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
                 rayColor = rayColor * prd.color;
                 if (!hit || !(prd.scatter > 0.0f)) break;
                 origin = prd.origin; direction = prd.direction;
@@ -758,6 +779,7 @@ __global__ void __launch_bounds__(128, VKP_LB_RT) k_raytrace(const __grid_consta
     }
     add_counter(F.counters, 2, n_refl);
     add_counter(F.counters, 3, n_sec);
+    if (F.count_trav) add_trav(F.counters, tc);
 }
 
 // raygen.rgen with ONE WARP PER PIXEL, for many shadow samples per hit (BASELINE configs[2]: 64 spp x 64 samples): a pixel
@@ -772,6 +794,8 @@ __global__ void __launch_bounds__(128, VKP_LB_RT) k_raytrace_warp(const __grid_c
     const int tx = tile % F.tiles_x, ty = tile / F.tiles_x;
     const int x = tx * F.tile_w + within % F.tile_w, y = ty * F.tile_h + within / F.tile_w;
     unsigned int n_refl = 0, n_sec = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
     if (ty < F.tiles_y && x < F.p.width && y < F.p.height) {           // warp-uniform
         const int W = F.p.width, H = F.p.height;
         const size_t i = (size_t)y * W + x;
@@ -788,8 +812,8 @@ __global__ void __launch_bounds__(128, VKP_LB_RT) k_raytrace_warp(const __grid_c
             for (int b = 0; b < F.p.max_bounces; b++) {
                 float3 ro = origin + direction * 1e-2f;
                 HitRec h; n_refl++;
-                bool hit = trace_ray<false>(S, ro, direction, 0.001f, 10000.0f, h);
-                if (hit) shade_hit<true, true>(S, F.p, ro, direction, h, prd, n_sec); else shade_miss(S, direction, prd);
+                bool hit = trace_ray<false>(S, ro, direction, 0.001f, 10000.0f, h, nullptr, tcp);
+                if (hit) shade_hit<true, true>(S, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
                 rayColor = rayColor * prd.color;
                 if (!hit || !(prd.scatter > 0.0f)) break;
                 origin = prd.origin; direction = prd.direction;
@@ -812,6 +836,7 @@ __global__ void __launch_bounds__(128, VKP_LB_RT) k_raytrace_warp(const __grid_c
     }
     add_counter(F.counters, 2, n_refl);
     add_counter(F.counters, 3, n_sec);
+    if (F.count_trav) add_trav(F.counters, tc);
 }
 
 // deferred.frag:30-133 (no gamma pass in DEFERRED mode upstream; the sRGB8 plane gets the plain 8-bit store)

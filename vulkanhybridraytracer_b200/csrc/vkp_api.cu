@@ -57,6 +57,7 @@ struct vkp_ctx {
     std::vector<void*> ipc_opened;
 
     bool profiling = false;
+    bool count_trav = false;
     cudaEvent_t ev[12]{};
     int ev_stage[12]{};
     int n_ev = 0;
@@ -191,6 +192,7 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.tiles_x = (F.p.width + F.tile_w - 1) / F.tile_w; F.tiles_y = (F.p.height + F.tile_h - 1) / F.tile_h;
     F.rank = ctx->rank; F.world = ctx->world;
     F.fused = 0;
+    F.count_trav = ctx->count_trav ? 1 : 0;
     F.static_camera = memcmp(F.cam.view, F.cam.prev_view, 64) == 0 && memcmp(F.cam.proj, F.cam.prev_proj, 64) == 0;
     F.position = ctx->position.as<uint2>(); F.normal = ctx->normal.as<uint2>(); F.albedo = ctx->albedo.as<uchar4>();
     F.motion = ctx->motion.as<uint32_t>(); F.material = ctx->material.as<uchar4>(); F.emissive = ctx->emissive.as<uchar4>();
@@ -678,9 +680,10 @@ int vkp_get_counters(vkp_ctx* ctx, vkp_counters* out)
     memset(out, 0, sizeof(*out));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->counters.p) {
-        unsigned long long c[4];
+        unsigned long long c[8];
         CK(cudaMemcpy(c, ctx->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
         out->rays_primary = c[0]; out->rays_shadow = c[1]; out->rays_reflect = c[2]; out->rays_secondary_shadow = c[3];
+        out->node_fetches = c[4]; out->triangle_tests = c[5]; out->instance_entries = c[6];
     }
     if (ctx->profiling && ctx->n_ev >= 2) {
         for (int i = 0; i + 1 < ctx->n_ev; i++) {
@@ -698,6 +701,7 @@ int vkp_set_profiling(vkp_ctx* ctx, int on)
 {
     if (!ctx) return VKP_ERR_INVALID;
     ctx->profiling = on != 0;
+    ctx->count_trav = on == 2;
     return VKP_OK;
 }
 

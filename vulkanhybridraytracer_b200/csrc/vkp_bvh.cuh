@@ -33,6 +33,10 @@ struct HitRec {
     int inst, prim;
 };
 
+// what a thread's rays actually requested from memory: node fetches (64 B each in the binary layout), triangle tests (48 B)
+// and instance entries (80 B); summed per frame into the device counters for the "requested bytes" figure of bench.py
+struct TravCount { unsigned int nodes, tris, entries; };
+
 VKP_D float3 safe_inv_dir(float3 d)
 {
     // a zero component would give inf and 0*inf = NaN in the slab test; a huge finite reciprocal keeps the
@@ -105,7 +109,7 @@ VKP_D bool hit_better(float t, int inst, int prim, const HitRec& h)
 #define VKP_TRACE_FN __device__ __forceinline__
 #endif
 template <bool ANY, bool STATS = false>
-VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax, HitRec& best, uint32_t* stats = nullptr)
+VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax, HitRec& best, uint32_t* stats = nullptr, TravCount* tcount = nullptr)
 {
     uint32_t n_steps = 0, n_tris = 0;      // STATS: node pairs fetched, triangles tested
     best.t = -1.0f; best.u = 0.0f; best.v = 0.0f; best.inst = -1; best.prim = -1;
@@ -139,6 +143,7 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
         while (!(cur & VKP_LEAF_BIT)) {
             const float4* c = nodes + 2u * (size_t)cur;      // both children: 64 contiguous bytes
             if (STATS) n_steps++;
+            if (tcount) tcount->nodes++;
             float4 lo0 = __ldg(c + 0), hi0 = __ldg(c + 1), lo1 = __ldg(c + 2), hi1 = __ldg(c + 3);
             float t0, t1;
             bool h0 = box_test(lo0, hi0, ro, rd, inv, par, tmin, limit, t0);
@@ -156,6 +161,7 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
         while (!(cur & VKP_LEAF_BIT)) {
             const float4* c = nodes + 8u * (size_t)cur;
             if (STATS) n_steps++;
+            if (tcount) tcount->nodes++;
             const float4 lox = __ldg(c + 0), loy = __ldg(c + 1), loz = __ldg(c + 2), hix = __ldg(c + 3), hiy = __ldg(c + 4), hiz = __ldg(c + 5), rf = __ldg(c + 6);
             const float inf = __int_as_float(0x7f800000);
             float t0, t1, t2, t3;
@@ -190,6 +196,7 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
         if (inst < 0) {
             // ---- TLAS leaf: one instance; its id rides in the leaf reference, its record is one 80-byte fetch ----------------
             inst = (int)((cur & 0x7fffffffu) >> 3);
+            if (tcount) tcount->entries++;
             const float4* rec = reinterpret_cast<const float4*>(S.inst_trav + inst);
             const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), pp = __ldg(rec + 3), rr = __ldg(rec + 4);
             // xform_point / xform_dir with the rows of inverse(model): same association as the contract
@@ -221,6 +228,7 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
             for (uint32_t k = 0; k < 4; k++) {
                 if (k < count) {
                     if (STATS) n_tris++;
+                    if (tcount) tcount->tris++;
                     float t, u, v;
                     if (tri_test(ro, rd, f3(ta[k].x, ta[k].y, ta[k].z), f3(tb[k].x, tb[k].y, tb[k].z), f3(tc[k].x, tc[k].y, tc[k].z), tmin, tmax, t, u, v)) {
                         int prim = __float_as_int(ta[k].w);

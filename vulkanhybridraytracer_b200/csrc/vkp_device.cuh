@@ -146,6 +146,7 @@ struct DFrame {
     vkp_params p;
     // multi-GPU tiling: this context renders tiles t with t % world == rank
     int tile_w, tile_h, tiles_x, tiles_y, rank, world;
+    int count_trav;       // accumulate node fetches / triangle tests / instance entries into counters[4..6]
     int fused;            // k_resolve also runs the shadow filter (vkp_render); 0 when the stages are run one by one
     int static_camera;    // prev_view/prev_proj are bit-identical to view/proj: motion vectors are exactly 0
     // planes
