@@ -86,6 +86,13 @@ VKP_API int vkp_reset_history(vkp_ctx* ctx);
 /* results ------------------------------------------------------------------------------------- */
 VKP_API int vkp_plane_bytes(const vkp_ctx* ctx, int plane, size_t* bytes);
 VKP_API int vkp_readback(vkp_ctx* ctx, int plane, void* dst, size_t bytes);       /* syncs */
+/* Present with frames in flight -- the FRAME_OVERLAP = 2 of renderer.h:34 / get_current_frame() renderer.cpp:363: the copy of
+ * `plane` to `dst` (pinned memory) is queued behind the frames submitted so far on a copy stream and the call returns at once;
+ * vkp_readback_wait blocks until at most `keep_in_flight` of the queued copies are still outstanding (0 = all landed).  For FINAL_SRGB8 alternate vkp_set_output_buffer(ctx, k & 1) per
+ * frame: frame k+1 then renders into the other buffer while frame k is still on the bus.  A later vkp_render that would
+ * overwrite a buffer still being copied waits for that copy on the device. */
+VKP_API int vkp_readback_async(vkp_ctx* ctx, int plane, void* dst, size_t bytes);
+VKP_API int vkp_readback_wait(vkp_ctx* ctx, int keep_in_flight);
 VKP_API int vkp_upload_plane(vkp_ctx* ctx, int plane, const void* src, size_t bytes);
 VKP_API int vkp_plane_device_ptr(vkp_ctx* ctx, int plane, void** device_ptr, size_t* bytes);
 VKP_API int vkp_get_counters(vkp_ctx* ctx, vkp_counters* out);                    /* syncs */

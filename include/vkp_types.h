@@ -140,6 +140,8 @@ typedef struct vkp_counters {
     uint64_t node_fetches;          /* traversal: child-pair fetches (64 B each)            */
     uint64_t triangle_tests;        /* traversal: leaf triangles fetched + tested (48 B)    */
     uint64_t instance_entries;      /* traversal: TLAS leaves entered (80 B record each)    */
+    uint32_t worst_thread_nodes;    /* most child-pair fetches any one thread made (the kernel-tail length) ...            */
+    uint32_t worst_thread_tag;      /* ... and who: bits[31:28] stage, [27:23] light, [22:0] pixel index y*W+x            */
 } vkp_counters;
 
 /* 32-byte BVH node (both BLAS and TLAS).  ref: bit31 = leaf; leaf: bits[30:3] = first item,

@@ -106,7 +106,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_the_reference_layouts():
     for cls, size in T.SIZES.items():
         assert C.sizeof(cls) == size, cls
-    assert C.sizeof(T.Counters) == 32 + 32 + 8 + 8 + 24
+    assert C.sizeof(T.Counters) == 32 + 32 + 8 + 8 + 24 + 8
 
 
 def test_create_fails_loudly_without_a_gpu():

@@ -162,6 +162,48 @@ def test_host_engine_equals_direct_abi(small_scene):
     eng.close()
 
 
+def test_present_with_frames_in_flight_delivers_every_frame(small_scene):
+    """FRAME_OVERLAP = 2 (renderer.h:34): vkp_readback_async / Renderer::present_async hand back exactly the images a
+    synchronous read-back of each frame gives, while the next frame already renders into the other output buffer."""
+    import torch
+    detail = (4, 3, 4, 6)
+    w, h = 208, 120
+    ref = vk.HostEngine(0, w, h, 0, detail=detail)
+    want = []
+    for _ in range(5):
+        ref.frames(1); want.append(ref.read_srgb8())
+    ref.close()
+    eng = vk.HostEngine(0, w, h, 0, detail=detail)
+    pinned = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    got = []
+    for k in range(5):
+        eng.frames(1)
+        eng.present(pinned[k & 1].data_ptr(), pinned[k & 1].numel())
+        eng.present_wait(1)
+        if k:
+            got.append(pinned[(k - 1) & 1].numpy().copy())
+    eng.present_wait(0)
+    got.append(pinned[4 & 1].numpy().copy())
+    assert np.array_equal(eng.read_srgb8(), want[4])          # a synchronous read still sees the last frame
+    eng.close()
+    for k in range(5):
+        assert np.array_equal(got[k], want[k]), k
+    # raw C-ABI, single-buffered plane: the next render waits for the copy on the device
+    sc = small_scene
+    ctx = vk.Context(0); ctx.upload_scene(sc); ctx.set_camera(sc.camera(w, h))
+    buf = torch.empty((h, w, 4), dtype=torch.float32).pin_memory()
+    ctx.set_params(vk.make_params(w, h, frame=0)); ctx.render()
+    first = ctx.readback(PLANE.FINAL_F32).copy()
+    ctx.readback_async(PLANE.FINAL_F32, buf.data_ptr(), buf.numel() * 4)
+    ctx.set_params(vk.make_params(w, h, frame=0, mode=vk.MODE_DEFERRED)); ctx.render()
+    ctx.readback_wait(0)
+    assert np.array_equal(buf.numpy().view(np.uint32), first.view(np.uint32))
+    assert not np.array_equal(ctx.readback(PLANE.FINAL_F32).view(np.uint32), first.view(np.uint32))
+    with pytest.raises(vk.VkpError):
+        ctx.readback_async(PLANE.FINAL_F32, buf.data_ptr(), 16)
+    ctx.close()
+
+
 def test_tiled_rendering_composites_to_the_single_gpu_image(gpu_ctx, small_scene):
     """rank r renders tiles t % world == r; pack -> (gather) -> unpack reproduces the 1-GPU frame bit for bit."""
     import torch

@@ -84,6 +84,8 @@ def load_vkp():
         "vkp_reset_history": (i, [vp]),
         "vkp_plane_bytes": (i, [vp, i, P(sz)]),
         "vkp_readback": (i, [vp, i, vp, sz]),
+        "vkp_readback_async": (i, [vp, i, vp, sz]),
+        "vkp_readback_wait": (i, [vp, i]),
         "vkp_upload_plane": (i, [vp, i, vp, sz]),
         "vkp_plane_device_ptr": (i, [vp, i, P(vp), P(sz)]),
         "vkp_get_counters": (i, [vp, P(T.Counters)]),
@@ -147,6 +149,8 @@ def load_host():
         "vkph_engine_frames": (i, [vp, i]),
         "vkph_engine_camera_move": (i, [vp, i, C.c_float]),
         "vkph_engine_read": (i, [vp, i, vp, C.c_size_t]),
+        "vkph_engine_present": (i, [vp, vp, C.c_size_t]),
+        "vkph_engine_present_wait": (i, [vp, i]),
         "vkph_engine_counters": (i, [vp, P(T.Counters)]),
         "vkph_engine_state": (i, [vp, P(i), P(i)]),
         "vkph_engine_ctx": (vp, [vp]),
@@ -370,6 +374,13 @@ class Context:
         self._ck(self.L.vkp_readback(self.h, plane, out.ctypes.data, out.nbytes), "vkp_readback")
         return out
 
+    def readback_async(self, plane, dst_ptr, nbytes):
+        """Queue the D2H of `plane` into pinned host memory behind the frames submitted so far (frames in flight)."""
+        self._ck(self.L.vkp_readback_async(self.h, plane, C.c_void_p(dst_ptr), nbytes), "vkp_readback_async")
+
+    def readback_wait(self, keep_in_flight=0):
+        self._ck(self.L.vkp_readback_wait(self.h, keep_in_flight), "vkp_readback_wait")
+
     def upload_plane(self, plane, arr):
         dt, _ = plane_format(plane)
         arr = np.ascontiguousarray(arr, dtype=dt)
@@ -482,6 +493,15 @@ class HostEngine:
 
     def move_camera(self, direction, dt):
         self._H.vkph_engine_camera_move(self._h, direction, C.c_float(dt))
+
+    def present(self, dst_ptr, nbytes):
+        """Queue the D2H of the frame just rendered into pinned memory at dst_ptr; the next frame renders into the other buffer."""
+        if self._H.vkph_engine_present(self._h, C.c_void_p(dst_ptr), nbytes) != 0:
+            raise VkpError(self._H.vkph_last_error().decode())
+
+    def present_wait(self, keep_in_flight=0):
+        if self._H.vkph_engine_present_wait(self._h, keep_in_flight) != 0:
+            raise VkpError(self._H.vkph_last_error().decode())
 
     def read_srgb8(self):
         out = np.empty((self.height, self.width, 4), dtype=np.uint8)

@@ -475,7 +475,7 @@ __global__ void k_w_emit(const float* __restrict__ boxes, const uint32_t* __rest
 
 inline unsigned blocks_for(uint32_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
-cudaError_t fit_and_emit(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches)
+cudaError_t fit_and_emit(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches, bool read_height = true)
 {
     const uint32_t n = B.n_prims;
     cudaError_t e;
@@ -485,9 +485,10 @@ cudaError_t fit_and_emit(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches
         B.n_nodes = 1; B.height = 0;
         return cudaGetLastError();
     }
-    if ((e = cudaMemsetAsync(B.flags.p, 0, sizeof(int) * (n - 1), s)) != cudaSuccess) return e;
+    // (clears by kernel, not cudaMemsetAsync: keeps the per-frame refit off the copy engines, see launch_stage_words)
+    if ((e = launch_stage_words(s, B.flags.p, nullptr, sizeof(int) * (n - 1))) != cudaSuccess) return e;
     int* height_dev = sc.misc.as<int>();
-    if ((e = cudaMemsetAsync(height_dev, 0, sizeof(int), s)) != cudaSuccess) return e;
+    if ((e = launch_stage_words(s, height_dev, nullptr, sizeof(int))) != cudaSuccess) return e;
     k_fit<<<blocks_for(n, 256), 256, 0, s>>>(sc.boxes.as<float>(), B.items.as<uint32_t>(), (int)n, B.child.as<int2>(), B.parent.as<int>(),
                                              B.ibox.as<float4>(), B.flags.as<int>(), height_dev, B.root);
     k_emit_nodes<<<blocks_for(n - 1, 256), 256, 0, s>>>(sc.boxes.as<float>(), B.items.as<uint32_t>(), (int)n, B.child.as<int2>(), B.range.as<int2>(),
@@ -500,6 +501,8 @@ cudaError_t fit_and_emit(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches
                                                         B.nodes4.as<float4>());
         if (launches) *launches += 1;
     }
+    // a refit keeps the topology, hence the height: no D2H (a copy into pageable memory would make the per-frame path wait for the device)
+    if (!read_height) return cudaSuccess;
     return cudaMemcpyAsync(&B.height, height_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
 }
 
@@ -674,7 +677,7 @@ cudaError_t bvh_build(cudaStream_t s, BuildScratch& sc, uint32_t n, int leaf_max
 
 cudaError_t bvh_refit(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches)
 {
-    return fit_and_emit(s, sc, B, launches);
+    return fit_and_emit(s, sc, B, launches, false);
 }
 
 cudaError_t bvh_emit_triangles(cudaStream_t s, const vkp_vertex* verts, const uint32_t* indices, Bvh& B)

@@ -53,9 +53,11 @@ __device__ __forceinline__ void add_counter(unsigned long long* counters, int sl
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(&counters[slot], (unsigned long long)n);
 }
 
-__device__ __forceinline__ void add_trav(unsigned long long* counters, const TravCount& tc)
+__device__ __forceinline__ void add_trav(unsigned long long* counters, const TravCount& tc, unsigned int tag = 0u)
 {
     add_counter(counters, 4, tc.nodes); add_counter(counters, 5, tc.tris); add_counter(counters, 6, tc.entries);
+    // the thread with the longest traversal sets the kernel's tail: remember it (stage | light | pixel)
+    if (tc.nodes > 128u) atomicMax(&counters[7], ((unsigned long long)tc.nodes << 32) | tag);
 }
 
 // image store into the B8G8R8A8_UNORM target (renderer.cpp:1535) followed by postFragment.frag:9-21
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(128, VKP_LB_GBUFFER) k_gbuffer(const __grid_co
         }
     }
     add_counter(F.counters, 0, nrays);
-    if (F.count_trav) add_trav(F.counters, tc);
+    if (F.count_trav) add_trav(F.counters, tc, (0u << 28) | (unsigned)(px.valid ? px.y * F.p.width + px.x : 0));
 }
 
 // per-light pieces of shadowRaygen.rgen:55-61 that decide whether rays are traced (and hence how far the RNG advances)
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(128, VKP_LB_SHADOW) k_shadow(const __grid_cons
         }
     }
     add_counter(F.counters, 1, nrays);
-    if (F.count_trav) add_trav(F.counters, tc);
+    if (F.count_trav) add_trav(F.counters, tc, (1u << 28) | ((unsigned)l << 23) | (unsigned)(px.valid ? px.y * F.p.width + px.x : 0));
 }
 
 // blur.comp:35-82 for one pixel and one light, with runtime W/H/NLIGHTS and an integer motion fetch; returns the new
@@ -976,6 +978,24 @@ __global__ void k_l2_flush(uint4* buf, size_t n)
     for (; i < n; i += stride) buf[i] = make_uint4((unsigned)i, 1u, 2u, 3u);
 }
 
+// per-frame uniforms: copy `words` 32-bit words from mapped pinned host memory (or anywhere) into device memory, or clear them when
+// src == nullptr.  A kernel rather than a DMA: copy-engine work queued on the render stream would sit behind the present copy of
+// the previous frame in the engine's queue and serialise the frames in flight.
+__global__ void k_stage_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t words)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) dst[i] = src ? src[i] : 0u;
+}
+
+// the same for blocks of a few hundred bytes, with the data travelling as the kernel's own parameter: nothing is read over PCIe while
+// the kernel runs (a read of pinned memory queues behind the posted writes of a present copy in flight -- measured +0.1 ms/frame)
+template <int WORDS>
+struct StagePayload { uint32_t w[WORDS]; };
+template <int WORDS>
+__global__ void k_stage_inline(uint32_t* __restrict__ dst, const __grid_constant__ StagePayload<WORDS> payload, uint32_t words)
+{
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = payload.w[i];
+}
+
 __global__ void k_eval_math(int func, const float* __restrict__ x, const float* __restrict__ y, uint32_t n, float* __restrict__ out)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1038,7 +1058,7 @@ cudaError_t launch_resolve(const FrameLaunch& L, int* launches)
 }
 cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream)
 {
-    cudaError_t e = cudaMemsetAsync(L.frame.path_count, 0, sizeof(unsigned int), stream);
+    cudaError_t e = launch_stage_words(stream, L.frame.path_count, nullptr, sizeof(unsigned int));
     if (e != cudaSuccess) return e;
     k_chain<<<frame_grid(L), 128, 0, stream>>>(L.scene, L.frame);
     return cudaGetLastError();
@@ -1115,6 +1135,39 @@ cudaError_t launch_eval_math(cudaStream_t s, int func, const float* x, const flo
     k_eval_math<<<(n + 255u) / 256u, 256, 0, s>>>(func, x, y, n, out);
     return cudaGetLastError();
 }
+cudaError_t launch_stage_words(cudaStream_t s, void* dst, const void* src_or_null, size_t bytes)
+{
+    const uint32_t words = (uint32_t)(bytes / 4);
+    if (!words) return cudaSuccess;
+    unsigned blocks = (words + 255u) / 256u; if (blocks > 592u) blocks = 592u;
+    k_stage_words<<<blocks, 256, 0, s>>>((uint32_t*)dst, (const uint32_t*)src_or_null, words);
+    return cudaGetLastError();
+}
+
+template <int WORDS>
+static cudaError_t stage_inline_t(cudaStream_t s, uint32_t* dst, const uint32_t* src, uint32_t words)
+{
+    StagePayload<WORDS> p;
+    memcpy(p.w, src, sizeof(uint32_t) * words);
+    k_stage_inline<WORDS><<<1, WORDS < 256 ? WORDS : 256, 0, s>>>(dst, p, words);
+    return cudaGetLastError();
+}
+
+// bytes % 4 == 0 and bytes <= VKP_STAGE_INLINE_MAX: host data -> device memory through kernel parameters
+cudaError_t launch_stage_inline(cudaStream_t s, void* dst, const void* src, size_t bytes)
+{
+    uint32_t words = (uint32_t)(bytes / 4);
+    const uint32_t* w = (const uint32_t*)src;
+    uint32_t* d = (uint32_t*)dst;
+    while (words) {
+        const uint32_t n = words > 960u ? 960u : words;
+        cudaError_t e = n <= 64u ? stage_inline_t<64>(s, d, w, n) : n <= 256u ? stage_inline_t<256>(s, d, w, n) : stage_inline_t<960>(s, d, w, n);
+        if (e != cudaSuccess) return e;
+        words -= n; w += n; d += n;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_l2_flush(cudaStream_t s, void* buf, size_t bytes)
 {
     k_l2_flush<<<1184, 256, 0, s>>>((uint4*)buf, bytes / 16);

@@ -32,10 +32,27 @@ struct vkp_ctx {
     std::vector<vkp_instance> instances;
     std::vector<int> inst_blas;
     std::vector<std::unique_ptr<BlasRec>> blas;
-    DevBuf d_materials, d_lights, d_instances, d_textures, d_inst_trav;
+    DevBuf d_materials, d_textures;
+    // Per-frame uniforms -- lights, instance records, refitted TLAS boxes -- exist twice, like the reference's FrameData[FRAME_OVERLAP]
+    // (renderer.h:34,49): frame k+1's VulkanEngine::update work (uploads + TLAS refit) runs on `update_stream` into the set frame k
+    // is not reading, overlapped with frame k; the render stream only waits for `ev_updated`.
+    struct FrameUniforms {
+        DevBuf lights, inst_trav, instances, tlas_nodes, tlas_nodes4;
+        unsigned long long lights_ver = 0, inst_ver = 0;       // version of the host state this set holds (0 = nothing)
+        cudaEvent_t last_use = nullptr;                         // end of the last frame that read the set
+        bool consumed = false;                                  // a frame has read it since it was last written
+    };
+    FrameUniforms uni[2];
+    int ucur = 0;
+    unsigned long long lights_ver = 0, inst_ver = 0;            // host-side versions: bumped by vkp_set_lights / vkp_build_tlas
+    std::vector<DInstance> h_inst;                              // host mirrors of the device records of the current instances
+    std::vector<DInstTrav> h_trav;
+    cudaStream_t update_stream = nullptr;
+    cudaEvent_t ev_updated = nullptr;
+    bool update_pending = false;
     Bvh tlas;
     BuildScratch scratch, tlas_scratch;
-    bool blas_built = false, tlas_built = false, textures_dirty = true;
+    bool blas_built = false, tlas_built = false, tlas_topology = false, textures_dirty = true;
 
     vkp_camera cam{};
     vkp_params params{};
@@ -55,6 +72,16 @@ struct vkp_ctx {
     DevBuf final_srgb8_alt;
     int out_sel = 0;
     std::vector<void*> ipc_opened;
+    // present with frames in flight (vkp_readback_async): D2H copies run on their own stream behind the frame that produced them
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_frame_done = nullptr, ev_copy_done[3] = {nullptr, nullptr, nullptr};   // [0],[1]: the two sRGB8 buffers, [2]: any other plane
+    bool copy_pending[3] = {false, false, false};
+    // per-frame uniforms (lights, instance records) go through a ring of pinned staging slabs: no host<->device rendezvous per frame
+    struct StageSlot { void* host = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool pending = false; };
+    StageSlot stage_ring[8];
+    unsigned stage_seq = 0;
+    cudaEvent_t ev_copy_ring[4] = {nullptr, nullptr, nullptr, nullptr};   // completion of the last 4 queued copies, by sequence number
+    unsigned long long copy_seq = 0;
 
     bool profiling = false;
     bool count_trav = false;
@@ -74,6 +101,32 @@ int fail(vkp_ctx* c, int code, const std::string& msg)
     if (c) c->err = msg; else g_create_error = msg;
     return code;
 }
+// H2D of a small pageable block, stream-ordered, without blocking on the frames in flight (a pageable cudaMemcpyAsync would
+// rendezvous with the stream).  The slab is reused 8 uploads later; its event guards that.
+cudaError_t upload_staged(vkp_ctx* ctx, cudaStream_t stream, void* dst, const void* src, size_t bytes)
+{
+    if (!bytes) return cudaSuccess;
+    if (bytes % 4 == 0 && bytes <= VKP_STAGE_INLINE_MAX) return launch_stage_inline(stream, dst, src, bytes);     // rides in the kernel parameters
+    vkp_ctx::StageSlot& sl = ctx->stage_ring[ctx->stage_seq++ & 7u];
+    cudaError_t e;
+    if (!sl.done && (e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if (sl.pending) { if ((e = cudaEventSynchronize(sl.done)) != cudaSuccess) return e; sl.pending = false; }
+    if (sl.cap < bytes) {
+        if (sl.host) cudaFreeHost(sl.host);
+        sl.host = nullptr; sl.cap = 0;
+        size_t cap = 4096; while (cap < bytes) cap <<= 1;
+        if ((e = cudaMallocHost(&sl.host, cap)) != cudaSuccess) return e;
+        sl.cap = cap;
+    }
+    memcpy(sl.host, src, bytes);
+    if (bytes % 4 == 0) e = launch_stage_words(stream, dst, sl.host, bytes);       // pinned memory is device-visible under UVA; no copy engine involved
+    else e = cudaMemcpyAsync(dst, sl.host, bytes, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaEventRecord(sl.done, stream)) != cudaSuccess) return e;
+    sl.pending = true;
+    return cudaSuccess;
+}
+
 int cuda_fail(vkp_ctx* c, cudaError_t e, const char* what)
 {
     return fail(c, e == cudaErrorMemoryAllocation ? VKP_ERR_OOM : VKP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -159,6 +212,79 @@ int upload_textures(vkp_ctx* ctx)
     return VKP_OK;
 }
 
+// Brings the uniform set the next frame will read up to date with the host state, on the update stream.  If the current set has
+// been read by a frame since it was written, the other set is taken (after the last frame that read *it*), so the frame in flight
+// is never disturbed and never waited for on the host.
+int flush_uniforms(vkp_ctx* ctx, bool lights_only = false)
+{
+    vkp_ctx::FrameUniforms* U = &ctx->uni[ctx->ucur];
+    const bool want_tlas = ctx->tlas_built;
+    if (U->lights_ver == ctx->lights_ver && (!want_tlas || U->inst_ver == ctx->inst_ver)) return VKP_OK;
+    if (!ctx->update_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CK(cudaStreamCreateWithPriority(&ctx->update_stream, cudaStreamNonBlocking, hi));      // its few small CTAs go first
+        CK(cudaEventCreateWithFlags(&ctx->ev_updated, cudaEventDisableTiming));
+        for (auto& u : ctx->uni) CK(cudaEventCreateWithFlags(&u.last_use, cudaEventDisableTiming));
+    }
+    cudaStream_t us = ctx->update_stream;
+    if (U->consumed) { ctx->ucur ^= 1; U = &ctx->uni[ctx->ucur]; }
+    if (U->consumed) { CK(cudaStreamWaitEvent(us, U->last_use, 0)); U->consumed = false; }
+    if (U->lights_ver != ctx->lights_ver) {
+        const size_t n = ctx->lights.size();
+        CK(U->lights.ensure(sizeof(vkp_light) * (n ? n : 1)));
+        if (n) CK(upload_staged(ctx, us, U->lights.p, ctx->lights.data(), sizeof(vkp_light) * n));
+        U->lights_ver = ctx->lights_ver;
+    }
+    if (want_tlas && !lights_only && U->inst_ver != ctx->inst_ver) {     // (lights_only: vkp_build_tlas or the next frame finishes the set)
+        const uint32_t n = (uint32_t)ctx->instances.size();
+        CK(U->inst_trav.ensure(sizeof(DInstTrav) * ctx->h_trav.size()));
+        CK(U->instances.ensure(sizeof(DInstance) * ctx->h_inst.size()));
+        CK(U->tlas_nodes.ensure(ctx->tlas.nodes.bytes ? ctx->tlas.nodes.bytes : sizeof(vkp_bvh_node)));
+        if (ctx->tlas.nodes4.bytes) CK(U->tlas_nodes4.ensure(ctx->tlas.nodes4.bytes));
+        CK(upload_staged(ctx, us, U->inst_trav.p, ctx->h_trav.data(), sizeof(DInstTrav) * ctx->h_trav.size()));
+        CK(upload_staged(ctx, us, U->instances.p, ctx->h_inst.data(), sizeof(DInstance) * ctx->h_inst.size()));
+        CK(ctx->tlas_scratch.boxes.ensure(sizeof(float) * 6 * (size_t)(n ? n : 1)));
+        CK(bvh_instance_boxes(us, U->instances.as<DInstance>(), n, ctx->tlas_scratch.boxes.as<float>()));
+        // refit on the topology of the last full build, boxes written into this set's node arrays
+        std::swap(ctx->tlas.nodes, U->tlas_nodes); std::swap(ctx->tlas.nodes4, U->tlas_nodes4);
+        int launches = 0;
+        cudaError_t e = bvh_refit(us, ctx->tlas_scratch, ctx->tlas, &launches);
+        std::swap(ctx->tlas.nodes, U->tlas_nodes); std::swap(ctx->tlas.nodes4, U->tlas_nodes4);
+        CK(e);
+        U->inst_ver = ctx->inst_ver;
+    }
+    CK(cudaEventRecord(ctx->ev_updated, us));
+    ctx->update_pending = true;
+    return VKP_OK;
+}
+
+// geometry + light pointers of the current uniform set; the caller's stream work is ordered behind the pending update
+int scene_uniforms(vkp_ctx* ctx, DScene& S)
+{
+    int r = flush_uniforms(ctx);
+    if (r != VKP_OK) return r;
+    if (ctx->update_pending) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_updated, 0)); ctx->update_pending = false; }
+    vkp_ctx::FrameUniforms& U = ctx->uni[ctx->ucur];
+    S.tlas_nodes4 = U.tlas_nodes4.as<float4>(); S.tlas_root_ref = ctx->tlas.root_ref4;
+    S.tlas_nodes2 = U.tlas_nodes.as<float4>(); S.tlas_root_ref2 = ctx->tlas.root_ref;
+    S.instances = U.instances.as<DInstance>();
+    S.inst_trav = U.inst_trav.as<DInstTrav>();
+    S.lights = U.lights.as<vkp_light>();
+    S.n_instances = (int)ctx->instances.size();
+    S.n_lights = (int)ctx->lights.size();
+    U.consumed = true;
+    return VKP_OK;
+}
+
+// after the last launch that reads the scene: the set may be rewritten once this point of the stream has passed
+int mark_scene_use(vkp_ctx* ctx)
+{
+    vkp_ctx::FrameUniforms& U = ctx->uni[ctx->ucur];
+    if (U.last_use) CK(cudaEventRecord(U.last_use, ctx->stream));
+    return VKP_OK;
+}
+
 int make_scene(vkp_ctx* ctx, DScene& S)
 {
     if (!ctx->tlas_built) return fail(ctx, VKP_ERR_INVALID, "acceleration structures are not built (vkp_build_blas / vkp_build_tlas)");
@@ -166,13 +292,9 @@ int make_scene(vkp_ctx* ctx, DScene& S)
     if (ctx->materials.empty()) return fail(ctx, VKP_ERR_INVALID, "vkp_set_materials has not been called");
     int r = upload_textures(ctx);
     if (r != VKP_OK) return r;
+    if ((r = scene_uniforms(ctx, S)) != VKP_OK) return r;
     S.lut_pow22 = ctx->luts.as<float>();
-    S.tlas_nodes4 = ctx->tlas.nodes4.as<float4>(); S.tlas_root_ref = ctx->tlas.root_ref4;
-    S.tlas_nodes2 = ctx->tlas.nodes.as<float4>(); S.tlas_root_ref2 = ctx->tlas.root_ref;
-    S.instances = ctx->d_instances.as<DInstance>();
-    S.inst_trav = ctx->d_inst_trav.as<DInstTrav>();
     S.materials = ctx->d_materials.as<vkp_material>();
-    S.lights = ctx->d_lights.as<vkp_light>();
     S.textures = ctx->d_textures.as<DTexture>();
     S.n_instances = (int)ctx->instances.size(); S.n_materials = (int)ctx->materials.size();
     S.n_lights = (int)ctx->lights.size(); S.n_textures = (int)ctx->textures.size();
@@ -315,12 +437,20 @@ void vkp_destroy(vkp_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->update_stream) cudaStreamSynchronize(ctx->update_stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
     for (auto& m : ctx->meshes) { m->verts.release(); m->idx.release(); }
     for (auto& t : ctx->textures) t->texels.release();
     for (auto& b : ctx->blas) b->bvh.release();
     ctx->tlas.release(); ctx->scratch.release(); ctx->tlas_scratch.release();
-    DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_lights, &ctx->d_instances, &ctx->d_textures, &ctx->d_inst_trav, &ctx->position, &ctx->normal, &ctx->albedo, &ctx->motion,
+    for (auto& U : ctx->uni) {
+        U.lights.release(); U.inst_trav.release(); U.instances.release(); U.tlas_nodes.release(); U.tlas_nodes4.release();
+        if (U.last_use) cudaEventDestroy(U.last_use);
+    }
+    if (ctx->update_stream) cudaStreamDestroy(ctx->update_stream);
+    if (ctx->ev_updated) cudaEventDestroy(ctx->ev_updated);
+    DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_textures, &ctx->position, &ctx->normal, &ctx->albedo, &ctx->motion,
                       &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
                       &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->final_srgb8_alt};
     for (DevBuf* b : bufs) b->release();
@@ -328,6 +458,11 @@ void vkp_destroy(vkp_ctx* ctx)
     if (ctx->timer0) cudaEventDestroy(ctx->timer0);
     if (ctx->timer1) cudaEventDestroy(ctx->timer1);
     if (ctx->chain_stream) cudaStreamDestroy(ctx->chain_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ev_frame_done) cudaEventDestroy(ctx->ev_frame_done);
+    for (auto& ev : ctx->ev_copy_done) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_copy_ring) if (ev) cudaEventDestroy(ev);
+    for (auto& sl : ctx->stage_ring) { if (sl.host) cudaFreeHost(sl.host); if (sl.done) cudaEventDestroy(sl.done); }
     if (ctx->ev_gbuffer) cudaEventDestroy(ctx->ev_gbuffer);
     if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -400,12 +535,9 @@ int vkp_set_lights(vkp_ctx* ctx, const vkp_light* l, int n)
 {
     if (!ctx || (n > 0 && !l) || n < 0 || n > VKP_MAX_LIGHTS) return fail(ctx, VKP_ERR_INVALID, "vkp_set_lights: bad argument (0..32 lights)");
     CK(cudaSetDevice(ctx->device));
-    // the previous frame may still be reading the staging vector through an async copy: order on the stream
-    CK(cudaStreamSynchronize(ctx->stream));
     ctx->lights.assign(l, l + n);
-    CK(ctx->d_lights.ensure(sizeof(vkp_light) * (n ? n : 1)));
-    if (n) CK(cudaMemcpyAsync(ctx->d_lights.p, ctx->lights.data(), sizeof(vkp_light) * n, cudaMemcpyHostToDevice, ctx->stream));
-    return VKP_OK;
+    ctx->lights_ver++;
+    return flush_uniforms(ctx, true);          // on the update stream, beside the frame in flight
 }
 
 int vkp_set_instances(vkp_ctx* ctx, const vkp_instance* inst, int n)
@@ -416,7 +548,6 @@ int vkp_set_instances(vkp_ctx* ctx, const vkp_instance* inst, int n)
         const MeshRec& m = *ctx->meshes[inst[i].mesh_id];
         if (inst[i].index_count % 3u || (uint64_t)inst[i].first_index + inst[i].index_count > m.ni) return fail(ctx, VKP_ERR_INVALID, "vkp_set_instances: index range out of the mesh");
     }
-    CK(cudaStreamSynchronize(ctx->stream));
     ctx->instances.assign(inst, inst + n);
     ctx->tlas_built = false;
     return VKP_OK;
@@ -464,8 +595,8 @@ int vkp_build_tlas(vkp_ctx* ctx, int update)
     if (!ctx->blas_built) return fail(ctx, VKP_ERR_INVALID, "vkp_build_tlas: call vkp_build_blas first");
     CK(cudaSetDevice(ctx->device));
     const int n = (int)ctx->instances.size();
-    std::vector<DInstance> d(n ? n : 1);
-    std::vector<DInstTrav> tv(n ? n : 1);
+    std::vector<DInstance>& d = ctx->h_inst; std::vector<DInstTrav>& tv = ctx->h_trav;
+    d.assign(n ? n : 1, DInstance{}); tv.assign(n ? n : 1, DInstTrav{});
     for (int i = 0; i < n; i++) {
         const vkp_instance& I = ctx->instances[i];
         BlasRec* rec = nullptr;
@@ -481,18 +612,26 @@ int vkp_build_tlas(vkp_ctx* ctx, int update)
         tv[i].nodes = rec->bvh.nodes4.as<float4>(); tv[i].tris = rec->bvh.tris.as<float4>(); tv[i].root_ref = rec->bvh.root_ref4;
         tv[i].nodes2 = rec->bvh.nodes.as<float4>(); tv[i].root_ref2 = rec->bvh.root_ref;
     }
-    CK(ctx->d_inst_trav.ensure(sizeof(DInstTrav) * tv.size()));
-    CK(cudaMemcpyAsync(ctx->d_inst_trav.p, tv.data(), sizeof(DInstTrav) * tv.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(ctx->d_instances.ensure(sizeof(DInstance) * d.size()));
-    CK(cudaMemcpyAsync(ctx->d_instances.p, d.data(), sizeof(DInstance) * d.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(ctx->tlas_scratch.boxes.ensure(sizeof(float) * 6 * (size_t)(n ? n : 1)));
-    CK(bvh_instance_boxes(ctx->stream, ctx->d_instances.as<DInstance>(), (uint32_t)n, ctx->tlas_scratch.boxes.as<float>()));
-    int launches = 0;
-    if (update && ctx->tlas.n_prims == (uint32_t)n && ctx->tlas.n_nodes > 0) CK(bvh_refit(ctx->stream, ctx->tlas_scratch, ctx->tlas, &launches));
-    else CK(bvh_build(ctx->stream, ctx->tlas_scratch, (uint32_t)n, 1, ctx->tlas, &launches, 0));
-    CK(cudaStreamSynchronize(ctx->stream));   // `d` is a stack vector the async copy reads
+    const bool refit = update && ctx->tlas_topology && ctx->tlas.n_prims == (uint32_t)n && ctx->tlas.n_nodes > 0;
+    if (!refit) {
+        // full build (topology): rare and synchronous.  Nothing may be in flight on either stream while the shared arrays are rebuilt.
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->update_stream) CK(cudaStreamSynchronize(ctx->update_stream));
+        vkp_ctx::FrameUniforms& U = ctx->uni[ctx->ucur];
+        CK(U.instances.ensure(sizeof(DInstance) * d.size()));
+        CK(cudaMemcpy(U.instances.p, d.data(), sizeof(DInstance) * d.size(), cudaMemcpyHostToDevice));
+        CK(ctx->tlas_scratch.boxes.ensure(sizeof(float) * 6 * (size_t)(n ? n : 1)));
+        CK(bvh_instance_boxes(ctx->stream, U.instances.as<DInstance>(), (uint32_t)n, ctx->tlas_scratch.boxes.as<float>()));
+        int launches = 0;
+        CK(bvh_build(ctx->stream, ctx->tlas_scratch, (uint32_t)n, 1, ctx->tlas, &launches, 0));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->tlas_topology = true;
+        for (auto& u : ctx->uni) { u.consumed = false; u.inst_ver = 0; }
+    }
+    // both sets are now stale; the one the next frame reads is brought up to date here, overlapping whatever frame is in flight
+    ctx->inst_ver++;
     ctx->tlas_built = true;
-    return VKP_OK;
+    return flush_uniforms(ctx);
 }
 
 int vkp_set_camera(vkp_ctx* ctx, const vkp_camera* cam)
@@ -529,7 +668,13 @@ int vkp_render(vkp_ctx* ctx)
     int r = make_launch(ctx, L);
     if (r != VKP_OK) return r;
     ctx->n_ev = 0; ctx->last_launches = 0;
-    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
+    // a D2H copy still reading a buffer this frame overwrites (vkp_readback_async) is waited for on the device, not the host
+    for (int b = 0; b < 3; b++) {
+        if (!ctx->copy_pending[b] || (b < 2 && b != ctx->out_sel)) continue;
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[b], 0));
+        ctx->copy_pending[b] = false;
+    }
+    CK(launch_stage_words(ctx->stream, ctx->counters.p, nullptr, 64));
     static const int hybrid[] = {VKP_STAGE_GBUFFER, VKP_STAGE_SHADOW, VKP_STAGE_DENOISE, VKP_STAGE_RESOLVE};
     static const int hybrid_fused[] = {VKP_STAGE_GBUFFER, VKP_STAGE_SHADOW, VKP_STAGE_RESOLVE};
     static const int rt[] = {VKP_STAGE_RAYTRACE};
@@ -553,6 +698,7 @@ int vkp_render(vkp_ctx* ctx)
             ctx->last_launches++;
         }
     }
+    if ((r = mark_scene_use(ctx)) != VKP_OK) return r;
     return stage_event(ctx, -1);
 }
 
@@ -564,8 +710,9 @@ int vkp_run_stage(vkp_ctx* ctx, int stage)
     int r = make_launch(ctx, L);
     if (r != VKP_OK) return r;
     ctx->n_ev = 0; ctx->last_launches = 0;
-    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
+    CK(launch_stage_words(ctx->stream, ctx->counters.p, nullptr, 64));
     if ((r = run_one(ctx, L, stage)) != VKP_OK) return r;
+    if ((r = mark_scene_use(ctx)) != VKP_OK) return r;
     return stage_event(ctx, -1);
 }
 
@@ -573,6 +720,7 @@ int vkp_sync(vkp_ctx* ctx)
 {
     if (!ctx) return VKP_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->update_stream) CK(cudaStreamSynchronize(ctx->update_stream));
     return VKP_OK;
 }
 
@@ -607,6 +755,42 @@ int vkp_readback(vkp_ctx* ctx, int plane, void* dst, size_t bytes)
     if (bytes < need) return fail(ctx, VKP_ERR_INVALID, "vkp_readback: destination too small");
     CK(cudaMemcpyAsync(dst, p, need, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return VKP_OK;
+}
+
+int vkp_readback_async(vkp_ctx* ctx, int plane, void* dst, size_t bytes)
+{
+    if (!ctx || !dst) return fail(ctx, VKP_ERR_INVALID, "vkp_readback_async: NULL");
+    int r = ensure_planes(ctx);
+    if (r != VKP_OK) return r;
+    void* p = plane_ptr(ctx, plane);
+    size_t need = plane_elem_bytes(plane) * (size_t)ctx->plane_w * ctx->plane_h;
+    if (!p || !need) return fail(ctx, VKP_ERR_INVALID, "vkp_readback_async: unknown plane");
+    if (bytes < need) return fail(ctx, VKP_ERR_INVALID, "vkp_readback_async: destination too small");
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_frame_done, cudaEventDisableTiming));
+        for (auto& ev : ctx->ev_copy_done) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : ctx->ev_copy_ring) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    const int slot = plane == VKP_PLANE_FINAL_SRGB8 ? ctx->out_sel : 2;
+    CK(cudaEventRecord(ctx->ev_frame_done, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_frame_done, 0));
+    CK(cudaMemcpyAsync(dst, p, need, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_copy_done[slot], ctx->copy_stream));
+    ctx->copy_pending[slot] = true;
+    CK(cudaEventRecord(ctx->ev_copy_ring[ctx->copy_seq & 3ull], ctx->copy_stream));
+    ctx->copy_seq++;
+    return VKP_OK;
+}
+
+int vkp_readback_wait(vkp_ctx* ctx, int keep_in_flight)
+{
+    if (!ctx || keep_in_flight < 0) return VKP_ERR_INVALID;
+    if (!ctx->copy_stream || ctx->copy_seq <= (unsigned long long)keep_in_flight) return VKP_OK;
+    if (keep_in_flight >= 4) return VKP_OK;      // the ring remembers 4 copies: nothing older can still be pending
+    if (keep_in_flight == 0) { CK(cudaStreamSynchronize(ctx->copy_stream)); return VKP_OK; }
+    CK(cudaEventSynchronize(ctx->ev_copy_ring[(ctx->copy_seq - 1ull - (unsigned long long)keep_in_flight) & 3ull]));
     return VKP_OK;
 }
 
@@ -684,6 +868,7 @@ int vkp_get_counters(vkp_ctx* ctx, vkp_counters* out)
         CK(cudaMemcpy(c, ctx->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
         out->rays_primary = c[0]; out->rays_shadow = c[1]; out->rays_reflect = c[2]; out->rays_secondary_shadow = c[3];
         out->node_fetches = c[4]; out->triangle_tests = c[5]; out->instance_entries = c[6];
+        out->worst_thread_nodes = (uint32_t)(c[7] >> 32); out->worst_thread_tag = (uint32_t)c[7];
     }
     if (ctx->profiling && ctx->n_ev >= 2) {
         for (int i = 0; i + 1 < ctx->n_ev; i++) {
@@ -713,15 +898,13 @@ int vkp_trace_rays(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, v
     // tracing needs only geometry: tolerate a missing environment / materials
     if (!ctx->tlas_built) return fail(ctx, VKP_ERR_INVALID, "vkp_trace_rays: acceleration structures are not built");
     memset(&S, 0, sizeof(S));
-    S.tlas_nodes4 = ctx->tlas.nodes4.as<float4>(); S.tlas_root_ref = ctx->tlas.root_ref4;
-    S.tlas_nodes2 = ctx->tlas.nodes.as<float4>(); S.tlas_root_ref2 = ctx->tlas.root_ref;
-    S.instances = ctx->d_instances.as<DInstance>(); S.n_instances = (int)ctx->instances.size();
-    S.inst_trav = ctx->d_inst_trav.as<DInstTrav>();
+    { int r = scene_uniforms(ctx, S); if (r != VKP_OK) return r; }
     if (n == 0) return VKP_OK;
     CK(ctx->io_tmp.ensure(sizeof(vkp_ray) * (size_t)n));
     CK(ctx->io_tmp2.ensure(sizeof(vkp_hit) * (size_t)n));
     CK(cudaMemcpyAsync(ctx->io_tmp.p, rays, sizeof(vkp_ray) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(launch_trace_rays(ctx->stream, S, ctx->io_tmp.as<vkp_ray>(), n, any_hit, ctx->io_tmp2.as<vkp_hit>()));
+    { int r = mark_scene_use(ctx); if (r != VKP_OK) return r; }
     CK(cudaMemcpyAsync(hits, ctx->io_tmp2.p, sizeof(vkp_hit) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return VKP_OK;
@@ -733,15 +916,13 @@ int vkp_trace_stats(vkp_ctx* ctx, const vkp_ray* rays, uint32_t n, int any_hit, 
     CK(cudaSetDevice(ctx->device));
     if (!ctx->tlas_built) return fail(ctx, VKP_ERR_INVALID, "vkp_trace_stats: acceleration structures are not built");
     DScene S; memset(&S, 0, sizeof(S));
-    S.tlas_nodes4 = ctx->tlas.nodes4.as<float4>(); S.tlas_root_ref = ctx->tlas.root_ref4;
-    S.tlas_nodes2 = ctx->tlas.nodes.as<float4>(); S.tlas_root_ref2 = ctx->tlas.root_ref;
-    S.instances = ctx->d_instances.as<DInstance>(); S.n_instances = (int)ctx->instances.size();
-    S.inst_trav = ctx->d_inst_trav.as<DInstTrav>();
+    { int r = scene_uniforms(ctx, S); if (r != VKP_OK) return r; }
     if (n == 0) return VKP_OK;
     CK(ctx->io_tmp.ensure(sizeof(vkp_ray) * (size_t)n));
     CK(ctx->io_tmp2.ensure(sizeof(uint32_t) * 3 * (size_t)n));
     CK(cudaMemcpyAsync(ctx->io_tmp.p, rays, sizeof(vkp_ray) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(launch_trace_stats(ctx->stream, S, ctx->io_tmp.as<vkp_ray>(), n, any_hit, ctx->io_tmp2.as<uint32_t>()));
+    { int r = mark_scene_use(ctx); if (r != VKP_OK) return r; }
     CK(cudaMemcpyAsync(steps_and_tris, ctx->io_tmp2.p, sizeof(uint32_t) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return VKP_OK;
@@ -793,8 +974,15 @@ int vkp_bvh_download(vkp_ctx* ctx, int blas_index, vkp_bvh_node* nodes, uint32_t
     if (!ctx) return VKP_ERR_INVALID;
     Bvh* b = pick_bvh(ctx, blas_index);
     if (!b) return fail(ctx, VKP_ERR_INVALID, "vkp_bvh_download: no such BVH");
+    const void* nodes_src = b->nodes.p;
+    if (blas_index < 0) {      // the TLAS boxes live in the current uniform set (refitted per frame), the topology in ctx->tlas
+        int r = flush_uniforms(ctx);
+        if (r != VKP_OK) return r;
+        if (ctx->update_stream) CK(cudaStreamSynchronize(ctx->update_stream));
+        nodes_src = ctx->uni[ctx->ucur].tlas_nodes.p;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
-    if (nodes) CK(cudaMemcpy(nodes, b->nodes.p, sizeof(vkp_bvh_node) * (size_t)b->n_nodes, cudaMemcpyDeviceToHost));
+    if (nodes) CK(cudaMemcpy(nodes, nodes_src, sizeof(vkp_bvh_node) * (size_t)b->n_nodes, cudaMemcpyDeviceToHost));
     if (prim_ids && b->n_prims) CK(cudaMemcpy(prim_ids, b->items.p, sizeof(uint32_t) * (size_t)b->n_prims, cudaMemcpyDeviceToHost));
     return VKP_OK;
 }

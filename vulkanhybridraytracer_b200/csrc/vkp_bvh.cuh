@@ -59,10 +59,16 @@ VKP_D bool box_test(const float4 lo, const float4 hi, float3 o, float3 d, float3
     float y0 = (lo.y - o.y) * inv.y, y1 = (hi.y - o.y) * inv.y;
     float z0 = (lo.z - o.z) * inv.z, z1 = (hi.z - o.z) * inv.z;
     if (PAR) {
+        // A ray parallel to a slab is inside it for every t or for none.  "None" has to leave here: no (t0, t1) pair survives
+        // the min / max below as an empty interval.  (It used to be encoded as (+inf, -inf), which the min / max turned back
+        // into "unbounded": such rays -- one per few frames, when a light sample cancels a coordinate exactly -- were never
+        // culled on that axis, walked thousands of nodes and set the tail of the whole kernel.)  The slack keeps the test
+        // conservative against the rounding of the triangle test for rays that run along a face of the box.
         const float inf = __int_as_float(0x7f800000);
-        if (fabsf(d.x) <= 1e-30f) { bool in = lo.x <= o.x && o.x <= hi.x; x0 = in ? -inf : inf; x1 = in ? inf : -inf; }
-        if (fabsf(d.y) <= 1e-30f) { bool in = lo.y <= o.y && o.y <= hi.y; y0 = in ? -inf : inf; y1 = in ? inf : -inf; }
-        if (fabsf(d.z) <= 1e-30f) { bool in = lo.z <= o.z && o.z <= hi.z; z0 = in ? -inf : inf; z1 = in ? inf : -inf; }
+        tnear = inf;
+        if (fabsf(d.x) <= 1e-30f) { const float s = 1e-5f * fmaxf(fabsf(o.x), fmaxf(fabsf(lo.x), fabsf(hi.x))); if (lo.x - o.x > s || o.x - hi.x > s) return false; x0 = -inf; x1 = inf; }
+        if (fabsf(d.y) <= 1e-30f) { const float s = 1e-5f * fmaxf(fabsf(o.y), fmaxf(fabsf(lo.y), fabsf(hi.y))); if (lo.y - o.y > s || o.y - hi.y > s) return false; y0 = -inf; y1 = inf; }
+        if (fabsf(d.z) <= 1e-30f) { const float s = 1e-5f * fmaxf(fabsf(o.z), fmaxf(fabsf(lo.z), fabsf(hi.z))); if (lo.z - o.z > s || o.z - hi.z > s) return false; z0 = -inf; z1 = inf; }
     }
     float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
     float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));

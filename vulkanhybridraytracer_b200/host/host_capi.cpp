@@ -149,6 +149,22 @@ VKPH_API int vkph_engine_read(void* p, int linear, void* dst, size_t bytes)
     } catch (const std::exception& ex) { g_err = ex.what(); return -1; }
 }
 
+// present with FRAME_OVERLAP frames in flight: queue the D2H of the frame just rendered into pinned `dst`; wait = all landed
+VKPH_API int vkph_engine_present(void* p, void* dst, size_t bytes)
+{
+    VulkanEngine* e = (VulkanEngine*)p;
+    try {
+        size_t need = (size_t)e->_width * e->_height * 4;
+        if (bytes < need) { g_err = "vkph_engine_present: destination too small"; return -1; }
+        e->renderer->present_async(dst, need);
+        return 0;
+    } catch (const std::exception& ex) { g_err = ex.what(); return -1; }
+}
+VKPH_API int vkph_engine_present_wait(void* p, int keep_in_flight)
+{
+    try { ((VulkanEngine*)p)->renderer->present_wait(keep_in_flight); return 0; } catch (const std::exception& ex) { g_err = ex.what(); return -1; }
+}
+
 VKPH_API int vkph_engine_counters(void* p, vkp_counters* out)
 {
     VulkanEngine* e = (VulkanEngine*)p;

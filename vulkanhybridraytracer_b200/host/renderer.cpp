@@ -89,8 +89,18 @@ void Renderer::submit(renderMode mode)
     p.mode = (int)mode;
     VKP_CHECK(vkp_set_params(_ctx, &p));
     VKP_CHECK(vkp_set_camera(_ctx, &e->_cameraData));
+    VKP_CHECK(vkp_set_output_buffer(_ctx, _frameSlot));
     VKP_CHECK(vkp_render(_ctx));
 }
+
+// The swapchain present of the reference with FRAME_OVERLAP = 2 frames in flight (renderer.h:34, get_current_frame renderer.cpp:363):
+// the image of the frame just submitted starts its way to `dst` and the next frame renders into the other output buffer meanwhile.
+void Renderer::present_async(void* dst, size_t bytes)
+{
+    VKP_CHECK(vkp_readback_async(_ctx, VKP_PLANE_FINAL_SRGB8, dst, bytes));
+    _frameSlot ^= 1;
+}
+void Renderer::present_wait(int keep_in_flight) { VKP_CHECK(vkp_readback_wait(_ctx, keep_in_flight)); }
 
 void Renderer::render() { submit(DEFERRED); }
 void Renderer::raytrace() { submit(RAYTRACING); }

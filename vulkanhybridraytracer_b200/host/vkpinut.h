@@ -244,6 +244,9 @@ public:
     std::vector<uint8_t> read_final_srgb8();
     std::vector<float> read_final_linear();
     void read_into(int plane, void* dst, size_t bytes);   // straight into caller (e.g. pinned) memory
+    void present_async(void* dst, size_t bytes);          // queue the D2H of the frame just submitted, flip the output buffer
+    void present_wait(int keep_in_flight = 0);            // until at most keep_in_flight queued presents are outstanding
+    int _frameSlot{0};                                    // _frameNumber % FRAME_OVERLAP (renderer.cpp:363)
     vkp_counters counters();
 
 private:

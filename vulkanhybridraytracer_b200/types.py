@@ -43,7 +43,8 @@ class Hit(C.Structure):             # vkp_hit, 20 B
 class Counters(C.Structure):        # vkp_counters
     _fields_ = [("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_reflect", C.c_uint64), ("rays_secondary_shadow", C.c_uint64),
                 ("ms_stage", C.c_float * 8), ("ms_tlas", C.c_float), ("ms_frame", C.c_float), ("kernel_launches", C.c_uint32), ("_pad", C.c_uint32),
-                ("node_fetches", C.c_uint64), ("triangle_tests", C.c_uint64), ("instance_entries", C.c_uint64)]
+                ("node_fetches", C.c_uint64), ("triangle_tests", C.c_uint64), ("instance_entries", C.c_uint64),
+                ("worst_thread_nodes", C.c_uint32), ("worst_thread_tag", C.c_uint32)]
 
 
 class BvhNode(C.Structure):         # vkp_bvh_node, 32 B
