@@ -31,11 +31,11 @@ namespace {
 
 struct Pixel { int x, y; bool valid; };
 
-__device__ __forceinline__ Pixel pixel_of_thread(const DFrame& F)
+__device__ __forceinline__ Pixel pixel_of_block(const DFrame& F, const unsigned int block)
 {
     const int bpt_x = F.tile_w >> 4, bpt_y = F.tile_h >> 3;
     const int bpt = bpt_x * bpt_y;
-    const int own_tile = blockIdx.x / bpt, sub = blockIdx.x - own_tile * bpt;
+    const int own_tile = (int)block / bpt, sub = (int)block - own_tile * bpt;
     const int tile = F.rank + own_tile * F.world;
     const int tx = tile % F.tiles_x, ty = tile / F.tiles_x;
     const int sbx = sub % bpt_x, sby = sub / bpt_x;
@@ -45,6 +45,60 @@ __device__ __forceinline__ Pixel pixel_of_thread(const DFrame& F)
     p.y = ty * F.tile_h + sby * 8 + (warp >> 1) * 4 + (lane >> 3);
     p.valid = p.x < F.p.width && p.y < F.p.height;
     return p;
+}
+
+__device__ __forceinline__ Pixel pixel_of_thread(const DFrame& F) { return pixel_of_block(F, blockIdx.x); }
+
+// Longest-first scheduling.  A frame kernel ends with its slowest thread, and which pixels are slow (rays grazing the dense meshes)
+// hardly changes from one frame to the next: every warp leaves the cycles it took in cost[virtual block]; k_build_order turns
+// last frame's costs into this frame's block order, expensive blocks first, so that the long traversals start at t = 0
+// instead of in the last wave.  Only the schedule changes -- every pixel is still computed by exactly one thread.
+__device__ __forceinline__ unsigned int virtual_block(const uint32_t* __restrict__ order) { return order ? __ldg(order + blockIdx.x) : blockIdx.x; }
+__device__ __forceinline__ void record_cost(uint32_t* __restrict__ cost, unsigned int vblock, long long t0)
+{
+    if (!cost) return;
+    const long long dt = clock64() - t0;          // the warp is converged here (after the warp-wide counter reduction)
+    if ((threadIdx.x & 31) == 0) atomicMax(cost + vblock, (uint32_t)(dt > 0xffffffffLL ? 0xffffffffLL : dt));
+}
+
+// One CTA of 256 threads per cost array (small enough to slip in beside the frame kernels): stable partition of the virtual blocks into 4 cost classes (> 8x, > 4x, > 2x the mean, rest);
+// resets the costs for the next frame.  Runs off the critical path on a side stream.
+__global__ void __launch_bounds__(256) k_build_order(uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t n)
+{
+    __shared__ unsigned long long s_sum;
+    __shared__ uint32_t s_cnt[4][256 + 1];
+    const uint32_t t = threadIdx.x;
+    const uint32_t chunk = (n + 255u) / 256u, lo = min(t * chunk, n), hi = min(lo + chunk, n);
+    if (t == 0) s_sum = 0ull;
+    __syncthreads();
+    unsigned long long sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += cost[i];
+    for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if ((t & 31u) == 0u && sum) atomicAdd(&s_sum, sum);
+    __syncthreads();
+    const unsigned long long mean = s_sum / (n ? n : 1u);
+    uint32_t c[4] = {0u, 0u, 0u, 0u};
+    for (uint32_t i = lo; i < hi; i++) { const unsigned long long v = cost[i]; c[v > 8ull * mean ? 0 : v > 4ull * mean ? 1 : v > 2ull * mean ? 2 : 3]++; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) s_cnt[k][t] = c[k];
+    __syncthreads();
+    if (t < 4) {      // exclusive scan over the 256 chunks of class t (serial, off the critical path)
+        uint32_t run = 0;
+        for (uint32_t j = 0; j < 256u; j++) { const uint32_t v = s_cnt[t][j]; s_cnt[t][j] = run; run += v; }
+        s_cnt[t][256] = run;
+    }
+    __syncthreads();
+    uint32_t base[4];
+    base[0] = 0u; base[1] = s_cnt[0][256]; base[2] = base[1] + s_cnt[1][256]; base[3] = base[2] + s_cnt[2][256];
+    uint32_t pos[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) pos[k] = base[k] + s_cnt[k][t];
+    for (uint32_t i = lo; i < hi; i++) {
+        const unsigned long long v = cost[i];
+        const int k = v > 8ull * mean ? 0 : v > 4ull * mean ? 1 : v > 2ull * mean ? 2 : 3;
+        order[pos[k]++] = i;
+        cost[i] = 0u;
+    }
 }
 
 __device__ __forceinline__ void add_counter(unsigned long long* counters, int slot, unsigned int n)
@@ -71,6 +125,7 @@ __global__ void k_build_luts(float* lut_pow22, uint8_t* lut_post)
 {
     const int k = threadIdx.x;
     const float x = (float)k / 255.0f;
+    g_unit255[k] = x;
     lut_pow22[k] = vkp_powf(x, 2.2f);
     lut_post[k] = vkp_unorm8(vkp_powf(fmaxf(x, 0.001f), 1.0f / 2.2f));
 }
@@ -271,7 +326,9 @@ __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, flo
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, VKP_LB_GBUFFER) k_gbuffer(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
-    const Pixel px = pixel_of_thread(F);
+    const long long t_start = clock64();
+    const unsigned int vb = virtual_block(F.cta_order[0]);
+    const Pixel px = pixel_of_block(F, vb);
     unsigned int nrays = 0;
     TravCount tc = {0u, 0u, 0u};
     TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
@@ -333,6 +390,7 @@ __global__ void __launch_bounds__(128, VKP_LB_GBUFFER) k_gbuffer(const __grid_co
     }
     add_counter(F.counters, 0, nrays);
     if (F.count_trav) add_trav(F.counters, tc, (0u << 28) | (unsigned)(px.valid ? px.y * F.p.width + px.x : 0));
+    record_cost(F.cta_cost[0], vb, t_start);
 }
 
 // per-light pieces of shadowRaygen.rgen:55-61 that decide whether rays are traced (and hence how far the RNG advances)
@@ -356,8 +414,10 @@ __device__ __forceinline__ LightGeom light_geom(const vkp_light& light, float3 p
 // cheap per-light conditions of the lights before it.
 __global__ void __launch_bounds__(128, VKP_LB_SHADOW) k_shadow(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
-    const Pixel px = pixel_of_thread(F);
-    const int l = blockIdx.y;
+    const long long t_start = clock64();
+    const unsigned int vb = virtual_block(F.cta_order[1]);      // = light * n_cta + pixel block
+    const int l = (int)(vb / (unsigned int)F.n_cta);
+    const Pixel px = pixel_of_block(F, vb - (unsigned int)l * (unsigned int)F.n_cta);
     unsigned int nrays = 0;
     TravCount tc = {0u, 0u, 0u};
     TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
@@ -405,6 +465,7 @@ __global__ void __launch_bounds__(128, VKP_LB_SHADOW) k_shadow(const __grid_cons
     }
     add_counter(F.counters, 1, nrays);
     if (F.count_trav) add_trav(F.counters, tc, (1u << 28) | ((unsigned)l << 23) | (unsigned)(px.valid ? px.y * F.p.width + px.x : 0));
+    record_cost(F.cta_cost[1], vb, t_start);
 }
 
 // blur.comp:35-82 for one pixel and one light, with runtime W/H/NLIGHTS and an integer motion fetch; returns the new
@@ -420,15 +481,15 @@ __device__ __forceinline__ uint8_t denoise_pixel(const DFrame& F, int l, int x, 
     if (!(x < Wc && y < Hc)) return hist[i];
     float pixelColor;
     if (frame > 0) {
-        float center = (float)in[i] / 255.0f;
-        float old = (float)hist[i] / 255.0f;
+        float center = unit255(in[i]);
+        float old = unit255(hist[i]);
         float a = 1.0f / (float)((float)frame + 1.0f);
         pixelColor = mix1(old, center, a);
     } else {
         uint32_t m = F.motion[i];
         float rx = vkp_f16_to_f32((uint16_t)(m & 0xffffu)) * 2.0f - 1.0f;
         float lastx = (float)x + rx * (float)W, lasty = (float)y + rx * (float)H;   // blur.comp:53 (r.x twice)
-        float center = (float)in[i] / 255.0f;
+        float center = unit255(in[i]);
         float minColor = center, maxColor = center;
 #pragma unroll
         for (int yy = -1; yy <= 1; yy++)
@@ -436,14 +497,14 @@ __device__ __forceinline__ uint8_t denoise_pixel(const DFrame& F, int l, int x, 
             for (int xx = -1; xx <= 1; xx++) {
                 if (xx == 0 && yy == 0) continue;
                 int qx = x + xx, qy = y + yy;
-                float c = (qx < 0 || qy < 0 || qx >= W || qy >= H) ? 0.0f : (float)in[(size_t)qy * W + qx] / 255.0f;
+                float c = (qx < 0 || qy < 0 || qx >= W || qy >= H) ? 0.0f : unit255(in[(size_t)qy * W + qx]);
                 minColor = fminf(minColor, c); maxColor = fmaxf(maxColor, c);
             }
         float cx = fminf(fmaxf(lastx, -2147483000.0f), 2147483000.0f), cy = fminf(fmaxf(lasty, -2147483000.0f), 2147483000.0f);
         if (cx != cx) cx = -1.0f;
         if (cy != cy) cy = -1.0f;
         int ix = (int)cx, iy = (int)cy;
-        float old = (ix < 0 || iy < 0 || ix >= W || iy >= H) ? 0.0f : (float)hist[(size_t)iy * W + ix] / 255.0f;
+        float old = (ix < 0 || iy < 0 || ix >= W || iy >= H) ? 0.0f : unit255(hist[(size_t)iy * W + ix]);
         old = fmaxf(minColor, old);
         old = fminf(maxColor, old);
         pixelColor = mix1(old, center, 0.4f);
@@ -458,6 +519,40 @@ __global__ void __launch_bounds__(128) k_denoise(const __grid_constant__ DScene 
     const size_t i = (size_t)px.y * F.p.width + px.x;
     const size_t plane = (size_t)F.p.width * F.p.height;
     for (int l = 0; l < S.n_lights; l++) F.denoised_next[l * plane + i] = denoise_pixel(F, l, px.x, px.y, i, plane);
+}
+
+// blur.comp:41-48, the accumulation path of every frame after a reset: out = mix(out_prev, in, 1 / (frame + 1)) -- pure byte
+// streaming (2L bytes in, L out per pixel).  One thread = 4 adjacent pixels of a row (32-bit loads / stores), one warp = one
+// 16 x 8 pixel block, same tile enumeration as the other frame kernels.  Needs W % 4 == 0 (rows stay 4-byte aligned).
+__global__ void __launch_bounds__(32) k_denoise_accumulate4(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    const int W = F.p.width, H = F.p.height;
+    const int bpt_x = F.tile_w >> 4, bpt = bpt_x * (F.tile_h >> 3);
+    const int own_tile = (int)blockIdx.x / bpt, sub = (int)blockIdx.x - own_tile * bpt;
+    const int tile = F.rank + own_tile * F.world;
+    const int tx = tile % F.tiles_x, ty = tile / F.tiles_x;
+    const int x = tx * F.tile_w + (sub % bpt_x) * 16 + (threadIdx.x & 3) * 4;
+    const int y = ty * F.tile_h + (sub / bpt_x) * 8 + (threadIdx.x >> 2);
+    if (x >= W || y >= H) return;
+    const int Wc = F.p.denoise_cover_remainder ? W : (W / 16) * 16;
+    const int Hc = F.p.denoise_cover_remainder ? H : (H / 16) * 16;
+    const size_t plane = (size_t)W * H, i = (size_t)y * W + x;
+    const bool covered = x < Wc && y < Hc;       // a group of 4 is entirely inside or outside (Wc, x are multiples of 4)
+    const float a = 1.0f / (float)((float)F.p.denoise_frame + 1.0f);
+    for (int l = 0; l < S.n_lights; l++) {
+        const uint32_t h4 = __ldg(reinterpret_cast<const uint32_t*>(F.denoised + l * plane + i));
+        uint32_t o4 = h4;
+        if (covered) {
+            const uint32_t c4 = __ldg(reinterpret_cast<const uint32_t*>(F.shadow + l * plane + i));
+            o4 = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float center = unit255((unsigned char)(c4 >> (8 * k))), old = unit255((unsigned char)(h4 >> (8 * k)));
+                o4 |= (uint32_t)vkp_unorm8(mix1(old, center, a)) << (8 * k);
+            }
+        }
+        *reinterpret_cast<uint32_t*>(F.denoised_next + l * plane + i) = o4;
+    }
 }
 
 // hybridRaygen.rgen:27-186
@@ -597,7 +692,7 @@ __global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_resolve(const __grid_co
             const float light_intensity = isDirectional ? 1.0f : (light.color[3] / (light_distance * light_distance));
             L = normalize3(L);
             const float NdotL = clamp01(dot3(N, L));
-            const float shadowFactor = (float)dq / 255.0f;
+            const float shadowFactor = unit255(dq);
             if (NdotL > 0.0f) {
                 if (light_intensity == 0.0f) attenuation = 0.0f;
                 else {
@@ -1027,11 +1122,22 @@ cudaError_t launch_gbuffer(const FrameLaunch& L) { k_gbuffer<<<frame_grid(L), 12
 cudaError_t launch_shadow(const FrameLaunch& L)
 {
     if (L.scene.n_lights == 0) return cudaSuccess;
-    dim3 g = frame_grid(L); g.y = (unsigned)L.scene.n_lights;
+    dim3 g = frame_grid(L); g.x *= (unsigned)L.scene.n_lights;      // light-major: virtual block = light * n_cta + pixel block
     k_shadow<<<g, 128, 0, L.stream>>>(L.scene, L.frame);
     return cudaGetLastError();
 }
-cudaError_t launch_denoise(const FrameLaunch& L) { k_denoise<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
+cudaError_t launch_build_order(cudaStream_t s, uint32_t* cost, uint32_t* order, uint32_t n)
+{
+    if (!n) return cudaSuccess;
+    k_build_order<<<1, 256, 0, s>>>(cost, order, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_denoise(const FrameLaunch& L)
+{
+    if (L.frame.p.denoise_frame > 0 && L.frame.p.width % 4 == 0) k_denoise_accumulate4<<<frame_grid(L), 32, 0, L.stream>>>(L.scene, L.frame);
+    else k_denoise<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);
+    return cudaGetLastError();
+}
 cudaError_t launch_resolve(const FrameLaunch& L, int* launches)
 {
     if (L.frame.p.wavefront == 0 || (L.frame.p.wavefront == 2 && L.frame.p.max_bounces > VKP_CHAIN_MAX)) {

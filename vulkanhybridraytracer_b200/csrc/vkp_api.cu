@@ -65,6 +65,13 @@ struct vkp_ctx {
     DevBuf counters, io_tmp, io_tmp2, flush, path_q[2], path_count, luts, chain_buf, chain_len, chain_slot;
     cudaStream_t chain_stream = nullptr;
     cudaEvent_t ev_gbuffer = nullptr, ev_chain = nullptr;
+    // longest-first CTA schedule of k_gbuffer [0] and k_shadow [1], rebuilt every frame from the previous frame's per-block cycles
+    DevBuf cta_cost[2], cta_order[2];
+    uint32_t order_n[2] = {0u, 0u};
+    bool order_ready[2] = {false, false}, order_pending[2] = {false, false};
+    cudaStream_t order_stream = nullptr;
+    cudaEvent_t ev_stage_done[2] = {nullptr, nullptr}, ev_order_done[2] = {nullptr, nullptr};
+    int schedule = 1;                 // 0 = hardware block order, 1 = longest first (VKP_SCHEDULE=0|1)
     bool chain_in_flight = false;
     // multi-GPU: FINAL_SRGB8 is double-buffered (vkp_set_output_buffer) and may be redirected into rank 0's two buffers over NVLink
     // (vkp_set_output_redirect): frame k+1 is written to the other buffer while rank 0 still consumes frame k
@@ -331,6 +338,20 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.chain_buf = ctx->chain_buf.as<float4>(); F.chain_len = ctx->chain_len.as<int>(); F.chain_slot = ctx->chain_slot.as<int>();
     const int total = F.tiles_x * F.tiles_y;
     L.n_own_tiles = total > F.rank ? (total - F.rank + F.world - 1) / F.world : 0;
+    F.n_cta = L.n_own_tiles * (F.tile_w >> 4) * (F.tile_h >> 3);
+    for (int k = 0; k < 2; k++) {
+        const uint32_t n = (uint32_t)F.n_cta * (k ? (uint32_t)L.scene.n_lights : 1u);
+        F.cta_cost[k] = nullptr; F.cta_order[k] = nullptr;
+        if (!ctx->schedule || !ctx->order_stream || n == 0) continue;
+        if (n != ctx->order_n[k]) {       // another grid: start over with the hardware order for one frame
+            if (ctx->order_pending[k]) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_order_done[k], 0)); ctx->order_pending[k] = false; }
+            CK(ctx->cta_cost[k].ensure(sizeof(uint32_t) * n)); CK(ctx->cta_order[k].ensure(sizeof(uint32_t) * n));
+            CK(launch_stage_words(ctx->stream, ctx->cta_cost[k].p, nullptr, sizeof(uint32_t) * n));
+            ctx->order_n[k] = n; ctx->order_ready[k] = false;
+        }
+        F.cta_cost[k] = ctx->cta_cost[k].as<uint32_t>();
+        if (ctx->order_ready[k]) F.cta_order[k] = ctx->cta_order[k].as<uint32_t>();
+    }
     L.stream = ctx->stream;
     L.frame_dev = nullptr;
     return VKP_OK;
@@ -352,8 +373,21 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
     if (r != VKP_OK) return r;
     if (L.n_own_tiles == 0) return VKP_OK;
     switch (stage) {
-    case VKP_STAGE_GBUFFER: CK(launch_gbuffer(L)); break;
-    case VKP_STAGE_SHADOW: CK(launch_shadow(L)); break;
+    case VKP_STAGE_GBUFFER:
+    case VKP_STAGE_SHADOW: {
+        const int k = stage == VKP_STAGE_SHADOW ? 1 : 0;
+        if (ctx->order_pending[k]) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_order_done[k], 0)); ctx->order_pending[k] = false; }
+        if (k) CK(launch_shadow(L)); else CK(launch_gbuffer(L));
+        if (L.frame.cta_cost[k]) {       // next frame's order from this frame's costs, beside the rest of the frame
+            CK(cudaEventRecord(ctx->ev_stage_done[k], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->order_stream, ctx->ev_stage_done[k], 0));
+            CK(launch_build_order(ctx->order_stream, ctx->cta_cost[k].as<uint32_t>(), ctx->cta_order[k].as<uint32_t>(), ctx->order_n[k]));
+            CK(cudaEventRecord(ctx->ev_order_done[k], ctx->order_stream));
+            ctx->order_pending[k] = true; ctx->order_ready[k] = true;
+            ctx->last_launches++;
+        }
+        break;
+    }
     case VKP_STAGE_DENOISE:
         CK(launch_denoise(L));
         ctx->denoised_cur ^= 1;
@@ -416,6 +450,9 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);               // hi = greatest priority (numerically lowest)
         cudaStreamCreateWithPriority(&ctx->chain_stream, cudaStreamNonBlocking, hi);
+        cudaStreamCreateWithPriority(&ctx->order_stream, cudaStreamNonBlocking, hi);
+        for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags(&ctx->ev_stage_done[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_order_done[k], cudaEventDisableTiming); }
+        if (const char* e = getenv("VKP_SCHEDULE")) ctx->schedule = atoi(e) != 0;
         cudaEventCreateWithFlags(&ctx->ev_gbuffer, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
     }
@@ -439,6 +476,7 @@ void vkp_destroy(vkp_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->update_stream) cudaStreamSynchronize(ctx->update_stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->order_stream) cudaStreamSynchronize(ctx->order_stream);
     for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
     for (auto& m : ctx->meshes) { m->verts.release(); m->idx.release(); }
     for (auto& t : ctx->textures) t->texels.release();
@@ -458,6 +496,12 @@ void vkp_destroy(vkp_ctx* ctx)
     if (ctx->timer0) cudaEventDestroy(ctx->timer0);
     if (ctx->timer1) cudaEventDestroy(ctx->timer1);
     if (ctx->chain_stream) cudaStreamDestroy(ctx->chain_stream);
+    if (ctx->order_stream) cudaStreamDestroy(ctx->order_stream);
+    for (int k = 0; k < 2; k++) {
+        ctx->cta_cost[k].release(); ctx->cta_order[k].release();
+        if (ctx->ev_stage_done[k]) cudaEventDestroy(ctx->ev_stage_done[k]);
+        if (ctx->ev_order_done[k]) cudaEventDestroy(ctx->ev_order_done[k]);
+    }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_frame_done) cudaEventDestroy(ctx->ev_frame_done);
     for (auto& ev : ctx->ev_copy_done) if (ev) cudaEventDestroy(ev);

@@ -170,7 +170,17 @@ struct DFrame {
     float4* chain_buf;              // chain mode 2: VKP_CHAIN_MAX colours per compacted path
     int* chain_len;                 // chain mode 2: number of bounces traced per path
     int* chain_slot;                // chain mode 2: per-pixel path slot (written for mirror / glass pixels only)
+    // longest-first CTA scheduling: cost[v] = SM cycles the slowest warp of virtual block v took in the
+    // previous frame, order[b] = the virtual block hardware block b works on (NULL = identity).  [0] k_gbuffer, [1] k_shadow.
+    const uint32_t* cta_order[2];
+    uint32_t* cta_cost[2];
+    int n_cta;                      // CTAs per pixel pass on this rank (k_shadow runs n_cta * n_lights of them)
 };
+
+// k / 255.0f for the 256 possible bytes, filled on the device by k_build_luts with the same IEEE division the contract
+// names (a multiplication by 1/255 differs in 126 of the 256 cases): one L1-resident load instead of a division sequence
+static __device__ float g_unit255[256];
+VKP_D float unit255(unsigned char x) { return __ldg(&g_unit255[x]); }
 
 // ---- texture / env -----------------------------------------------------------------------------------------
 // texture(): VK_FILTER_NEAREST + REPEAT on R8G8B8A8_UNORM (vk_textures.cpp:15,26; vk_initializers.h:86)
@@ -181,7 +191,7 @@ VKP_D float4 tex_nearest(const DTexture& T, float u, float v)
     ix %= T.w; if (ix < 0) ix += T.w;
     iy %= T.h; if (iy < 0) iy += T.h;
     uchar4 t = __ldg(&T.texels[(size_t)iy * T.w + ix]);
-    return make_float4((float)t.x / 255.0f, (float)t.y / 255.0f, (float)t.z / 255.0f, (float)t.w / 255.0f);
+    return make_float4(unit255(t.x), unit255(t.y), unit255(t.z), unit255(t.w));
 }
 VKP_D uchar4 tex_nearest_raw(const DTexture& T, float u, float v)
 {
@@ -265,7 +275,7 @@ VKP_D uchar4 pack_unorm4(float x, float y, float z, float w)
     return make_uchar4(vkp_unorm8(x), vkp_unorm8(y), vkp_unorm8(z), vkp_unorm8(w));
 }
 VKP_D float3 lut3(const float* __restrict__ lut, uchar4 c) { return f3(__ldg(&lut[c.x]), __ldg(&lut[c.y]), __ldg(&lut[c.z])); }
-VKP_D float3 unorm3(uchar4 c) { return f3((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f); }
+VKP_D float3 unorm3(uchar4 c) { return f3(unit255(c.x), unit255(c.y), unit255(c.z)); }
 
 // camera ray of raygen.rgen:32-40
 VKP_D void camera_ray(const vkp_camera& cam, int x, int y, float ox, float oy, int W, int H, float3& origin, float3& dir)

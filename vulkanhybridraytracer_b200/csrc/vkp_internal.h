@@ -84,6 +84,7 @@ struct FrameLaunch {
 cudaError_t launch_gbuffer(const FrameLaunch& L);
 cudaError_t launch_shadow(const FrameLaunch& L);
 cudaError_t launch_denoise(const FrameLaunch& L);
+cudaError_t launch_build_order(cudaStream_t s, uint32_t* cost, uint32_t* order, uint32_t n);
 cudaError_t launch_resolve(const FrameLaunch& L, int* launches);
 cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream);
 cudaError_t launch_post(const FrameLaunch& L);
