@@ -15,7 +15,7 @@
 
 // occupancy knobs (min resident CTAs per SM -> register cap), tuned by measurement
 #ifndef VKP_LB_GBUFFER
-#define VKP_LB_GBUFFER 8
+#define VKP_LB_GBUFFER 4      /* 128 registers, no spills: 0.183 -> 0.148 ms at 1080p (8 CTAs / 64 registers spilled in the loop) */
 #endif
 #ifndef VKP_LB_SHADOW
 #define VKP_LB_SHADOW 6

@@ -75,6 +75,36 @@ VKP_D bool box_test(const float4 lo, const float4 hi, float3 o, float3 d, float3
     tnear = tn;
     return tn * 0.999999f <= tf * 1.000001f;
 }
+// The common-case slab test: t = b * (1/d) - o * (1/d) as one FMA per plane, the near / far plane of each axis chosen by the sign
+// of the direction (no min / max per axis), and the rounding of the precomputed o * (1/d) -- the only absolute error of this
+// form -- folded into two copies of it: oin = o/d + e for the near planes, oif = o/d - e for the far ones, e = |o/d| * 2^-22.
+// 18 instructions per box instead of 26.  Not used when a direction component is (near) zero: that is box_test<true>.
+#ifndef VKP_SLAB_FMA
+#define VKP_SLAB_FMA 0      /* measured 2-3 % slower per frame than the (b - o) * inv form: fewer instructions, more live registers */
+#endif
+struct SlabRay { float3 inv, oin, oif; bool nx, ny, nz; };
+VKP_D SlabRay slab_setup(float3 o, float3 inv)
+{
+    SlabRay R;
+    R.inv = inv;
+    const float ox = o.x * inv.x, oy = o.y * inv.y, oz = o.z * inv.z;
+    const float ex = fabsf(ox) * 2.4e-7f, ey = fabsf(oy) * 2.4e-7f, ez = fabsf(oz) * 2.4e-7f;
+    R.oin = f3(ox + ex, oy + ey, oz + ez);
+    R.oif = f3(ox - ex, oy - ey, oz - ez);
+    R.nx = inv.x < 0.0f; R.ny = inv.y < 0.0f; R.nz = inv.z < 0.0f;
+    return R;
+}
+VKP_D bool box_test_fast(const float4 lo, const float4 hi, const SlabRay& R, float tmin, float tmax, float& tnear)
+{
+    const float ax = __fmaf_rn(R.nx ? hi.x : lo.x, R.inv.x, -R.oin.x), bx = __fmaf_rn(R.nx ? lo.x : hi.x, R.inv.x, -R.oif.x);
+    const float ay = __fmaf_rn(R.ny ? hi.y : lo.y, R.inv.y, -R.oin.y), by = __fmaf_rn(R.ny ? lo.y : hi.y, R.inv.y, -R.oif.y);
+    const float az = __fmaf_rn(R.nz ? hi.z : lo.z, R.inv.z, -R.oin.z), bz = __fmaf_rn(R.nz ? lo.z : hi.z, R.inv.z, -R.oif.z);
+    const float tn = fmaxf(fmaxf(ax, ay), fmaxf(az, tmin));
+    const float tf = fminf(fminf(bx, by), fminf(bz, tmax));
+    tnear = tn;
+    return tn <= tf * 1.000001f;
+}
+
 VKP_D bool has_parallel_axis(float3 d) { return fabsf(d.x) <= 1e-30f || fabsf(d.y) <= 1e-30f || fabsf(d.z) <= 1e-30f; }
 VKP_D bool box_test(const float4 lo, const float4 hi, float3 o, float3 d, float3 inv, bool par, float tmin, float tmax, float& tnear)
 {
@@ -131,6 +161,10 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
     float3 inv = winv;
     const bool wpar = has_parallel_axis(d);
     bool par = wpar;
+#if !VKP_WIDE
+    const SlabRay wslab = slab_setup(o, winv);
+    SlabRay slab = wslab;
+#endif
 #if VKP_WIDE
     const float4* nodes = S.tlas_nodes4;
     uint32_t cur = S.tlas_root_ref;
@@ -152,8 +186,21 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
             if (tcount) tcount->nodes++;
             float4 lo0 = __ldg(c + 0), hi0 = __ldg(c + 1), lo1 = __ldg(c + 2), hi1 = __ldg(c + 3);
             float t0, t1;
-            bool h0 = box_test(lo0, hi0, ro, rd, inv, par, tmin, limit, t0);
-            bool h1 = box_test(lo1, hi1, ro, rd, inv, par, tmin, limit, t1);
+            bool h0, h1;
+#if !VKP_SLAB_FMA
+            if (true) {
+                h0 = box_test(lo0, hi0, ro, rd, inv, par, tmin, limit, t0);
+                h1 = box_test(lo1, hi1, ro, rd, inv, par, tmin, limit, t1);
+            } else {
+#else
+            if (par) {      // rare: a direction component is zero
+                h0 = box_test<true>(lo0, hi0, ro, rd, inv, tmin, limit, t0);
+                h1 = box_test<true>(lo1, hi1, ro, rd, inv, tmin, limit, t1);
+            } else {
+#endif
+                h0 = box_test_fast(lo0, hi0, slab, tmin, limit, t0);
+                h1 = box_test_fast(lo1, hi1, slab, tmin, limit, t1);
+            }
             uint32_t r0 = __float_as_uint(lo0.w), r1 = __float_as_uint(lo1.w);
             if (h0 && h1) {
                 bool swap = t1 < t0;
@@ -191,6 +238,9 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
         if (cur == VKP_STACK_SENTINEL) break;
         if (cur == VKP_STACK_RETURN) {
             inst = -1; ro = o; rd = d; inv = winv; par = wpar;
+#if !VKP_WIDE
+            slab = wslab;
+#endif
 #if VKP_WIDE
             nodes = S.tlas_nodes4;
 #else
@@ -210,6 +260,9 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
             rd = f3((r0.x * d.x + r0.y * d.y) + r0.z * d.z, (r1.x * d.x + r1.y * d.y) + r1.z * d.z, (r2.x * d.x + r2.y * d.y) + r2.z * d.z);
             inv = safe_inv_dir(rd);
             par = has_parallel_axis(rd);
+#if !VKP_WIDE
+            slab = slab_setup(ro, inv);
+#endif
             tris = reinterpret_cast<const float4*>(((unsigned long long)__float_as_uint(pp.w) << 32) | (unsigned long long)__float_as_uint(pp.z));
             // the TLAS leaf box is the world box of this instance: go straight to the BLAS root's content
             stack[sp++] = VKP_STACK_RETURN;
