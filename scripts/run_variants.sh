@@ -2,7 +2,7 @@
 # run the bench for every built variant (under gpurun)
 for d in variants/*/; do
   n=$(basename $d)
-  VKP_LIB=$PWD/variants/$n/libvkp.so python bench.py --steps 60 --warmup 5 --no-cpu-baseline > gpurun_out/var_$n.json 2> gpurun_out/var_$n.err
+  VKP_LIB=$PWD/variants/$n/libvkp.so python bench.py --workload ${WORKLOAD:-cfg2} --steps ${STEPS:-60} --warmup 5 --no-cpu-baseline > gpurun_out/var_$n.json 2> gpurun_out/var_$n.err
   python - <<PY
 import json
 try:

@@ -18,13 +18,19 @@
 #define VKP_LB_GBUFFER 4      /* 128 registers, no spills: 0.183 -> 0.148 ms at 1080p (8 CTAs / 64 registers spilled in the loop) */
 #endif
 #ifndef VKP_LB_SHADOW
-#define VKP_LB_SHADOW 6
+#define VKP_LB_SHADOW 8       /* latency-bound: more resident warps beat the 176 bytes it spills at 64 registers */
+#endif
+#ifndef VKP_LB_SHADOW_MANY
+#define VKP_LB_SHADOW_MANY 5
 #endif
 #ifndef VKP_LB_RT
 #define VKP_LB_RT 4
 #endif
 #ifndef VKP_LB_RESOLVE
-#define VKP_LB_RESOLVE 4
+#define VKP_LB_RESOLVE 5
+#endif
+#ifndef VKP_LB_CHAIN
+#define VKP_LB_CHAIN 3        /* 168 registers: the sparse chain kernel gains nothing from occupancy, a lot from not spilling */
 #endif
 
 namespace {
@@ -412,7 +418,11 @@ __device__ __forceinline__ LightGeom light_geom(const vkp_light& light, float3 p
 // traversal of a pixel is not serialised behind the other lights' (the kernel's duration is set by its slowest
 // thread: DESIGN.md section 4).  With the non-faithful RNG the seed a light starts from is replayed from the
 // cheap per-light conditions of the lights before it.
-__global__ void __launch_bounds__(128, VKP_LB_SHADOW) k_shadow(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+// MINB = resident CTAs per SM the register budget is set for: 8 (64 registers) when a thread traces one ray and waits on it
+// (latency-bound: 0.39 -> 0.36 ms at 1080p), 5 (96 registers, no spills) when it loops over many soft-shadow samples
+// (issue-bound: cfg5 209 ms against 227 ms at 8).
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_shadow(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     const long long t_start = clock64();
     const unsigned int vb = virtual_block(F.cta_order[1]);      // = light * n_cta + pixel block
@@ -579,7 +589,7 @@ __device__ __forceinline__ void first_bounce(int shadingMode, const vkp_material
 // The bounce chain of hybridRaygen.rgen:153-170 depends only on the G-buffer, not on the shadow / denoise passes, so in
 // chain mode 2 it runs in this kernel on a second, high-priority stream CONCURRENTLY with k_shadow + k_denoise; the
 // per-bounce colours are stored (<= 8 per path) and k_resolve<2> multiplies them into rayColor in the reference's order.
-__global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_chain(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+__global__ void __launch_bounds__(128, VKP_LB_CHAIN) k_chain(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     const Pixel px = pixel_of_thread(F);
     unsigned int n_refl = 0, n_sec = 0;
@@ -1123,7 +1133,8 @@ cudaError_t launch_shadow(const FrameLaunch& L)
 {
     if (L.scene.n_lights == 0) return cudaSuccess;
     dim3 g = frame_grid(L); g.x *= (unsigned)L.scene.n_lights;      // light-major: virtual block = light * n_cta + pixel block
-    k_shadow<<<g, 128, 0, L.stream>>>(L.scene, L.frame);
+    if (L.frame.p.shadow_samples >= 4) k_shadow<VKP_LB_SHADOW_MANY><<<g, 128, 0, L.stream>>>(L.scene, L.frame);
+    else k_shadow<VKP_LB_SHADOW><<<g, 128, 0, L.stream>>>(L.scene, L.frame);
     return cudaGetLastError();
 }
 cudaError_t launch_build_order(cudaStream_t s, uint32_t* cost, uint32_t* order, uint32_t n)
