@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
+    ap.add_argument("--nccl-barrier", action="store_true", help="N > 1, peer composite: 4-byte NCCL all-reduce per frame instead of the device-side flag barrier")
     ap.add_argument("--no-peer", action="store_true", help="N > 1: composite with pack + NCCL gather + unpack instead of NVLink peer stores")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-identity check of the composite against a 1-GPU render")
     ap.add_argument("--chain", type=int, default=2, choices=[0, 1, 2],
@@ -201,7 +202,7 @@ def main():
     peer = False
     if world > 1 and not args.no_peer:
         ctx.set_params(params(0))
-        peer = tr.enable_peer_output()
+        peer = tr.enable_peer_output(device_barrier=not args.nccl_barrier)
 
     def composite():
         return tr.composite(PLANE.FINAL_SRGB8)
@@ -230,23 +231,48 @@ def main():
     sampler = ClockSampler(dev); sampler.start()
     barrier()
     total_ms = 0.0
-    for k in range(args.steps):
-        if not args.no_flush:
-            ctx.flush_l2()
-        p_k = params(frame)
-        if world > 1:
-            dist.barrier()
-        ctx.timer_begin()
-        tr.render(p_k)
-        n_launch = 0
-        if world > 1:
-            n_launch = composite()
-        total_ms += ctx.timer_end()
+    if world == 1:
+        for k in range(args.steps):
+            if not args.no_flush:
+                ctx.flush_l2()
+            p_k = params(frame)
+            ctx.timer_begin()
+            tr.render(p_k)
+            total_ms += ctx.timer_end()
+            c = ctx.counters()
+            stage_ms += np.array(list(c.ms_stage))
+            rays += np.array([c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow], dtype=np.int64)
+            launches += c.kernel_launches
+            frame += 1
+    else:
+        # N ranks: the K frames are queued back to back on the rank's stream -- flush, [event] render + composite [event] -- with no
+        # host round trip in between (a per-frame host sync would put the enqueue latency of the NCCL barrier into every frame);
+        # the frame barrier (4-byte all-reduce / gather) keeps the ranks in lockstep on the device.  Ray counters accumulate.
+        ctx.set_profiling(False)
+        ctx.set_counter_accumulation(True)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for k in range(args.steps):
+            if not args.no_flush:
+                ctx.flush_l2()
+            ev[k][0].record(tr.stream)
+            tr.render(params(frame))
+            launches += composite()
+            ev[k][1].record(tr.stream)
+            frame += 1
+        barrier()
+        total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
         c = ctx.counters()
-        stage_ms += np.array(list(c.ms_stage))
         rays += np.array([c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow], dtype=np.int64)
-        launches += c.kernel_launches + n_launch
-        frame += 1
+        launches += c.kernel_launches * args.steps
+        ctx.set_counter_accumulation(False)
+        # per-stage times: a few more frames, profiled one by one (not part of `value`)
+        ctx.set_profiling(True)
+        n_prof = min(8, args.steps)
+        for k in range(n_prof):
+            tr.render(params(frame)); composite()
+            c = ctx.counters()
+            stage_ms += np.array(list(c.ms_stage)) * (args.steps / n_prof)
+            frame += 1
     barrier()
     clocks = sampler.stop()
     # one extra, untimed frame with traversal accounting on: what the rays actually requested from memory
@@ -325,26 +351,51 @@ def main():
                       "API over the C-ABI, wall clock; FRAME_OVERLAP = 2 as renderer.h:34"}
         eng.close()
     else:
-        # tile-sharded / other workloads: same loop through the C-ABI with per-frame host inputs and a read-back on rank 0
-        pinned = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+        # tile-sharded / other workloads: same loop through the C-ABI with per-frame host inputs and a present on rank 0.
+        # Two frames in flight (FRAME_OVERLAP = 2, renderer.h:34): frame k's image travels to pinned memory while frame k+1 renders
+        # into the other output buffer.  With peer output the other ranks store into rank 0's buffers, so rank 0 lets the copy of
+        # frame k-1 land before it joins the barrier that releases frame k+1 (which reuses that buffer).
+        pinned = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        nbytes = pinned[0].numel()
+        def e2e_frame(k):
+            ctx.set_lights(scene.lights); ctx.set_camera(cam)
+            if world == 1:
+                ctx.set_output_buffer(k & 1)
+            tr.render(params(frame + k))
+            if world > 1:
+                if rank == 0 and not getattr(tr, "device_barrier", False):
+                    ctx.readback_wait(0)
+                tr.composite(PLANE.FINAL_SRGB8, release=False)
+            if rank == 0:
+                ctx.readback_async(PLANE.FINAL_SRGB8, pinned[k & 1].data_ptr(), nbytes)
+                if world == 1:
+                    ctx.readback_wait(1)
+                else:
+                    tr.release(after_present=True)      # the peers may reuse this buffer once the copy has landed
+                    ctx.readback_wait(1)
+        for k in range(args.warmup):
+            e2e_frame(k)
+        if rank == 0:
+            ctx.readback_wait(0)
+        ctx.sync()
         barrier()
         t0 = time.perf_counter()
         for k in range(args.steps):
-            ctx.set_lights(scene.lights); ctx.set_camera(cam)
-            tr.render(params(frame + k))
-            if world > 1:
-                composite()
-            if rank == 0:
-                ctx.L.vkp_readback(ctx.h, PLANE.FINAL_SRGB8, pinned.data_ptr(), pinned.numel())
+            e2e_frame(args.warmup + k)
+        if rank == 0:
+            ctx.readback_wait(0)
+        ctx.sync()
         barrier()
         dt = time.perf_counter() - t0
+        if world == 1:
+            ctx.set_output_buffer(0)
         tt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{dev}")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         e2e = {"value": counted / args.steps / (dt / args.steps) / 1e6, "unit": "Mrays/s", "ms_per_step": dt / args.steps * 1e3,
-               "h2d_bytes_per_step": 48 * L + 400 + 64, "d2h_bytes_per_step": W * H * 4,
-               "api": "vkp_set_lights/camera/params + vkp_render (+ NCCL tile gather) + vkp_readback(FINAL_SRGB8) on rank 0, wall clock"}
+               "h2d_bytes_per_step": 48 * L + 400 + 64, "d2h_bytes_per_step": W * H * 4, "frames_in_flight": 2,
+               "api": "vkp_set_lights/camera/params + vkp_render (+ NVLink peer composite) + vkp_readback_async(FINAL_SRGB8) into pinned memory on rank 0, wall clock"}
 
     if rank != 0:
         if world > 1:

@@ -96,6 +96,9 @@ VKP_API int vkp_readback_wait(vkp_ctx* ctx, int keep_in_flight);
 VKP_API int vkp_upload_plane(vkp_ctx* ctx, int plane, const void* src, size_t bytes);
 VKP_API int vkp_plane_device_ptr(vkp_ctx* ctx, int plane, void** device_ptr, size_t* bytes);
 VKP_API int vkp_get_counters(vkp_ctx* ctx, vkp_counters* out);                    /* syncs */
+/* on: the ray counters are not cleared per frame but run on until vkp_get_counters reads them (which also clears them): a frame
+ * loop can then be timed with events only, without a host round trip per frame */
+VKP_API int vkp_set_counter_accumulation(vkp_ctx* ctx, int on);
 VKP_API int vkp_set_profiling(vkp_ctx* ctx, int on);            /* 0 off, 1 per-stage CUDA events, 2 also count traversal fetches (slower) */
 
 /* traceRayEXT made explicit: trace n rays against the current TLAS (host buffers). any_hit != 0
@@ -132,6 +135,19 @@ VKP_API int vkp_set_output_redirect(vkp_ctx* ctx, void* peer_buffer0, void* peer
 /* FINAL_SRGB8 is double-buffered: select which buffer (0 / 1) the next frame writes and vkp_readback / export read.  With peer
  * stores, alternating per frame lets rank 0 consume frame k while the peers already write frame k+1 (one barrier per frame). */
 VKP_API int vkp_set_output_buffer(vkp_ctx* ctx, int which);
+/* Frame barrier of the peer composite, on the device over NVLink (no collective call, no host round trip per frame).  Rank 0
+ * exports a small flag array; the others attach to it.  All calls are stream-ordered kernels on the context's stream:
+ *   peer rank:  [vkp_sync_wait_release(f - 2)]  render frame f (pixels land in rank 0's buffer f & 1)  vkp_sync_arrive(f)
+ *   rank 0:     render frame f   vkp_sync_wait_arrivals(f)   <frame complete: present it>   vkp_sync_release(f, after_present)
+ * after_present != 0 queues the release behind the present copies (vkp_readback_async).  A wait gives up after ~10 s and sets a
+ * flag vkp_sync_timed_out reports (a dead peer must not hang the GPU). */
+VKP_API int vkp_sync_export(vkp_ctx* ctx, void* handle64);
+VKP_API int vkp_sync_attach(vkp_ctx* ctx, const void* handle64);
+VKP_API int vkp_sync_arrive(vkp_ctx* ctx, uint32_t frame);
+VKP_API int vkp_sync_wait_arrivals(vkp_ctx* ctx, uint32_t frame);
+VKP_API int vkp_sync_release(vkp_ctx* ctx, uint32_t frame, int after_present);
+VKP_API int vkp_sync_wait_release(vkp_ctx* ctx, uint32_t frame);
+VKP_API int vkp_sync_timed_out(vkp_ctx* ctx, int* timed_out);
 /* build-primitive probe (tests): stable radix sort of (keys[i], i) on bits [0, end_bit) and an exclusive 64-bit prefix sum of
  * ((keys[i] & 1) << 32 | (keys[i] & 3)) with the BVH builder's own kernels (bvh_sort.cuh) */
 VKP_API int vkp_selftest_sort(vkp_ctx* ctx, const uint32_t* keys, uint32_t n, int end_bit, uint32_t* sorted_keys, uint32_t* sorted_vals, uint64_t* scan);

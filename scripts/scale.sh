@@ -4,7 +4,7 @@ N=$1; WL=${2:-cfg2}; STEPS=${3:-20}
 if [ "$N" = "1" ]; then
   python bench.py --gpus 1 --workload $WL --steps $STEPS --warmup 3 --no-cpu-baseline > gpurun_out/scale_${WL}_n$N.json 2> gpurun_out/scale_${WL}_n$N.err
 else
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --workload $WL --steps $STEPS --warmup 3 > gpurun_out/scale_${WL}_n$N.json 2> gpurun_out/scale_${WL}_n$N.err
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --workload $WL --steps $STEPS --warmup 3 $EXTRA > gpurun_out/scale_${WL}_n$N.json 2> gpurun_out/scale_${WL}_n$N.err
 fi
 python - <<PY
 import json

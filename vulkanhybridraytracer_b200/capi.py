@@ -90,6 +90,7 @@ def load_vkp():
         "vkp_plane_device_ptr": (i, [vp, i, P(vp), P(sz)]),
         "vkp_get_counters": (i, [vp, P(T.Counters)]),
         "vkp_set_profiling": (i, [vp, i]),
+        "vkp_set_counter_accumulation": (i, [vp, i]),
         "vkp_trace_rays": (i, [vp, vp, u32, i, vp]),
         "vkp_bvh_info": (i, [vp, i, P(u32), P(u32)]),
         "vkp_bvh_download": (i, [vp, i, vp, vp]),
@@ -107,6 +108,13 @@ def load_vkp():
         "vkp_ipc_open": (i, [vp, vp, P(vp)]),
         "vkp_set_output_redirect": (i, [vp, vp, vp]),
         "vkp_set_output_buffer": (i, [vp, i]),
+        "vkp_sync_export": (i, [vp, vp]),
+        "vkp_sync_attach": (i, [vp, vp]),
+        "vkp_sync_arrive": (i, [vp, C.c_uint32]),
+        "vkp_sync_wait_arrivals": (i, [vp, C.c_uint32]),
+        "vkp_sync_release": (i, [vp, C.c_uint32, i]),
+        "vkp_sync_wait_release": (i, [vp, C.c_uint32]),
+        "vkp_sync_timed_out": (i, [vp, P(i)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -363,6 +371,9 @@ class Context:
     def set_profiling(self, on):
         self._ck(self.L.vkp_set_profiling(self.h, int(on)), "vkp_set_profiling")
 
+    def set_counter_accumulation(self, on):
+        self._ck(self.L.vkp_set_counter_accumulation(self.h, 1 if on else 0), "vkp_set_counter_accumulation")
+
     def set_stream(self, stream_ptr):
         self._ck(self.L.vkp_set_stream(self.h, C.c_void_p(stream_ptr)), "vkp_set_stream")
 
@@ -425,6 +436,33 @@ class Context:
 
     def set_output_buffer(self, which):
         self._ck(self.L.vkp_set_output_buffer(self.h, which), "vkp_set_output_buffer")
+
+    # frame barrier of the peer composite (device-side flags over NVLink)
+    def sync_export(self):
+        h = (C.c_ubyte * 64)()
+        self._ck(self.L.vkp_sync_export(self.h, h), "vkp_sync_export")
+        return bytes(h)
+
+    def sync_attach(self, handle):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._ck(self.L.vkp_sync_attach(self.h, buf), "vkp_sync_attach")
+
+    def sync_arrive(self, frame):
+        self._ck(self.L.vkp_sync_arrive(self.h, frame & 0xFFFFFFFF), "vkp_sync_arrive")
+
+    def sync_wait_arrivals(self, frame):
+        self._ck(self.L.vkp_sync_wait_arrivals(self.h, frame & 0xFFFFFFFF), "vkp_sync_wait_arrivals")
+
+    def sync_release(self, frame, after_present=False):
+        self._ck(self.L.vkp_sync_release(self.h, frame & 0xFFFFFFFF, 1 if after_present else 0), "vkp_sync_release")
+
+    def sync_wait_release(self, frame):
+        self._ck(self.L.vkp_sync_wait_release(self.h, frame & 0xFFFFFFFF), "vkp_sync_wait_release")
+
+    def sync_timed_out(self):
+        v = C.c_int(0)
+        self._ck(self.L.vkp_sync_timed_out(self.h, C.byref(v)), "vkp_sync_timed_out")
+        return bool(v.value)
 
     def trace_stats(self, rays, any_hit=False):
         rays = np.ascontiguousarray(rays, dtype=T.ray_dtype)

@@ -1101,6 +1101,33 @@ __global__ void k_stage_inline(uint32_t* __restrict__ dst, const __grid_constant
     for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = payload.w[i];
 }
 
+// ---- frame barrier over NVLink peer memory (multi-GPU composite) ------------------------------------------
+// The other ranks' resolve kernels store their pixels straight into rank 0's image; what remains of a "gather" is knowing when
+// they are all there, and when rank 0 is done with a buffer.  Both are 4-byte flags in rank 0's memory, written with
+// st.release.sys after a system fence and polled with ld.acquire.sys by a one-warp kernel in the waiting rank's stream: no
+// collective library call, no host round trip per frame.  Flags carry frame numbers (wrap-safe compare); a wait gives up after
+// ~10 s and raises the context's timeout flag instead of hanging the GPU when a peer died.
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void k_sync_signal(uint32_t* flag, uint32_t value)
+{
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+__global__ void k_sync_wait(const uint32_t* flags, int count, uint32_t value, uint32_t* timeout_flag)
+{
+    if ((int)threadIdx.x >= count) return;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - value) < 0) {
+        if (clock64() - t0 > 20000000000LL) { atomicExch(timeout_flag, 1u); break; }
+        __nanosleep(200);
+    }
+}
+
 __global__ void k_eval_math(int func, const float* __restrict__ x, const float* __restrict__ y, uint32_t n, float* __restrict__ out)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1283,6 +1310,18 @@ cudaError_t launch_stage_inline(cudaStream_t s, void* dst, const void* src, size
         words -= n; w += n; d += n;
     }
     return cudaSuccess;
+}
+
+cudaError_t launch_sync_signal(cudaStream_t s, uint32_t* flag, uint32_t value)
+{
+    k_sync_signal<<<1, 1, 0, s>>>(flag, value);
+    return cudaGetLastError();
+}
+cudaError_t launch_sync_wait(cudaStream_t s, const uint32_t* flags, int count, uint32_t value, uint32_t* timeout_flag)
+{
+    if (count <= 0) return cudaSuccess;
+    k_sync_wait<<<1, 64, 0, s>>>(flags, count, value, timeout_flag);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_l2_flush(cudaStream_t s, void* buf, size_t bytes)

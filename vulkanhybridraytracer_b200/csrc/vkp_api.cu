@@ -79,6 +79,10 @@ struct vkp_ctx {
     DevBuf final_srgb8_alt;
     int out_sel = 0;
     std::vector<void*> ipc_opened;
+    // frame barrier flags (vkp_sync_*): rank 0 owns [0..63] "rank r finished frame f" and [64] "rank 0 released frame f";
+    // every rank keeps [65] of its own buffer as the timeout flag of its waits
+    DevBuf sync_buf;
+    uint32_t* sync_flags = nullptr;       // rank 0's flag array (own memory on rank 0, IPC mapping elsewhere)
     // present with frames in flight (vkp_readback_async): D2H copies run on their own stream behind the frame that produced them
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_frame_done = nullptr, ev_copy_done[3] = {nullptr, nullptr, nullptr};   // [0],[1]: the two sRGB8 buffers, [2]: any other plane
@@ -92,6 +96,7 @@ struct vkp_ctx {
 
     bool profiling = false;
     bool count_trav = false;
+    bool accumulate_counters = false;     // ray counters run on across frames until vkp_get_counters reads (and clears) them
     cudaEvent_t ev[12]{};
     int ev_stage[12]{};
     int n_ev = 0;
@@ -490,7 +495,7 @@ void vkp_destroy(vkp_ctx* ctx)
     if (ctx->ev_updated) cudaEventDestroy(ctx->ev_updated);
     DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_textures, &ctx->position, &ctx->normal, &ctx->albedo, &ctx->motion,
                       &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
-                      &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->final_srgb8_alt};
+                      &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->final_srgb8_alt};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->timer0) cudaEventDestroy(ctx->timer0);
@@ -718,7 +723,7 @@ int vkp_render(vkp_ctx* ctx)
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[b], 0));
         ctx->copy_pending[b] = false;
     }
-    CK(launch_stage_words(ctx->stream, ctx->counters.p, nullptr, 64));
+    if (!ctx->accumulate_counters) CK(launch_stage_words(ctx->stream, ctx->counters.p, nullptr, 64));
     static const int hybrid[] = {VKP_STAGE_GBUFFER, VKP_STAGE_SHADOW, VKP_STAGE_DENOISE, VKP_STAGE_RESOLVE};
     static const int hybrid_fused[] = {VKP_STAGE_GBUFFER, VKP_STAGE_SHADOW, VKP_STAGE_RESOLVE};
     static const int rt[] = {VKP_STAGE_RAYTRACE};
@@ -754,7 +759,7 @@ int vkp_run_stage(vkp_ctx* ctx, int stage)
     int r = make_launch(ctx, L);
     if (r != VKP_OK) return r;
     ctx->n_ev = 0; ctx->last_launches = 0;
-    CK(launch_stage_words(ctx->stream, ctx->counters.p, nullptr, 64));
+    if (!ctx->accumulate_counters) CK(launch_stage_words(ctx->stream, ctx->counters.p, nullptr, 64));
     if ((r = run_one(ctx, L, stage)) != VKP_OK) return r;
     if ((r = mark_scene_use(ctx)) != VKP_OK) return r;
     return stage_event(ctx, -1);
@@ -887,6 +892,77 @@ int vkp_ipc_open(vkp_ctx* ctx, const void* handle64, void** device_ptr)
     return VKP_OK;
 }
 
+static int ensure_sync_buf(vkp_ctx* ctx)
+{
+    if (ctx->sync_buf.p) return VKP_OK;
+    CK(ctx->sync_buf.ensure(1024));
+    CK(cudaMemset(ctx->sync_buf.p, 0, 1024));
+    return VKP_OK;
+}
+
+int vkp_sync_export(vkp_ctx* ctx, void* handle64)
+{
+    if (!ctx || !handle64) return VKP_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int r = ensure_sync_buf(ctx);
+    if (r != VKP_OK) return r;
+    ctx->sync_flags = ctx->sync_buf.as<uint32_t>();
+    CK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), ctx->sync_buf.p));
+    return VKP_OK;
+}
+
+int vkp_sync_attach(vkp_ctx* ctx, const void* handle64)
+{
+    if (!ctx || !handle64) return VKP_ERR_INVALID;
+    int r = ensure_sync_buf(ctx);
+    if (r != VKP_OK) return r;
+    void* p = nullptr;
+    if ((r = vkp_ipc_open(ctx, handle64, &p)) != VKP_OK) return r;
+    ctx->sync_flags = reinterpret_cast<uint32_t*>(p);
+    return VKP_OK;
+}
+
+int vkp_sync_arrive(vkp_ctx* ctx, uint32_t frame)
+{
+    if (!ctx || !ctx->sync_flags || ctx->rank <= 0 || ctx->rank >= 64) return fail(ctx, VKP_ERR_INVALID, "vkp_sync_arrive: not an attached peer rank");
+    CK(launch_sync_signal(ctx->stream, ctx->sync_flags + ctx->rank, frame));
+    return VKP_OK;
+}
+
+int vkp_sync_wait_arrivals(vkp_ctx* ctx, uint32_t frame)
+{
+    if (!ctx || !ctx->sync_flags || ctx->rank != 0 || ctx->world > 64) return fail(ctx, VKP_ERR_INVALID, "vkp_sync_wait_arrivals: rank 0 of <= 64 only");
+    CK(launch_sync_wait(ctx->stream, ctx->sync_flags + 1, ctx->world - 1, frame, ctx->sync_buf.as<uint32_t>() + 65));
+    return VKP_OK;
+}
+
+int vkp_sync_release(vkp_ctx* ctx, uint32_t frame, int after_present)
+{
+    if (!ctx || !ctx->sync_flags || ctx->rank != 0) return fail(ctx, VKP_ERR_INVALID, "vkp_sync_release: rank 0 only");
+    cudaStream_t s = (after_present && ctx->copy_stream) ? ctx->copy_stream : ctx->stream;      // behind the queued present copies
+    CK(launch_sync_signal(s, ctx->sync_flags + 64, frame));
+    return VKP_OK;
+}
+
+int vkp_sync_wait_release(vkp_ctx* ctx, uint32_t frame)
+{
+    if (!ctx || !ctx->sync_flags) return fail(ctx, VKP_ERR_INVALID, "vkp_sync_wait_release: not attached");
+    CK(launch_sync_wait(ctx->stream, ctx->sync_flags + 64, 1, frame, ctx->sync_buf.as<uint32_t>() + 65));
+    return VKP_OK;
+}
+
+int vkp_sync_timed_out(vkp_ctx* ctx, int* timed_out)
+{
+    if (!ctx || !timed_out) return VKP_ERR_INVALID;
+    *timed_out = 0;
+    if (!ctx->sync_buf.p) return VKP_OK;
+    uint32_t v = 0;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(&v, ctx->sync_buf.as<uint32_t>() + 65, 4, cudaMemcpyDeviceToHost));
+    *timed_out = (int)v;
+    return VKP_OK;
+}
+
 int vkp_set_output_redirect(vkp_ctx* ctx, void* peer_buffer0, void* peer_buffer1)
 {
     if (!ctx) return VKP_ERR_INVALID;
@@ -913,6 +989,7 @@ int vkp_get_counters(vkp_ctx* ctx, vkp_counters* out)
         out->rays_primary = c[0]; out->rays_shadow = c[1]; out->rays_reflect = c[2]; out->rays_secondary_shadow = c[3];
         out->node_fetches = c[4]; out->triangle_tests = c[5]; out->instance_entries = c[6];
         out->worst_thread_nodes = (uint32_t)(c[7] >> 32); out->worst_thread_tag = (uint32_t)c[7];
+        if (ctx->accumulate_counters) CK(launch_stage_words(ctx->stream, ctx->counters.p, nullptr, 64));
     }
     if (ctx->profiling && ctx->n_ev >= 2) {
         for (int i = 0; i + 1 < ctx->n_ev; i++) {
@@ -923,6 +1000,15 @@ int vkp_get_counters(vkp_ctx* ctx, vkp_counters* out)
         CK(cudaEventElapsedTime(&out->ms_frame, ctx->ev[0], ctx->ev[ctx->n_ev - 1]));
     }
     out->kernel_launches = ctx->last_launches;
+    return VKP_OK;
+}
+
+int vkp_set_counter_accumulation(vkp_ctx* ctx, int on)
+{
+    if (!ctx) return VKP_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->accumulate_counters = on != 0;
+    if (ctx->counters.p) CK(launch_stage_words(ctx->stream, ctx->counters.p, nullptr, 64));
     return VKP_OK;
 }
 

@@ -97,6 +97,8 @@ cudaError_t launch_tiles_unpack(cudaStream_t s, void* plane, const void* src, in
 cudaError_t launch_build_luts(cudaStream_t s, float* lut_pow22, uint8_t* lut_post);
 cudaError_t launch_eval_math(cudaStream_t s, int func, const float* x, const float* y, uint32_t n, float* out);
 cudaError_t launch_l2_flush(cudaStream_t s, void* buf, size_t bytes);
+cudaError_t launch_sync_signal(cudaStream_t s, uint32_t* flag, uint32_t value);
+cudaError_t launch_sync_wait(cudaStream_t s, const uint32_t* flags, int count /* <= 64 */, uint32_t value, uint32_t* timeout_flag);
 #define VKP_STAGE_INLINE_MAX 15360u     /* four launches of 3840 bytes */
 cudaError_t launch_stage_inline(cudaStream_t s, void* dst, const void* src, size_t bytes);     // bytes % 4 == 0, <= VKP_STAGE_INLINE_MAX
 cudaError_t launch_stage_words(cudaStream_t s, void* dst, const void* src_or_null, size_t bytes);     // bytes % 4 == 0; src NULL = clear

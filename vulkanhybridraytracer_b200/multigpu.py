@@ -39,10 +39,13 @@ class TiledRenderer:
         self._bufs = {}
         self.collectives = 0
         self.peer_output = False
+        self.device_barrier = False
 
-    def enable_peer_output(self):
+    def enable_peer_output(self, device_barrier=True):
         """Composite of FINAL_SRGB8 without a gather: every rank's resolve kernel stores its pixels straight into rank 0's
-        image over NVLink peer memory (CUDA IPC); a frame then only needs a barrier.  NCCL backend, one GPU per rank."""
+        image over NVLink peer memory (CUDA IPC); a frame then only needs a barrier.  With device_barrier that barrier is a
+        pair of flags in rank 0's memory written / polled by one-warp kernels (vkp_sync_*): no collective call and no host
+        round trip per frame; otherwise a 4-byte NCCL all-reduce.  NCCL backend (set-up only), one GPU per rank."""
         import torch.distributed as dist
         if self.world == 1:
             return False
@@ -56,7 +59,14 @@ class TiledRenderer:
         dist.broadcast_object_list(box, src=0, group=self.group)
         if self.rank != 0:
             self.ctx.set_output_redirect(self.ctx.ipc_open(box[0]), self.ctx.ipc_open(box[1]))
+        self.device_barrier = bool(device_barrier) and self.world <= 64
+        if self.device_barrier:
+            hs = [self.ctx.sync_export() if self.rank == 0 else None]
+            dist.broadcast_object_list(hs, src=0, group=self.group)
+            if self.rank != 0:
+                self.ctx.sync_attach(hs[0])
         self._frame_no = 0
+        self._released = 0
         self._flag = self.torch.zeros(1, dtype=self.torch.int32, device=self.device if self.backend == "nccl" else "cpu")
         self.peer_output = True
         return True
@@ -109,6 +119,8 @@ class TiledRenderer:
         if self.peer_output:
             self._frame_no += 1
             ctx.set_output_buffer(self._frame_no & 1)
+            if self.device_barrier and self.rank != 0 and self._frame_no > 2:
+                ctx.sync_wait_release(self._frame_no - 2)      # rank 0 is done with the buffer this frame's pixels go to
         if self.world == 1 or params.mode != MODE_HYBRID or params.denoise_frame > 0:
             ctx.render()
             return
@@ -121,12 +133,28 @@ class TiledRenderer:
         ctx.run_stage(STAGE.DENOISE)
         ctx.run_stage(STAGE.RESOLVE)
 
-    def composite(self, plane=PLANE.FINAL_SRGB8):
+    def release(self, after_present=False):
+        """Rank 0, device barrier: the frame composited last has been consumed (after_present: once its queued present copy
+        has landed); the peers may overwrite its buffer two frames later."""
+        if self.peer_output and self.device_barrier and self.rank == 0 and self._released != self._frame_no:
+            self.ctx.sync_release(self._frame_no, after_present)
+            self._released = self._frame_no
+            return 1
+        return 0
+
+    def composite(self, plane=PLANE.FINAL_SRGB8, release=True):
         """Gather the finished tiles of `plane` to rank 0 (the one collective of a static frame).  Returns the number of
-        kernels launched on this rank."""
+        kernels launched on this rank.  release=False (device barrier): the caller presents the frame first and then calls
+        release(after_present=True)."""
         import torch.distributed as dist
         if self.world == 1:
             return 0
+        if self.peer_output and plane == PLANE.FINAL_SRGB8 and self.device_barrier:
+            if self.rank == 0:
+                self.ctx.sync_wait_arrivals(self._frame_no)
+                return 1 + (self.release() if release else 0)
+            self.ctx.sync_arrive(self._frame_no)
+            return 1
         if self.peer_output and plane == PLANE.FINAL_SRGB8:
             # the pixels are already in rank 0's image; a 4-byte all-reduce is the completion barrier (stream-ordered)
             if self.stream_ordered:
