@@ -652,9 +652,33 @@ void orc_gbuffer_pass(const orc_scene* sp, const vkp_camera* cam, const vkp_para
             vec3 inColor = vec3(v0.color[0], v0.color[1], v0.color[2]) * b0 + vec3(v1.color[0], v1.color[1], v1.color[2]) * b1 + vec3(v2.color[0], v2.color[1], v2.color[2]) * b2;
             vec2 uv; uv.x = v0.uv[0] * b0 + v1.uv[0] * b1 + v2.uv[0] * b2; uv.y = v0.uv[1] * b0 + v1.uv[1] * b1 + v2.uv[1] * b2;
             const vkp_material& mat = S.materials[std::min<int>(std::max<int>(I.rec.material_id, 0), (int)S.materials.size() - 1)];
-            /* geometry_shader.frag:54-59 (normal mapping, :55/:61-64, is out of scope: needs dFdx/dFdy) */
+            /* geometry_shader.frag:54-59 */
             vec3 color = mat.textures[0] > -1 ? xyz(tex_fetch(S.textures[(int)mat.textures[0]], uv.x, uv.y)) * inColor : vec3(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2]);
             vec3 N = normalize(inNormal);
+            if (mat.textures[1] > -1) {
+                /* geometry_shader.frag:55,60-63 perturbNormal(inNormal, inWorldPos, inUV, texel) with cotangent_frame :28-49.
+                 * dFdx / dFdy of the world position are ray differentials here (declared deviation, no rasteriser quads):
+                 * the camera rays of the right / lower neighbour pixel intersected with the plane of the hit triangle.
+                 * As upstream: the frame is built from the UN-normalised inNormal, and duv1 / duv2 are dFdx(p).xy /
+                 * dFdy(p).xy (:32-33 take them from p, not from uv). */
+                vec3 normal_pixel = xyz(tex_fetch(S.textures[(int)mat.textures[1]], uv.x, uv.y));
+                normal_pixel = normal_pixel * 255.0f / 127.0f - vec3(128.0f / 127.0f);
+                const vec3 ng = cross(P1 - P0, P2 - P0);
+                vec3 ox_, dx_, oy_, dy_;
+                camera_ray(*cam, x + 1, y, 0.5f, 0.5f, W, H, ox_, dx_);
+                camera_ray(*cam, x, y + 1, 0.5f, 0.5f, W, H, oy_, dy_);
+                const vec3 px_ = ox_ + dx_ * (dot(P0 - ox_, ng) / dot(dx_, ng));
+                const vec3 py_ = oy_ + dy_ * (dot(P0 - oy_, ng) / dot(dy_, ng));
+                const vec3 dp1 = px_ - worldPos, dp2 = py_ - worldPos;
+                const float duv1x = dp1.x, duv1y = dp1.y, duv2x = dp2.x, duv2y = dp2.y;
+                const vec3 dp2perp = cross(dp2, inNormal), dp1perp = cross(inNormal, dp1);
+                const vec3 T = dp2perp * duv1x + dp1perp * duv2x;
+                const vec3 Bt = dp2perp * duv1y + dp1perp * duv2y;
+                const float invmax = 1.0f / sqrtf(fmaxf(dot(T, T), dot(Bt, Bt)));
+                const vec3 Tn = T * invmax, Bn = Bt * invmax;
+                /* mat3(T, B, N) * v = T * v.x + B * v.y + N * v.z */
+                N = normalize(Tn * normal_pixel.x + Bn * normal_pixel.y + inNormal * normal_pixel.z);
+            }
             vec3 emissive = mat.textures[2] > -1 ? xyz(tex_fetch(S.textures[(int)mat.textures[2]], uv.x, uv.y)) : vec3(0.0f);
             vec3 material = mat.textures[3] > -1 ? xyz(tex_fetch(S.textures[(int)mat.textures[3]], uv.x, uv.y)) : vec3(0.0f, mat.shadingMetallicRoughness[2], mat.shadingMetallicRoughness[1]);
             float materialIdx = mat.shadingMetallicRoughness[3];

@@ -21,7 +21,7 @@ def test_default_scene_matches_scene_cpp():
     assert smr[:, 0].tolist() == [0, 0, 3, 4, 0, 0] and smr[:, 3].tolist() == [0, 1, 2, 3, 4, 5]
     assert smr[1, 1] == np.float32(0.1) and smr[5, 1] == np.float32(0.5) and smr[5, 2] == np.float32(0.1)
     assert np.allclose(sc.materials["diffuse"][3], [0.7, 0.7, 1.0, 1.125]) and np.allclose(sc.materials["diffuse"][5][:3], [1.0, 0.71, 0.29])
-    assert (sc.materials["textures"][[0, 1, 2, 3, 5]] == -1).all() and sc.materials["textures"][4].tolist() == [0, -1, 1, 2]
+    assert (sc.materials["textures"][[0, 1, 2, 3, 5]] == -1).all() and sc.materials["textures"][4].tolist() == [0, 3, 1, 2]       # (diffuse, normal, emissive, metalRough)
     # lights (scene.cpp:41-60, vk_engine.cpp:146-164): pos.w = maxDistance 500, color.w = intensity
     assert np.allclose(sc.lights["position"], [[10, 12, -5, 500], [-10, 15, -5, 500], [0, 15, 5, 500]])
     assert np.allclose(sc.lights["color"], [[1, 0.8, 0.5, 500], [0.5, 1, 1, 250], [1, 1, 1, 500]])
@@ -37,7 +37,7 @@ def test_default_scene_matches_scene_cpp():
     assert qi.tolist() == [0, 1, 2, 2, 3, 0] and qv["position"].tolist() == [[1, 1, 0], [-1, 1, 0], [-1, -1, 0], [1, -1, 0]]
     cv, ci = sc.meshes[2]
     assert len(cv) == 24 and len(ci) == 36 and (cv["uv"] == 1).all() and np.abs(cv["position"]).max() == 1
-    assert len(sc.textures) == 5 and sc.textures[sc.sky_tex].shape == (1024, 2048, 4) and sc.textures[sc.irradiance_tex].shape == (32, 64, 4)
+    assert len(sc.textures) == 6 and sc.textures[sc.sky_tex].shape == (1024, 2048, 4) and sc.textures[sc.irradiance_tex].shape == (32, 64, 4)
     sc.close()
 
 

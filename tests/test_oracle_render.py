@@ -163,3 +163,36 @@ def test_libm_twin_is_within_north_star_tolerance(small_scene, small_oracle):
     assert flips.mean() <= 1e-3                       # epsilon-tie penumbra flips only
     assert d.mean() <= 1e-3
     assert d[~flips].max() <= 1e-2
+
+
+def test_normal_mapping_with_ray_differentials():
+    """geometry_shader.frag:28-63: the helmet material carries a normal map; the cotangent frame comes from the position
+    derivatives (neighbour camera rays on the hit triangle's plane).  Only that instance changes, the result is a unit
+    vector near the interpolated normal, and a flat map (128, 128, 255) gives the interpolated normal back."""
+    detail = (4, 3, 4, 6)
+    w, h = 240, 136
+    sc = vk.HostScene(0, detail=detail)
+    cam = sc.camera(w, h); p = vk.make_params(w, h)
+    assert sc.materials["textures"][4][1] >= 0
+    g = Oracle(sc).gbuffer(cam, p)
+    helmet = g.hit_ids[..., 0] == 5
+    assert helmet.sum() > 100
+    n = g.normal.astype(np.float32)[..., :3] * 2 - 1
+    flat = vk.HostScene(0, detail=detail)
+    tid = int(flat.materials["textures"][4][1])
+    flat.textures[tid][...] = np.array([128, 128, 255, 255], np.uint8)
+    gf = Oracle(flat).gbuffer(cam, p)
+    off = vk.HostScene(0, detail=detail)
+    off.materials["textures"][4][1] = -1
+    g0 = Oracle(off).gbuffer(cam, p)
+    n0 = g0.normal.astype(np.float32)[..., :3] * 2 - 1
+    nf = gf.normal.astype(np.float32)[..., :3] * 2 - 1
+    assert np.array_equal(g.normal[~helmet], g0.normal[~helmet])              # nobody else has a normal map
+    for k in ("position", "albedo", "material", "emissive", "hit_ids"):
+        assert np.array_equal(getattr(g, k), getattr(g0, k))
+    assert (g.normal[helmet] != g0.normal[helmet]).any(axis=1).mean() > 0.9    # the map does perturb
+    assert np.abs(np.linalg.norm(n[helmet], axis=1) - 1).max() < 2e-3
+    cosang = (n[helmet] * n0[helmet]).sum(axis=1)
+    assert cosang.min() > 0.5 and cosang.mean() > 0.9
+    # flat map: normal_pixel = (1/127, 1/127, 1): within a degree of the interpolated normal
+    assert ((nf[helmet] * n0[helmet]).sum(axis=1) > 0.998).mean() > 0.95          # (fp16 storage: +-5e-4 per component)

@@ -371,6 +371,26 @@ __global__ void __launch_bounds__(128, VKP_LB_GBUFFER) k_gbuffer(const __grid_co
             const vkp_material& mat = S.materials[max(0, min(I.material_id, S.n_materials - 1))];
             float3 color = mat.textures[0] > -1 ? xyz(tex_nearest(S.textures[(int)mat.textures[0]], uvx, uvy)) * inColor : f3(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2]);
             float3 N = normalize3(inNormal);
+            if (mat.textures[1] > -1) {
+                // geometry_shader.frag:55,60-63 perturbNormal + cotangent_frame :28-49.  dFdx / dFdy of the world position are ray
+                // differentials: the camera rays of the right / lower neighbour pixel intersected with the hit triangle's plane.
+                // As upstream, the frame uses the un-normalised inNormal and takes duv1 / duv2 from dFdx(p).xy / dFdy(p).xy.
+                float3 normal_pixel = xyz(tex_nearest(S.textures[(int)mat.textures[1]], uvx, uvy));
+                normal_pixel = normal_pixel * 255.0f / 127.0f - f3s(128.0f / 127.0f);
+                const float3 ng = cross3(P1 - P0, P2 - P0);
+                float3 ox_, dx_, oy_, dy_;
+                camera_ray(F.cam, px.x + 1, px.y, 0.5f, 0.5f, W, H, ox_, dx_);
+                camera_ray(F.cam, px.x, px.y + 1, 0.5f, 0.5f, W, H, oy_, dy_);
+                const float3 px_ = ox_ + dx_ * (dot3(P0 - ox_, ng) / dot3(dx_, ng));
+                const float3 py_ = oy_ + dy_ * (dot3(P0 - oy_, ng) / dot3(dy_, ng));
+                const float3 dp1 = px_ - worldPos, dp2 = py_ - worldPos;
+                const float3 dp2perp = cross3(dp2, inNormal), dp1perp = cross3(inNormal, dp1);
+                const float3 T = dp2perp * dp1.x + dp1perp * dp2.x;
+                const float3 Bt = dp2perp * dp1.y + dp1perp * dp2.y;
+                const float invmax = 1.0f / sqrtf(fmaxf(dot3(T, T), dot3(Bt, Bt)));
+                const float3 Tn = T * invmax, Bn = Bt * invmax;
+                N = normalize3((Tn * normal_pixel.x + Bn * normal_pixel.y) + inNormal * normal_pixel.z);
+            }
             float3 emissive = mat.textures[2] > -1 ? xyz(tex_nearest(S.textures[(int)mat.textures[2]], uvx, uvy)) : f3s(0.0f);
             float3 material = mat.textures[3] > -1 ? xyz(tex_nearest(S.textures[(int)mat.textures[3]], uvx, uvy))
                                                    : f3(0.0f, mat.shadingMetallicRoughness[2], mat.shadingMetallicRoughness[1]);

@@ -233,9 +233,9 @@ void irradiance_texture(int w, int h, std::vector<uint8_t>& rgba)
         }
 }
 
-void helmet_textures(int w, int h, std::vector<uint8_t>& albedo, std::vector<uint8_t>& emissive, std::vector<uint8_t>& metal_rough)
+void helmet_textures(int w, int h, std::vector<uint8_t>& albedo, std::vector<uint8_t>& emissive, std::vector<uint8_t>& metal_rough, std::vector<uint8_t>& normal)
 {
-    albedo.resize(4 * (size_t)w * h); emissive.resize(4 * (size_t)w * h); metal_rough.resize(4 * (size_t)w * h);
+    albedo.resize(4 * (size_t)w * h); emissive.resize(4 * (size_t)w * h); metal_rough.resize(4 * (size_t)w * h); normal.resize(4 * (size_t)w * h);
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
             float u = ((float)x + 0.5f) / (float)w, v = ((float)y + 0.5f) / (float)h;
@@ -249,6 +249,13 @@ void helmet_textures(int w, int h, std::vector<uint8_t>& albedo, std::vector<uin
             emissive[o + 0] = u8(0.05f * stripe); emissive[o + 1] = u8(0.6f * stripe); emissive[o + 2] = u8(0.9f * stripe); emissive[o + 3] = 255;
             // glTF packing read by the shaders as (x, roughness = .y, metallic = .z)
             metal_rough[o + 0] = 0; metal_rough[o + 1] = u8(0.25f + 0.5f * scratches); metal_rough[o + 2] = u8(panel ? 0.9f : 0.6f); metal_rough[o + 3] = 255;
+            // tangent-space normal map (the glTF sample has one, vk_mesh.cpp:783-786): dents from the gradient of a noise field
+            const float e = 1.0f / 512.0f;
+            float hx = vnoise((u + e) * 24.0f, v * 24.0f, 7.0f, 999u) - vnoise((u - e) * 24.0f, v * 24.0f, 7.0f, 999u);
+            float hy = vnoise(u * 24.0f, (v + e) * 24.0f, 7.0f, 999u) - vnoise(u * 24.0f, (v - e) * 24.0f, 7.0f, 999u);
+            float nx = -6.0f * hx, ny = -6.0f * hy, nz = 1.0f;
+            float inv = 1.0f / std::sqrt(nx * nx + ny * ny + nz * nz);
+            normal[o + 0] = u8(nx * inv * 0.5f + 0.5f); normal[o + 1] = u8(ny * inv * 0.5f + 0.5f); normal[o + 2] = u8(nz * inv * 0.5f + 0.5f); normal[o + 3] = 255;
         }
 }
 

@@ -11,5 +11,5 @@ void helmet_standin(std::vector<Vertex>& v, std::vector<uint32_t>& idx, int subd
 void displaced_icosphere(std::vector<Vertex>& v, std::vector<uint32_t>& idx, int subdiv, uint32_t seed, float amount);
 void sky_texture(int w, int h, std::vector<uint8_t>& rgba);
 void irradiance_texture(int w, int h, std::vector<uint8_t>& rgba);
-void helmet_textures(int w, int h, std::vector<uint8_t>& albedo, std::vector<uint8_t>& emissive, std::vector<uint8_t>& metal_rough);
+void helmet_textures(int w, int h, std::vector<uint8_t>& albedo, std::vector<uint8_t>& emissive, std::vector<uint8_t>& metal_rough, std::vector<uint8_t>& normal);
 }

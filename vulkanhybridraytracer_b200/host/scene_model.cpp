@@ -361,12 +361,13 @@ Prefab* Prefab::GET(std::string filename)
     slot = make_single_primitive_prefab(name, mesh);
     if (name.find(".gltf") != std::string::npos || name.find(".glb") != std::string::npos) {
         // stand-in for the glTF material import (vk_mesh.cpp:777-829): one textured PBR material
-        std::vector<uint8_t> a, e, mr;
-        proc::helmet_textures(512, 512, a, e, mr);
+        std::vector<uint8_t> a, e, mr, nm;
+        proc::helmet_textures(512, 512, a, e, mr, nm);
         Material* m = new Material();
         m->diffuseTexture = Texture::add((name + ":albedo").c_str(), 512, 512, std::move(a));
         m->emissiveTexture = Texture::add((name + ":emissive").c_str(), 512, 512, std::move(e));
         m->metallicRoughnessTexture = Texture::add((name + ":metalRough").c_str(), 512, 512, std::move(mr));
+        m->normalTexture = Texture::add((name + ":normal").c_str(), 512, 512, std::move(nm));
         slot->_root[0]->addMaterial(m);
     }
     return slot;
