@@ -22,7 +22,7 @@ CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-unused-variable
 CU_SRCS := $(CSRC)/vkp_api.cu $(CSRC)/bvh_build.cu $(CSRC)/kernels_frame.cu
 CU_OBJS := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
 CU_HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard $(ROOT)include/*.h)
-HOST_SRCS := $(HOST)/scene_model.cpp $(HOST)/procedural.cpp $(HOST)/renderer.cpp $(HOST)/output.cpp $(HOST)/host_capi.cpp
+HOST_SRCS := $(HOST)/scene_model.cpp $(HOST)/procedural.cpp $(HOST)/renderer.cpp $(HOST)/output.cpp $(HOST)/image_decode.cpp $(HOST)/gltf.cpp $(HOST)/host_capi.cpp
 HOST_HDRS := $(wildcard $(HOST)/*.h) $(wildcard $(ROOT)include/*.h)
 
 all: libvkp host oracle

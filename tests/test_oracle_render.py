@@ -196,3 +196,36 @@ def test_normal_mapping_with_ray_differentials():
     assert cosang.min() > 0.5 and cosang.mean() > 0.9
     # flat map: normal_pixel = (1/127, 1/127, 1): within a degree of the interpolated normal
     assert ((nf[helmet] * n0[helmet]).sum(axis=1) > 0.998).mean() > 0.95          # (fp16 storage: +-5e-4 per component)
+
+
+def test_gltf_viewer_scene_renders_through_the_oracle(tmp_path):
+    """a multi-primitive, textured glTF prefab (host/gltf.cpp) goes through the same flat buffers as the
+    built-in scenes: one TLAS instance per primitive with its own index range of the shared mesh, BVH == brute force,
+    and the G-buffer shows the prefab's textures (albedo, emissive, metallic-roughness, normal map)."""
+    from util import make_test_glb
+    info = make_test_glb(tmp_path / "model.glb")
+    sc = vk.HostScene.from_prefab(tmp_path / "model.glb")
+    assert len(sc.instances) == 4 and sc.n_triangles == 2 + info["triangles"]
+    assert sc.instances["first_index"][1:].tolist() == [6, 6 + int(sc.instances["index_count"][1]), 0]      # child (quad) was loaded first
+    o = Oracle(sc)
+    rays = random_rays(sc, 3000, seed=4)
+    a = o.trace_rays(rays, brute_force=True); b = o.trace_rays(rays, brute_force=False)
+    assert np.array_equal(a["instance"], b["instance"]) and np.array_equal(a["primitive"], b["primitive"])
+    assert np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32)) and set(np.unique(a["instance"])) >= {0, 1, 2, 3}
+    w, h = 160, 90
+    cam = sc.camera(w, h)
+    fr = o.hybrid_frame(cam, vk.make_params(w, h))
+    g = fr["g"]
+    ids = g.hit_ids[..., 0]
+    assert all((ids == k).sum() > 20 for k in range(4))
+    textured = (ids == 1) | (ids == 3)                 # instance order is node_to_instance's: root's two primitives, then the child's quad
+    plain = ids == 2
+    base = info["textures"][0].reshape(-1, 3)
+    texels = {tuple(t) for t in base.tolist()}
+    seen = {tuple(t) for t in g.albedo[textured][:, :3].tolist()}
+    assert len(seen) > 20 and seen <= texels           # baseColorFactor 1: albedo is exactly a texel of the base-colour map (NEAREST)
+    assert len({tuple(t) for t in g.albedo[plain][:, :3].tolist()}) == 1          # untextured primitive: one flat colour
+    assert (g.emissive[textured][:, :3] != 0).any() and (g.emissive[plain][:, :3] == 0).all()
+    assert len(np.unique(g.material[textured][:, 1])) > 5 and len(np.unique(g.material[plain][:, 1])) == 1
+    assert np.isfinite(fr["final"]).all() and fr["final"][..., :3].max() > 0.05
+    o.close(); sc.close()

@@ -1,0 +1,46 @@
+"""GPU parity on the real-asset path.  Sorted after the established GPU suite on purpose: these cases were
+added in a session whose GPU budget was spent, so they are the first to look at if the round-end run reports a failure."""
+import numpy as np
+import pytest
+
+import vulkanhybridraytracer_b200 as vk
+from vulkanhybridraytracer_b200 import PLANE
+from oracle.oracle_py import Oracle
+
+from util import make_test_glb, random_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gltf_prefab_frames_match_the_oracle(tmp_path):
+    """A multi-primitive glTF prefab (several TLAS instances sharing one mesh through different index ranges, embedded PNG
+    textures of a non-power-of-two size, normal map, REPEAT addressing past [0,1]): traversal and two Hybrid frames, bit for bit."""
+    make_test_glb(tmp_path / "model.glb")
+    sc = vk.HostScene.from_prefab(tmp_path / "model.glb")
+    ctx = vk.Context(0); ctx.upload_scene(sc)
+    o = Oracle(sc)
+    rays = random_rays(sc, 20000, seed=9)
+    for any_hit in (False, True):
+        a = ctx.trace_rays(rays, any_hit=any_hit); b = o.trace_rays(rays, any_hit=any_hit)
+        if any_hit:
+            assert np.array_equal(a["t"] >= 0, b["t"] >= 0)
+        else:
+            assert np.array_equal(a["instance"], b["instance"]) and np.array_equal(a["primitive"], b["primitive"])
+            assert np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+    w, h = 256, 144
+    cam = sc.camera(w, h); ctx.set_camera(cam)
+    hist = None
+    for f in range(2):
+        p = vk.make_params(w, h, frame=f)
+        ctx.set_params(p); ctx.render()
+        ref = o.hybrid_frame(cam, p, history=hist); hist = ref["denoised"]
+        g = ref["g"]
+        assert np.array_equal(ctx.readback(PLANE.HIT_IDS), g.hit_ids)
+        for plane, want in ((PLANE.POSITION, g.position), (PLANE.NORMAL, g.normal), (PLANE.ALBEDO, g.albedo), (PLANE.MATERIAL, g.material),
+                            (PLANE.EMISSIVE, g.emissive)):
+            got = ctx.readback(plane)
+            assert np.array_equal(got.view(np.uint8), np.ascontiguousarray(want).view(np.uint8)), (f, plane)
+        for l in range(len(sc.lights)):
+            assert np.array_equal(ctx.readback(PLANE.DENOISED0 + l), ref["denoised"][l]), (f, l)
+        assert np.array_equal(ctx.readback(PLANE.FINAL_F32).view(np.uint32), ref["final"].view(np.uint32)), f
+    ctx.close(); sc.close(); o.close()

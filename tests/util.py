@@ -77,3 +77,91 @@ def bits(a):
     if a.dtype == np.float32:
         return a.view(np.uint32)
     return a
+
+
+def make_test_glb(path, seed=0):
+    """A small self-contained .glb for the real-asset path: a UV sphere split into two primitives (textured
+    upper half with base-colour / normal / emissive / metallic-roughness PNGs embedded in the binary chunk, plain lower
+    half) under a rotated + scaled root node, and a child node holding a tilted quad.  Every primitive has normals."""
+    import io
+    import json
+    import struct
+    from PIL import Image
+
+    rng = np.random.default_rng(seed)
+    n_lon, n_lat = 24, 12
+    lat = np.linspace(0, np.pi, n_lat + 1); lon = np.linspace(0, 2 * np.pi, n_lon + 1)
+    la, lo = np.meshgrid(lat, lon, indexing="ij")
+    pos = np.stack([np.sin(la) * np.cos(lo), np.cos(la), np.sin(la) * np.sin(lo)], -1).reshape(-1, 3).astype(np.float32)
+    nrm = pos.copy()
+    uv = np.stack([lo / (2 * np.pi), la / np.pi], -1).reshape(-1, 2).astype(np.float32)
+
+    def band(r0, r1):
+        tri = []
+        for r in range(r0, r1):
+            for c in range(n_lon):
+                a, b = r * (n_lon + 1) + c, (r + 1) * (n_lon + 1) + c
+                if r > 0:
+                    tri += [a, b, a + 1]
+                if r < n_lat - 1:
+                    tri += [a + 1, b, b + 1]
+        return np.array(tri, np.uint32)
+    upper, lower = band(0, n_lat // 2), band(n_lat // 2, n_lat)
+    quad_p = np.array([[-1.5, 0, -1.5], [1.5, 0, -1.5], [1.5, 0, 1.5], [-1.5, 0, 1.5]], np.float32)
+    quad_n = np.array([[0, 1, 0]] * 4, np.float32)
+    quad_uv = np.array([[0, 0], [2, 0], [2, 2], [0, 2]], np.float32)            # REPEAT addressing
+    quad_i = np.array([0, 2, 1, 0, 3, 2], np.uint16)
+
+    chunks, views = [], []
+
+    def add(arr):
+        off = sum(len(c) for c in chunks)
+        b = np.ascontiguousarray(arr).tobytes()
+        chunks.append(b + b"\0" * (-len(b) % 4))
+        views.append({"buffer": 0, "byteOffset": off, "byteLength": len(b)})
+        return len(views) - 1
+
+    def png(a):
+        buf = io.BytesIO(); Image.fromarray(a).save(buf, "PNG"); return np.frombuffer(buf.getvalue(), np.uint8)
+    th, tw = 24, 48
+    yy, xx = np.mgrid[0:th, 0:tw]
+    base = np.stack([64 + 191 * ((xx // 6 + yy // 6) % 2), 255 - 4 * xx, 40 + 8 * yy], -1).astype(np.uint8)
+    bump = rng.normal(0, 0.25, size=(th, tw, 2))
+    nz = np.sqrt(np.clip(1 - (bump ** 2).sum(-1), 0.2, 1))
+    normal = np.clip(np.dstack([bump, nz]) * 127.5 + 127.5, 0, 255).astype(np.uint8)
+    emissive = np.zeros((th, tw, 3), np.uint8); emissive[::5, ::7] = [255, 120, 30]
+    mr = np.stack([np.zeros_like(xx), 40 + 4 * xx, 255 - 9 * yy], -1).astype(np.uint8)     # G = roughness, B = metallic
+    acc = [
+        {"bufferView": add(pos), "componentType": 5126, "count": len(pos), "type": "VEC3", "min": pos.min(0).tolist(), "max": pos.max(0).tolist()},
+        {"bufferView": add(nrm), "componentType": 5126, "count": len(nrm), "type": "VEC3"},
+        {"bufferView": add(uv), "componentType": 5126, "count": len(uv), "type": "VEC2"},
+        {"bufferView": add(upper), "componentType": 5125, "count": len(upper), "type": "SCALAR"},
+        {"bufferView": add(lower), "componentType": 5125, "count": len(lower), "type": "SCALAR"},
+        {"bufferView": add(quad_p), "componentType": 5126, "count": 4, "type": "VEC3"},
+        {"bufferView": add(quad_n), "componentType": 5126, "count": 4, "type": "VEC3"},
+        {"bufferView": add(quad_uv), "componentType": 5126, "count": 4, "type": "VEC2"},
+        {"bufferView": add(quad_i), "componentType": 5123, "count": 6, "type": "SCALAR"},
+    ]
+    images = [{"bufferView": add(png(t)), "mimeType": "image/png"} for t in (base, normal, emissive, mr)]
+    s = float(np.sin(np.radians(20) / 2)); c = float(np.cos(np.radians(20) / 2))
+    doc = {
+        "asset": {"version": "2.0", "generator": "tests/util.py"},
+        "scenes": [{"nodes": [0]}],
+        "nodes": [{"translation": [0.0, 0.6, 0.0], "rotation": [0.0, 0.0, s, c], "scale": [1.4, 1.4, 1.4], "mesh": 0, "children": [1]},
+                  {"translation": [0.0, -0.9, 0.0], "rotation": [s, 0.0, 0.0, c], "mesh": 1}],
+        "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "NORMAL": 1, "TEXCOORD_0": 2}, "indices": 3, "material": 0},
+                                   {"attributes": {"POSITION": 0, "NORMAL": 1, "TEXCOORD_0": 2}, "indices": 4, "material": 1}]},
+                   {"primitives": [{"attributes": {"POSITION": 5, "NORMAL": 6, "TEXCOORD_0": 7}, "indices": 8, "material": 0}]}],
+        "accessors": acc, "bufferViews": views,
+        "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}, "metallicRoughnessTexture": {"index": 3}, "metallicFactor": 0.9, "roughnessFactor": 0.8},
+                       "normalTexture": {"index": 1}, "emissiveTexture": {"index": 2}},
+                      {"pbrMetallicRoughness": {"baseColorFactor": [0.9, 0.3, 0.2, 1.0], "metallicFactor": 0.2, "roughnessFactor": 0.4}}],
+        "textures": [{"source": k} for k in range(4)], "images": images,
+        "buffers": [{"byteLength": sum(len(c_) for c_ in chunks)}],
+    }
+    blob = b"".join(chunks)
+    js = json.dumps(doc).encode(); js += b" " * (-len(js) % 4)
+    body = struct.pack("<II", len(js), 0x4E4F534A) + js + struct.pack("<II", len(blob), 0x004E4942) + blob
+    with open(path, "wb") as f:
+        f.write(struct.pack("<III", 0x46546C67, 2, 12 + len(body)) + body)
+    return {"triangles": (len(upper) + len(lower) + 6) // 3, "textures": [base, normal, emissive, mr]}

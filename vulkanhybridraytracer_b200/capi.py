@@ -140,6 +140,7 @@ def load_host():
         "vkph_last_error": (C.c_char_p, []),
         "vkph_set_detail": (None, [i, i, i, i]),
         "vkph_scene_create": (vp, [i]),
+        "vkph_scene_create_prefab": (vp, [C.c_char_p]),
         "vkph_scene_destroy": (None, [vp]),
         "vkph_scene_counts": (i, [vp] + [P(i)] * 7),
         "vkph_scene_mesh": (i, [vp, i, P(vp), P(u32), P(vp), P(u32)]),
@@ -165,12 +166,25 @@ def load_host():
         "vkph_engine_destroy": (None, [vp]),
         "vkph_write_png": (i, [C.c_char_p, vp, i, i]),
         "vkph_write_exr": (i, [C.c_char_p, vp, i, i]),
+        "vkph_decode_image_file": (i, [C.c_char_p, P(i), P(i), vp, C.c_size_t]),
     }
     for name, (res, args) in sig.items():
         f = getattr(H, name)
         f.restype, f.argtypes = res, args
     _host = H
     return H
+
+
+def decode_image(path):
+    """Texture::GET's image loader (host/image_decode.cpp, the stbi_load(..., 4) replacement): H x W x 4 uint8."""
+    H = load_host()
+    w, h = C.c_int(), C.c_int()
+    if H.vkph_decode_image_file(str(path).encode(), C.byref(w), C.byref(h), None, 0) != 0:
+        raise VkpError(H.vkph_last_error().decode())
+    out = np.empty((h.value, w.value, 4), dtype=np.uint8)
+    if H.vkph_decode_image_file(str(path).encode(), C.byref(w), C.byref(h), out.ctypes.data_as(C.c_void_p), out.nbytes) != 0:
+        raise VkpError(H.vkph_last_error().decode())
+    return out
 
 
 def make_params(width, height, mode=MODE_HYBRID, spp=1, shadow_samples=1, max_bounces=8, frame=0, denoise_frame=None,
@@ -198,6 +212,21 @@ class HostScene:
             raise VkpError(H.vkph_last_error().decode())
         self.index = index
         self._export()
+
+    @classmethod
+    def from_prefab(cls, path, detail=None):
+        """Scene::create_viewer_scene: the default scene's floor, lights and camera around one .obj / .gltf / .glb file."""
+        H = load_host()
+        if detail is not None:
+            H.vkph_set_detail(*detail)
+        self = cls.__new__(cls)
+        self._H = H
+        self._h = H.vkph_scene_create_prefab(str(path).encode())
+        if not self._h:
+            raise VkpError(H.vkph_last_error().decode())
+        self.index = -1
+        self._export()
+        return self
 
     def _export(self):
         H, h = self._H, self._h

@@ -2,6 +2,7 @@
 // test-suite and bench.py can drive them with ctypes.  Scene export gives the exact arrays that both the
 // C-ABI (include/vkp.h) and the CPU oracle consume.
 #include "vkpinut.h"
+#include "image_decode.h"
 
 #include <cstring>
 #include <exception>
@@ -27,6 +28,19 @@ VKPH_API void* vkph_scene_create(int index)
         vkph_scene* s = new vkph_scene();
         s->scene = new Scene();
         s->scene->create_scene(index);
+        s->buffers = build_scene_buffers(s->scene);
+        return s;
+    } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+
+// floor + lights + camera of the default scene around one asset file (.obj / .gltf / .glb): Scene::create_viewer_scene
+VKPH_API void* vkph_scene_create_prefab(const char* file)
+{
+    try {
+        Scene::reset_registries();
+        vkph_scene* s = new vkph_scene();
+        s->scene = new Scene();
+        s->scene->create_viewer_scene(file);
         s->buffers = build_scene_buffers(s->scene);
         return s;
     } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
@@ -189,6 +203,19 @@ VKPH_API void vkph_engine_destroy(void* p)
 }
 
 VKPH_API int vkph_write_png(const char* path, const uint8_t* rgba, int w, int h) { return write_png_rgba8(path, rgba, w, h) ? 0 : -1; }
+// stbi_load(path, ..., STBI_rgb_alpha) replacement (image_decode.cpp): dst == NULL only reports the size
+VKPH_API int vkph_decode_image_file(const char* path, int* w, int* h, uint8_t* dst, size_t capacity)
+{
+    std::vector<uint8_t> rgba;
+    std::string err;
+    if (!imgdec::load_rgba8(path, *w, *h, rgba, &err)) { g_err = err; return -1; }
+    if (dst) {
+        if (capacity < rgba.size()) { g_err = "vkph_decode_image_file: destination too small"; return -2; }
+        std::memcpy(dst, rgba.data(), rgba.size());
+    }
+    return 0;
+}
+
 VKPH_API int vkph_write_exr(const char* path, const float* rgba, int w, int h) { return write_exr_rgba32f(path, rgba, w, h) ? 0 : -1; }
 
 } // extern "C"

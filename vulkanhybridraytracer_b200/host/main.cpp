@@ -1,6 +1,8 @@
 // main.cpp -- headless replacement of src/main.cpp + window.cpp: VulkanEngine engine; init(); run(); cleanup();
 //   vkpinut [--scene N] [--mode deferred|raytracing|hybrid] [--width W --height H] [--frames F] [--samples S]
-//           [--spp N] [--device D] [--png out.png] [--exr out.exr]
+//           [--spp N] [--device D] [--png out.png] [--exr out.exr] [--prefab model.obj|.gltf|.glb]
+// Assets (sphere.obj, lucy.obj, DamagedHelmet.gltf + textures, the sky .jpg / .hdr) are picked up from the reference's
+// search paths or $VKPINUT_ASSETS when present; otherwise the deterministic stand-ins are used.
 #include "vkpinut.h"
 
 #include <cstdio>
@@ -24,6 +26,7 @@ int main(int argc, char** argv)
         else if (a == "--samples") engine._samples = std::atoi(next());
         else if (a == "--spp") engine._spp = std::atoi(next());
         else if (a == "--device") engine._device = std::atoi(next());
+        else if (a == "--prefab") engine._prefabFile = next();
         else if (a == "--png") png = next();
         else if (a == "--exr") exr = next();
         else if (a == "--mode") {

@@ -136,7 +136,8 @@ void VulkanEngine::init()
     engine = this;
     Scene::reset_registries();
     _scene = new Scene();
-    _scene->create_scene(_sceneIndex);
+    if (!_prefabFile.empty()) _scene->create_viewer_scene(_prefabFile);
+    else _scene->create_scene(_sceneIndex);
     renderer = new Renderer(_scene);
     _denoise_frame = 0; _frameNumber = 0; _havePrev = false;
     _refMatrix = glm::mat4(0.0f);

@@ -3,12 +3,14 @@
 // deterministic stand-ins of procedural.cpp because the reference's assets are git-ignored.
 #include "vkpinut.h"
 #include "procedural.h"
+#include "image_decode.h"
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <stdexcept>
 
 // ---- Material (src/material.cpp:4-62) -------------------------------------------------------------
 std::vector<Material*> Material::_materials;
@@ -111,7 +113,24 @@ int Texture::add(const char* name, int w, int h, std::vector<uint8_t> rgba)
     return (int)_textures.size() - 1;
 }
 Texture* Texture::GET(const char* filename) { int id = get_id(filename); return id < 0 ? nullptr : _textures[id]; }
-int Texture::get_id(const char* filename) { auto it = _ids.find(filename); return it == _ids.end() ? -1 : it->second; }
+
+// Texture::get_id (vk_textures.cpp:156-168) loads the file on first use; the registry is keyed by the resolved path
+// (:129).  Names registered with Texture::add (procedural stand-ins, embedded glTF images) are found first.
+int Texture::get_id(const char* filename)
+{
+    auto it = _ids.find(filename);
+    if (it != _ids.end()) return it->second;
+    std::string path = vkutil_find_file(filename);
+    if (path.empty()) return -1;
+    it = _ids.find(path);
+    if (it != _ids.end()) return it->second;
+    int w = 0, h = 0;
+    std::vector<uint8_t> rgba;
+    std::string err;
+    if (!imgdec::load_rgba8(path.c_str(), w, h, rgba, &err))
+        throw std::runtime_error("Failed to load texture file: " + path + " (" + err + ")");   // vk_textures.cpp:16-19 only prints; we refuse to go on with an undefined image
+    return add(path.c_str(), w, h, std::move(rgba));
+}
 
 // ---- Mesh (src/vk_mesh.cpp:72-263) ---------------------------------------------------------------------
 std::unordered_map<std::string, Mesh*> Mesh::_loadedMeshes;
@@ -125,6 +144,7 @@ extern "C" void vkph_set_detail(int lucy_subdiv, int helmet_subdiv, int stress_s
     if (stress_instances > 0) g_stress_instances = stress_instances;
 }
 
+static std::string find_file(const std::string& filename);
 static std::string base_name(const std::string& p)
 {
     size_t s = p.find_last_of("/\\");
@@ -132,6 +152,7 @@ static std::string base_name(const std::string& p)
 }
 
 // vkutil::findFile over the search paths of vk_engine.cpp:29-34, plus $VKPINUT_ASSETS
+std::string vkutil_find_file(const std::string& filename) { return find_file(filename); }
 static std::string find_file(const std::string& filename)
 {
     std::vector<std::string> paths = {"", "data/", "data/meshes/", "data/textures/", "../data/meshes/", "../data/textures/"};
@@ -351,15 +372,29 @@ static Prefab* make_single_primitive_prefab(const std::string& name, Mesh* mesh)
     return prefab;
 }
 
-Prefab* Prefab::GET(std::string filename)
+Prefab* Prefab::GET(std::string filename, const bool invertNormals)
 {
     std::string name = base_name(filename);
     Prefab*& slot = _prefabsMap[name];
     if (slot) return slot;
+    const bool gltf = name.find(".gltf") != std::string::npos, glb = name.find(".glb") != std::string::npos;
+    if (gltf || glb) {
+        // the real asset when it is on the search paths (vk_mesh.cpp:857-896) ...
+        std::string path = find_file(filename);
+        if (!path.empty()) {
+            slot = load_gltf_prefab(path, glb && !gltf, invertNormals);
+            slot->_name = name;
+            Mesh*& owned = Mesh::_loadedMeshes[name];   // so that reset_registries frees it
+            delete owned;
+            owned = slot->_mesh;
+            return slot;
+        }
+    }
+    // ... else the deterministic stand-in (the reference's assets are git-ignored)
     Mesh* mesh = Mesh::GET(filename.c_str());
     if (!mesh) return nullptr;
     slot = make_single_primitive_prefab(name, mesh);
-    if (name.find(".gltf") != std::string::npos || name.find(".glb") != std::string::npos) {
+    if (gltf || glb) {
         // stand-in for the glTF material import (vk_mesh.cpp:777-829): one textured PBR material
         std::vector<uint8_t> a, e, mr, nm;
         proc::helmet_textures(512, 512, a, e, mr, nm);
@@ -419,11 +454,24 @@ void Scene::create_scene(int i)
     case 3: ring_lights_scene(); break;
     default: break;
     }
-    // environment (renderer.cpp:3073-3074 binds an 8k sky JPG and an .hdr irradiance map, both 8-bit)
+    finish_environment();
+}
+
+// environment (renderer.cpp:3073-3074 binds an 8k sky JPG and an .hdr irradiance map, both 8-bit)
+void Scene::finish_environment()
+{
+    // The real files are used when they are on the search paths, else the analytic stand-ins.
+    _skyTexture = Texture::get_id("LA_Downtown_Helipad_GoldenHour_8k.jpg");
+    _irradianceTexture = Texture::get_id("LA_Downtown_Helipad_GoldenHour_Env.hdr");
     std::vector<uint8_t> sky, irr;
-    if (Texture::get_id("sky") < 0) { proc::sky_texture(2048, 1024, sky); Texture::add("sky", 2048, 1024, std::move(sky)); }
-    if (Texture::get_id("irradiance") < 0) { proc::irradiance_texture(64, 32, irr); Texture::add("irradiance", 64, 32, std::move(irr)); }
-    _skyTexture = Texture::get_id("sky"); _irradianceTexture = Texture::get_id("irradiance");
+    if (_skyTexture < 0) {
+        if (Texture::get_id("sky") < 0) { proc::sky_texture(2048, 1024, sky); Texture::add("sky", 2048, 1024, std::move(sky)); }
+        _skyTexture = Texture::get_id("sky");
+    }
+    if (_irradianceTexture < 0) {
+        if (Texture::get_id("irradiance") < 0) { proc::irradiance_texture(64, 32, irr); Texture::add("irradiance", 64, 32, std::move(irr)); }
+        _irradianceTexture = Texture::get_id("irradiance");
+    }
 }
 
 static Object* make_object(Prefab* prefab, const glm::mat4& m)
@@ -433,6 +481,27 @@ static Object* make_object(Prefab* prefab, const glm::mat4& m)
     o->prefab = prefab; o->m_matrix = m;
     o->material = Material::_materials[prefab->_root[0]->_primitives[0]->materialID];
     return o;
+}
+
+// Not in the reference: its default lights, floor and camera around one asset file, for the headless CLI (--prefab)
+void Scene::create_viewer_scene(const std::string& prefabFile)
+{
+    _camera = new Camera(glm::vec3(0, 5, 10));
+    Light* a = new Light(); a->m_matrix = glm::translate(glm::mat4(1), glm::vec3(10, 12, -5)); a->color = glm::vec3{1.0f, 0.8f, 0.5f}; a->intensity = 500.0f; a->radius = 0.1f;
+    Light* b = new Light(); b->m_matrix = glm::translate(glm::mat4(1), glm::vec3(-10, 15, -5)); b->color = glm::vec3{0.5f, 1.0f, 1.0f}; b->intensity = 250.0f; b->radius = 0.2f;
+    Light* c = new Light(); c->m_matrix = glm::translate(glm::mat4(1), glm::vec3(0, 15, 5)); c->intensity = 500.f; c->radius = 0.09f;
+    _lights = {a, b, c};
+    for (Light* l : _lights) l->update();
+    Material* m_floor = new Material(); m_floor->metallicFactor = 0.1f;
+    Prefab* p_quad = Prefab::GET("quad", Mesh::get_quad()); p_quad->_root[0]->addMaterial(m_floor);
+    if (vkutil_find_file(prefabFile).empty()) throw std::runtime_error("File not found " + prefabFile);   // vk_utils.cpp:48-50
+    Prefab* prefab = Prefab::GET(prefabFile);
+    if (!prefab) throw std::runtime_error("No valid filename " + prefabFile);                            // vk_mesh.cpp:863-866
+    Object* floor = make_object(p_quad, glm::translate(glm::mat4(1), glm::vec3(0, 0, -5)) *
+                                            glm::rotate(glm::mat4(1), glm::radians(-90.0f), glm::vec3(1, 0, 0)) * glm::scale(glm::mat4(1), glm::vec3(15)));
+    Object* object = make_object(prefab, glm::translate(glm::mat4(1), glm::vec3(0, 1, -5)));
+    _entities = {floor, object};
+    finish_environment();
 }
 
 // scene.cpp:34-160

@@ -82,8 +82,8 @@ struct Texture {
     int _width{0}, _height{0};
     std::vector<uint8_t> _rgba;
 
-    static Texture* GET(const char* filename);                       // registered (procedural) image or nullptr
-    static int get_id(const char* filename);                         // -1 when unknown
+    static Texture* GET(const char* filename);                       // registered image, else PNG / JPEG / HDR file on the search paths, else nullptr
+    static int get_id(const char* filename);                         // loads on first use like the reference; -1 when there is no such image
     static int add(const char* name, int w, int h, std::vector<uint8_t> rgba);
 };
 
@@ -147,9 +147,14 @@ public:
     Mesh* _mesh{nullptr};
     std::vector<Node*> _root;
 
-    static Prefab* GET(std::string filename);                // "x.obj" / "x.gltf" (stand-in when absent)
+    static Prefab* GET(std::string filename, const bool invertNormals = false);   // "x.obj" / "x.gltf" / "x.glb" (stand-in when absent)
     static Prefab* GET(std::string name, Mesh* mesh);
 };
+
+// vkutil::findFile (vk_utils.cpp:30-60) over the search paths of vk_engine.cpp:29-34 plus $VKPINUT_ASSETS; "" when absent
+std::string vkutil_find_file(const std::string& filename);
+// glTF branch of Prefab::GET (vk_mesh.cpp:857-896), gltf.cpp; throws std::runtime_error on a malformed file
+Prefab* load_gltf_prefab(const std::string& path, bool binary, bool invertNormals);
 
 // ---- entity.h -----------------------------------------------------------------------------------
 enum lightType { DIRECTIONAL_LIGHT, POINT_LIGHT, SPOT_LIGHT };
@@ -198,6 +203,7 @@ public:
 
     unsigned int get_drawable_nodes_size();
     void create_scene(int i);   // 0 default, 1 cornell, 2 instanced stress (cfg4), 3 ring lights (cfg5)
+    void create_viewer_scene(const std::string& prefabFile);   // the default scene's floor, lights and camera around one .obj / .gltf / .glb
     static void reset_registries();   // clear the static registries (tests create several scenes)
 
 private:
@@ -205,6 +211,7 @@ private:
     void cornell_scene();
     void stress_scene();
     void ring_lights_scene();
+    void finish_environment();
 };
 
 // Flat buffers the renderer binds (hybrid descriptor set 0-12): what both the C-ABI and the
@@ -273,6 +280,7 @@ public:
     bool _skyboxFollow{true};
     int _width{1700}, _height{900};     // hard-coded window of vk_engine.cpp:27
     int _sceneIndex{0};
+    std::string _prefabFile;            // headless CLI --prefab: Scene::create_viewer_scene instead of create_scene(_sceneIndex)
     int _device{0};
     int _spp{1};
     int _maxBounces{8};
