@@ -83,7 +83,10 @@ typedef struct vkp_params {
                                         1 = wavefront path queues with ray compaction, one launch per bounce,
                                         2 = compacted chain kernel on a second stream, overlapping shadow + denoise  */
     int32_t fuse_denoise;            /* vkp_render (Hybrid): run blur.comp inside the resolve kernel instead of as its own pass */
-    int32_t reserved[3];
+    int32_t reproject_fix;           /* blur.comp:52-53 on a reset frame.  0 (default): the reference's history fetch, pixel + motion.x * (W, H)
+                                        (wrong sign and scale, x component used for both axes).
+                                        1: the previous frame's pixel, floor(pixel + 0.5 - 0.5 * motion * (W, H))                */
+    int32_t reserved[2];
 } vkp_params;
 
 /* Planes readable with vkp_readback / writable with vkp_upload_plane.  Layouts are row-major,

@@ -797,6 +797,13 @@ void orc_denoise_pass(const vkp_params* p, int n_lights, const orc_gbuffer* g, c
                     /* blur.comp:53: lastUV = (x + r.x*W, y + r*H) -- the vec2 ctor keeps r.x for the second
                      * component too (App. A #12) */
                     float lastx = (float)x + rx * (float)W, lasty = (float)y + rx * (float)H;
+                    if (p->reproject_fix) {
+                        /* vkp_params.reproject_fix: motion = ndc - ndcPrev (geometry_shader.frag:73-76), ndc spans 2 over
+                         * the screen: the pixel this surface point covered last frame */
+                        float ry = from_half(g->motion[2 * px + 1]) * 2.0f - 1.0f;
+                        lastx = floorf(((float)x + 0.5f) - (rx * 0.5f) * (float)W);
+                        lasty = floorf(((float)y + 0.5f) - (ry * 0.5f) * (float)H);
+                    }
                     float center = in_at(l, x, y);
                     float minColor = center, maxColor = center;
                     for (int yy = -1; yy <= 1; yy++)

@@ -229,3 +229,49 @@ def test_gltf_viewer_scene_renders_through_the_oracle(tmp_path):
     assert len(np.unique(g.material[textured][:, 1])) > 5 and len(np.unique(g.material[plain][:, 1])) == 1
     assert np.isfinite(fr["final"]).all() and fr["final"][..., :3].max() > 0.05
     o.close(); sc.close()
+
+
+def test_reproject_fix_fetches_the_previous_frames_pixel(small_scene, small_oracle):
+    """vkp_params.reproject_fix.  blur.comp:52-53 fetches the history at pixel + motion.x * (W, H) -- wrong sign
+    and scale, x for both axes; the flag fetches floor(pixel + 0.5 - 0.5 * motion * (W, H)) instead.  After a camera move the
+    re-projected history must (a) be the value the same surface point had in the previous frame and (b) bring the reset
+    frame closer to the converged shadow than the reference's fetch does.  Default (0) stays the reference's behaviour."""
+    sc = vk.HostScene(0, detail=(4, 3, 4, 6))
+    o = small_oracle
+    w, h = 160, 90
+    cam0 = sc.camera(w, h)
+    hist = None
+    for f in range(8):                                          # converge the soft shadows at the first camera
+        fr0 = o.hybrid_frame(cam0, vk.make_params(w, h, frame=f), history=hist); hist = fr0["denoised"]
+    sc.move_camera(3, 6.0); sc.rotate_camera(12.0, 4.0)         # strafe + look: a few pixels of image motion
+    cam1 = sc.camera(w, h, prev=cam0)
+    truth = None
+    for f in range(8):
+        t = o.hybrid_frame(cam1, vk.make_params(w, h, frame=f), history=truth); truth = t["denoised"]
+    p_ref = vk.make_params(w, h, frame=0)
+    p_fix = vk.make_params(w, h, frame=0, reproject_fix=1)
+    a = o.hybrid_frame(cam1, p_ref, history=hist)
+    b = o.hybrid_frame(cam1, p_fix, history=hist)
+    g = b["g"]
+    assert np.array_equal(a["shadow"], b["shadow"]) and np.array_equal(a["g"].motion, g.motion)      # only the filter changes
+    # (a) re-projection lands on the same surface: previous-frame instance id at the fetched pixel == current id
+    mo = g.motion.astype(np.float32) * 2 - 1
+    ys, xs = np.mgrid[0:h, 0:w]
+    lx = np.floor((xs + np.float32(0.5)) - (mo[..., 0] * np.float32(0.5)) * np.float32(w)).astype(int)
+    ly = np.floor((ys + np.float32(0.5)) - (mo[..., 1] * np.float32(0.5)) * np.float32(h)).astype(int)
+    inside = (lx >= 0) & (ly >= 0) & (lx < w) & (ly < h) & (g.hit_ids[..., 0] >= 0)
+    same = fr0["g"].hit_ids[ly[inside], lx[inside], 0] == g.hit_ids[..., 0][inside]
+    assert inside.mean() > 0.3 and same.mean() > 0.97
+    moved = (np.abs(lx - xs) + np.abs(ly - ys))[inside]
+    assert moved.max() >= 2                                      # the move is not a no-op
+    # (b) closer to the converged result, on the pixels whose history is available
+    err_ref = np.abs(a["denoised"].astype(int) - truth.astype(int))[:, inside].mean()
+    err_fix = np.abs(b["denoised"].astype(int) - truth.astype(int))[:, inside].mean()
+    assert err_fix < err_ref, (err_fix, err_ref)
+    # static camera: motion == 0 on geometry, the two fetches coincide there (sky pixels store motion 0 = decoded -1,
+    # skybox.frag:19; their shadow value is never used, hybridRaygen.rgen:182-183) and the image is the same
+    s0 = o.hybrid_frame(cam0, vk.make_params(w, h, frame=0), history=hist)
+    s1 = o.hybrid_frame(cam0, vk.make_params(w, h, frame=0, reproject_fix=1), history=hist)
+    geo = s0["g"].hit_ids[..., 0] >= 0
+    assert np.array_equal(s0["denoised"][:, geo], s1["denoised"][:, geo]) and np.array_equal(s0["final"].view(np.uint32), s1["final"].view(np.uint32))
+    sc.close()

@@ -44,3 +44,32 @@ def test_gltf_prefab_frames_match_the_oracle(tmp_path):
             assert np.array_equal(ctx.readback(PLANE.DENOISED0 + l), ref["denoised"][l]), (f, l)
         assert np.array_equal(ctx.readback(PLANE.FINAL_F32).view(np.uint32), ref["final"].view(np.uint32)), f
     ctx.close(); sc.close(); o.close()
+
+
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_reproject_fix_matches_the_oracle(small_scene, small_oracle, fuse):
+    """vkp_params.reproject_fix = 1: converge the history at one camera, move, and compare the reset frame that
+    re-projects that history -- through the stand-alone filter pass and through the one fused into the resolve kernel."""
+    o = small_oracle
+    sc = vk.HostScene(0, detail=(4, 3, 4, 6))
+    ctx = vk.Context(0); ctx.upload_scene(sc)
+    w, h = 192, 108
+    cam0 = sc.camera(w, h)
+    hist = None
+    ctx.set_camera(cam0)
+    for f in range(3):
+        p = vk.make_params(w, h, frame=f, fuse_denoise=fuse, reproject_fix=1)
+        ctx.set_params(p); ctx.render()
+        ref = o.hybrid_frame(cam0, p, history=hist); hist = ref["denoised"]
+    sc.move_camera(3, 6.0); sc.rotate_camera(12.0, 4.0)
+    cam1 = sc.camera(w, h, prev=cam0)
+    p = vk.make_params(w, h, frame=0, fuse_denoise=fuse, reproject_fix=1)
+    ctx.set_camera(cam1); ctx.set_params(p); ctx.render()
+    ref = o.hybrid_frame(cam1, p, history=hist)
+    faithful = o.hybrid_frame(cam1, vk.make_params(w, h, frame=0), history=hist)
+    assert not np.array_equal(ref["denoised"], faithful["denoised"])            # the flag does change the fetch
+    assert np.array_equal(ctx.readback(PLANE.MOTION).view(np.uint16), ref["g"].motion.view(np.uint16))
+    for l in range(len(sc.lights)):
+        assert np.array_equal(ctx.readback(PLANE.DENOISED0 + l), ref["denoised"][l]), l
+    assert np.array_equal(ctx.readback(PLANE.FINAL_F32).view(np.uint32), ref["final"].view(np.uint32))
+    ctx.close(); sc.close()

@@ -188,7 +188,7 @@ def decode_image(path):
 
 
 def make_params(width, height, mode=MODE_HYBRID, spp=1, shadow_samples=1, max_bounces=8, frame=0, denoise_frame=None,
-                faithful_rng=1, denoise_cover_remainder=1, debug_target=0, wavefront=0, fuse_denoise=0):
+                faithful_rng=1, denoise_cover_remainder=1, debug_target=0, wavefront=0, fuse_denoise=0, reproject_fix=0):
     p = T.Params()
     p.width, p.height, p.mode, p.spp, p.shadow_samples, p.max_bounces = width, height, mode, spp, shadow_samples, max_bounces
     p.frame = frame
@@ -196,6 +196,7 @@ def make_params(width, height, mode=MODE_HYBRID, spp=1, shadow_samples=1, max_bo
     p.faithful_rng, p.denoise_cover_remainder, p.debug_target = faithful_rng, denoise_cover_remainder, debug_target
     p.wavefront = wavefront
     p.fuse_denoise = fuse_denoise
+    p.reproject_fix = reproject_fix
     return p
 
 

@@ -519,6 +519,12 @@ __device__ __forceinline__ uint8_t denoise_pixel(const DFrame& F, int l, int x, 
         uint32_t m = F.motion[i];
         float rx = vkp_f16_to_f32((uint16_t)(m & 0xffffu)) * 2.0f - 1.0f;
         float lastx = (float)x + rx * (float)W, lasty = (float)y + rx * (float)H;   // blur.comp:53 (r.x twice)
+        if (F.p.reproject_fix) {
+            // motion = ndc - ndcPrev (geometry_shader.frag:73-76), ndc spans 2 over the screen: where this surface point was last frame
+            float ry = vkp_f16_to_f32((uint16_t)(m >> 16)) * 2.0f - 1.0f;
+            lastx = floorf(((float)x + 0.5f) - (rx * 0.5f) * (float)W);
+            lasty = floorf(((float)y + 0.5f) - (ry * 0.5f) * (float)H);
+        }
         float center = unit255(in[i]);
         float minColor = center, maxColor = center;
 #pragma unroll

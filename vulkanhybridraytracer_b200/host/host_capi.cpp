@@ -140,6 +140,7 @@ VKPH_API int vkph_engine_set(void* p, const char* key, int value)
     else if (k == "faithful_rng") e->_faithfulRng = value != 0;
     else if (k == "debug_target") e->debugTarget = value;
     else if (k == "chain") e->_chainMode = value;
+    else if (k == "reproject_fix") e->_reprojectFix = value != 0;
     else return -1;
     return 0;
 }

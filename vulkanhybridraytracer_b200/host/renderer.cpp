@@ -154,6 +154,7 @@ vkp_params VulkanEngine::current_params() const
     p.denoise_cover_remainder = 1;
     p.debug_target = debugTarget;
     p.wavefront = _chainMode;
+    p.reproject_fix = _reprojectFix ? 1 : 0;
     p.fuse_denoise = 0;   // measured: the stand-alone filter pass hides under the overlapped reflection chain, fused it lands on the critical path
     return p;
 }

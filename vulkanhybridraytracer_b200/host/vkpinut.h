@@ -285,6 +285,7 @@ public:
     int _spp{1};
     int _maxBounces{8};
     bool _faithfulRng{true};
+    bool _reprojectFix{false};          // vkp_params.reproject_fix: false = the reference's blur.comp history fetch, true = the previous frame's pixel
     int _chainMode{2};                  // vkp_params.wavefront: how the reflection chain is scheduled (0 inline, 1 wavefront, 2 overlapped)
 
     void init();
