@@ -86,7 +86,10 @@ typedef struct vkp_params {
     int32_t reproject_fix;           /* blur.comp:52-53 on a reset frame.  0 (default): the reference's history fetch, pixel + motion.x * (W, H)
                                         (wrong sign and scale, x component used for both axes).
                                         1: the previous frame's pixel, floor(pixel + 0.5 - 0.5 * motion * (W, H))                */
-    int32_t reserved[2];
+    int32_t shadow_tail_budget;      /* k_shadow, one-sample frames: child-pair fetches a thread spends on a shadow ray before it hands the
+                                        ray to the warp-cooperative tail kernel.  0 = the context default
+                                        (VKP_SHADOW_TAIL in the environment, else built in), < 0 = off.  Changes the schedule, never a bit. */
+    int32_t reserved[1];
 } vkp_params;
 
 /* Planes readable with vkp_readback / writable with vkp_upload_plane.  Layouts are row-major,

@@ -73,3 +73,37 @@ def test_reproject_fix_matches_the_oracle(small_scene, small_oracle, fuse):
         assert np.array_equal(ctx.readback(PLANE.DENOISED0 + l), ref["denoised"][l]), l
     assert np.array_equal(ctx.readback(PLANE.FINAL_F32).view(np.uint32), ref["final"].view(np.uint32))
     ctx.close(); sc.close()
+
+
+@pytest.mark.parametrize("budget,cap", [(1, 0), (6, 0), (40, 0), (3, 500)])
+def test_shadow_tail_kernel_changes_no_bit(small_scene, small_oracle, budget, cap, monkeypatch):
+    """vkp_params.shadow_tail_budget: k_shadow hands rays that are still unanswered after `budget` child-pair fetches to the
+    warp-cooperative tail kernel (one warp per ray, lanes share the stack items).  An any-hit answer does not depend on the order
+    of the walk, so every shadow plane -- and everything downstream -- must stay bit-identical to the oracle: with nearly every
+    ray spilled (budget 1), with a realistic budget, and with a queue too small for the spills (the thread then carries on)."""
+    if cap:
+        monkeypatch.setenv("VKP_SHADOW_TAIL_CAP", str(cap))
+    o = small_oracle
+    ctx = vk.Context(0); ctx.upload_scene(small_scene)
+    w, h = 320, 184
+    cam = small_scene.camera(w, h); ctx.set_camera(cam)
+    hist = None
+    for f in range(3):
+        p = vk.make_params(w, h, frame=f, shadow_tail_budget=budget, wavefront=2)
+        ctx.set_params(p); ctx.render()
+        o.reset_counters()
+        ref = o.hybrid_frame(cam, vk.make_params(w, h, frame=f), history=hist); hist = ref["denoised"]
+        for l in range(len(small_scene.lights)):
+            assert np.array_equal(ctx.readback(PLANE.SHADOW0 + l), ref["shadow"][l]), (f, l)
+            assert np.array_equal(ctx.readback(PLANE.DENOISED0 + l), ref["denoised"][l]), (f, l)
+        assert np.array_equal(ctx.readback(PLANE.FINAL_F32).view(np.uint32), ref["final"].view(np.uint32)), f
+        c = ctx.counters()
+        assert [c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow] == list(o.counters.rays)
+        assert c.kernel_launches >= 6                       # + k_shadow_tail
+    # the stage alone, and switched off again
+    ctx.set_params(vk.make_params(w, h, frame=0, shadow_tail_budget=budget)); ctx.run_stage(vk.STAGE.SHADOW)
+    a = [ctx.readback(PLANE.SHADOW0 + l) for l in range(3)]
+    ctx.set_params(vk.make_params(w, h, frame=0, shadow_tail_budget=-1)); ctx.run_stage(vk.STAGE.SHADOW)
+    for l in range(3):
+        assert np.array_equal(a[l], ctx.readback(PLANE.SHADOW0 + l))
+    ctx.close()

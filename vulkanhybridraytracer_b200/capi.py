@@ -188,7 +188,7 @@ def decode_image(path):
 
 
 def make_params(width, height, mode=MODE_HYBRID, spp=1, shadow_samples=1, max_bounces=8, frame=0, denoise_frame=None,
-                faithful_rng=1, denoise_cover_remainder=1, debug_target=0, wavefront=0, fuse_denoise=0, reproject_fix=0):
+                faithful_rng=1, denoise_cover_remainder=1, debug_target=0, wavefront=0, fuse_denoise=0, reproject_fix=0, shadow_tail_budget=0):
     p = T.Params()
     p.width, p.height, p.mode, p.spp, p.shadow_samples, p.max_bounces = width, height, mode, spp, shadow_samples, max_bounces
     p.frame = frame
@@ -197,6 +197,7 @@ def make_params(width, height, mode=MODE_HYBRID, spp=1, shadow_samples=1, max_bo
     p.wavefront = wavefront
     p.fuse_denoise = fuse_denoise
     p.reproject_fix = reproject_fix
+    p.shadow_tail_budget = shadow_tail_budget
     return p
 
 

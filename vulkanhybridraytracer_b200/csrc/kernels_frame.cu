@@ -441,7 +441,9 @@ __device__ __forceinline__ LightGeom light_geom(const vkp_light& light, float3 p
 // MINB = resident CTAs per SM the register budget is set for: 8 (64 registers) when a thread traces one ray and waits on it
 // (latency-bound: 0.39 -> 0.36 ms at 1080p), 5 (96 registers, no spills) when it loops over many soft-shadow samples
 // (issue-bound: cfg5 209 ms against 227 ms at 8).
-template <int MINB>
+// SPILL: the frame traces one ray per (pixel, light) and a thread hands a ray that is still unanswered after
+// F.spill_budget child-pair fetches to k_shadow_tail (below) instead of setting the duration of the whole kernel with it.
+template <int MINB, bool SPILL>
 __global__ void __launch_bounds__(128, MINB) k_shadow(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     const long long t_start = clock64();
@@ -469,6 +471,7 @@ __global__ void __launch_bounds__(128, MINB) k_shadow(const __grid_constant__ DS
             const vkp_light light = S.lights[l];
             const LightGeom g = light_geom(light, position, N);
             float shadowFactor = 0.0f;
+            bool spilled = false;
             if (g.NdotL > 0.0f) {
                 if (g.dist < g.maxd) {
                     // the RNG is only needed when rays are traced: TEA (16 rounds) is the most expensive part of an unlit pixel
@@ -480,6 +483,19 @@ __global__ void __launch_bounds__(128, MINB) k_shadow(const __grid_constant__ DS
                                 for (int r = 0; r < 2 * shadowSamples; r++) seed = 1664525u * seed + 1013904223u;   // two rnd() per sampleDisk
                         }
                     }
+                    if (SPILL) {
+                        const float3 dir = sample_disk(light, position, g.L, seed, advance);
+                        const float3 org = position + dir * 1e-1f;
+                        HitRec h; nrays++;
+                        const bool hit = trace_ray<true, false, true>(S, org, dir, 0.001f, g.dist + 1.0f, h, nullptr, tcp, F.spill_budget,
+                                                                      F.spill_cnt + 2 * F.spill_parity, F.spill_cap);
+                        if (h.prim == VKP_TRACE_SPILLED) {
+                            float4* rec = F.spill_rec + 2u * (size_t)h.inst;
+                            rec[0] = make_float4(org.x, org.y, org.z, g.dist + 1.0f);
+                            rec[1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float((unsigned int)(l * plane + i)));
+                            spilled = true;
+                        } else if (!hit) shadowFactor += 1.0f;
+                    } else
                     for (int s = 0; s < shadowSamples; s++) {
                         const float3 dir = sample_disk(light, position, g.L, seed, advance);
                         HitRec h; nrays++;
@@ -490,13 +506,38 @@ __global__ void __launch_bounds__(128, MINB) k_shadow(const __grid_constant__ DS
                 }
                 shadowFactor /= (float)shadowSamples;
             }
-            F.shadow[l * plane + i] = vkp_unorm8(shadowFactor);
+            if (!spilled) F.shadow[l * plane + i] = vkp_unorm8(shadowFactor);      // a spilled ray's byte is written by k_shadow_tail
         }
     }
     add_counter(F.counters, 1, nrays);
     if (F.count_trav) add_trav(F.counters, tc, (1u << 28) | ((unsigned)l << 23) | (unsigned)(px.valid ? px.y * F.p.width + px.x : 0));
     record_cost(F.cta_cost[1], vb, t_start);
 }
+
+// The rays k_shadow<., true> gave up on, one warp per ray (warp_any_hit, vkp_bvh.cuh).  Warps take rays from the queue with an
+// atomic head; the block that starts first clears the counter pair of the other parity for the next frame's k_shadow, so no
+// memset sits between the kernels of a frame.  shadowFactor of a one-sample ray is 0 or 1: the byte is 0 or 255.
+#if !VKP_WIDE
+__global__ void __launch_bounds__(128) k_shadow_tail(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    unsigned int* cnt = F.spill_cnt + 2 * F.spill_parity;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned int* other = F.spill_cnt + 2 * (F.spill_parity ^ 1); other[0] = 0u; other[1] = 0u; }
+    const unsigned int n = min(cnt[0], F.spill_cap);
+    const int lane = (int)(threadIdx.x & 31u);
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;
+    while (true) {
+        unsigned int r = 0u;
+        if (lane == 0) r = atomicAdd(cnt + 1, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= n) break;
+        const float4 a = F.spill_rec[2u * (size_t)r], b = F.spill_rec[2u * (size_t)r + 1u];
+        const bool hit = warp_any_hit(S, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), 0.001f, a.w, tcp);
+        if (lane == 0) F.shadow[__float_as_uint(b.w)] = hit ? (uint8_t)0 : (uint8_t)255;
+    }
+    if (F.count_trav) add_trav(F.counters, tc);
+}
+#endif
 
 // blur.comp:35-82 for one pixel and one light, with runtime W/H/NLIGHTS and an integer motion fetch; returns the new
 // R8 history value (pixels outside the faithful dispatch area keep their history)
@@ -1181,13 +1222,20 @@ inline dim3 frame_grid(const FrameLaunch& L)
 
 } // namespace
 
+bool shadow_spills(const FrameLaunch& L) { return !VKP_WIDE && L.frame.p.shadow_samples == 1 && L.frame.spill_budget > 0 && L.frame.spill_rec && L.scene.n_lights > 0 && L.n_own_tiles > 0; }
 cudaError_t launch_gbuffer(const FrameLaunch& L) { k_gbuffer<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
 cudaError_t launch_shadow(const FrameLaunch& L)
 {
     if (L.scene.n_lights == 0) return cudaSuccess;
     dim3 g = frame_grid(L); g.x *= (unsigned)L.scene.n_lights;      // light-major: virtual block = light * n_cta + pixel block
-    if (L.frame.p.shadow_samples >= 4) k_shadow<VKP_LB_SHADOW_MANY><<<g, 128, 0, L.stream>>>(L.scene, L.frame);
-    else k_shadow<VKP_LB_SHADOW><<<g, 128, 0, L.stream>>>(L.scene, L.frame);
+    if (L.frame.p.shadow_samples >= 4) k_shadow<VKP_LB_SHADOW_MANY, false><<<g, 128, 0, L.stream>>>(L.scene, L.frame);
+#if !VKP_WIDE
+    else if (shadow_spills(L)) {
+        k_shadow<VKP_LB_SHADOW, true><<<g, 128, 0, L.stream>>>(L.scene, L.frame);
+        k_shadow_tail<<<148 * 4, 128, 0, L.stream>>>(L.scene, L.frame);
+    }
+#endif
+    else k_shadow<VKP_LB_SHADOW, false><<<g, 128, 0, L.stream>>>(L.scene, L.frame);
     return cudaGetLastError();
 }
 cudaError_t launch_build_order(cudaStream_t s, uint32_t* cost, uint32_t* order, uint32_t n)

@@ -19,6 +19,11 @@ std::string g_create_error;
 
 } // namespace
 
+// default of vkp_params.shadow_tail_budget == 0 when VKP_SHADOW_TAIL is not in the environment (measured: DESIGN.md section 4)
+#ifndef VKP_SHADOW_TAIL_DEFAULT
+#define VKP_SHADOW_TAIL_DEFAULT 0
+#endif
+
 struct vkp_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -60,6 +65,12 @@ struct vkp_ctx {
     int rank = 0, world = 1, tile_w = 16, tile_h = 8;
 
     DevBuf position, normal, albedo, motion, material, emissive, hit_ids, final_f32, final_srgb8, shadow, denoised[2];
+    // tail of k_shadow: spill queue (32 B per ray), {count, head} x 2 parities, the default step budget (0 = off)
+    DevBuf spill_rec, spill_cnt;
+    unsigned int spill_cap = 0;
+    int spill_parity = 0;
+    int shadow_tail = VKP_SHADOW_TAIL_DEFAULT;
+    long long spill_cap_env = 0;
     int denoised_cur = 0;
     int plane_w = 0, plane_h = 0, plane_lights = 0;
     DevBuf counters, io_tmp, io_tmp2, flush, path_q[2], path_count, luts, chain_buf, chain_len, chain_slot;
@@ -194,6 +205,16 @@ int ensure_planes(vkp_ctx* ctx)
     CK(ctx->final_f32.ensure(px * 16)); CK(ctx->final_srgb8.ensure(px * 4)); CK(ctx->final_srgb8_alt.ensure(px * 4));
     CK(ctx->shadow.ensure(px * L)); CK(ctx->denoised[0].ensure(px * L)); CK(ctx->denoised[1].ensure(px * L));
     CK(ctx->counters.ensure(64));
+    {
+        // a budget worth having spills a few per cent of the rays; a full queue is not an error (the thread finishes its ray itself)
+        const size_t rays = px * (size_t)L;
+        size_t cap = rays / 8 > 65536 ? rays / 8 : 65536;
+        if (ctx->spill_cap_env > 0) cap = (size_t)ctx->spill_cap_env;
+        if (cap > 0x7fffffffu) cap = 0x7fffffffu;
+        CK(ctx->spill_rec.ensure(cap * 32)); CK(ctx->spill_cnt.ensure(16));
+        ctx->spill_cap = (unsigned int)cap; ctx->spill_parity = 0;
+        CK(cudaMemsetAsync(ctx->spill_cnt.p, 0, 16, ctx->stream));
+    }
     CK(ctx->path_q[0].ensure(px * sizeof(PathItem))); CK(ctx->path_q[1].ensure(px * sizeof(PathItem)));
     CK(ctx->path_count.ensure(sizeof(unsigned int) * (VKP_MAX_BOUNCES + 2)));
     CK(ctx->chain_buf.ensure(px * sizeof(float4) * VKP_CHAIN_MAX)); CK(ctx->chain_len.ensure(px * sizeof(int))); CK(ctx->chain_slot.ensure(px * sizeof(int)));
@@ -337,6 +358,9 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.denoised = ctx->denoised[ctx->denoised_cur].as<uint8_t>();
     F.denoised_next = ctx->denoised[ctx->denoised_cur ^ 1].as<uint8_t>();
     F.counters = ctx->counters.as<unsigned long long>();
+    F.spill_rec = ctx->spill_rec.as<float4>(); F.spill_cnt = ctx->spill_cnt.as<unsigned int>(); F.spill_cap = ctx->spill_cap;
+    F.spill_parity = ctx->spill_parity;
+    F.spill_budget = F.p.shadow_tail_budget > 0 ? F.p.shadow_tail_budget : (F.p.shadow_tail_budget < 0 ? 0 : ctx->shadow_tail);
     F.path_q[0] = ctx->path_q[0].as<PathItem>(); F.path_q[1] = ctx->path_q[1].as<PathItem>();
     F.path_count = ctx->path_count.as<unsigned int>();
     F.lut_pow22 = ctx->luts.as<float>(); F.lut_post = ctx->luts.as<uint8_t>() + 1024;
@@ -382,7 +406,10 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
     case VKP_STAGE_SHADOW: {
         const int k = stage == VKP_STAGE_SHADOW ? 1 : 0;
         if (ctx->order_pending[k]) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_order_done[k], 0)); ctx->order_pending[k] = false; }
-        if (k) CK(launch_shadow(L)); else CK(launch_gbuffer(L));
+        if (k) {
+            CK(launch_shadow(L));
+            if (shadow_spills(L)) { ctx->spill_parity ^= 1; L.frame.spill_parity = ctx->spill_parity; ctx->last_launches++; }      // + k_shadow_tail
+        } else CK(launch_gbuffer(L));
         if (L.frame.cta_cost[k]) {       // next frame's order from this frame's costs, beside the rest of the frame
             CK(cudaEventRecord(ctx->ev_stage_done[k], ctx->stream));
             CK(cudaStreamWaitEvent(ctx->order_stream, ctx->ev_stage_done[k], 0));
@@ -461,6 +488,8 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
         cudaEventCreateWithFlags(&ctx->ev_gbuffer, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
     }
+    if (const char* t = getenv("VKP_SHADOW_TAIL")) ctx->shadow_tail = atoi(t) > 0 ? atoi(t) : 0;
+    if (const char* c = getenv("VKP_SHADOW_TAIL_CAP")) ctx->spill_cap_env = atoll(c);
     if (const char* b = getenv("VKP_BLAS_BUILDER")) ctx->builder = (strcmp(b, "lbvh") == 0) ? 0 : 1;
     cudaEventCreate(&ctx->timer0); cudaEventCreate(&ctx->timer1);
     // decode / gamma tables, computed on the device with the contract's own vkp_powf so they are bit-identical to the call
@@ -495,7 +524,7 @@ void vkp_destroy(vkp_ctx* ctx)
     if (ctx->ev_updated) cudaEventDestroy(ctx->ev_updated);
     DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_textures, &ctx->position, &ctx->normal, &ctx->albedo, &ctx->motion,
                       &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
-                      &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->final_srgb8_alt};
+                      &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->final_srgb8_alt, &ctx->spill_rec, &ctx->spill_cnt};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->timer0) cudaEventDestroy(ctx->timer0);

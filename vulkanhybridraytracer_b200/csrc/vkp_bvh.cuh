@@ -144,10 +144,17 @@ VKP_D bool hit_better(float t, int inst, int prim, const HitRec& h)
 #else
 #define VKP_TRACE_FN __device__ __forceinline__
 #endif
-template <bool ANY, bool STATS = false>
-VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax, HitRec& best, uint32_t* stats = nullptr, TravCount* tcount = nullptr)
+// LIMITED == true (one-sample shadow rays, k_shadow): after `max_steps` child-pair fetches the thread reserves a slot in the
+// spill queue and gives the ray up -- best.prim = VKP_TRACE_SPILLED, best.inst = slot -- for the warp-cooperative tail kernel
+// (warp_any_hit below); when the queue is full it simply carries on.  A kernel ends with its slowest thread, and the slowest
+// shadow rays walk 50-100x the average number of nodes.
+#define VKP_TRACE_SPILLED (-2)
+template <bool ANY, bool STATS = false, bool LIMITED = false>
+VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, float tmax, HitRec& best, uint32_t* stats = nullptr, TravCount* tcount = nullptr,
+                            int max_steps = 0, unsigned int* spill_count = nullptr, unsigned int spill_cap = 0u)
 {
     uint32_t n_steps = 0, n_tris = 0;      // STATS: node pairs fetched, triangles tested
+    int n_limited = 0;
     best.t = -1.0f; best.u = 0.0f; best.v = 0.0f; best.inst = -1; best.prim = -1;
     if (S.n_instances == 0) return false;     // empty TLAS: its root box is inverted, which a slab test cannot reject
     float limit = tmax;                       // current far bound (closest so far)
@@ -181,6 +188,12 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
     while (true) {
 #if !VKP_WIDE
         while (!(cur & VKP_LEAF_BIT)) {
+            if (LIMITED) {
+                if (++n_limited == max_steps) {
+                    const unsigned int slot = atomicAdd(spill_count, 1u);
+                    if (slot < spill_cap) { best.prim = VKP_TRACE_SPILLED; best.inst = (int)slot; return false; }
+                }
+            }
             const float4* c = nodes + 2u * (size_t)cur;      // both children: 64 contiguous bytes
             if (STATS) n_steps++;
             if (tcount) tcount->nodes++;
@@ -305,3 +318,114 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
     if (STATS) { stats[0] = n_steps; stats[1] = n_tris; }
     return best.inst >= 0;
 }
+
+
+#if !VKP_WIDE
+// ---- warp-cooperative any-hit traversal (the tail of k_shadow) --------------------------------------------------------------------
+// One warp, ONE ray.  An any-hit query is the OR over every leaf the ray's interval reaches, so the order of the walk is free:
+// each lane keeps its own stack of (node reference, instance) items and walks depth-first; a lane that runs dry takes the OLDEST
+// item (the root of the largest unexplored subtree) of a lane that still has some, through two shuffles.  Items carry their
+// instance (-1 = TLAS level), so there are no "return to the TLAS" markers and a lane re-derives the object-space ray only when
+// the instance of its item changes.  A ray that needs N child-pair fetches finishes in about N / 32 + tree depth trips instead
+// of N.  Same box test, same triangle test, same far bound as trace_ray<true>: the answer is the same boolean.
+static __device__ __forceinline__ bool warp_any_hit(const DScene& S, float3 o, float3 d, float tmin, float tmax, TravCount* tcount)
+{
+    const unsigned int full = 0xffffffffu;
+    const int lane = (int)(threadIdx.x & 31u);
+    const unsigned int lt = (1u << lane) - 1u;
+    if (S.n_instances == 0) return false;
+
+    uint2 stack[VKP_TRAV_STACK];
+    int base = 0, sp = 0;                    // live items: stack[base .. sp)
+    bool has = false;                        // a current item
+    uint32_t cur = 0u;
+    int cinst = -1;
+    int finst = -2;                          // instance the cached object-space ray belongs to (-1 world, -2 none yet)
+    float3 ro = o, rd = d;
+    const float3 winv = safe_inv_dir(d);
+    const bool wpar = has_parallel_axis(d);
+    float3 inv = winv;
+    bool par = wpar;
+    const float4* nodes = S.tlas_nodes2;
+    const float4* tris = nullptr;
+    if (lane == 0) { has = true; cur = S.tlas_root_ref2; cinst = -1; }
+
+    while (true) {
+        if (!has && sp > base) {
+            const uint2 e = stack[--sp];
+            cur = e.x; cinst = (int)e.y; has = true;
+            if (sp == base) sp = base = 0;
+        }
+        bool found = false;
+        if (has) {
+            if (cinst != finst) {
+                finst = cinst;
+                if (cinst < 0) { ro = o; rd = d; inv = winv; par = wpar; nodes = S.tlas_nodes2; tris = nullptr; }
+                else {
+                    const float4* rec = reinterpret_cast<const float4*>(S.inst_trav + cinst);
+                    const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), pp = __ldg(rec + 3), rr = __ldg(rec + 4);
+                    ro = f3(((r0.x * o.x + r0.y * o.y) + r0.z * o.z) + r0.w, ((r1.x * o.x + r1.y * o.y) + r1.z * o.z) + r1.w, ((r2.x * o.x + r2.y * o.y) + r2.z * o.z) + r2.w);
+                    rd = f3((r0.x * d.x + r0.y * d.y) + r0.z * d.z, (r1.x * d.x + r1.y * d.y) + r1.z * d.z, (r2.x * d.x + r2.y * d.y) + r2.z * d.z);
+                    inv = safe_inv_dir(rd);
+                    par = has_parallel_axis(rd);
+                    tris = reinterpret_cast<const float4*>(((unsigned long long)__float_as_uint(pp.w) << 32) | (unsigned long long)__float_as_uint(pp.z));
+                    nodes = reinterpret_cast<const float4*>(((unsigned long long)__float_as_uint(rr.w) << 32) | (unsigned long long)__float_as_uint(rr.z));
+                }
+            }
+            if (!(cur & VKP_LEAF_BIT)) {
+                const float4* c = nodes + 2u * (size_t)cur;
+                if (tcount) tcount->nodes++;
+                const float4 lo0 = __ldg(c + 0), hi0 = __ldg(c + 1), lo1 = __ldg(c + 2), hi1 = __ldg(c + 3);
+                float t0, t1;
+                const bool h0 = box_test(lo0, hi0, ro, rd, inv, par, tmin, tmax, t0);
+                const bool h1 = box_test(lo1, hi1, ro, rd, inv, par, tmin, tmax, t1);
+                const uint32_t r0 = __float_as_uint(lo0.w), r1 = __float_as_uint(lo1.w);
+                if (h0 && h1) { stack[sp++] = make_uint2(r1, (unsigned int)cinst); cur = r0; }
+                else if (h0) cur = r0;
+                else if (h1) cur = r1;
+                else has = false;
+            } else if (cinst < 0) {
+                // TLAS leaf: the item becomes (root of that instance's BLAS, instance); the record is read on the next trip
+                cinst = (int)((cur & 0x7fffffffu) >> 3);
+                if (tcount) tcount->entries++;
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(S.inst_trav + cinst) + 4);
+                cur = __float_as_uint(rr.y);
+            } else {
+                const uint32_t first = (cur & 0x7fffffffu) >> 3, count = (cur & 7u) + 1u;
+                const float4* tp = tris + 3u * (size_t)first;
+                float4 ta[4], tb[4], tc[4];
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++)
+                    if (k < count) { ta[k] = __ldg(tp + 3 * k); tb[k] = __ldg(tp + 3 * k + 1); tc[k] = __ldg(tp + 3 * k + 2); }
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++) {
+                    if (k < count) {
+                        if (tcount) tcount->tris++;
+                        float t, u, v;
+                        if (tri_test(ro, rd, f3(ta[k].x, ta[k].y, ta[k].z), f3(tb[k].x, tb[k].y, tb[k].z), f3(tc[k].x, tc[k].y, tc[k].z), tmin, tmax, t, u, v)) found = true;
+                    }
+                }
+                has = false;
+            }
+        }
+        if (__any_sync(full, found)) return true;
+        const bool dry = !has && sp == base;
+        const unsigned int need = __ballot_sync(full, dry);
+        if (need == full) return false;                       // nobody has anything left: unoccluded
+        if (need) {
+            const bool can = has && sp > base;               // keeps its current item, gives the oldest one on its stack
+            const unsigned int have = __ballot_sync(full, can);
+            if (have) {
+                const int n = min(__popc(need), __popc(have));
+                const int rank_give = __popc(have & lt), rank_need = __popc(need & lt);
+                uint2 give = make_uint2(0u, 0u);
+                if (can && rank_give < n) { give = stack[base++]; if (sp == base) sp = base = 0; }
+                const bool take = dry && rank_need < n;
+                const int src = take ? (int)__fns(have, 0u, rank_need + 1) : lane;
+                const uint32_t gx = __shfl_sync(full, give.x, src), gy = __shfl_sync(full, give.y, src);
+                if (take) { cur = gx; cinst = (int)gy; has = true; }
+            }
+        }
+    }
+}
+#endif   // !VKP_WIDE

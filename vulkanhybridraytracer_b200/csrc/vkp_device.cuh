@@ -175,6 +175,14 @@ struct DFrame {
     const uint32_t* cta_order[2];
     uint32_t* cta_cost[2];
     int n_cta;                      // CTAs per pixel pass on this rank (k_shadow runs n_cta * n_lights of them)
+    // tail of k_shadow (one-sample shadow rays): a thread that has fetched spill_budget child pairs without an answer appends
+    // its ray to spill_rec (2 x float4: origin | tmax, direction | index into `shadow`) and k_shadow_tail finishes it with one
+    // warp per ray.  spill_cnt = {count, head} x 2: the pair of this frame and the pair the tail kernel clears for the next one.
+    float4* spill_rec;
+    unsigned int* spill_cnt;
+    unsigned int spill_cap;
+    int spill_budget;               // 0 = off
+    int spill_parity;
 };
 
 // k / 255.0f for the 256 possible bytes, filled on the device by k_build_luts with the same IEEE division the contract

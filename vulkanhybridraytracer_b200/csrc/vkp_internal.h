@@ -83,6 +83,7 @@ struct FrameLaunch {
 };
 cudaError_t launch_gbuffer(const FrameLaunch& L);
 cudaError_t launch_shadow(const FrameLaunch& L);
+bool shadow_spills(const FrameLaunch& L);     // launch_shadow runs k_shadow<., true> + k_shadow_tail: one more launch, flip the counter parity
 cudaError_t launch_denoise(const FrameLaunch& L);
 cudaError_t launch_build_order(cudaStream_t s, uint32_t* cost, uint32_t* order, uint32_t n);
 cudaError_t launch_resolve(const FrameLaunch& L, int* launches);

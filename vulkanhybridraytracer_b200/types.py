@@ -29,7 +29,7 @@ class Camera(C.Structure):          # vkp_camera, 400 B
 class Params(C.Structure):          # vkp_params, 64 B
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("mode", C.c_int32), ("spp", C.c_int32), ("shadow_samples", C.c_int32),
                 ("max_bounces", C.c_int32), ("frame", C.c_int32), ("denoise_frame", C.c_int32), ("faithful_rng", C.c_int32),
-                ("denoise_cover_remainder", C.c_int32), ("debug_target", C.c_int32), ("wavefront", C.c_int32), ("fuse_denoise", C.c_int32), ("reproject_fix", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("denoise_cover_remainder", C.c_int32), ("debug_target", C.c_int32), ("wavefront", C.c_int32), ("fuse_denoise", C.c_int32), ("reproject_fix", C.c_int32), ("shadow_tail_budget", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class Ray(C.Structure):             # vkp_ray, 32 B
