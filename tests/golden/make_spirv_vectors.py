@@ -108,7 +108,103 @@ def gen_functions():
     print("spirv_functions.npz:", {k: v.shape for k, v in out.items()})
 
 
-GENERATORS = {"functions": gen_functions}
+
+# ------------------------------------------------------------------------------------------------------- scene plumbing
+def golden_scene():
+    import vulkanhybridraytracer_b200 as vk
+    from oracle.oracle_py import Oracle
+    from util import GOLDEN_DETAIL, GOLDEN_W, GOLDEN_H
+    sc = vk.HostScene(0, detail=GOLDEN_DETAIL)
+    return vk, sc, Oracle(sc), GOLDEN_W, GOLDEN_H
+
+
+def mat4_cols(m16):
+    a = np.asarray(m16, dtype=F32).reshape(4, 4)          # column-major float[16]: row k of the reshape = column k
+    return [a[k].copy() for k in range(4)]
+
+
+def lights_block(sc):
+    return [[light_value(l["position"], l["color"], l["radius"]) for l in sc.lights]]
+
+
+def materials_block(sc):
+    return [[[vec(*m["diffuse"]), vec(*m["textures"]), vec(*m["shadingMetallicRoughness"])] for m in sc.materials]]
+
+
+def gbuffer_images(g):
+    """gbuffers[0..2] as bound by the shadow pass (position | material index, normal, motion), fp16 storage read as float."""
+    h, w = g.position.shape[:2]
+    motion = np.zeros((h, w, 4), F32); motion[..., :2] = g.motion.astype(F32); motion[..., 3] = 1
+    return [Image2D(g.position.astype(F32)), Image2D(g.normal.astype(F32)), Image2D(motion)]
+
+
+class ShadowPipeline:
+    """traceRayEXT of a ray-gen shader that only asks "occluded?": the oracle answers the any-hit query on the ray the shader
+    built; on a miss shadow.rmiss.spv main() runs on the caller's payload."""
+
+    def __init__(self, oracle, T):
+        self.o, self.T = oracle, T
+        self.miss = Interpreter(module("shadow.rmiss"))
+        self.miss_payload = self.miss.m.global_by_name("shadowed")
+        self.rays = []
+
+    def __call__(self, interp, flags, cull, sbt_offset, sbt_stride, miss_index, origin, tmin, direction, tmax, payload):
+        assert flags == (0x01 | 0x04 | 0x08) and cull == 0xFF and miss_index in (0, 1)      # Opaque | TerminateOnFirstHit | SkipClosestHit
+        ray = np.zeros(1, self.T.ray_dtype)
+        ray["origin"] = origin; ray["dir"] = direction; ray["tmin"] = tmin; ray["tmax"] = tmax
+        self.rays.append(ray[0].copy())
+        hit = self.o.trace_rays(ray, any_hit=True)
+        if hit["t"][0] < 0:
+            assert not payload.path
+            self.miss.cells[self.miss_payload] = payload.cell
+            self.miss.run_entry()
+
+
+# ------------------------------------------------------------------------------------------------------- a4: shadowRaygen.rgen
+def gen_shadow():
+    vk, sc, o, W, H = golden_scene()
+    from vulkanhybridraytracer_b200 import types as T
+    cam = sc.camera(W, H)
+    m = module("shadowRaygen.rgen")
+    out = {}
+    for tag, frame, samples, step in (("f0", 0, 1, 1), ("f3s4", 3, 4, 3)):
+        p = vk.make_params(W, H, frame=frame, shadow_samples=samples)
+        g = o.gbuffer(cam, p)
+        pipe = ShadowPipeline(o, T)
+        shadow_imgs = [Image2D(np.zeros((H, W, 4), F32), unorm8=True) for _ in sc.lights]
+        res = {"cam": [mat4_cols(cam.inv_view), mat4_cols(cam.inv_proj), F32(frame)], "Lights": lights_block(sc), "SampleBuffer": [I32(samples)],
+               "MaterialBuffer": materials_block(sc), "gbuffers": gbuffer_images(g), "shadowImage": shadow_imgs,
+               "LaunchSizeKHR": np.array([W, H, 1], U32)}
+        it = Interpreter(m, res, trace_ray=pipe)
+        launch = it.m.builtin_globals()["LaunchIdKHR"]
+        pixels, bytes_, ray_rows = [], [], []
+        for y in range(0, H, step):
+            for x in range(0, W, step):
+                it.cells[launch][0] = np.array([x, y, 0], U32)
+                n0 = len(pipe.rays)
+                it.run_entry()
+                pixels.append((x, y))
+                bytes_.append([int(np.rint(img.a[y, x, 0] * 255)) for img in shadow_imgs])
+                rays = pipe.rays[n0:]
+                if samples > 1 and rays:
+                    # App. A #1 straight from the binary: every sample of every light of a pixel re-uses the same (r1, r2), so the
+                    # `samples` rays of one light are one and the same ray
+                    per_light = len(rays) // samples
+                    assert per_light * samples == len(rays)
+                    for k in range(per_light):
+                        grp = rays[k * samples:(k + 1) * samples]
+                        assert all(np.array_equal(grp[0]["dir"], r["dir"]) for r in grp)
+                for r in rays:
+                    ray_rows.append([x, y] + r["origin"].tolist() + r["dir"].tolist() + [float(r["tmax"])])
+        out[f"{tag}_params"] = np.array([W, H, frame, samples], np.int32)
+        out[f"{tag}_pixels"] = np.array(pixels, np.int32)
+        out[f"{tag}_shadow"] = np.array(bytes_, np.uint8)
+        out[f"{tag}_rays"] = np.array(ray_rows, np.float32)
+        print(tag, "pixels", len(pixels), "rays", len(ray_rows), "interpreted instructions", it.steps)
+    np.savez_compressed(os.path.join(OUT, "spirv_shadow.npz"), **out)
+    o.close(); sc.close()
+
+GENERATORS = {"functions": gen_functions, "shadow": gen_shadow}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(GENERATORS)
