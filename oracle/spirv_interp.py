@@ -693,6 +693,12 @@ class Interpreter:
         if inst == 32:
             with np.errstate(divide="ignore", invalid="ignore"):
                 return np.divide(F32(1), np.sqrt(a[0]), dtype=F32)
+        if inst == 33:      # Determinant
+            return F32(np.linalg.det(np.array([c.astype(np.float64) for c in a[0]]).T))
+        if inst == 34:      # MatrixInverse: float64, rounded once (precision is implementation-defined)
+            M = np.array([c.astype(np.float64) for c in a[0]]).T
+            inv = np.linalg.inv(M)
+            return [inv[:, k].astype(F32) for k in range(inv.shape[1])]
         if inst == 37:
             return np.where(a[1] < a[0], a[1], a[0]).astype(F32) if isinstance(a[0], np.ndarray) else (a[1] if a[1] < a[0] else a[0])
         if inst == 40:

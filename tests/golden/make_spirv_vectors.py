@@ -204,7 +204,107 @@ def gen_shadow():
     np.savez_compressed(os.path.join(OUT, "spirv_shadow.npz"), **out)
     o.close(); sc.close()
 
-GENERATORS = {"functions": gen_functions, "shadow": gen_shadow}
+
+# ------------------------------------------------------------------------------------------------------- a6-a8: hybridRaygen.rgen + hybridHit.rchit + miss.rmiss
+def unorm_image(a_u8, repeat=True):
+    return Image2D(np.asarray(a_u8, np.uint8).astype(F32) / F32(255), repeat=repeat)
+
+
+def hybrid_gbuffer_images(g):
+    """gbuffers[0..5] of the hybrid descriptor set: position, normal, albedo, motion, material, emissive (renderer.cpp:2932-2958)."""
+    h, w = g.position.shape[:2]
+    motion = np.zeros((h, w, 4), F32); motion[..., :2] = g.motion.astype(F32); motion[..., 3] = 1
+    return [Image2D(g.position.astype(F32)), Image2D(g.normal.astype(F32)), unorm_image(g.albedo), Image2D(motion), unorm_image(g.material), unorm_image(g.emissive)]
+
+
+class HybridPipeline:
+    """traceRayEXT of hybridRaygen.rgen: closest hit by the oracle on the ray the shader built, then hybridHit.rchit.spv or
+    miss.rmiss.spv main() on the caller's payload; hybridHit's own shadow rays go through ShadowPipeline."""
+
+    def __init__(self, sc, oracle, T):
+        self.o, self.T, self.sc = oracle, T, sc
+        self.shadow = ShadowPipeline(oracle, T)
+        verts, inds = {}, {}
+        for mid, (v, ix) in enumerate(sc.meshes):
+            # rtVertexAttribute: normal.xyz1, color.xyz1, uv.xy11 (renderer.cpp:3027-3029)
+            verts[mid] = [[[vec(n[0], n[1], n[2], 1), vec(c[0], c[1], c[2], 1), vec(u[0], u[1], 1, 1)] for n, c, u in zip(v["normal"], v["color"], v["uv"])]]
+            inds[mid] = [[I32(int(k)) for k in ix]]
+        inst = sc.instances
+        env = [unorm_image(sc.textures[sc.sky_tex]), unorm_image(sc.textures[sc.irradiance_tex])]
+        res = {"Lights": lights_block(sc), "MaterialBuffer": materials_block(sc),
+               "vertices": [verts[int(i["mesh_id"])] for i in inst], "indices": [inds[int(i["mesh_id"])] for i in inst],
+               "textures": [unorm_image(t) for t in sc.textures], "environmentTexture": env,
+               "sceneBuffer": [[vec(k, int(i["material_id"]), k, int(i["first_index"])) for k, i in enumerate(inst)]],
+               "Matrices": [[mat4_cols(i["model"]) for i in inst]]}
+        self.hit = Interpreter(module("hybridHit.rchit"), res, trace_ray=self.shadow)
+        self.miss = Interpreter(module("miss.rmiss"), {"skybox": env})
+        self.hit_prd = self.hit.m.global_by_name("prd"); self.miss_prd = self.miss.m.global_by_name("prd")
+        self.hb = self.hit.m.builtin_globals(); self.mb = self.miss.m.builtin_globals()
+        self.hit_attr = self.hit.m.global_by_name("attribs")
+        self.rays, self.hits = [], []
+
+    def __call__(self, interp, flags, cull, sbt_offset, sbt_stride, miss_index, origin, tmin, direction, tmax, payload):
+        assert flags == 0x01 and cull == 0xFF and miss_index == 0 and not payload.path
+        ray = np.zeros(1, self.T.ray_dtype)
+        ray["origin"] = origin; ray["dir"] = direction; ray["tmin"] = tmin; ray["tmax"] = tmax
+        h = self.o.trace_rays(ray, any_hit=False)[0]
+        self.rays.append(ray[0].copy()); self.hits.append((int(h["instance"]), int(h["primitive"]), float(h["t"])))
+        if h["instance"] < 0:
+            self.miss.cells[self.miss_prd] = payload.cell
+            self.miss.cells[self.mb["WorldRayDirectionKHR"]][0] = np.asarray(direction, F32).copy()
+            self.miss.run_entry()
+            return
+        it = self.hit
+        it.cells[self.hit_prd] = payload.cell
+        it.cells[self.hit_attr][0] = vec(h["u"], h["v"], 0)
+        it.cells[self.hb["InstanceCustomIndexKHR"]][0] = I32(int(h["instance"]))
+        it.cells[self.hb["PrimitiveId"]][0] = I32(int(h["primitive"]))
+        it.cells[self.hb["WorldRayOriginKHR"]][0] = np.asarray(origin, F32).copy()
+        it.cells[self.hb["WorldRayDirectionKHR"]][0] = np.asarray(direction, F32).copy()
+        it.cells[self.hb["RayTmaxKHR"]][0] = F32(h["t"])          # gl_HitTEXT is RayTmaxKHR in a hit shader
+        it.run_entry()
+
+
+def gen_resolve():
+    vk, sc, o, W, H = golden_scene()
+    from vulkanhybridraytracer_b200 import types as T
+    cam = sc.camera(W, H)
+    out = {}
+    frame = 0
+    p = vk.make_params(W, H, frame=frame)
+    fr = o.hybrid_frame(cam, p)
+    g, den = fr["g"], fr["denoised"]
+    pipe = HybridPipeline(sc, o, T)
+    image = Image2D(np.zeros((H, W, 4), F32))          # the float value BEFORE the store into the B8G8R8A8 target (App. A #7)
+    env = [unorm_image(sc.textures[sc.sky_tex]), unorm_image(sc.textures[sc.irradiance_tex])]
+    shadow_imgs = []
+    for l in range(len(sc.lights)):
+        a = np.zeros((H, W, 4), F32); a[..., 0] = den[l].astype(F32) / F32(255); a[..., 3] = 1
+        shadow_imgs.append(Image2D(a))
+    res = {"cam": [mat4_cols(cam.inv_view), mat4_cols(cam.inv_proj), vec(frame, 0, 0, 0)], "gbuffers": hybrid_gbuffer_images(g), "Lights": lights_block(sc),
+           "MaterialBuffer": materials_block(sc), "environmentTexture": env, "shadowImage": shadow_imgs, "image": image,
+           "LaunchSizeKHR": np.array([W, H, 1], U32)}
+    it = Interpreter(module("hybridRaygen.rgen"), res, trace_ray=pipe)
+    launch = it.m.builtin_globals()["LaunchIdKHR"]
+    pixels, colors, n_rays, chain = [], [], [], []
+    for y in range(H):
+        for x in range(W):
+            it.cells[launch][0] = np.array([x, y, 0], U32)
+            n0 = len(pipe.rays); s0 = len(pipe.shadow.rays)
+            it.run_entry()
+            pixels.append((x, y)); colors.append(image.a[y, x].copy())
+            n_rays.append((len(pipe.rays) - n0, len(pipe.shadow.rays) - s0))
+            for k in range(n0, len(pipe.rays)):
+                chain.append([x, y, k - n0, pipe.hits[k][0], pipe.hits[k][1]])
+    out["params"] = np.array([W, H, frame], np.int32)
+    out["pixels"] = np.array(pixels, np.int32); out["final"] = np.array(colors, np.float32); out["ray_counts"] = np.array(n_rays, np.int32)
+    out["chain_hits"] = np.array(chain, np.int32).reshape(-1, 5)
+    np.savez_compressed(os.path.join(OUT, "spirv_resolve.npz"), **out)
+    print("resolve: pixels", len(pixels), "reflection rays", len(pipe.rays), "secondary shadow rays", len(pipe.shadow.rays),
+          "instructions", it.steps + pipe.hit.steps + pipe.miss.steps)
+    o.close(); sc.close()
+
+GENERATORS = {"functions": gen_functions, "shadow": gen_shadow, "resolve": gen_resolve}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(GENERATORS)

@@ -144,3 +144,34 @@ def test_shadow_pass_is_shadowraygen_spv(L, golden_setup, tag):
         assert best <= 3e-6, (x, y, best)
         n_checked += 1
     assert n_checked >= 100
+
+
+def test_resolve_pass_is_hybridraygen_hybridhit_miss_spv(golden_setup):
+    """SURVEY 8a-6 / 7 / 8.  hybridRaygen.rgen.spv main() was executed for every pixel of the golden frame; each traceRayEXT ran
+    hybridHit.rchit.spv or miss.rmiss.spv main() in the same interpreter on the oracle's closest hit, and hybridHit's shadow rays
+    went through the oracle's any-hit query + shadow.rmiss.spv.  Inputs are the oracle's own G-buffer and filtered shadow planes,
+    so what is compared is exactly the deferred lighting resolve and the reflection / refraction chain.
+    Tolerance: the binaries were evaluated with float64-then-rounded pow / atan / asin / inverse(), the oracle with the
+    numerics contract: 2e-5 relative (+ 2e-6 absolute) per channel.  A chain whose bounce lands on another triangle because
+    the two directions differ in the last bits would differ by more; none does at this size, one pixel in 500 is allowed."""
+    vk, sc, o = golden_setup
+    z = vectors("resolve")
+    W, H, frame = [int(v) for v in z["params"]]
+    p = vk.make_params(W, H, frame=frame)
+    cam = sc.camera(W, H)
+    o.reset_counters()
+    fr = o.hybrid_frame(cam, p)
+    px = z["pixels"]
+    got = fr["final"][px[:, 1], px[:, 0], :3]
+    want = z["final"][:, :3]
+    err = np.abs(got - want)
+    ok = (err <= 2e-5 * np.abs(want) + 2e-6).all(1)
+    assert ok.mean() >= 0.998, (ok.mean(), px[~ok][:5], got[~ok][:5], want[~ok][:5])
+    assert err.mean() <= 1e-5 and np.isfinite(want).all()
+    # the binaries traced exactly as many rays as the oracle counts: reflection / refraction rays and secondary shadow rays
+    assert int(z["ray_counts"][:, 0].sum()) == o.counters.rays[2] and int(z["ray_counts"][:, 1].sum()) == o.counters.rays[3]
+    # every kind of pixel is in the frame: sky (albedo passthrough), diffuse, mirror and glass chains of several bounces
+    ids = fr["g"].hit_ids[..., 0]
+    assert (ids < 0).any() and z["ray_counts"][:, 0].max() >= 3 and (z["ray_counts"][:, 0] == 0).sum() > 1000
+    modes = sc.materials["shadingMetallicRoughness"][:, 0][sc.instances["material_id"][np.maximum(ids, 0)]]
+    assert {0.0, 3.0, 4.0} <= set(np.unique(modes[ids >= 0]).tolist())
