@@ -84,8 +84,9 @@ typedef struct vkp_params {
                                         2 = compacted chain kernel on a second stream, overlapping shadow + denoise  */
     int32_t fuse_denoise;            /* vkp_render (Hybrid): run blur.comp inside the resolve kernel instead of as its own pass */
     int32_t reproject_fix;           /* blur.comp:52-53 on a reset frame.  0 (default): the reference's history fetch, pixel + motion.x * (W, H)
-                                        (wrong sign and scale, x component used for both axes).
-                                        1: the previous frame's pixel, floor(pixel + 0.5 - 0.5 * motion * (W, H))                */
+                                        (twice the right distance, x component used for both axes).
+                                        1: the previous frame's pixel, floor(pixel + 0.5 + 0.5 * motion * (W, H)); the stored motion is
+                                        previous - current NDC position (basic.vert / geometry_shader.frag cross the two varyings)      */
     int32_t shadow_tail_budget;      /* k_shadow, one-sample frames: child-pair fetches a thread spends on a shadow ray before it hands the
                                         ray to the warp-cooperative tail kernel.  0 = the context default
                                         (VKP_SHADOW_TAIL in the environment, else built in), < 0 = off.  Changes the schedule, never a bit. */

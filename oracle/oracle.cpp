@@ -690,12 +690,15 @@ void orc_gbuffer_pass(const orc_scene* sp, const vkp_camera* cam, const vkp_para
             g->albedo[4 * px + 0] = to_unorm8(color.x); g->albedo[4 * px + 1] = to_unorm8(color.y); g->albedo[4 * px + 2] = to_unorm8(color.z); g->albedo[4 * px + 3] = 255;
             g->material[4 * px + 0] = to_unorm8(material.x); g->material[4 * px + 1] = to_unorm8(material.y); g->material[4 * px + 2] = to_unorm8(material.z); g->material[4 * px + 3] = 255;
             g->emissive[4 * px + 0] = to_unorm8(emissive.x); g->emissive[4 * px + 1] = to_unorm8(emissive.y); g->emissive[4 * px + 2] = to_unorm8(emissive.z); g->emissive[4 * px + 3] = 255;
-            /* geometry_shader.frag:73-76 motion = ndc.xy - ndcPrev.xy, stored *0.5+0.5 in RG16F */
+            /* geometry_shader.frag:73-76 motion = ndc.xy - ndcPrev.xy, stored *0.5+0.5 in RG16F -- where the fragment shader's
+             * `inNdc` (location 4) is what basic.vert:47 wrote as `ndcPrev` (location 4) and `inNdcPrev` (location 5) is the
+             * vertex shader's `ndc` (location 5, basic.vert:46): the names are crossed over, the stored vector is
+             * previous - current.  Found by executing basic.vert.spv + geometry_shader.frag.spv (make_spirv_vectors.py). */
             vec4 wp; wp.x = worldPos.x; wp.y = worldPos.y; wp.z = worldPos.z; wp.w = 1.0f;
             vec4 clip = mul_vec4(cam->proj, mul_vec4(cam->view, wp));
             vec4 clipPrev = mul_vec4(cam->prev_proj, mul_vec4(cam->prev_view, wp));
-            float mx = clip.x / clip.w - clipPrev.x / clipPrev.w;
-            float my = clip.y / clip.w - clipPrev.y / clipPrev.w;
+            float mx = clipPrev.x / clipPrev.w - clip.x / clip.w;
+            float my = clipPrev.y / clipPrev.w - clip.y / clip.w;
             g->motion[2 * px + 0] = to_half(mx * 0.5f + 0.5f); g->motion[2 * px + 1] = to_half(my * 0.5f + 0.5f);
         }
     }
@@ -798,11 +801,11 @@ void orc_denoise_pass(const vkp_params* p, int n_lights, const orc_gbuffer* g, c
                      * component too (App. A #12) */
                     float lastx = (float)x + rx * (float)W, lasty = (float)y + rx * (float)H;
                     if (p->reproject_fix) {
-                        /* vkp_params.reproject_fix: motion = ndc - ndcPrev (geometry_shader.frag:73-76), ndc spans 2 over
-                         * the screen: the pixel this surface point covered last frame */
+                        /* vkp_params.reproject_fix: motion = previous - current NDC position (see orc_gbuffer_pass), NDC spans
+                         * 2 over the screen: the pixel this surface point covered last frame */
                         float ry = from_half(g->motion[2 * px + 1]) * 2.0f - 1.0f;
-                        lastx = floorf(((float)x + 0.5f) - (rx * 0.5f) * (float)W);
-                        lasty = floorf(((float)y + 0.5f) - (ry * 0.5f) * (float)H);
+                        lastx = floorf(((float)x + 0.5f) + (rx * 0.5f) * (float)W);
+                        lasty = floorf(((float)y + 0.5f) + (ry * 0.5f) * (float)H);
                     }
                     float center = in_at(l, x, y);
                     float minColor = center, maxColor = center;

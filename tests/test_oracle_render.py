@@ -232,8 +232,8 @@ def test_gltf_viewer_scene_renders_through_the_oracle(tmp_path):
 
 
 def test_reproject_fix_fetches_the_previous_frames_pixel(small_scene, small_oracle):
-    """vkp_params.reproject_fix.  blur.comp:52-53 fetches the history at pixel + motion.x * (W, H) -- wrong sign
-    and scale, x for both axes; the flag fetches floor(pixel + 0.5 - 0.5 * motion * (W, H)) instead.  After a camera move the
+    """vkp_params.reproject_fix.  blur.comp:52-53 fetches the history at pixel + motion.x * (W, H) -- twice the
+    right distance, x for both axes; the flag fetches floor(pixel + 0.5 + 0.5 * motion * (W, H)) instead (motion = previous - current).  After a camera move the
     re-projected history must (a) be the value the same surface point had in the previous frame and (b) bring the reset
     frame closer to the converged shadow than the reference's fetch does.  Default (0) stays the reference's behaviour."""
     sc = vk.HostScene(0, detail=(4, 3, 4, 6))
@@ -257,8 +257,8 @@ def test_reproject_fix_fetches_the_previous_frames_pixel(small_scene, small_orac
     # (a) re-projection lands on the same surface: previous-frame instance id at the fetched pixel == current id
     mo = g.motion.astype(np.float32) * 2 - 1
     ys, xs = np.mgrid[0:h, 0:w]
-    lx = np.floor((xs + np.float32(0.5)) - (mo[..., 0] * np.float32(0.5)) * np.float32(w)).astype(int)
-    ly = np.floor((ys + np.float32(0.5)) - (mo[..., 1] * np.float32(0.5)) * np.float32(h)).astype(int)
+    lx = np.floor((xs + np.float32(0.5)) + (mo[..., 0] * np.float32(0.5)) * np.float32(w)).astype(int)
+    ly = np.floor((ys + np.float32(0.5)) + (mo[..., 1] * np.float32(0.5)) * np.float32(h)).astype(int)
     inside = (lx >= 0) & (ly >= 0) & (lx < w) & (ly < h) & (g.hit_ids[..., 0] >= 0)
     same = fr0["g"].hit_ids[ly[inside], lx[inside], 0] == g.hit_ids[..., 0][inside]
     assert inside.mean() > 0.3 and same.mean() > 0.97

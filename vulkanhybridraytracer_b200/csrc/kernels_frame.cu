@@ -408,8 +408,11 @@ __global__ void __launch_bounds__(128, VKP_LB_GBUFFER) k_gbuffer(const __grid_co
                 float4 wp = make_float4(worldPos.x, worldPos.y, worldPos.z, 1.0f);
                 float4 clip = xform_vec4(F.cam.proj, xform_vec4(F.cam.view, wp));
                 float4 clipPrev = xform_vec4(F.cam.prev_proj, xform_vec4(F.cam.prev_view, wp));
-                float mx = clip.x / clip.w - clipPrev.x / clipPrev.w;
-                float my = clip.y / clip.w - clipPrev.y / clipPrev.w;
+                // basic.vert writes `ndc` to location 5 and `ndcPrev` to location 4, geometry_shader.frag reads location 4 as inNdc and
+                // location 5 as inNdcPrev: what the fragment shader calls ndc is the PREVIOUS frame's clip position, so the stored
+                // motion is previous - current (seen by executing the two binaries, tests/golden/make_spirv_vectors.py "gbuffer")
+                float mx = clipPrev.x / clipPrev.w - clip.x / clip.w;
+                float my = clipPrev.y / clipPrev.w - clip.y / clip.w;
                 F.motion[i] = (uint32_t)vkp_f32_to_f16(mx * 0.5f + 0.5f) | ((uint32_t)vkp_f32_to_f16(my * 0.5f + 0.5f) << 16);
             }
         }
@@ -561,10 +564,10 @@ __device__ __forceinline__ uint8_t denoise_pixel(const DFrame& F, int l, int x, 
         float rx = vkp_f16_to_f32((uint16_t)(m & 0xffffu)) * 2.0f - 1.0f;
         float lastx = (float)x + rx * (float)W, lasty = (float)y + rx * (float)H;   // blur.comp:53 (r.x twice)
         if (F.p.reproject_fix) {
-            // motion = ndc - ndcPrev (geometry_shader.frag:73-76), ndc spans 2 over the screen: where this surface point was last frame
+            // motion = previous - current position in NDC (see k_gbuffer), NDC spans 2 over the screen: where this surface point was last frame
             float ry = vkp_f16_to_f32((uint16_t)(m >> 16)) * 2.0f - 1.0f;
-            lastx = floorf(((float)x + 0.5f) - (rx * 0.5f) * (float)W);
-            lasty = floorf(((float)y + 0.5f) - (ry * 0.5f) * (float)H);
+            lastx = floorf(((float)x + 0.5f) + (rx * 0.5f) * (float)W);
+            lasty = floorf(((float)y + 0.5f) + (ry * 0.5f) * (float)H);
         }
         float center = unit255(in[i]);
         float minColor = center, maxColor = center;
