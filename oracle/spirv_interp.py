@@ -756,9 +756,11 @@ class Image2D:
     """storage image / sampled texture over a float32 H x W x 4 array.  NEAREST filtering; out-of-range imageLoad gives 0,
     out-of-range imageStore is dropped (robust buffer access); texture() wraps with REPEAT unless clamp=True."""
 
-    def __init__(self, array, unorm8=False, repeat=True, f16=False):
+    def __init__(self, array, unorm8=False, repeat=True, f16=False, corner_eps=0.0, write_to=None):
         self.a = np.asarray(array, dtype=F32).copy()
         self.unorm8, self.repeat, self.f16 = unorm8, repeat, f16
+        self.corner_eps = corner_eps      # texture() exactly on a texel corner (uv = x / W) is implementation-defined: > 0 snaps up
+        self.out = write_to               # imageStore target when reads must keep seeing the previous contents (ping-pong)
         self.reads, self.writes = [], []
 
     def read(self, coord):
@@ -780,13 +782,13 @@ class Image2D:
             t = (np.rint(np.clip(t, 0, 1) * F32(255)) / F32(255)).astype(F32)
         if self.f16:
             t = t.astype(np.float16).astype(F32)
-        self.a[y, x] = t
+        (self.a if self.out is None else self.out)[y, x] = t
 
     def sample(self, uv):
         h, w = self.a.shape[:2]
         fx, fy = F32(uv[0]) * F32(w), F32(uv[1]) * F32(h)
-        ix = int(math.floor(float(fx))) if fx == fx else 0
-        iy = int(math.floor(float(fy))) if fy == fy else 0
+        ix = int(math.floor(float(fx) + self.corner_eps)) if fx == fx else 0
+        iy = int(math.floor(float(fy) + self.corner_eps)) if fy == fy else 0
         if self.repeat:
             ix %= w
             iy %= h

@@ -304,7 +304,90 @@ def gen_resolve():
           "instructions", it.steps + pipe.hit.steps + pipe.miss.steps)
     o.close(); sc.close()
 
-GENERATORS = {"functions": gen_functions, "shadow": gen_shadow, "resolve": gen_resolve}
+
+# ------------------------------------------------------------------------------------------------------- a12: deferred.frag
+def io_by_location(m, storage):
+    """{location: global id} of the Input (1) or Output (3) interface variables."""
+    return {m.decor[g][30][0]: g for g, (t, st, _i) in m.globals.items() if st == storage and 30 in m.decor.get(g, {})}
+
+
+def gen_deferred():
+    vk, sc, o, W, H = golden_scene()
+    cam = sc.camera(W, H)
+    g = o.gbuffer(cam, vk.make_params(W, H))
+    imgs = hybrid_gbuffer_images(g)
+    m = module("deferred.frag")
+    out = {"params": np.array([W, H], np.int32)}
+    for target in range(7):
+        res = {"positionTexture": imgs[0], "normalTexture": imgs[1], "albedoTexture": imgs[2], "motionTexture": imgs[3], "materialTexture": imgs[4],
+               "emissiveTexture": imgs[5], "environmentTexture": unorm_image(sc.textures[sc.irradiance_tex]), "LightBuffer": lights_block(sc),
+               "debugInfo": [I32(target)]}
+        it = Interpreter(m, res)
+        ins, outs = io_by_location(m, 1), io_by_location(m, 3)
+        step = 1 if target == 0 else 5
+        pixels, colors = [], []
+        for y in range(0, H, step):
+            for x in range(0, W, step):
+                it.cells[ins[0]][0] = vec((x + 0.5) / W, (y + 0.5) / H)            # quad.vert: the full-screen triangle's uv at the pixel centre
+                it.cells[ins[1]][0] = vec(*cam.position[:3])
+                it.run_entry()
+                pixels.append((x, y)); colors.append(it.cells[outs[0]][0].copy())
+        out[f"t{target}_pixels"] = np.array(pixels, np.int32); out[f"t{target}_color"] = np.array(colors, np.float32)
+        print("deferred target", target, "pixels", len(pixels))
+    np.savez_compressed(os.path.join(OUT, "spirv_deferred.npz"), **out)
+    o.close(); sc.close()
+
+
+# ------------------------------------------------------------------------------------------------------- a10: postFragment.frag
+def gen_post():
+    m = module("postFragment.frag")
+    levels = np.arange(256, dtype=np.uint8)
+    tex = np.zeros((1, 256, 4), np.uint8)
+    tex[0, :, 0] = levels; tex[0, :, 1] = levels[::-1]; tex[0, :, 2] = (levels.astype(int) * 7 + 3) % 256; tex[0, :, 3] = 255
+    it = Interpreter(m, {"finalTexture": unorm_image(tex)})
+    ins, outs = io_by_location(m, 1), io_by_location(m, 3)
+    res = []
+    for k in range(256):
+        it.cells[ins[0]][0] = vec((k + 0.5) / 256, 0.5)
+        it.run_entry()
+        res.append(it.cells[outs[0]][0].copy())
+    np.savez_compressed(os.path.join(OUT, "spirv_post.npz"), texels=tex, frag_color=np.array(res, np.float32))
+    print("post: 256 texels")
+
+
+# ------------------------------------------------------------------------------------------------------- a5: blur.comp
+def gen_blur():
+    """blur.comp.spv at its compiled-in size (WIDTH 1700, HEIGHT 900, NLIGHTS 3) on seeded byte planes.  imageLoad / imageStore work
+    on R8_UNORM images (renderer.cpp:1538) declared rgba8 in the shader: reads give (r, 0, 0, 1).  Stores go to a second buffer so
+    that every invocation sees last frame's history, as on a GPU where the neighbours have not run yet (the oracle copies it too).
+    The motion texture is sampled exactly on texel corners (uv = x / W): which texel that returns is implementation-defined, the
+    stub snaps to texel x like the oracle's integer fetch."""
+    from util import blur_inputs
+    W, H, L, shadow, hist, motion, pix = blur_inputs()
+    pix = [(int(x), int(y)) for x, y in pix]
+    m = module("blur.comp")
+    out = {"pixels": np.array(pix, np.int32)}
+    for frame in (0, 5):
+        def rgba(plane):
+            a = np.zeros((H, W, 4), F32); a[..., 0] = plane.astype(F32) / F32(255); a[..., 3] = 1
+            return a
+        inputs = [Image2D(rgba(shadow[l])) for l in range(L)]
+        outs_buf = [rgba(hist[l]) for l in range(L)]
+        outputs = [Image2D(rgba(hist[l]), unorm8=True, write_to=outs_buf[l]) for l in range(L)]
+        mo = np.zeros((H, W, 4), F32); mo[..., :2] = motion.astype(F32); mo[..., 3] = 1
+        res = {"inputImage": inputs, "outputImage": outputs, "FrameCount": [I32(frame)], "motionTexture": Image2D(mo, repeat=False, corner_eps=1e-3)}
+        it = Interpreter(m, res)
+        gid = it.m.builtin_globals()["GlobalInvocationId"]
+        vals = []
+        for (x, y) in pix:
+            it.cells[gid][0] = np.array([x, y, 0], U32)
+            it.run_entry()
+            vals.append([int(np.rint(outs_buf[l][y, x, 0] * 255)) for l in range(L)])
+        out[f"f{frame}_denoised"] = np.array(vals, np.uint8)
+        print("blur frame", frame, "pixels", len(pix), "instructions", it.steps)
+    np.savez_compressed(os.path.join(OUT, "spirv_blur.npz"), **out)
+
+GENERATORS = {"functions": gen_functions, "shadow": gen_shadow, "resolve": gen_resolve, "deferred": gen_deferred, "post": gen_post, "blur": gen_blur}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(GENERATORS)

@@ -175,3 +175,64 @@ def test_resolve_pass_is_hybridraygen_hybridhit_miss_spv(golden_setup):
     assert (ids < 0).any() and z["ray_counts"][:, 0].max() >= 3 and (z["ray_counts"][:, 0] == 0).sum() > 1000
     modes = sc.materials["shadingMetallicRoughness"][:, 0][sc.instances["material_id"][np.maximum(ids, 0)]]
     assert {0.0, 3.0, 4.0} <= set(np.unique(modes[ids >= 0]).tolist())
+
+
+@pytest.mark.parametrize("frame", [0, 5])
+def test_denoise_pass_is_blur_comp_spv(frame):
+    """SURVEY 8a-5.  blur.comp.spv main() at its compiled-in 1700 x 900 x 3 lights for 269 invocations (corners, borders, random),
+    a reset frame (3x3 clamp + history fetch at pixel + motion.x * (W, H), out-of-range reads = 0) and an accumulation frame
+    (mix(old, new, 1 / (frame + 1))).  The oracle's filter must store the same R8 value; a mix() landing within float rounding of
+    x.5 / 255 may round the other way (the oracle evaluates the same expression: none seen)."""
+    import vulkanhybridraytracer_b200 as vk
+    from oracle.oracle_py import GBuffer, Oracle
+    from util import blur_inputs
+    W, H, Lc, shadow, hist, motion, pix = blur_inputs()
+    z = vectors("blur")
+    assert np.array_equal(z["pixels"], pix)
+    sc = vk.HostScene(0, detail=(2, 2, 2, 2))                # the default scene has three lights: the filter only needs the count
+    o = Oracle(sc)
+    assert o.n_lights == Lc
+    g = GBuffer(W, H); g.motion[...] = motion
+    p = vk.make_params(W, H, frame=frame, denoise_frame=frame, denoise_cover_remainder=1)
+    den = o.denoise(p, g, np.ascontiguousarray(shadow), np.ascontiguousarray(hist))
+    got = np.stack([den[l][pix[:, 1], pix[:, 0]] for l in range(Lc)], 1)
+    want = z[f"f{frame}_denoised"]
+    assert np.abs(got.astype(int) - want.astype(int)).max() <= 1 and (got == want).mean() >= 0.995, (got != want).sum()
+    assert len(np.unique(want)) > 10
+    o.close(); sc.close()
+
+
+def test_post_pass_is_postfragment_spv(L):
+    """SURVEY 8a-10.  postFragment.frag.spv main() on all 256 possible 8-bit inputs per channel: max(rgb, 0.001) ^ (1 / 2.2), alpha
+    passed through.  The oracle's post pass stores unorm8 of the same: equal bytes, +-1 where pow() lands within an ulp of a
+    rounding boundary."""
+    import vulkanhybridraytracer_b200 as vk
+    from oracle.oracle_py import Oracle
+    z = vectors("post")
+    tex = z["texels"][0]                                       # 256 x RGBA8
+    want = np.rint(np.clip(z["frag_color"], 0, 1) * 255).astype(int)
+    # the oracle's post pass takes the float frame: feed it the texel values so that its own 8-bit store reproduces them
+    final = (tex.astype(np.float32) / np.float32(255)).reshape(1, 256, 4)
+    sc = vk.HostScene(1, detail=(2, 2, 2, 2)); o = Oracle(sc)
+    got = o.post(vk.make_params(256, 1), np.ascontiguousarray(final)).reshape(256, 4).astype(int)
+    o.close(); sc.close()
+    assert np.abs(got - want).max() <= 1 and (got == want).mean() >= 0.99, np.argwhere(got != want)[:5]
+    assert (got[:, 3] == 255).all() and got[0, 0] == want[0, 0] > 0          # the 0.001 floor: black does not stay 0
+
+
+@pytest.mark.parametrize("target", range(7))
+def test_deferred_pass_is_deferred_frag_spv(golden_setup, target):
+    """SURVEY 8a-12.  deferred.frag.spv main() on the oracle's G-buffer: the full shading path (target 0, every pixel) and the six
+    debug views (deferred.frag:50-73).  2e-5 relative + 2e-6 absolute, as for the resolve pass."""
+    vk, sc, o = golden_setup
+    z = vectors("deferred")
+    W, H = [int(v) for v in z["params"]]
+    cam = sc.camera(W, H)
+    g = o.gbuffer(cam, vk.make_params(W, H))
+    d = o.deferred(cam, vk.make_params(W, H, mode=vk.MODE_DEFERRED, debug_target=target), g)
+    px = z[f"t{target}_pixels"]; want = z[f"t{target}_color"]
+    got = d[px[:, 1], px[:, 0]]
+    nch = 4
+    err = np.abs(got[:, :nch] - want[:, :nch])
+    ok = (err <= 2e-5 * np.abs(want[:, :nch]) + 2e-6).all(1)
+    assert ok.mean() >= 0.998, (target, ok.mean(), px[~ok][:5], got[~ok][:5], want[~ok][:5])

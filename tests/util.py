@@ -165,3 +165,22 @@ def make_test_glb(path, seed=0):
     with open(path, "wb") as f:
         f.write(struct.pack("<III", 0x46546C67, 2, 12 + len(body)) + body)
     return {"triangles": (len(upper) + len(lower) + 6) // 3, "textures": [base, normal, emissive, mr]}
+
+
+def blur_inputs():
+    """Seeded inputs of the blur.comp vectors (shared by tests/golden/make_spirv_vectors.py and tests/test_oracle_spirv.py): byte planes
+    at the shader's compiled-in 1700 x 900 x 3 lights, a motion plane with static, shifted, noisy and sky (0 -> decoded -1) bands,
+    and the invocations that were executed."""
+    W, H, L = 1700, 900, 3
+    rng = np.random.default_rng(77)
+    shadow = rng.choice(np.array([0, 255, 255, 255, 64, 191], np.uint8), size=(L, H, W))
+    hist = rng.integers(0, 256, size=(L, H, W), dtype=np.uint8)
+    motion = np.full((H, W, 2), 0.5, np.float16)
+    ys, xs = np.mgrid[0:H, 0:W]
+    band = (ys // 60) % 3
+    motion[band == 1] = np.float16(0.5 + 3.0 / W)
+    motion[band == 2, 0] = (0.5 + rng.uniform(-0.02, 0.02, size=int((band == 2).sum()))).astype(np.float16)
+    motion[:40] = 0
+    pix = [(0, 0), (W - 1, 0), (0, H - 1), (W - 1, H - 1), (1, 1), (W // 2, 0), (0, H // 2), (W - 1, H // 2), (W // 2, H - 1)]
+    pix += [(int(x), int(y)) for x, y in zip(rng.integers(0, W, 260), rng.integers(0, H, 260))]
+    return W, H, L, shadow, hist, motion, np.array(pix, np.int32)
