@@ -387,7 +387,89 @@ def gen_blur():
         print("blur frame", frame, "pixels", len(pix), "instructions", it.steps)
     np.savez_compressed(os.path.join(OUT, "spirv_blur.npz"), **out)
 
-GENERATORS = {"functions": gen_functions, "shadow": gen_shadow, "resolve": gen_resolve, "deferred": gen_deferred, "post": gen_post, "blur": gen_blur}
+
+# ------------------------------------------------------------------------------------------------------- a3: basic.vert + geometry_shader.frag
+def camera_ray(cam, x, y, W, H):
+    """raygen.rgen:32-40 in float32 (the oracle's primary ray: DESIGN.md section 2, "G-buffer by ray casting")."""
+    u, v = F32(F32(x) + F32(0.5)) / F32(W), F32(F32(y) + F32(0.5)) / F32(H)
+    d = vec(u * F32(2) - F32(1), v * F32(2) - F32(1), 1, 1)
+    ip, iv = mat4_cols(cam.inv_proj), mat4_cols(cam.inv_view)
+    t = ip[0] * d[0] + ip[1] * d[1] + ip[2] * d[2] + ip[3] * d[3]
+    tn = t[:3] / np.sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2])
+    dirv = (iv[0] * tn[0] + iv[1] * tn[1] + iv[2] * tn[2])[:3]
+    return iv[3][:3].copy(), dirv.astype(F32)
+
+
+def gen_gbuffer():
+    """The raster G-buffer pass, per covered pixel: basic.vert.spv main() on the three vertices of the triangle the oracle's primary
+    ray hits, varyings interpolated with the hit's barycentrics (what the rasteriser's perspective-correct interpolation gives at
+    that point) and handed over BY LOCATION to geometry_shader.frag.spv main().  dFdx / dFdy of the world position -- only used by
+    the normal-mapped material -- are supplied as the oracle defines them (neighbour camera rays on the triangle's plane)."""
+    vk, sc, o, W, H = golden_scene()
+    from vulkanhybridraytracer_b200 import types as T
+    cam0 = sc.camera(W, H)
+    sc.move_camera(3, 6.0); sc.rotate_camera(12.0, 4.0)
+    cam = sc.camera(W, H, prev=cam0)                      # a moving camera: motion vectors are not zero
+    p = vk.make_params(W, H)
+    g = o.gbuffer(cam, p)
+    vm, fm = module("basic.vert"), module("geometry_shader.frag")
+    cam_block = [mat4_cols(cam.view), mat4_cols(cam.proj), mat4_cols(cam.prev_view), mat4_cols(cam.prev_proj)]
+    vs = Interpreter(vm, {"CameraBuffer": cam_block})
+    v_in, v_out = io_by_location(vm, 1), io_by_location(vm, 3)
+    v_push = vm.global_by_name("pushC")
+    deriv = {}
+    fs = Interpreter(fm, {"textures": [unorm_image(t) for t in sc.textures]}, derivative=lambda rid, axis, value: deriv["d"][axis])
+    f_in, f_out = io_by_location(fm, 1), io_by_location(fm, 3)
+    f_push = fm.global_by_name("pushC")
+    rows = {k: [] for k in ("pixels", "position", "normal", "albedo", "motion", "material", "emissive", "normal_mapped")}
+    for y in range(H):
+        for x in range(W):
+            inst, prim = [int(t) for t in g.hit_ids[y, x]]
+            if inst < 0:
+                continue
+            org, dirv = camera_ray(cam, x, y, W, H)
+            ray = np.zeros(1, T.ray_dtype); ray["origin"] = org + dirv * F32(1e-2); ray["dir"] = dirv; ray["tmin"] = 0.001; ray["tmax"] = 10000.0
+            h = o.trace_rays(ray)[0]
+            if int(h["instance"]) != inst or int(h["primitive"]) != prim:
+                continue                                  # the float32 re-derivation of the ray picked a neighbour at an edge: skip
+            I = sc.instances[inst]
+            verts, idx = sc.meshes[int(I["mesh_id"])]
+            tri = idx[int(I["first_index"]) + 3 * prim: int(I["first_index"]) + 3 * prim + 3]
+            vs.cells[v_push][0] = [mat4_cols(I["model"]), mat4_cols(I["inv_model"])]
+            outs = []
+            for k in tri:
+                vtx = verts[int(k)]
+                vs.cells[v_in[0]][0] = vec(*vtx["position"]); vs.cells[v_in[1]][0] = vec(*vtx["normal"])
+                vs.cells[v_in[2]][0] = vec(*vtx["color"]); vs.cells[v_in[3]][0] = vec(*vtx["uv"])
+                vs.run_entry()
+                outs.append({loc: vs.cells[gid][0].copy() for loc, gid in v_out.items()})
+            b = [F32(1) - F32(h["u"]) - F32(h["v"]), F32(h["u"]), F32(h["v"])]
+            for loc, gid in f_in.items():
+                fs.cells[gid][0] = outs[0][loc] * b[0] + outs[1][loc] * b[1] + outs[2][loc] * b[2]
+            mat = sc.materials[int(I["material_id"])]
+            fs.cells[f_push][0] = [vec(*mat["diffuse"]), vec(*mat["textures"]), vec(*mat["shadingMetallicRoughness"])]
+            mapped = mat["textures"][1] > -1
+            if mapped:
+                P = [outs[k][0] for k in range(3)]
+                ng = np.cross(P[1] - P[0], P[2] - P[0]).astype(F32)
+                wp = fs.cells[f_in[0]][0]
+                d = []
+                for (nx, ny) in ((x + 1, y), (x, y + 1)):
+                    o2, d2 = camera_ray(cam, nx, ny, W, H)
+                    q = o2 + d2 * (np.dot(P[0] - o2, ng) / np.dot(d2, ng))
+                    d.append((q - wp).astype(F32))
+                deriv["d"] = d
+            fs.run_entry()
+            res = {loc: fs.cells[gid][0].copy() for loc, gid in f_out.items()}
+            rows["pixels"].append((x, y)); rows["position"].append(res[0]); rows["normal"].append(res[1]); rows["albedo"].append(res[2])
+            rows["motion"].append(res[3]); rows["material"].append(res[4]); rows["emissive"].append(res[5]); rows["normal_mapped"].append(bool(mapped))
+    out = {k: np.array(v, np.int32 if k == "pixels" else (np.bool_ if k == "normal_mapped" else np.float32)) for k, v in rows.items()}
+    out["params"] = np.array([W, H], np.int32)
+    np.savez_compressed(os.path.join(OUT, "spirv_gbuffer.npz"), **out)
+    print("gbuffer: pixels", len(rows["pixels"]), "normal-mapped", int(np.sum(out["normal_mapped"])))
+    o.close(); sc.close()
+
+GENERATORS = {"gbuffer": gen_gbuffer, "functions": gen_functions, "shadow": gen_shadow, "resolve": gen_resolve, "deferred": gen_deferred, "post": gen_post, "blur": gen_blur}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(GENERATORS)

@@ -236,3 +236,60 @@ def test_deferred_pass_is_deferred_frag_spv(golden_setup, target):
     err = np.abs(got[:, :nch] - want[:, :nch])
     ok = (err <= 2e-5 * np.abs(want[:, :nch]) + 2e-6).all(1)
     assert ok.mean() >= 0.998, (target, ok.mean(), px[~ok][:5], got[~ok][:5], want[~ok][:5])
+
+
+def test_gbuffer_pass_is_basic_vert_and_geometry_frag_spv(golden_setup):
+    """SURVEY 8a-3.  basic.vert.spv main() ran on the three vertices of the triangle under each covered pixel, its outputs were
+    interpolated with the hit's barycentrics and passed BY LOCATION to geometry_shader.frag.spv main() -- with a camera that moved
+    since the previous frame, so the motion plane is exercised (and its previous - current orientation: basic.vert writes ndcPrev to
+    location 4 and ndc to 5, the fragment shader reads 4 as inNdc and 5 as inNdcPrev).  The oracle's ray-cast G-buffer must store
+    the same fp16 / unorm8 values: exact for most, +-1 ulp of the storage format where interpolate-then-transform and
+    transform-then-interpolate round differently.  Normal-mapped pixels (dFdx / dFdy from neighbour rays) get 2e-3 on the normal."""
+    import vulkanhybridraytracer_b200 as vk2
+    from oracle.oracle_py import Oracle
+    from util import GOLDEN_DETAIL
+    sc = vk2.HostScene(0, detail=GOLDEN_DETAIL)            # own scene: the camera is moved
+    o = Oracle(sc)
+    z = vectors("gbuffer")
+    W, H = [int(v) for v in z["params"]]
+    cam0 = sc.camera(W, H)
+    sc.move_camera(3, 6.0); sc.rotate_camera(12.0, 4.0)
+    cam = sc.camera(W, H, prev=cam0)
+    g = o.gbuffer(cam, vk2.make_params(W, H))
+    px = z["pixels"]; X, Y = px[:, 0], px[:, 1]
+    assert len(px) > 500
+
+    def half_ulps(got_f16, want_f32):
+        a = got_f16.view(np.int16).astype(np.int32); b = want_f32.astype(np.float16).view(np.int16).astype(np.int32)
+        a = np.where(a < 0, -(a & 0x7fff), a); b = np.where(b < 0, -(b & 0x7fff), b)
+        return np.abs(a - b)
+    pos = half_ulps(g.position[Y, X], z["position"])
+    assert pos.max() <= 1 and (pos == 0).mean() > 0.97, (pos.max(), (pos == 0).mean())
+    plain = ~z["normal_mapped"]
+    nrm = half_ulps(g.normal[Y, X], z["normal"])
+    assert nrm[plain].max() <= 1 and (nrm[plain] == 0).mean() > 0.97
+    if (~plain).any():
+        assert np.abs(g.normal[Y, X][~plain].astype(np.float32) - z["normal"][~plain]).max() <= 2e-3
+    mot = half_ulps(g.motion[Y, X], z["motion"])
+    assert mot.max() <= 1 and (mot == 0).mean() > 0.95, (mot.max(), (mot == 0).mean())
+    assert (np.abs(z["motion"] - 0.5) > 1e-3).mean() > 0.5                     # the camera did move
+    for name in ("albedo", "material", "emissive"):
+        want = np.rint(np.clip(z[name], 0, 1) * 255).astype(int)
+        got = getattr(g, name)[Y, X][:, :3].astype(int)
+        assert np.abs(got - want).max() <= 1 and (got == want).mean() > 0.995, name
+    # the sign of the stored vector: re-projecting with it must land on the same surface in the previous frame
+    g0 = o.gbuffer(cam0, vk2.make_params(W, H))
+    mo = z["motion"] * 2 - 1
+    lx = np.floor(X + 0.5 + 0.5 * mo[:, 0] * W).astype(int); ly = np.floor(Y + 0.5 + 0.5 * mo[:, 1] * H).astype(int)
+    inside = (lx >= 0) & (ly >= 0) & (lx < W) & (ly < H)
+    same = g0.hit_ids[ly[inside], lx[inside], 0] == g.hit_ids[Y[inside], X[inside], 0]
+    wrong = np.floor(X + 0.5 - 0.5 * mo[:, 0] * W).astype(int), np.floor(Y + 0.5 - 0.5 * mo[:, 1] * H).astype(int)
+    ins2 = (wrong[0] >= 0) & (wrong[1] >= 0) & (wrong[0] < W) & (wrong[1] < H)
+    same2 = g0.hit_ids[wrong[1][ins2], wrong[0][ins2], 0] == g.hit_ids[Y[ins2], X[ins2], 0]
+    # (most pixels show the floor, which is "the same surface" for either sign: the objects on it tell the two apart)
+    obj = g.hit_ids[Y, X, 0] > 0
+    same_o = g0.hit_ids[ly[inside & obj], lx[inside & obj], 0] == g.hit_ids[Y[inside & obj], X[inside & obj], 0]
+    same2_o = g0.hit_ids[wrong[1][ins2 & obj], wrong[0][ins2 & obj], 0] == g.hit_ids[Y[ins2 & obj], X[ins2 & obj], 0]
+    assert same.mean() > 0.95 and same.mean() > same2.mean() and same_o.mean() > 0.85 and same_o.mean() > same2_o.mean() + 0.1, \
+        (same.mean(), same2.mean(), same_o.mean(), same2_o.mean())
+    o.close(); sc.close()
