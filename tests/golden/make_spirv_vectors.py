@@ -221,7 +221,7 @@ class HybridPipeline:
     """traceRayEXT of hybridRaygen.rgen: closest hit by the oracle on the ray the shader built, then hybridHit.rchit.spv or
     miss.rmiss.spv main() on the caller's payload; hybridHit's own shadow rays go through ShadowPipeline."""
 
-    def __init__(self, sc, oracle, T):
+    def __init__(self, sc, oracle, T, hit_module="hybridHit.rchit", env_name="environmentTexture", extra=None):
         self.o, self.T, self.sc = oracle, T, sc
         self.shadow = ShadowPipeline(oracle, T)
         verts, inds = {}, {}
@@ -233,10 +233,11 @@ class HybridPipeline:
         env = [unorm_image(sc.textures[sc.sky_tex]), unorm_image(sc.textures[sc.irradiance_tex])]
         res = {"Lights": lights_block(sc), "MaterialBuffer": materials_block(sc),
                "vertices": [verts[int(i["mesh_id"])] for i in inst], "indices": [inds[int(i["mesh_id"])] for i in inst],
-               "textures": [unorm_image(t) for t in sc.textures], "environmentTexture": env,
+               "textures": [unorm_image(t) for t in sc.textures], env_name: env,
                "sceneBuffer": [[vec(k, int(i["material_id"]), k, int(i["first_index"])) for k, i in enumerate(inst)]],
                "Matrices": [[mat4_cols(i["model"]) for i in inst]]}
-        self.hit = Interpreter(module("hybridHit.rchit"), res, trace_ray=self.shadow)
+        res.update(extra or {})
+        self.hit = Interpreter(module(hit_module), res, trace_ray=self.shadow)
         self.miss = Interpreter(module("miss.rmiss"), {"skybox": env})
         self.hit_prd = self.hit.m.global_by_name("prd"); self.miss_prd = self.miss.m.global_by_name("prd")
         self.hb = self.hit.m.builtin_globals(); self.mb = self.miss.m.builtin_globals()
@@ -469,7 +470,38 @@ def gen_gbuffer():
     print("gbuffer: pixels", len(rows["pixels"]), "normal-mapped", int(np.sum(out["normal_mapped"])))
     o.close(); sc.close()
 
-GENERATORS = {"gbuffer": gen_gbuffer, "functions": gen_functions, "shadow": gen_shadow, "resolve": gen_resolve, "deferred": gen_deferred, "post": gen_post, "blur": gen_blur}
+
+# ------------------------------------------------------------------------------------------------------- a11: raygen.rgen + closesthit.rchit + miss.rmiss
+def gen_raytrace():
+    vk, sc, o, W, H = golden_scene()
+    from vulkanhybridraytracer_b200 import types as T
+    cam = sc.camera(W, H)
+    out = {}
+    for tag, frame, samples, step in (("f0s1", 0, 1, 1), ("f2s3", 2, 3, 3)):
+        pipe = HybridPipeline(sc, o, T, hit_module="closesthit.rchit", env_name="environment_texture",
+                              extra={"SampleBuffer": [I32(samples)], "shadowImage": [Image2D(np.zeros((1, 1, 4), F32)) for _ in sc.lights]})
+        rng = np.random.default_rng(5)
+        prev = rng.uniform(0, 1, size=(H, W, 4)).astype(F32) if frame else np.zeros((H, W, 4), F32)      # the accumulation image
+        image = Image2D(prev)
+        res = {"cam": [mat4_cols(cam.inv_view), mat4_cols(cam.inv_proj), vec(frame, 0, 0, 0)], "image": image, "LaunchSizeKHR": np.array([W, H, 1], U32)}
+        it = Interpreter(module("raygen.rgen"), res, trace_ray=pipe)
+        launch = it.m.builtin_globals()["LaunchIdKHR"]
+        pixels, colors, counts = [], [], []
+        for y in range(0, H, step):
+            for x in range(0, W, step):
+                it.cells[launch][0] = np.array([x, y, 0], U32)
+                n0, s0 = len(pipe.rays), len(pipe.shadow.rays)
+                it.run_entry()
+                pixels.append((x, y)); colors.append(image.a[y, x].copy()); counts.append((len(pipe.rays) - n0, len(pipe.shadow.rays) - s0))
+        out[f"{tag}_params"] = np.array([W, H, frame, samples], np.int32); out[f"{tag}_pixels"] = np.array(pixels, np.int32)
+        out[f"{tag}_color"] = np.array(colors, np.float32); out[f"{tag}_ray_counts"] = np.array(counts, np.int32)
+        if frame:
+            out[f"{tag}_previous"] = prev
+        print("raytrace", tag, "pixels", len(pixels), "rays", len(pipe.rays), "shadow rays", len(pipe.shadow.rays))
+    np.savez_compressed(os.path.join(OUT, "spirv_raytrace.npz"), **out)
+    o.close(); sc.close()
+
+GENERATORS = {"raytrace": gen_raytrace, "gbuffer": gen_gbuffer, "functions": gen_functions, "shadow": gen_shadow, "resolve": gen_resolve, "deferred": gen_deferred, "post": gen_post, "blur": gen_blur}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(GENERATORS)

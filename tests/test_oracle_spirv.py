@@ -293,3 +293,26 @@ def test_gbuffer_pass_is_basic_vert_and_geometry_frag_spv(golden_setup):
     assert same.mean() > 0.95 and same.mean() > same2.mean() and same_o.mean() > 0.85 and same_o.mean() > same2_o.mean() + 0.1, \
         (same.mean(), same2.mean(), same_o.mean(), same2_o.mean())
     o.close(); sc.close()
+
+
+@pytest.mark.parametrize("tag", ["f0s1", "f2s3"])
+def test_raytraced_mode_is_raygen_closesthit_miss_spv(golden_setup, tag):
+    """SURVEY 8a-11 (the Raytraced mode of BASELINE configs[2]).  raygen.rgen.spv main() per pixel -- NSAMPLES is 1 in the shipped
+    binary -- with closesthit.rchit.spv / miss.rmiss.spv on the oracle's closest hit and shadow.rmiss.spv behind the any-hit
+    shadow rays; second case: frame 2 (accumulation over a seeded previous image, a = 1 / 3) with 3 shadow samples per light.
+    Same tolerance as the resolve pass; the ray counts must agree exactly."""
+    vk, sc, o = golden_setup
+    z = vectors("raytrace")
+    W, H, frame, samples = [int(v) for v in z[f"{tag}_params"]]
+    p = vk.make_params(W, H, mode=vk.MODE_RAYTRACING, spp=1, shadow_samples=samples, frame=frame, faithful_rng=1)
+    cam = sc.camera(W, H)
+    prev = z[f"{tag}_previous"] if frame else None
+    o.reset_counters()
+    a = o.raytrace(cam, p, None if prev is None else prev.copy())
+    px = z[f"{tag}_pixels"]; want = z[f"{tag}_color"][:, :3]
+    got = a[px[:, 1], px[:, 0], :3]
+    err = np.abs(got - want)
+    ok = (err <= 2e-5 * np.abs(want) + 2e-6).all(1)
+    assert ok.mean() >= 0.998, (ok.mean(), px[~ok][:5], got[~ok][:5], want[~ok][:5])
+    if len(px) == W * H:
+        assert int(z[f"{tag}_ray_counts"][:, 0].sum()) == o.counters.rays[2] and int(z[f"{tag}_ray_counts"][:, 1].sum()) == o.counters.rays[3]
