@@ -2,8 +2,15 @@
  * oracle.cpp -- TEST INFRASTRUCTURE: scalar CPU restatement of the reference's hot path.
  *
  * NOT shipped, NOT on the product path.  Only tests/, __graft_entry__.smoke() and bench.py
- * (cpu_baseline / --impl reference) may load liboracle.so.  PARITY UNPINNED BY THE REFERENCE
- * (no tests / golden vectors upstream; BVH traversal is in the Vulkan driver) -- see oracle.h.
+ * (cpu_baseline / --impl reference) may load liboracle.so.
+ *
+ * PINNING.  The reference ships no tests or golden vectors and cannot be built or run here, but it
+ * ships its COMPILED shaders (data/shaders/output/*.spv).  oracle/spirv_interp.py executes them and
+ * tests/test_oracle_spirv.py holds every shading stage below to their outputs (committed under
+ * tests/golden/spirv_*.npz with the generating script): G-buffer, shadow ray generation, blur.comp,
+ * the resolve + hit + miss shaders, Raytraced mode, deferred.frag, postFragment.frag.  What stays
+ * UNPINNED is what the reference does not contain: BVH build, traversal and the ray-triangle test
+ * live in the Vulkan driver / RT hardware -- see the intersection contract in oracle.h.
  *
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
  * The code is deliberately plain: one pixel at a time, GLSL evaluation order, OpenMP over rows.

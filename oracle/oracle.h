@@ -3,10 +3,15 @@
  *
  * A scalar restatement of the reference's Hybrid / Raytraced / Deferred shader math
  * (data/shaders/{x}.rgen|rchit|rmiss|comp|frag, see oracle.cpp for file:line citations) over a
- * brute-force or simple binned-SAH CPU BVH.  PARITY IS UNPINNED BY THE REFERENCE: it ships no tests,
- * golden images or known-answer vectors, and its BVH traversal lives in the
- * Vulkan driver.  The pins we do have: the TEA/LCG known answers of SURVEY App. D, brute-force ==
- * BVH agreement, and the mathematical definition of nearest-hit with the tie rule below.
+ * brute-force or simple binned-SAH CPU BVH.
+ *
+ * PINNING.  The reference ships no tests, golden images or known-answer vectors
+ * and cannot be built or run here; it does ship its compiled shaders.  Every SHADING stage of this oracle is
+ * pinned against outputs of those binaries executed by oracle/spirv_interp.py (tests/golden/spirv_*.npz,
+ * tests/test_oracle_spirv.py: integer results identical, float results within 2e-5 relative, stored bytes
+ * identical).  The INTERSECTION side is unpinned by nature -- the reference's BVH build / traversal /
+ * ray-triangle test live in the Vulkan driver and RT hardware; its pins are brute-force == BVH agreement
+ * and the mathematical definition of nearest-hit with the tie rule below.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may load this.
  *
