@@ -37,14 +37,22 @@ namespace {
 
 struct Pixel { int x, y; bool valid; };
 
+// n / d for the block-index arithmetic every thread of every frame kernel starts with.  d is a launch constant the compiler cannot
+// see, so `/` and `%` were ~20-instruction sequences: 10 % of all instructions k_shadow executed (ncu source page,
+// profiles/r1o_*).  magic = floor(2^40 / d) + 1 (host, make_launch) is exact while n * d < 2^40; otherwise F.div_exact is 0.
+__device__ __forceinline__ unsigned int fast_div(const DFrame& F, unsigned int n, unsigned long long magic, unsigned int d)
+{
+    return F.div_exact ? (unsigned int)(((unsigned long long)n * magic) >> 40) : n / d;
+}
+
 __device__ __forceinline__ Pixel pixel_of_block(const DFrame& F, const unsigned int block)
 {
     const int bpt_x = F.tile_w >> 4, bpt_y = F.tile_h >> 3;
     const int bpt = bpt_x * bpt_y;
-    const int own_tile = (int)block / bpt, sub = (int)block - own_tile * bpt;
+    const int own_tile = (int)fast_div(F, block, F.magic_bpt, (unsigned int)bpt), sub = (int)block - own_tile * bpt;
     const int tile = F.rank + own_tile * F.world;
-    const int tx = tile % F.tiles_x, ty = tile / F.tiles_x;
-    const int sbx = sub % bpt_x, sby = sub / bpt_x;
+    const int ty = (int)fast_div(F, (unsigned int)tile, F.magic_tiles_x, (unsigned int)F.tiles_x), tx = tile - ty * F.tiles_x;
+    const int sby = (int)fast_div(F, (unsigned int)sub, F.magic_bpt_x, (unsigned int)bpt_x), sbx = sub - sby * bpt_x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Pixel p;
     p.x = tx * F.tile_w + sbx * 16 + (warp & 1) * 8 + (lane & 7);
@@ -109,7 +117,7 @@ __global__ void __launch_bounds__(256) k_build_order(uint32_t* __restrict__ cost
 
 __device__ __forceinline__ void add_counter(unsigned long long* counters, int slot, unsigned int n)
 {
-    for (int off = 16; off; off >>= 1) n += __shfl_xor_sync(0xffffffffu, n, off);
+    n = __reduce_add_sync(0xffffffffu, n);      // redux.sync: one instruction instead of five shuffle + add pairs
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(&counters[slot], (unsigned long long)n);
 }
 
@@ -451,7 +459,7 @@ __global__ void __launch_bounds__(128, MINB) k_shadow(const __grid_constant__ DS
 {
     const long long t_start = clock64();
     const unsigned int vb = virtual_block(F.cta_order[1]);      // = light * n_cta + pixel block
-    const int l = (int)(vb / (unsigned int)F.n_cta);
+    const int l = (int)fast_div(F, vb, F.magic_n_cta, (unsigned int)F.n_cta);
     const Pixel px = pixel_of_block(F, vb - (unsigned int)l * (unsigned int)F.n_cta);
     unsigned int nrays = 0;
     TravCount tc = {0u, 0u, 0u};

@@ -368,6 +368,18 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     const int total = F.tiles_x * F.tiles_y;
     L.n_own_tiles = total > F.rank ? (total - F.rank + F.world - 1) / F.world : 0;
     F.n_cta = L.n_own_tiles * (F.tile_w >> 4) * (F.tile_h >> 3);
+    {
+        // magic numbers of fast_div: q = (n * (floor(2^40 / d) + 1)) >> 40 equals n / d whenever n * d < 2^40
+        auto magic = [](unsigned long long d) { return ((1ull << 40) / (d ? d : 1ull)) + 1ull; };
+        const unsigned long long bpt_x = (unsigned long long)(F.tile_w >> 4), bpt = bpt_x * (unsigned long long)(F.tile_h >> 3);
+        const unsigned long long n_lights = ctx->lights.empty() ? 1ull : (unsigned long long)ctx->lights.size();
+        const unsigned long long max_block = (unsigned long long)(F.n_cta > 0 ? F.n_cta : 1) * n_lights, max_tile = (unsigned long long)total + (unsigned long long)F.world;
+        F.magic_bpt = magic(bpt); F.magic_tiles_x = magic((unsigned long long)F.tiles_x); F.magic_bpt_x = magic(bpt_x);
+        F.magic_n_cta = magic((unsigned long long)F.n_cta);
+        const unsigned long long lim = 1ull << 40;
+        F.div_exact = (max_block * bpt < lim && max_tile * (unsigned long long)F.tiles_x < lim && bpt * bpt_x < lim &&
+                       max_block * (unsigned long long)(F.n_cta > 0 ? F.n_cta : 1) < lim) ? 1 : 0;
+    }
     for (int k = 0; k < 2; k++) {
         const uint32_t n = (uint32_t)F.n_cta * (k ? (uint32_t)L.scene.n_lights : 1u);
         F.cta_cost[k] = nullptr; F.cta_order[k] = nullptr;

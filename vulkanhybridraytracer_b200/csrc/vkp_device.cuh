@@ -175,6 +175,9 @@ struct DFrame {
     const uint32_t* cta_order[2];
     uint32_t* cta_cost[2];
     int n_cta;                      // CTAs per pixel pass on this rank (k_shadow runs n_cta * n_lights of them)
+    // fast_div (kernels_frame.cu): floor(2^40 / d) + 1 for the four divisors of the block-index arithmetic
+    unsigned long long magic_bpt, magic_tiles_x, magic_bpt_x, magic_n_cta;
+    int div_exact;                  // all four are exact for the index ranges of this launch (n * d < 2^40)
     // tail of k_shadow (one-sample shadow rays): a thread that has fetched spill_budget child pairs without an answer appends
     // its ray to spill_rec (2 x float4: origin | tmax, direction | index into `shadow`) and k_shadow_tail finishes it with one
     // warp per ray.  spill_cnt = {count, head} x 2: the pair of this frame and the pair the tail kernel clears for the next one.
