@@ -117,14 +117,6 @@ def test_image_errors_are_reported(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------------------------ JPEG
-def _idct_reference(coef):
-    """Float64 inverse DCT of dequantised 8x8 blocks (T.81 A.3.3), + 128 level shift."""
-    k = np.arange(8)
-    c = np.where(k == 0, 1 / np.sqrt(2), 1.0)
-    basis = c[None, :] * np.cos((2 * k[:, None] + 1) * k[None, :] * np.pi / 16) / 2        # [x, u]
-    return basis @ coef @ basis.T + 128
-
-
 @pytest.mark.parametrize("subsampling,progressive,grey,restart", [
     ("4:4:4", False, False, 0), ("4:2:0", False, False, 0), ("4:2:2", False, False, 0), ("4:2:0", True, False, 0),
     ("4:4:4", True, False, 0), ("4:4:4", False, True, 0), ("4:2:0", False, False, 3), ("4:2:0", True, False, 2)])
@@ -163,9 +155,9 @@ def test_jpeg_agrees_with_pillow_within_decoder_tolerance(tmp_path, subsampling,
     assert np.abs(got[..., :3] - src).mean() <= np.abs(want[..., :3] - src).mean() + 0.25
 
 
-def test_jpeg_idct_and_colour_conversion_are_the_stated_integer_pipeline(tmp_path):
-    """Grey 4:4:4-free case pins the IDCT: decode == round(float IDCT of the dequantised coefficients) up to the +-1 of a
-    12-bit fixed-point butterfly, never more; a flat block must be exact."""
+def test_jpeg_flat_block_and_colour_conversion_are_the_stated_integer_pipeline(tmp_path):
+    """A DC-only block must decode exactly (the IDCT's DC shortcut and its full path agree on d0 * 4), and a flat colour patch
+    must follow the stated 20-bit fixed-point BT.601 conversion bit for bit, masking of the Cb term included."""
     flat = np.full((16, 16), 77, np.uint8)
     PIL.fromarray(flat).save(tmp_path / "flat.jpg", "JPEG", quality=100)
     assert (decode_image(tmp_path / "flat.jpg")[..., :3] == 77).all()

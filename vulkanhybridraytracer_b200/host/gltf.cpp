@@ -19,7 +19,10 @@
 // u8 / u16, primitives without indices get 0..n-1, images may be embedded (bufferView or data: URI), buffers may be data: URIs.
 #include "vkpinut.h"
 
+#include <cctype>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
@@ -82,7 +85,7 @@ std::string percent_decode(const std::string& s)
 {
     std::string out;
     for (size_t i = 0; i < s.size(); i++) {
-        if (s[i] == '%' && i + 2 < s.size() + 0 && std::isxdigit((unsigned char)s[i + 1]) && std::isxdigit((unsigned char)s[i + 2])) {
+        if (s[i] == '%' && i + 2 < s.size() && std::isxdigit((unsigned char)s[i + 1]) && std::isxdigit((unsigned char)s[i + 2])) {
             out += (char)std::strtol(s.substr(i + 1, 2).c_str(), nullptr, 16);
             i += 2;
         } else out += s[i];
