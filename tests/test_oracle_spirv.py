@@ -316,3 +316,52 @@ def test_raytraced_mode_is_raygen_closesthit_miss_spv(golden_setup, tag):
     assert ok.mean() >= 0.998, (ok.mean(), px[~ok][:5], got[~ok][:5], want[~ok][:5])
     if len(px) == W * H:
         assert int(z[f"{tag}_ray_counts"][:, 0].sum()) == o.counters.rays[2] and int(z[f"{tag}_ray_counts"][:, 1].sum()) == o.counters.rays[3]
+
+
+def test_spirv_interpreter_on_a_hand_assembled_module(tmp_path):
+    """The interpreter itself, without the reference: a module assembled word by word here -- uint f(uint* a, uint* b) { uint s = 0;
+    for (uint i = 0; i < *b; i++) s += *a * i; return s; } and float g(float* x) { return sqrt(*x) * 0.5 } -- must wrap like
+    32-bit hardware and round like fp32."""
+    import struct
+    from oracle.spirv_interp import Interpreter, Module, U32, F32
+
+    def ins(op, *ops):
+        return [((len(ops) + 1) << 16) | op] + list(ops)
+
+    def s(text):
+        b = text.encode() + b"\0"
+        b += b"\0" * (-len(b) % 4)
+        return list(struct.unpack("<%dI" % (len(b) // 4), b))
+    VOID, UINT, FLOAT, BOOL, PU, PF, FN_U, FN_F, C0, C1, CH, EXT = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
+    F, A, B, L0, S, I, LH, LB, LC, LM, LCND = 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30
+    t = list(range(40, 60))
+    G, X, GL = 70, 71, 72
+    w = [0x07230203, 0x00010500, 0, 100, 0]
+    w += ins(17, 1)                                     # OpCapability Shader
+    w += ins(11, EXT, *s("GLSL.std.450"))
+    w += ins(14, 0, 1)                                  # OpMemoryModel Logical GLSL450
+    w += ins(5, F, *s("f(u1;u1;")) + ins(5, G, *s("g(f1;"))
+    w += ins(19, VOID) + ins(21, UINT, 32, 0) + ins(22, FLOAT, 32) + ins(20, BOOL)
+    w += ins(32, PU, 7, UINT) + ins(32, PF, 7, FLOAT) + ins(33, FN_U, UINT, PU, PU) + ins(33, FN_F, FLOAT, PF)
+    w += ins(43, UINT, C0, 0) + ins(43, UINT, C1, 1) + ins(43, FLOAT, CH, struct.unpack("<I", struct.pack("<f", 0.5))[0])
+    # uint f(a, b)
+    w += ins(54, UINT, F, 0, FN_U) + ins(55, PU, A) + ins(55, PU, B) + ins(248, L0)
+    w += ins(59, PU, S, 7) + ins(59, PU, I, 7) + ins(62, S, C0) + ins(62, I, C0) + ins(249, LH)
+    w += ins(248, LH) + ins(246, LM, LC, 0) + ins(249, LCND)
+    w += ins(248, LCND) + ins(61, UINT, t[0], I) + ins(61, UINT, t[1], B) + ins(176, BOOL, t[2], t[0], t[1]) + ins(250, t[2], LB, LM)
+    w += ins(248, LB) + ins(61, UINT, t[3], A) + ins(61, UINT, t[4], I) + ins(132, UINT, t[5], t[3], t[4]) + ins(61, UINT, t[6], S)
+    w += ins(128, UINT, t[7], t[6], t[5]) + ins(62, S, t[7]) + ins(249, LC)
+    w += ins(248, LC) + ins(61, UINT, t[8], I) + ins(128, UINT, t[9], t[8], C1) + ins(62, I, t[9]) + ins(249, LH)
+    w += ins(248, LM) + ins(61, UINT, t[10], S) + ins(254, t[10]) + ins(56)
+    # float g(x)
+    w += ins(54, FLOAT, G, 0, FN_F) + ins(55, PF, X) + ins(248, GL) + ins(61, FLOAT, t[11], X) + ins(12, FLOAT, t[12], EXT, 31, t[11])
+    w += ins(133, FLOAT, t[13], t[12], CH) + ins(254, t[13]) + ins(56)
+    path = tmp_path / "m.spv"
+    path.write_bytes(struct.pack("<%dI" % len(w), *w))
+    it = Interpreter(Module(str(path)))
+    for a, b in ((3, 5), (0xdeadbeef, 1000), (7, 0)):
+        want = sum((a * i) & 0xffffffff for i in range(b)) & 0xffffffff
+        assert int(it.call("f", U32(a), U32(b))[0]) == want
+    for x in (2.0, 1e-20, 3.4e38, 0.0):
+        got = it.call("g", F32(x))[0]
+        assert np.float32(got).view(np.uint32) == (np.sqrt(np.float32(x)) * np.float32(0.5)).view(np.uint32)
