@@ -123,8 +123,8 @@ def mat4_cols(m16):
     return [a[k].copy() for k in range(4)]
 
 
-def lights_block(sc):
-    return [[light_value(l["position"], l["color"], l["radius"]) for l in sc.lights]]
+def lights_block(sc, lights=None):
+    return [[light_value(l["position"], l["color"], l["radius"]) for l in (sc.lights if lights is None else lights)]]
 
 
 def materials_block(sc):
@@ -221,7 +221,7 @@ class HybridPipeline:
     """traceRayEXT of hybridRaygen.rgen: closest hit by the oracle on the ray the shader built, then hybridHit.rchit.spv or
     miss.rmiss.spv main() on the caller's payload; hybridHit's own shadow rays go through ShadowPipeline."""
 
-    def __init__(self, sc, oracle, T, hit_module="hybridHit.rchit", env_name="environmentTexture", extra=None):
+    def __init__(self, sc, oracle, T, hit_module="hybridHit.rchit", env_name="environmentTexture", extra=None, lights=None):
         self.o, self.T, self.sc = oracle, T, sc
         self.shadow = ShadowPipeline(oracle, T)
         verts, inds = {}, {}
@@ -231,7 +231,7 @@ class HybridPipeline:
             inds[mid] = [[I32(int(k)) for k in ix]]
         inst = sc.instances
         env = [unorm_image(sc.textures[sc.sky_tex]), unorm_image(sc.textures[sc.irradiance_tex])]
-        res = {"Lights": lights_block(sc), "MaterialBuffer": materials_block(sc),
+        res = {"Lights": lights_block(sc, lights), "MaterialBuffer": materials_block(sc),
                "vertices": [verts[int(i["mesh_id"])] for i in inst], "indices": [inds[int(i["mesh_id"])] for i in inst],
                "textures": [unorm_image(t) for t in sc.textures], env_name: env,
                "sceneBuffer": [[vec(k, int(i["material_id"]), k, int(i["first_index"])) for k, i in enumerate(inst)]],
@@ -501,7 +501,67 @@ def gen_raytrace():
     np.savez_compressed(os.path.join(OUT, "spirv_raytrace.npz"), **out)
     o.close(); sc.close()
 
-GENERATORS = {"raytrace": gen_raytrace, "gbuffer": gen_gbuffer, "functions": gen_functions, "shadow": gen_shadow, "resolve": gen_resolve, "deferred": gen_deferred, "post": gen_post, "blur": gen_blur}
+
+# ------------------------------------------------------------------------------------------------------- light edge cases through a4 + a6-a8
+def variant_lights(sc):
+    """The branches the default scene never takes: a directional light (pos.w < 0: L = pos.xyz, attenuation 0.3 in hybridHit,
+    intensity 1), a point light whose maxDistance most of the scene lies beyond (unshadowed in shadowRaygen.rgen:81-83 but
+    shadowed in hybridHit.rchit:115-125, attenuation clamps to 0), and a light of zero intensity (attenuation = 0, the
+    irradiance branch of the mirror / glass terms)."""
+    lights = sc.lights.copy()
+    lights["position"][0] = [0.3, 0.8, 0.5, -1.0]
+    lights["position"][1][3] = 14.0
+    lights["color"][2][3] = 0.0
+    return lights
+
+
+def gen_variants():
+    vk, sc, o, W, H = golden_scene()
+    from vulkanhybridraytracer_b200 import types as T
+    lights = variant_lights(sc)
+    o.set_lights(lights)
+    cam = sc.camera(W, H)
+    p = vk.make_params(W, H, frame=1, shadow_samples=2)
+    g = o.gbuffer(cam, p)
+    # a4
+    pipe = ShadowPipeline(o, T)
+    shadow_imgs = [Image2D(np.zeros((H, W, 4), F32), unorm8=True) for _ in lights]
+    res = {"cam": [mat4_cols(cam.inv_view), mat4_cols(cam.inv_proj), F32(1)], "Lights": lights_block(sc, lights), "SampleBuffer": [I32(2)],
+           "MaterialBuffer": materials_block(sc), "gbuffers": gbuffer_images(g), "shadowImage": shadow_imgs, "LaunchSizeKHR": np.array([W, H, 1], U32)}
+    it = Interpreter(module("shadowRaygen.rgen"), res, trace_ray=pipe)
+    launch = it.m.builtin_globals()["LaunchIdKHR"]
+    pixels, sh = [], []
+    for y in range(0, H, 2):
+        for x in range(0, W, 2):
+            it.cells[launch][0] = np.array([x, y, 0], U32)
+            it.run_entry()
+            pixels.append((x, y)); sh.append([int(np.rint(img.a[y, x, 0] * 255)) for img in shadow_imgs])
+    out = {"params": np.array([W, H, 1, 2], np.int32), "lights": lights, "pixels": np.array(pixels, np.int32), "shadow": np.array(sh, np.uint8)}
+    # a6-a8 on the oracle's filtered planes of that frame
+    fr = o.hybrid_frame(cam, p)
+    den = fr["denoised"]
+    hp = HybridPipeline(sc, o, T, lights=lights)
+    image = Image2D(np.zeros((H, W, 4), F32))
+    env = [unorm_image(sc.textures[sc.sky_tex]), unorm_image(sc.textures[sc.irradiance_tex])]
+    simgs = []
+    for l in range(len(lights)):
+        a = np.zeros((H, W, 4), F32); a[..., 0] = den[l].astype(F32) / F32(255); a[..., 3] = 1
+        simgs.append(Image2D(a))
+    res = {"cam": [mat4_cols(cam.inv_view), mat4_cols(cam.inv_proj), vec(1, 0, 0, 0)], "gbuffers": hybrid_gbuffer_images(g), "Lights": lights_block(sc, lights),
+           "MaterialBuffer": materials_block(sc), "environmentTexture": env, "shadowImage": simgs, "image": image, "LaunchSizeKHR": np.array([W, H, 1], U32)}
+    it = Interpreter(module("hybridRaygen.rgen"), res, trace_ray=hp)
+    launch = it.m.builtin_globals()["LaunchIdKHR"]
+    colors = []
+    for (x, y) in pixels:
+        it.cells[launch][0] = np.array([x, y, 0], U32)
+        it.run_entry()
+        colors.append(image.a[y, x].copy())
+    out["final"] = np.array(colors, np.float32)
+    np.savez_compressed(os.path.join(OUT, "spirv_variants.npz"), **out)
+    print("variants: pixels", len(pixels), "shadow rays", len(pipe.rays), "chain rays", len(hp.rays), "secondary shadow rays", len(hp.shadow.rays))
+    o.close(); sc.close()
+
+GENERATORS = {"variants": gen_variants, "raytrace": gen_raytrace, "gbuffer": gen_gbuffer, "functions": gen_functions, "shadow": gen_shadow, "resolve": gen_resolve, "deferred": gen_deferred, "post": gen_post, "blur": gen_blur}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(GENERATORS)

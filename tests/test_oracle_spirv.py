@@ -365,3 +365,31 @@ def test_spirv_interpreter_on_a_hand_assembled_module(tmp_path):
     for x in (2.0, 1e-20, 3.4e38, 0.0):
         got = it.call("g", F32(x))[0]
         assert np.float32(got).view(np.uint32) == (np.sqrt(np.float32(x)) * np.float32(0.5)).view(np.uint32)
+
+
+def test_light_edge_cases_are_the_shader_binaries():
+    """Branches the default lights never take, through shadowRaygen.rgen.spv and hybridRaygen.rgen.spv + hybridHit.rchit.spv:
+    a directional light (pos.w < 0), a point light most of the scene lies beyond the maxDistance of (unshadowed in the shadow pass,
+    shadowRaygen.rgen:81-83, but shadowed in the hit shader, hybridHit.rchit:115-125 -- App. A #4), and a zero-intensity light
+    (attenuation 0 / the irradiance branch of the mirror and glass terms, App. A #8); frame 1, two shadow samples."""
+    import vulkanhybridraytracer_b200 as vk2
+    from oracle.oracle_py import Oracle
+    from util import GOLDEN_DETAIL
+    z = vectors("variants")
+    W, H, frame, samples = [int(v) for v in z["params"]]
+    sc = vk2.HostScene(0, detail=GOLDEN_DETAIL); o = Oracle(sc)
+    lights = sc.lights.copy()
+    for k in ("position", "color", "radius"):
+        lights[k] = z["lights"][k]
+    assert lights["position"][0][3] < 0 and lights["color"][2][3] == 0
+    o.set_lights(lights)
+    p = vk2.make_params(W, H, frame=frame, shadow_samples=samples)
+    fr = o.hybrid_frame(sc.camera(W, H), p)
+    px = z["pixels"]
+    got = np.stack([fr["shadow"][l][px[:, 1], px[:, 0]] for l in range(3)], 1)
+    assert (got == z["shadow"]).all(1).mean() >= 0.998
+    assert (z["shadow"][:, 1] == 255).mean() > 0.25                # light 1: "beyond maxDistance" counts as lit in the shadow pass
+    want = z["final"][:, :3]; have = fr["final"][px[:, 1], px[:, 0], :3]
+    ok = (np.abs(have - want) <= 2e-5 * np.abs(want) + 2e-6).all(1)
+    assert ok.mean() >= 0.996, (ok.mean(), px[~ok][:5], have[~ok][:5], want[~ok][:5])
+    o.close(); sc.close()

@@ -155,3 +155,34 @@ def test_cuda_path_against_the_reference_shader_binaries():
         want = np.rint(np.clip(zg[name], 0, 1) * 255).astype(int)
         assert np.abs(ctx.readback(plane)[Y, X][:, :3].astype(int) - want).max() <= 1, name
     ctx.close(); sc.close()
+
+
+def test_light_edge_cases_on_the_gpu():
+    """Directional light, a light most of the scene lies beyond the maxDistance of, a zero-intensity light (the branches of
+    shadowRaygen.rgen:55-83, hybridRaygen.rgen:71-147 and hybridHit.rchit:97-175 the default lights never take): CUDA path == oracle
+    bit for bit, and within the stated tolerance of the reference's shader binaries (tests/golden/spirv_variants.npz)."""
+    import os
+    from util import GOLDEN_DETAIL, GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "spirv_variants.npz"))
+    W, H, frame, samples = [int(v) for v in z["params"]]
+    sc = vk.HostScene(0, detail=GOLDEN_DETAIL)
+    lights = sc.lights.copy()
+    for k in ("position", "color", "radius"):
+        lights[k] = z["lights"][k]
+    o = Oracle(sc); o.set_lights(lights)
+    ctx = vk.Context(0); ctx.upload_scene(sc); ctx.set_lights(lights)
+    cam = sc.camera(W, H); ctx.set_camera(cam)
+    for wavefront in (0, 2):
+        p = vk.make_params(W, H, frame=frame, shadow_samples=samples, wavefront=wavefront)
+        ctx.set_params(p); ctx.reset_history(); ctx.render()
+        ref = o.hybrid_frame(cam, p)
+        for l in range(3):
+            assert np.array_equal(ctx.readback(PLANE.SHADOW0 + l), ref["shadow"][l]), (wavefront, l)
+            assert np.array_equal(ctx.readback(PLANE.DENOISED0 + l), ref["denoised"][l]), (wavefront, l)
+        final = ctx.readback(PLANE.FINAL_F32)
+        assert np.array_equal(final.view(np.uint32), ref["final"].view(np.uint32)), wavefront
+    px = z["pixels"]; want = z["final"][:, :3]; have = final[px[:, 1], px[:, 0], :3]
+    assert ((np.abs(have - want) <= 2e-5 * np.abs(want) + 2e-6).all(1)).mean() >= 0.996
+    got = np.stack([ctx.readback(PLANE.SHADOW0 + l)[px[:, 1], px[:, 0]] for l in range(3)], 1)
+    assert (got == z["shadow"]).all(1).mean() >= 0.998
+    ctx.close(); sc.close(); o.close()
