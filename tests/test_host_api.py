@@ -124,3 +124,24 @@ def test_png_and_exr_writers(tmp_path):
         assert raw[:4] == bytes([0x76, 0x2F, 0x31, 0x01]) and len(raw) > 21 * 33 * 16
     else:
         assert np.array_equal(back[..., [2, 1, 0, 3]], f)
+
+
+def test_cli_arguments_and_loud_failure_without_a_gpu():
+    """bin/vkpinut (headless src/main.cpp + window.cpp): scripted camera motion is parsed, unknown input is refused, and without a
+    GPU the program says so and exits non-zero instead of falling back to anything."""
+    import subprocess
+    exe = os.path.join(vk.lib_dir(), "..", "bin", "vkpinut")
+    r = subprocess.run([exe, "--walk", "sideways:3"], capture_output=True, text=True)
+    assert r.returncode == 2 and "unknown direction" in r.stderr
+    r = subprocess.run([exe, "--bogus"], capture_output=True, text=True)
+    assert r.returncode == 2 and "unknown argument" in r.stderr
+    r = subprocess.run([exe, "--walk", "right:20,forward:5", "--turn", "3:1", "--frames", "2", "--width", "64", "--height", "36"], capture_output=True, text=True)
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        assert r.returncode == 0 and "rays:" in r.stdout
+    else:
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr

@@ -203,6 +203,7 @@ void VulkanEngine::update(const float)
 void VulkanEngine::run(int frames)
 {
     for (int f = 0; f < frames; f++) {
+        if (_onFrame) _onFrame(_frameNumber);
         update(16.6f);
         if (_mode == DEFERRED) renderer->render();
         else if (_mode == RAYTRACING) renderer->raytrace();

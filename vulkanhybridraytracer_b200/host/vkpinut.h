@@ -288,6 +288,10 @@ public:
     bool _reprojectFix{false};          // vkp_params.reproject_fix: false = the reference's blur.comp history fetch, true = the previous frame's pixel
     int _chainMode{2};                  // vkp_params.wavefront: how the reflection chain is scheduled (0 inline, 1 wavefront, 2 overlapped)
 
+    // headless replacement of Window::input_update (window.cpp:40-110): called at the top of every frame of run(), before
+    // update(); a script moves the camera there (Camera::processKeyboard / rotate), which resets the accumulation like a key press does
+    std::function<void(int frame)> _onFrame;
+
     void init();
     void run(int frames = 1);
     void update(const float dt);
