@@ -17,7 +17,8 @@ ARCH   := -gencode arch=compute_100a,code=sm_100a
 # -fmad=false: the numerics contract (bit-identical to the scalar fp32 evaluation); explicit __fmaf_rn where safe
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-fvisibility=hidden -ccbin $(CXX) --cudart static \
            -Xptxas -v -diag-suppress 20012
-CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-unused-variable
+# -fwrapv: the integer IDCT of the JPEG reader may overflow on corrupt streams (as in stb_image); wrapping keeps that defined
+CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-unused-variable -fwrapv
 
 CU_SRCS := $(CSRC)/vkp_api.cu $(CSRC)/bvh_build.cu $(CSRC)/kernels_frame.cu
 CU_OBJS := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
