@@ -10,7 +10,7 @@ import vulkanhybridraytracer_b200 as vk
 
 
 def test_default_scene_matches_scene_cpp():
-    sc = vk.HostScene(0)
+    sc = vk.HostScene(0, detail=(7, 5, 7, 31))      # the library's defaults, stated: the detail setting is global in libvkp_host
     # TLAS order floor, mirror sphere, glass sphere, mirror slab, lucy, helmet (scene.cpp:151-158)
     assert sc.instances["material_id"].tolist() == [1, 2, 3, 2, 5, 4]
     tris = (sc.instances["index_count"] // 3).tolist()
