@@ -204,11 +204,10 @@ def make_params(width, height, mode=MODE_HYBRID, spp=1, shadow_samples=1, max_bo
 class HostScene:
     """Scene::create_scene(i) of the host library, exported as the flat arrays both the C-ABI and the oracle consume."""
 
-    DEFAULT_DETAIL = (7, 5, 7, 31)      # lucy / helmet / stress-blob subdivisions, stress instances (scene_model.cpp)
-
     def __init__(self, index=0, detail=None):
         H = load_host()
-        H.vkph_set_detail(*(detail if detail is not None else self.DEFAULT_DETAIL))      # the setting is global in the library: always state it
+        if detail is not None:
+            H.vkph_set_detail(*detail)
         self._H = H
         self._h = H.vkph_scene_create(index)
         if not self._h:
@@ -220,7 +219,8 @@ class HostScene:
     def from_prefab(cls, path, detail=None):
         """Scene::create_viewer_scene: the default scene's floor, lights and camera around one .obj / .gltf / .glb file."""
         H = load_host()
-        H.vkph_set_detail(*(detail if detail is not None else cls.DEFAULT_DETAIL))
+        if detail is not None:
+            H.vkph_set_detail(*detail)
         self = cls.__new__(cls)
         self._H = H
         self._h = H.vkph_scene_create_prefab(str(path).encode())
