@@ -110,11 +110,11 @@ def gen_functions():
 
 
 # ------------------------------------------------------------------------------------------------------- scene plumbing
-def golden_scene():
+def golden_scene(index=0, detail=None):
     import vulkanhybridraytracer_b200 as vk
     from oracle.oracle_py import Oracle
     from util import GOLDEN_DETAIL, GOLDEN_W, GOLDEN_H
-    sc = vk.HostScene(0, detail=GOLDEN_DETAIL)
+    sc = vk.HostScene(index, detail=detail or GOLDEN_DETAIL)
     return vk, sc, Oracle(sc), GOLDEN_W, GOLDEN_H
 
 
@@ -561,7 +561,46 @@ def gen_variants():
     print("variants: pixels", len(pixels), "shadow rays", len(pipe.rays), "chain rays", len(hp.rays), "secondary shadow rays", len(hp.shadow.rays))
     o.close(); sc.close()
 
-GENERATORS = {"variants": gen_variants, "raytrace": gen_raytrace, "gbuffer": gen_gbuffer, "functions": gen_functions, "shadow": gen_shadow, "resolve": gen_resolve, "deferred": gen_deferred, "post": gen_post, "blur": gen_blur}
+
+# ------------------------------------------------------------------------------------------------------- a6-a8 on the other scenes
+SCENES_DETAIL = (3, 2, 3, 14)      # 14 instances in the stress scene
+
+
+def gen_scenes():
+    """The resolve + hit + miss binaries on the Cornell scene (scene.cpp:162-272) and on the instanced stress scene (rotated and
+    non-uniformly scaled instances: hybridHit.rchit:50 takes the normal matrix from inverse(model) in the shader, the oracle from
+    the host-supplied inverse; materials cycle through the three shading models)."""
+    from vulkanhybridraytracer_b200 import types as T
+    out = {}
+    for index, step in ((1, 1), (2, 1)):
+        vk, sc, o, W, H = golden_scene(index, SCENES_DETAIL)
+        cam = sc.camera(W, H)
+        p = vk.make_params(W, H, frame=2)
+        fr = o.hybrid_frame(cam, p)
+        g, den = fr["g"], fr["denoised"]
+        pipe = HybridPipeline(sc, o, T)
+        image = Image2D(np.zeros((H, W, 4), F32))
+        env = [unorm_image(sc.textures[sc.sky_tex]), unorm_image(sc.textures[sc.irradiance_tex])]
+        simgs = []
+        for l in range(len(sc.lights)):
+            a = np.zeros((H, W, 4), F32); a[..., 0] = den[l].astype(F32) / F32(255); a[..., 3] = 1
+            simgs.append(Image2D(a))
+        res = {"cam": [mat4_cols(cam.inv_view), mat4_cols(cam.inv_proj), vec(2, 0, 0, 0)], "gbuffers": hybrid_gbuffer_images(g), "Lights": lights_block(sc),
+               "MaterialBuffer": materials_block(sc), "environmentTexture": env, "shadowImage": simgs, "image": image, "LaunchSizeKHR": np.array([W, H, 1], U32)}
+        it = Interpreter(module("hybridRaygen.rgen"), res, trace_ray=pipe)
+        launch = it.m.builtin_globals()["LaunchIdKHR"]
+        pixels, colors = [], []
+        for y in range(0, H, step):
+            for x in range(0, W, step):
+                it.cells[launch][0] = np.array([x, y, 0], U32)
+                it.run_entry()
+                pixels.append((x, y)); colors.append(image.a[y, x].copy())
+        out[f"s{index}_params"] = np.array([W, H, 2], np.int32); out[f"s{index}_pixels"] = np.array(pixels, np.int32); out[f"s{index}_final"] = np.array(colors, np.float32)
+        print("scene", index, "pixels", len(pixels), "chain rays", len(pipe.rays), "secondary shadow rays", len(pipe.shadow.rays), "lights", len(sc.lights), "instances", len(sc.instances))
+        o.close(); sc.close()
+    np.savez_compressed(os.path.join(OUT, "spirv_scenes.npz"), **out)
+
+GENERATORS = {"scenes": gen_scenes, "variants": gen_variants, "raytrace": gen_raytrace, "gbuffer": gen_gbuffer, "functions": gen_functions, "shadow": gen_shadow, "resolve": gen_resolve, "deferred": gen_deferred, "post": gen_post, "blur": gen_blur}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(GENERATORS)

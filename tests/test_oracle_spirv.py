@@ -393,3 +393,22 @@ def test_light_edge_cases_are_the_shader_binaries():
     ok = (np.abs(have - want) <= 2e-5 * np.abs(want) + 2e-6).all(1)
     assert ok.mean() >= 0.996, (ok.mean(), px[~ok][:5], have[~ok][:5], want[~ok][:5])
     o.close(); sc.close()
+
+
+@pytest.mark.parametrize("index", [1, 2])
+def test_resolve_on_the_other_scenes_is_the_shader_binaries(index):
+    """hybridRaygen.rgen.spv + hybridHit.rchit.spv + miss.rmiss.spv on the Cornell scene (scene.cpp:162-272, one light) and on the
+    instanced stress scene (rotated, non-uniformly scaled instances: the shader derives the normal matrix from inverse(model)
+    itself, hybridHit.rchit:50, the oracle takes the host-supplied inverse), frame 2."""
+    import vulkanhybridraytracer_b200 as vk2
+    from oracle.oracle_py import Oracle
+    z = vectors("scenes")
+    W, H, frame = [int(v) for v in z[f"s{index}_params"]]
+    sc = vk2.HostScene(index, detail=(3, 2, 3, 14)); o = Oracle(sc)
+    fr = o.hybrid_frame(sc.camera(W, H), vk2.make_params(W, H, frame=frame))
+    px = z[f"s{index}_pixels"]; want = z[f"s{index}_final"][:, :3]
+    have = fr["final"][px[:, 1], px[:, 0], :3]
+    ok = (np.abs(have - want) <= 2e-5 * np.abs(want) + 2e-6).all(1)
+    assert ok.mean() >= 0.998, (index, ok.mean(), px[~ok][:5], have[~ok][:5], want[~ok][:5])
+    assert (fr["g"].hit_ids[..., 0] >= 0).mean() > 0.2
+    o.close(); sc.close()
