@@ -6,9 +6,19 @@
  * helpers.glsl:71 pow); their rounding is implementation-defined.  Shadow
  * visibility is binary, so two "correct" libms that differ by one ulp flip
  * pixels on penumbra edges.  This header pins ONE implementation, built only
- * from IEEE-754 correctly-rounded +,-,*,/,sqrt and integer bit operations in a
- * fixed order, so that host (gcc, -ffp-contract=off) and device (nvcc,
- * -fmad=false) produce bit-identical results.  It is the numerics contract of
+ * from IEEE-754 correctly-rounded +,-,*,/,sqrt, fused multiply-add and integer
+ * bit operations in a fixed order, so that host (gcc, -ffp-contract=off) and
+ * device (nvcc, -fmad=false) produce bit-identical results.
+ *
+ * Contract v2 (round 2): fused multiply-add is part of the contract, but only
+ * where it is WRITTEN -- vkp_fmaf() is fmaf() on the host (correctly rounded by
+ * C99, one vfmadd with -mfma) and __fmaf_rn() on the device; neither compiler
+ * may contract anything on its own.  The polynomial kernels below are Horner
+ * chains of vkp_fmaf, and the vector primitives at the end of the file (dot,
+ * cross component, matrix row, mix) are what BOTH the CUDA kernels
+ * (vkp_device.cuh) and the CPU oracle (oracle/orc_math.h) are built from: the
+ * traversal and shading kernels issue half as many FP instructions as the
+ * mul/add form of round 1 and stay bit-identical to the scalar evaluation.  It is the numerics contract of
  * the C-ABI, not part of the reference's algorithm; the CPU oracle may be
  * compiled against it (default) or against glibc (-DORC_USE_LIBM) and the
  * tests run both.
@@ -52,6 +62,16 @@ VKP_HD float vkp_u2f(uint32_t u)
 #endif
 }
 
+/* fused multiply-add, one rounding: fmaf (C99) on the host, FFMA on the device */
+VKP_HD float vkp_fmaf(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+
 /* IEEE sqrt: correctly rounded on both sides (nvcc default -prec-sqrt=true). */
 VKP_HD float vkp_sqrtf(float x) { return sqrtf(x); }
 
@@ -72,14 +92,14 @@ VKP_HD void vkp_sincosf(float x, float* s, float* c)
     /* k = nearest integer to x * 2/pi ; r = x - k*pi/2 via 3-term Cody-Waite */
     float kf = vkp_rintf_small(x * 0.636619772367581343f);
     int   k  = (int)kf;
-    float r  = x - kf * 1.5703125f;              /* pi/2 high bits (exact product for small k) */
-    r = r - kf * 4.837512969970703125e-4f;
-    r = r - kf * 7.54978995489188e-8f;
+    float r  = vkp_fmaf(-kf, 1.5703125f, x);     /* pi/2 high bits (exact product for small k) */
+    r = vkp_fmaf(-kf, 4.837512969970703125e-4f, r);
+    r = vkp_fmaf(-kf, 7.54978995489188e-8f, r);
     float z = r * r;
     /* Cephes sinf / cosf kernels on [-pi/4, pi/4] */
-    float ps = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
-    float pc = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z
-               - 0.5f * z + 1.0f;
+    float ps = vkp_fmaf(vkp_fmaf(vkp_fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f) * z, r, r);
+    float pc = vkp_fmaf(vkp_fmaf(vkp_fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f) * z, z,
+                        vkp_fmaf(-0.5f, z, 1.0f));
     float sv, cv;
     switch (k & 3) {
     case 0:  sv =  ps; cv =  pc; break;
@@ -107,8 +127,8 @@ VKP_HD float vkp_atanf(float xx)
         y = 0.0f;
     }
     float z = x * x;
-    y = y + ((((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z
-              - 3.33329491539e-1f) * z * x + x);
+    y = y + vkp_fmaf(vkp_fmaf(vkp_fmaf(vkp_fmaf(8.05374449538e-2f, z, -1.38776856032e-1f), z, 1.99777106478e-1f), z,
+                              -3.33329491539e-1f) * z, x, x);
     return xx < 0.0f ? -y : y;
 }
 
@@ -139,8 +159,8 @@ VKP_HD float vkp_asinf(float xx)
         x = a;
         z = x * x;
     }
-    float p = ((((4.2163199048e-2f * z + 2.4181311049e-2f) * z + 4.5470025998e-2f) * z
-                + 7.4953002686e-2f) * z + 1.6666752422e-1f) * z * x + x;
+    float p = vkp_fmaf(vkp_fmaf(vkp_fmaf(vkp_fmaf(vkp_fmaf(4.2163199048e-2f, z, 2.4181311049e-2f), z, 4.5470025998e-2f), z,
+                                         7.4953002686e-2f), z, 1.6666752422e-1f) * z, x, x);
     if (big) {
         p = p + p;
         p = 1.57079632679489661923f - p;
@@ -159,11 +179,12 @@ VKP_HD float vkp_log2f(float x)
     float f = m - 1.0f;
     float z = f * f;
     /* Cephes logf polynomial: ln(1+f) = f - z/2 + f*z*P(f) */
-    float p = ((((((((7.0376836292e-2f * f - 1.1514610310e-1f) * f + 1.1676998740e-1f) * f
-                    - 1.2420140846e-1f) * f + 1.4249322787e-1f) * f - 1.6668057665e-1f) * f
-                 + 2.0000714765e-1f) * f - 2.4999993993e-1f) * f + 3.3333331174e-1f);
-    float ln = f * z * p;
-    ln = ln - 0.5f * z;
+    float p = 7.0376836292e-2f;
+    p = vkp_fmaf(p, f, -1.1514610310e-1f); p = vkp_fmaf(p, f, 1.1676998740e-1f); p = vkp_fmaf(p, f, -1.2420140846e-1f);
+    p = vkp_fmaf(p, f, 1.4249322787e-1f); p = vkp_fmaf(p, f, -1.6668057665e-1f); p = vkp_fmaf(p, f, 2.0000714765e-1f);
+    p = vkp_fmaf(p, f, -2.4999993993e-1f); p = vkp_fmaf(p, f, 3.3333331174e-1f);
+    float ln = (f * z) * p;
+    ln = vkp_fmaf(-0.5f, z, ln);
     ln = ln + f;
     /* ln -> log2: split 1/ln2 for accuracy */
     float r = ln * 1.44269504088896341f;
@@ -179,9 +200,9 @@ VKP_HD float vkp_exp2f(float x)
     int   k  = (int)kf;
     float f  = x - kf;                 /* [-0.5, 0.5] exact */
     /* Cephes exp2f polynomial */
-    float p = (((((1.535336188319500e-4f * f + 1.339887440266574e-3f) * f + 9.618437357674640e-3f) * f
-                 + 5.550332471162809e-2f) * f + 2.402264791363012e-1f) * f + 6.931472028550421e-1f) * f
-              + 1.0f;
+    float p = 1.535336188319500e-4f;
+    p = vkp_fmaf(p, f, 1.339887440266574e-3f); p = vkp_fmaf(p, f, 9.618437357674640e-3f); p = vkp_fmaf(p, f, 5.550332471162809e-2f);
+    p = vkp_fmaf(p, f, 2.402264791363012e-1f); p = vkp_fmaf(p, f, 6.931472028550421e-1f); p = vkp_fmaf(p, f, 1.0f);
     /* scale by 2^k through the exponent field; k in [-126,128] */
     int e = k + 127;
     if (e <= 0) return 0.0f;
@@ -261,5 +282,28 @@ VKP_HD float vkp_f16_to_f32(uint16_t h)
     if (e == 31u) return vkp_u2f(sign | 0x7f800000u | (m << 13));
     return vkp_u2f(sign | ((e + 112u) << 23) | (m << 13));
 }
+
+/* ---- vector primitives of contract v2 (scalars in, scalar out: float3 on the device and orc::vec3 on the host are built from them) ---- */
+/* a . b */
+VKP_HD float vkp_dot3(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return vkp_fmaf(az, bz, vkp_fmaf(ay, by, ax * bx));
+}
+/* a*b - c*d: one component of a cross product */
+VKP_HD float vkp_diff_of_products(float a, float b, float c, float d) { return vkp_fmaf(a, b, -(c * d)); }
+/* m0*x + m1*y + m2*z + m3: one row of a 3x4 affine map applied to a point */
+VKP_HD float vkp_row_point(float m0, float m1, float m2, float m3, float x, float y, float z)
+{
+    return vkp_fmaf(m2, z, vkp_fmaf(m1, y, vkp_fmaf(m0, x, m3)));
+}
+/* m0*x + m1*y + m2*z + m3*w: one row of a 4x4 matrix applied to a vec4 */
+VKP_HD float vkp_row_vec4(float m0, float m1, float m2, float m3, float x, float y, float z, float w)
+{
+    return vkp_fmaf(m3, w, vkp_fmaf(m2, z, vkp_fmaf(m1, y, m0 * x)));
+}
+/* GLSL mix(x, y, a) = x*(1-a) + y*a */
+VKP_HD float vkp_mixf(float x, float y, float a) { return vkp_fmaf(y, a, x * (1.0f - a)); }
+/* c - a*b (reflect / refract tails, Cody-Waite steps) */
+VKP_HD float vkp_nmsubf(float a, float b, float c) { return vkp_fmaf(-a, b, c); }
 
 #endif /* VKP_DETMATH_H */

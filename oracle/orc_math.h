@@ -3,8 +3,9 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may use oracle/.
  *
  * GLSL built-ins the reference shaders use, restated as scalar C++ with ONE fixed evaluation order
- * (left-to-right as written in the GLSL source, no FMA contraction: compile with
- * -ffp-contract=off).  Elementary functions come from include/vkp_detmath.h (the numerics contract
+ * (left-to-right as written in the GLSL source, no FMA contraction by the compiler: compile with
+ * -ffp-contract=off; the only fused operations are the ones written as vkp_fmaf in the contract-v2
+ * primitives of include/vkp_detmath.h).  Elementary functions come from include/vkp_detmath.h (the numerics contract
  * of the C-ABI) unless ORC_USE_LIBM is defined, in which case glibc's are used (independence
  * check: the tests then allow epsilon-tie flips).
  */
@@ -56,10 +57,11 @@ inline vec3& operator*=(vec3& a, vec3 b) { a = a * b; return a; }
 inline vec3& operator*=(vec3& a, float s) { a = a * s; return a; }
 inline bool operator==(vec3 a, vec3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 
-inline float dot(vec3 a, vec3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+/* contract v2 (include/vkp_detmath.h): dot, cross, matrix rows, mix, reflect / refract are FMA forms shared with the CUDA kernels */
+inline float dot(vec3 a, vec3 b) { return vkp_dot3(a.x, a.y, a.z, b.x, b.y, b.z); }
 inline vec3 cross(vec3 a, vec3 b)
 {
-    return vec3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+    return vec3(vkp_diff_of_products(a.y, b.z, a.z, b.y), vkp_diff_of_products(a.z, b.x, a.x, b.z), vkp_diff_of_products(a.x, b.y, a.y, b.x));
 }
 inline float length(vec3 a) { return sqrtf(dot(a, a)); }
 inline vec3 normalize(vec3 a) { float inv = 1.0f / sqrtf(dot(a, a)); return a * inv; }
@@ -67,46 +69,47 @@ inline float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi
 inline float maxf(float a, float b) { return fmaxf(a, b); }
 inline float minf(float a, float b) { return fminf(a, b); }
 inline vec3 max3(vec3 a, float s) { return vec3(fmaxf(a.x, s), fmaxf(a.y, s), fmaxf(a.z, s)); }
-inline float mixf(float x, float y, float a) { return x * (1.0f - a) + y * a; }
-inline vec3 mix(vec3 x, vec3 y, float a) { return x * (1.0f - a) + y * a; }
+inline float mixf(float x, float y, float a) { return vkp_mixf(x, y, a); }
+inline vec3 mix(vec3 x, vec3 y, float a) { return vec3(vkp_mixf(x.x, y.x, a), vkp_mixf(x.y, y.y, a), vkp_mixf(x.z, y.z, a)); }
 inline vec3 pow3(vec3 a, float e) { return vec3(e_pow(a.x, e), e_pow(a.y, e), e_pow(a.z, e)); }
-inline vec3 reflect(vec3 I, vec3 N) { return I - N * (2.0f * dot(N, I)); }
+inline vec3 reflect(vec3 I, vec3 N) { const float k = 2.0f * dot(N, I); return vec3(vkp_nmsubf(N.x, k, I.x), vkp_nmsubf(N.y, k, I.y), vkp_nmsubf(N.z, k, I.z)); }
 inline vec3 refract(vec3 I, vec3 N, float eta)
 {
     float d = dot(N, I);
-    float k = 1.0f - (eta * eta) * (1.0f - d * d);
+    float k = vkp_nmsubf(eta * eta, vkp_nmsubf(d, d, 1.0f), 1.0f);
     if (k < 0.0f) return vec3(0.0f);
-    return I * eta - N * (eta * d + sqrtf(k));
+    const float s = vkp_fmaf(eta, d, sqrtf(k));
+    return vec3(vkp_nmsubf(N.x, s, I.x * eta), vkp_nmsubf(N.y, s, I.y * eta), vkp_nmsubf(N.z, s, I.z * eta));
 }
 
 /* column-major mat4 (GLM): m[c*4+r] */
 inline vec3 mul_point(const float* m, vec3 p)   /* (M * vec4(p,1)).xyz */
 {
-    return vec3(((m[0] * p.x + m[4] * p.y) + m[8] * p.z) + m[12],
-                ((m[1] * p.x + m[5] * p.y) + m[9] * p.z) + m[13],
-                ((m[2] * p.x + m[6] * p.y) + m[10] * p.z) + m[14]);
+    return vec3(vkp_row_point(m[0], m[4], m[8], m[12], p.x, p.y, p.z),
+                vkp_row_point(m[1], m[5], m[9], m[13], p.x, p.y, p.z),
+                vkp_row_point(m[2], m[6], m[10], m[14], p.x, p.y, p.z));
 }
 inline vec3 mul_dir(const float* m, vec3 d)     /* (M * vec4(d,0)).xyz */
 {
-    return vec3((m[0] * d.x + m[4] * d.y) + m[8] * d.z,
-                (m[1] * d.x + m[5] * d.y) + m[9] * d.z,
-                (m[2] * d.x + m[6] * d.y) + m[10] * d.z);
+    return vec3(vkp_dot3(m[0], m[4], m[8], d.x, d.y, d.z),
+                vkp_dot3(m[1], m[5], m[9], d.x, d.y, d.z),
+                vkp_dot3(m[2], m[6], m[10], d.x, d.y, d.z));
 }
 inline vec4 mul_vec4(const float* m, vec4 v)
 {
     vec4 r;
-    r.x = ((m[0] * v.x + m[4] * v.y) + m[8] * v.z) + m[12] * v.w;
-    r.y = ((m[1] * v.x + m[5] * v.y) + m[9] * v.z) + m[13] * v.w;
-    r.z = ((m[2] * v.x + m[6] * v.y) + m[10] * v.z) + m[14] * v.w;
-    r.w = ((m[3] * v.x + m[7] * v.y) + m[11] * v.z) + m[15] * v.w;
+    r.x = vkp_row_vec4(m[0], m[4], m[8], m[12], v.x, v.y, v.z, v.w);
+    r.y = vkp_row_vec4(m[1], m[5], m[9], m[13], v.x, v.y, v.z, v.w);
+    r.z = vkp_row_vec4(m[2], m[6], m[10], m[14], v.x, v.y, v.z, v.w);
+    r.w = vkp_row_vec4(m[3], m[7], m[11], m[15], v.x, v.y, v.z, v.w);
     return r;
 }
 /* mat3(transpose(M)) * n : row i of the result = dot(column i of M, n) */
 inline vec3 mul_transpose3(const float* m, vec3 n)
 {
-    return vec3((m[0] * n.x + m[1] * n.y) + m[2] * n.z,
-                (m[4] * n.x + m[5] * n.y) + m[6] * n.z,
-                (m[8] * n.x + m[9] * n.y) + m[10] * n.z);
+    return vec3(vkp_dot3(m[0], m[1], m[2], n.x, n.y, n.z),
+                vkp_dot3(m[4], m[5], m[6], n.x, n.y, n.z),
+                vkp_dot3(m[8], m[9], m[10], n.x, n.y, n.z));
 }
 
 /* random.glsl:3-17 */

@@ -138,9 +138,8 @@ def load_host():
     P = C.POINTER
     sig = {
         "vkph_last_error": (C.c_char_p, []),
-        "vkph_set_detail": (None, [i, i, i, i]),
-        "vkph_scene_create": (vp, [i]),
-        "vkph_scene_create_prefab": (vp, [C.c_char_p]),
+        "vkph_scene_create": (vp, [i, P(i)]),
+        "vkph_scene_create_prefab": (vp, [C.c_char_p, P(i)]),
         "vkph_scene_destroy": (None, [vp]),
         "vkph_scene_counts": (i, [vp] + [P(i)] * 7),
         "vkph_scene_mesh": (i, [vp, i, P(vp), P(u32), P(vp), P(u32)]),
@@ -153,7 +152,7 @@ def load_host():
         "vkph_scene_camera_rotate": (i, [vp, C.c_float, C.c_float]),
         "vkph_scene_camera_set": (i, [vp, P(C.c_float * 3), C.c_float, C.c_float]),
         "vkph_scene_set_entity_matrix": (i, [vp, i, P(C.c_float * 16)]),
-        "vkph_engine_create": (vp, [i, i, i, i]),
+        "vkph_engine_create": (vp, [i, i, i, i, P(i)]),
         "vkph_engine_set": (i, [vp, C.c_char_p, i]),
         "vkph_engine_frames": (i, [vp, i]),
         "vkph_engine_camera_move": (i, [vp, i, C.c_float]),
@@ -201,15 +200,20 @@ def make_params(width, height, mode=MODE_HYBRID, spp=1, shadow_samples=1, max_bo
     return p
 
 
+def _detail4(detail):
+    """detail = (lucy subdivisions, helmet subdivisions, stress subdivisions, stress instances) of the procedural stand-in meshes,
+    or None for the full-size scene.  It is an argument of every scene / engine creation, never library state."""
+    return None if detail is None else (C.c_int * 4)(*[int(x) for x in detail])
+
+
 class HostScene:
     """Scene::create_scene(i) of the host library, exported as the flat arrays both the C-ABI and the oracle consume."""
 
     def __init__(self, index=0, detail=None):
         H = load_host()
-        if detail is not None:
-            H.vkph_set_detail(*detail)
         self._H = H
-        self._h = H.vkph_scene_create(index)
+        self.detail = None if detail is None else tuple(int(x) for x in detail)
+        self._h = H.vkph_scene_create(index, _detail4(detail))
         if not self._h:
             raise VkpError(H.vkph_last_error().decode())
         self.index = index
@@ -219,11 +223,10 @@ class HostScene:
     def from_prefab(cls, path, detail=None):
         """Scene::create_viewer_scene: the default scene's floor, lights and camera around one .obj / .gltf / .glb file."""
         H = load_host()
-        if detail is not None:
-            H.vkph_set_detail(*detail)
         self = cls.__new__(cls)
         self._H = H
-        self._h = H.vkph_scene_create_prefab(str(path).encode())
+        self.detail = None if detail is None else tuple(int(x) for x in detail)
+        self._h = H.vkph_scene_create_prefab(str(path).encode(), _detail4(detail))
         if not self._h:
             raise VkpError(H.vkph_last_error().decode())
         self.index = -1
@@ -544,11 +547,9 @@ class HostEngine:
 
     def __init__(self, scene_index=0, width=1700, height=900, device=0, detail=None):
         H = load_host()
-        if detail is not None:
-            H.vkph_set_detail(*detail)
         self._H = H
         self.width, self.height = width, height
-        self._h = H.vkph_engine_create(scene_index, width, height, device)
+        self._h = H.vkph_engine_create(scene_index, width, height, device, _detail4(detail))
         if not self._h:
             raise VkpError(H.vkph_last_error().decode())
 

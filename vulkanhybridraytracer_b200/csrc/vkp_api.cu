@@ -376,9 +376,10 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
         const unsigned long long max_block = (unsigned long long)(F.n_cta > 0 ? F.n_cta : 1) * n_lights, max_tile = (unsigned long long)total + (unsigned long long)F.world;
         F.magic_bpt = magic(bpt); F.magic_tiles_x = magic((unsigned long long)F.tiles_x); F.magic_bpt_x = magic(bpt_x);
         F.magic_n_cta = magic((unsigned long long)F.n_cta);
-        const unsigned long long lim = 1ull << 40;
-        F.div_exact = (max_block * bpt < lim && max_tile * (unsigned long long)F.tiles_x < lim && bpt * bpt_x < lim &&
-                       max_block * (unsigned long long)(F.n_cta > 0 ? F.n_cta : 1) < lim) ? 1 : 0;
+        // exact while n * d < 2^40; the 64-bit product n * magic must not wrap either: n < 2^24 * d
+        auto ok = [](unsigned long long n, unsigned long long d) { return n * d < (1ull << 40) && n < (d << 24); };
+        F.div_exact = (ok(max_block, bpt) && ok(max_tile, (unsigned long long)F.tiles_x) && ok(bpt, bpt_x) &&
+                       ok(max_block, (unsigned long long)(F.n_cta > 0 ? F.n_cta : 1))) ? 1 : 0;
     }
     for (int k = 0; k < 2; k++) {
         const uint32_t n = (uint32_t)F.n_cta * (k ? (uint32_t)L.scene.n_lights : 1u);
@@ -715,6 +716,17 @@ int vkp_build_tlas(vkp_ctx* ctx, int update)
         int launches = 0;
         CK(bvh_build(ctx->stream, ctx->tlas_scratch, (uint32_t)n, 1, ctx->tlas, &launches, 0));
         CK(cudaStreamSynchronize(ctx->stream));
+        {
+            // the per-thread traversal stack holds the sentinel, the TLAS part, the return marker and the deepest BLAS part
+            int blas_h = 0;
+            for (auto& b : ctx->blas) blas_h = b->bvh.height > blas_h ? b->bvh.height : blas_h;
+            const int need = VKP_WIDE ? 3 * ((blas_h + 1) / 2 + (ctx->tlas.height + 1) / 2 + 2) + 2 : ctx->tlas.height + blas_h + 3;
+            if (need > VKP_TRAV_STACK) {
+                char msg[200]; snprintf(msg, sizeof msg, "TLAS height %d + BLAS height %d exceed the traversal stack budget (%d entries)", ctx->tlas.height, blas_h, VKP_TRAV_STACK);
+                ctx->tlas_topology = false;
+                return fail(ctx, VKP_ERR_INVALID, msg);
+            }
+        }
         ctx->tlas_topology = true;
         for (auto& u : ctx->uni) { u.consumed = false; u.inst_ver = 0; }
     }

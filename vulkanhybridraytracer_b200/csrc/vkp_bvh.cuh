@@ -269,8 +269,8 @@ VKP_TRACE_FN bool trace_ray(const DScene& S, float3 o, float3 d, float tmin, flo
             const float4* rec = reinterpret_cast<const float4*>(S.inst_trav + inst);
             const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), pp = __ldg(rec + 3), rr = __ldg(rec + 4);
             // xform_point / xform_dir with the rows of inverse(model): same association as the contract
-            ro = f3(((r0.x * o.x + r0.y * o.y) + r0.z * o.z) + r0.w, ((r1.x * o.x + r1.y * o.y) + r1.z * o.z) + r1.w, ((r2.x * o.x + r2.y * o.y) + r2.z * o.z) + r2.w);
-            rd = f3((r0.x * d.x + r0.y * d.y) + r0.z * d.z, (r1.x * d.x + r1.y * d.y) + r1.z * d.z, (r2.x * d.x + r2.y * d.y) + r2.z * d.z);
+            ro = f3(vkp_row_point(r0.x, r0.y, r0.z, r0.w, o.x, o.y, o.z), vkp_row_point(r1.x, r1.y, r1.z, r1.w, o.x, o.y, o.z), vkp_row_point(r2.x, r2.y, r2.z, r2.w, o.x, o.y, o.z));
+            rd = f3(vkp_dot3(r0.x, r0.y, r0.z, d.x, d.y, d.z), vkp_dot3(r1.x, r1.y, r1.z, d.x, d.y, d.z), vkp_dot3(r2.x, r2.y, r2.z, d.x, d.y, d.z));
             inv = safe_inv_dir(rd);
             par = has_parallel_axis(rd);
 #if !VKP_WIDE
@@ -364,8 +364,8 @@ static __device__ __forceinline__ bool warp_any_hit(const DScene& S, float3 o, f
                 else {
                     const float4* rec = reinterpret_cast<const float4*>(S.inst_trav + cinst);
                     const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), pp = __ldg(rec + 3), rr = __ldg(rec + 4);
-                    ro = f3(((r0.x * o.x + r0.y * o.y) + r0.z * o.z) + r0.w, ((r1.x * o.x + r1.y * o.y) + r1.z * o.z) + r1.w, ((r2.x * o.x + r2.y * o.y) + r2.z * o.z) + r2.w);
-                    rd = f3((r0.x * d.x + r0.y * d.y) + r0.z * d.z, (r1.x * d.x + r1.y * d.y) + r1.z * d.z, (r2.x * d.x + r2.y * d.y) + r2.z * d.z);
+                    ro = f3(vkp_row_point(r0.x, r0.y, r0.z, r0.w, o.x, o.y, o.z), vkp_row_point(r1.x, r1.y, r1.z, r1.w, o.x, o.y, o.z), vkp_row_point(r2.x, r2.y, r2.z, r2.w, o.x, o.y, o.z));
+                    rd = f3(vkp_dot3(r0.x, r0.y, r0.z, d.x, d.y, d.z), vkp_dot3(r1.x, r1.y, r1.z, d.x, d.y, d.z), vkp_dot3(r2.x, r2.y, r2.z, d.x, d.y, d.z));
                     inv = safe_inv_dir(rd);
                     par = has_parallel_axis(rd);
                     tris = reinterpret_cast<const float4*>(((unsigned long long)__float_as_uint(pp.w) << 32) | (unsigned long long)__float_as_uint(pp.z));
@@ -380,7 +380,13 @@ static __device__ __forceinline__ bool warp_any_hit(const DScene& S, float3 o, f
                 const bool h0 = box_test(lo0, hi0, ro, rd, inv, par, tmin, tmax, t0);
                 const bool h1 = box_test(lo1, hi1, ro, rd, inv, par, tmin, tmax, t1);
                 const uint32_t r0 = __float_as_uint(lo0.w), r1 = __float_as_uint(lo1.w);
-                if (h0 && h1) { stack[sp++] = make_uint2(r1, (unsigned int)cinst); cur = r0; }
+                if (h0 && h1) {
+                    if (sp == VKP_TRAV_STACK) {      // the window [base, sp) only moves up while items are given away: slide it back down
+                        for (int k = base; k < sp; k++) stack[k - base] = stack[k];
+                        sp -= base; base = 0;
+                    }
+                    stack[sp++] = make_uint2(r1, (unsigned int)cinst); cur = r0;
+                }
                 else if (h0) cur = r0;
                 else if (h1) cur = r1;
                 else has = false;

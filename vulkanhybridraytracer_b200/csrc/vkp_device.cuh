@@ -3,7 +3,8 @@
 // Numerics contract (DESIGN.md "Numerics"): all translation units are compiled with -fmad=false, IEEE
 // div/sqrt (nvcc defaults), and every expression below keeps the left-to-right order of the GLSL source
 // it implements, so results are bit-identical to a scalar fp32 evaluation of the same shader.  FMA is
-// only used explicitly (__fmaf_rn) where the result cannot change an output (conservative box tests).
+// only used where it is written: the contract-v2 primitives of include/vkp_detmath.h (dot, cross, matrix
+// rows, mix, reflect / refract -- the CPU checker calls the same functions) and the conservative box tests.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -26,51 +27,56 @@ VKP_D float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s)
 VKP_D float3 operator+(float3 a, float s) { return f3(a.x + s, a.y + s, a.z + s); }
 VKP_D float3 operator-(float s, float3 a) { return f3(s - a.x, s - a.y, s - a.z); }
 VKP_D float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
-VKP_D float dot3(float3 a, float3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
-VKP_D float3 cross3(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+// contract v2: dot / cross / matrix rows / mix are the FMA forms of include/vkp_detmath.h, shared with the CPU checker
+VKP_D float dot3(float3 a, float3 b) { return vkp_dot3(a.x, a.y, a.z, b.x, b.y, b.z); }
+VKP_D float3 cross3(float3 a, float3 b)
+{
+    return f3(vkp_diff_of_products(a.y, b.z, a.z, b.y), vkp_diff_of_products(a.z, b.x, a.x, b.z), vkp_diff_of_products(a.x, b.y, a.y, b.x));
+}
 VKP_D float length3(float3 a) { return sqrtf(dot3(a, a)); }
 VKP_D float3 normalize3(float3 a) { float inv = 1.0f / sqrtf(dot3(a, a)); return a * inv; }
 VKP_D float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
-VKP_D float mix1(float x, float y, float a) { return x * (1.0f - a) + y * a; }
-VKP_D float3 mix3(float3 x, float3 y, float a) { return x * (1.0f - a) + y * a; }
+VKP_D float mix1(float x, float y, float a) { return vkp_mixf(x, y, a); }
+VKP_D float3 mix3(float3 x, float3 y, float a) { return f3(vkp_mixf(x.x, y.x, a), vkp_mixf(x.y, y.y, a), vkp_mixf(x.z, y.z, a)); }
 VKP_D float3 pow3(float3 a, float e) { return f3(vkp_powf(a.x, e), vkp_powf(a.y, e), vkp_powf(a.z, e)); }
-VKP_D float3 reflect3(float3 I, float3 N) { return I - N * (2.0f * dot3(N, I)); }
+VKP_D float3 reflect3(float3 I, float3 N) { const float k = 2.0f * dot3(N, I); return f3(vkp_nmsubf(N.x, k, I.x), vkp_nmsubf(N.y, k, I.y), vkp_nmsubf(N.z, k, I.z)); }
 VKP_D float3 refract3(float3 I, float3 N, float eta)
 {
     float d = dot3(N, I);
-    float k = 1.0f - (eta * eta) * (1.0f - d * d);
+    float k = vkp_nmsubf(eta * eta, vkp_nmsubf(d, d, 1.0f), 1.0f);
     if (k < 0.0f) return f3s(0.0f);
-    return I * eta - N * (eta * d + sqrtf(k));
+    const float s = vkp_fmaf(eta, d, sqrtf(k));
+    return f3(vkp_nmsubf(N.x, s, I.x * eta), vkp_nmsubf(N.y, s, I.y * eta), vkp_nmsubf(N.z, s, I.z * eta));
 }
 
 // column-major 4x4 (m[c*4+r]) applied to points / directions; same association as the oracle
 VKP_D float3 xform_point(const float* __restrict__ m, float3 p)
 {
-    return f3(((m[0] * p.x + m[4] * p.y) + m[8] * p.z) + m[12],
-              ((m[1] * p.x + m[5] * p.y) + m[9] * p.z) + m[13],
-              ((m[2] * p.x + m[6] * p.y) + m[10] * p.z) + m[14]);
+    return f3(vkp_row_point(m[0], m[4], m[8], m[12], p.x, p.y, p.z),
+              vkp_row_point(m[1], m[5], m[9], m[13], p.x, p.y, p.z),
+              vkp_row_point(m[2], m[6], m[10], m[14], p.x, p.y, p.z));
 }
 VKP_D float3 xform_dir(const float* __restrict__ m, float3 d)
 {
-    return f3((m[0] * d.x + m[4] * d.y) + m[8] * d.z,
-              (m[1] * d.x + m[5] * d.y) + m[9] * d.z,
-              (m[2] * d.x + m[6] * d.y) + m[10] * d.z);
+    return f3(vkp_dot3(m[0], m[4], m[8], d.x, d.y, d.z),
+              vkp_dot3(m[1], m[5], m[9], d.x, d.y, d.z),
+              vkp_dot3(m[2], m[6], m[10], d.x, d.y, d.z));
 }
 VKP_D float4 xform_vec4(const float* __restrict__ m, float4 v)
 {
     float4 r;
-    r.x = ((m[0] * v.x + m[4] * v.y) + m[8] * v.z) + m[12] * v.w;
-    r.y = ((m[1] * v.x + m[5] * v.y) + m[9] * v.z) + m[13] * v.w;
-    r.z = ((m[2] * v.x + m[6] * v.y) + m[10] * v.z) + m[14] * v.w;
-    r.w = ((m[3] * v.x + m[7] * v.y) + m[11] * v.z) + m[15] * v.w;
+    r.x = vkp_row_vec4(m[0], m[4], m[8], m[12], v.x, v.y, v.z, v.w);
+    r.y = vkp_row_vec4(m[1], m[5], m[9], m[13], v.x, v.y, v.z, v.w);
+    r.z = vkp_row_vec4(m[2], m[6], m[10], m[14], v.x, v.y, v.z, v.w);
+    r.w = vkp_row_vec4(m[3], m[7], m[11], m[15], v.x, v.y, v.z, v.w);
     return r;
 }
 // mat3(transpose(M)) * n
 VKP_D float3 xform_normal_by_inverse(const float* __restrict__ inv, float3 n)
 {
-    return f3((inv[0] * n.x + inv[1] * n.y) + inv[2] * n.z,
-              (inv[4] * n.x + inv[5] * n.y) + inv[6] * n.z,
-              (inv[8] * n.x + inv[9] * n.y) + inv[10] * n.z);
+    return f3(vkp_dot3(inv[0], inv[1], inv[2], n.x, n.y, n.z),
+              vkp_dot3(inv[4], inv[5], inv[6], n.x, n.y, n.z),
+              vkp_dot3(inv[8], inv[9], inv[10], n.x, n.y, n.z));
 }
 
 // ---- RNG: random.glsl:3-33 ---------------------------------------------------------------------------------

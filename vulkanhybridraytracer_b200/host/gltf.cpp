@@ -121,6 +121,14 @@ int type_components(const std::string& t)
     return 0;
 }
 
+// a JSON number used as a byte offset / count: a non-negative integer below 2^53, anything else is a malformed file
+size_t json_size(const Model& M, const Value& obj, const char* key, double dflt = 0)
+{
+    const double d = obj.get_num(key, dflt);
+    if (!(d >= 0.0) || d > 9007199254740992.0 || d != std::floor(d)) gfail(M, std::string(key) + " is not a non-negative integer");
+    return (size_t)d;
+}
+
 // accessor -> bufferView -> buffer, like vk_mesh.cpp:676-679 (data + accessor.byteOffset + view.byteOffset), bounds-checked
 View accessor_view(const Model& M, int index)
 {
@@ -134,18 +142,29 @@ View accessor_view(const Model& M, int index)
     View v;
     v.componentType = acc.get_int("componentType", 0);
     v.ncomp = type_components(acc.get_str("type"));
-    v.count = (size_t)acc.get_num("count", 0);
+    v.count = json_size(M, acc, "count");
     const Value* nrm = acc.find("normalized");
     v.normalized = nrm && nrm->type == Value::Bool && nrm->boolean;
     const int csz = component_size(v.componentType);
     if (csz == 0 || v.ncomp == 0) gfail(M, "accessor with unknown component type / type");
     const size_t elem = (size_t)csz * v.ncomp;
-    const size_t byteStride = (size_t)view.get_num("byteStride", 0);
+    const size_t byteStride = json_size(M, view, "byteStride");
     v.stride = byteStride ? byteStride : elem;
-    const size_t off = (size_t)acc.get_num("byteOffset", 0) + (size_t)view.get_num("byteOffset", 0);
     const std::vector<uint8_t>& B = M.buffers[(size_t)buf];
-    if (v.count && off + v.stride * (v.count - 1) + elem > B.size()) gfail(M, "accessor reaches past the end of its buffer");
-    v.data = B.data() + off;
+    // the accessor must lie inside its bufferView, the bufferView inside its buffer; every comparison is written so that it cannot wrap
+    const size_t view_off = json_size(M, view, "byteOffset"), acc_off = json_size(M, acc, "byteOffset");
+    if (view_off > B.size()) gfail(M, "bufferView starts past the end of its buffer");
+    size_t view_len = B.size() - view_off;
+    if (view.find("byteLength")) {
+        const size_t bl = json_size(M, view, "byteLength");
+        if (bl > view_len) gfail(M, "bufferView reaches past the end of its buffer");
+        view_len = bl;
+    }
+    if (v.count) {
+        if (acc_off > view_len || elem > view_len - acc_off) gfail(M, "accessor reaches past the end of its bufferView");
+        if (v.count - 1 > (view_len - acc_off - elem) / v.stride) gfail(M, "accessor reaches past the end of its bufferView");
+    }
+    v.data = B.data() + view_off + acc_off;
     return v;
 }
 
@@ -217,8 +236,8 @@ int register_image(const Model& M, int imageIndex)
         const Value& view = element(M, "bufferViews", bv);
         const int buf = view.get_int("buffer", -1);
         if (buf < 0 || (size_t)buf >= M.buffers.size()) gfail(M, "image bufferView names a missing buffer");
-        const size_t off = (size_t)view.get_num("byteOffset", 0), len = (size_t)view.get_num("byteLength", 0);
-        if (off + len > M.buffers[(size_t)buf].size()) gfail(M, "image bufferView reaches past the end of its buffer");
+        const size_t off = json_size(M, view, "byteOffset"), len = json_size(M, view, "byteLength");
+        if (off > M.buffers[(size_t)buf].size() || len > M.buffers[(size_t)buf].size() - off) gfail(M, "image bufferView reaches past the end of its buffer");
         if (!imgdec::decode_rgba8(M.buffers[(size_t)buf].data() + off, len, w, h, rgba, &err)) gfail(M, "image " + std::to_string(imageIndex) + ": " + err);
     }
     return Texture::add(key.c_str(), w, h, std::move(rgba));

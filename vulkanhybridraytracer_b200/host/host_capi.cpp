@@ -21,12 +21,27 @@ extern "C" {
 
 VKPH_API const char* vkph_last_error(void) { return g_err.c_str(); }
 
-VKPH_API void* vkph_scene_create(int index)
+// detail4 = {lucy subdivisions, helmet subdivisions, stress-blob subdivisions, stress instances}; NULL = the full-size scene.
+// Negative / zero entries keep the full-size default of that entry.
+static MeshDetail detail_of(const int* d)
+{
+    MeshDetail m;
+    if (d) {
+        if (d[0] >= 0) m.lucy_subdiv = d[0];
+        if (d[1] >= 0) m.helmet_subdiv = d[1];
+        if (d[2] >= 0) m.stress_subdiv = d[2];
+        if (d[3] > 0) m.stress_instances = d[3];
+    }
+    return m;
+}
+
+VKPH_API void* vkph_scene_create(int index, const int* detail4)
 {
     try {
         Scene::reset_registries();
         vkph_scene* s = new vkph_scene();
         s->scene = new Scene();
+        s->scene->_detail = detail_of(detail4);
         s->scene->create_scene(index);
         s->buffers = build_scene_buffers(s->scene);
         return s;
@@ -34,12 +49,13 @@ VKPH_API void* vkph_scene_create(int index)
 }
 
 // floor + lights + camera of the default scene around one asset file (.obj / .gltf / .glb): Scene::create_viewer_scene
-VKPH_API void* vkph_scene_create_prefab(const char* file)
+VKPH_API void* vkph_scene_create_prefab(const char* file, const int* detail4)
 {
     try {
         Scene::reset_registries();
         vkph_scene* s = new vkph_scene();
         s->scene = new Scene();
+        s->scene->_detail = detail_of(detail4);
         s->scene->create_viewer_scene(file);
         s->buffers = build_scene_buffers(s->scene);
         return s;
@@ -118,10 +134,11 @@ VKPH_API int vkph_scene_set_entity_matrix(void* p, int entity, const float m[16]
 }
 
 // ---- engine --------------------------------------------------------------------------------------------------
-VKPH_API void* vkph_engine_create(int scene_index, int width, int height, int device)
+VKPH_API void* vkph_engine_create(int scene_index, int width, int height, int device, const int* detail4)
 {
     VulkanEngine* e = new VulkanEngine();
     try {
+        e->_detail = detail_of(detail4);
         e->_sceneIndex = scene_index; e->_width = width; e->_height = height; e->_device = device;
         e->init();
         return e;

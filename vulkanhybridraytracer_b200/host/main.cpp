@@ -1,7 +1,7 @@
 // main.cpp -- headless replacement of src/main.cpp + window.cpp: VulkanEngine engine; init(); run(); cleanup();
 //   vkpinut [--scene N] [--mode deferred|raytracing|hybrid] [--width W --height H] [--frames F] [--samples S]
 //           [--spp N] [--device D] [--png out.png] [--exr out.exr] [--prefab model.obj|.gltf|.glb]
-//           [--walk DIR:DT[,DIR:DT...]] [--turn DX:DY] [--sequence prefix] [--reproject-fix]
+//           [--walk DIR:DT[,DIR:DT...]] [--turn DX:DY] [--sequence prefix] [--reproject-fix] [--detail a,b,c,d]
 // --walk / --turn replay key presses and mouse motion every frame (DIR = forward|backward|left|right|up|down, DT in ms as in
 // Camera::processKeyboard; DX, DY in pixels as in Camera::rotate): a moving-camera sequence.  --sequence writes prefix_%04d.png per frame.
 // Assets (sphere.obj, lucy.obj, DamagedHelmet.gltf + textures, the sky .jpg / .hdr) are picked up from the reference's
@@ -34,6 +34,10 @@ int main(int argc, char** argv)
         else if (a == "--spp") engine._spp = std::atoi(next());
         else if (a == "--device") engine._device = std::atoi(next());
         else if (a == "--prefab") engine._prefabFile = next();
+        else if (a == "--detail") {      // tessellation of the procedural stand-ins: lucy,helmet,stress,instances (default 7,5,7,31)
+            MeshDetail& d = engine._detail;
+            if (std::sscanf(next(), "%d,%d,%d,%d", &d.lucy_subdiv, &d.helmet_subdiv, &d.stress_subdiv, &d.stress_instances) != 4) { std::fprintf(stderr, "--detail wants a,b,c,d\n"); return 2; }
+        }
         else if (a == "--sequence") sequence = next();
         else if (a == "--reproject-fix") engine._reprojectFix = true;
         else if (a == "--turn") { if (std::sscanf(next(), "%f:%f", &turn_x, &turn_y) != 2) { std::fprintf(stderr, "--turn wants DX:DY\n"); return 2; } }

@@ -136,6 +136,7 @@ void VulkanEngine::init()
     engine = this;
     Scene::reset_registries();
     _scene = new Scene();
+    _scene->_detail = _detail;
     if (!_prefabFile.empty()) _scene->create_viewer_scene(_prefabFile);
     else _scene->create_scene(_sceneIndex);
     renderer = new Renderer(_scene);

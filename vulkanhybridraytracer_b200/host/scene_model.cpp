@@ -135,14 +135,9 @@ int Texture::get_id(const char* filename)
 // ---- Mesh (src/vk_mesh.cpp:72-263) ---------------------------------------------------------------------
 std::unordered_map<std::string, Mesh*> Mesh::_loadedMeshes;
 
-static int g_lucy_subdiv = 7, g_helmet_subdiv = 5, g_stress_subdiv = 7, g_stress_instances = 31;
-extern "C" void vkph_set_detail(int lucy_subdiv, int helmet_subdiv, int stress_subdiv, int stress_instances)
-{
-    if (lucy_subdiv >= 0) g_lucy_subdiv = lucy_subdiv;
-    if (helmet_subdiv >= 0) g_helmet_subdiv = helmet_subdiv;
-    if (stress_subdiv >= 0) g_stress_subdiv = stress_subdiv;
-    if (stress_instances > 0) g_stress_instances = stress_instances;
-}
+// detail of the scene under construction: Scene::create_scene / create_viewer_scene copy their own _detail here first, so a mesh
+// generated for one scene can never inherit the tessellation an earlier scene (or test) asked for
+static thread_local MeshDetail g_detail;
 
 static std::string find_file(const std::string& filename);
 static std::string base_name(const std::string& p)
@@ -175,9 +170,9 @@ Mesh* Mesh::GET(const char* filename)
     if (!path.empty() && name.find(".obj") != std::string::npos) ok = mesh->load_from_obj(path.c_str());
     if (!ok) {
         if (name == "sphere.obj") proc::uv_sphere(64, 32, mesh->_vertices, mesh->_indices);
-        else if (name == "lucy.obj") proc::lucy_standin(mesh->_vertices, mesh->_indices, g_lucy_subdiv);
-        else if (name == "DamagedHelmet.gltf") proc::helmet_standin(mesh->_vertices, mesh->_indices, g_helmet_subdiv);
-        else if (name == "stress_blob") proc::displaced_icosphere(mesh->_vertices, mesh->_indices, g_stress_subdiv, 1234u, 0.35f);
+        else if (name == "lucy.obj") proc::lucy_standin(mesh->_vertices, mesh->_indices, g_detail.lucy_subdiv);
+        else if (name == "DamagedHelmet.gltf") proc::helmet_standin(mesh->_vertices, mesh->_indices, g_detail.helmet_subdiv);
+        else if (name == "stress_blob") proc::displaced_icosphere(mesh->_vertices, mesh->_indices, g_detail.stress_subdiv, 1234u, 0.35f);
         else { delete mesh; return nullptr; }
     }
     _loadedMeshes[name] = mesh;
@@ -447,6 +442,7 @@ unsigned int Scene::get_drawable_nodes_size()
 
 void Scene::create_scene(int i)
 {
+    g_detail = _detail;
     switch (i) {
     case 0: default_scene(); break;
     case 1: cornell_scene(); break;
@@ -486,6 +482,7 @@ static Object* make_object(Prefab* prefab, const glm::mat4& m)
 // Not in the reference: its default lights, floor and camera around one asset file, for the headless CLI (--prefab)
 void Scene::create_viewer_scene(const std::string& prefabFile)
 {
+    g_detail = _detail;
     _camera = new Camera(glm::vec3(0, 5, 10));
     Light* a = new Light(); a->m_matrix = glm::translate(glm::mat4(1), glm::vec3(10, 12, -5)); a->color = glm::vec3{1.0f, 0.8f, 0.5f}; a->intensity = 500.0f; a->radius = 0.1f;
     Light* b = new Light(); b->m_matrix = glm::translate(glm::mat4(1), glm::vec3(-10, 15, -5)); b->color = glm::vec3{0.5f, 1.0f, 1.0f}; b->intensity = 250.0f; b->radius = 0.2f;
@@ -610,7 +607,7 @@ void Scene::stress_scene()
     Mesh* blob = Mesh::GET("stress_blob");
     uint32_t rng = 1234u;
     auto rnd01 = [&rng]() { rng = 1664525u * rng + 1013904223u; return (float)(rng >> 8) / 16777216.0f; };
-    const int n = g_stress_instances;
+    const int n = g_detail.stress_instances;
     int cols = 1; while (cols * cols < n) cols++;
     for (int i = 0; i < n; i++) {
         Prefab* p = Prefab::GET("blob" + std::to_string(i), blob);
