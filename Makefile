@@ -1,6 +1,7 @@
 # Builds everything in-tree (the .so files travel to the GPU box with the gpurun snapshot):
 #   vulkanhybridraytracer_b200/lib/libvkp.so       CUDA kernels + C-ABI (include/vkp.h), sm_100a only
-#   vulkanhybridraytracer_b200/lib/libvkp_host.so  host C++ mirror of the reference API + C shim
+#   vulkanhybridraytracer_b200/lib/libvkp_scene.so host scene model (Scene / Prefab / Mesh / Material / Camera, OBJ / glTF / image readers): no CUDA
+#   vulkanhybridraytracer_b200/lib/libvkp_host.so  host Renderer / VulkanEngine over libvkp + C shim
 #   vulkanhybridraytracer_b200/bin/vkpinut         headless CLI (replaces src/main.cpp + window.cpp)
 #   oracle/liboracle*.so                           CPU oracle (test infrastructure)
 ROOT   := $(dir $(abspath $(lastword $(MAKEFILE_LIST))))
@@ -23,12 +24,13 @@ CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-unused-variable -fwrapv
 CU_SRCS := $(CSRC)/vkp_api.cu $(CSRC)/bvh_build.cu $(CSRC)/kernels_frame.cu
 CU_OBJS := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
 CU_HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard $(ROOT)include/*.h)
-HOST_SRCS := $(HOST)/scene_model.cpp $(HOST)/procedural.cpp $(HOST)/renderer.cpp $(HOST)/output.cpp $(HOST)/image_decode.cpp $(HOST)/gltf.cpp $(HOST)/host_capi.cpp
+SCENE_SRCS := $(HOST)/scene_model.cpp $(HOST)/procedural.cpp $(HOST)/output.cpp $(HOST)/image_decode.cpp $(HOST)/gltf.cpp $(HOST)/scene_capi.cpp
+HOST_SRCS := $(HOST)/renderer.cpp $(HOST)/host_capi.cpp
 HOST_HDRS := $(wildcard $(HOST)/*.h) $(wildcard $(ROOT)include/*.h)
 
 all: libvkp host oracle
 libvkp: $(LIBDIR)/libvkp.so
-host: $(LIBDIR)/libvkp_host.so $(BINDIR)/vkpinut
+host: $(LIBDIR)/libvkp_scene.so $(LIBDIR)/libvkp_host.so $(BINDIR)/vkpinut
 oracle:
 	$(MAKE) -C $(ROOT)oracle
 
@@ -40,12 +42,16 @@ $(LIBDIR)/libvkp.so: $(CU_OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared --cudart static -ccbin $(CXX) -o $@ $(CU_OBJS) -lpthread -ldl -lrt
 
-$(LIBDIR)/libvkp_host.so: $(HOST_SRCS) $(HOST_HDRS) $(LIBDIR)/libvkp.so
-	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) -L$(LIBDIR) -lvkp -lz -Wl,-rpath,'$$ORIGIN'
+$(LIBDIR)/libvkp_scene.so: $(SCENE_SRCS) $(HOST_HDRS)
+	@mkdir -p $(LIBDIR)
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(SCENE_SRCS) -lz
+
+$(LIBDIR)/libvkp_host.so: $(HOST_SRCS) $(HOST_HDRS) $(LIBDIR)/libvkp.so $(LIBDIR)/libvkp_scene.so
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) -L$(LIBDIR) -lvkp_scene -lvkp -Wl,-rpath,'$$ORIGIN'
 
 $(BINDIR)/vkpinut: $(HOST)/main.cpp $(LIBDIR)/libvkp_host.so
 	@mkdir -p $(BINDIR)
-	$(CXX) $(CXXFLAGS) -o $@ $(HOST)/main.cpp -L$(LIBDIR) -lvkp_host -lvkp -Wl,-rpath,'$$ORIGIN/../lib'
+	$(CXX) $(CXXFLAGS) -o $@ $(HOST)/main.cpp -L$(LIBDIR) -lvkp_host -lvkp_scene -lvkp -Wl,-rpath,'$$ORIGIN/../lib'
 
 sass: $(LIBDIR)/libvkp.so
 	@mkdir -p $(ROOT)profiles

@@ -1,25 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- Mrays/s and ms/frame of the Hybrid pipeline hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3|cfg4|cfg5]
 
 One "step" = one frame of the hot path (Renderer::rasterize_hybrid: G-buffer -> shadow rays -> denoise -> resolve +
 reflection rays) on the default scene at 1920x1080 with a static camera, frame index advancing (temporal accumulation),
 i.e. BASELINE.json configs[1].  Rays counted are the traceRayEXT calls the reference would issue (shadow + reflection +
 secondary shadow); our own primary-visibility rays are reported separately and NOT counted.
 
-N > 1 (torchrun, one rank per GPU): the frame is tile-sharded over a replicated BVH (tile t -> rank t % N) and the
-finished sRGB8 tiles are gathered to rank 0 over NCCL -- the only collective; "scaling": "strong".
+N > 1 (torchrun, one rank per GPU): the frame is tile-sharded over a replicated BVH and the finished sRGB8 pixels are stored
+straight into rank 0's image over NVLink peer memory -- the composite is the only exchange; "scaling": "strong".
 
-Prints ONE JSON line (rank 0) with the contract keys plus "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches".
-The CPU oracle (oracle/) is used only for the cpu_baseline leg and for --impl reference; it is never on the GPU path.
+Prints ONE JSON line (rank 0) with the contract keys plus "roofline", "cpu_baseline", "parity", "e2e", "clocks", "gpu_launches",
+"frame_ms", "build", "cfg3".  `config` is the static description of the workload (identical in both arms); everything measured
+lives outside it.  The CPU oracle (oracle/) is used only for the parity / cpu_baseline leg and for --impl reference; it is never
+on the GPU path.  A parity result below north_star's bar makes the run fail (exit code 1) after the line is printed.
 """
 import argparse
+import glob
 import json
 import math
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -36,10 +40,20 @@ WORKLOADS = {
     "cfg4": (2, 3840, 2160, 2, 1, 1, 1, "instanced stress scene (~10M instanced triangles), Hybrid 3840x2160"),
     "cfg5": (3, 3840, 2160, 2, 1, 16, 0, "default scene, 16 ring lights x 16 shadow samples, Hybrid 3840x2160"),
 }
+METRIC = "Mrays/s (Hybrid 1080p hot path: shadow + reflection + secondary-shadow rays per second)"
+
+
+def workload_config(name, scene):
+    """The static description of the workload: the same dict in the GPU arm and in the reference arm."""
+    scene_idx, W, H, mode, spp, samples, faithful, desc = WORKLOADS[name]
+    return {"workload": f"{name}: {desc}", "scene": scene_idx, "width": W, "height": H, "mode": {0: "deferred", 1: "raytraced", 2: "hybrid"}[mode],
+            "spp": spp, "shadow_samples": samples, "max_bounces": 8, "rng": "faithful (seed by value)" if faithful else "advancing",
+            "triangles": scene.n_triangles, "instances": int(len(scene.instances)), "lights": int(len(scene.lights)), "pixels": W * H}
 
 
 def b_ray(T):
-    """algorithmic bytes per traced ray for a BVH over T triangles."""
+    """bytes a ray would request on a root-to-leaf walk of a BVH over T triangles (32-B nodes, both children
+    inspected per level, 4 leaf triangles, one instance record).  A *request* model: almost all of it is served by L1 / L2."""
     return 32 + 16 + 32 * (1 + 2 * math.ceil(math.log2(max(T, 4) / 4))) + 4 * 36
 
 
@@ -47,10 +61,17 @@ def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy figure)"
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 class ClockSampler:
@@ -87,11 +108,22 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_leg(scene, W, H, mode, spp, samples, faithful, budget_s, steps, warmup, grow_steps=False):
-    """Times the CPU oracle (the reference's shader math on host cores) on a bounded row sample of the workload."""
+def stats_ms(xs):
+    xs = np.asarray(xs, dtype=np.float64)
+    if xs.size == 0:
+        return None
+    return {"min": float(xs.min()), "median": float(np.median(xs)), "max": float(xs.max()), "mean": float(xs.mean()), "n": int(xs.size)}
+
+
+# ------------------------------------------------------------------------------------------------ the CPU oracle, timed ----
+def oracle_steps(scene, name, steps, warmup, budget_s):
+    """--impl reference: the oracle on all host cores, K timed steps after W warm-up steps, each step a bounded sample of the
+    workload (every stride-th row of the frame, stride chosen so that the whole run fits budget_s)."""
     import vulkanhybridraytracer_b200 as vk
     from oracle.oracle_py import Oracle
-    o = Oracle(scene)
+    scene_idx, W, H, mode, spp, samples, faithful, desc = WORKLOADS[name]
+    cores = host_threads()
+    o = Oracle(scene, threads=cores)      # orc_set_num_threads: torchrun exports OMP_NUM_THREADS=1, the oracle must not inherit that
     cores = o.threads()
     cam = scene.camera(W, H)
 
@@ -108,27 +140,108 @@ def oracle_leg(scene, W, H, mode, spp, samples, faithful, budget_s, steps, warmu
         c = list(o.counters.rays)
         return dt, c[1] + c[2] + c[3], c[0]
 
-    # calibrate on a sparse sample, then pick the row stride so that (steps + warmup) samples fit the budget
     stride = 16 if mode == 2 else 270
     one(1, stride)                                  # first touch (page faults, OpenMP team start-up)
     dt, _, _ = one(1, stride)
-    per_row = dt / max(1, H // stride)
-    rows = max(8, min(H, int(budget_s / max(1, steps + warmup) / max(per_row, 1e-9))))
+    per_row = dt / max(1, len(range(stride // 2, H, stride)))
+    rows = max(4, min(H, int(budget_s / max(1, steps + warmup) / max(per_row, 1e-9))))
     stride = max(1, H // rows)
-    if grow_steps and stride == 1:
-        # fast host: whole frames fit the budget -- spend it on more frames so the sample is 10-30 s of CPU work
-        steps = int(min(200, max(steps, budget_s / max(per_row * H, 1e-9) - warmup)))
     for w in range(warmup):
         one(1 + w, stride)
-    tot_t, tot_rays = 0.0, 0
+    times, tot_rays = [], 0
     for k in range(steps):
         dt, rays, _ = one(1 + warmup + k, stride)
-        tot_t += dt; tot_rays += rays
+        times.append(dt); tot_rays += rays
     o.set_row_sampling(1, 0)
     o.close()
     rows = len(range(stride // 2, H, stride))
-    return {"mrays_s": tot_rays / tot_t / 1e6, "ms_per_frame_est": tot_t / steps * 1e3 * (H / rows), "cores": cores,
-            "sample": f"{steps} steps x every {stride}th row ({rows} of {H} rows) of the {W}x{H} frame, {tot_t:.1f} s of CPU time", "seconds": tot_t}
+    tot_t = float(sum(times))
+    return {"mrays_s": tot_rays / tot_t / 1e6, "ms_per_frame_est": tot_t / steps * 1e3 * (H / rows), "cores": cores, "step_ms": stats_ms(np.array(times) * 1e3),
+            "sample": f"{steps} steps x every {stride}th row ({rows} of {H} rows) of the {W}x{H} frame, {tot_t:.1f} s wall on {cores} threads", "seconds": tot_t}
+
+
+def parity_and_cpu_baseline(vk, ctx, scene, name, chain, budget_s):
+    """N = 1: the oracle renders the frames the GPU renders -- whole frames of the benchmark's own size where the oracle manages
+    them, a row sample otherwise -- and its wall time for exactly those rows is the cpu_baseline (oracle/parity.py)."""
+    from oracle.oracle_py import Oracle
+    from oracle import parity
+    scene_idx, W, H, mode, spp, samples, faithful, desc = WORKLOADS[name]
+    cores = host_threads()
+    o = Oracle(scene, threads=cores)
+    cores = o.threads()
+    cam = scene.camera(W, H)
+    # calibrate on a sparse row sample
+    stride0 = 32 if mode == 2 else 270
+    o.set_row_sampling(stride0, stride0 // 2)
+    p = vk.make_params(W, H, mode=mode, spp=spp, shadow_samples=samples, faithful_rng=faithful, frame=1)
+    (o.hybrid_frame if mode == 2 else o.raytrace)(cam, p)
+    t0 = time.perf_counter()
+    (o.hybrid_frame if mode == 2 else o.raytrace)(cam, p)
+    per_row = (time.perf_counter() - t0) / len(range(stride0 // 2, H, stride0))
+    o.set_row_sampling(1, 0)
+    full = per_row * H
+    if mode == 2 and 2.5 * full <= budget_s:
+        frames = int(max(3, min(12, budget_s / full)))
+        par, cpu = parity.run_pair(vk, ctx, o, scene, W, H, mode, spp, samples, faithful, frames=frames, stride=1, chain=chain, time_budget_s=budget_s)
+        sample = f"{cpu['frames']} whole frames (indices 0..{cpu['frames'] - 1}, all {H} rows) of the {W}x{H} frame"
+    else:
+        rows = max(4, min(H, int(budget_s / max(per_row, 1e-9))))
+        stride = max(2, H // rows)
+        par, cpu = parity.run_pair(vk, ctx, o, scene, W, H, mode, spp, samples, faithful, stride=stride, chain=chain)
+        sample = f"1 frame x every {stride}th row ({cpu['rows']} of {H} rows) of the {W}x{H} frame"
+    o.close()
+    sec = max(cpu["seconds"], 1e-9)
+    rows_total = cpu["rows"] * cpu["frames"]
+    base = {"value": cpu["rays"] / sec / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+            "sample": f"{sample}, {sec:.1f} s wall on {cores} threads ({sec * cores:.0f} core-seconds); the same rows are the parity check",
+            "ms_per_frame_est": sec / max(rows_total, 1) * H * 1e3}
+    return par, base
+
+
+def nccl_debug_to_file(rank):
+    """The driver checks the communicator size from NCCL's own log; NCCL writes that log to stdout by default, where the contract
+    wants exactly one JSON line.  Route it into a per-rank file and replay the interesting lines on stderr afterwards."""
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("INFO", "TRACE") and "NCCL_DEBUG_SUBSYS" not in os.environ:
+        os.environ["NCCL_DEBUG_SUBSYS"] = "INIT,ENV"
+    if "NCCL_DEBUG_FILE" in os.environ:
+        return None
+    d = tempfile.mkdtemp(prefix="vkp_nccl_")
+    os.environ["NCCL_DEBUG_FILE"] = os.path.join(d, "nccl_%h_%p.log")
+    return d
+
+
+def replay_nccl_log(d):
+    if not d:
+        return None
+    seen = []
+    for f in sorted(glob.glob(os.path.join(d, "nccl_*.log"))):
+        try:
+            for line in open(f, errors="replace"):
+                if "nranks" in line or "NCCL version" in line or "NVLS" in line:
+                    seen.append(line.rstrip())
+        except OSError:
+            pass
+    for line in seen[:40]:
+        print(line, file=sys.stderr)
+    nr = set()
+    for line in seen:
+        parts = line.replace("=", " ").split()
+        for a, b in zip(parts, parts[1:]):
+            if a == "nranks" and b.strip(",").isdigit():
+                nr.add(int(b.strip(",")))
+    return sorted(nr)
+
+
+def load_ncu_measured():
+    """Per-kernel ncu figures of the committed capture (profiles/ncu_kernels.json, written by scripts/ncu_summary.py)."""
+    p = os.path.join(ROOT, "profiles", "ncu_kernels.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
 
 
 def main():
@@ -138,13 +251,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle leg (no parity block, no cpu_baseline)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
     ap.add_argument("--nccl-barrier", action="store_true", help="N > 1, peer composite: 4-byte NCCL all-reduce per frame instead of the device-side flag barrier")
     ap.add_argument("--no-peer", action="store_true", help="N > 1: composite with pack + NCCL gather + unpack instead of NVLink peer stores")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-identity check of the composite against a 1-GPU render")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the 2-step Raytraced 64 spp x 64 samples block (BASELINE configs[2])")
     ap.add_argument("--chain", type=int, default=2, choices=[0, 1, 2],
                     help="reflection-chain schedule: 0 inline in k_resolve, 1 wavefront queues, 2 k_chain overlapped with the shadow pass (default)")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="wall seconds the parity / cpu_baseline oracle leg may take")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -158,15 +273,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        scene = vk.HostScene(scene_idx)
-        leg = oracle_leg(scene, W, H, mode, spp, samples, faithful, budget_s=90.0, steps=args.steps, warmup=args.warmup)
+        scene = vk.HostScene(scene_idx)          # libvkp_scene.so only: this arm never maps the CUDA library
+        leg = oracle_steps(scene, args.workload, args.steps, args.warmup, budget_s=90.0)
         line = {
-            "impl": "reference", "metric": "Mrays/s (Hybrid 1080p hot path: shadow + reflection + secondary-shadow rays per second)", "value": leg["mrays_s"],
+            "impl": "reference", "metric": METRIC, "value": leg["mrays_s"],
             "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_frame_est"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "triangles": scene.n_triangles, "note": "the reference (Vulkan RT, MSVC) cannot be built or run here; "
-                       "this arm times the CPU oracle = scalar port of its shaders + a binned-SAH BVH, OpenMP over rows, all host cores; ms_per_step is the "
-                       "full-frame estimate from the row sample"},
+            "config": workload_config(args.workload, scene),
+            "note": "the reference (Vulkan RT, MSVC) cannot be built or run here; this arm times the CPU oracle = scalar port of its shaders + a "
+                    "binned-SAH BVH, OpenMP over rows, all host threads; ms_per_step is the full-frame estimate from the row sample",
+            "frame_ms": leg["step_ms"],
             "cpu_baseline": {"value": leg["mrays_s"], "unit": "Mrays/s", "cores": leg["cores"], "kind": "port", "sample": leg["sample"]},
             "e2e": {"value": leg["mrays_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -177,9 +293,10 @@ def main():
     # ------------------------------------------------------------------------------------------------ ours ----
     import torch
     import torch.distributed as dist
-    from vulkanhybridraytracer_b200 import PLANE, tiling
+    from vulkanhybridraytracer_b200 import PLANE
+    nccl_dir = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: the contract is ONE JSON line
+        nccl_dir = nccl_debug_to_file(rank)
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = local if world > 1 else 0
@@ -187,14 +304,16 @@ def main():
     T = scene.n_triangles
     ctx = vk.Context(dev)
     ctx.upload_scene(scene)
+    build = ctx.build_stats() if hasattr(ctx, "build_stats") else None
     cam = scene.camera(W, H)
     ctx.set_camera(cam)
     TW, TH = (32, 16)
     ctx.set_tiling(rank, world, TW, TH)
     L = len(scene.lights)
 
-    def params(frame):
-        return vk.make_params(W, H, mode=mode, spp=spp, shadow_samples=samples, faithful_rng=faithful, frame=frame, wavefront=args.chain)
+    def params(frame, wl=None):
+        _, w_, h_, mode_, spp_, samples_, faithful_, _ = WORKLOADS[wl or args.workload]
+        return vk.make_params(w_, h_, mode=mode_, spp=spp_, shadow_samples=samples_, faithful_rng=faithful_, frame=frame, wavefront=args.chain)
 
     from vulkanhybridraytracer_b200.multigpu import TiledRenderer
     tr = TiledRenderer(ctx, rank, world, L, tile=(TW, TH), backend="nccl", device=torch.device("cuda", dev), stream_ordered=world > 1)
@@ -228,6 +347,7 @@ def main():
     rays = np.zeros(4, dtype=np.int64)
     trav = np.zeros(3, dtype=np.int64)
     launches = 0
+    frame_times = []
     sampler = ClockSampler(dev); sampler.start()
     barrier()
     total_ms = 0.0
@@ -238,7 +358,8 @@ def main():
             p_k = params(frame)
             ctx.timer_begin()
             tr.render(p_k)
-            total_ms += ctx.timer_end()
+            ms = ctx.timer_end()
+            total_ms += ms; frame_times.append(ms)
             c = ctx.counters()
             stage_ms += np.array(list(c.ms_stage))
             rays += np.array([c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow], dtype=np.int64)
@@ -246,8 +367,8 @@ def main():
             frame += 1
     else:
         # N ranks: the K frames are queued back to back on the rank's stream -- flush, [event] render + composite [event] -- with no
-        # host round trip in between (a per-frame host sync would put the enqueue latency of the NCCL barrier into every frame);
-        # the frame barrier (4-byte all-reduce / gather) keeps the ranks in lockstep on the device.  Ray counters accumulate.
+        # host round trip in between (a per-frame host sync would put the enqueue latency of the barrier into every frame);
+        # the frame barrier keeps the ranks in lockstep on the device.  Ray counters accumulate.
         ctx.set_profiling(False)
         ctx.set_counter_accumulation(True)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -260,7 +381,8 @@ def main():
             ev[k][1].record(tr.stream)
             frame += 1
         barrier()
-        total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+        frame_times = [a.elapsed_time(b) for a, b in ev]
+        total_ms = float(sum(frame_times))
         c = ctx.counters()
         rays += np.array([c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow], dtype=np.int64)
         launches += c.kernel_launches * args.steps
@@ -306,12 +428,57 @@ def main():
             solo.close()
         dist.barrier()
 
+    # -- BASELINE configs[2] (Raytraced, 64 spp x 64 shadow samples), 2 timed frames after 1: the workload north_star's 80 % target is on ---
+    cfg3 = None
+    if not args.no_cfg3 and args.workload == "cfg2":
+        ctx.set_profiling(False)
+        ctx.set_counter_accumulation(True)
+        ctx.set_params(params(0, "cfg3")); ctx.reset_history()
+        tr.render(params(0, "cfg3"))
+        if world > 1:
+            composite()
+        barrier()
+        ctx.counters()                                     # clears the accumulated counters
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream3 = tr.stream if world > 1 else None
+        if world == 1:
+            ctx.timer_begin()
+        else:
+            e0.record(stream3)
+        for k in range(2):
+            tr.render(params(1 + k, "cfg3"))
+            if world > 1:
+                composite()
+        if world == 1:
+            ms3 = ctx.timer_end()
+        else:
+            e1.record(stream3)
+            barrier()
+            ms3 = e0.elapsed_time(e1)
+        c3 = ctx.counters()
+        ctx.set_counter_accumulation(False)
+        t3 = torch.tensor([ms3], dtype=torch.float64, device=f"cuda:{dev}")
+        r3 = torch.tensor([c3.rays_reflect + c3.rays_secondary_shadow], dtype=torch.int64, device=f"cuda:{dev}")
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX); dist.all_reduce(r3, op=dist.ReduceOp.SUM)
+        cfg3 = {"workload": "cfg3: " + WORKLOADS["cfg3"][7], "steps": 2, "warmup": 1, "ms_per_step": float(t3.item()) / 2,
+                "mrays_s": float(r3.item()) / 2 / (float(t3.item()) / 2 * 1e-3) / 1e6, "n_gpus": world, "scaling": "strong",
+                "timing": "CUDA events around 2 frames incl. the composite, max over ranks, no L2 flush (a frame is 1.6e10 rays)"}
+        ctx.set_params(params(frame)); ctx.reset_history()
+
     # -- timed region 2: end to end through the reference-facing host API (VulkanEngine::update + rasterize_hybrid + read-back) ---
     e2e = None
+    parity = None
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        # parity at the benchmark's own size + the cpu_baseline, from the same oracle frames (before the context goes away)
+        ctx.set_tiling(0, 1, TW, TH)
+        parity, cpu = parity_and_cpu_baseline(vk, ctx, scene, args.workload, args.chain, args.cpu_budget)
     if world == 1 and mode == 2 and scene_idx == 0:
         ctx.close()
         eng = vk.HostEngine(scene_idx, W, H, dev)
         eng.set("chain", args.chain)
+        eng.set("samples", samples)
         pinned = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
         nbytes = pinned[0].numel()
         # (1) fully synchronous: every frame is read back before the next one is submitted (vkQueueWaitIdle per frame)
@@ -321,7 +488,7 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for k in range(args.steps):
-            eng.frames(1)          # update(): lights + instance matrices H2D, TLAS refit; then the 4 frame kernels
+            eng.frames(1)          # update(): lights + instance matrices H2D, TLAS refit; then the frame kernels
             eng._H.vkph_engine_read(eng._h, 0, pinned[0].data_ptr(), nbytes)      # D2H of the presented image into pinned memory
         dt_sync = time.perf_counter() - t0
         # (2) the reference's FRAME_OVERLAP = 2 (renderer.h:34): frame k's image travels to the host while frame k+1 renders
@@ -330,11 +497,15 @@ def main():
             eng.frames(1); eng.present(pinned[k & 1].data_ptr(), nbytes); eng.present_wait(1)
         eng.present_wait(0)
         torch.cuda.synchronize()
+        eng.counters()
+        iter_t = []
         t0 = time.perf_counter()
         for k in range(args.steps):
+            ta = time.perf_counter()
             eng.frames(1)
             eng.present(pinned[k & 1].data_ptr(), nbytes)
             eng.present_wait(1)        # frame k-1 is complete in pinned[(k-1) & 1]
+            iter_t.append((time.perf_counter() - ta) * 1e3)
         eng.present_wait(0)
         dt = time.perf_counter() - t0
         c = eng.counters()
@@ -345,10 +516,12 @@ def main():
             present_ok = bool(np.array_equal(last, eng.read_srgb8()))
         e2e = {"value": e_rays / (dt / args.steps) / 1e6, "unit": "Mrays/s", "ms_per_step": dt / args.steps * 1e3,
                "h2d_bytes_per_step": 48 * L + 144 * len(scene.instances) + 400 + 64, "d2h_bytes_per_step": W * H * 4,
-               "frames_in_flight": 2, "presented_image_equals_sync_readback": present_ok,
+               "frames_in_flight": 2, "presented_image_equals_sync_readback": present_ok, "iteration_ms": stats_ms(iter_t),
                "sync": {"value": e_rays / (dt_sync / args.steps) / 1e6, "ms_per_step": dt_sync / args.steps * 1e3, "frames_in_flight": 1},
                "api": "VulkanEngine::update + Renderer::rasterize_hybrid + present (D2H of the sRGB8 image into pinned memory) through the host C++ "
-                      "API over the C-ABI, wall clock; FRAME_OVERLAP = 2 as renderer.h:34"}
+                      "API over the C-ABI, wall clock; FRAME_OVERLAP = 2 as renderer.h:34",
+               "vs_value": "e2e keeps two frames in flight and does not flush L2 between frames; `value` times each frame alone after an L2 flush, so "
+                           "e2e may be the faster of the two"}
         eng.close()
     else:
         # tile-sharded / other workloads: same loop through the C-ABI with per-frame host inputs and a present on rank 0.
@@ -357,6 +530,8 @@ def main():
         # frame k-1 land before it joins the barrier that releases frame k+1 (which reuses that buffer).
         pinned = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
         nbytes = pinned[0].numel()
+        ctx.set_tiling(rank, world, TW, TH)
+
         def e2e_frame(k):
             ctx.set_lights(scene.lights); ctx.set_camera(cam)
             if world == 1:
@@ -395,79 +570,104 @@ def main():
         dt = float(tt.item())
         e2e = {"value": counted / args.steps / (dt / args.steps) / 1e6, "unit": "Mrays/s", "ms_per_step": dt / args.steps * 1e3,
                "h2d_bytes_per_step": 48 * L + 400 + 64, "d2h_bytes_per_step": W * H * 4, "frames_in_flight": 2,
-               "api": "vkp_set_lights/camera/params + vkp_render (+ NVLink peer composite) + vkp_readback_async(FINAL_SRGB8) into pinned memory on rank 0, wall clock"}
+               "api": "vkp_set_lights/camera/params + vkp_render (+ NVLink peer composite) + vkp_readback_async(FINAL_SRGB8) into pinned memory on rank 0, wall clock",
+               "vs_value": "e2e keeps two frames in flight and does not flush L2 between frames; `value` times each frame alone after an L2 flush, so "
+                           "e2e may be the faster of the two"}
 
+    comm_nranks = None
+    if world > 1:
+        dist.barrier()
+        comm_nranks = replay_nccl_log(nccl_dir) if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
         return 0
 
-    # -- roofline of the dominant kernel (SURVEY 8d algorithmic bytes / CUDA-event duration) ------------------------------------------
+    # -- roofline of the dominant kernel -----------------------------------------------------------------------------------------------
+    # achieved = algorithmic bytes / CUDA-event duration.  Algorithmic = what the stage has to move to and from HBM once:
+    # its planes, plus the part of the acceleration structure its rays touch -- at most all of it, because a node fetched by a second
+    # ray is an L2 / L1 hit, not HBM traffic.  SURVEY 8d's per-ray figure R * B_ray(T) is kept beside it as `requested_model`: a request
+    # volume the caches serve, which is why it may exceed the HBM peak.
     P = W * H
     names = ["k_gbuffer", "k_shadow", "k_denoise", "k_resolve", "k_post", "k_raytrace", "k_deferred"]
     per_frame = rays_all / args.steps / world          # this rank's share (tiles are balanced)
     Pr = P / world
     BR = b_ray(T)
-    kbytes = {
-        "k_gbuffer": Pr * 32 + per_frame[0] * BR,
-        "k_shadow": Pr * (16 + L) + per_frame[1] * BR,
-        "k_denoise": Pr * (2 * L + 4 + L),
-        "k_resolve": Pr * (32 + L + 16) + (per_frame[2] + per_frame[3]) * BR,
-        "k_raytrace": Pr * 32 + (per_frame[2] + per_frame[3]) * BR,
-    }
+    bvh_bytes = 32.0 * (T / 2.0) + 48.0 * T             # ~T/2 nodes of 32 B (<= 4-triangle leaves) + 48 B per leaf-ordered triangle
+    plane_bytes = {"k_gbuffer": Pr * 40, "k_shadow": Pr * (16 + L), "k_denoise": Pr * (2 * L + 4 + L), "k_resolve": Pr * (32 + L + 16 + 4),
+                   "k_raytrace": Pr * (16 + 16 + 4)}
+    ray_count = {"k_gbuffer": per_frame[0], "k_shadow": per_frame[1], "k_denoise": 0.0, "k_resolve": per_frame[2] + per_frame[3],
+                 "k_raytrace": per_frame[2] + per_frame[3]}
+    kbytes = {k: plane_bytes[k] + min(ray_count[k] * BR, bvh_bytes if ray_count[k] > 0 else 0.0) for k in plane_bytes}
+    kreq = {k: plane_bytes[k] + ray_count[k] * BR for k in plane_bytes}
     ms = stage_ms / args.steps
     dom = int(np.argmax(ms))
     dname = names[dom]
     achieved = kbytes.get(dname, 0.0) / (ms[dom] * 1e-3) / 1e9 if ms[dom] > 0 else 0.0
-    frame_bytes = sum(kbytes[n] for n in (("k_gbuffer", "k_shadow", "k_denoise", "k_resolve") if mode == 2 else ("k_raytrace",)))
-    roofline = {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": kbytes.get(dname, 0.0), "kernel_ms": float(ms[dom]),
+    frame_kernels = ("k_gbuffer", "k_shadow", "k_denoise", "k_resolve") if mode == 2 else ("k_raytrace",)
+    frame_bytes = sum(kbytes[n] for n in frame_kernels)
+    ncu = load_ncu_measured() or {}
+    ncu_k = ncu.get("kernels", {}).get(dname)
+    bound = "hbm"
+    if ncu_k and ncu_k.get("dram_frac") is not None and ncu_k["dram_frac"] < 0.5:
+        bound = ncu_k.get("bound", "issue+latency")
+    roofline = {"bound": bound, "kernel": dname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": kbytes.get(dname, 0.0),
+                "algorithmic_model": "planes of the stage + min(rays * B_ray(T), bytes of the BVH): the compulsory HBM traffic (DESIGN.md section 5)",
+                "stage_ms": float(ms[dom]), "stage_note": "CUDA-event time of the stage inside the frame (k_shadow shares the SMs with the concurrent k_chain); "
+                                                          "the kernel alone is measured.kernel_us",
                 "kernel_share_of_step": float(ms[dom] / max(ms.sum(), 1e-9)),
-                "stage_ms": {names[i]: float(ms[i]) for i in range(7) if ms[i] > 0},
-                "frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_bytes * world / (ms_per_step * 1e-3) / 1e9, "frac": frame_bytes * world / (ms_per_step * 1e-3) / 1e9 / (peak * world)},
-                "requested": {"note": "bytes the traversal actually asked the memory system for on this rank (device counters): 64 B per child-pair fetch, 48 B per "
-                                      "triangle, 80 B per instance entry, + the per-pixel plane traffic of SURVEY 8d",
-                              "node_fetches_per_frame": int(trav[0] // args.steps), "triangle_tests_per_frame": int(trav[1] // args.steps),
-                              "instance_entries_per_frame": int(trav[2] // args.steps),
-                              "bytes_per_frame": float((64 * trav[0] + 48 * trav[1] + 80 * trav[2]) / args.steps + Pr * (100 + 5 * L)),
-                              "GBps": float(((64 * trav[0] + 48 * trav[1] + 80 * trav[2]) / args.steps + Pr * (100 + 5 * L)) / (ms_per_step * 1e-3) / 1e9)},
-                "note": "algorithmic bytes = P*B_px(stage) + rays*B_ray(T) (SURVEY 8d, B_ray=%d B at T=%d); traversal is latency/L2 bound, measured DRAM traffic is far below this" % (BR, T)}
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
-        try:
-            tj = json.load(open(prof))
-            roofline["traffic"] = tj.get(dname, tj.get(dname + "<2>"))
-            roofline["traffic_source"] = tj.get("_source")
-        except Exception:
-            pass
-
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        leg = oracle_leg(scene, W, H, mode, spp, samples, faithful, budget_s=15.0, steps=2, warmup=1, grow_steps=True)
-        cpu = {"value": leg["mrays_s"], "unit": "Mrays/s", "cores": leg["cores"], "kind": "port", "sample": leg["sample"],
-               "ms_per_frame_est": leg["ms_per_frame_est"]}
+                "stage_ms_all": {names[i]: float(ms[i]) for i in range(7) if ms[i] > 0},
+                "frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_bytes * world / (ms_per_step * 1e-3) / 1e9,
+                          "frac": frame_bytes * world / (ms_per_step * 1e-3) / 1e9 / (peak * world)},
+                "requested_model": {"note": "SURVEY 8d: planes + rays * B_ray(T), B_ray = %d B at T = %d -- a request volume served by L1 / L2, not an HBM figure" % (BR, T),
+                                    "bytes_per_launch": kreq.get(dname, 0.0), "GBps": kreq.get(dname, 0.0) / (ms[dom] * 1e-3) / 1e9 if ms[dom] > 0 else 0.0},
+                "requested_counted": {"note": "bytes the traversal actually asked the memory system for on this rank (device counters): 64 B per child-pair fetch, "
+                                              "48 B per triangle, 80 B per instance entry, + the per-pixel plane traffic",
+                                      "node_fetches_per_frame": int(trav[0] // args.steps), "triangle_tests_per_frame": int(trav[1] // args.steps),
+                                      "instance_entries_per_frame": int(trav[2] // args.steps),
+                                      "bytes_per_frame": float((64 * trav[0] + 48 * trav[1] + 80 * trav[2]) / args.steps + Pr * (100 + 5 * L)),
+                                      "GBps": float(((64 * trav[0] + 48 * trav[1] + 80 * trav[2]) / args.steps + Pr * (100 + 5 * L)) / (ms_per_step * 1e-3) / 1e9)},
+                "measured": ncu_k, "measured_source": ncu.get("_source")}
+    if ncu_k and ncu_k.get("dram_bytes") is not None:
+        roofline["traffic"] = ncu_k["dram_bytes"]
+    else:
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            try:
+                tj = json.load(open(prof))
+                roofline["traffic"] = tj.get(dname, tj.get(dname + "<2>"))
+                roofline["traffic_source"] = tj.get("_source")
+            except Exception:
+                pass
 
     line = {
-        "metric": "Mrays/s (Hybrid 1080p hot path: shadow + reflection + secondary-shadow rays per second)", "value": value, "unit": "Mrays/s",
+        "metric": METRIC, "value": value, "unit": "Mrays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "triangles": T, "lights": L, "pixels": P,
-                   "rays_per_frame": {"shadow": int(rays_all[1] // args.steps), "reflect": int(rays_all[2] // args.steps),
-                                      "secondary_shadow": int(rays_all[3] // args.steps), "primary_not_counted": int(rays_all[0] // args.steps)},
-                   "mrays_s_incl_primary": float(rays_all.sum()) / args.steps / (ms_per_step * 1e-3) / 1e6,
-                   "nominal_2P_mrays_s": 2 * P / (ms_per_step * 1e-3) / 1e6,
-                   "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain on a second stream overlapping k_shadow + k_denoise"}[args.chain],
-                   "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
-                   "parallelism": (f"tiles {TW}x{TH} interleaved over {world} GPU(s), replicated BVH, " +
-                                   ("resolve kernels store sRGB8 pixels straight into rank 0's image over NVLink peer memory (CUDA IPC) + 4-byte all-reduce as the frame barrier"
-                                    if peer else "pack + NCCL gather of sRGB8 tiles + unpack")) if world > 1 else "1 GPU",
-                   "composite_bit_identical_to_1gpu": composite_ok,
-                   "timing": "CUDA events on the context stream around each frame, summed over K frames, max over ranks"},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
+        "config": workload_config(args.workload, scene),
+        "run": {"rays_per_frame": {"shadow": int(rays_all[1] // args.steps), "reflect": int(rays_all[2] // args.steps),
+                                   "secondary_shadow": int(rays_all[3] // args.steps), "primary_not_counted": int(rays_all[0] // args.steps)},
+                "mrays_s_incl_primary": float(rays_all.sum()) / args.steps / (ms_per_step * 1e-3) / 1e6,
+                "nominal_2P_mrays_s": 2 * P / (ms_per_step * 1e-3) / 1e6,
+                "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain on a second stream overlapping k_shadow + k_denoise"}[args.chain],
+                "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
+                "parallelism": (f"tiles {TW}x{TH} dealt over {world} GPU(s), replicated BVH, " +
+                                ("resolve kernels store sRGB8 pixels straight into rank 0's image over NVLink peer memory (CUDA IPC) + a device-side flag barrier"
+                                 if peer else "pack + NCCL gather of sRGB8 tiles + unpack")) if world > 1 else "1 GPU",
+                "composite_bit_identical_to_1gpu": composite_ok,
+                "comm_nranks_seen": comm_nranks,
+                "timing": "CUDA events on the context stream around each frame, summed over K frames, max over ranks"},
+        "frame_ms": stats_ms(frame_times),
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "build": build, "cfg3": cfg3, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
     }
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
+    if parity is not None and not parity.get("pass", False):
+        print("bench.py: PARITY BELOW THE BAR: %s" % json.dumps({k: parity[k] for k in ("hit_id_agreement", "mae", "max")}), file=sys.stderr)
+        return 1
     return 0
 
 

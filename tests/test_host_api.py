@@ -10,7 +10,7 @@ import vulkanhybridraytracer_b200 as vk
 
 
 def test_default_scene_matches_scene_cpp():
-    sc = vk.HostScene(0, detail=(7, 5, 7, 31))      # the library's defaults, stated: the detail setting is global in libvkp_host
+    sc = vk.HostScene(0, detail=(7, 5, 7, 31))      # the full-size scene, stated (detail=None means the same)
     # TLAS order floor, mirror sphere, glass sphere, mirror slab, lucy, helmet (scene.cpp:151-158)
     assert sc.instances["material_id"].tolist() == [1, 2, 3, 2, 5, 4]
     tris = (sc.instances["index_count"] // 3).tolist()
@@ -103,7 +103,7 @@ def test_obj_loader(tmp_path, monkeypatch):
 
 def test_png_and_exr_writers(tmp_path):
     import cv2
-    H = vk.load_host()
+    H = vk.load_scene()
     rng = np.random.default_rng(0)
     img = rng.integers(0, 255, size=(37, 53, 4), dtype=np.uint8); img[..., 3] = 255
     p = str(tmp_path / "a.png")

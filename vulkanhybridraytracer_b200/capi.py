@@ -124,16 +124,19 @@ def load_vkp():
     return L
 
 
-def load_host():
-    """Load libvkp_host.so (host mirror of the reference classes + C shim)."""
-    global _host
-    if _host is not None:
-        return _host
-    load_vkp()
-    path = os.path.join(lib_dir(), "libvkp_host.so")
+_scene = None
+
+
+def load_scene():
+    """Load libvkp_scene.so: the host scene model and the image readers / writers.  It depends on neither CUDA nor libvkp.so, so a
+    process that only needs scenes (bench.py --impl reference) never maps the GPU library."""
+    global _scene
+    if _scene is not None:
+        return _scene
+    path = os.path.join(lib_dir(), "libvkp_scene.so")
     if not os.path.exists(path):
         raise VkpError(f"{path} is missing: run `make`")
-    H = C.CDLL(path)
+    S = C.CDLL(path, mode=C.RTLD_GLOBAL)
     vp, i, u32 = C.c_void_p, C.c_int, C.c_uint32
     P = C.POINTER
     sig = {
@@ -152,6 +155,31 @@ def load_host():
         "vkph_scene_camera_rotate": (i, [vp, C.c_float, C.c_float]),
         "vkph_scene_camera_set": (i, [vp, P(C.c_float * 3), C.c_float, C.c_float]),
         "vkph_scene_set_entity_matrix": (i, [vp, i, P(C.c_float * 16)]),
+        "vkph_write_png": (i, [C.c_char_p, vp, i, i]),
+        "vkph_write_exr": (i, [C.c_char_p, vp, i, i]),
+        "vkph_decode_image_file": (i, [C.c_char_p, P(i), P(i), vp, C.c_size_t]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(S, name)
+        f.restype, f.argtypes = res, args
+    _scene = S
+    return S
+
+
+def load_host():
+    """Load libvkp_host.so (host Renderer / VulkanEngine over libvkp.so + libvkp_scene.so, and its C shim)."""
+    global _host
+    if _host is not None:
+        return _host
+    load_vkp()
+    load_scene()
+    path = os.path.join(lib_dir(), "libvkp_host.so")
+    if not os.path.exists(path):
+        raise VkpError(f"{path} is missing: run `make`")
+    H = C.CDLL(path)
+    vp, i, u32 = C.c_void_p, C.c_int, C.c_uint32
+    P = C.POINTER
+    sig = {
         "vkph_engine_create": (vp, [i, i, i, i, P(i)]),
         "vkph_engine_set": (i, [vp, C.c_char_p, i]),
         "vkph_engine_frames": (i, [vp, i]),
@@ -163,20 +191,18 @@ def load_host():
         "vkph_engine_state": (i, [vp, P(i), P(i)]),
         "vkph_engine_ctx": (vp, [vp]),
         "vkph_engine_destroy": (None, [vp]),
-        "vkph_write_png": (i, [C.c_char_p, vp, i, i]),
-        "vkph_write_exr": (i, [C.c_char_p, vp, i, i]),
-        "vkph_decode_image_file": (i, [C.c_char_p, P(i), P(i), vp, C.c_size_t]),
     }
     for name, (res, args) in sig.items():
         f = getattr(H, name)
         f.restype, f.argtypes = res, args
+    H.vkph_last_error = load_scene().vkph_last_error
     _host = H
     return H
 
 
 def decode_image(path):
     """Texture::GET's image loader (host/image_decode.cpp, the stbi_load(..., 4) replacement): H x W x 4 uint8."""
-    H = load_host()
+    H = load_scene()
     w, h = C.c_int(), C.c_int()
     if H.vkph_decode_image_file(str(path).encode(), C.byref(w), C.byref(h), None, 0) != 0:
         raise VkpError(H.vkph_last_error().decode())
@@ -210,7 +236,7 @@ class HostScene:
     """Scene::create_scene(i) of the host library, exported as the flat arrays both the C-ABI and the oracle consume."""
 
     def __init__(self, index=0, detail=None):
-        H = load_host()
+        H = load_scene()
         self._H = H
         self.detail = None if detail is None else tuple(int(x) for x in detail)
         self._h = H.vkph_scene_create(index, _detail4(detail))
@@ -222,7 +248,7 @@ class HostScene:
     @classmethod
     def from_prefab(cls, path, detail=None):
         """Scene::create_viewer_scene: the default scene's floor, lights and camera around one .obj / .gltf / .glb file."""
-        H = load_host()
+        H = load_scene()
         self = cls.__new__(cls)
         self._H = H
         self.detail = None if detail is None else tuple(int(x) for x in detail)

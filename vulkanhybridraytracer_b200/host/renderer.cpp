@@ -13,6 +13,17 @@
         if (_e != VKP_OK) throw std::runtime_error(std::string(#x) + ": " + vkp_last_error(_ctx));                \
     } while (0)
 
+// ---- Mesh::upload (vk_mesh.cpp upload_to_gpu: vertex + index buffers) -------------------------------------------
+void Mesh::upload(vkp_ctx* ctx)
+{
+    if (_deviceMeshId >= 0) return;
+    static_assert(sizeof(Vertex) == sizeof(vkp_vertex), "Vertex / vkp_vertex layout");
+    int id = -1;
+    if (vkp_upload_mesh(ctx, reinterpret_cast<const vkp_vertex*>(_vertices.data()), (uint32_t)_vertices.size(), _indices.data(),
+                        (uint32_t)_indices.size(), &id) == VKP_OK)
+        _deviceMeshId = id;
+}
+
 // ---- Renderer ---------------------------------------------------------------------------------------------
 Renderer::Renderer(Scene* scene) : _scene(scene)
 {

@@ -287,15 +287,7 @@ Mesh* Mesh::get_cube()
     return slot;
 }
 
-void Mesh::upload(vkp_ctx* ctx)
-{
-    if (_deviceMeshId >= 0) return;
-    static_assert(sizeof(Vertex) == sizeof(vkp_vertex), "Vertex / vkp_vertex layout");
-    int id = -1;
-    if (vkp_upload_mesh(ctx, reinterpret_cast<const vkp_vertex*>(_vertices.data()), (uint32_t)_vertices.size(), _indices.data(),
-                        (uint32_t)_indices.size(), &id) == VKP_OK)
-        _deviceMeshId = id;
-}
+// Mesh::upload lives in renderer.cpp: it is the only member that talks to libvkp, and the scene library must not depend on it
 
 // ---- Node / Prefab (src/vk_mesh.cpp:361-546, :831-912) ---------------------------------------------------
 glm::mat4 Node::getGlobalMatrix(bool fast)
