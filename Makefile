@@ -28,8 +28,11 @@ SCENE_SRCS := $(HOST)/scene_model.cpp $(HOST)/procedural.cpp $(HOST)/output.cpp 
 HOST_SRCS := $(HOST)/renderer.cpp $(HOST)/host_capi.cpp
 HOST_HDRS := $(wildcard $(HOST)/*.h) $(wildcard $(ROOT)include/*.h)
 
-all: libvkp host oracle
+all: libvkp host oracle stress
 libvkp: $(LIBDIR)/libvkp.so
+# test artefact: the same library with a 2-level shared-memory traversal stack and a 48-item warp queue, so that the local-memory
+# overflow of the stack and the serial fall-back of the warp-cooperative traversal are exercised by tests/ on small scenes
+stress: $(LIBDIR)/libvkp_stress.so
 host: $(LIBDIR)/libvkp_scene.so $(LIBDIR)/libvkp_host.so $(BINDIR)/vkpinut
 oracle:
 	$(MAKE) -C $(ROOT)oracle
@@ -37,6 +40,14 @@ oracle:
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(CU_HDRS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
+
+STRESS_OBJS := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/stress_%.o,$(CU_SRCS))
+$(OBJDIR)/stress_%.o: $(CSRC)/%.cu $(CU_HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -DVKP_SSTACK=2 -DVKP_WQ_CAP=48 -c $< -o $@ 2> $(OBJDIR)/stress_$*.ptxas.log || (cat $(OBJDIR)/stress_$*.ptxas.log; exit 1)
+$(LIBDIR)/libvkp_stress.so: $(STRESS_OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared --cudart static -ccbin $(CXX) -o $@ $(STRESS_OBJS) -lpthread -ldl -lrt
 
 $(LIBDIR)/libvkp.so: $(CU_OBJS)
 	@mkdir -p $(LIBDIR)
@@ -61,4 +72,4 @@ clean:
 	rm -rf $(OBJDIR) $(LIBDIR) $(BINDIR)
 	$(MAKE) -C $(ROOT)oracle clean
 
-.PHONY: all libvkp host oracle clean sass
+.PHONY: all libvkp host oracle stress clean sass

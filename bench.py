@@ -257,7 +257,7 @@ def main():
     ap.add_argument("--no-peer", action="store_true", help="N > 1: composite with pack + NCCL gather + unpack instead of NVLink peer stores")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-identity check of the composite against a 1-GPU render")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the 2-step Raytraced 64 spp x 64 samples block (BASELINE configs[2])")
-    ap.add_argument("--chain", type=int, default=2, choices=[0, 1, 2],
+    ap.add_argument("--chain", type=int, default=2, choices=[0, 1, 2, 3],
                     help="reflection-chain schedule: 0 inline in k_resolve, 1 wavefront queues, 2 k_chain overlapped with the shadow pass (default)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="wall seconds the parity / cpu_baseline oracle leg may take")
     args = ap.parse_args()
@@ -304,7 +304,17 @@ def main():
     T = scene.n_triangles
     ctx = vk.Context(dev)
     ctx.upload_scene(scene)
-    build = ctx.build_stats() if hasattr(ctx, "build_stats") else None
+    # acceleration-structure build as a measured component (buildBlas renderer.cpp:1696-1753, buildTlas :1757-1865, per-frame refit
+    # vk_engine.cpp:172-187): CUDA-event times from the library, against the algorithmic bytes of SURVEY 8d (132 B read + 80 B written per triangle)
+    for _ in range(3):
+        ctx.build_tlas(True)
+    ctx.sync()
+    build = ctx.build_stats()
+    if build["blas_ms"] > 0:
+        build["blas_algorithmic_bytes"] = int(build["blas_triangles"]) * (132 + 80)
+        build["blas_GBps"] = build["blas_algorithmic_bytes"] / (build["blas_ms"] * 1e-3) / 1e9
+        build["blas_mtris_s"] = build["blas_triangles"] / (build["blas_ms"] * 1e-3) / 1e6
+        build["builder"] = os.environ.get("VKP_BLAS_BUILDER", "ploc")
     cam = scene.camera(W, H)
     ctx.set_camera(cam)
     TW, TH = (32, 16)
@@ -650,7 +660,7 @@ def main():
                                    "secondary_shadow": int(rays_all[3] // args.steps), "primary_not_counted": int(rays_all[0] // args.steps)},
                 "mrays_s_incl_primary": float(rays_all.sum()) / args.steps / (ms_per_step * 1e-3) / 1e6,
                 "nominal_2P_mrays_s": 2 * P / (ms_per_step * 1e-3) / 1e6,
-                "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain on a second stream overlapping k_shadow + k_denoise"}[args.chain],
+                "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise", 3: "k_chain_warp (one warp per queued path, cooperative traversal) on a second stream"}[args.chain],
                 "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
                 "parallelism": (f"tiles {TW}x{TH} dealt over {world} GPU(s), replicated BVH, " +
                                 ("resolve kernels store sRGB8 pixels straight into rank 0's image over NVLink peer memory (CUDA IPC) + a device-side flag barrier"

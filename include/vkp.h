@@ -66,6 +66,13 @@ VKP_API int vkp_set_builder(vkp_ctx* ctx, int builder);
 /* Renderer::buildTlas(instances, flags, update) (renderer.cpp:1757-1865); update=1 == MODE_UPDATE refit */
 VKP_API int vkp_build_tlas(vkp_ctx* ctx, int update);
 
+/* build / refit times, tree heights, the BLAS arena and its L2 persistence window (syncs) */
+VKP_API int vkp_get_build_stats(vkp_ctx* ctx, vkp_build_stats* out);
+/* L2 persistence window over the BLAS arena (cudaStreamAttributeAccessPolicyWindow, hitProp persisting) on the context's streams:
+ * what north_star calls "node and triangle fetches staged through ... the L2 persistence window".  -1 = the built-in default
+ * (VKP_L2_PERSIST in the environment overrides it), 0 = off, 1 = on.  Takes effect at once; changes no result. */
+VKP_API int vkp_set_l2_persistence(vkp_ctx* ctx, int on);
+
 /* per-frame state --------------------------------------------------------------------------- */
 /* VulkanEngine::updateCameraMatrices (vk_engine.cpp:688-741) */
 VKP_API int vkp_set_camera(vkp_ctx* ctx, const vkp_camera* camera);

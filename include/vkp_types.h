@@ -81,15 +81,16 @@ typedef struct vkp_params {
     int32_t debug_target;            /* deferred.frag debug.target 0..6                            */
     int32_t wavefront;               /* reflection chain (hybridRaygen.rgen:153-170): 0 = inline in the resolve kernel,
                                         1 = wavefront path queues with ray compaction, one launch per bounce,
-                                        2 = compacted chain kernel on a second stream, overlapping shadow + denoise  */
+                                        2 = mirror / glass pixels compacted into a path queue, one thread per path, on a second stream
+                                            overlapping shadow + denoise (default of the host engine),
+                                        3 = as 2 with one warp per path and warp-cooperative traversal (measured slower, kept for A/B) */
     int32_t fuse_denoise;            /* vkp_render (Hybrid): run blur.comp inside the resolve kernel instead of as its own pass */
     int32_t reproject_fix;           /* blur.comp:52-53 on a reset frame.  0 (default): the reference's history fetch, pixel + motion.x * (W, H)
                                         (twice the right distance, x component used for both axes).
                                         1: the previous frame's pixel, floor(pixel + 0.5 + 0.5 * motion * (W, H)); the stored motion is
                                         previous - current NDC position (basic.vert / geometry_shader.frag cross the two varyings)      */
-    int32_t shadow_tail_budget;      /* k_shadow, one-sample frames: child-pair fetches a thread spends on a shadow ray before it hands the
-                                        ray to the warp-cooperative tail kernel.  0 = the context default
-                                        (VKP_SHADOW_TAIL in the environment, else built in), < 0 = off.  Changes the schedule, never a bit. */
+    int32_t denoiser;                /* shadow filter: 0 = the reference's blur.comp (3x3 clamp + temporal blend), 1 = edge-aware a-trous
+                                        filter over the R8 planes guided by the G-buffer */
     int32_t reserved[1];
 } vkp_params;
 
@@ -150,6 +151,25 @@ typedef struct vkp_counters {
     uint32_t worst_thread_nodes;    /* most child-pair fetches any one thread made (the kernel-tail length) ...            */
     uint32_t worst_thread_tag;      /* ... and who: bits[31:28] stage, [27:23] light, [22:0] pixel index y*W+x            */
 } vkp_counters;
+
+/* acceleration-structure build / refit figures (vkp_get_build_stats): what vkCmdBuildAccelerationStructuresKHR cost the
+ * reference's driver (renderer.cpp:1747 buildBlas, :1853 buildTlas, per-frame MODE_UPDATE refit vk_engine.cpp:172-187) */
+typedef struct vkp_build_stats {
+    float    blas_ms;               /* CUDA-event time of the last vkp_build_blas (all BLAS it built, incl. compaction into the arena) */
+    float    tlas_ms;               /* last full TLAS build */
+    float    refit_ms;              /* last TLAS refit (instance boxes + bottom-up fit + node emit), on the update stream */
+    uint32_t blas_built;            /* BLAS built by the last vkp_build_blas */
+    uint32_t blas_launches;         /* kernels it launched */
+    uint32_t blas_host_syncs;       /* stream synchronisations the host needed inside the build (0 = fully device-driven) */
+    uint32_t blas_height_max;       /* tallest BLAS of the scene */
+    uint32_t tlas_height;
+    uint32_t refit_launches;
+    uint64_t blas_triangles;        /* triangles of the BLAS built by the last vkp_build_blas (not instanced) */
+    uint64_t arena_bytes;           /* nodes + leaf triangles of every BLAS, one contiguous allocation (the L2 persistence window) */
+    uint64_t l2_persist_bytes;      /* bytes of the arena set aside as persisting L2 lines (0 = window off) */
+    float    l2_hit_ratio;          /* hitRatio of the access-policy window */
+    uint32_t _pad;
+} vkp_build_stats;
 
 /* 32-byte BVH node (both BLAS and TLAS).  ref: bit31 = leaf; leaf: bits[30:3] = first item,
  * bits[2:0] = count-1 ... see DESIGN.md "BVH layout". */

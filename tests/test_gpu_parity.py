@@ -118,9 +118,9 @@ def test_hybrid_frames_stage_by_stage(gpu_ctx, small_scene, small_oracle, w, h, 
         assert np.array_equal(final.view(np.uint32), ref["final"].view(np.uint32))          # stronger than the bar: same bits
         assert np.array_equal(ctx.readback(PLANE.FINAL_SRGB8), o.post(p, ref["final"]))
         assert [c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow] == list(o.counters.rays)
-        # gbuffer, shadow, [denoise], resolve; 1: + one k_bounce per bounce (8), never fused; 2: + k_chain;
+        # gbuffer, shadow, [denoise], resolve; 1: + one k_bounce per bounce (8), never fused; 2: + queue clear, k_chain_scan, k_chain;
         # + the two k_build_order launches of the longest-first schedule (side stream)
-        assert c.kernel_launches == {0: 4, 1: 4 + 8, 2: 5}[wavefront] - (1 if fuse and wavefront != 1 else 0) + 2
+        assert c.kernel_launches == {0: 4, 1: 4 + 8, 2: 7}[wavefront] - (1 if fuse and wavefront != 1 else 0) + 2
 
 
 def test_stage_isolation(gpu_ctx, small_scene, small_oracle):

@@ -1,7 +1,9 @@
-"""GPU parity on what round 1 added last: the real-asset path (glTF prefab), `reproject_fix`, the k_shadow tail
-kernel, light edge cases, and the CUDA path directly against the vectors produced by the reference's own shader binaries.
+"""GPU parity on the later additions: the real-asset path (glTF prefab), `reproject_fix`, the overflow / fall-back
+paths of the round-2 traversal, light edge cases, and the CUDA path directly against the vectors produced by the reference's own shader binaries.
 Sorted after the established GPU suite on purpose (the driver runs pytest with -x): a failure here cannot mask the core parity tests.
 All of them were run on a B200 before they were committed (gpurun logs r1k / r1l / r1o / r1q)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -77,38 +79,50 @@ def test_reproject_fix_matches_the_oracle(small_scene, small_oracle, fuse):
     ctx.close(); sc.close()
 
 
-@pytest.mark.parametrize("budget,cap", [(1, 0), (6, 0), (40, 0), (3, 500)])
-def test_shadow_tail_kernel_changes_no_bit(small_scene, small_oracle, budget, cap, monkeypatch):
-    """vkp_params.shadow_tail_budget: k_shadow hands rays that are still unanswered after `budget` child-pair fetches to the
-    warp-cooperative tail kernel (one warp per ray, lanes share the stack items).  An any-hit answer does not depend on the order
-    of the walk, so every shadow plane -- and everything downstream -- must stay bit-identical to the oracle: with nearly every
-    ray spilled (budget 1), with a realistic budget, and with a queue too small for the spills (the thread then carries on)."""
-    if cap:
-        monkeypatch.setenv("VKP_SHADOW_TAIL_CAP", str(cap))
-    o = small_oracle
-    ctx = vk.Context(0); ctx.upload_scene(small_scene)
-    w, h = 320, 184
-    cam = small_scene.camera(w, h); ctx.set_camera(cam)
-    hist = None
-    for f in range(3):
-        p = vk.make_params(w, h, frame=f, shadow_tail_budget=budget, wavefront=2)
+_STRESS_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import vulkanhybridraytracer_b200 as vk
+from vulkanhybridraytracer_b200 import PLANE
+from oracle.oracle_py import Oracle
+sc = vk.HostScene(0, detail=(5, 4, 5, 8)); o = Oracle(sc)
+ctx = vk.Context(0); ctx.upload_scene(sc)
+w, h = 256, 144
+cam = sc.camera(w, h); ctx.set_camera(cam)
+hist = None
+for chain in (2, 3, 0):
+    ctx.reset_history(); hist = None
+    for f in range(2):
+        p = vk.make_params(w, h, frame=f, wavefront=chain)
         ctx.set_params(p); ctx.render()
         o.reset_counters()
-        ref = o.hybrid_frame(cam, vk.make_params(w, h, frame=f), history=hist); hist = ref["denoised"]
-        for l in range(len(small_scene.lights)):
-            assert np.array_equal(ctx.readback(PLANE.SHADOW0 + l), ref["shadow"][l]), (f, l)
-            assert np.array_equal(ctx.readback(PLANE.DENOISED0 + l), ref["denoised"][l]), (f, l)
-        assert np.array_equal(ctx.readback(PLANE.FINAL_F32).view(np.uint32), ref["final"].view(np.uint32)), f
+        ref = o.hybrid_frame(cam, p, history=hist); hist = ref["denoised"]
+        assert np.array_equal(ctx.readback(PLANE.HIT_IDS), ref["g"].hit_ids)
+        for l in range(len(sc.lights)):
+            assert np.array_equal(ctx.readback(PLANE.SHADOW0 + l), ref["shadow"][l]), (chain, f, l)
+        assert np.array_equal(ctx.readback(PLANE.FINAL_F32).view(np.uint32), ref["final"].view(np.uint32)), (chain, f)
         c = ctx.counters()
-        assert [c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow] == list(o.counters.rays)
-        assert c.kernel_launches >= 6                       # + k_shadow_tail
-    # the stage alone, and switched off again
-    ctx.set_params(vk.make_params(w, h, frame=0, shadow_tail_budget=budget)); ctx.run_stage(vk.STAGE.SHADOW)
-    a = [ctx.readback(PLANE.SHADOW0 + l) for l in range(3)]
-    ctx.set_params(vk.make_params(w, h, frame=0, shadow_tail_budget=-1)); ctx.run_stage(vk.STAGE.SHADOW)
-    for l in range(3):
-        assert np.array_equal(a[l], ctx.readback(PLANE.SHADOW0 + l))
-    ctx.close()
+        assert [c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow] == list(o.counters.rays), (chain, f)
+p = vk.make_params(w, h, mode=vk.MODE_RAYTRACING, spp=2, shadow_samples=9, faithful_rng=0, frame=0)
+ctx.set_params(p); ctx.reset_history(); ctx.render()
+assert np.array_equal(ctx.readback(PLANE.FINAL_F32).view(np.uint32), o.raytrace(cam, p).view(np.uint32))
+print("STRESS_OK")
+"""
+
+
+def test_stack_overflow_and_warp_queue_fallback_change_no_bit():
+    """libvkp_stress.so is libvkp.so compiled with VKP_SSTACK=2 (all but two levels of every traversal stack live in the local-memory
+    overflow array) and VKP_WQ_CAP=48 (the warp-cooperative traversal of k_chain overflows its queue on most rays and restarts in
+    the serial general traversal).  Hybrid frames with the overlapped and the inline chain and a Raytraced frame with 9 shadow
+    samples (warp-per-pixel kernel) must stay bit-identical to the oracle.  Own process: the library is chosen at load time."""
+    import subprocess
+    import sys
+    lib = os.path.join(vk.lib_dir(), "libvkp_stress.so")
+    assert os.path.exists(lib), "make stress"
+    env = dict(os.environ, VKP_LIB=lib)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _STRESS_SCRIPT % root], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "STRESS_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def test_cuda_path_against_the_reference_shader_binaries():

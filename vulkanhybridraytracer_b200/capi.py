@@ -75,6 +75,8 @@ def load_vkp():
         "vkp_build_blas": (i, [vp]),
         "vkp_set_builder": (i, [vp, i]),
         "vkp_build_tlas": (i, [vp, i]),
+        "vkp_get_build_stats": (i, [vp, P(T.BuildStats)]),
+        "vkp_set_l2_persistence": (i, [vp, i]),
         "vkp_set_camera": (i, [vp, P(T.Camera)]),
         "vkp_set_params": (i, [vp, P(T.Params)]),
         "vkp_set_tiling": (i, [vp, i, i, i, i]),
@@ -213,7 +215,7 @@ def decode_image(path):
 
 
 def make_params(width, height, mode=MODE_HYBRID, spp=1, shadow_samples=1, max_bounces=8, frame=0, denoise_frame=None,
-                faithful_rng=1, denoise_cover_remainder=1, debug_target=0, wavefront=0, fuse_denoise=0, reproject_fix=0, shadow_tail_budget=0):
+                faithful_rng=1, denoise_cover_remainder=1, debug_target=0, wavefront=0, fuse_denoise=0, reproject_fix=0, denoiser=0):
     p = T.Params()
     p.width, p.height, p.mode, p.spp, p.shadow_samples, p.max_bounces = width, height, mode, spp, shadow_samples, max_bounces
     p.frame = frame
@@ -222,7 +224,7 @@ def make_params(width, height, mode=MODE_HYBRID, spp=1, shadow_samples=1, max_bo
     p.wavefront = wavefront
     p.fuse_denoise = fuse_denoise
     p.reproject_fix = reproject_fix
-    p.shadow_tail_budget = shadow_tail_budget
+    p.denoiser = denoiser
     return p
 
 
@@ -391,6 +393,15 @@ class Context:
 
     def build_tlas(self, update=False):
         self._ck(self.L.vkp_build_tlas(self.h, 1 if update else 0), "vkp_build_tlas")
+
+    def build_stats(self):
+        """vkp_get_build_stats as a dict (build / refit milliseconds, heights, arena and L2 window)."""
+        b = T.BuildStats()
+        self._ck(self.L.vkp_get_build_stats(self.h, C.byref(b)), "vkp_get_build_stats")
+        return {k: getattr(b, k) for k, _ in T.BuildStats._fields_ if k != "_pad"}
+
+    def set_l2_persistence(self, on):
+        self._ck(self.L.vkp_set_l2_persistence(self.h, int(on)), "vkp_set_l2_persistence")
 
     def upload_scene(self, scene: HostScene):
         """Renderer::load_data_to_gpu + create_*_acceleration_structure in C-ABI calls."""

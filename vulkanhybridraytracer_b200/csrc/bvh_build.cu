@@ -409,70 +409,6 @@ __global__ void k_ploc_permute(int n_leaves, const uint32_t* __restrict__ newpos
     }
 }
 
-// ---- 4-wide collapse ---------------------------------------------------------------------------------------------
-// Every other level of the binary tree is folded into its parent: a kept internal node at even depth becomes a 128-byte
-// node holding the boxes (SoA) and references of up to 4 grandchildren (a child that is itself a leaf stays one entry).
-// Traversal then needs half as many dependent node fetches per ray, which is what bounds the slowest warps.
-#define VKP_W_EMPTY 0xfffffffdu
-
-__global__ void k_w_mark(const int* __restrict__ parent, const uint32_t* __restrict__ keep, int n_internal, int root, uint32_t* __restrict__ is4)
-{
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_internal) return;
-    uint32_t v = 0;
-    if (keep[k]) {
-        int depth = 0;
-        for (int p = (k == root ? -1 : parent[k]); p >= 0; p = (p == root ? -1 : parent[p])) depth++;
-        v = (depth & 1) ? 0u : 1u;
-    }
-    is4[k] = v;
-}
-
-__device__ __forceinline__ void w_entry(int e, const float* __restrict__ boxes, const uint32_t* __restrict__ items, const int2* __restrict__ range,
-                                        const float4* __restrict__ ibox, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ rank4, int ref_items,
-                                        float lo[3], float hi[3], uint32_t& ref)
-{
-    if (e < 0) {
-        const int pos = ~e;
-        const float* b = boxes + 6 * (size_t)items[pos];
-        lo[0] = b[0]; lo[1] = b[1]; lo[2] = b[2]; hi[0] = b[3]; hi[1] = b[4]; hi[2] = b[5];
-        ref = 0x80000000u | ((ref_items ? items[pos] : (uint32_t)pos) << 3);
-    } else {
-        float4 l = ibox[2 * (size_t)e], h = ibox[2 * (size_t)e + 1];
-        lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; hi[0] = h.x; hi[1] = h.y; hi[2] = h.z;
-        int2 r = range[e];
-        ref = keep[e] ? rank4[e] : (0x80000000u | ((uint32_t)r.x << 3) | (uint32_t)(r.y - r.x));
-    }
-}
-
-__global__ void k_w_emit(const float* __restrict__ boxes, const uint32_t* __restrict__ items, int n_internal, const int2* __restrict__ child,
-                         const int2* __restrict__ range, const float4* __restrict__ ibox, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ is4,
-                         const uint32_t* __restrict__ rank4, int ref_items, float4* __restrict__ nodes4)
-{
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_internal || !is4[k]) return;
-    int e[4]; int ne = 0;
-    const int2 c = child[k];
-    const int cc[2] = {c.x, c.y};
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-        const int ci = cc[s];
-        if (ci >= 0 && keep[ci]) { const int2 g = child[ci]; e[ne++] = g.x; e[ne++] = g.y; }      // absorbed level
-        else e[ne++] = ci;
-    }
-    float lo[4][3], hi[4][3]; uint32_t ref[4];
-    for (int j = 0; j < 4; j++) {
-        if (j < ne) w_entry(e[j], boxes, items, range, ibox, keep, rank4, ref_items, lo[j], hi[j], ref[j]);
-        else { lo[j][0] = lo[j][1] = lo[j][2] = 0.f; hi[j][0] = hi[j][1] = hi[j][2] = 0.f; ref[j] = VKP_W_EMPTY; }
-    }
-    float4* o = nodes4 + 8 * (size_t)rank4[k];
-    o[0] = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]); o[1] = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]);
-    o[2] = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]); o[3] = make_float4(hi[0][0], hi[1][0], hi[2][0], hi[3][0]);
-    o[4] = make_float4(hi[0][1], hi[1][1], hi[2][1], hi[3][1]); o[5] = make_float4(hi[0][2], hi[1][2], hi[2][2], hi[3][2]);
-    o[6] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), __uint_as_float(ref[2]), __uint_as_float(ref[3]));
-    o[7] = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
 inline unsigned blocks_for(uint32_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
 cudaError_t fit_and_emit(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches, bool read_height = true)
@@ -495,47 +431,9 @@ cudaError_t fit_and_emit(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches
                                                         B.ibox.as<float4>(), B.keep.as<uint32_t>(), B.rank.as<uint32_t>(), B.nodes.as<vkp_bvh_node>(), B.root, B.leaf_max == 1 ? 1 : 0);
     if (launches) *launches += 2;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (B.n_nodes4 > 0) {      // refit: the wide layout follows the new boxes (topology, marks and ranks are unchanged)
-        k_w_emit<<<blocks_for(n - 1, 256), 256, 0, s>>>(sc.boxes.as<float>(), B.items.as<uint32_t>(), (int)(n - 1), B.child.as<int2>(), B.range.as<int2>(),
-                                                        B.ibox.as<float4>(), B.keep.as<uint32_t>(), B.is4.as<uint32_t>(), B.rank4.as<uint32_t>(), B.leaf_max == 1 ? 1 : 0,
-                                                        B.nodes4.as<float4>());
-        if (launches) *launches += 1;
-    }
     // a refit keeps the topology, hence the height: no D2H (a copy into pageable memory would make the per-frame path wait for the device)
     if (!read_height) return cudaSuccess;
     return cudaMemcpyAsync(&B.height, height_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
-}
-
-// builds the 4-wide layout on top of a finished binary tree (marks, ranks, first emit) and sets B.root_ref4
-cudaError_t build_wide(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches)
-{
-    const uint32_t n = B.n_prims;
-    cudaError_t e;
-    B.n_nodes4 = 0;
-    if (n <= 1) { B.root_ref4 = 0x80000000u; return cudaSuccess; }      // one leaf (TLAS: instance 0, BLAS: item 0 / degenerate)
-    const uint32_t ni = n - 1;
-    if ((e = B.is4.ensure(sizeof(uint32_t) * ni)) != cudaSuccess) return e;
-    if ((e = B.rank4.ensure(sizeof(uint32_t) * ni)) != cudaSuccess) return e;
-    k_w_mark<<<blocks_for(ni, 256), 256, 0, s>>>(B.parent.as<int>(), B.keep.as<uint32_t>(), (int)ni, B.root, B.is4.as<uint32_t>());
-    if ((e = vkpsort::exclusive_scan<uint32_t>(s, B.is4.as<uint32_t>(), B.rank4.as<uint32_t>(), ni, sc.cub_tmp.p, launches)) != cudaSuccess) return e;
-    uint32_t last_rank = 0, last_is = 0, root_keep = 0, root_rank = 0; int2 root_range = make_int2(0, 0);
-    cudaMemcpyAsync(&last_rank, B.rank4.as<uint32_t>() + (ni - 1), 4, cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(&last_is, B.is4.as<uint32_t>() + (ni - 1), 4, cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(&root_keep, B.keep.as<uint32_t>() + B.root, 4, cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(&root_rank, B.rank4.as<uint32_t>() + B.root, 4, cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(&root_range, B.range.as<int2>() + B.root, 8, cudaMemcpyDeviceToHost, s);
-    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
-    const uint32_t n4 = last_rank + last_is;
-    if (!root_keep) {            // the whole tree is one (multi-item) leaf
-        B.root_ref4 = 0x80000000u | ((uint32_t)root_range.x << 3) | (uint32_t)(root_range.y - root_range.x);
-        return cudaSuccess;
-    }
-    if ((e = B.nodes4.ensure(sizeof(float4) * 8 * (size_t)n4)) != cudaSuccess) return e;
-    B.n_nodes4 = n4; B.root_ref4 = root_rank;
-    k_w_emit<<<blocks_for(ni, 256), 256, 0, s>>>(sc.boxes.as<float>(), B.items.as<uint32_t>(), (int)ni, B.child.as<int2>(), B.range.as<int2>(), B.ibox.as<float4>(),
-                                                 B.keep.as<uint32_t>(), B.is4.as<uint32_t>(), B.rank4.as<uint32_t>(), B.leaf_max == 1 ? 1 : 0, B.nodes4.as<float4>());
-    if (launches) *launches += 2;
-    return cudaGetLastError();
 }
 
 } // namespace
@@ -554,7 +452,7 @@ cudaError_t bvh_instance_boxes(cudaStream_t s, const DInstance* inst, uint32_t n
     return cudaGetLastError();
 }
 
-static cudaError_t ploc_hierarchy(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches)
+static cudaError_t ploc_hierarchy(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches, int* host_syncs)
 {
     const int n = (int)B.n_prims;
     cudaError_t e;
@@ -589,6 +487,7 @@ static cudaError_t ploc_hierarchy(cudaStream_t s, BuildScratch& sc, Bvh& B, int*
         if ((e = cudaMemcpyAsync(&last_scan, sc.ploc_scan.as<unsigned long long>() + (n_cur - 1), 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         if ((e = cudaMemcpyAsync(&last_flag, sc.ploc_flags.as<unsigned long long>() + (n_cur - 1), 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        if (host_syncs) *host_syncs += 1;
         const unsigned long long tot = last_scan + last_flag;
         const int merges = (int)(tot >> 32), survivors = (int)(tot & 0xffffffffull);
         if (merges <= 0) return cudaErrorUnknown;              // cannot happen: the globally closest pair is always mutual
@@ -600,6 +499,7 @@ static cudaError_t ploc_hierarchy(cudaStream_t s, BuildScratch& sc, Bvh& B, int*
     int root = 0;
     if ((e = cudaMemcpyAsync(&root, sc.ploc_cid[cur].as<int>(), 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    if (host_syncs) *host_syncs += 1;
     B.root = root;
     // depth-first leaf order, contiguous ranges, permuted leaf references
     k_ploc_ranges<<<blocks_for(n, 256), 256, 0, s>>>(n, B.child.as<int2>(), B.parent.as<int>(), sc.ploc_icnt.as<uint32_t>(), root, B.range.as<int2>(), sc.ploc_nn.as<uint32_t>());
@@ -613,7 +513,7 @@ static cudaError_t ploc_hierarchy(cudaStream_t s, BuildScratch& sc, Bvh& B, int*
     return cudaGetLastError();
 }
 
-cudaError_t bvh_build(cudaStream_t s, BuildScratch& sc, uint32_t n, int leaf_max, Bvh& B, int* launches, int builder)
+cudaError_t bvh_build(cudaStream_t s, BuildScratch& sc, uint32_t n, int leaf_max, Bvh& B, int* launches, int builder, int* host_syncs)
 {
     cudaError_t e;
     B.n_prims = n; B.leaf_max = leaf_max;
@@ -624,7 +524,6 @@ cudaError_t bvh_build(cudaStream_t s, BuildScratch& sc, uint32_t n, int leaf_max
     if (n <= 1) {
         if (n == 1 && (e = cudaMemsetAsync(B.items.p, 0, sizeof(uint32_t), s)) != cudaSuccess) return e;
         B.root_ref = 0x80000000u;     // a single leaf: first item 0, one item (an empty BLAS holds one degenerate triangle)
-        B.root_ref4 = 0x80000000u; B.n_nodes4 = 0;
         return fit_and_emit(s, sc, B, launches);
     }
     if ((e = B.child.ensure(sizeof(int2) * ni)) != cudaSuccess) return e;
@@ -654,7 +553,7 @@ cudaError_t bvh_build(cudaStream_t s, BuildScratch& sc, uint32_t n, int leaf_max
     B.root = 0;
     bool fitted = false;
     if (builder == 1) {
-        if ((e = ploc_hierarchy(s, sc, B, launches)) != cudaSuccess) return e;
+        if ((e = ploc_hierarchy(s, sc, B, launches, host_syncs)) != cudaSuccess) return e;
         fitted = true;
     } else {
         k_hierarchy<<<blocks_for(ni, 256), 256, 0, s>>>(sc.keys_alt.as<uint32_t>(), (int)n, B.child.as<int2>(), B.parent.as<int>(), B.range.as<int2>());
@@ -671,8 +570,9 @@ cudaError_t bvh_build(cudaStream_t s, BuildScratch& sc, uint32_t n, int leaf_max
     if ((e = fit_and_emit(s, sc, B, launches)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(&B.root_ref, &B.nodes.as<vkp_bvh_node>()[0].ref, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    if (host_syncs) *host_syncs += 1;
     B.n_nodes = 1u + 2u * (last_rank + last_keep);
-    return build_wide(s, sc, B, launches);
+    return cudaSuccess;
 }
 
 cudaError_t bvh_refit(cudaStream_t s, BuildScratch& sc, Bvh& B, int* launches)

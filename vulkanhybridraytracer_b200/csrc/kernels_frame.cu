@@ -168,11 +168,12 @@ __device__ __forceinline__ void shade_miss(const DScene& S, float3 rayDir, Paylo
 }
 
 // hybridHit.rchit:24-184 (RT == false) / closesthit.rchit:26-186 (RT == true)
-// WARP == true (k_raytrace_warp): the 32 lanes of the warp hold the SAME path; everything is computed redundantly
-// (one SIMT instruction stream, broadcast loads) except the per-light shadow samples, which are spread over the lanes.
-template <bool RT, bool WARP = false>
-__device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, float3 rayD, const HitRec& h, Payload& prd,
-                          unsigned int& n_secondary, TravCount* tcp)
+// WARP != 0: the 32 lanes of the warp hold the SAME path; everything is computed redundantly (one SIMT instruction stream,
+// broadcast loads) except the shadow rays: WARP == 1 (k_raytrace_warp) spreads the per-light shadow samples over the lanes,
+// WARP == 2 (k_chain) traces the one shadow ray per light with the whole warp (warp_trace).
+template <bool RT, int WARP = 0>
+__device__ void shade_hit(const DScene& S, uint32_t* __restrict__ sstack, const vkp_params& P, float3 rayO, float3 rayD, const HitRec& h, Payload& prd,
+                          unsigned int& n_secondary, TravCount* tcp, const WarpQueue* wq = nullptr)
 {
     const DInstance& I = S.instances[h.inst];
     const float b0 = 1.0f - h.u - h.v, b1 = h.u, b2 = h.v;
@@ -222,7 +223,7 @@ __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, flo
         const float NdotH = clamp01(dot3(N, H));
         float shadowFactor = RT ? 0.0f : 1.0f;
 
-        if (RT && WARP) {
+        if (RT && WARP == 1) {
             // closesthit.rchit:99-120 with the samples of this light traced by different lanes.  Every traced sample
             // advances the RNG by exactly two LCG steps whatever it hits, so sample a starts from LCG^(2a)(seed); the
             // unshadowed count is an integer, so the sum does not depend on the order.
@@ -238,7 +239,7 @@ __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, flo
                             if (advance) for (int r = 0; r < 2 * a; r++) sd = 1664525u * sd + 1013904223u;
                             float3 dir = sample_disk(light, worldPos, L, sd, false);
                             HitRec sh; n_secondary++;
-                            unshadowed = !trace_ray<true>(S, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, nullptr, tcp);
+                            unshadowed = !trace_ray<true>(S, sstack, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, nullptr, tcp);
                         }
                         lit += (unsigned)__popc(__ballot_sync(0xffffffffu, unshadowed));
                     }
@@ -261,7 +262,7 @@ __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, flo
                     if (light_distance < light_max_distance) {
                         float3 dir = sample_disk(light, worldPos, L, prd.seed, advance);
                         HitRec sh; n_secondary++;
-                        shadowed = trace_ray<true>(S, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, nullptr, tcp);
+                        shadowed = trace_ray<true>(S, sstack, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, nullptr, tcp);
                     }
                     if (!shadowed) shadowFactor += 1.0f;
                 }
@@ -291,7 +292,8 @@ __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, flo
                     if (light_distance < light_max_distance) {
                         float3 dir = sample_disk(light, worldPos, L, prd.seed, advance);
                         HitRec sh; n_secondary++;
-                        shadowed = trace_ray<true>(S, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, nullptr, tcp);
+                        if (WARP == 2) shadowed = warp_trace<true>(S, *wq, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, tcp);
+                        else shadowed = trace_ray<true>(S, sstack, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, nullptr, tcp);
                     }
                     if (!shadowed) shadowFactor += 1.0f;
                 }
@@ -338,8 +340,10 @@ __device__ void shade_hit(const DScene& S, const vkp_params& P, float3 rayO, flo
 }
 
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, VKP_LB_GBUFFER) k_gbuffer(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_GBUFFER) k_gbuffer(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
     const long long t_start = clock64();
     const unsigned int vb = virtual_block(F.cta_order[0]);
     const Pixel px = pixel_of_block(F, vb);
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(128, VKP_LB_GBUFFER) k_gbuffer(const __grid_co
         const size_t i = (size_t)px.y * W + px.x;
         float3 o, d; camera_ray(F.cam, px.x, px.y, 0.5f, 0.5f, W, H, o, d);
         HitRec h; nrays = 1;
-        bool hit = trace_ray<false>(S, o + d * 1e-2f, d, 0.001f, 10000.0f, h, nullptr, tcp);
+        bool hit = trace_ray<false>(S, sstack, o + d * 1e-2f, d, 0.001f, 10000.0f, h, nullptr, tcp);
         F.hit_ids[i] = make_int2(h.inst, h.prim);
         if (!hit) {
             // skybox.frag:16-21
@@ -450,13 +454,14 @@ __device__ __forceinline__ LightGeom light_geom(const vkp_light& light, float3 p
 // thread: DESIGN.md section 4).  With the non-faithful RNG the seed a light starts from is replayed from the
 // cheap per-light conditions of the lights before it.
 // MINB = resident CTAs per SM the register budget is set for: 8 (64 registers) when a thread traces one ray and waits on it
-// (latency-bound: 0.39 -> 0.36 ms at 1080p), 5 (96 registers, no spills) when it loops over many soft-shadow samples
-// (issue-bound: cfg5 209 ms against 227 ms at 8).
-// SPILL: the frame traces one ray per (pixel, light) and a thread hands a ray that is still unanswered after
-// F.spill_budget child-pair fetches to k_shadow_tail (below) instead of setting the duration of the whole kernel with it.
-template <int MINB, bool SPILL>
-__global__ void __launch_bounds__(128, MINB) k_shadow(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+// (latency-bound), 5 (96 registers) when it loops over many soft-shadow samples (issue-bound: cfg5).
+// ONE: the frame traces one sample per light (BASELINE configs[1]): no sample loop, so nothing of the light / G-buffer state
+// stays in registers across the traversal.
+template <int MINB, bool ONE>
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, MINB) k_shadow(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
     const long long t_start = clock64();
     const unsigned int vb = virtual_block(F.cta_order[1]);      // = light * n_cta + pixel block
     const int l = (int)fast_div(F, vb, F.magic_n_cta, (unsigned int)F.n_cta);
@@ -482,7 +487,6 @@ __global__ void __launch_bounds__(128, MINB) k_shadow(const __grid_constant__ DS
             const vkp_light light = S.lights[l];
             const LightGeom g = light_geom(light, position, N);
             float shadowFactor = 0.0f;
-            bool spilled = false;
             if (g.NdotL > 0.0f) {
                 if (g.dist < g.maxd) {
                     // the RNG is only needed when rays are traced: TEA (16 rounds) is the most expensive part of an unlit pixel
@@ -494,61 +498,28 @@ __global__ void __launch_bounds__(128, MINB) k_shadow(const __grid_constant__ DS
                                 for (int r = 0; r < 2 * shadowSamples; r++) seed = 1664525u * seed + 1013904223u;   // two rnd() per sampleDisk
                         }
                     }
-                    if (SPILL) {
+                    if (ONE) {
                         const float3 dir = sample_disk(light, position, g.L, seed, advance);
-                        const float3 org = position + dir * 1e-1f;
                         HitRec h; nrays++;
-                        const bool hit = trace_ray<true, false, true>(S, org, dir, 0.001f, g.dist + 1.0f, h, nullptr, tcp, F.spill_budget,
-                                                                      F.spill_cnt + 2 * F.spill_parity, F.spill_cap);
-                        if (h.prim == VKP_TRACE_SPILLED) {
-                            float4* rec = F.spill_rec + 2u * (size_t)h.inst;
-                            rec[0] = make_float4(org.x, org.y, org.z, g.dist + 1.0f);
-                            rec[1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float((unsigned int)(l * plane + i)));
-                            spilled = true;
-                        } else if (!hit) shadowFactor += 1.0f;
+                        if (!trace_ray<true>(S, sstack, position + dir * 1e-1f, dir, 0.001f, g.dist + 1.0f, h, nullptr, tcp)) shadowFactor += 1.0f;
                     } else
                     for (int s = 0; s < shadowSamples; s++) {
                         const float3 dir = sample_disk(light, position, g.L, seed, advance);
                         HitRec h; nrays++;
-                        if (!trace_ray<true>(S, position + dir * 1e-1f, dir, 0.001f, g.dist + 1.0f, h, nullptr, tcp)) shadowFactor += 1.0f;
+                        if (!trace_ray<true>(S, sstack, position + dir * 1e-1f, dir, 0.001f, g.dist + 1.0f, h, nullptr, tcp)) shadowFactor += 1.0f;
                     }
                 } else {
                     for (int s = 0; s < shadowSamples; s++) shadowFactor += 1.0f;      // beyond maxDistance: unshadowed (shadowRaygen.rgen:81-83)
                 }
                 shadowFactor /= (float)shadowSamples;
             }
-            if (!spilled) F.shadow[l * plane + i] = vkp_unorm8(shadowFactor);      // a spilled ray's byte is written by k_shadow_tail
+            F.shadow[l * plane + i] = vkp_unorm8(shadowFactor);
         }
     }
     add_counter(F.counters, 1, nrays);
     if (F.count_trav) add_trav(F.counters, tc, (1u << 28) | ((unsigned)l << 23) | (unsigned)(px.valid ? px.y * F.p.width + px.x : 0));
     record_cost(F.cta_cost[1], vb, t_start);
 }
-
-// The rays k_shadow<., true> gave up on, one warp per ray (warp_any_hit, vkp_bvh.cuh).  Warps take rays from the queue with an
-// atomic head; the block that starts first clears the counter pair of the other parity for the next frame's k_shadow, so no
-// memset sits between the kernels of a frame.  shadowFactor of a one-sample ray is 0 or 1: the byte is 0 or 255.
-#if !VKP_WIDE
-__global__ void __launch_bounds__(128) k_shadow_tail(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
-{
-    unsigned int* cnt = F.spill_cnt + 2 * F.spill_parity;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned int* other = F.spill_cnt + 2 * (F.spill_parity ^ 1); other[0] = 0u; other[1] = 0u; }
-    const unsigned int n = min(cnt[0], F.spill_cap);
-    const int lane = (int)(threadIdx.x & 31u);
-    TravCount tc = {0u, 0u, 0u};
-    TravCount* const tcp = F.count_trav ? &tc : nullptr;
-    while (true) {
-        unsigned int r = 0u;
-        if (lane == 0) r = atomicAdd(cnt + 1, 1u);
-        r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= n) break;
-        const float4 a = F.spill_rec[2u * (size_t)r], b = F.spill_rec[2u * (size_t)r + 1u];
-        const bool hit = warp_any_hit(S, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), 0.001f, a.w, tcp);
-        if (lane == 0) F.shadow[__float_as_uint(b.w)] = hit ? (uint8_t)0 : (uint8_t)255;
-    }
-    if (F.count_trav) add_trav(F.counters, tc);
-}
-#endif
 
 // blur.comp:35-82 for one pixel and one light, with runtime W/H/NLIGHTS and an integer motion fetch; returns the new
 // R8 history value (pixels outside the faithful dispatch area keep their history)
@@ -665,23 +636,24 @@ __device__ __forceinline__ void first_bounce(int shadingMode, const vkp_material
 }
 
 // The bounce chain of hybridRaygen.rgen:153-170 depends only on the G-buffer, not on the shadow / denoise passes, so in
-// chain mode 2 it runs in this kernel on a second, high-priority stream CONCURRENTLY with k_shadow + k_denoise; the
-// per-bounce colours are stored (<= 8 per path) and k_resolve<2> multiplies them into rayColor in the reference's order.
-__global__ void __launch_bounds__(128, VKP_LB_CHAIN) k_chain(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+// chain mode 2 it runs on a second, high-priority stream CONCURRENTLY with k_shadow + k_denoise; the per-bounce colours are
+// stored (<= 8 per path) and k_resolve<2> multiplies them into rayColor in the reference's order.
+//
+// k_chain_scan compacts the mirror / glass pixels (3 % of the default frame) into a path list: one atomic per warp, slots by
+// ballot + popc prefix.  k_chain is a PERSISTENT grid fed from that queue: every warp takes the next path with one atomic and
+// walks it with ALL 32 lanes -- the shading is computed redundantly (one instruction stream, broadcast loads), every ray of the
+// path is traced cooperatively (warp_trace, vkp_bvh.cuh).  A path is a chain of up to 8 dependent closest-hit rays and its longest
+// ray set the duration of the whole kernel when one thread walked it alone (round 1: 270 us for 3 % of the pixels).
+__global__ void __launch_bounds__(128) k_chain_scan(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     const Pixel px = pixel_of_thread(F);
-    unsigned int n_refl = 0, n_sec = 0;
-    TravCount tc = {0u, 0u, 0u};
-    TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
     bool path = false;
     size_t i = 0;
-    float4 pos4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (px.valid) {
         i = (size_t)px.y * F.p.width + px.x;
-        pos4 = unpack_half4(F.position[i]);
-        path = (int)material_by_float_index(S, pos4.w).shadingMetallicRoughness[0] != 0 && F.p.max_bounces > 0;
+        const float matIdx = vkp_f16_to_f32((uint16_t)(F.position[i].y >> 16));
+        path = (int)material_by_float_index(S, matIdx).shadingMetallicRoughness[0] != 0 && F.p.max_bounces > 0;
     }
-    // compaction: one atomic per warp, slots by ballot + popc prefix
     const unsigned mask = __ballot_sync(0xffffffffu, path);
     if (mask == 0u) return;
     const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
@@ -691,10 +663,28 @@ __global__ void __launch_bounds__(128, VKP_LB_CHAIN) k_chain(const __grid_consta
     if (path) {
         const unsigned slot = base + __popc(mask & ((1u << lane) - 1u));
         F.chain_slot[i] = (int)slot;
+        F.chain_pix[slot] = (int)i;
+    }
+}
+
+// One THREAD per queued path (chain mode 2, the default): all paths are in flight at once -- a path is a chain of dependent
+// rays, so what counts is how many of them overlap, and one thread per path keeps every path of the frame resident.
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
+    const unsigned int n_paths = F.path_count[0];
+    unsigned int n_refl = 0, n_sec = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
+    for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
+        const size_t i = (size_t)F.chain_pix[slot];
+        const int py = (int)(i / (size_t)F.p.width), pxl = (int)(i - (size_t)py * F.p.width);
+        const float4 pos4 = unpack_half4(F.position[i]);
         float4* rec = F.chain_buf + (size_t)slot * VKP_CHAIN_MAX;
         const vkp_material& mat = material_by_float_index(S, pos4.w);
         const int shadingMode = (int)mat.shadingMetallicRoughness[0];
-        float4 nrm4 = unpack_half4(F.normal[i]);
+        const float4 nrm4 = unpack_half4(F.normal[i]);
         const float3 position = xyz(pos4);
         const float3 N = normalize3(xyz(nrm4) * 2.0f - f3s(1.0f));
         const float3 camPosition = f3(F.cam.inv_view[12], F.cam.inv_view[13], F.cam.inv_view[14]);
@@ -702,13 +692,13 @@ __global__ void __launch_bounds__(128, VKP_LB_CHAIN) k_chain(const __grid_consta
         float3 origin = f3s(0.0f), direction = f3s(0.0f);
         if (S.n_lights > 0) first_bounce(shadingMode, mat, position, N, V, origin, direction);   // upstream sets them inside the light loop
         Payload prd;
-        prd.seed = tea16((uint32_t)px.y * (uint32_t)F.p.width + (uint32_t)px.x, (uint32_t)F.p.frame);
+        prd.seed = tea16((uint32_t)py * (uint32_t)F.p.width + (uint32_t)pxl, (uint32_t)F.p.frame);
         int n = 0;
         for (int depth = 0; depth < F.p.max_bounces; depth++) {
             float3 ro = origin + direction * 1e-2f;
             HitRec h; n_refl++;
-            bool hit = trace_ray<false>(S, ro, direction, 0.001f, 1000.0f, h, nullptr, tcp);
-            if (hit) shade_hit<false>(S, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
+            const bool hit = trace_ray<false>(S, sstack, ro, direction, 0.001f, 1000.0f, h, nullptr, tcp);
+            if (hit) shade_hit<false>(S, sstack, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
             rec[n] = make_float4(prd.color.x, prd.color.y, prd.color.z, 0.0f);
             n++;
             if (!hit || !(prd.scatter > 0.0f)) break;
@@ -721,12 +711,68 @@ __global__ void __launch_bounds__(128, VKP_LB_CHAIN) k_chain(const __grid_consta
     if (F.count_trav) add_trav(F.counters, tc);
 }
 
+// One WARP per queued path (chain mode 3): a PERSISTENT grid fed from the path queue -- every warp takes the next path with one
+// atomic and walks it with all 32 lanes: the shading is computed redundantly (one instruction stream, broadcast loads), every ray
+// of the path is traced cooperatively (warp_trace, vkp_bvh.cuh).  Built to shorten the critical path of a path; measured on the
+// 1080p default frame it is 8x SLOWER than one thread per path (2.1 ms against 0.27): 62 000 paths x 32 lanes want 2 M threads
+// where a B200 holds 57 000 at this kernel's register count, so the paths run in 35 consecutive rounds instead of all at once.
+// Kept selectable (vkp_params.wavefront = 3) and bit-identical; DESIGN.md section 4 has the numbers.
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_warp(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    __shared__ uint32_t s_wq[VKP_WQ_SMEM_WORDS];
+    const WarpQueue Q = warp_queue_of(s_wq);
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_paths = F.path_count[0];
+    unsigned int n_refl = 0, n_sec = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
+    while (true) {
+        unsigned int slot = 0u;
+        if (lane == 0) slot = atomicAdd(&F.path_count[1], 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= n_paths) break;
+        const size_t i = (size_t)F.chain_pix[slot];
+        const int py = (int)(i / (size_t)F.p.width), pxl = (int)(i - (size_t)py * F.p.width);
+        const float4 pos4 = unpack_half4(F.position[i]);
+        float4* rec = F.chain_buf + (size_t)slot * VKP_CHAIN_MAX;
+        const vkp_material& mat = material_by_float_index(S, pos4.w);
+        const int shadingMode = (int)mat.shadingMetallicRoughness[0];
+        const float4 nrm4 = unpack_half4(F.normal[i]);
+        const float3 position = xyz(pos4);
+        const float3 N = normalize3(xyz(nrm4) * 2.0f - f3s(1.0f));
+        const float3 camPosition = f3(F.cam.inv_view[12], F.cam.inv_view[13], F.cam.inv_view[14]);
+        const float3 V = normalize3(camPosition - position);
+        float3 origin = f3s(0.0f), direction = f3s(0.0f);
+        if (S.n_lights > 0) first_bounce(shadingMode, mat, position, N, V, origin, direction);   // upstream sets them inside the light loop
+        Payload prd;
+        prd.seed = tea16((uint32_t)py * (uint32_t)F.p.width + (uint32_t)pxl, (uint32_t)F.p.frame);
+        int n = 0;
+        for (int depth = 0; depth < F.p.max_bounces; depth++) {
+            float3 ro = origin + direction * 1e-2f;
+            HitRec h; n_refl++;
+            const bool hit = warp_trace<false>(S, Q, ro, direction, 0.001f, 1000.0f, h, tcp);
+            if (hit) shade_hit<false, 2>(S, nullptr, F.p, ro, direction, h, prd, n_sec, tcp, &Q); else shade_miss(S, direction, prd);
+            if (lane == 0) rec[n] = make_float4(prd.color.x, prd.color.y, prd.color.z, 0.0f);
+            n++;
+            if (!hit || !(prd.scatter > 0.0f)) break;
+            origin = prd.origin; direction = prd.direction;
+        }
+        if (lane == 0) F.chain_len[slot] = n;
+    }
+    add_counter(F.counters, 2, lane == 0 ? n_refl : 0u);       // the rays are the warp's: count them once
+    add_counter(F.counters, 3, lane == 0 ? n_sec : 0u);
+    if (F.count_trav) add_trav(F.counters, tc);
+}
+
 // CHAIN == 0: the bounce chain runs inline in this kernel (its latency hides behind the other pixels' shading);
 // CHAIN == 1: mirror / glass pixels are compacted into a path queue consumed by k_bounce, one launch per bounce;
 // CHAIN == 2: the chain was traced by k_chain concurrently with the shadow pass; multiply its stored colours in.
 template <int CHAIN>
-__global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_resolve(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_RESOLVE) k_resolve(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
+    // (only the inline chain, CHAIN == 0, traces rays here; the other instantiations drop the array)
+    __shared__ uint32_t s_trav[CHAIN == 0 ? VKP_TRAV_SMEM_WORDS : 1];
+    uint32_t* const sstack = s_trav + (CHAIN == 0 ? threadIdx.x : 0u);
     const Pixel px = pixel_of_thread(F);
     bool wants_path = false;
     unsigned int n_refl = 0, n_sec = 0;
@@ -840,8 +886,8 @@ __global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_resolve(const __grid_co
             for (int depth = 0; depth < F.p.max_bounces; depth++) {
                 float3 ro = origin + direction * 1e-2f;
                 HitRec h; n_refl++;
-                bool hit = trace_ray<false>(S, ro, direction, 0.001f, 1000.0f, h, nullptr, tcp);
-                if (hit) shade_hit<false>(S, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
+                bool hit = trace_ray<false>(S, sstack, ro, direction, 0.001f, 1000.0f, h, nullptr, tcp);
+                if (hit) shade_hit<false>(S, sstack, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
                 rayColor = rayColor * prd.color;
                 if (!hit || !(prd.scatter > 0.0f)) break;
                 origin = prd.origin; direction = prd.direction;
@@ -868,8 +914,10 @@ __global__ void __launch_bounds__(128, VKP_LB_RESOLVE) k_resolve(const __grid_co
 // One bounce of the reflection / refraction chain of hybridRaygen.rgen:153-170 for every queued path: closest-hit
 // traversal, hit shading (hybridHit.rchit, with its per-light secondary shadow rays) or sky (miss.rmiss), throughput
 // update, then either re-queue (compacted with warp ballot + prefix) or finish the pixel.
-__global__ void __launch_bounds__(128) k_bounce(const __grid_constant__ DScene S, const __grid_constant__ DFrame F, int depth)
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK) k_bounce(const __grid_constant__ DScene S, const __grid_constant__ DFrame F, int depth)
 {
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
     const uint32_t n_in = F.path_count[depth];
     const PathItem* __restrict__ qin = F.path_q[depth & 1];
     PathItem* qout = F.path_q[(depth + 1) & 1];
@@ -890,8 +938,8 @@ __global__ void __launch_bounds__(128) k_bounce(const __grid_constant__ DScene S
             Payload prd; prd.seed = __float_as_uint(item.b.w);
             float3 ro = origin + direction * 1e-2f;
             HitRec h; n_refl++;
-            bool hit = trace_ray<false>(S, ro, direction, 0.001f, 1000.0f, h, nullptr, tcp);
-            if (hit) shade_hit<false>(S, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
+            bool hit = trace_ray<false>(S, sstack, ro, direction, 0.001f, 1000.0f, h, nullptr, tcp);
+            if (hit) shade_hit<false>(S, sstack, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
             rayColor = rayColor * prd.color;
             again = hit && (prd.scatter > 0.0f) && (depth + 1 < F.p.max_bounces);
             if (again) {
@@ -922,8 +970,10 @@ __global__ void __launch_bounds__(128) k_post(const __grid_constant__ DFrame F)
 }
 
 // raygen.rgen:20-81 with NSAMPLES = params.spp; the accumulation target is kept in fp32
-__global__ void __launch_bounds__(128, VKP_LB_RT) k_raytrace(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_RT) k_raytrace(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
     const Pixel px = pixel_of_thread(F);
     unsigned int n_refl = 0, n_sec = 0;
     TravCount tc = {0u, 0u, 0u};
@@ -944,8 +994,8 @@ __global__ void __launch_bounds__(128, VKP_LB_RT) k_raytrace(const __grid_consta
             for (int b = 0; b < F.p.max_bounces; b++) {
                 float3 ro = origin + direction * 1e-2f;
                 HitRec h; n_refl++;
-                bool hit = trace_ray<false>(S, ro, direction, 0.001f, 10000.0f, h, nullptr, tcp);
-                if (hit) shade_hit<true>(S, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
+                bool hit = trace_ray<false>(S, sstack, ro, direction, 0.001f, 10000.0f, h, nullptr, tcp);
+                if (hit) shade_hit<true>(S, sstack, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
                 rayColor = rayColor * prd.color;
                 if (!hit || !(prd.scatter > 0.0f)) break;
                 origin = prd.origin; direction = prd.direction;
@@ -970,8 +1020,10 @@ __global__ void __launch_bounds__(128, VKP_LB_RT) k_raytrace(const __grid_consta
 // raygen.rgen with ONE WARP PER PIXEL, for many shadow samples per hit (BASELINE configs[2]: 64 spp x 64 samples): a pixel
 // is ~12 000 rays, so one thread per pixel leaves a tile-sharded GPU with less than one wave of threads and a ~100 ms
 // critical path per pixel.  Here the lanes share the path and split each light's shadow samples (shade_hit<true, true>).
-__global__ void __launch_bounds__(128, VKP_LB_RT) k_raytrace_warp(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_RT) k_raytrace_warp(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
     const int tpp = F.tile_w * F.tile_h;
     const long long gw = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     const int own_tile = (int)(gw / tpp), within = (int)(gw - (long long)own_tile * tpp);
@@ -997,8 +1049,8 @@ __global__ void __launch_bounds__(128, VKP_LB_RT) k_raytrace_warp(const __grid_c
             for (int b = 0; b < F.p.max_bounces; b++) {
                 float3 ro = origin + direction * 1e-2f;
                 HitRec h; n_refl++;
-                bool hit = trace_ray<false>(S, ro, direction, 0.001f, 10000.0f, h, nullptr, tcp);
-                if (hit) shade_hit<true, true>(S, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
+                bool hit = trace_ray<false>(S, sstack, ro, direction, 0.001f, 10000.0f, h, nullptr, tcp);
+                if (hit) shade_hit<true, 1>(S, sstack, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
                 rayColor = rayColor * prd.color;
                 if (!hit || !(prd.scatter > 0.0f)) break;
                 origin = prd.origin; direction = prd.direction;
@@ -1110,28 +1162,32 @@ __global__ void __launch_bounds__(128) k_deferred(const __grid_constant__ DScene
 
 // traceRayEXT over an explicit ray list (vkp_trace_rays)
 template <bool ANY>
-__global__ void __launch_bounds__(128) k_trace_list(const __grid_constant__ DScene S, const vkp_ray* __restrict__ rays, uint32_t n, vkp_hit* __restrict__ hits)
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK) k_trace_list(const __grid_constant__ DScene S, const vkp_ray* __restrict__ rays, uint32_t n, vkp_hit* __restrict__ hits)
 {
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     vkp_ray r = rays[i];
     HitRec h;
-    bool hit = trace_ray<ANY>(S, f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax, h);
+    bool hit = trace_ray<ANY>(S, sstack, f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax, h);
     vkp_hit o; o.t = hit ? h.t : -1.0f; o.u = h.u; o.v = h.v; o.instance = h.inst; o.primitive = h.prim;
     hits[i] = o;
 }
 
 // instrumented traversal (vkp_trace_stats): node-pair fetches and triangle tests per ray, for build-quality studies
 template <bool ANY>
-__global__ void __launch_bounds__(128) k_trace_stats(const __grid_constant__ DScene S, const vkp_ray* __restrict__ rays, uint32_t n, uint32_t* __restrict__ stats)
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK) k_trace_stats(const __grid_constant__ DScene S, const vkp_ray* __restrict__ rays, uint32_t n, uint32_t* __restrict__ stats)
 {
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     vkp_ray r = rays[i];
     HitRec h;
     uint32_t st[2] = {0u, 0u};
     const long long t0 = clock64();
-    trace_ray<ANY, true>(S, f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax, h, st);
+    trace_ray<ANY, true>(S, sstack, f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax, h, st);
     const long long t1 = clock64();
     stats[3 * (size_t)i] = st[0]; stats[3 * (size_t)i + 1] = st[1]; stats[3 * (size_t)i + 2] = (uint32_t)(t1 - t0);   // SM cycles for this ray's traversal
 }
@@ -1233,20 +1289,14 @@ inline dim3 frame_grid(const FrameLaunch& L)
 
 } // namespace
 
-bool shadow_spills(const FrameLaunch& L) { return !VKP_WIDE && L.frame.p.shadow_samples == 1 && L.frame.spill_budget > 0 && L.frame.spill_rec && L.scene.n_lights > 0 && L.n_own_tiles > 0; }
 cudaError_t launch_gbuffer(const FrameLaunch& L) { k_gbuffer<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
 cudaError_t launch_shadow(const FrameLaunch& L)
 {
     if (L.scene.n_lights == 0) return cudaSuccess;
     dim3 g = frame_grid(L); g.x *= (unsigned)L.scene.n_lights;      // light-major: virtual block = light * n_cta + pixel block
-    if (L.frame.p.shadow_samples >= 4) k_shadow<VKP_LB_SHADOW_MANY, false><<<g, 128, 0, L.stream>>>(L.scene, L.frame);
-#if !VKP_WIDE
-    else if (shadow_spills(L)) {
-        k_shadow<VKP_LB_SHADOW, true><<<g, 128, 0, L.stream>>>(L.scene, L.frame);
-        k_shadow_tail<<<148 * 4, 128, 0, L.stream>>>(L.scene, L.frame);
-    }
-#endif
-    else k_shadow<VKP_LB_SHADOW, false><<<g, 128, 0, L.stream>>>(L.scene, L.frame);
+    if (L.frame.p.shadow_samples >= 4) k_shadow<VKP_LB_SHADOW_MANY, false><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);
+    else if (L.frame.p.shadow_samples == 1) k_shadow<VKP_LB_SHADOW, true><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);
+    else k_shadow<VKP_LB_SHADOW, false><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);
     return cudaGetLastError();
 }
 cudaError_t launch_build_order(cudaStream_t s, uint32_t* cost, uint32_t* order, uint32_t n)
@@ -1263,12 +1313,12 @@ cudaError_t launch_denoise(const FrameLaunch& L)
 }
 cudaError_t launch_resolve(const FrameLaunch& L, int* launches)
 {
-    if (L.frame.p.wavefront == 0 || (L.frame.p.wavefront == 2 && L.frame.p.max_bounces > VKP_CHAIN_MAX)) {
+    if (L.frame.p.wavefront == 0 || (L.frame.p.wavefront >= 2 && L.frame.p.max_bounces > VKP_CHAIN_MAX)) {
         k_resolve<0><<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
-    if (L.frame.p.wavefront == 2) {
+    if (L.frame.p.wavefront >= 2) {
         k_resolve<2><<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);     // launch_chain has run (and been waited for) before
         if (launches) *launches += 1;
         return cudaGetLastError();
@@ -1287,9 +1337,17 @@ cudaError_t launch_resolve(const FrameLaunch& L, int* launches)
 }
 cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream)
 {
-    cudaError_t e = launch_stage_words(stream, L.frame.path_count, nullptr, sizeof(unsigned int));
+    // path_count[0] = number of paths, [1] = head of the queue the persistent warps of mode 3 pull from
+    cudaError_t e = launch_stage_words(stream, L.frame.path_count, nullptr, 2 * sizeof(unsigned int));
     if (e != cudaSuccess) return e;
-    k_chain<<<frame_grid(L), 128, 0, stream>>>(L.scene, L.frame);
+    k_chain_scan<<<frame_grid(L), 128, 0, stream>>>(L.scene, L.frame);
+    if (L.frame.p.wavefront == 3) k_chain_warp<<<148 * VKP_LB_CHAIN, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    else {
+        // every queued path gets its own thread in ONE pass (a second pass would double the critical path): the queue length is
+        // only known on the device, so the grid covers a quarter of the rank's pixels and the threads beyond the queue leave at once
+        const unsigned int px_blocks = frame_grid(L).x;
+        k_chain<<<px_blocks / 4u + 1u, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_post(const FrameLaunch& L) { k_post<<<frame_grid(L), 128, 0, L.stream>>>(L.frame); return cudaGetLastError(); }

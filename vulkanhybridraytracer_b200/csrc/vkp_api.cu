@@ -9,6 +9,8 @@
 #include <cstring>
 #include <memory>
 
+static_assert(sizeof(vkp_build_stats) == 72, "vkp_build_stats layout (types.py BuildStats)");
+
 namespace {
 
 struct MeshRec { DevBuf verts, idx; uint32_t nv = 0, ni = 0; };
@@ -18,11 +20,6 @@ struct BlasRec { int mesh; uint32_t first, count; Bvh bvh; };
 std::string g_create_error;
 
 } // namespace
-
-// default of vkp_params.shadow_tail_budget == 0 when VKP_SHADOW_TAIL is not in the environment (measured: DESIGN.md section 4)
-#ifndef VKP_SHADOW_TAIL_DEFAULT
-#define VKP_SHADOW_TAIL_DEFAULT 0
-#endif
 
 struct vkp_ctx {
     int device = 0;
@@ -42,7 +39,7 @@ struct vkp_ctx {
     // (renderer.h:34,49): frame k+1's VulkanEngine::update work (uploads + TLAS refit) runs on `update_stream` into the set frame k
     // is not reading, overlapped with frame k; the render stream only waits for `ev_updated`.
     struct FrameUniforms {
-        DevBuf lights, inst_trav, instances, tlas_nodes, tlas_nodes4;
+        DevBuf lights, inst_trav, instances, tlas_nodes;
         unsigned long long lights_ver = 0, inst_ver = 0;       // version of the host state this set holds (0 = nothing)
         cudaEvent_t last_use = nullptr;                         // end of the last frame that read the set
         bool consumed = false;                                  // a frame has read it since it was last written
@@ -65,15 +62,9 @@ struct vkp_ctx {
     int rank = 0, world = 1, tile_w = 16, tile_h = 8;
 
     DevBuf position, normal, albedo, motion, material, emissive, hit_ids, final_f32, final_srgb8, shadow, denoised[2];
-    // tail of k_shadow: spill queue (32 B per ray), {count, head} x 2 parities, the default step budget (0 = off)
-    DevBuf spill_rec, spill_cnt;
-    unsigned int spill_cap = 0;
-    int spill_parity = 0;
-    int shadow_tail = VKP_SHADOW_TAIL_DEFAULT;
-    long long spill_cap_env = 0;
     int denoised_cur = 0;
     int plane_w = 0, plane_h = 0, plane_lights = 0;
-    DevBuf counters, io_tmp, io_tmp2, flush, path_q[2], path_count, luts, chain_buf, chain_len, chain_slot;
+    DevBuf counters, io_tmp, io_tmp2, flush, path_q[2], path_count, luts, chain_buf, chain_len, chain_slot, chain_pix;
     cudaStream_t chain_stream = nullptr;
     cudaEvent_t ev_gbuffer = nullptr, ev_chain = nullptr;
     // longest-first CTA schedule of k_gbuffer [0] and k_shadow [1], rebuilt every frame from the previous frame's per-block cycles
@@ -114,6 +105,14 @@ struct vkp_ctx {
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     uint32_t last_launches = 0;
     int build_launches = 0;
+    // acceleration-structure figures (vkp_get_build_stats)
+    vkp_build_stats bstats{};
+    cudaEvent_t ev_build0 = nullptr, ev_build1 = nullptr, ev_refit0 = nullptr, ev_refit1 = nullptr;
+    bool refit_timed = false;
+    // every BLAS's nodes + leaf triangles, compacted into ONE allocation after the builds: the L2 persistence window covers it
+    DevBuf bvh_arena;
+    int l2_persist = -1;          // -1 built-in default, 0 off, 1 on (vkp_set_l2_persistence / VKP_L2_PERSIST)
+    size_t l2_set_aside = 0;
     int builder = 1;      // BLAS hierarchy: 0 = Karras LBVH, 1 = PLOC (default; VKP_BLAS_BUILDER=lbvh|ploc or vkp_set_builder)
 };
 
@@ -205,19 +204,9 @@ int ensure_planes(vkp_ctx* ctx)
     CK(ctx->final_f32.ensure(px * 16)); CK(ctx->final_srgb8.ensure(px * 4)); CK(ctx->final_srgb8_alt.ensure(px * 4));
     CK(ctx->shadow.ensure(px * L)); CK(ctx->denoised[0].ensure(px * L)); CK(ctx->denoised[1].ensure(px * L));
     CK(ctx->counters.ensure(64));
-    {
-        // a budget worth having spills a few per cent of the rays; a full queue is not an error (the thread finishes its ray itself)
-        const size_t rays = px * (size_t)L;
-        size_t cap = rays / 8 > 65536 ? rays / 8 : 65536;
-        if (ctx->spill_cap_env > 0) cap = (size_t)ctx->spill_cap_env;
-        if (cap > 0x7fffffffu) cap = 0x7fffffffu;
-        CK(ctx->spill_rec.ensure(cap * 32)); CK(ctx->spill_cnt.ensure(16));
-        ctx->spill_cap = (unsigned int)cap; ctx->spill_parity = 0;
-        CK(cudaMemsetAsync(ctx->spill_cnt.p, 0, 16, ctx->stream));
-    }
     CK(ctx->path_q[0].ensure(px * sizeof(PathItem))); CK(ctx->path_q[1].ensure(px * sizeof(PathItem)));
     CK(ctx->path_count.ensure(sizeof(unsigned int) * (VKP_MAX_BOUNCES + 2)));
-    CK(ctx->chain_buf.ensure(px * sizeof(float4) * VKP_CHAIN_MAX)); CK(ctx->chain_len.ensure(px * sizeof(int))); CK(ctx->chain_slot.ensure(px * sizeof(int)));
+    CK(ctx->chain_buf.ensure(px * sizeof(float4) * VKP_CHAIN_MAX)); CK(ctx->chain_len.ensure(px * sizeof(int))); CK(ctx->chain_slot.ensure(px * sizeof(int))); CK(ctx->chain_pix.ensure(px * sizeof(int)));
     ctx->plane_w = W; ctx->plane_h = H; ctx->plane_lights = L;
     // defined initial state: history and accumulation start at zero (blur.comp:73 reads uninitialised memory upstream)
     CK(cudaMemsetAsync(ctx->position.p, 0, px * 8, ctx->stream)); CK(cudaMemsetAsync(ctx->normal.p, 0, px * 8, ctx->stream));
@@ -274,17 +263,20 @@ int flush_uniforms(vkp_ctx* ctx, bool lights_only = false)
         CK(U->inst_trav.ensure(sizeof(DInstTrav) * ctx->h_trav.size()));
         CK(U->instances.ensure(sizeof(DInstance) * ctx->h_inst.size()));
         CK(U->tlas_nodes.ensure(ctx->tlas.nodes.bytes ? ctx->tlas.nodes.bytes : sizeof(vkp_bvh_node)));
-        if (ctx->tlas.nodes4.bytes) CK(U->tlas_nodes4.ensure(ctx->tlas.nodes4.bytes));
         CK(upload_staged(ctx, us, U->inst_trav.p, ctx->h_trav.data(), sizeof(DInstTrav) * ctx->h_trav.size()));
         CK(upload_staged(ctx, us, U->instances.p, ctx->h_inst.data(), sizeof(DInstance) * ctx->h_inst.size()));
         CK(ctx->tlas_scratch.boxes.ensure(sizeof(float) * 6 * (size_t)(n ? n : 1)));
+        if (!ctx->ev_refit0) { CK(cudaEventCreate(&ctx->ev_refit0)); CK(cudaEventCreate(&ctx->ev_refit1)); }
+        CK(cudaEventRecord(ctx->ev_refit0, us));
         CK(bvh_instance_boxes(us, U->instances.as<DInstance>(), n, ctx->tlas_scratch.boxes.as<float>()));
         // refit on the topology of the last full build, boxes written into this set's node arrays
-        std::swap(ctx->tlas.nodes, U->tlas_nodes); std::swap(ctx->tlas.nodes4, U->tlas_nodes4);
-        int launches = 0;
+        std::swap(ctx->tlas.nodes, U->tlas_nodes);
+        int launches = 1;      // k_instance_boxes
         cudaError_t e = bvh_refit(us, ctx->tlas_scratch, ctx->tlas, &launches);
-        std::swap(ctx->tlas.nodes, U->tlas_nodes); std::swap(ctx->tlas.nodes4, U->tlas_nodes4);
+        std::swap(ctx->tlas.nodes, U->tlas_nodes);
         CK(e);
+        CK(cudaEventRecord(ctx->ev_refit1, us));
+        ctx->refit_timed = true; ctx->bstats.refit_launches = (uint32_t)launches;
         U->inst_ver = ctx->inst_ver;
     }
     CK(cudaEventRecord(ctx->ev_updated, us));
@@ -299,7 +291,6 @@ int scene_uniforms(vkp_ctx* ctx, DScene& S)
     if (r != VKP_OK) return r;
     if (ctx->update_pending) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_updated, 0)); ctx->update_pending = false; }
     vkp_ctx::FrameUniforms& U = ctx->uni[ctx->ucur];
-    S.tlas_nodes4 = U.tlas_nodes4.as<float4>(); S.tlas_root_ref = ctx->tlas.root_ref4;
     S.tlas_nodes2 = U.tlas_nodes.as<float4>(); S.tlas_root_ref2 = ctx->tlas.root_ref;
     S.instances = U.instances.as<DInstance>();
     S.inst_trav = U.inst_trav.as<DInstTrav>();
@@ -358,13 +349,10 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.denoised = ctx->denoised[ctx->denoised_cur].as<uint8_t>();
     F.denoised_next = ctx->denoised[ctx->denoised_cur ^ 1].as<uint8_t>();
     F.counters = ctx->counters.as<unsigned long long>();
-    F.spill_rec = ctx->spill_rec.as<float4>(); F.spill_cnt = ctx->spill_cnt.as<unsigned int>(); F.spill_cap = ctx->spill_cap;
-    F.spill_parity = ctx->spill_parity;
-    F.spill_budget = F.p.shadow_tail_budget > 0 ? F.p.shadow_tail_budget : (F.p.shadow_tail_budget < 0 ? 0 : ctx->shadow_tail);
     F.path_q[0] = ctx->path_q[0].as<PathItem>(); F.path_q[1] = ctx->path_q[1].as<PathItem>();
     F.path_count = ctx->path_count.as<unsigned int>();
     F.lut_pow22 = ctx->luts.as<float>(); F.lut_post = ctx->luts.as<uint8_t>() + 1024;
-    F.chain_buf = ctx->chain_buf.as<float4>(); F.chain_len = ctx->chain_len.as<int>(); F.chain_slot = ctx->chain_slot.as<int>();
+    F.chain_buf = ctx->chain_buf.as<float4>(); F.chain_len = ctx->chain_len.as<int>(); F.chain_slot = ctx->chain_slot.as<int>(); F.chain_pix = ctx->chain_pix.as<int>();
     const int total = F.tiles_x * F.tiles_y;
     L.n_own_tiles = total > F.rank ? (total - F.rank + F.world - 1) / F.world : 0;
     F.n_cta = L.n_own_tiles * (F.tile_w >> 4) * (F.tile_h >> 3);
@@ -399,6 +387,64 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     return VKP_OK;
 }
 
+#ifndef VKP_L2_PERSIST_DEFAULT
+#define VKP_L2_PERSIST_DEFAULT 1
+#endif
+
+// (re)applies the access-policy window over the BLAS arena to the streams that trace rays
+int apply_l2_window(vkp_ctx* ctx)
+{
+    const bool on = (ctx->l2_persist < 0 ? VKP_L2_PERSIST_DEFAULT : ctx->l2_persist) != 0 && ctx->bvh_arena.p && ctx->bvh_arena.bytes;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    ctx->bstats.l2_persist_bytes = 0; ctx->bstats.l2_hit_ratio = 0.0f;
+    if (on && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+        size_t window = ctx->bvh_arena.bytes < (size_t)prop.accessPolicyMaxWindowSize ? ctx->bvh_arena.bytes : (size_t)prop.accessPolicyMaxWindowSize;
+        size_t aside = window < (size_t)prop.persistingL2CacheMaxSize ? window : (size_t)prop.persistingL2CacheMaxSize;
+        if (aside != ctx->l2_set_aside) { CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, aside)); ctx->l2_set_aside = aside; }
+        attr.accessPolicyWindow.base_ptr = ctx->bvh_arena.p;
+        attr.accessPolicyWindow.num_bytes = window;
+        attr.accessPolicyWindow.hitRatio = (float)((double)aside / (double)window);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        ctx->bstats.l2_persist_bytes = aside; ctx->bstats.l2_hit_ratio = attr.accessPolicyWindow.hitRatio;
+    } else {
+        attr.accessPolicyWindow.num_bytes = 0;      // disables the window
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal; attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    cudaStream_t streams[] = {ctx->stream, ctx->own_stream, ctx->chain_stream};
+    for (cudaStream_t st : streams) if (st) CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+    if (!on && ctx->l2_set_aside) { cudaCtxResetPersistingL2Cache(); }
+    return VKP_OK;
+}
+
+// nodes + leaf triangles of every BLAS into one allocation (256-byte aligned pieces); the build's own arrays are released
+int compact_blas_arena(vkp_ctx* ctx)
+{
+    auto al = [](size_t n) { return (n + 255u) & ~(size_t)255u; };
+    size_t total = 0;
+    for (auto& b : ctx->blas) total += al(sizeof(vkp_bvh_node) * (size_t)b->bvh.n_nodes) + al(sizeof(float4) * 3 * (size_t)(b->bvh.n_prims ? b->bvh.n_prims : 1));
+    DevBuf arena;
+    CK(arena.ensure(total ? total : 256));
+    size_t off = 0;
+    for (auto& b : ctx->blas) {
+        const size_t nb = sizeof(vkp_bvh_node) * (size_t)b->bvh.n_nodes, tb = sizeof(float4) * 3 * (size_t)(b->bvh.n_prims ? b->bvh.n_prims : 1);
+        char* base = static_cast<char*>(arena.p);
+        CK(cudaMemcpyAsync(base + off, b->bvh.nodes.p, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        void* np = base + off; off += al(nb);
+        CK(cudaMemcpyAsync(base + off, b->bvh.tris.p, tb, cudaMemcpyDeviceToDevice, ctx->stream));
+        void* tp = base + off; off += al(tb);
+        CK(cudaStreamSynchronize(ctx->stream));       // the sources are freed (or are views of the old arena, freed below)
+        b->bvh.nodes.view(np, nb); b->bvh.tris.view(tp, tb);
+    }
+    ctx->bvh_arena.release();
+    ctx->bvh_arena = arena;
+    ctx->bstats.arena_bytes = total;
+    return apply_l2_window(ctx);
+}
+
 int stage_event(vkp_ctx* ctx, int stage)
 {
     if (!ctx->profiling || ctx->n_ev >= 12) return VKP_OK;
@@ -421,7 +467,6 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
         if (ctx->order_pending[k]) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_order_done[k], 0)); ctx->order_pending[k] = false; }
         if (k) {
             CK(launch_shadow(L));
-            if (shadow_spills(L)) { ctx->spill_parity ^= 1; L.frame.spill_parity = ctx->spill_parity; ctx->last_launches++; }      // + k_shadow_tail
         } else CK(launch_gbuffer(L));
         if (L.frame.cta_cost[k]) {       // next frame's order from this frame's costs, beside the rest of the frame
             CK(cudaEventRecord(ctx->ev_stage_done[k], ctx->stream));
@@ -441,8 +486,8 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
         break;
     case VKP_STAGE_RESOLVE: {
         int n = 0;
-        const bool chain2 = L.frame.p.wavefront == 2 && L.frame.p.max_bounces <= VKP_CHAIN_MAX;
-        if (chain2 && !ctx->chain_in_flight) { CK(launch_chain(L, ctx->stream)); ctx->last_launches++; }      // stand-alone stage: serial
+        const bool chain2 = L.frame.p.wavefront >= 2 && L.frame.p.max_bounces <= VKP_CHAIN_MAX;
+        if (chain2 && !ctx->chain_in_flight) { CK(launch_chain(L, ctx->stream)); ctx->last_launches += 3; }      // stand-alone stage: serial (clear + scan + chain)
         if (chain2 && ctx->chain_in_flight) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0)); ctx->chain_in_flight = false; }
         CK(launch_resolve(L, &n));
         if (L.frame.fused) {
@@ -501,9 +546,8 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
         cudaEventCreateWithFlags(&ctx->ev_gbuffer, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
     }
-    if (const char* t = getenv("VKP_SHADOW_TAIL")) ctx->shadow_tail = atoi(t) > 0 ? atoi(t) : 0;
-    if (const char* c = getenv("VKP_SHADOW_TAIL_CAP")) ctx->spill_cap_env = atoll(c);
     if (const char* b = getenv("VKP_BLAS_BUILDER")) ctx->builder = (strcmp(b, "lbvh") == 0) ? 0 : 1;
+    if (const char* l = getenv("VKP_L2_PERSIST")) ctx->l2_persist = atoi(l) != 0;
     cudaEventCreate(&ctx->timer0); cudaEventCreate(&ctx->timer1);
     // decode / gamma tables, computed on the device with the contract's own vkp_powf so they are bit-identical to the call
     if ((e = ctx->luts.ensure(2048)) != cudaSuccess || (e = launch_build_luts(ctx->stream, ctx->luts.as<float>(), ctx->luts.as<uint8_t>() + 1024)) != cudaSuccess ||
@@ -529,15 +573,18 @@ void vkp_destroy(vkp_ctx* ctx)
     for (auto& t : ctx->textures) t->texels.release();
     for (auto& b : ctx->blas) b->bvh.release();
     ctx->tlas.release(); ctx->scratch.release(); ctx->tlas_scratch.release();
+    if (ctx->l2_set_aside) cudaCtxResetPersistingL2Cache();
+    ctx->bvh_arena.release();
+    for (cudaEvent_t ev : {ctx->ev_build0, ctx->ev_build1, ctx->ev_refit0, ctx->ev_refit1}) if (ev) cudaEventDestroy(ev);
     for (auto& U : ctx->uni) {
-        U.lights.release(); U.inst_trav.release(); U.instances.release(); U.tlas_nodes.release(); U.tlas_nodes4.release();
+        U.lights.release(); U.inst_trav.release(); U.instances.release(); U.tlas_nodes.release();
         if (U.last_use) cudaEventDestroy(U.last_use);
     }
     if (ctx->update_stream) cudaStreamDestroy(ctx->update_stream);
     if (ctx->ev_updated) cudaEventDestroy(ctx->ev_updated);
     DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_textures, &ctx->position, &ctx->normal, &ctx->albedo, &ctx->motion,
                       &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
-                      &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->final_srgb8_alt, &ctx->spill_rec, &ctx->spill_cnt};
+                      &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->chain_pix, &ctx->final_srgb8_alt};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->timer0) cudaEventDestroy(ctx->timer0);
@@ -565,7 +612,7 @@ int vkp_set_stream(vkp_ctx* ctx, void* cuda_stream)
     if (!ctx) return VKP_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
-    return VKP_OK;
+    return apply_l2_window(ctx);
 }
 
 int vkp_upload_mesh(vkp_ctx* ctx, const vkp_vertex* vertices, uint32_t nv, const uint32_t* indices, uint32_t ni, int* mesh_id)
@@ -656,6 +703,9 @@ int vkp_build_blas(vkp_ctx* ctx)
     if (!ctx) return VKP_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     ctx->build_launches = 0;
+    if (!ctx->ev_build0) { CK(cudaEventCreate(&ctx->ev_build0)); CK(cudaEventCreate(&ctx->ev_build1)); }
+    CK(cudaEventRecord(ctx->ev_build0, ctx->stream));
+    int host_syncs = 0; uint32_t built = 0; uint64_t built_tris = 0;
     for (const vkp_instance& I : ctx->instances) {
         bool found = false;
         for (auto& b : ctx->blas) if (b->mesh == I.mesh_id && b->first == I.first_index && b->count == I.index_count) { found = true; break; }
@@ -667,15 +717,31 @@ int vkp_build_blas(vkp_ctx* ctx)
         CK(ctx->scratch.boxes.ensure(sizeof(float) * 6 * (size_t)(ntri ? ntri : 1)));
         const uint32_t* idx = m.idx.as<uint32_t>() + I.first_index;
         CK(bvh_triangle_boxes(ctx->stream, m.verts.as<vkp_vertex>(), idx, ntri, ctx->scratch.boxes.as<float>()));
-        CK(bvh_build(ctx->stream, ctx->scratch, ntri, 4, b->bvh, &ctx->build_launches, ctx->builder));
+        CK(bvh_build(ctx->stream, ctx->scratch, ntri, 4, b->bvh, &ctx->build_launches, ctx->builder, &host_syncs));
         CK(bvh_emit_triangles(ctx->stream, m.verts.as<vkp_vertex>(), idx, b->bvh));
-        CK(cudaStreamSynchronize(ctx->stream));
-        if ((VKP_WIDE ? 3 * ((b->bvh.height + 1) / 2 + 1) + 16 : b->bvh.height + 16) > VKP_TRAV_STACK) {     // pushes per level + the TLAS part
+        ctx->build_launches += 2;      // k_triangle_boxes, k_emit_triangles
+        built++; built_tris += ntri;
+        if (b->bvh.height + 16 > VKP_TRAV_STACK) {     // one push per level + the TLAS part (checked exactly in vkp_build_tlas)
             char msg[160]; snprintf(msg, sizeof msg, "BLAS height %d exceeds the traversal stack budget", b->bvh.height);
             return fail(ctx, VKP_ERR_INVALID, msg);
         }
         ctx->blas.push_back(std::move(b));
     }
+    if (built) {
+        int r = compact_blas_arena(ctx);      // one allocation for every BLAS + the L2 persistence window over it
+        if (r != VKP_OK) return r;
+        ctx->tlas_built = false;              // the instance records name the old arrays: vkp_build_tlas has to follow
+    }
+    CK(cudaEventRecord(ctx->ev_build1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev_build1));
+    if (built) {
+        CK(cudaEventElapsedTime(&ctx->bstats.blas_ms, ctx->ev_build0, ctx->ev_build1));
+        ctx->bstats.blas_built = built; ctx->bstats.blas_launches = (uint32_t)ctx->build_launches; ctx->bstats.blas_host_syncs = (uint32_t)host_syncs;
+        ctx->bstats.blas_triangles = built_tris;
+    }
+    uint32_t hmax = 0;
+    for (auto& b : ctx->blas) hmax = (uint32_t)b->bvh.height > hmax ? (uint32_t)b->bvh.height : hmax;
+    ctx->bstats.blas_height_max = hmax;
     ctx->blas_built = true;
     return VKP_OK;
 }
@@ -700,8 +766,7 @@ int vkp_build_tlas(vkp_ctx* ctx, int update)
         d[i].material_id = I.material_id;
         const float* im = I.inv_model;
         tv[i].r0 = make_float4(im[0], im[4], im[8], im[12]); tv[i].r1 = make_float4(im[1], im[5], im[9], im[13]); tv[i].r2 = make_float4(im[2], im[6], im[10], im[14]);
-        tv[i].nodes = rec->bvh.nodes4.as<float4>(); tv[i].tris = rec->bvh.tris.as<float4>(); tv[i].root_ref = rec->bvh.root_ref4;
-        tv[i].nodes2 = rec->bvh.nodes.as<float4>(); tv[i].root_ref2 = rec->bvh.root_ref;
+        tv[i].nodes = rec->bvh.nodes.as<float4>(); tv[i].tris = rec->bvh.tris.as<float4>(); tv[i].root_ref = rec->bvh.root_ref;
     }
     const bool refit = update && ctx->tlas_topology && ctx->tlas.n_prims == (uint32_t)n && ctx->tlas.n_nodes > 0;
     if (!refit) {
@@ -714,13 +779,18 @@ int vkp_build_tlas(vkp_ctx* ctx, int update)
         CK(ctx->tlas_scratch.boxes.ensure(sizeof(float) * 6 * (size_t)(n ? n : 1)));
         CK(bvh_instance_boxes(ctx->stream, U.instances.as<DInstance>(), (uint32_t)n, ctx->tlas_scratch.boxes.as<float>()));
         int launches = 0;
+        if (!ctx->ev_build0) { CK(cudaEventCreate(&ctx->ev_build0)); CK(cudaEventCreate(&ctx->ev_build1)); }
+        CK(cudaEventRecord(ctx->ev_build0, ctx->stream));
         CK(bvh_build(ctx->stream, ctx->tlas_scratch, (uint32_t)n, 1, ctx->tlas, &launches, 0));
+        CK(cudaEventRecord(ctx->ev_build1, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaEventElapsedTime(&ctx->bstats.tlas_ms, ctx->ev_build0, ctx->ev_build1));
+        ctx->bstats.tlas_height = (uint32_t)ctx->tlas.height;
         {
             // the per-thread traversal stack holds the sentinel, the TLAS part, the return marker and the deepest BLAS part
             int blas_h = 0;
             for (auto& b : ctx->blas) blas_h = b->bvh.height > blas_h ? b->bvh.height : blas_h;
-            const int need = VKP_WIDE ? 3 * ((blas_h + 1) / 2 + (ctx->tlas.height + 1) / 2 + 2) + 2 : ctx->tlas.height + blas_h + 3;
+            const int need = ctx->tlas.height + blas_h + 3;
             if (need > VKP_TRAV_STACK) {
                 char msg[200]; snprintf(msg, sizeof msg, "TLAS height %d + BLAS height %d exceed the traversal stack budget (%d entries)", ctx->tlas.height, blas_h, VKP_TRAV_STACK);
                 ctx->tlas_topology = false;
@@ -734,6 +804,25 @@ int vkp_build_tlas(vkp_ctx* ctx, int update)
     ctx->inst_ver++;
     ctx->tlas_built = true;
     return flush_uniforms(ctx);
+}
+
+int vkp_get_build_stats(vkp_ctx* ctx, vkp_build_stats* out)
+{
+    if (!ctx || !out) return VKP_ERR_INVALID;
+    if (ctx->refit_timed) {
+        CK(cudaEventSynchronize(ctx->ev_refit1));
+        CK(cudaEventElapsedTime(&ctx->bstats.refit_ms, ctx->ev_refit0, ctx->ev_refit1));
+    }
+    *out = ctx->bstats;
+    return VKP_OK;
+}
+
+int vkp_set_l2_persistence(vkp_ctx* ctx, int on)
+{
+    if (!ctx || on < -1 || on > 1) return fail(ctx, VKP_ERR_INVALID, "vkp_set_l2_persistence: -1 default, 0 off, 1 on");
+    CK(cudaSetDevice(ctx->device));
+    ctx->l2_persist = on;
+    return apply_l2_window(ctx);
 }
 
 int vkp_set_camera(vkp_ctx* ctx, const vkp_camera* cam)
@@ -789,7 +878,7 @@ int vkp_render(vkp_ctx* ctx)
     else if (ctx->params.mode == VKP_MODE_DEFERRED) { seq = deferred; n = 2; }
     for (int i = 0; i < n; i++) {
         if ((r = run_one(ctx, L, seq[i])) != VKP_OK) return r;
-        if (seq[i] == VKP_STAGE_GBUFFER && ctx->params.mode == VKP_MODE_HYBRID && ctx->params.wavefront == 2 &&
+        if (seq[i] == VKP_STAGE_GBUFFER && ctx->params.mode == VKP_MODE_HYBRID && ctx->params.wavefront >= 2 &&
             ctx->params.max_bounces <= VKP_CHAIN_MAX && L.n_own_tiles > 0) {
             // fork: the reflection chain needs only the G-buffer; it overlaps the shadow + denoise passes on its own stream
             CK(cudaEventRecord(ctx->ev_gbuffer, ctx->stream));
@@ -797,7 +886,7 @@ int vkp_render(vkp_ctx* ctx)
             CK(launch_chain(L, ctx->chain_stream));
             CK(cudaEventRecord(ctx->ev_chain, ctx->chain_stream));
             ctx->chain_in_flight = true;
-            ctx->last_launches++;
+            ctx->last_launches += 3;      // counter clear + k_chain_scan + k_chain
         }
     }
     if ((r = mark_scene_use(ctx)) != VKP_OK) return r;

@@ -112,23 +112,20 @@ struct DInstance {
 };
 
 // what traversal needs to enter an instance, in one 80-byte record (5 independent 16-byte loads = one memory round trip):
-// the rows of inverse(model) 3x4 in xform_point()'s association, the BLAS arrays and the BLAS root reference
+// the rows of inverse(model) 3x4 (applied with vkp_row_point / vkp_dot3), the BLAS arrays and the BLAS root reference
 struct DInstTrav {
     float4 r0, r1, r2;
-    const float4* nodes;        // 4-wide nodes
+    const float4* nodes;        // BLAS nodes (32 B each)
     const float4* tris;
-    uint32_t root_ref;          // wide root reference
-    uint32_t root_ref2;         // binary root reference
-    const float4* nodes2;       // binary nodes (32 B each)
+    uint32_t root_ref;          // nodes[0].ref of the BLAS
+    uint32_t _pad[3];
 };
 
 struct DScene {
     const float* lut_pow22;
     const DInstTrav* inst_trav;          // same table as DFrame::lut_pow22 (hit / miss shading has only the scene)
-    const float4* tlas_nodes4;       // 4-wide TLAS nodes (8 x float4 each)
-    const float4* tlas_nodes2;       // binary TLAS nodes (2 x float4 each)
-    uint32_t tlas_root_ref;          // wide: node index or leaf reference (single instance)
-    uint32_t tlas_root_ref2;         // binary: nodes[0].ref
+    const float4* tlas_nodes2;       // TLAS nodes (2 x float4 each)
+    uint32_t tlas_root_ref2;         // nodes[0].ref
     const DInstance* instances;
     const vkp_material* materials;
     const vkp_light* lights;
@@ -176,6 +173,7 @@ struct DFrame {
     float4* chain_buf;              // chain mode 2: VKP_CHAIN_MAX colours per compacted path
     int* chain_len;                 // chain mode 2: number of bounces traced per path
     int* chain_slot;                // chain mode 2: per-pixel path slot (written for mirror / glass pixels only)
+    int* chain_pix;                 // chain mode 2: pixel index of every path slot (the queue k_chain's warps pull from)
     // longest-first CTA scheduling: cost[v] = SM cycles the slowest warp of virtual block v took in the
     // previous frame, order[b] = the virtual block hardware block b works on (NULL = identity).  [0] k_gbuffer, [1] k_shadow.
     const uint32_t* cta_order[2];
@@ -184,14 +182,6 @@ struct DFrame {
     // fast_div (kernels_frame.cu): floor(2^40 / d) + 1 for the four divisors of the block-index arithmetic
     unsigned long long magic_bpt, magic_tiles_x, magic_bpt_x, magic_n_cta;
     int div_exact;                  // all four are exact for the index ranges of this launch (n * d < 2^40)
-    // tail of k_shadow (one-sample shadow rays): a thread that has fetched spill_budget child pairs without an answer appends
-    // its ray to spill_rec (2 x float4: origin | tmax, direction | index into `shadow`) and k_shadow_tail finishes it with one
-    // warp per ray.  spill_cnt = {count, head} x 2: the pair of this frame and the pair the tail kernel clears for the next one.
-    float4* spill_rec;
-    unsigned int* spill_cnt;
-    unsigned int spill_cap;
-    int spill_budget;               // 0 = off
-    int spill_parity;
 };
 
 // k / 255.0f for the 256 possible bytes, filled on the device by k_build_luts with the same IEEE division the contract

@@ -10,16 +10,18 @@
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    bool owned = true;          // false: a view into somebody else's allocation (the BLAS arena)
     cudaError_t ensure(size_t n)
     {
-        if (n <= bytes) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; bytes = 0;
+        if (n <= bytes && owned) return cudaSuccess;
+        if (p && owned) cudaFree(p);
+        p = nullptr; bytes = 0; owned = true;
         cudaError_t e = cudaMalloc(&p, n);
         if (e == cudaSuccess) bytes = n;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void release() { if (p && owned) cudaFree(p); p = nullptr; bytes = 0; owned = true; }
+    void view(void* q, size_t n) { release(); p = q; bytes = n; owned = false; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -31,9 +33,6 @@ struct Bvh {
     int height = 0;
     int root = 0;        // index of the root among the internal nodes (0 for the Karras tree)
     uint32_t root_ref = 0x80000000u;   // nodes[0].ref of the binary layout
-    uint32_t n_nodes4 = 0;             // 4-wide layout (what traversal uses): 128-byte nodes
-    uint32_t root_ref4 = 0x80000000u;  // reference traversal starts from: wide node index, or a leaf reference
-    DevBuf nodes4, is4, rank4;
     DevBuf nodes;        // vkp_bvh_node[n_nodes]
     DevBuf items;        // uint32_t[n_prims]: leaf-ordered primitive ids
     DevBuf tris;         // BLAS only: float4[3*n_prims]
@@ -48,7 +47,7 @@ struct Bvh {
     void release()
     {
         nodes.release(); items.release(); tris.release(); child.release(); parent.release(); ibox.release();
-        flags.release(); rank.release(); keep.release(); range.release(); nodes4.release(); is4.release(); rank4.release();
+        flags.release(); rank.release(); keep.release(); range.release();
     }
 };
 
@@ -67,7 +66,8 @@ struct BuildScratch {
 // bvh_build.cu
 cudaError_t bvh_triangle_boxes(cudaStream_t s, const vkp_vertex* verts, const uint32_t* indices, uint32_t n_tris, float* boxes);
 cudaError_t bvh_instance_boxes(cudaStream_t s, const DInstance* inst, uint32_t n, float* boxes);
-cudaError_t bvh_build(cudaStream_t s, BuildScratch& scratch, uint32_t n_prims, int leaf_max, Bvh& out, int* launches, int builder /*0 LBVH (Karras), 1 PLOC*/);
+cudaError_t bvh_build(cudaStream_t s, BuildScratch& scratch, uint32_t n_prims, int leaf_max, Bvh& out, int* launches, int builder /*0 LBVH (Karras), 1 PLOC*/,
+                      int* host_syncs = nullptr);
 cudaError_t bvh_refit(cudaStream_t s, BuildScratch& scratch, Bvh& bvh, int* launches);
 cudaError_t bvh_selftest_sort(cudaStream_t s, const uint32_t* keys_host, uint32_t n, int end_bit, uint32_t* keys_sorted_host, uint32_t* vals_sorted_host,
                               unsigned long long* scan_host);
@@ -83,7 +83,6 @@ struct FrameLaunch {
 };
 cudaError_t launch_gbuffer(const FrameLaunch& L);
 cudaError_t launch_shadow(const FrameLaunch& L);
-bool shadow_spills(const FrameLaunch& L);     // launch_shadow runs k_shadow<., true> + k_shadow_tail: one more launch, flip the counter parity
 cudaError_t launch_denoise(const FrameLaunch& L);
 cudaError_t launch_build_order(cudaStream_t s, uint32_t* cost, uint32_t* order, uint32_t n);
 cudaError_t launch_resolve(const FrameLaunch& L, int* launches);

@@ -29,7 +29,7 @@ class Camera(C.Structure):          # vkp_camera, 400 B
 class Params(C.Structure):          # vkp_params, 64 B
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("mode", C.c_int32), ("spp", C.c_int32), ("shadow_samples", C.c_int32),
                 ("max_bounces", C.c_int32), ("frame", C.c_int32), ("denoise_frame", C.c_int32), ("faithful_rng", C.c_int32),
-                ("denoise_cover_remainder", C.c_int32), ("debug_target", C.c_int32), ("wavefront", C.c_int32), ("fuse_denoise", C.c_int32), ("reproject_fix", C.c_int32), ("shadow_tail_budget", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("denoise_cover_remainder", C.c_int32), ("debug_target", C.c_int32), ("wavefront", C.c_int32), ("fuse_denoise", C.c_int32), ("reproject_fix", C.c_int32), ("denoiser", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class Ray(C.Structure):             # vkp_ray, 32 B
@@ -47,11 +47,17 @@ class Counters(C.Structure):        # vkp_counters
                 ("worst_thread_nodes", C.c_uint32), ("worst_thread_tag", C.c_uint32)]
 
 
+class BuildStats(C.Structure):      # vkp_build_stats
+    _fields_ = [("blas_ms", C.c_float), ("tlas_ms", C.c_float), ("refit_ms", C.c_float), ("blas_built", C.c_uint32), ("blas_launches", C.c_uint32),
+                ("blas_host_syncs", C.c_uint32), ("blas_height_max", C.c_uint32), ("tlas_height", C.c_uint32), ("refit_launches", C.c_uint32),
+                ("blas_triangles", C.c_uint64), ("arena_bytes", C.c_uint64), ("l2_persist_bytes", C.c_uint64), ("l2_hit_ratio", C.c_float), ("_pad", C.c_uint32)]
+
+
 class BvhNode(C.Structure):         # vkp_bvh_node, 32 B
     _fields_ = [("bmin", C.c_float * 3), ("ref", C.c_uint32), ("bmax", C.c_float * 3), ("aux", C.c_uint32)]
 
 
-SIZES = {Vertex: 44, Material: 48, Light: 48, Instance: 144, Camera: 400, Params: 64, Ray: 32, Hit: 20, BvhNode: 32}
+SIZES = {Vertex: 44, Material: 48, Light: 48, Instance: 144, Camera: 400, Params: 64, Ray: 32, Hit: 20, BvhNode: 32, BuildStats: 72}
 
 vertex_dtype = np.dtype([("position", "<f4", 3), ("normal", "<f4", 3), ("color", "<f4", 3), ("uv", "<f4", 2)])
 material_dtype = np.dtype([("diffuse", "<f4", 4), ("textures", "<f4", 4), ("shadingMetallicRoughness", "<f4", 4)])
