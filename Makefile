@@ -21,7 +21,7 @@ NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-fvisib
 # -fwrapv: the integer IDCT of the JPEG reader may overflow on corrupt streams (as in stb_image); wrapping keeps that defined
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-unused-variable -fwrapv
 
-CU_SRCS := $(CSRC)/vkp_api.cu $(CSRC)/bvh_build.cu $(CSRC)/kernels_frame.cu
+CU_SRCS := $(CSRC)/vkp_api.cu $(CSRC)/bvh_build.cu $(CSRC)/kernels_frame.cu $(CSRC)/vkp_group.cu
 CU_OBJS := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
 CU_HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard $(ROOT)include/*.h)
 SCENE_SRCS := $(HOST)/scene_model.cpp $(HOST)/procedural.cpp $(HOST)/output.cpp $(HOST)/image_decode.cpp $(HOST)/gltf.cpp $(HOST)/scene_capi.cpp

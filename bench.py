@@ -257,7 +257,7 @@ def main():
     ap.add_argument("--no-peer", action="store_true", help="N > 1: composite with pack + NCCL gather + unpack instead of NVLink peer stores")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-identity check of the composite against a 1-GPU render")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the 2-step Raytraced 64 spp x 64 samples block (BASELINE configs[2])")
-    ap.add_argument("--chain", type=int, default=2, choices=[0, 1, 2, 3],
+    ap.add_argument("--chain", type=int, default=2, choices=[0, 1, 2, 3, 4, 5],
                     help="reflection-chain schedule: 0 inline in k_resolve, 1 wavefront queues, 2 k_chain overlapped with the shadow pass (default)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="wall seconds the parity / cpu_baseline oracle leg may take")
     args = ap.parse_args()
@@ -310,11 +310,19 @@ def main():
         ctx.build_tlas(True)
     ctx.sync()
     build = ctx.build_stats()
+    build["blas_ms_first"] = build["blas_ms"]          # the process's first build: includes loading every build kernel (lazy module loading)
+    if world == 1 or rank == 0:
+        warm = vk.Context(dev); warm.upload_scene(scene)       # the same builds again in a fresh context: what a scene change costs
+        w2 = warm.build_stats(); warm.close()
+        build["blas_ms"] = w2["blas_ms"]; build["tlas_ms"] = w2["tlas_ms"]
+        build["blas_launches"] = w2["blas_launches"]; build["blas_host_syncs"] = w2["blas_host_syncs"]
     if build["blas_ms"] > 0:
         build["blas_algorithmic_bytes"] = int(build["blas_triangles"]) * (132 + 80)
         build["blas_GBps"] = build["blas_algorithmic_bytes"] / (build["blas_ms"] * 1e-3) / 1e9
         build["blas_mtris_s"] = build["blas_triangles"] / (build["blas_ms"] * 1e-3) / 1e6
         build["builder"] = os.environ.get("VKP_BLAS_BUILDER", "ploc")
+        build["how"] = ("CUDA events around every BLAS build of the scene + the compaction into one arena, queued without a host wait "
+                        "(device-driven PLOC rounds), one synchronisation at the end; blas_ms = second context (kernels loaded), blas_ms_first = first")
     cam = scene.camera(W, H)
     ctx.set_camera(cam)
     TW, TH = (32, 16)
@@ -660,7 +668,7 @@ def main():
                                    "secondary_shadow": int(rays_all[3] // args.steps), "primary_not_counted": int(rays_all[0] // args.steps)},
                 "mrays_s_incl_primary": float(rays_all.sum()) / args.steps / (ms_per_step * 1e-3) / 1e6,
                 "nominal_2P_mrays_s": 2 * P / (ms_per_step * 1e-3) / 1e6,
-                "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise", 3: "k_chain_warp (one warp per queued path, cooperative traversal) on a second stream"}[args.chain],
+                "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise", 3: "k_chain_warp (one warp per queued path, cooperative traversal) on a second stream", 4: "staged chain on a second stream overlapping k_shadow + k_denoise: first bounce as a wavefront (k_chain_first, k_chain_shadow0, k_chain_shade0), continuing paths compacted (k_chain_rest)", 5: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges the chain into the mirror / glass pixels"}[args.chain],
                 "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
                 "parallelism": (f"tiles {TW}x{TH} dealt over {world} GPU(s), replicated BVH, " +
                                 ("resolve kernels store sRGB8 pixels straight into rank 0's image over NVLink peer memory (CUDA IPC) + a device-side flag barrier"

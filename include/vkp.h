@@ -164,6 +164,37 @@ VKP_API int vkp_eval_math(vkp_ctx* ctx, int func, const float* x, const float* y
 /* run subsequent work on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
 VKP_API int vkp_set_stream(vkp_ctx* ctx, void* cuda_stream);
 
+/* multi-GPU group ------------------------------------------------------------------------------
+ * Several GPUs of one box behind one handle, in ONE process: what the C++ host (Renderer, vkpinut --gpus N) uses where the
+ * reference has its single device and queue (vk_engine.cpp:296-302, frame seam Renderer::rasterize_hybrid renderer.cpp:530-600).
+ * One vkp_ctx per device, scene and BVH replicated, screen tiles dealt t -> rank t % n; the resolve kernels of ranks 1..n-1
+ * store their sRGB8 pixels straight into rank 0's double-buffered image over NVLink peer memory (cudaDeviceEnablePeerAccess),
+ * ordered by one CUDA event per rank; Hybrid reset frames exchange their shadow / history tiles between the shadow pass and the
+ * filter.  Every vkp_group_<call> below means vkp_<call> on every member.  Images are bit-identical to one GPU. */
+typedef struct vkp_group vkp_group;
+VKP_API int      vkp_group_create(vkp_group** out, const int* device_ordinals, int n_devices, int tile_w, int tile_h);
+VKP_API void     vkp_group_destroy(vkp_group* g);
+VKP_API int      vkp_group_size(const vkp_group* g);
+VKP_API vkp_ctx* vkp_group_member(vkp_group* g, int rank);           /* rank 0 owns the composited image */
+VKP_API const char* vkp_group_last_error(const vkp_group* g);
+VKP_API int vkp_group_upload_mesh(vkp_group* g, const vkp_vertex* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices, int* mesh_id);
+VKP_API int vkp_group_upload_texture_rgba8(vkp_group* g, const uint8_t* rgba, int width, int height, int* tex_id);
+VKP_API int vkp_group_set_env(vkp_group* g, int sky_tex_id, int irradiance_tex_id);
+VKP_API int vkp_group_set_materials(vkp_group* g, const vkp_material* materials, int n);
+VKP_API int vkp_group_set_lights(vkp_group* g, const vkp_light* lights, int n);
+VKP_API int vkp_group_set_instances(vkp_group* g, const vkp_instance* instances, int n);
+VKP_API int vkp_group_build_blas(vkp_group* g);
+VKP_API int vkp_group_build_tlas(vkp_group* g, int update);
+VKP_API int vkp_group_set_camera(vkp_group* g, const vkp_camera* camera);
+VKP_API int vkp_group_set_params(vkp_group* g, const vkp_params* params);
+VKP_API int vkp_group_reset_history(vkp_group* g);
+/* one frame of params.mode across the group; asynchronous.  Afterwards rank 0's stream is ordered behind every rank's part. */
+VKP_API int vkp_group_render(vkp_group* g);
+VKP_API int vkp_group_sync(vkp_group* g);
+/* FINAL_SRGB8 is read from rank 0 (already composited); any other plane is gathered to rank 0 first (pack, peer copy, unpack) */
+VKP_API int vkp_group_readback(vkp_group* g, int plane, void* dst, size_t bytes);
+VKP_API int vkp_group_get_counters(vkp_group* g, vkp_counters* out);            /* ray / launch counters summed over the ranks */
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,7 +83,11 @@ typedef struct vkp_params {
                                         1 = wavefront path queues with ray compaction, one launch per bounce,
                                         2 = mirror / glass pixels compacted into a path queue, one thread per path, on a second stream
                                             overlapping shadow + denoise (default of the host engine),
-                                        3 = as 2 with one warp per path and warp-cooperative traversal (measured slower, kept for A/B) */
+                                        3 = as 2 with one warp per path and warp-cooperative traversal (measured slower, kept for A/B),
+                                        4 = as 2 with the first bounce staged as a wavefront: closest hit, per-light any-hit rays and hit
+                                            shading in three lean kernels, the paths that scatter compacted for the remaining bounces,
+                                        5 = as 2, and the resolve does not wait for the chain either: mirror / glass pixels are finished by
+                                            k_resolve_paths once the chain is there (the chain overlaps shadow + denoise + resolve) */
     int32_t fuse_denoise;            /* vkp_render (Hybrid): run blur.comp inside the resolve kernel instead of as its own pass */
     int32_t reproject_fix;           /* blur.comp:52-53 on a reset frame.  0 (default): the reference's history fetch, pixel + motion.x * (W, H)
                                         (twice the right distance, x component used for both axes).
@@ -155,7 +159,7 @@ typedef struct vkp_counters {
 /* acceleration-structure build / refit figures (vkp_get_build_stats): what vkCmdBuildAccelerationStructuresKHR cost the
  * reference's driver (renderer.cpp:1747 buildBlas, :1853 buildTlas, per-frame MODE_UPDATE refit vk_engine.cpp:172-187) */
 typedef struct vkp_build_stats {
-    float    blas_ms;               /* CUDA-event time of the last vkp_build_blas (all BLAS it built, incl. compaction into the arena) */
+    float    blas_ms;               /* CUDA-event time of the last vkp_build_blas: every BLAS it built, queued back to back (memory allocated before) */
     float    tlas_ms;               /* last full TLAS build */
     float    refit_ms;              /* last TLAS refit (instance boxes + bottom-up fit + node emit), on the update stream */
     uint32_t blas_built;            /* BLAS built by the last vkp_build_blas */
@@ -168,7 +172,10 @@ typedef struct vkp_build_stats {
     uint64_t arena_bytes;           /* nodes + leaf triangles of every BLAS, one contiguous allocation (the L2 persistence window) */
     uint64_t l2_persist_bytes;      /* bytes of the arena set aside as persisting L2 lines (0 = window off) */
     float    l2_hit_ratio;          /* hitRatio of the access-policy window */
-    uint32_t _pad;
+    uint16_t blas_ploc_rounds_max;  /* most PLOC rounds any BLAS of the last vkp_build_blas needed */
+    uint16_t blas_rebuilt;          /* BLAS whose queued rounds did not suffice and which were built again with host waits (0 = none) */
+    float    blas_wall_ms;          /* host wall clock of the whole vkp_build_blas call: allocations + queueing + the one wait + compaction + frees */
+    float    blas_compact_ms;       /* CUDA-event time of the copies into the arena (part of blas_wall_ms, not of blas_ms) */
 } vkp_build_stats;
 
 /* 32-byte BVH node (both BLAS and TLAS).  ref: bit31 = leaf; leaf: bits[30:3] = first item,

@@ -772,6 +772,50 @@ void orc_shadow_pass(const orc_scene* sp, const vkp_camera* cam, const vkp_param
     if (C) C->rays[1] += nrays;
 }
 
+/* vkp_params.denoiser == 1 (no reference counterpart: SURVEY 8f-3 "a better denoiser").
+ * One iteration of an edge-aware a-trous filter over the R8 shadow planes, guided by the G-buffer: 5 x 5 taps `step` pixels apart,
+ * B3-spline weights (3/8, 1/4, 1/16 per axis), times a normal weight max(0, N_p . N_q)^32 and a plane-distance weight
+ * max(0, 1 - |N_p . (P_q - P_p)| / (0.1 * step)).  Background pixels (normal.w == 0) pass through and are never taps.
+ * Taps outside the image are skipped.  out = unorm8(sum w v / sum w); the centre tap has weight 9/64, so the sum is never empty. */
+static void atrous_iteration(const vkp_params* p, int n_lights, const orc_gbuffer* g, const uint8_t* in, uint8_t* out, int step)
+{
+    const int W = p->width, H = p->height;
+    const size_t plane = (size_t)W * H;
+    static const float k[3] = {0.375f, 0.25f, 0.0625f};
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++) {
+        if (g_row_stride > 1 && y % g_row_stride != g_row_offset) continue;
+        for (int x = 0; x < W; x++) {
+            const size_t px = (size_t)y * W + x;
+            const vec4 np4 = load_half4(g->normal, px);
+            if (np4.w == 0.0f) { for (int l = 0; l < n_lights; l++) out[l * plane + px] = in[l * plane + px]; continue; }
+            const vec3 Np = normalize(xyz(np4) * 2.0f - vec3(1.0f));
+            const vec3 Pp = xyz(load_half4(g->position, px));
+            const float inv_sigma = 1.0f / (0.1f * (float)step);
+            float sum[VKP_MAX_LIGHTS], wsum = 0.0f;
+            for (int l = 0; l < n_lights; l++) sum[l] = 0.0f;
+            for (int dy = -2; dy <= 2; dy++)
+                for (int dx = -2; dx <= 2; dx++) {
+                    const int qx = x + dx * step, qy = y + dy * step;
+                    if (qx < 0 || qy < 0 || qx >= W || qy >= H) continue;
+                    const size_t q = (size_t)qy * W + qx;
+                    const vec4 nq4 = load_half4(g->normal, q);
+                    if (nq4.w == 0.0f) continue;
+                    const vec3 Nq = normalize(xyz(nq4) * 2.0f - vec3(1.0f));
+                    const vec3 Pq = xyz(load_half4(g->position, q));
+                    float wn = maxf(dot(Np, Nq), 0.0f);
+                    wn = wn * wn; wn = wn * wn; wn = wn * wn; wn = wn * wn; wn = wn * wn;          /* ^32 */
+                    const float dist = fabsf(dot(Np, Pq - Pp));
+                    const float wp = maxf(1.0f - dist * inv_sigma, 0.0f);
+                    const float w = (k[dx < 0 ? -dx : dx] * k[dy < 0 ? -dy : dy]) * wn * wp;
+                    wsum = wsum + w;
+                    for (int l = 0; l < n_lights; l++) sum[l] = sum[l] + w * from_unorm8(in[l * plane + q]);
+                }
+            for (int l = 0; l < n_lights; l++) out[l * plane + px] = to_unorm8(sum[l] / wsum);
+        }
+    }
+}
+
 /* blur.comp:35-82 with runtime W/H/NLIGHTS and integer motion fetch; R8 storage */
 void orc_denoise_pass(const vkp_params* p, int n_lights, const orc_gbuffer* g, const uint8_t* shadow, uint8_t* denoised)
 {
@@ -782,6 +826,18 @@ void orc_denoise_pass(const vkp_params* p, int n_lights, const orc_gbuffer* g, c
     const int Wc = p->denoise_cover_remainder ? W : (W / 16) * 16;
     const int Hc = p->denoise_cover_remainder ? H : (H / 16) * 16;
     std::vector<uint8_t> prev(denoised, denoised + plane * n_lights);   /* reads see last frame's image */
+    std::vector<uint8_t> filtered, tmp;
+    if (p->denoiser == 1) {
+        /* three a-trous iterations (steps 1, 2, 4: a 29 x 29 footprint) replace the raw shadow planes as the input of blur.comp's
+         * temporal stage below.  Row sampling (bench timing aid) does not apply: every iteration needs its neighbours' rows. */
+        const int keep_stride = g_row_stride; g_row_stride = 1;
+        filtered.assign(plane * n_lights, 0); tmp.assign(plane * n_lights, 0);
+        atrous_iteration(p, n_lights, g, shadow, filtered.data(), 1);
+        atrous_iteration(p, n_lights, g, filtered.data(), tmp.data(), 2);
+        atrous_iteration(p, n_lights, g, tmp.data(), filtered.data(), 4);
+        shadow = filtered.data();
+        g_row_stride = keep_stride;
+    }
     auto in_at = [&](int l, int x, int y) -> float {
         if (x < 0 || y < 0 || x >= W || y >= H) return 0.0f;            /* out-of-bounds imageLoad -> 0 */
         return from_unorm8(shadow[l * plane + (size_t)y * W + x]);

@@ -14,7 +14,7 @@ ctx.set_camera(sc.camera(W, H))
 ctx.set_profiling(1)
 prev = 0
 base = None
-for chain in (2, 3):
+for chain in [int(c) for c in (sys.argv[1:] or ["2", "3"])]:
     print("chain mode", chain)
     for mb in range(0, 9):
         ts = []

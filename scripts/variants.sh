@@ -7,7 +7,7 @@ CS=$ROOT/vulkanhybridraytracer_b200/csrc
 while [ $# -ge 2 ]; do
   NAME=$1; FLAGS=$2; shift 2
   OUT=$ROOT/variants/$NAME; mkdir -p $OUT
-  for f in vkp_api bvh_build kernels_frame; do
+  for f in vkp_api bvh_build kernels_frame vkp_group; do
     /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-fvisibility=hidden -ccbin /usr/bin/g++ \
       --cudart static -Xptxas -v -diag-suppress 20012 $FLAGS -c $CS/$f.cu -o $OUT/$f.o 2> $OUT/$f.log &
   done

@@ -94,7 +94,7 @@ def test_trace_edge_cases(gpu_ctx, small_scene, small_oracle):
     assert got["instance"][0] == -1 and got["instance"][1] == 0 and abs(got["t"][1] - 5.0) < 1e-5 and got["instance"][2] == -1 and got["instance"][3] == -1
 
 
-@pytest.mark.parametrize("w,h,wavefront,fuse", [(320, 184, 0, 1), (250, 130, 0, 0), (320, 184, 1, 1), (250, 130, 1, 0), (320, 184, 2, 0), (250, 130, 2, 1)])
+@pytest.mark.parametrize("w,h,wavefront,fuse", [(320, 184, 0, 1), (250, 130, 0, 0), (320, 184, 1, 1), (250, 130, 1, 0), (320, 184, 2, 0), (250, 130, 2, 1), (320, 184, 4, 0), (250, 130, 4, 1), (320, 184, 5, 0), (250, 130, 5, 1)])
 def test_hybrid_frames_stage_by_stage(gpu_ctx, small_scene, small_oracle, w, h, wavefront, fuse):
     ctx, sc, o = gpu_ctx, small_scene, small_oracle
     cam = sc.camera(w, h)
@@ -119,8 +119,69 @@ def test_hybrid_frames_stage_by_stage(gpu_ctx, small_scene, small_oracle, w, h, 
         assert np.array_equal(ctx.readback(PLANE.FINAL_SRGB8), o.post(p, ref["final"]))
         assert [c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow] == list(o.counters.rays)
         # gbuffer, shadow, [denoise], resolve; 1: + one k_bounce per bounce (8), never fused; 2: + queue clear, k_chain_scan, k_chain;
+        # 4: + queue clear, k_chain_scan, k_chain_first, k_chain_shadow0, k_chain_shade0, k_chain_rest; 5: as 2 + k_resolve_paths;
         # + the two k_build_order launches of the longest-first schedule (side stream)
-        assert c.kernel_launches == {0: 4, 1: 4 + 8, 2: 7}[wavefront] - (1 if fuse and wavefront != 1 else 0) + 2
+        assert c.kernel_launches == {0: 4, 1: 4 + 8, 2: 7, 4: 10, 5: 8}[wavefront] - (1 if fuse and wavefront != 1 else 0) + 2
+
+
+@pytest.mark.parametrize("wavefront", [0, 1, 2, 3, 4, 5])
+def test_chain_schedules_with_the_advancing_rng(gpu_ctx, small_scene, small_oracle, wavefront):
+    """faithful_rng = 0: every sampleDisk call advances the path's seed, so the secondary shadow ray of light l depends on which of the
+    lights before it were sampled (hybridHit.rchit:99-131).  The staged chain (4) replays that per (path, light) thread; all five
+    schedules must give the oracle's bits and ray counts."""
+    ctx, sc, o = gpu_ctx, small_scene, small_oracle
+    w, h = 280, 160
+    cam = sc.camera(w, h)
+    ctx.set_camera(cam)
+    ctx.set_params(vk.make_params(w, h)); ctx.reset_history()
+    hist = None
+    for frame in range(2):
+        p = vk.make_params(w, h, frame=frame, wavefront=wavefront, faithful_rng=0, shadow_samples=2)
+        ctx.set_params(p)
+        o.reset_counters()
+        ref = o.hybrid_frame(cam, p, history=hist)
+        hist = ref["denoised"]
+        ctx.render()
+        c = ctx.counters()
+        final = ctx.readback(PLANE.FINAL_F32)
+        assert np.array_equal(final.view(np.uint32), ref["final"].view(np.uint32))
+        assert [c.rays_primary, c.rays_shadow, c.rays_reflect, c.rays_secondary_shadow] == list(o.counters.rays)
+
+
+def test_atrous_denoiser_matches_the_oracle(gpu_ctx, small_scene, small_oracle):
+    """vkp_params.denoiser = 1: three a-trous iterations (k_atrous) in front of blur.comp's temporal stage.  Reset frame,
+    two accumulation frames and the stage in isolation against the oracle's restatement, bit for bit; 16 x 16 remainder handling
+    and the advancing RNG with soft shadows (the noise the filter is for) included.  A tile-sharded context refuses the flag."""
+    ctx, sc, o = gpu_ctx, small_scene, small_oracle
+    w, h = 278, 154
+    cam = sc.camera(w, h)
+    ctx.set_camera(cam)
+    ctx.set_params(vk.make_params(w, h)); ctx.reset_history()
+    hist = None
+    for frame in range(3):
+        p = vk.make_params(w, h, frame=frame, wavefront=2, denoiser=1, faithful_rng=0, shadow_samples=2)
+        ctx.set_params(p)
+        ref = o.hybrid_frame(cam, p, history=hist)
+        hist = ref["denoised"]
+        ctx.render()
+        c = ctx.counters()
+        for l in range(len(sc.lights)):
+            assert np.array_equal(ctx.readback(PLANE.SHADOW0 + l), ref["shadow"][l]), (frame, l)
+            assert np.array_equal(ctx.readback(PLANE.DENOISED0 + l), ref["denoised"][l]), (frame, l)
+        assert np.array_equal(ctx.readback(PLANE.FINAL_F32).view(np.uint32), ref["final"].view(np.uint32)), frame
+        assert c.kernel_launches == 7 + 3 + 2          # chain mode 2 + the three k_atrous launches + the two k_build_order
+    # the filter changes the image (it is not a no-op on this scene) ...
+    p_off = vk.make_params(w, h, frame=0, wavefront=2, denoiser=0, faithful_rng=0, shadow_samples=2)
+    p_on = vk.make_params(w, h, frame=0, wavefront=2, denoiser=1, faithful_rng=0, shadow_samples=2)
+    ctx.set_params(p_off); ctx.reset_history(); ctx.render(); a = ctx.readback(PLANE.DENOISED0).copy()
+    ctx.set_params(p_on); ctx.reset_history(); ctx.render(); b = ctx.readback(PLANE.DENOISED0).copy()
+    assert not np.array_equal(a, b)
+    # ... and a tile-sharded context says no
+    ctx.set_tiling(0, 2, 32, 16)
+    with pytest.raises(vk.VkpError):
+        ctx.render()
+    ctx.set_tiling(0, 1, 16, 8)
+    ctx.set_params(p_off); ctx.reset_history(); ctx.render()
 
 
 def test_stage_isolation(gpu_ctx, small_scene, small_oracle):

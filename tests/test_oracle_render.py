@@ -275,3 +275,36 @@ def test_reproject_fix_fetches_the_previous_frames_pixel(small_scene, small_orac
     geo = s0["g"].hit_ids[..., 0] >= 0
     assert np.array_equal(s0["denoised"][:, geo], s1["denoised"][:, geo]) and np.array_equal(s0["final"].view(np.uint32), s1["final"].view(np.uint32))
     sc.close()
+
+
+def test_atrous_denoiser_smooths_noise_and_keeps_edges(small_scene, small_oracle):
+    """vkp_params.denoiser = 1 (no reference counterpart): the a-trous iterations are a weighted mean with non-negative
+    weights, so (a) uniform planes pass through unchanged, (b) every output lies between the minimum and the maximum of the input,
+    (c) noise on a smooth surface shrinks, (d) background pixels are copied, and the default (0) is untouched by the new code."""
+    sc, o = small_scene, small_oracle
+    w, h = 128, 72
+    cam = sc.camera(w, h)
+    p0 = vk.make_params(w, h, frame=0)
+    p1 = vk.make_params(w, h, frame=0, denoiser=1)
+    g = o.gbuffer(cam, p0)
+    L = len(sc.lights)
+    nrm = g.normal.view(np.float16).reshape(h, w, 4)
+    surface = nrm[..., 3] != 0
+    assert surface.mean() > 0.3 and (~surface).any()
+    zero_hist = np.zeros((L, h, w), np.uint8)
+    for v in (0, 255, 77):
+        flat = np.full((L, h, w), v, np.uint8)
+        out = o.denoise(p1, g, flat, zero_hist)
+        # reset frame: blur.comp's temporal stage with a clamped history gives mix(v, v, 0.4) = v on a uniform plane (borders read 0 outside the image)
+        assert np.array_equal(out[:, 2:-2, 2:-2], flat[:, 2:-2, 2:-2])
+    rng = np.random.default_rng(11)
+    base = np.where(rng.random((L, h, w)) < 0.5, 255, 0).astype(np.uint8)          # 1-sample soft-shadow noise: binary
+    acc = vk.make_params(w, h, frame=5, denoise_frame=5)                            # accumulation frame: out = mix(old, center, 1/6)
+    acc1 = vk.make_params(w, h, frame=5, denoise_frame=5, denoiser=1)
+    hist = np.full((L, h, w), 128, np.uint8)
+    raw = o.denoise(acc, g, base, hist).astype(np.float32)
+    fil = o.denoise(acc1, g, base, hist).astype(np.float32)
+    s = np.broadcast_to(surface, raw.shape)
+    assert fil[s].std() < 0.5 * raw[s].std()                                       # the filtered centre carries far less noise into the history
+    assert np.array_equal(fil[~s], raw[~s])                                        # background: the raw value, as before
+    assert np.array_equal(o.denoise(p0, g, base, zero_hist), o.denoise(vk.make_params(w, h, frame=0, denoiser=0), g, base, zero_hist))

@@ -11,6 +11,7 @@ there is no Python or CPU compute path.  Loading fails loudly when the libraries
 """
 from .capi import (  # noqa: F401
     Context,
+    Group,
     HostEngine,
     HostScene,
     VkpError,
@@ -28,6 +29,6 @@ from .capi import (  # noqa: F401
 from . import types  # noqa: F401
 
 __all__ = [
-    "Context", "HostEngine", "HostScene", "VkpError", "load_host", "load_scene", "load_vkp", "lib_dir",
+    "Context", "Group", "HostEngine", "HostScene", "VkpError", "load_host", "load_scene", "load_vkp", "lib_dir",
     "MODE_DEFERRED", "MODE_HYBRID", "MODE_RAYTRACING", "PLANE", "STAGE", "make_params", "types",
 ]

@@ -117,6 +117,26 @@ def load_vkp():
         "vkp_sync_release": (i, [vp, C.c_uint32, i]),
         "vkp_sync_wait_release": (i, [vp, C.c_uint32]),
         "vkp_sync_timed_out": (i, [vp, P(i)]),
+        "vkp_group_create": (i, [P(vp), P(i), i, i, i]),
+        "vkp_group_destroy": (None, [vp]),
+        "vkp_group_size": (i, [vp]),
+        "vkp_group_member": (vp, [vp, i]),
+        "vkp_group_last_error": (C.c_char_p, [vp]),
+        "vkp_group_upload_mesh": (i, [vp, vp, u32, vp, u32, P(i)]),
+        "vkp_group_upload_texture_rgba8": (i, [vp, vp, i, i, P(i)]),
+        "vkp_group_set_env": (i, [vp, i, i]),
+        "vkp_group_set_materials": (i, [vp, vp, i]),
+        "vkp_group_set_lights": (i, [vp, vp, i]),
+        "vkp_group_set_instances": (i, [vp, vp, i]),
+        "vkp_group_build_blas": (i, [vp]),
+        "vkp_group_build_tlas": (i, [vp, i]),
+        "vkp_group_set_camera": (i, [vp, P(T.Camera)]),
+        "vkp_group_set_params": (i, [vp, P(T.Params)]),
+        "vkp_group_reset_history": (i, [vp]),
+        "vkp_group_render": (i, [vp]),
+        "vkp_group_sync": (i, [vp]),
+        "vkp_group_readback": (i, [vp, i, vp, sz]),
+        "vkp_group_get_counters": (i, [vp, P(T.Counters)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -183,6 +203,7 @@ def load_host():
     P = C.POINTER
     sig = {
         "vkph_engine_create": (vp, [i, i, i, i, P(i)]),
+        "vkph_engine_create_multi": (vp, [i, i, i, i, i, P(i)]),
         "vkph_engine_set": (i, [vp, C.c_char_p, i]),
         "vkph_engine_frames": (i, [vp, i]),
         "vkph_engine_camera_move": (i, [vp, i, C.c_float]),
@@ -582,11 +603,11 @@ class Context:
 class HostEngine:
     """VulkanEngine of the host library (init / run(frames) / cleanup), driven through the shim."""
 
-    def __init__(self, scene_index=0, width=1700, height=900, device=0, detail=None):
+    def __init__(self, scene_index=0, width=1700, height=900, device=0, detail=None, gpus=1):
         H = load_host()
         self._H = H
         self.width, self.height = width, height
-        self._h = H.vkph_engine_create(scene_index, width, height, device, _detail4(detail))
+        self._h = H.vkph_engine_create_multi(scene_index, width, height, device, gpus, _detail4(detail))
         if not self._h:
             raise VkpError(H.vkph_last_error().decode())
 
@@ -643,3 +664,87 @@ class HostEngine:
             self.close()
         except Exception:
             pass
+
+
+class Group:
+    """One vkp_group: several GPUs of the box render every frame together in ONE process (tiles dealt over the members, the
+    composite lands in rank 0's image over NVLink peer stores).  Thin: every method is one vkp_group_* call."""
+
+    def __init__(self, devices, tile=(32, 16)):
+        self.L = load_vkp()
+        h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        r = self.L.vkp_group_create(C.byref(h), arr, len(devices), tile[0], tile[1])
+        if r != 0:
+            raise VkpError(f"vkp_group_create failed ({r}): {self.L.vkp_last_error(None).decode()}")
+        self.h = h
+        self.width = self.height = 0
+
+    def _ck(self, r, what):
+        if r != 0:
+            raise VkpError(f"{what} failed ({r}): {self.L.vkp_group_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vkp_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        return self.L.vkp_group_size(self.h)
+
+    def upload_scene(self, scene):
+        for verts, idx in scene.meshes:
+            verts = np.ascontiguousarray(verts, dtype=T.vertex_dtype); idx = np.ascontiguousarray(idx, dtype=np.uint32)
+            mid = C.c_int(-1)
+            self._ck(self.L.vkp_group_upload_mesh(self.h, verts.ctypes.data, len(verts), idx.ctypes.data, len(idx), C.byref(mid)), "vkp_group_upload_mesh")
+        for tex in scene.textures:
+            rgba = np.ascontiguousarray(tex, dtype=np.uint8)
+            tid = C.c_int(-1)
+            self._ck(self.L.vkp_group_upload_texture_rgba8(self.h, rgba.ctypes.data, rgba.shape[1], rgba.shape[0], C.byref(tid)), "vkp_group_upload_texture_rgba8")
+        self._ck(self.L.vkp_group_set_env(self.h, scene.sky_tex, scene.irradiance_tex), "vkp_group_set_env")
+        m = np.ascontiguousarray(scene.materials, dtype=T.material_dtype)
+        self._ck(self.L.vkp_group_set_materials(self.h, m.ctypes.data, len(m)), "vkp_group_set_materials")
+        self.set_lights(scene.lights)
+        inst = np.ascontiguousarray(scene.instances, dtype=T.instance_dtype)
+        self._ck(self.L.vkp_group_set_instances(self.h, inst.ctypes.data, len(inst)), "vkp_group_set_instances")
+        self._ck(self.L.vkp_group_build_blas(self.h), "vkp_group_build_blas")
+        self._ck(self.L.vkp_group_build_tlas(self.h, 0), "vkp_group_build_tlas")
+
+    def set_lights(self, lights):
+        l = np.ascontiguousarray(lights, dtype=T.light_dtype)
+        self._ck(self.L.vkp_group_set_lights(self.h, l.ctypes.data, len(l)), "vkp_group_set_lights")
+
+    def set_camera(self, cam):
+        self._ck(self.L.vkp_group_set_camera(self.h, C.byref(cam)), "vkp_group_set_camera")
+
+    def set_params(self, p):
+        self.width, self.height = p.width, p.height
+        self._ck(self.L.vkp_group_set_params(self.h, C.byref(p)), "vkp_group_set_params")
+
+    def reset_history(self):
+        self._ck(self.L.vkp_group_reset_history(self.h), "vkp_group_reset_history")
+
+    def render(self):
+        self._ck(self.L.vkp_group_render(self.h), "vkp_group_render")
+
+    def sync(self):
+        self._ck(self.L.vkp_group_sync(self.h), "vkp_group_sync")
+
+    def readback(self, plane):
+        dt, ch = plane_format(plane)
+        shape = (self.height, self.width, ch) if ch > 1 else (self.height, self.width)
+        out = np.empty(shape, dtype=dt)
+        self._ck(self.L.vkp_group_readback(self.h, plane, out.ctypes.data, out.nbytes), "vkp_group_readback")
+        return out
+
+    def counters(self):
+        c = T.Counters()
+        self._ck(self.L.vkp_group_get_counters(self.h, C.byref(c)), "vkp_group_get_counters")
+        return c
+

@@ -12,6 +12,7 @@
 // rank owns (tile t belongs to rank t % world).
 #include "vkp_internal.h"
 #include "vkp_bvh.cuh"
+#include <cstdlib>
 
 // occupancy knobs (min resident CTAs per SM -> register cap), tuned by measurement
 #ifndef VKP_LB_GBUFFER
@@ -28,6 +29,9 @@
 #endif
 #ifndef VKP_LB_RESOLVE
 #define VKP_LB_RESOLVE 5
+#endif
+#ifndef VKP_CHAIN_CALL
+#define VKP_CHAIN_CALL 0      /* 1: k_chain calls the traversal (trace_ray_call) instead of inlining it */
 #endif
 #ifndef VKP_LB_CHAIN
 #define VKP_LB_CHAIN 3        /* 168 registers: the sparse chain kernel gains nothing from occupancy, a lot from not spilling */
@@ -158,6 +162,15 @@ __device__ __forceinline__ void path_push(PathItem* q, unsigned int* count, bool
 
 struct Payload { float3 color; float dist; float3 direction; float scatter; float3 origin; uint32_t seed; };
 
+// trace_ray as a real call (CALL == true below): in the chain kernels the hit shader's state and the traversal's state then do not
+// have to be in registers at the same time -- what is live across the call goes to the stack once per ray instead of the register
+// allocator spilling inside the node loop
+template <bool ANY>
+__device__ __noinline__ bool trace_ray_call(const DScene& S, uint32_t* __restrict__ sstack, float3 o, float3 d, float tmin, float tmax, HitRec& best, TravCount* tcount)
+{
+    return trace_ray<ANY>(S, sstack, o, d, tmin, tmax, best, nullptr, tcount);
+}
+
 // miss.rmiss:13-19
 __device__ __forceinline__ void shade_miss(const DScene& S, float3 rayDir, Payload& prd)
 {
@@ -171,9 +184,11 @@ __device__ __forceinline__ void shade_miss(const DScene& S, float3 rayDir, Paylo
 // WARP != 0: the 32 lanes of the warp hold the SAME path; everything is computed redundantly (one SIMT instruction stream,
 // broadcast loads) except the shadow rays: WARP == 1 (k_raytrace_warp) spreads the per-light shadow samples over the lanes,
 // WARP == 2 (k_chain) traces the one shadow ray per light with the whole warp (warp_trace).
-template <bool RT, int WARP = 0>
+// PRE (Hybrid only): the per-light secondary shadow rays of this hit were traced by k_chain_shadow0 (staged chain, mode 4);
+// bit l of pre_mask = the ray towards light l was blocked.  Nothing is traced here; the RNG still advances as if it were.
+template <bool RT, int WARP = 0, bool PRE = false, bool CALL = false>
 __device__ void shade_hit(const DScene& S, uint32_t* __restrict__ sstack, const vkp_params& P, float3 rayO, float3 rayD, const HitRec& h, Payload& prd,
-                          unsigned int& n_secondary, TravCount* tcp, const WarpQueue* wq = nullptr)
+                          unsigned int& n_secondary, TravCount* tcp, const WarpQueue* wq = nullptr, uint32_t pre_mask = 0u)
 {
     const DInstance& I = S.instances[h.inst];
     const float b0 = 1.0f - h.u - h.v, b1 = h.u, b2 = h.v;
@@ -290,10 +305,16 @@ __device__ void shade_hit(const DScene& S, uint32_t* __restrict__ sstack, const 
                 if (NdotL > 0.0f) {
                     bool shadowed = true;
                     if (light_distance < light_max_distance) {
-                        float3 dir = sample_disk(light, worldPos, L, prd.seed, advance);
-                        HitRec sh; n_secondary++;
-                        if (WARP == 2) shadowed = warp_trace<true>(S, *wq, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, tcp);
-                        else shadowed = trace_ray<true>(S, sstack, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, nullptr, tcp);
+                        if (PRE) {
+                            if (advance) { prd.seed = 1664525u * prd.seed + 1013904223u; prd.seed = 1664525u * prd.seed + 1013904223u; }   // the two rnd() of sampleDisk
+                            shadowed = ((pre_mask >> i) & 1u) != 0u;
+                        } else {
+                            float3 dir = sample_disk(light, worldPos, L, prd.seed, advance);
+                            HitRec sh; n_secondary++;
+                            if (WARP == 2) shadowed = warp_trace<true>(S, *wq, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, tcp);
+                            else if (CALL) shadowed = trace_ray_call<true>(S, sstack, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, tcp);
+                            else shadowed = trace_ray<true>(S, sstack, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, nullptr, tcp);
+                        }
                     }
                     if (!shadowed) shadowFactor += 1.0f;
                 }
@@ -571,6 +592,52 @@ __device__ __forceinline__ uint8_t denoise_pixel(const DFrame& F, int l, int x, 
     return vkp_unorm8(pixelColor);
 }
 
+// vkp_params.denoiser == 1 (SURVEY 8f-3 "a better denoiser"; no reference counterpart, restated by the oracle's
+// atrous_iteration): one iteration of an edge-aware a-trous filter over the R8 shadow planes, guided by the G-buffer.  5 x 5 taps `step`
+// pixels apart, B3-spline weights, a normal weight max(0, N_p . N_q)^32 and a plane-distance weight max(0, 1 - |N_p . (P_q - P_p)| /
+// (0.1 step)); background pixels pass through and are never taps.  Lights are filtered four at a time (the weights do not depend on
+// the light); the accumulation order -- rows, then columns -- is the oracle's.
+__global__ void __launch_bounds__(128) k_atrous(const __grid_constant__ DScene S, const __grid_constant__ DFrame F, const uint8_t* __restrict__ in,
+                                                uint8_t* __restrict__ out, int step)
+{
+    const Pixel px = pixel_of_thread(F);
+    if (!px.valid) return;
+    const int W = F.p.width, H = F.p.height;
+    const size_t plane = (size_t)W * H, i = (size_t)px.y * W + px.x;
+    const float4 np4 = unpack_half4(F.normal[i]);
+    if (np4.w == 0.0f) { for (int l = 0; l < S.n_lights; l++) out[l * plane + i] = in[l * plane + i]; return; }
+    const float3 Np = normalize3(xyz(np4) * 2.0f - f3s(1.0f));
+    const float3 Pp = xyz(unpack_half4(F.position[i]));
+    const float inv_sigma = 1.0f / (0.1f * (float)step);
+    for (int l0 = 0; l0 < S.n_lights; l0 += 4) {
+        float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f}, wsum = 0.0f;
+        for (int dy = -2; dy <= 2; dy++)
+            for (int dx = -2; dx <= 2; dx++) {
+                const int qx = px.x + dx * step, qy = px.y + dy * step;
+                if (qx < 0 || qy < 0 || qx >= W || qy >= H) continue;
+                const size_t q = (size_t)qy * W + qx;
+                const float4 nq4 = unpack_half4(F.normal[q]);
+                if (nq4.w == 0.0f) continue;
+                const float3 Nq = normalize3(xyz(nq4) * 2.0f - f3s(1.0f));
+                const float3 Pq = xyz(unpack_half4(F.position[q]));
+                float wn = fmaxf(dot3(Np, Nq), 0.0f);
+                wn = wn * wn; wn = wn * wn; wn = wn * wn; wn = wn * wn; wn = wn * wn;
+                const float dist = fabsf(dot3(Np, Pq - Pp));
+                const float wp = fmaxf(1.0f - dist * inv_sigma, 0.0f);
+                const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
+                const float kx = ax == 0 ? 0.375f : ax == 1 ? 0.25f : 0.0625f, ky = ay == 0 ? 0.375f : ay == 1 ? 0.25f : 0.0625f;
+                const float w = (kx * ky) * wn * wp;
+                wsum = wsum + w;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (l0 + k < S.n_lights) sum[k] = sum[k] + w * unit255(in[(l0 + k) * plane + q]);
+            }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (l0 + k < S.n_lights) out[(l0 + k) * plane + i] = vkp_unorm8(sum[k] / wsum);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_denoise(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     const Pixel px = pixel_of_thread(F);
@@ -697,8 +764,13 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain(const __
         for (int depth = 0; depth < F.p.max_bounces; depth++) {
             float3 ro = origin + direction * 1e-2f;
             HitRec h; n_refl++;
+#if VKP_CHAIN_CALL
+            const bool hit = trace_ray_call<false>(S, sstack, ro, direction, 0.001f, 1000.0f, h, tcp);
+            if (hit) shade_hit<false, 0, false, true>(S, sstack, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
+#else
             const bool hit = trace_ray<false>(S, sstack, ro, direction, 0.001f, 1000.0f, h, nullptr, tcp);
             if (hit) shade_hit<false>(S, sstack, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
+#endif
             rec[n] = make_float4(prd.color.x, prd.color.y, prd.color.z, 0.0f);
             n++;
             if (!hit || !(prd.scatter > 0.0f)) break;
@@ -764,9 +836,192 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_warp(con
     if (F.count_trav) add_trav(F.counters, tc);
 }
 
+// ---- staged chain (mode 4): the FIRST bounce of every path as a wavefront ---------------------------------------------------------
+// 8 % of the 1080p default frame's pixels start a path and 87 % of all reflection rays are first bounces.  One thread per path
+// (k_chain) runs them at the register count of the hit shader -- 12 resident warps per SM, three waves of latency-bound traversals --
+// and that kernel, not k_shadow, set the length of the overlapped stage.  Here the first bounce is split at its two trace calls so
+// that each traversal runs in a lean kernel at full occupancy, and what continues is compacted before it goes on:
+//   k_chain_first    one thread per path: first_bounce() + closest hit                -> path record (ray, hit)
+//   k_chain_shadow0  one thread per (path, light): hybridHit.rchit:99-131's any-hit ray -> blocked-light mask of the record
+//   k_chain_shade0   one thread per path: hybridHit.rchit / miss.rmiss with the mask    -> colour 0; paths that scatter are
+//                    appended to a second queue (ballot + popc prefix, one atomic per warp)
+//   k_chain_rest     one thread per continuing path (5 % of the first bounces): bounces 1 .. max_bounces-1 as in k_chain
+// Records live in path_q[0] (by slot) and path_q[1] (continuing paths); path_count[2] counts the latter.  Same arithmetic in the
+// same order as k_chain: every stored colour is bit-identical.
+//   record.a = ray origin (already offset), t of the hit or -1     record.b = direction, u     record.c = v, instance, primitive, mask
+__device__ __forceinline__ void chain_first_ray(const DScene& S, const DFrame& F, size_t i, float3& ro, float3& direction)
+{
+    const float4 pos4 = unpack_half4(F.position[i]);
+    const vkp_material& mat = material_by_float_index(S, pos4.w);
+    const int shadingMode = (int)mat.shadingMetallicRoughness[0];
+    const float4 nrm4 = unpack_half4(F.normal[i]);
+    const float3 position = xyz(pos4);
+    const float3 N = normalize3(xyz(nrm4) * 2.0f - f3s(1.0f));
+    const float3 camPosition = f3(F.cam.inv_view[12], F.cam.inv_view[13], F.cam.inv_view[14]);
+    const float3 V = normalize3(camPosition - position);
+    float3 origin = f3s(0.0f); direction = f3s(0.0f);
+    if (S.n_lights > 0) first_bounce(shadingMode, mat, position, N, V, origin, direction);   // upstream sets them inside the light loop
+    ro = origin + direction * 1e-2f;
+}
+
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, 8) k_chain_first(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
+    const unsigned int n_paths = F.path_count[0];
+    unsigned int n_refl = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;
+    for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
+        const size_t i = (size_t)F.chain_pix[slot];
+        float3 ro, direction;
+        chain_first_ray(S, F, i, ro, direction);
+        HitRec h; n_refl++;
+        const bool hit = trace_ray<false>(S, sstack, ro, direction, 0.001f, 1000.0f, h, nullptr, tcp);
+        PathItem* rec = F.path_q[0] + slot;
+        rec->a = make_float4(ro.x, ro.y, ro.z, hit ? h.t : -1.0f);
+        rec->b = make_float4(direction.x, direction.y, direction.z, h.u);
+        rec->c = make_float4(h.v, __int_as_float(h.inst), __int_as_float(h.prim), __uint_as_float(0u));
+    }
+    add_counter(F.counters, 2, n_refl);
+    if (F.count_trav) add_trav(F.counters, tc);
+}
+
+// world position, shading normal and shading mode of a hit, as shade_hit computes them
+__device__ __forceinline__ void hit_normal_pos(const DScene& S, float3 rayO, float3 rayD, const HitRec& h, float3& N, float3& worldPos, int& shadingMode)
+{
+    const DInstance& I = S.instances[h.inst];
+    const float b0 = 1.0f - h.u - h.v, b1 = h.u, b2 = h.v;
+    const uint32_t* ind = I.indices + 3u * (uint32_t)h.prim;
+    const vkp_vertex& v0 = I.vertices[__ldg(ind)]; const vkp_vertex& v1 = I.vertices[__ldg(ind + 1)]; const vkp_vertex& v2 = I.vertices[__ldg(ind + 2)];
+    const float3 normal = f3(v0.normal[0], v0.normal[1], v0.normal[2]) * b0 + f3(v1.normal[0], v1.normal[1], v1.normal[2]) * b1 +
+                          f3(v2.normal[0], v2.normal[1], v2.normal[2]) * b2;
+    N = normalize3(xform_normal_by_inverse(I.inv_model, normal));
+    worldPos = rayO + rayD * h.t;
+    const vkp_material& mat = S.materials[max(0, min(I.material_id, S.n_materials - 1))];
+    shadingMode = (int)mat.shadingMetallicRoughness[0];
+}
+
+// blockIdx.y = light.  hybridHit.rchit:99-131: a diffuse hit facing a light within its range traces one any-hit ray towards it.
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, 8) k_chain_shadow0(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
+    const unsigned int n_paths = F.path_count[0];
+    const int l = (int)blockIdx.y;
+    unsigned int n_sec = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;
+    const bool advance = F.p.faithful_rng == 0;
+    for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
+        PathItem* rec = F.path_q[0] + slot;
+        const float4 a = rec->a;
+        if (a.w < 0.0f) continue;                                       // the first ray missed: sky
+        const float4 b = rec->b, c = rec->c;
+        HitRec h; h.t = a.w; h.u = b.w; h.v = c.x; h.inst = __float_as_int(c.y); h.prim = __float_as_int(c.z);
+        float3 N, worldPos; int shadingMode;
+        hit_normal_pos(S, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), h, N, worldPos, shadingMode);
+        if (shadingMode != 0) continue;                                 // mirror / glass hits trace no shadow rays (hybridHit.rchit:133-183)
+        const vkp_light light = S.lights[l];
+        const LightGeom g = light_geom(light, worldPos, N);
+        if (!(g.NdotL > 0.0f) || !(g.dist < g.maxd)) continue;
+        const size_t i = (size_t)F.chain_pix[slot];
+        const int py = (int)(i / (size_t)F.p.width), pxl = (int)(i - (size_t)py * F.p.width);
+        uint32_t seed = tea16((uint32_t)py * (uint32_t)F.p.width + (uint32_t)pxl, (uint32_t)F.p.frame);
+        if (advance) {
+            for (int k = 0; k < l; k++) {
+                const LightGeom gk = light_geom(S.lights[k], worldPos, N);
+                if (gk.NdotL > 0.0f && gk.dist < gk.maxd) { seed = 1664525u * seed + 1013904223u; seed = 1664525u * seed + 1013904223u; }
+            }
+        }
+        const float3 dir = sample_disk(light, worldPos, g.L, seed, advance);
+        HitRec sh; n_sec++;
+        if (trace_ray<true>(S, sstack, worldPos + dir * 1e-2f, dir, 0.001f, g.dist + 1.0f, sh, nullptr, tcp))
+            atomicOr(reinterpret_cast<unsigned int*>(&rec->c.w), 1u << l);
+    }
+    add_counter(F.counters, 3, n_sec);
+    if (F.count_trav) add_trav(F.counters, tc);
+}
+
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_shade0(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    const unsigned int n_paths = F.path_count[0];
+    const unsigned int n_round = (n_paths + 31u) & ~31u;              // whole warps stay in the loop so that the ballots are convergent
+    unsigned int n_sec = 0;
+    for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_round; slot += gridDim.x * blockDim.x) {
+        bool again = false;
+        PathItem item;
+        if (slot < n_paths) {
+            const PathItem* rec = F.path_q[0] + slot;
+            const float4 a = rec->a, b = rec->b, c = rec->c;
+            const size_t i = (size_t)F.chain_pix[slot];
+            const int py = (int)(i / (size_t)F.p.width), pxl = (int)(i - (size_t)py * F.p.width);
+            Payload prd;
+            prd.seed = tea16((uint32_t)py * (uint32_t)F.p.width + (uint32_t)pxl, (uint32_t)F.p.frame);
+            const float3 ro = f3(a.x, a.y, a.z), direction = f3(b.x, b.y, b.z);
+            const bool hit = !(a.w < 0.0f);
+            if (hit) {
+                HitRec h; h.t = a.w; h.u = b.w; h.v = c.x; h.inst = __float_as_int(c.y); h.prim = __float_as_int(c.z);
+                shade_hit<false, 0, true>(S, nullptr, F.p, ro, direction, h, prd, n_sec, nullptr, nullptr, __float_as_uint(c.w));
+            } else shade_miss(S, direction, prd);
+            F.chain_buf[(size_t)slot * VKP_CHAIN_MAX] = make_float4(prd.color.x, prd.color.y, prd.color.z, 0.0f);
+            again = hit && (prd.scatter > 0.0f) && F.p.max_bounces > 1;
+            if (!again) F.chain_len[slot] = 1;
+            else {
+                item.a = make_float4(prd.origin.x, prd.origin.y, prd.origin.z, __uint_as_float(slot));
+                item.b = make_float4(prd.direction.x, prd.direction.y, prd.direction.z, __uint_as_float(prd.seed));
+            }
+        }
+        // the continuing paths, compacted (only a and b of the item are used)
+        const unsigned mask = __ballot_sync(0xffffffffu, again);
+        if (mask) {
+            const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(&F.path_count[2], (unsigned)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (again) { PathItem* q = F.path_q[1] + base + __popc(mask & ((1u << lane) - 1u)); q->a = item.a; q->b = item.b; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_rest(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
+    const unsigned int n_cont = F.path_count[2];
+    unsigned int n_refl = 0, n_sec = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_cont; k += gridDim.x * blockDim.x) {
+        const float4 qa = F.path_q[1][k].a, qb = F.path_q[1][k].b;
+        const unsigned int slot = __float_as_uint(qa.w);
+        float4* rec = F.chain_buf + (size_t)slot * VKP_CHAIN_MAX;
+        float3 origin = f3(qa.x, qa.y, qa.z), direction = f3(qb.x, qb.y, qb.z);
+        Payload prd; prd.seed = __float_as_uint(qb.w);
+        int n = 1;
+        for (int depth = 1; depth < F.p.max_bounces; depth++) {
+            float3 ro = origin + direction * 1e-2f;
+            HitRec h; n_refl++;
+            const bool hit = trace_ray<false>(S, sstack, ro, direction, 0.001f, 1000.0f, h, nullptr, tcp);
+            if (hit) shade_hit<false>(S, sstack, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
+            rec[n] = make_float4(prd.color.x, prd.color.y, prd.color.z, 0.0f);
+            n++;
+            if (!hit || !(prd.scatter > 0.0f)) break;
+            origin = prd.origin; direction = prd.direction;
+        }
+        F.chain_len[slot] = n;
+    }
+    add_counter(F.counters, 2, n_refl);
+    add_counter(F.counters, 3, n_sec);
+    if (F.count_trav) add_trav(F.counters, tc);
+}
+
 // CHAIN == 0: the bounce chain runs inline in this kernel (its latency hides behind the other pixels' shading);
 // CHAIN == 1: mirror / glass pixels are compacted into a path queue consumed by k_bounce, one launch per bounce;
 // CHAIN == 2: the chain was traced by k_chain concurrently with the shadow pass; multiply its stored colours in.
+// CHAIN == 3: as 2, but this kernel does not wait for the chain: a mirror / glass pixel leaves its direct term and its ambient tail in
+//             the path's record and k_resolve_paths finishes it once the chain is there -- the chain's longest path then overlaps
+//             the shadow pass, the filter AND the resolve of the other 92 % of the pixels.
 template <int CHAIN>
 __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_RESOLVE) k_resolve(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
@@ -893,7 +1148,11 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_RESOLVE) k_resolve(cons
                 origin = prd.origin; direction = prd.direction;
             }
         }
-        if (CHAIN != 1 || !wants_path) {
+        if (CHAIN == 3 && wants_path) {
+            PathItem* rec = F.path_q[1] + F.chain_slot[i];
+            rec->c = make_float4(rayColor.x, rayColor.y, rayColor.z, background ? 1.0f : 0.0f);
+            rec->d = background ? make_float4(albedo.x, albedo.y, albedo.z, 0.0f) : make_float4(tail.x, tail.y, tail.z, 0.0f);
+        } else if (CHAIN != 1 || !wants_path) {
             float3 finalColor = rayColor + tail;
             if (background) finalColor = albedo;
             float4 outc = make_float4(finalColor.x, finalColor.y, finalColor.z, 1.0f);
@@ -959,6 +1218,27 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK) k_bounce(const __grid_constant
     add_counter(F.counters, 2, n_refl);
     add_counter(F.counters, 3, n_sec);
     if (F.count_trav) add_trav(F.counters, tc);
+}
+
+// the end of hybridRaygen.rgen:153-183 for the mirror / glass pixels of k_resolve<3>: throughput = direct term x the chain's colours in
+// bounce order, + ambient tail (or the sky albedo); one thread per path slot
+__global__ void __launch_bounds__(128) k_resolve_paths(const __grid_constant__ DFrame F)
+{
+    const unsigned int n_paths = F.path_count[0];
+    for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
+        const size_t i = (size_t)F.chain_pix[slot];
+        const float4 c0 = F.path_q[1][slot].c, t0 = F.path_q[1][slot].d;
+        float3 rayColor = f3(c0.x, c0.y, c0.z);
+        const float4* rec = F.chain_buf + (size_t)slot * VKP_CHAIN_MAX;
+        const int n = F.chain_len[slot];
+        for (int k = 0; k < n; k++) { float4 c = rec[k]; rayColor = rayColor * f3(c.x, c.y, c.z); }
+        const float3 tail = f3(t0.x, t0.y, t0.z);
+        float3 finalColor = rayColor + tail;
+        if (c0.w != 0.0f) finalColor = tail;                    // background: the sky albedo
+        float4 outc = make_float4(finalColor.x, finalColor.y, finalColor.z, 1.0f);
+        F.final_f32[i] = outc;
+        F.final_srgb8[i] = post_pixel(F.lut_post, outc);
+    }
 }
 
 __global__ void __launch_bounds__(128) k_post(const __grid_constant__ DFrame F)
@@ -1305,8 +1585,17 @@ cudaError_t launch_build_order(cudaStream_t s, uint32_t* cost, uint32_t* order, 
     k_build_order<<<1, 256, 0, s>>>(cost, order, n);
     return cudaGetLastError();
 }
-cudaError_t launch_denoise(const FrameLaunch& L)
+cudaError_t launch_denoise(const FrameLaunch& L, uint8_t* atrous_a, uint8_t* atrous_b)
 {
+    if (L.frame.p.denoiser == 1 && atrous_a && atrous_b) {
+        // three a-trous iterations (steps 1, 2, 4), then blur.comp's temporal stage on the filtered planes
+        k_atrous<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame, L.frame.shadow, atrous_a, 1);
+        k_atrous<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame, atrous_a, atrous_b, 2);
+        k_atrous<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame, atrous_b, atrous_a, 4);
+        FrameLaunch T = L;
+        T.frame.shadow = atrous_a;
+        return launch_denoise(T, nullptr, nullptr);
+    }
     if (L.frame.p.denoise_frame > 0 && L.frame.p.width % 4 == 0) k_denoise_accumulate4<<<frame_grid(L), 32, 0, L.stream>>>(L.scene, L.frame);
     else k_denoise<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);
     return cudaGetLastError();
@@ -1315,6 +1604,11 @@ cudaError_t launch_resolve(const FrameLaunch& L, int* launches)
 {
     if (L.frame.p.wavefront == 0 || (L.frame.p.wavefront >= 2 && L.frame.p.max_bounces > VKP_CHAIN_MAX)) {
         k_resolve<0><<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
+    if (L.frame.p.wavefront == 5) {
+        k_resolve<3><<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);     // needs k_chain_scan only; launch_resolve_paths follows the chain
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
@@ -1335,18 +1629,45 @@ cudaError_t launch_resolve(const FrameLaunch& L, int* launches)
     }
     return cudaGetLastError();
 }
-cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream)
+cudaError_t launch_resolve_paths(const FrameLaunch& L)
+{
+    k_resolve_paths<<<frame_grid(L).x / 4u + 1u, 128, 0, L.stream>>>(L.frame);
+    return cudaGetLastError();
+}
+cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t after_scan)
 {
     // path_count[0] = number of paths, [1] = head of the queue the persistent warps of mode 3 pull from
-    cudaError_t e = launch_stage_words(stream, L.frame.path_count, nullptr, 2 * sizeof(unsigned int));
+    // [2] = number of paths that go on after their first bounce (staged chain, mode 4)
+    cudaError_t e = launch_stage_words(stream, L.frame.path_count, nullptr, 3 * sizeof(unsigned int));
     if (e != cudaSuccess) return e;
     k_chain_scan<<<frame_grid(L), 128, 0, stream>>>(L.scene, L.frame);
-    if (L.frame.p.wavefront == 3) k_chain_warp<<<148 * VKP_LB_CHAIN, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    if (after_scan && (e = cudaEventRecord(after_scan, stream)) != cudaSuccess) return e;
+    if (L.frame.p.wavefront == 4) {
+        // the queue lengths are only known on the device: grids sized for the usual share of path pixels, grid-stride loops beyond it
+        const unsigned int px_blocks = frame_grid(L).x;
+        const unsigned int g1 = px_blocks / 4u + 1u, g2 = px_blocks / 16u + 1u;
+        k_chain_first<<<g1, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+        if (L.scene.n_lights > 0) k_chain_shadow0<<<dim3(g1, (unsigned)L.scene.n_lights), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+        k_chain_shade0<<<g1, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+        k_chain_rest<<<g2, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    } else if (L.frame.p.wavefront == 3) k_chain_warp<<<148 * VKP_LB_CHAIN, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
     else {
         // every queued path gets its own thread in ONE pass (a second pass would double the critical path): the queue length is
         // only known on the device, so the grid covers a quarter of the rank's pixels and the threads beyond the queue leave at once
         const unsigned int px_blocks = frame_grid(L).x;
-        k_chain<<<px_blocks / 4u + 1u, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+        // VKP_CHAIN_CTAS=n (A/B knob): at most n chain CTAs per SM, enforced with a dynamic shared-memory reservation nobody uses, so
+        // that the high-priority chain cannot take every register of an SM away from k_shadow
+        static int ctas = -1;
+        static size_t dyn = 0;
+        if (ctas < 0) {
+            const char* e = getenv("VKP_CHAIN_CTAS");
+            ctas = e ? atoi(e) : 0;
+            if (ctas > 0) {
+                dyn = (size_t)(220 * 1024) / (size_t)ctas - (size_t)(VKP_TRAV_SMEM_WORDS * 4) - 1024;
+                cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            }
+        }
+        k_chain<<<px_blocks / 4u + 1u, VKP_TRAV_BLOCK, dyn, stream>>>(L.scene, L.frame);
     }
     return cudaGetLastError();
 }

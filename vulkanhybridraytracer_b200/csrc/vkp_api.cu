@@ -7,9 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <memory>
 
-static_assert(sizeof(vkp_build_stats) == 72, "vkp_build_stats layout (types.py BuildStats)");
+static_assert(sizeof(vkp_build_stats) == 80, "vkp_build_stats layout (types.py BuildStats)");
 
 namespace {
 
@@ -64,9 +65,10 @@ struct vkp_ctx {
     DevBuf position, normal, albedo, motion, material, emissive, hit_ids, final_f32, final_srgb8, shadow, denoised[2];
     int denoised_cur = 0;
     int plane_w = 0, plane_h = 0, plane_lights = 0;
+    DevBuf atrous[2];                 // ping-pong planes of the a-trous shadow filter (vkp_params.denoiser = 1)
     DevBuf counters, io_tmp, io_tmp2, flush, path_q[2], path_count, luts, chain_buf, chain_len, chain_slot, chain_pix;
     cudaStream_t chain_stream = nullptr;
-    cudaEvent_t ev_gbuffer = nullptr, ev_chain = nullptr;
+    cudaEvent_t ev_gbuffer = nullptr, ev_chain = nullptr, ev_scan = nullptr;
     // longest-first CTA schedule of k_gbuffer [0] and k_shadow [1], rebuilt every frame from the previous frame's per-block cycles
     DevBuf cta_cost[2], cta_order[2];
     uint32_t order_n[2] = {0u, 0u};
@@ -107,6 +109,9 @@ struct vkp_ctx {
     int build_launches = 0;
     // acceleration-structure figures (vkp_get_build_stats)
     vkp_build_stats bstats{};
+    BvhBuildResult* build_results = nullptr;    // pinned: one record per BLAS of the batch being built
+    uint32_t build_results_cap = 0;
+    uint32_t bstats_rebuilt = 0;                // BLAS whose queued PLOC rounds did not suffice (rebuilt with waits)
     cudaEvent_t ev_build0 = nullptr, ev_build1 = nullptr, ev_refit0 = nullptr, ev_refit1 = nullptr;
     bool refit_timed = false;
     // every BLAS's nodes + leaf triangles, compacted into ONE allocation after the builds: the L2 persistence window covers it
@@ -421,7 +426,7 @@ int apply_l2_window(vkp_ctx* ctx)
 }
 
 // nodes + leaf triangles of every BLAS into one allocation (256-byte aligned pieces); the build's own arrays are released
-int compact_blas_arena(vkp_ctx* ctx)
+int compact_blas_arena(vkp_ctx* ctx, float* copy_ms = nullptr)
 {
     auto al = [](size_t n) { return (n + 255u) & ~(size_t)255u; };
     size_t total = 0;
@@ -429,15 +434,24 @@ int compact_blas_arena(vkp_ctx* ctx)
     DevBuf arena;
     CK(arena.ensure(total ? total : 256));
     size_t off = 0;
+    std::vector<void*> placed;
+    cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;
+    if (copy_ms) { CK(cudaEventCreate(&ev_c0)); CK(cudaEventCreate(&ev_c1)); CK(cudaEventRecord(ev_c0, ctx->stream)); }
     for (auto& b : ctx->blas) {
         const size_t nb = sizeof(vkp_bvh_node) * (size_t)b->bvh.n_nodes, tb = sizeof(float4) * 3 * (size_t)(b->bvh.n_prims ? b->bvh.n_prims : 1);
         char* base = static_cast<char*>(arena.p);
         CK(cudaMemcpyAsync(base + off, b->bvh.nodes.p, nb, cudaMemcpyDeviceToDevice, ctx->stream));
-        void* np = base + off; off += al(nb);
+        placed.push_back(base + off); off += al(nb);
         CK(cudaMemcpyAsync(base + off, b->bvh.tris.p, tb, cudaMemcpyDeviceToDevice, ctx->stream));
-        void* tp = base + off; off += al(tb);
-        CK(cudaStreamSynchronize(ctx->stream));       // the sources are freed (or are views of the old arena, freed below)
-        b->bvh.nodes.view(np, nb); b->bvh.tris.view(tp, tb);
+        placed.push_back(base + off); off += al(tb);
+    }
+    if (copy_ms) CK(cudaEventRecord(ev_c1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));           // one wait for all copies: the sources are freed (or are views of the old arena, freed below)
+    if (copy_ms) { CK(cudaEventElapsedTime(copy_ms, ev_c0, ev_c1)); cudaEventDestroy(ev_c0); cudaEventDestroy(ev_c1); }
+    for (size_t k = 0; k < ctx->blas.size(); k++) {
+        Bvh& v = ctx->blas[k]->bvh;
+        v.nodes.view(placed[2 * k], sizeof(vkp_bvh_node) * (size_t)v.n_nodes);
+        v.tris.view(placed[2 * k + 1], sizeof(float4) * 3 * (size_t)(v.n_prims ? v.n_prims : 1));
     }
     ctx->bvh_arena.release();
     ctx->bvh_arena = arena;
@@ -454,6 +468,9 @@ int stage_event(vkp_ctx* ctx, int stage)
     ctx->n_ev++;
     return VKP_OK;
 }
+
+// kernels launch_chain() queues: counter clear + k_chain_scan + k_chain, or the four kernels of the staged chain (mode 4)
+uint32_t chain_launches(const FrameLaunch& L) { return L.frame.p.wavefront == 4 ? (L.scene.n_lights > 0 ? 6u : 5u) : 3u; }
 
 int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
 {
@@ -479,6 +496,14 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
         break;
     }
     case VKP_STAGE_DENOISE:
+        if (L.frame.p.denoiser == 1) {
+            // the a-trous taps reach 8 pixels across tile borders: one GPU only (a tile-sharded frame would need a halo exchange every frame)
+            if (L.frame.world > 1) return fail(ctx, VKP_ERR_INVALID, "vkp_params.denoiser = 1 (a-trous) is not available on a tile-sharded frame (world > 1)");
+            const size_t bytes = (size_t)ctx->plane_w * ctx->plane_h * ctx->plane_lights;
+            CK(ctx->atrous[0].ensure(bytes)); CK(ctx->atrous[1].ensure(bytes));
+            CK(launch_denoise(L, ctx->atrous[0].as<uint8_t>(), ctx->atrous[1].as<uint8_t>()));
+            ctx->last_launches += 3;
+        } else
         CK(launch_denoise(L));
         ctx->denoised_cur ^= 1;
         L.frame.denoised = ctx->denoised[ctx->denoised_cur].as<uint8_t>();
@@ -487,9 +512,16 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
     case VKP_STAGE_RESOLVE: {
         int n = 0;
         const bool chain2 = L.frame.p.wavefront >= 2 && L.frame.p.max_bounces <= VKP_CHAIN_MAX;
-        if (chain2 && !ctx->chain_in_flight) { CK(launch_chain(L, ctx->stream)); ctx->last_launches += 3; }      // stand-alone stage: serial (clear + scan + chain)
-        if (chain2 && ctx->chain_in_flight) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0)); ctx->chain_in_flight = false; }
+        const bool late = chain2 && L.frame.p.wavefront == 5;      // the resolve does not wait for the chain: k_resolve_paths merges it afterwards
+        if (chain2 && !ctx->chain_in_flight) { CK(launch_chain(L, ctx->stream)); ctx->last_launches += chain_launches(L); }      // stand-alone stage: serial (clear + scan + chain)
+        if (chain2 && ctx->chain_in_flight && !late) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0)); ctx->chain_in_flight = false; }
+        if (late && ctx->chain_in_flight) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_scan, 0));
         CK(launch_resolve(L, &n));
+        if (late) {
+            if (ctx->chain_in_flight) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0)); ctx->chain_in_flight = false; }
+            CK(launch_resolve_paths(L));
+            n++;
+        }
         if (L.frame.fused) {
             ctx->denoised_cur ^= 1;             // the fused filter wrote the other ping-pong buffer
             L.frame.denoised = ctx->denoised[ctx->denoised_cur].as<uint8_t>();
@@ -534,17 +566,28 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
     if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
     ctx = new vkp_ctx();
     ctx->device = device_ordinal;
-    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+    {
+        // VKP_CHAIN_PRIO=low: the frame's own stream takes the greatest priority and the chain stream the least (see below)
+        const char* cp = getenv("VKP_CHAIN_PRIO");
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = (cp && strcmp(cp, "low") == 0) ? cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, hi) : cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+    }
     ctx->stream = ctx->own_stream;
     {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);               // hi = greatest priority (numerically lowest)
-        cudaStreamCreateWithPriority(&ctx->chain_stream, cudaStreamNonBlocking, hi);
+        // the reflection chain's stream: greatest priority by default (its CTAs start the moment slots free up);
+        // VKP_CHAIN_PRIO=low lets it fill only what the main stream leaves idle (A/B knob)
+        const char* cp = getenv("VKP_CHAIN_PRIO");
+        cudaStreamCreateWithPriority(&ctx->chain_stream, cudaStreamNonBlocking, (cp && strcmp(cp, "low") == 0) ? lo : hi);
         cudaStreamCreateWithPriority(&ctx->order_stream, cudaStreamNonBlocking, hi);
         for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags(&ctx->ev_stage_done[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_order_done[k], cudaEventDisableTiming); }
         if (const char* e = getenv("VKP_SCHEDULE")) ctx->schedule = atoi(e) != 0;
         cudaEventCreateWithFlags(&ctx->ev_gbuffer, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_scan, cudaEventDisableTiming);
     }
     if (const char* b = getenv("VKP_BLAS_BUILDER")) ctx->builder = (strcmp(b, "lbvh") == 0) ? 0 : 1;
     if (const char* l = getenv("VKP_L2_PERSIST")) ctx->l2_persist = atoi(l) != 0;
@@ -573,6 +616,7 @@ void vkp_destroy(vkp_ctx* ctx)
     for (auto& t : ctx->textures) t->texels.release();
     for (auto& b : ctx->blas) b->bvh.release();
     ctx->tlas.release(); ctx->scratch.release(); ctx->tlas_scratch.release();
+    ctx->atrous[0].release(); ctx->atrous[1].release();
     if (ctx->l2_set_aside) cudaCtxResetPersistingL2Cache();
     ctx->bvh_arena.release();
     for (cudaEvent_t ev : {ctx->ev_build0, ctx->ev_build1, ctx->ev_refit0, ctx->ev_refit1}) if (ev) cudaEventDestroy(ev);
@@ -601,8 +645,10 @@ void vkp_destroy(vkp_ctx* ctx)
     for (auto& ev : ctx->ev_copy_done) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_copy_ring) if (ev) cudaEventDestroy(ev);
     for (auto& sl : ctx->stage_ring) { if (sl.host) cudaFreeHost(sl.host); if (sl.done) cudaEventDestroy(sl.done); }
+    if (ctx->build_results) cudaFreeHost(ctx->build_results);
     if (ctx->ev_gbuffer) cudaEventDestroy(ctx->ev_gbuffer);
     if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
+    if (ctx->ev_scan) cudaEventDestroy(ctx->ev_scan);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -702,42 +748,88 @@ int vkp_build_blas(vkp_ctx* ctx)
 {
     if (!ctx) return VKP_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    const auto wall0 = std::chrono::steady_clock::now();
     ctx->build_launches = 0;
     if (!ctx->ev_build0) { CK(cudaEventCreate(&ctx->ev_build0)); CK(cudaEventCreate(&ctx->ev_build1)); }
-    CK(cudaEventRecord(ctx->ev_build0, ctx->stream));
-    int host_syncs = 0; uint32_t built = 0; uint64_t built_tris = 0;
+    // the geometries that have no BLAS yet (Renderer::create_bottom_acceleration_structure builds one per Node geometry, renderer.cpp:1696-1753)
+    std::vector<std::unique_ptr<BlasRec>> fresh;
+    uint32_t n_max = 0;
     for (const vkp_instance& I : ctx->instances) {
         bool found = false;
         for (auto& b : ctx->blas) if (b->mesh == I.mesh_id && b->first == I.first_index && b->count == I.index_count) { found = true; break; }
+        for (auto& b : fresh) if (b->mesh == I.mesh_id && b->first == I.first_index && b->count == I.index_count) { found = true; break; }
         if (found) continue;
         std::unique_ptr<BlasRec> b(new BlasRec());
         b->mesh = I.mesh_id; b->first = I.first_index; b->count = I.index_count;
-        const MeshRec& m = *ctx->meshes[I.mesh_id];
-        const uint32_t ntri = I.index_count / 3u;
-        CK(ctx->scratch.boxes.ensure(sizeof(float) * 6 * (size_t)(ntri ? ntri : 1)));
-        const uint32_t* idx = m.idx.as<uint32_t>() + I.first_index;
-        CK(bvh_triangle_boxes(ctx->stream, m.verts.as<vkp_vertex>(), idx, ntri, ctx->scratch.boxes.as<float>()));
-        CK(bvh_build(ctx->stream, ctx->scratch, ntri, 4, b->bvh, &ctx->build_launches, ctx->builder, &host_syncs));
-        CK(bvh_emit_triangles(ctx->stream, m.verts.as<vkp_vertex>(), idx, b->bvh));
-        ctx->build_launches += 2;      // k_triangle_boxes, k_emit_triangles
-        built++; built_tris += ntri;
-        if (b->bvh.height + 16 > VKP_TRAV_STACK) {     // one push per level + the TLAS part (checked exactly in vkp_build_tlas)
-            char msg[160]; snprintf(msg, sizeof msg, "BLAS height %d exceeds the traversal stack budget", b->bvh.height);
-            return fail(ctx, VKP_ERR_INVALID, msg);
+        n_max = I.index_count / 3u > n_max ? I.index_count / 3u : n_max;
+        fresh.push_back(std::move(b));
+    }
+    int host_syncs = 0; const uint32_t built = (uint32_t)fresh.size(); uint64_t built_tris = 0;
+    ctx->bstats_rebuilt = 0;
+    if (built) {
+        // Every build of the batch is queued before anything is waited for: scratch sized once for the largest geometry (no
+        // cudaFree between builds), PLOC rounds driven from device memory, one pinned result record per BLAS, ONE synchronisation.
+        CK(bvh_reserve(ctx->scratch, n_max, ctx->builder, true));
+        if (ctx->build_results_cap < built) {
+            if (ctx->build_results) cudaFreeHost(ctx->build_results);
+            ctx->build_results = nullptr; ctx->build_results_cap = 0;
+            CK(cudaMallocHost(&ctx->build_results, sizeof(BvhBuildResult) * built));
+            ctx->build_results_cap = built;
         }
-        ctx->blas.push_back(std::move(b));
-    }
-    if (built) {
-        int r = compact_blas_arena(ctx);      // one allocation for every BLAS + the L2 persistence window over it
+        memset(ctx->build_results, 0, sizeof(BvhBuildResult) * built);
+        // the per-BLAS outputs are allocated up front as well (upper bounds: 2n - 1 nodes): no cudaMalloc between the queued builds
+        for (uint32_t k = 0; k < built; k++) {
+            Bvh& v = fresh[k]->bvh;
+            const size_t ntri = fresh[k]->count / 3u, ni = ntri > 1 ? ntri - 1 : 0;
+            CK(v.nodes.ensure(sizeof(vkp_bvh_node) * (2 * ni + 1))); CK(v.items.ensure(sizeof(uint32_t) * (ntri ? ntri : 1)));
+            CK(v.tris.ensure(sizeof(float4) * 3 * (ntri ? ntri : 1)));
+        }
+        CK(cudaEventRecord(ctx->ev_build0, ctx->stream));
+        for (uint32_t k = 0; k < built; k++) {
+            BlasRec& b = *fresh[k];
+            const MeshRec& m = *ctx->meshes[b.mesh];
+            const uint32_t ntri = b.count / 3u;
+            const uint32_t* idx = m.idx.as<uint32_t>() + b.first;
+            CK(bvh_triangle_boxes(ctx->stream, m.verts.as<vkp_vertex>(), idx, ntri, ctx->scratch.boxes.as<float>()));
+            CK(bvh_build(ctx->stream, ctx->scratch, ntri, 4, b.bvh, &ctx->build_launches, ctx->builder, &host_syncs, ctx->build_results + k, true));
+            CK(bvh_emit_triangles(ctx->stream, m.verts.as<vkp_vertex>(), idx, b.bvh));
+            ctx->build_launches += 2;      // k_triangle_boxes, k_emit_triangles
+            built_tris += ntri;
+        }
+        CK(cudaEventRecord(ctx->ev_build1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream)); host_syncs++;
+        for (uint32_t k = 0; k < built; k++) {
+            BlasRec& b = *fresh[k];
+            if (!bvh_build_finish(b.bvh, ctx->build_results[k])) {
+                // the queued PLOC rounds did not finish this hierarchy (never seen on triangle meshes): build it again, waiting per batch of rounds
+                const MeshRec& m = *ctx->meshes[b.mesh];
+                const uint32_t ntri = b.count / 3u;
+                const uint32_t* idx = m.idx.as<uint32_t>() + b.first;
+                CK(bvh_triangle_boxes(ctx->stream, m.verts.as<vkp_vertex>(), idx, ntri, ctx->scratch.boxes.as<float>()));
+                CK(bvh_build(ctx->stream, ctx->scratch, ntri, 4, b.bvh, &ctx->build_launches, ctx->builder, &host_syncs, nullptr, true));
+                CK(bvh_emit_triangles(ctx->stream, m.verts.as<vkp_vertex>(), idx, b.bvh));
+                ctx->bstats_rebuilt++;
+            }
+            // the topology arrays were views of the scratch: a BLAS is never refitted
+            b.bvh.child.release(); b.bvh.range.release(); b.bvh.parent.release(); b.bvh.ibox.release(); b.bvh.flags.release(); b.bvh.rank.release(); b.bvh.keep.release();
+            if (b.bvh.height + 16 > VKP_TRAV_STACK) {     // one push per level + the TLAS part (checked exactly in vkp_build_tlas)
+                char msg[160]; snprintf(msg, sizeof msg, "BLAS height %d exceeds the traversal stack budget", b.bvh.height);
+                return fail(ctx, VKP_ERR_INVALID, msg);
+            }
+        }
+        for (auto& b : fresh) ctx->blas.push_back(std::move(b));
+        float ms_build = 0.0f, ms_compact = 0.0f;
+        int r = compact_blas_arena(ctx, &ms_compact);      // one allocation for every BLAS + the L2 persistence window over it
         if (r != VKP_OK) return r;
+        CK(cudaEventElapsedTime(&ms_build, ctx->ev_build0, ctx->ev_build1));
         ctx->tlas_built = false;              // the instance records name the old arrays: vkp_build_tlas has to follow
-    }
-    CK(cudaEventRecord(ctx->ev_build1, ctx->stream));
-    CK(cudaEventSynchronize(ctx->ev_build1));
-    if (built) {
-        CK(cudaEventElapsedTime(&ctx->bstats.blas_ms, ctx->ev_build0, ctx->ev_build1));
+        ctx->bstats.blas_ms = ms_build; ctx->bstats.blas_compact_ms = ms_compact;
+        ctx->bstats.blas_wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
         ctx->bstats.blas_built = built; ctx->bstats.blas_launches = (uint32_t)ctx->build_launches; ctx->bstats.blas_host_syncs = (uint32_t)host_syncs;
         ctx->bstats.blas_triangles = built_tris;
+        int rmax = 0;
+        for (auto& b : ctx->blas) rmax = b->bvh.ploc_rounds > rmax ? b->bvh.ploc_rounds : rmax;
+        ctx->bstats.blas_ploc_rounds_max = (uint16_t)rmax; ctx->bstats.blas_rebuilt = (uint16_t)ctx->bstats_rebuilt;
     }
     uint32_t hmax = 0;
     for (auto& b : ctx->blas) hmax = (uint32_t)b->bvh.height > hmax ? (uint32_t)b->bvh.height : hmax;
@@ -839,6 +931,8 @@ int vkp_set_params(vkp_ctx* ctx, const vkp_params* p)
     if (p->mode < 0 || p->mode > 2) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: bad mode");
     if (p->max_bounces > VKP_MAX_BOUNCES) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: max_bounces > 64");
     if (p->spp < 1 || p->shadow_samples < 1 || p->max_bounces < 0) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: spp / shadow_samples must be >= 1");
+    if (p->denoiser < 0 || p->denoiser > 1) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: denoiser is 0 (blur.comp) or 1 (a-trous)");
+    if (p->wavefront < 0 || p->wavefront > 5) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: wavefront (chain schedule) is 0 .. 5");
     ctx->params = *p; ctx->have_params = true;
     return VKP_OK;
 }
@@ -872,7 +966,7 @@ int vkp_render(vkp_ctx* ctx)
     static const int deferred[] = {VKP_STAGE_GBUFFER, VKP_STAGE_DEFERRED};
     const int* seq = hybrid; int n = 4;
     // the wavefront variant re-reads the resolve inputs per bounce; it keeps the stand-alone filter pass
-    const bool fused = ctx->params.mode == VKP_MODE_HYBRID && ctx->params.fuse_denoise != 0 && ctx->params.wavefront != 1;
+    const bool fused = ctx->params.mode == VKP_MODE_HYBRID && ctx->params.fuse_denoise != 0 && ctx->params.wavefront != 1 && ctx->params.denoiser == 0;
     if (fused) { seq = hybrid_fused; n = 3; L.frame.fused = 1; }
     if (ctx->params.mode == VKP_MODE_RAYTRACING) { seq = rt; n = 1; }
     else if (ctx->params.mode == VKP_MODE_DEFERRED) { seq = deferred; n = 2; }
@@ -883,10 +977,10 @@ int vkp_render(vkp_ctx* ctx)
             // fork: the reflection chain needs only the G-buffer; it overlaps the shadow + denoise passes on its own stream
             CK(cudaEventRecord(ctx->ev_gbuffer, ctx->stream));
             CK(cudaStreamWaitEvent(ctx->chain_stream, ctx->ev_gbuffer, 0));
-            CK(launch_chain(L, ctx->chain_stream));
+            CK(launch_chain(L, ctx->chain_stream, ctx->ev_scan));
             CK(cudaEventRecord(ctx->ev_chain, ctx->chain_stream));
             ctx->chain_in_flight = true;
-            ctx->last_launches += 3;      // counter clear + k_chain_scan + k_chain
+            ctx->last_launches += chain_launches(L);
         }
     }
     if ((r = mark_scene_use(ctx)) != VKP_OK) return r;
@@ -1323,3 +1417,15 @@ int vkp_tiles_unpack(vkp_ctx* ctx, int plane, int rank, int world, const void* d
 }
 
 } // extern "C"
+
+// ---- internal accessors for vkp_group.cu ---------------------------------------------------------------------------------------
+cudaStream_t vkp_internal_stream(vkp_ctx* ctx) { return ctx->stream; }
+// the queued present copy (vkp_readback_async) still reading sRGB8 output buffer `buf`, or NULL
+cudaEvent_t vkp_internal_pending_copy(vkp_ctx* ctx, int buf) { return (buf >= 0 && buf < 2 && ctx->copy_pending[buf]) ? ctx->ev_copy_done[buf] : nullptr; }
+int vkp_internal_output_buffers(vkp_ctx* ctx, void** b0, void** b1)
+{
+    int r = ensure_planes(ctx);
+    if (r != VKP_OK) return r;
+    *b0 = ctx->final_srgb8.p; *b1 = ctx->final_srgb8_alt.p;
+    return VKP_OK;
+}

@@ -31,6 +31,8 @@ struct Bvh {
     uint32_t n_nodes = 0;
     int leaf_max = 4;
     int height = 0;
+    int ploc_rounds = 0;
+    const void* gate = nullptr;   // device PlocState the consumers of a freshly built PLOC hierarchy check (NULL: nothing to check)
     int root = 0;        // index of the root among the internal nodes (0 for the Karras tree)
     uint32_t root_ref = 0x80000000u;   // nodes[0].ref of the binary layout
     DevBuf nodes;        // vkp_bvh_node[n_nodes]
@@ -54,20 +56,28 @@ struct Bvh {
 struct BuildScratch {
     DevBuf boxes;       // float[6*n] primitive boxes
     DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, bounds, misc;
-    DevBuf ploc_cid[2], ploc_box[2], ploc_cnt[2], ploc_nn, ploc_flags, ploc_scan, ploc_icnt, ploc_parent;
+    DevBuf ploc_cid[2], ploc_box[2], ploc_cnt[2], ploc_nn, ploc_scan, ploc_icnt, ploc_parent, ploc_state, ploc_tiles;
+    DevBuf t_child, t_range, t_parent, t_ibox, t_flags, t_rank, t_keep;     // topology arrays of a build whose Bvh does not keep them (BLAS)
+    void* result_host = nullptr;                                             // pinned BvhBuildResult of the synchronous path
     void release()
     {
         DevBuf* all[] = {&boxes, &keys, &keys_alt, &vals, &vals_alt, &cub_tmp, &bounds, &misc, &ploc_cid[0], &ploc_cid[1], &ploc_box[0], &ploc_box[1],
-                         &ploc_cnt[0], &ploc_cnt[1], &ploc_nn, &ploc_flags, &ploc_scan, &ploc_icnt, &ploc_parent};
+                         &ploc_cnt[0], &ploc_cnt[1], &ploc_nn, &ploc_scan, &ploc_icnt, &ploc_parent, &ploc_state, &ploc_tiles,
+                         &t_child, &t_range, &t_parent, &t_ibox, &t_flags, &t_rank, &t_keep};
         for (DevBuf* b : all) b->release();
+        if (result_host) { cudaFreeHost(result_host); result_host = nullptr; }
     }
 };
 
 // bvh_build.cu
 cudaError_t bvh_triangle_boxes(cudaStream_t s, const vkp_vertex* verts, const uint32_t* indices, uint32_t n_tris, float* boxes);
 cudaError_t bvh_instance_boxes(cudaStream_t s, const DInstance* inst, uint32_t n, float* boxes);
+// what the host learns from a finished build (written by its last kernel into pinned host memory)
+struct BvhBuildResult { uint32_t n_nodes, root_ref; int height, ploc_left, ploc_rounds, valid; uint32_t _pad[2]; };
+cudaError_t bvh_reserve(BuildScratch& scratch, uint32_t n_prims, int builder, bool temps);
 cudaError_t bvh_build(cudaStream_t s, BuildScratch& scratch, uint32_t n_prims, int leaf_max, Bvh& out, int* launches, int builder /*0 LBVH (Karras), 1 PLOC*/,
-                      int* host_syncs = nullptr);
+                      int* host_syncs = nullptr, BvhBuildResult* async_result = nullptr, bool temps_in_scratch = false);
+bool bvh_build_finish(Bvh& B, const BvhBuildResult& r);
 cudaError_t bvh_refit(cudaStream_t s, BuildScratch& scratch, Bvh& bvh, int* launches);
 cudaError_t bvh_selftest_sort(cudaStream_t s, const uint32_t* keys_host, uint32_t n, int end_bit, uint32_t* keys_sorted_host, uint32_t* vals_sorted_host,
                               unsigned long long* scan_host);
@@ -83,10 +93,11 @@ struct FrameLaunch {
 };
 cudaError_t launch_gbuffer(const FrameLaunch& L);
 cudaError_t launch_shadow(const FrameLaunch& L);
-cudaError_t launch_denoise(const FrameLaunch& L);
+cudaError_t launch_denoise(const FrameLaunch& L, uint8_t* atrous_a = nullptr, uint8_t* atrous_b = nullptr);
 cudaError_t launch_build_order(cudaStream_t s, uint32_t* cost, uint32_t* order, uint32_t n);
 cudaError_t launch_resolve(const FrameLaunch& L, int* launches);
-cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream);
+cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t after_scan = nullptr);
+cudaError_t launch_resolve_paths(const FrameLaunch& L);
 cudaError_t launch_post(const FrameLaunch& L);
 cudaError_t launch_raytrace(const FrameLaunch& L);
 cudaError_t launch_deferred(const FrameLaunch& L);
@@ -102,3 +113,9 @@ cudaError_t launch_sync_wait(cudaStream_t s, const uint32_t* flags, int count /*
 #define VKP_STAGE_INLINE_MAX 15360u     /* four launches of 3840 bytes */
 cudaError_t launch_stage_inline(cudaStream_t s, void* dst, const void* src, size_t bytes);     // bytes % 4 == 0, <= VKP_STAGE_INLINE_MAX
 cudaError_t launch_stage_words(cudaStream_t s, void* dst, const void* src_or_null, size_t bytes);     // bytes % 4 == 0; src NULL = clear
+
+// vkp_api.cu, for vkp_group.cu
+struct vkp_ctx;
+cudaStream_t vkp_internal_stream(vkp_ctx* ctx);
+cudaEvent_t vkp_internal_pending_copy(vkp_ctx* ctx, int buf);
+int vkp_internal_output_buffers(vkp_ctx* ctx, void** buffer0, void** buffer1);

@@ -26,15 +26,20 @@ extern "C" {
 #define VKPH_API __attribute__((visibility("default")))
 
 // ---- engine --------------------------------------------------------------------------------------------------
-VKPH_API void* vkph_engine_create(int scene_index, int width, int height, int device, const int* detail4)
+// gpus > 1: GPUs device .. device + gpus - 1 render every frame together (VulkanEngine::_gpus, one process, vkp_group)
+VKPH_API void* vkph_engine_create_multi(int scene_index, int width, int height, int device, int gpus, const int* detail4)
 {
     VulkanEngine* e = new VulkanEngine();
     try {
         e->_detail = detail_of(detail4);
-        e->_sceneIndex = scene_index; e->_width = width; e->_height = height; e->_device = device;
+        e->_sceneIndex = scene_index; e->_width = width; e->_height = height; e->_device = device; e->_gpus = gpus < 1 ? 1 : gpus;
         e->init();
         return e;
     } catch (const std::exception& ex) { g_err = ex.what(); delete e; return nullptr; }
+}
+VKPH_API void* vkph_engine_create(int scene_index, int width, int height, int device, const int* detail4)
+{
+    return vkph_engine_create_multi(scene_index, width, height, device, 1, detail4);
 }
 
 VKPH_API int vkph_engine_set(void* p, const char* key, int value)

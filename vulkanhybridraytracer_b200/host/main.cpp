@@ -1,6 +1,6 @@
 // main.cpp -- headless replacement of src/main.cpp + window.cpp: VulkanEngine engine; init(); run(); cleanup();
 //   vkpinut [--scene N] [--mode deferred|raytracing|hybrid] [--width W --height H] [--frames F] [--samples S]
-//           [--spp N] [--device D] [--png out.png] [--exr out.exr] [--prefab model.obj|.gltf|.glb]
+//           [--spp N] [--device D] [--gpus N] [--png out.png] [--exr out.exr] [--prefab model.obj|.gltf|.glb]
 //           [--walk DIR:DT[,DIR:DT...]] [--turn DX:DY] [--sequence prefix] [--reproject-fix] [--detail a,b,c,d]
 // --walk / --turn replay key presses and mouse motion every frame (DIR = forward|backward|left|right|up|down, DT in ms as in
 // Camera::processKeyboard; DX, DY in pixels as in Camera::rotate): a moving-camera sequence.  --sequence writes prefix_%04d.png per frame.
@@ -33,6 +33,7 @@ int main(int argc, char** argv)
         else if (a == "--samples") engine._samples = std::atoi(next());
         else if (a == "--spp") engine._spp = std::atoi(next());
         else if (a == "--device") engine._device = std::atoi(next());
+        else if (a == "--gpus") engine._gpus = std::atoi(next());          // GPUs device .. device + N - 1 share every frame (tile-sharded)
         else if (a == "--prefab") engine._prefabFile = next();
         else if (a == "--detail") {      // tessellation of the procedural stand-ins: lucy,helmet,stress,instances (default 7,5,7,31)
             MeshDetail& d = engine._detail;

@@ -4,14 +4,18 @@
 #include "vkpinut.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
 #define VKP_CHECK(x)                                                                                              \
     do {                                                                                                          \
         int _e = (x);                                                                                             \
-        if (_e != VKP_OK) throw std::runtime_error(std::string(#x) + ": " + vkp_last_error(_ctx));                \
+        if (_e != VKP_OK) throw std::runtime_error(std::string(#x) + ": " + (_group ? vkp_group_last_error(_group) : vkp_last_error(_ctx))); \
     } while (0)
+// one GPU: the context call; several: the group call of the same name (every member)
+#define VKP_ALL(name, ...) VKP_CHECK(_group ? vkp_group_##name(_group, __VA_ARGS__) : vkp_##name(_ctx, __VA_ARGS__))
+#define VKP_ALL0(name) VKP_CHECK(_group ? vkp_group_##name(_group) : vkp_##name(_ctx))
 
 // ---- Mesh::upload (vk_mesh.cpp upload_to_gpu: vertex + index buffers) -------------------------------------------
 void Mesh::upload(vkp_ctx* ctx)
@@ -30,13 +34,24 @@ Renderer::Renderer(Scene* scene) : _scene(scene)
     VulkanEngine* e = VulkanEngine::engine;
     _width = e ? e->_width : 1700; _height = e ? e->_height : 900;
     int dev = e ? e->_device : 0;
-    if (vkp_create(&_ctx, dev) != VKP_OK) throw std::runtime_error(std::string("vkp_create: ") + vkp_last_error(nullptr));
+    const int gpus = e ? e->_gpus : 1;
+    if (gpus > 1) {
+        std::vector<int> devs;
+        const bool same = std::getenv("VKP_GROUP_SAME_DEVICE") != nullptr;     // tests on a one-GPU box: every rank on `dev`
+        for (int k = 0; k < gpus; k++) devs.push_back(same ? dev : dev + k);
+        if (vkp_group_create(&_group, devs.data(), gpus, 32, 16) != VKP_OK) throw std::runtime_error(std::string("vkp_group_create: ") + vkp_last_error(nullptr));
+        _ctx = vkp_group_member(_group, 0);
+    } else if (vkp_create(&_ctx, dev) != VKP_OK) throw std::runtime_error(std::string("vkp_create: ") + vkp_last_error(nullptr));
     load_data_to_gpu();
     create_bottom_acceleration_structure();
     create_top_acceleration_structure();
 }
 
-Renderer::~Renderer() { if (_ctx) vkp_destroy(_ctx); }
+Renderer::~Renderer()
+{
+    if (_group) vkp_group_destroy(_group);
+    else if (_ctx) vkp_destroy(_ctx);
+}
 
 // renderer.cpp:1477-1530 (lights, materials, matrices) + create_hybrid_descriptors (:2917-3129: vertex /
 // index / id / texture / environment bindings)
@@ -45,18 +60,24 @@ void Renderer::load_data_to_gpu()
     SceneBuffers B = build_scene_buffers(_scene);
     for (Mesh* m : B.meshes) m->_deviceMeshId = -1;
     for (size_t i = 0; i < B.meshes.size(); i++) {
-        B.meshes[i]->upload(_ctx);
+        if (_group) {
+            Mesh* m = B.meshes[i];
+            int id = -1;
+            VKP_CHECK(vkp_group_upload_mesh(_group, reinterpret_cast<const vkp_vertex*>(m->_vertices.data()), (uint32_t)m->_vertices.size(), m->_indices.data(),
+                                            (uint32_t)m->_indices.size(), &id));
+            m->_deviceMeshId = id;
+        } else B.meshes[i]->upload(_ctx);
         if (B.meshes[i]->_deviceMeshId != (int)i) throw std::runtime_error("mesh upload order");
     }
     for (Texture* t : B.textures) {
         int id = -1;
-        VKP_CHECK(vkp_upload_texture_rgba8(_ctx, t->_rgba.data(), t->_width, t->_height, &id));
+        VKP_ALL(upload_texture_rgba8, t->_rgba.data(), t->_width, t->_height, &id);
     }
-    VKP_CHECK(vkp_set_env(_ctx, B.sky_tex, B.irradiance_tex));
-    VKP_CHECK(vkp_set_materials(_ctx, B.materials.data(), (int)B.materials.size()));
-    VKP_CHECK(vkp_set_lights(_ctx, B.lights.data(), (int)B.lights.size()));
+    VKP_ALL(set_env, B.sky_tex, B.irradiance_tex);
+    VKP_ALL(set_materials, B.materials.data(), (int)B.materials.size());
+    VKP_ALL(set_lights, B.lights.data(), (int)B.lights.size());
     _instances = B.instances;
-    VKP_CHECK(vkp_set_instances(_ctx, _instances.data(), (int)_instances.size()));
+    VKP_ALL(set_instances, _instances.data(), (int)_instances.size());
     _tlas.clear();
     for (size_t i = 0; i < _instances.size(); i++) {
         TlasInstance t; t.blasId = t.instanceId = (uint32_t)i;
@@ -65,8 +86,9 @@ void Renderer::load_data_to_gpu()
     }
 }
 
-void Renderer::create_bottom_acceleration_structure() { VKP_CHECK(vkp_build_blas(_ctx)); }
-void Renderer::create_top_acceleration_structure() { VKP_CHECK(vkp_build_tlas(_ctx, 0)); }
+void Renderer::create_bottom_acceleration_structure() { VKP_ALL0(build_blas); }
+void Renderer::create_top_acceleration_structure() { VKP_ALL(build_tlas, 0); }
+void Renderer::set_lights(const std::vector<vkp_light>& lights) { VKP_ALL(set_lights, lights.data(), (int)lights.size()); }
 
 // Renderer::buildTlas(input, flags, update) (renderer.cpp:1757-1865)
 void Renderer::buildTlas(const std::vector<TlasInstance>& input, bool update)
@@ -82,15 +104,15 @@ void Renderer::buildTlas(const std::vector<TlasInstance>& input, bool update)
         }
     }
     // the reference refits every frame whether or not anything moved (vk_engine.cpp:172-187): so do we
-    if (changed || !update) VKP_CHECK(vkp_set_instances(_ctx, _instances.data(), (int)_instances.size()));
-    VKP_CHECK(vkp_build_tlas(_ctx, update ? 1 : 0));
+    if (changed || !update) VKP_ALL(set_instances, _instances.data(), (int)_instances.size());
+    VKP_ALL(build_tlas, update ? 1 : 0);
 }
 
 void Renderer::recreate_renderer()
 {
     VulkanEngine* e = VulkanEngine::engine;
     if (e) { _width = e->_width; _height = e->_height; }
-    VKP_CHECK(vkp_reset_history(_ctx));
+    VKP_ALL0(reset_history);
 }
 
 void Renderer::submit(renderMode mode)
@@ -98,8 +120,9 @@ void Renderer::submit(renderMode mode)
     VulkanEngine* e = VulkanEngine::engine;
     vkp_params p = e->current_params();
     p.mode = (int)mode;
-    VKP_CHECK(vkp_set_params(_ctx, &p));
-    VKP_CHECK(vkp_set_camera(_ctx, &e->_cameraData));
+    VKP_ALL(set_params, &p);
+    VKP_ALL(set_camera, &e->_cameraData);
+    if (_group) { VKP_CHECK(vkp_group_render(_group)); return; }       // the group alternates the output buffers itself
     VKP_CHECK(vkp_set_output_buffer(_ctx, _frameSlot));
     VKP_CHECK(vkp_render(_ctx));
 }
@@ -117,7 +140,11 @@ void Renderer::render() { submit(DEFERRED); }
 void Renderer::raytrace() { submit(RAYTRACING); }
 void Renderer::rasterize_hybrid() { submit(HYBRID); }
 
-void Renderer::read_into(int plane, void* dst, size_t bytes) { VKP_CHECK(vkp_readback(_ctx, plane, dst, bytes)); }
+void Renderer::read_into(int plane, void* dst, size_t bytes)
+{
+    if (_group) VKP_CHECK(vkp_group_readback(_group, plane, dst, bytes));
+    else VKP_CHECK(vkp_readback(_ctx, plane, dst, bytes));
+}
 
 std::vector<uint8_t> Renderer::read_final_srgb8()
 {
@@ -128,13 +155,15 @@ std::vector<uint8_t> Renderer::read_final_srgb8()
 std::vector<float> Renderer::read_final_linear()
 {
     std::vector<float> out((size_t)_width * _height * 4);
-    VKP_CHECK(vkp_readback(_ctx, VKP_PLANE_FINAL_F32, out.data(), out.size() * sizeof(float)));
+    if (_group) VKP_CHECK(vkp_group_readback(_group, VKP_PLANE_FINAL_F32, out.data(), out.size() * sizeof(float)));   // gathers the tiles first
+    else VKP_CHECK(vkp_readback(_ctx, VKP_PLANE_FINAL_F32, out.data(), out.size() * sizeof(float)));
     return out;
 }
 vkp_counters Renderer::counters()
 {
     vkp_counters c{};
-    VKP_CHECK(vkp_get_counters(_ctx, &c));
+    if (_group) VKP_CHECK(vkp_group_get_counters(_group, &c));
+    else VKP_CHECK(vkp_get_counters(_ctx, &c));
     return c;
 }
 
@@ -202,7 +231,7 @@ void VulkanEngine::update(const float)
     updateFrame();
     updateCameraMatrices();
     std::vector<vkp_light> lights = build_lights(_scene);
-    if (vkp_set_lights(renderer->_ctx, lights.data(), (int)lights.size()) != VKP_OK) throw std::runtime_error(vkp_last_error(renderer->_ctx));
+    renderer->set_lights(lights);
     int instanceIndex = 0;
     renderer->_tlas.clear();
     for (Object* obj : _scene->_entities)

@@ -243,7 +243,8 @@ public:
     ~Renderer();
 
     Scene* _scene;
-    vkp_ctx* _ctx{nullptr};
+    vkp_ctx* _ctx{nullptr};            // the device context; with several GPUs: rank 0 of the group (owner of the composited image)
+    vkp_group* _group{nullptr};        // VulkanEngine::_gpus > 1: one context per GPU, tiles dealt over them (include/vkp.h "multi-GPU group")
     std::vector<TlasInstance> _tlas;
     int _width, _height;
 
@@ -263,6 +264,7 @@ public:
     void present_wait(int keep_in_flight = 0);            // until at most keep_in_flight queued presents are outstanding
     int _frameSlot{0};                                    // _frameNumber % FRAME_OVERLAP (renderer.cpp:363)
     vkp_counters counters();
+    void set_lights(const std::vector<vkp_light>& lights);   // binding 4, every frame (vk_engine.cpp:146-164)
 
 private:
     void load_data_to_gpu();
@@ -291,6 +293,7 @@ public:
     MeshDetail _detail;                 // handed to the Scene in init()
     std::string _prefabFile;            // headless CLI --prefab: Scene::create_viewer_scene instead of create_scene(_sceneIndex)
     int _device{0};
+    int _gpus{1};                       // GPUs _device .. _device + _gpus - 1 render one frame together (tile-sharded, bit-identical image)
     int _spp{1};
     int _maxBounces{8};
     bool _faithfulRng{true};

@@ -50,14 +50,15 @@ class Counters(C.Structure):        # vkp_counters
 class BuildStats(C.Structure):      # vkp_build_stats
     _fields_ = [("blas_ms", C.c_float), ("tlas_ms", C.c_float), ("refit_ms", C.c_float), ("blas_built", C.c_uint32), ("blas_launches", C.c_uint32),
                 ("blas_host_syncs", C.c_uint32), ("blas_height_max", C.c_uint32), ("tlas_height", C.c_uint32), ("refit_launches", C.c_uint32),
-                ("blas_triangles", C.c_uint64), ("arena_bytes", C.c_uint64), ("l2_persist_bytes", C.c_uint64), ("l2_hit_ratio", C.c_float), ("_pad", C.c_uint32)]
+                ("blas_triangles", C.c_uint64), ("arena_bytes", C.c_uint64), ("l2_persist_bytes", C.c_uint64), ("l2_hit_ratio", C.c_float), ("blas_ploc_rounds_max", C.c_uint16), ("blas_rebuilt", C.c_uint16),
+                ("blas_wall_ms", C.c_float), ("blas_compact_ms", C.c_float)]
 
 
 class BvhNode(C.Structure):         # vkp_bvh_node, 32 B
     _fields_ = [("bmin", C.c_float * 3), ("ref", C.c_uint32), ("bmax", C.c_float * 3), ("aux", C.c_uint32)]
 
 
-SIZES = {Vertex: 44, Material: 48, Light: 48, Instance: 144, Camera: 400, Params: 64, Ray: 32, Hit: 20, BvhNode: 32, BuildStats: 72}
+SIZES = {Vertex: 44, Material: 48, Light: 48, Instance: 144, Camera: 400, Params: 64, Ray: 32, Hit: 20, BvhNode: 32, BuildStats: 80}
 
 vertex_dtype = np.dtype([("position", "<f4", 3), ("normal", "<f4", 3), ("color", "<f4", 3), ("uv", "<f4", 2)])
 material_dtype = np.dtype([("diffuse", "<f4", 4), ("textures", "<f4", 4), ("shadingMetallicRoughness", "<f4", 4)])
