@@ -257,8 +257,9 @@ def main():
     ap.add_argument("--no-peer", action="store_true", help="N > 1: composite with pack + NCCL gather + unpack instead of NVLink peer stores")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-identity check of the composite against a 1-GPU render")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the 2-step Raytraced 64 spp x 64 samples block (BASELINE configs[2])")
-    ap.add_argument("--chain", type=int, default=2, choices=[0, 1, 2, 3, 4, 5],
-                    help="reflection-chain schedule: 0 inline in k_resolve, 1 wavefront queues, 2 k_chain overlapped with the shadow pass (default)")
+    ap.add_argument("--chain", type=int, default=5, choices=[0, 1, 2, 3, 4, 5, 6],
+                    help="reflection-chain schedule: 0 inline in k_resolve, 1 wavefront queues, 2 k_chain overlapped with the shadow pass, 3 warp per path, 4 staged first bounce, 5 = 2 + the resolve does not wait for the chain (default)")
+    ap.add_argument("--fuse-denoise", action="store_true", help="run blur.comp inside the resolve kernel instead of as its own pass (A/B)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="wall seconds the parity / cpu_baseline oracle leg may take")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -331,7 +332,8 @@ def main():
 
     def params(frame, wl=None):
         _, w_, h_, mode_, spp_, samples_, faithful_, _ = WORKLOADS[wl or args.workload]
-        return vk.make_params(w_, h_, mode=mode_, spp=spp_, shadow_samples=samples_, faithful_rng=faithful_, frame=frame, wavefront=args.chain)
+        return vk.make_params(w_, h_, mode=mode_, spp=spp_, shadow_samples=samples_, faithful_rng=faithful_, frame=frame, wavefront=args.chain,
+                              fuse_denoise=1 if args.fuse_denoise else 0)
 
     from vulkanhybridraytracer_b200.multigpu import TiledRenderer
     tr = TiledRenderer(ctx, rank, world, L, tile=(TW, TH), backend="nccl", device=torch.device("cuda", dev), stream_ordered=world > 1)
@@ -619,7 +621,8 @@ def main():
     kbytes = {k: plane_bytes[k] + min(ray_count[k] * BR, bvh_bytes if ray_count[k] > 0 else 0.0) for k in plane_bytes}
     kreq = {k: plane_bytes[k] + ray_count[k] * BR for k in plane_bytes}
     ms = stage_ms / args.steps
-    dom = int(np.argmax(ms))
+    chain_stream_ms = float(ms[7])                       # the reflection chain on its own stream (start to end), beside the main stream's stages
+    dom = int(np.argmax(ms[:7]))
     dname = names[dom]
     achieved = kbytes.get(dname, 0.0) / (ms[dom] * 1e-3) / 1e9 if ms[dom] > 0 else 0.0
     frame_kernels = ("k_gbuffer", "k_shadow", "k_denoise", "k_resolve") if mode == 2 else ("k_raytrace",)
@@ -636,6 +639,7 @@ def main():
                                                           "the kernel alone is measured.kernel_us",
                 "kernel_share_of_step": float(ms[dom] / max(ms.sum(), 1e-9)),
                 "stage_ms_all": {names[i]: float(ms[i]) for i in range(7) if ms[i] > 0},
+                "chain_stream_ms": chain_stream_ms,
                 "frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_bytes * world / (ms_per_step * 1e-3) / 1e9,
                           "frac": frame_bytes * world / (ms_per_step * 1e-3) / 1e9 / (peak * world)},
                 "requested_model": {"note": "SURVEY 8d: planes + rays * B_ray(T), B_ray = %d B at T = %d -- a request volume served by L1 / L2, not an HBM figure" % (BR, T),
@@ -668,7 +672,7 @@ def main():
                                    "secondary_shadow": int(rays_all[3] // args.steps), "primary_not_counted": int(rays_all[0] // args.steps)},
                 "mrays_s_incl_primary": float(rays_all.sum()) / args.steps / (ms_per_step * 1e-3) / 1e6,
                 "nominal_2P_mrays_s": 2 * P / (ms_per_step * 1e-3) / 1e6,
-                "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise", 3: "k_chain_warp (one warp per queued path, cooperative traversal) on a second stream", 4: "staged chain on a second stream overlapping k_shadow + k_denoise: first bounce as a wavefront (k_chain_first, k_chain_shadow0, k_chain_shade0), continuing paths compacted (k_chain_rest)", 5: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges the chain into the mirror / glass pixels"}[args.chain],
+                "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise", 3: "k_chain_warp (one warp per queued path, cooperative traversal) on a second stream", 4: "staged chain on a second stream overlapping k_shadow + k_denoise: first bounce as a wavefront (k_chain_first, k_chain_shadow0, k_chain_shade0), continuing paths compacted (k_chain_rest)", 5: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges the chain into the mirror / glass pixels", 6: "k_chain_q: persistent queue-fed grid, one bounce per work item, scattered paths appended to the queue (ballot / prefix compaction), on a second stream overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges it"}[args.chain],
                 "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
                 "parallelism": (f"tiles {TW}x{TH} dealt over {world} GPU(s), replicated BVH, " +
                                 ("resolve kernels store sRGB8 pixels straight into rank 0's image over NVLink peer memory (CUDA IPC) + a device-side flag barrier"

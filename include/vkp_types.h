@@ -87,7 +87,9 @@ typedef struct vkp_params {
                                         4 = as 2 with the first bounce staged as a wavefront: closest hit, per-light any-hit rays and hit
                                             shading in three lean kernels, the paths that scatter compacted for the remaining bounces,
                                         5 = as 2, and the resolve does not wait for the chain either: mirror / glass pixels are finished by
-                                            k_resolve_paths once the chain is there (the chain overlaps shadow + denoise + resolve) */
+                                            k_resolve_paths once the chain is there (the chain overlaps shadow + denoise + resolve),
+                                        6 = as 5 with the chain as a persistent wavefront: one bounce per work item, a queue-fed persistent
+                                            grid, scattered paths appended to the queue (ballot / prefix compaction) instead of looping */
     int32_t fuse_denoise;            /* vkp_render (Hybrid): run blur.comp inside the resolve kernel instead of as its own pass */
     int32_t reproject_fix;           /* blur.comp:52-53 on a reset frame.  0 (default): the reference's history fetch, pixel + motion.x * (W, H)
                                         (twice the right distance, x component used for both axes).

@@ -16,7 +16,8 @@
 
 // occupancy knobs (min resident CTAs per SM -> register cap), tuned by measurement
 #ifndef VKP_LB_GBUFFER
-#define VKP_LB_GBUFFER 4      /* 128 registers, no spills: 0.183 -> 0.148 ms at 1080p (8 CTAs / 64 registers spilled in the loop) */
+#define VKP_LB_GBUFFER 5      /* 96 registers.  Round 1 (local-memory stack): 4 CTAs / 128 registers beat 8 / 64 (0.148 vs 0.183 ms at 1080p).  Round 2
+                                 (shared-memory stack): 3 / 4 / 5 / 6 CTAs -> 0.152 / 0.151 / 0.143 / 0.166 ms (profiles/r2p_*) */
 #endif
 #ifndef VKP_LB_SHADOW
 #define VKP_LB_SHADOW 8       /* latency-bound: more resident warps beat the 176 bytes it spills at 64 registers */
@@ -28,7 +29,7 @@
 #define VKP_LB_RT 4
 #endif
 #ifndef VKP_LB_RESOLVE
-#define VKP_LB_RESOLVE 5
+#define VKP_LB_RESOLVE 6      /* 4 / 5 / 6 CTAs -> 0.137 / 0.121 / 0.110 ms for the resolve stage (profiles/r2p_*) */
 #endif
 #ifndef VKP_CHAIN_CALL
 #define VKP_CHAIN_CALL 0      /* 1: k_chain calls the traversal (trace_ray_call) instead of inlining it */
@@ -66,6 +67,15 @@ __device__ __forceinline__ Pixel pixel_of_block(const DFrame& F, const unsigned 
 }
 
 __device__ __forceinline__ Pixel pixel_of_thread(const DFrame& F) { return pixel_of_block(F, blockIdx.x); }
+
+// The per-pixel RNG seed of shadowRaygen.rgen:31 / hybridRaygen.rgen:31: tea(pixel index, frame), 16 rounds = ~190 integer instructions.
+// k_shadow runs one thread per (pixel, light), the chain one per path: inside a frame (vkp_render) k_gbuffer evaluates it once per pixel
+// into a plane and the later stages load it (26 % of k_shadow's instructions were TEA).  A stage run on its own has no such plane
+// (seed_r == NULL) and evaluates it.
+__device__ __forceinline__ uint32_t pixel_seed(const DFrame& F, size_t i, int x, int y)
+{
+    return F.seed_r ? __ldg(F.seed_r + i) : tea16((uint32_t)y * (uint32_t)F.p.width + (uint32_t)x, (uint32_t)F.p.frame);
+}
 
 // Longest-first scheduling.  A frame kernel ends with its slowest thread, and which pixels are slow (rays grazing the dense meshes)
 // hardly changes from one frame to the next: every warp leaves the cycles it took in cost[virtual block]; k_build_order turns
@@ -378,6 +388,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_GBUFFER) k_gbuffer(cons
         HitRec h; nrays = 1;
         bool hit = trace_ray<false>(S, sstack, o + d * 1e-2f, d, 0.001f, 10000.0f, h, nullptr, tcp);
         F.hit_ids[i] = make_int2(h.inst, h.prim);
+        if (F.seed_w) F.seed_w[i] = tea16((uint32_t)px.y * (uint32_t)W + (uint32_t)px.x, (uint32_t)F.p.frame);      // pixel_seed() of the later stages
         if (!hit) {
             // skybox.frag:16-21
             F.position[i] = make_uint2(0u, 0u); F.normal[i] = make_uint2(0u, 0u);
@@ -511,7 +522,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, MINB) k_shadow(const __grid_co
             if (g.NdotL > 0.0f) {
                 if (g.dist < g.maxd) {
                     // the RNG is only needed when rays are traced: TEA (16 rounds) is the most expensive part of an unlit pixel
-                    uint32_t seed = tea16((uint32_t)px.y * (uint32_t)W + (uint32_t)px.x, (uint32_t)F.p.frame);
+                    uint32_t seed = pixel_seed(F, i, px.x, px.y);
                     if (advance) {
                         for (int k = 0; k < l; k++) {
                             const LightGeom gk = light_geom(S.lights[k], position, N);
@@ -734,6 +745,22 @@ __global__ void __launch_bounds__(128) k_chain_scan(const __grid_constant__ DSce
     }
 }
 
+// the first reflection / refraction ray of a queued path, from the G-buffer (origin already offset along the direction)
+__device__ __forceinline__ void chain_first_ray(const DScene& S, const DFrame& F, size_t i, float3& ro, float3& direction)
+{
+    const float4 pos4 = unpack_half4(F.position[i]);
+    const vkp_material& mat = material_by_float_index(S, pos4.w);
+    const int shadingMode = (int)mat.shadingMetallicRoughness[0];
+    const float4 nrm4 = unpack_half4(F.normal[i]);
+    const float3 position = xyz(pos4);
+    const float3 N = normalize3(xyz(nrm4) * 2.0f - f3s(1.0f));
+    const float3 camPosition = f3(F.cam.inv_view[12], F.cam.inv_view[13], F.cam.inv_view[14]);
+    const float3 V = normalize3(camPosition - position);
+    float3 origin = f3s(0.0f); direction = f3s(0.0f);
+    if (S.n_lights > 0) first_bounce(shadingMode, mat, position, N, V, origin, direction);   // upstream sets them inside the light loop
+    ro = origin + direction * 1e-2f;
+}
+
 // One THREAD per queued path (chain mode 2, the default): all paths are in flight at once -- a path is a chain of dependent
 // rays, so what counts is how many of them overlap, and one thread per path keeps every path of the frame resident.
 __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
@@ -744,7 +771,18 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain(const __
     unsigned int n_refl = 0, n_sec = 0;
     TravCount tc = {0u, 0u, 0u};
     TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
-    for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
+    // A PERSISTENT grid fed from the path queue (north_star: "persistent-thread ... traversal"): every warp takes the next 32 paths with
+    // one atomic until the queue is empty.  The grid is a few CTAs per SM, all resident from the start.  That matters for the OTHER
+    // stream: while CTAs of this high-priority kernel are waiting for a slot, the block scheduler places nothing of k_shadow, so a
+    // one-thread-per-path grid (three waves at this register count) kept the main stream out for half the chain's duration.
+    const int lane = (int)(threadIdx.x & 31u);
+    while (true) {
+        unsigned int base = 0u;
+        if (lane == 0) base = atomicAdd(&F.path_count[1], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_paths) break;
+        const unsigned int slot = base + (unsigned int)lane;
+        if (slot < n_paths) {
         const size_t i = (size_t)F.chain_pix[slot];
         const int py = (int)(i / (size_t)F.p.width), pxl = (int)(i - (size_t)py * F.p.width);
         const float4 pos4 = unpack_half4(F.position[i]);
@@ -759,7 +797,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain(const __
         float3 origin = f3s(0.0f), direction = f3s(0.0f);
         if (S.n_lights > 0) first_bounce(shadingMode, mat, position, N, V, origin, direction);   // upstream sets them inside the light loop
         Payload prd;
-        prd.seed = tea16((uint32_t)py * (uint32_t)F.p.width + (uint32_t)pxl, (uint32_t)F.p.frame);
+        prd.seed = pixel_seed(F, i, pxl, py);
         int n = 0;
         for (int depth = 0; depth < F.p.max_bounces; depth++) {
             float3 ro = origin + direction * 1e-2f;
@@ -777,6 +815,132 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain(const __
             origin = prd.origin; direction = prd.direction;
         }
         F.chain_len[slot] = n;
+        }
+        __syncwarp();
+    }
+    add_counter(F.counters, 2, n_refl);
+    add_counter(F.counters, 3, n_sec);
+    if (F.count_trav) add_trav(F.counters, tc);
+}
+
+// ---- chain schedule 6: a persistent WAVEFRONT (north_star: "persistent-thread ... traversal ... ray compaction with warp ballot/prefix") ----
+// k_chain keeps a path in its thread for up to 8 bounces, and 91 % of the paths end after the first: a warp carries on for the few
+// lanes that go on, holding 32 x 168 registers for one or two live paths (61 us per 32 paths where a single bounce takes ~25).
+// Here ONE BOUNCE is the unit of work.  A persistent grid pulls items from a queue -- items [0, n_paths) are the first bounces of the
+// compacted path list, the rest are continuations -- traces and shades one bounce per lane, and a path that scatters is APPENDED to
+// the queue (one atomic per warp, slots by ballot + popc prefix) instead of looping: warps always work on full batches.
+//   path_count[0] n_paths   [1] head (next item to hand out)   [2] continuations reserved so far   [3] items completed
+// A continuation becomes visible through a per-item tag written with st.release after its data (consumers that got the index
+// early spin on ld.acquire).  The grid ends when every item ever created has been completed: continuations are reserved before
+// their parent is counted, so completed == created means nothing is in flight.  If the continuation array is full the lane simply
+// goes on with its path itself.  Same arithmetic as k_chain: every stored colour is bit-identical.
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_volatile_u32(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
+
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_q(const __grid_constant__ DScene S, const __grid_constant__ DFrame F, const uint32_t tag,
+                                                                          const unsigned int cont_cap)
+{
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
+    const unsigned int full = 0xffffffffu;
+    const int lane = (int)(threadIdx.x & 31u);
+    const unsigned int lt = (1u << lane) - 1u;
+    const unsigned int n_paths = F.path_count[0];
+    unsigned int* const head = &F.path_count[1];
+    unsigned int* const conts = &F.path_count[2];
+    unsigned int* const completed = &F.path_count[3];
+    PathItem* const cq = F.path_q[1];
+    unsigned int n_refl = 0, n_sec = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;
+    // A warp CLAIMS 32 consecutive item indices with one atomicAdd (no compare-and-swap: 1776 warps retrying on one word took
+    // milliseconds) and works through its claim as the items come into existence: [cur, end) is what is left of it.
+    unsigned int cur = 0u, end = 0u;
+    while (true) {
+        // ---- the warp's next batch --------------------------------------------------------------------------------------------
+        unsigned int base = 0u, cnt = 0u;
+        if (lane == 0) {
+            unsigned int backoff = 64u;
+            while (true) {
+                if (cur == end) { cur = atomicAdd(head, 32u); end = cur + 32u; }
+                const unsigned int t = n_paths + ld_volatile_u32(conts);              // items created so far
+                if (cur < t) { base = cur; cnt = (end < t ? end : t) - cur; cur += cnt; break; }
+                const unsigned int done = ld_volatile_u32(completed), t2 = n_paths + ld_volatile_u32(conts);
+                if (done == t2 && t2 == t) break;                      // everything ever created is completed: nothing can appear any more
+                __nanosleep(backoff);
+                if (backoff < 1024u) backoff <<= 1;
+            }
+        }
+        base = __shfl_sync(full, base, 0); cnt = __shfl_sync(full, cnt, 0);
+        if (cnt == 0u) break;
+        // ---- one bounce per lane -------------------------------------------------------------------------------------------------
+        bool active = (unsigned int)lane < cnt;
+        unsigned int slot = 0u;
+        int depth = 0;
+        float3 ro = f3s(0.0f), direction = f3s(0.0f);
+        Payload prd; prd.seed = 0u;
+        if (active) {
+            const unsigned int k = base + (unsigned int)lane;
+            if (k < n_paths) {
+                slot = k;
+                const size_t i = (size_t)F.chain_pix[slot];
+                const int py = (int)(i / (size_t)F.p.width), pxl = (int)(i - (size_t)py * F.p.width);
+                chain_first_ray(S, F, i, ro, direction);
+                prd.seed = pixel_seed(F, i, pxl, py);
+            } else {
+                PathItem* it = cq + (k - n_paths);
+                while (ld_acquire_gpu(reinterpret_cast<const uint32_t*>(&it->d.w)) != tag) __nanosleep(40);      // reserved, not yet written
+                const float4 a = it->a, b = it->b, c = it->c;
+                slot = __float_as_uint(a.w); depth = __float_as_int(c.x);
+                direction = f3(b.x, b.y, b.z);
+                ro = f3(a.x, a.y, a.z) + direction * 1e-2f;
+                prd.seed = __float_as_uint(b.w);
+            }
+        }
+        while (__any_sync(full, active)) {
+            bool again = false;
+            if (active) {
+                HitRec h; n_refl++;
+                const bool hit = trace_ray<false>(S, sstack, ro, direction, 0.001f, 1000.0f, h, nullptr, tcp);
+                if (hit) shade_hit<false>(S, sstack, F.p, ro, direction, h, prd, n_sec, tcp); else shade_miss(S, direction, prd);
+                F.chain_buf[(size_t)slot * VKP_CHAIN_MAX + depth] = make_float4(prd.color.x, prd.color.y, prd.color.z, 0.0f);
+                again = hit && (prd.scatter > 0.0f) && depth + 1 < F.p.max_bounces;
+                if (!again) { F.chain_len[slot] = depth + 1; active = false; }
+            }
+            // the paths that go on: appended to the queue, compacted
+            const unsigned int m = __ballot_sync(full, again);
+            if (m) {
+                unsigned int at = 0xffffffffu;
+                if (lane == __ffs(m) - 1) {
+                    const unsigned int want = (unsigned int)__popc(m);
+                    if (ld_volatile_u32(conts) + want + 4096u <= cont_cap) at = atomicAdd(conts, want);     // (slack: other warps reserve concurrently)
+                }
+                at = __shfl_sync(full, at, __ffs(m) - 1);
+                if (again) {
+                    if (at != 0xffffffffu) {
+                        PathItem* it = cq + at + __popc(m & lt);
+                        it->a = make_float4(prd.origin.x, prd.origin.y, prd.origin.z, __uint_as_float(slot));
+                        it->b = make_float4(prd.direction.x, prd.direction.y, prd.direction.z, __uint_as_float(prd.seed));
+                        it->c = make_float4(__int_as_float(depth + 1), 0.0f, 0.0f, 0.0f);
+                        st_release_gpu(reinterpret_cast<uint32_t*>(&it->d.w), tag);
+                        active = false;
+                    } else {
+                        // no room: this lane walks the rest of its path itself
+                        depth++;
+                        direction = prd.direction;
+                        ro = prd.origin + direction * 1e-2f;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence(); atomicAdd(completed, cnt); }
     }
     add_counter(F.counters, 2, n_refl);
     add_counter(F.counters, 3, n_sec);
@@ -817,7 +981,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_warp(con
         float3 origin = f3s(0.0f), direction = f3s(0.0f);
         if (S.n_lights > 0) first_bounce(shadingMode, mat, position, N, V, origin, direction);   // upstream sets them inside the light loop
         Payload prd;
-        prd.seed = tea16((uint32_t)py * (uint32_t)F.p.width + (uint32_t)pxl, (uint32_t)F.p.frame);
+        prd.seed = pixel_seed(F, i, pxl, py);
         int n = 0;
         for (int depth = 0; depth < F.p.max_bounces; depth++) {
             float3 ro = origin + direction * 1e-2f;
@@ -849,21 +1013,6 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_warp(con
 // Records live in path_q[0] (by slot) and path_q[1] (continuing paths); path_count[2] counts the latter.  Same arithmetic in the
 // same order as k_chain: every stored colour is bit-identical.
 //   record.a = ray origin (already offset), t of the hit or -1     record.b = direction, u     record.c = v, instance, primitive, mask
-__device__ __forceinline__ void chain_first_ray(const DScene& S, const DFrame& F, size_t i, float3& ro, float3& direction)
-{
-    const float4 pos4 = unpack_half4(F.position[i]);
-    const vkp_material& mat = material_by_float_index(S, pos4.w);
-    const int shadingMode = (int)mat.shadingMetallicRoughness[0];
-    const float4 nrm4 = unpack_half4(F.normal[i]);
-    const float3 position = xyz(pos4);
-    const float3 N = normalize3(xyz(nrm4) * 2.0f - f3s(1.0f));
-    const float3 camPosition = f3(F.cam.inv_view[12], F.cam.inv_view[13], F.cam.inv_view[14]);
-    const float3 V = normalize3(camPosition - position);
-    float3 origin = f3s(0.0f); direction = f3s(0.0f);
-    if (S.n_lights > 0) first_bounce(shadingMode, mat, position, N, V, origin, direction);   // upstream sets them inside the light loop
-    ro = origin + direction * 1e-2f;
-}
-
 __global__ void __launch_bounds__(VKP_TRAV_BLOCK, 8) k_chain_first(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
@@ -927,7 +1076,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, 8) k_chain_shadow0(const __gri
         if (!(g.NdotL > 0.0f) || !(g.dist < g.maxd)) continue;
         const size_t i = (size_t)F.chain_pix[slot];
         const int py = (int)(i / (size_t)F.p.width), pxl = (int)(i - (size_t)py * F.p.width);
-        uint32_t seed = tea16((uint32_t)py * (uint32_t)F.p.width + (uint32_t)pxl, (uint32_t)F.p.frame);
+        uint32_t seed = pixel_seed(F, i, pxl, py);
         if (advance) {
             for (int k = 0; k < l; k++) {
                 const LightGeom gk = light_geom(S.lights[k], worldPos, N);
@@ -957,7 +1106,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_shade0(c
             const size_t i = (size_t)F.chain_pix[slot];
             const int py = (int)(i / (size_t)F.p.width), pxl = (int)(i - (size_t)py * F.p.width);
             Payload prd;
-            prd.seed = tea16((uint32_t)py * (uint32_t)F.p.width + (uint32_t)pxl, (uint32_t)F.p.frame);
+            prd.seed = pixel_seed(F, i, pxl, py);
             const float3 ro = f3(a.x, a.y, a.z), direction = f3(b.x, b.y, b.z);
             const bool hit = !(a.w < 0.0f);
             if (hit) {
@@ -1039,7 +1188,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_RESOLVE) k_resolve(cons
         const size_t i = (size_t)px.y * W + px.x;
         const size_t plane = (size_t)W * H;
         Payload prd;
-        prd.seed = tea16((uint32_t)px.y * (uint32_t)W + (uint32_t)px.x, (uint32_t)F.p.frame);
+        prd.seed = pixel_seed(F, i, px.x, px.y);
         float4 pos4 = unpack_half4(F.position[i]);
         float4 nrm4 = unpack_half4(F.normal[i]);
         const vkp_material& mat = material_by_float_index(S, pos4.w);
@@ -1149,7 +1298,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_RESOLVE) k_resolve(cons
             }
         }
         if (CHAIN == 3 && wants_path) {
-            PathItem* rec = F.path_q[1] + F.chain_slot[i];
+            PathItem* rec = F.path_q[0] + F.chain_slot[i];      // (path_q[1] is the continuation queue of schedule 6)
             rec->c = make_float4(rayColor.x, rayColor.y, rayColor.z, background ? 1.0f : 0.0f);
             rec->d = background ? make_float4(albedo.x, albedo.y, albedo.z, 0.0f) : make_float4(tail.x, tail.y, tail.z, 0.0f);
         } else if (CHAIN != 1 || !wants_path) {
@@ -1227,7 +1376,7 @@ __global__ void __launch_bounds__(128) k_resolve_paths(const __grid_constant__ D
     const unsigned int n_paths = F.path_count[0];
     for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
         const size_t i = (size_t)F.chain_pix[slot];
-        const float4 c0 = F.path_q[1][slot].c, t0 = F.path_q[1][slot].d;
+        const float4 c0 = F.path_q[0][slot].c, t0 = F.path_q[0][slot].d;
         float3 rayColor = f3(c0.x, c0.y, c0.z);
         const float4* rec = F.chain_buf + (size_t)slot * VKP_CHAIN_MAX;
         const int n = F.chain_len[slot];
@@ -1569,6 +1718,25 @@ inline dim3 frame_grid(const FrameLaunch& L)
 
 } // namespace
 
+// Every kernel that can share an SM with another one of the frame (the chain stream runs beside the main stream) asks for the SAME
+// shared-memory / L1 split: an SM has to drain before its split can change, so two concurrent kernels that prefer different
+// splits take turns on it instead of sharing it.  pct = share of the 228 KB that is shared memory (-1: leave the driver's choice).
+cudaError_t launch_set_carveout(int pct)
+{
+    if (pct < 0) return cudaSuccess;
+    const void* fns[] = {(const void*)k_gbuffer, (const void*)k_shadow<VKP_LB_SHADOW, true>, (const void*)k_shadow<VKP_LB_SHADOW, false>,
+                         (const void*)k_shadow<VKP_LB_SHADOW_MANY, false>, (const void*)k_chain, (const void*)k_chain_q, (const void*)k_chain_scan, (const void*)k_chain_warp,
+                         (const void*)k_chain_first, (const void*)k_chain_shadow0, (const void*)k_chain_shade0, (const void*)k_chain_rest,
+                         (const void*)k_denoise, (const void*)k_denoise_accumulate4, (const void*)k_resolve<0>, (const void*)k_resolve<1>,
+                         (const void*)k_resolve<2>, (const void*)k_resolve<3>, (const void*)k_resolve_paths, (const void*)k_bounce, (const void*)k_build_order,
+                         (const void*)k_raytrace, (const void*)k_raytrace_warp, (const void*)k_atrous};
+    for (const void* f : fns) {
+        cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_gbuffer(const FrameLaunch& L) { k_gbuffer<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
 cudaError_t launch_shadow(const FrameLaunch& L)
 {
@@ -1607,7 +1775,7 @@ cudaError_t launch_resolve(const FrameLaunch& L, int* launches)
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
-    if (L.frame.p.wavefront == 5) {
+    if (L.frame.p.wavefront == 5 || L.frame.p.wavefront == 6) {
         k_resolve<3><<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);     // needs k_chain_scan only; launch_resolve_paths follows the chain
         if (launches) *launches += 1;
         return cudaGetLastError();
@@ -1634,11 +1802,11 @@ cudaError_t launch_resolve_paths(const FrameLaunch& L)
     k_resolve_paths<<<frame_grid(L).x / 4u + 1u, 128, 0, L.stream>>>(L.frame);
     return cudaGetLastError();
 }
-cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t after_scan)
+cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t after_scan, uint32_t tag, unsigned int cont_cap)
 {
     // path_count[0] = number of paths, [1] = head of the queue the persistent warps of mode 3 pull from
     // [2] = number of paths that go on after their first bounce (staged chain, mode 4)
-    cudaError_t e = launch_stage_words(stream, L.frame.path_count, nullptr, 3 * sizeof(unsigned int));
+    cudaError_t e = launch_stage_words(stream, L.frame.path_count, nullptr, 4 * sizeof(unsigned int));
     if (e != cudaSuccess) return e;
     k_chain_scan<<<frame_grid(L), 128, 0, stream>>>(L.scene, L.frame);
     if (after_scan && (e = cudaEventRecord(after_scan, stream)) != cudaSuccess) return e;
@@ -1650,24 +1818,31 @@ cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t 
         if (L.scene.n_lights > 0) k_chain_shadow0<<<dim3(g1, (unsigned)L.scene.n_lights), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
         k_chain_shade0<<<g1, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
         k_chain_rest<<<g2, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    } else if (L.frame.p.wavefront == 6) {
+        static int per_sm6 = 0, n_sm6 = 0;
+        if (!per_sm6) {
+            const char* e6 = getenv("VKP_CHAIN_PERSIST"); per_sm6 = e6 ? atoi(e6) : 3; if (per_sm6 < 1 || per_sm6 > 16) per_sm6 = 3;
+            int dev = 0; cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&n_sm6, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm6 <= 0) n_sm6 = 148;
+        }
+        k_chain_q<<<(unsigned)(per_sm6 * n_sm6), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame, tag, cont_cap);
     } else if (L.frame.p.wavefront == 3) k_chain_warp<<<148 * VKP_LB_CHAIN, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
     else {
         // every queued path gets its own thread in ONE pass (a second pass would double the critical path): the queue length is
         // only known on the device, so the grid covers a quarter of the rank's pixels and the threads beyond the queue leave at once
         const unsigned int px_blocks = frame_grid(L).x;
-        // VKP_CHAIN_CTAS=n (A/B knob): at most n chain CTAs per SM, enforced with a dynamic shared-memory reservation nobody uses, so
-        // that the high-priority chain cannot take every register of an SM away from k_shadow
-        static int ctas = -1;
-        static size_t dyn = 0;
-        if (ctas < 0) {
-            const char* e = getenv("VKP_CHAIN_CTAS");
-            ctas = e ? atoi(e) : 0;
-            if (ctas > 0) {
-                dyn = (size_t)(220 * 1024) / (size_t)ctas - (size_t)(VKP_TRAV_SMEM_WORDS * 4) - 1024;
-                cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-            }
+        // CTAs of ONE warp (VKP_CHAIN_BLOCK, default 32): an SM gets a chain CTA's registers back when its last thread ends, and most
+        // paths end after one bounce while a few go on for eight -- with 128-thread CTAs one long path kept 128 x 168 registers away
+        // from k_shadow on the other stream
+        // VKP_CHAIN_PERSIST = CTAs per SM of the persistent grid (default 3: what fits at 168 registers per thread; measured 1 .. 6)
+        static int per_sm = 0, n_sm = 0;
+        if (!per_sm) {
+            const char* e = getenv("VKP_CHAIN_PERSIST"); per_sm = e ? atoi(e) : 3; if (per_sm < 1 || per_sm > 16) per_sm = 3;
+            int dev = 0; cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
         }
-        k_chain<<<px_blocks / 4u + 1u, VKP_TRAV_BLOCK, dyn, stream>>>(L.scene, L.frame);
+        (void)px_blocks;
+        k_chain<<<(unsigned)(per_sm * n_sm), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
     }
     return cudaGetLastError();
 }

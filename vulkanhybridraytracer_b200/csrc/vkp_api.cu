@@ -62,6 +62,7 @@ struct vkp_ctx {
     bool have_cam = false, have_params = false;
     int rank = 0, world = 1, tile_w = 16, tile_h = 8;
 
+    DevBuf seed;                      // per-pixel RNG seeds of the frame being rendered (k_gbuffer -> k_shadow / chain / resolve)
     DevBuf position, normal, albedo, motion, material, emissive, hit_ids, final_f32, final_srgb8, shadow, denoised[2];
     int denoised_cur = 0;
     int plane_w = 0, plane_h = 0, plane_lights = 0;
@@ -69,6 +70,9 @@ struct vkp_ctx {
     DevBuf counters, io_tmp, io_tmp2, flush, path_q[2], path_count, luts, chain_buf, chain_len, chain_slot, chain_pix;
     cudaStream_t chain_stream = nullptr;
     cudaEvent_t ev_gbuffer = nullptr, ev_chain = nullptr, ev_scan = nullptr;
+    cudaEvent_t ev_chain_t0 = nullptr, ev_chain_t1 = nullptr;     // profiling: the chain on its own stream (vkp_counters.ms_stage[7], ms_tlas = its end in the frame)
+    bool chain_timed = false;
+    uint32_t chain_tag = 0;           // launch counter: the "written" mark of the continuation items of chain schedule 6 (never 0)
     // longest-first CTA schedule of k_gbuffer [0] and k_shadow [1], rebuilt every frame from the previous frame's per-block cycles
     DevBuf cta_cost[2], cta_order[2];
     uint32_t order_n[2] = {0u, 0u};
@@ -76,6 +80,7 @@ struct vkp_ctx {
     cudaStream_t order_stream = nullptr;
     cudaEvent_t ev_stage_done[2] = {nullptr, nullptr}, ev_order_done[2] = {nullptr, nullptr};
     int schedule = 1;                 // 0 = hardware block order, 1 = longest first (VKP_SCHEDULE=0|1)
+    bool use_seed_plane = true;       // k_gbuffer evaluates TEA once per pixel for the frame's later stages (VKP_SEED_PLANE=0: every stage evaluates it)
     bool chain_in_flight = false;
     // multi-GPU: FINAL_SRGB8 is double-buffered (vkp_set_output_buffer) and may be redirected into rank 0's two buffers over NVLink
     // (vkp_set_output_redirect): frame k+1 is written to the other buffer while rank 0 still consumes frame k
@@ -205,7 +210,7 @@ int ensure_planes(vkp_ctx* ctx)
     if (W == ctx->plane_w && H == ctx->plane_h && L == ctx->plane_lights) return VKP_OK;
     const size_t px = (size_t)W * H;
     CK(ctx->position.ensure(px * 8)); CK(ctx->normal.ensure(px * 8)); CK(ctx->albedo.ensure(px * 4)); CK(ctx->motion.ensure(px * 4));
-    CK(ctx->material.ensure(px * 4)); CK(ctx->emissive.ensure(px * 4)); CK(ctx->hit_ids.ensure(px * 8));
+    CK(ctx->material.ensure(px * 4)); CK(ctx->emissive.ensure(px * 4)); CK(ctx->hit_ids.ensure(px * 8)); CK(ctx->seed.ensure(px * 4));
     CK(ctx->final_f32.ensure(px * 16)); CK(ctx->final_srgb8.ensure(px * 4)); CK(ctx->final_srgb8_alt.ensure(px * 4));
     CK(ctx->shadow.ensure(px * L)); CK(ctx->denoised[0].ensure(px * L)); CK(ctx->denoised[1].ensure(px * L));
     CK(ctx->counters.ensure(64));
@@ -348,6 +353,7 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.position = ctx->position.as<uint2>(); F.normal = ctx->normal.as<uint2>(); F.albedo = ctx->albedo.as<uchar4>();
     F.motion = ctx->motion.as<uint32_t>(); F.material = ctx->material.as<uchar4>(); F.emissive = ctx->emissive.as<uchar4>();
     F.hit_ids = ctx->hit_ids.as<int2>(); F.final_f32 = ctx->final_f32.as<float4>();
+    F.seed_w = nullptr; F.seed_r = nullptr;       // vkp_render (Hybrid) switches the seed plane on for the frame it renders
     F.final_srgb8 = ctx->peer_srgb8[ctx->out_sel] ? reinterpret_cast<uchar4*>(ctx->peer_srgb8[ctx->out_sel])
                                                   : (ctx->out_sel ? ctx->final_srgb8_alt.as<uchar4>() : ctx->final_srgb8.as<uchar4>());
     F.shadow = ctx->shadow.as<uint8_t>();
@@ -469,6 +475,9 @@ int stage_event(vkp_ctx* ctx, int stage)
     return VKP_OK;
 }
 
+// continuation items the path queue of chain schedule 6 can hold (path_q[1]: one PathItem per pixel)
+unsigned int chain_cont_cap(const vkp_ctx* ctx) { return (unsigned int)((size_t)ctx->plane_w * ctx->plane_h); }
+
 // kernels launch_chain() queues: counter clear + k_chain_scan + k_chain, or the four kernels of the staged chain (mode 4)
 uint32_t chain_launches(const FrameLaunch& L) { return L.frame.p.wavefront == 4 ? (L.scene.n_lights > 0 ? 6u : 5u) : 3u; }
 
@@ -512,8 +521,8 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
     case VKP_STAGE_RESOLVE: {
         int n = 0;
         const bool chain2 = L.frame.p.wavefront >= 2 && L.frame.p.max_bounces <= VKP_CHAIN_MAX;
-        const bool late = chain2 && L.frame.p.wavefront == 5;      // the resolve does not wait for the chain: k_resolve_paths merges it afterwards
-        if (chain2 && !ctx->chain_in_flight) { CK(launch_chain(L, ctx->stream)); ctx->last_launches += chain_launches(L); }      // stand-alone stage: serial (clear + scan + chain)
+        const bool late = chain2 && (L.frame.p.wavefront == 5 || L.frame.p.wavefront == 6);      // the resolve does not wait for the chain: k_resolve_paths merges it afterwards
+        if (chain2 && !ctx->chain_in_flight) { CK(launch_chain(L, ctx->stream, nullptr, ++ctx->chain_tag, chain_cont_cap(ctx))); ctx->last_launches += chain_launches(L); }      // stand-alone stage: serial (clear + scan + chain)
         if (chain2 && ctx->chain_in_flight && !late) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0)); ctx->chain_in_flight = false; }
         if (late && ctx->chain_in_flight) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_scan, 0));
         CK(launch_resolve(L, &n));
@@ -585,9 +594,17 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
         cudaStreamCreateWithPriority(&ctx->order_stream, cudaStreamNonBlocking, hi);
         for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags(&ctx->ev_stage_done[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_order_done[k], cudaEventDisableTiming); }
         if (const char* e = getenv("VKP_SCHEDULE")) ctx->schedule = atoi(e) != 0;
+        if (const char* e = getenv("VKP_SEED_PLANE")) ctx->use_seed_plane = atoi(e) != 0;
         cudaEventCreateWithFlags(&ctx->ev_gbuffer, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_scan, cudaEventDisableTiming);
+    }
+    {
+        // one shared-memory / L1 split for all frame kernels (launch_set_carveout): 100 KB of shared memory covers 8 k_shadow CTAs (64 KB of
+        // traversal stacks) plus the chain's beside them; VKP_SMEM_CARVEOUT=<percent> or -1 (driver default per kernel) for A/B runs
+        int pct = 44;
+        if (const char* c = getenv("VKP_SMEM_CARVEOUT")) pct = atoi(c);
+        if ((e = launch_set_carveout(pct)) != cudaSuccess) { vkp_destroy(ctx); return cuda_fail(nullptr, e, "cudaFuncSetAttribute(carveout)"); }
     }
     if (const char* b = getenv("VKP_BLAS_BUILDER")) ctx->builder = (strcmp(b, "lbvh") == 0) ? 0 : 1;
     if (const char* l = getenv("VKP_L2_PERSIST")) ctx->l2_persist = atoi(l) != 0;
@@ -626,7 +643,7 @@ void vkp_destroy(vkp_ctx* ctx)
     }
     if (ctx->update_stream) cudaStreamDestroy(ctx->update_stream);
     if (ctx->ev_updated) cudaEventDestroy(ctx->ev_updated);
-    DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_textures, &ctx->position, &ctx->normal, &ctx->albedo, &ctx->motion,
+    DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_textures, &ctx->position, &ctx->seed, &ctx->normal, &ctx->albedo, &ctx->motion,
                       &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
                       &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->chain_pix, &ctx->final_srgb8_alt};
     for (DevBuf* b : bufs) b->release();
@@ -932,7 +949,7 @@ int vkp_set_params(vkp_ctx* ctx, const vkp_params* p)
     if (p->max_bounces > VKP_MAX_BOUNCES) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: max_bounces > 64");
     if (p->spp < 1 || p->shadow_samples < 1 || p->max_bounces < 0) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: spp / shadow_samples must be >= 1");
     if (p->denoiser < 0 || p->denoiser > 1) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: denoiser is 0 (blur.comp) or 1 (a-trous)");
-    if (p->wavefront < 0 || p->wavefront > 5) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: wavefront (chain schedule) is 0 .. 5");
+    if (p->wavefront < 0 || p->wavefront > 6) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: wavefront (chain schedule) is 0 .. 6");
     ctx->params = *p; ctx->have_params = true;
     return VKP_OK;
 }
@@ -970,14 +987,22 @@ int vkp_render(vkp_ctx* ctx)
     if (fused) { seq = hybrid_fused; n = 3; L.frame.fused = 1; }
     if (ctx->params.mode == VKP_MODE_RAYTRACING) { seq = rt; n = 1; }
     else if (ctx->params.mode == VKP_MODE_DEFERRED) { seq = deferred; n = 2; }
+    const bool seeds = ctx->params.mode == VKP_MODE_HYBRID && ctx->use_seed_plane;
+    if (seeds) L.frame.seed_w = ctx->seed.as<uint32_t>();
     for (int i = 0; i < n; i++) {
         if ((r = run_one(ctx, L, seq[i])) != VKP_OK) return r;
+        if (seq[i] == VKP_STAGE_GBUFFER && seeds) { L.frame.seed_w = nullptr; L.frame.seed_r = ctx->seed.as<uint32_t>(); }
         if (seq[i] == VKP_STAGE_GBUFFER && ctx->params.mode == VKP_MODE_HYBRID && ctx->params.wavefront >= 2 &&
             ctx->params.max_bounces <= VKP_CHAIN_MAX && L.n_own_tiles > 0) {
             // fork: the reflection chain needs only the G-buffer; it overlaps the shadow + denoise passes on its own stream
             CK(cudaEventRecord(ctx->ev_gbuffer, ctx->stream));
             CK(cudaStreamWaitEvent(ctx->chain_stream, ctx->ev_gbuffer, 0));
-            CK(launch_chain(L, ctx->chain_stream, ctx->ev_scan));
+            if (ctx->profiling) {
+                if (!ctx->ev_chain_t0) { CK(cudaEventCreate(&ctx->ev_chain_t0)); CK(cudaEventCreate(&ctx->ev_chain_t1)); }
+                CK(cudaEventRecord(ctx->ev_chain_t0, ctx->chain_stream));
+            }
+            CK(launch_chain(L, ctx->chain_stream, ctx->ev_scan, ++ctx->chain_tag, chain_cont_cap(ctx)));
+            if (ctx->profiling) { CK(cudaEventRecord(ctx->ev_chain_t1, ctx->chain_stream)); ctx->chain_timed = true; }
             CK(cudaEventRecord(ctx->ev_chain, ctx->chain_stream));
             ctx->chain_in_flight = true;
             ctx->last_launches += chain_launches(L);
@@ -1234,6 +1259,14 @@ int vkp_get_counters(vkp_ctx* ctx, vkp_counters* out)
             if (ctx->ev_stage[i] >= 0 && ctx->ev_stage[i] < 8) out->ms_stage[ctx->ev_stage[i]] += ms;
         }
         CK(cudaEventElapsedTime(&out->ms_frame, ctx->ev[0], ctx->ev[ctx->n_ev - 1]));
+        if (ctx->chain_timed) {
+            // the reflection chain on its own stream: [7] = its duration (queue clear + k_chain_scan + chain kernels), ms_tlas = when it ended,
+            // measured from the start of the frame
+            CK(cudaEventSynchronize(ctx->ev_chain_t1));
+            CK(cudaEventElapsedTime(&out->ms_stage[7], ctx->ev_chain_t0, ctx->ev_chain_t1));
+            CK(cudaEventElapsedTime(&out->ms_tlas, ctx->ev[0], ctx->ev_chain_t1));
+            ctx->chain_timed = false;
+        }
     }
     out->kernel_launches = ctx->last_launches;
     return VKP_OK;

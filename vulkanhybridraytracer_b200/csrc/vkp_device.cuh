@@ -160,6 +160,8 @@ struct DFrame {
     uchar4* material;
     uchar4* emissive;
     int2* hit_ids;
+    uint32_t* seed_w;               // k_gbuffer writes tea(pixel, frame) here (NULL: not wanted) ...
+    const uint32_t* seed_r;         // ... and the later stages of the same frame read it (NULL: evaluate TEA; see pixel_seed)
     float4* final_f32;
     uchar4* final_srgb8;
     uint8_t* shadow;      // n_lights planes

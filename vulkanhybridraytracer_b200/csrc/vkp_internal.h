@@ -91,12 +91,13 @@ struct FrameLaunch {
     DFrame frame;              // host copy (for grid sizing)
     int n_own_tiles;
 };
+cudaError_t launch_set_carveout(int pct);
 cudaError_t launch_gbuffer(const FrameLaunch& L);
 cudaError_t launch_shadow(const FrameLaunch& L);
 cudaError_t launch_denoise(const FrameLaunch& L, uint8_t* atrous_a = nullptr, uint8_t* atrous_b = nullptr);
 cudaError_t launch_build_order(cudaStream_t s, uint32_t* cost, uint32_t* order, uint32_t n);
 cudaError_t launch_resolve(const FrameLaunch& L, int* launches);
-cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t after_scan = nullptr);
+cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t after_scan = nullptr, uint32_t tag = 1u, unsigned int cont_cap = 0u);
 cudaError_t launch_resolve_paths(const FrameLaunch& L);
 cudaError_t launch_post(const FrameLaunch& L);
 cudaError_t launch_raytrace(const FrameLaunch& L);
