@@ -105,7 +105,9 @@ class ClockSampler:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        # the first sample or two may precede the load (nvidia-smi reports the idle clock then): the median is over the window
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "sm_mhz_min": min(sm) if sm else None}
 
 
 def stats_ms(xs):
@@ -198,39 +200,14 @@ def parity_and_cpu_baseline(vk, ctx, scene, name, chain, budget_s):
     return par, base
 
 
-def nccl_debug_to_file(rank):
-    """The driver checks the communicator size from NCCL's own log; NCCL writes that log to stdout by default, where the contract
-    wants exactly one JSON line.  Route it into a per-rank file and replay the interesting lines on stderr afterwards."""
+def nccl_debug_to_stderr():
+    """The driver checks the communicator size from NCCL's own log ("... nranks N ...").  NCCL writes that log to stdout by default,
+    where the contract wants exactly one JSON line: NCCL_DEBUG_FILE=/dev/stderr sends every rank's INIT lines to stderr instead
+    (torchrun forwards them).  Nothing is overridden if the caller has set these variables."""
     os.environ.setdefault("NCCL_DEBUG", "INFO")
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("INFO", "TRACE") and "NCCL_DEBUG_SUBSYS" not in os.environ:
-        os.environ["NCCL_DEBUG_SUBSYS"] = "INIT,ENV"
-    if "NCCL_DEBUG_FILE" in os.environ:
-        return None
-    d = tempfile.mkdtemp(prefix="vkp_nccl_")
-    os.environ["NCCL_DEBUG_FILE"] = os.path.join(d, "nccl_%h_%p.log")
-    return d
-
-
-def replay_nccl_log(d):
-    if not d:
-        return None
-    seen = []
-    for f in sorted(glob.glob(os.path.join(d, "nccl_*.log"))):
-        try:
-            for line in open(f, errors="replace"):
-                if "nranks" in line or "NCCL version" in line or "NVLS" in line:
-                    seen.append(line.rstrip())
-        except OSError:
-            pass
-    for line in seen[:40]:
-        print(line, file=sys.stderr)
-    nr = set()
-    for line in seen:
-        parts = line.replace("=", " ").split()
-        for a, b in zip(parts, parts[1:]):
-            if a == "nranks" and b.strip(",").isdigit():
-                nr.add(int(b.strip(",")))
-    return sorted(nr)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("INFO", "TRACE"):
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 
 def load_ncu_measured():
@@ -257,8 +234,8 @@ def main():
     ap.add_argument("--no-peer", action="store_true", help="N > 1: composite with pack + NCCL gather + unpack instead of NVLink peer stores")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-identity check of the composite against a 1-GPU render")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the 2-step Raytraced 64 spp x 64 samples block (BASELINE configs[2])")
-    ap.add_argument("--chain", type=int, default=5, choices=[0, 1, 2, 3, 4, 5, 6],
-                    help="reflection-chain schedule: 0 inline in k_resolve, 1 wavefront queues, 2 k_chain overlapped with the shadow pass, 3 warp per path, 4 staged first bounce, 5 = 2 + the resolve does not wait for the chain (default)")
+    ap.add_argument("--chain", type=int, default=7, choices=[0, 1, 2, 3, 4, 5, 6, 7],
+                    help="reflection-chain schedule: 0 inline in k_resolve, 1 wavefront queues, 2 k_chain overlapped with the shadow pass, 3 warp per path, 4 staged first bounce, 5 = 2 + the resolve does not wait for the chain, 6 persistent wavefront, 7 = 5 with the paths split by predicted length (default)")
     ap.add_argument("--fuse-denoise", action="store_true", help="run blur.comp inside the resolve kernel instead of as its own pass (A/B)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="wall seconds the parity / cpu_baseline oracle leg may take")
     args = ap.parse_args()
@@ -295,9 +272,8 @@ def main():
     import torch
     import torch.distributed as dist
     from vulkanhybridraytracer_b200 import PLANE
-    nccl_dir = None
     if world > 1:
-        nccl_dir = nccl_debug_to_file(rank)
+        nccl_debug_to_stderr()
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = local if world > 1 else 0
@@ -354,6 +330,7 @@ def main():
 
     ctx.set_params(params(0)); ctx.reset_history()
     frame = 0
+    sampler = ClockSampler(dev); sampler.start()      # nvidia-smi starts before the warm-up: the timed region itself is a few tens of ms
     for _ in range(args.warmup):                      # warm-up: frame 0 (reset frame, with its halo exchange for N > 1) .. W-1
         tr.render(params(frame))
         if world > 1:
@@ -368,7 +345,6 @@ def main():
     trav = np.zeros(3, dtype=np.int64)
     launches = 0
     frame_times = []
-    sampler = ClockSampler(dev); sampler.start()
     barrier()
     total_ms = 0.0
     if world == 1:
@@ -416,7 +392,6 @@ def main():
             stage_ms += np.array(list(c.ms_stage)) * (args.steps / n_prof)
             frame += 1
     barrier()
-    clocks = sampler.stop()
     # one extra, untimed frame with traversal accounting on: what the rays actually requested from memory
     ctx.set_profiling(2)
     tr.render(params(frame))
@@ -435,6 +410,19 @@ def main():
     ms_per_step = total_ms / args.steps
     counted = int(rays_all[1] + rays_all[2] + rays_all[3])
     value = counted / args.steps / (ms_per_step * 1e-3) / 1e6
+
+    # -- clocks: K timed frames are over in 10-30 ms, less than one nvidia-smi sampling period.  The same frames go on, untimed, until
+    #    the GPU has been under this load for ~0.7 s since the warm-up began (the same count on every rank), and the sampler -- started
+    #    before the warm-up -- reports the median over that whole window: warm-up + timed frames + hold frames of one workload.
+    hold = int(min(4000, max(0.0, 700.0 - args.steps * ms_per_step) / max(ms_per_step, 1e-3)))
+    for _ in range(hold):
+        tr.render(params(frame))
+        if world > 1:
+            composite()
+        frame += 1
+    barrier()
+    clocks = sampler.stop()
+    clocks["window"] = f"warm-up ({args.warmup}) + timed ({args.steps}) + {hold} untimed frames of the same workload, nvidia-smi -lms 100"
 
     # -- N > 1: the composited image must be bit-identical to the same frame sequence rendered on one GPU ---------------------------
     composite_ok = None
@@ -597,7 +585,7 @@ def main():
     comm_nranks = None
     if world > 1:
         dist.barrier()
-        comm_nranks = replay_nccl_log(nccl_dir) if rank == 0 else None
+        comm_nranks = dist.get_world_size()          # NCCL's own "nranks" lines are on stderr (nccl_debug_to_stderr)
     if rank != 0:
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
@@ -672,13 +660,13 @@ def main():
                                    "secondary_shadow": int(rays_all[3] // args.steps), "primary_not_counted": int(rays_all[0] // args.steps)},
                 "mrays_s_incl_primary": float(rays_all.sum()) / args.steps / (ms_per_step * 1e-3) / 1e6,
                 "nominal_2P_mrays_s": 2 * P / (ms_per_step * 1e-3) / 1e6,
-                "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise", 3: "k_chain_warp (one warp per queued path, cooperative traversal) on a second stream", 4: "staged chain on a second stream overlapping k_shadow + k_denoise: first bounce as a wavefront (k_chain_first, k_chain_shadow0, k_chain_shade0), continuing paths compacted (k_chain_rest)", 5: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges the chain into the mirror / glass pixels", 6: "k_chain_q: persistent queue-fed grid, one bounce per work item, scattered paths appended to the queue (ballot / prefix compaction), on a second stream overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges it"}[args.chain],
+                "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise", 3: "k_chain_warp (one warp per queued path, cooperative traversal) on a second stream", 4: "staged chain on a second stream overlapping k_shadow + k_denoise: first bounce as a wavefront (k_chain_first, k_chain_shadow0, k_chain_shade0), continuing paths compacted (k_chain_rest)", 5: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges the chain into the mirror / glass pixels", 6: "k_chain_q: persistent queue-fed grid, one bounce per work item, scattered paths appended to the queue (ballot / prefix compaction), on a second stream overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges it", 7: "paths split by last frame's length: the long ones first in k_chain (persistent, queue-fed), the others through the staged kernels (k_chain_first / _shadow0 / _shade0 / _rest) on a third stream, both overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges them"}[args.chain],
                 "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
                 "parallelism": (f"tiles {TW}x{TH} dealt over {world} GPU(s), replicated BVH, " +
                                 ("resolve kernels store sRGB8 pixels straight into rank 0's image over NVLink peer memory (CUDA IPC) + a device-side flag barrier"
                                  if peer else "pack + NCCL gather of sRGB8 tiles + unpack")) if world > 1 else "1 GPU",
                 "composite_bit_identical_to_1gpu": composite_ok,
-                "comm_nranks_seen": comm_nranks,
+                "comm_world_size": comm_nranks,
                 "timing": "CUDA events on the context stream around each frame, summed over K frames, max over ranks"},
         "frame_ms": stats_ms(frame_times),
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "build": build, "cfg3": cfg3, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),

@@ -89,7 +89,9 @@ typedef struct vkp_params {
                                         5 = as 2, and the resolve does not wait for the chain either: mirror / glass pixels are finished by
                                             k_resolve_paths once the chain is there (the chain overlaps shadow + denoise + resolve),
                                         6 = as 5 with the chain as a persistent wavefront: one bounce per work item, a queue-fed persistent
-                                            grid, scattered paths appended to the queue (ballot / prefix compaction) instead of looping */
+                                            grid, scattered paths appended to the queue (ballot / prefix compaction) instead of looping,
+                                        7 = as 5 with the paths split by what they did in the previous frame: those that went beyond their first
+                                            bounce start first in k_chain, the others go through the lean staged kernels of 4 on a third stream */
     int32_t fuse_denoise;            /* vkp_render (Hybrid): run blur.comp inside the resolve kernel instead of as its own pass */
     int32_t reproject_fix;           /* blur.comp:52-53 on a reset frame.  0 (default): the reference's history fetch, pixel + motion.x * (W, H)
                                         (twice the right distance, x component used for both axes).

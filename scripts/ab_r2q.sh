@@ -1,7 +1,6 @@
-TAG=r2u; . scripts/ab_r2n.sh
-run base A=1
-runf() { name=$1; shift
-  env "$@" timeout 200 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-cfg3 --fuse-denoise > gpurun_out/${TAG}_$name.json 2> gpurun_out/${TAG}_$name.err
+TAG=r2y; . scripts/ab_r2n.sh
+run7() { name=$1; shift
+  env "$@" timeout 200 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-cfg3 --chain 7 > gpurun_out/${TAG}_$name.json 2> gpurun_out/${TAG}_$name.err
   python - <<PY
 import json
 for l in open("gpurun_out/${TAG}_$name.json"):
@@ -9,4 +8,7 @@ for l in open("gpurun_out/${TAG}_$name.json"):
         d=json.loads(l); print("%-14s ms %.4f min %.4f stages %s chain %.3f e2e %.4f" % ("$name", d["ms_per_step"], d["frame_ms"]["min"], {k[2:]:round(v,3) for k,v in d["roofline"]["stage_ms_all"].items()}, d["roofline"].get("chain_stream_ms",0), d["e2e"]["ms_per_step"]))
 PY
 }
-runf fused A=1
+run7 c7 A=1
+run7 c7_low2 VKP_CHAIN2_PRIO=low
+run7 c7_ct6 VKP_LIB=$PWD/variants/ct6/libvkp.so
+run7 c7_ct5 VKP_LIB=$PWD/variants/ct5/libvkp.so

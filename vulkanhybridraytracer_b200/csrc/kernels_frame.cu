@@ -34,6 +34,9 @@
 #ifndef VKP_CHAIN_CALL
 #define VKP_CHAIN_CALL 0      /* 1: k_chain calls the traversal (trace_ray_call) instead of inlining it */
 #endif
+#ifndef VKP_LB_CHAIN_TRACE
+#define VKP_LB_CHAIN_TRACE 8  /* the lean traversal kernels of the staged chain (k_chain_first, k_chain_shadow0) */
+#endif
 #ifndef VKP_LB_CHAIN
 #define VKP_LB_CHAIN 3        /* 168 registers: the sparse chain kernel gains nothing from occupancy, a lot from not spilling */
 #endif
@@ -732,9 +735,26 @@ __global__ void __launch_bounds__(128) k_chain_scan(const __grid_constant__ DSce
         const float matIdx = vkp_f16_to_f32((uint16_t)(F.position[i].y >> 16));
         path = (int)material_by_float_index(S, matIdx).shadingMetallicRoughness[0] != 0 && F.p.max_bounces > 0;
     }
+    const int lane = threadIdx.x & 31;
+    if (F.chain_split) {
+        // schedule 7: two path lists in one array.  Paths that went beyond their first bounce in the previous frame (chain_long, one byte
+        // per pixel, written by the chain kernels) are queued from slot 0 upwards for k_chain -- the few long paths start first --
+        // the others from the last slot downwards for the staged kernels.  A wrong prediction costs time, never a bit.
+        const bool lng = path && F.chain_long[i] != 0;
+        const bool sht = path && !lng;
+        const unsigned ml = __ballot_sync(0xffffffffu, lng), ms = __ballot_sync(0xffffffffu, sht);
+        unsigned bl = 0, bs = 0;
+        if (ml && lane == __ffs(ml) - 1) bl = atomicAdd(&F.path_count[0], (unsigned)__popc(ml));
+        if (ms && lane == __ffs(ms) - 1) bs = atomicAdd(&F.path_count[4], (unsigned)__popc(ms));
+        if (ml) bl = __shfl_sync(0xffffffffu, bl, __ffs(ml) - 1);
+        if (ms) bs = __shfl_sync(0xffffffffu, bs, __ffs(ms) - 1);
+        if (lng) { const unsigned slot = bl + __popc(ml & ((1u << lane) - 1u)); F.chain_slot[i] = (int)slot; F.chain_pix[slot] = (int)i; }
+        if (sht) { const unsigned slot = F.chain_cap - 1u - (bs + __popc(ms & ((1u << lane) - 1u))); F.chain_slot[i] = (int)slot; F.chain_pix[slot] = (int)i; }
+        return;
+    }
     const unsigned mask = __ballot_sync(0xffffffffu, path);
     if (mask == 0u) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    const int leader = __ffs(mask) - 1;
     unsigned base = 0;
     if (lane == leader) base = atomicAdd(&F.path_count[0], (unsigned)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
@@ -744,6 +764,10 @@ __global__ void __launch_bounds__(128) k_chain_scan(const __grid_constant__ DSce
         F.chain_pix[slot] = (int)i;
     }
 }
+
+// the staged kernels' path list: slots [0, path_count[0]) (schedule 4) or, counted downwards from the last slot, path_count[4] of them (7)
+__device__ __forceinline__ unsigned int staged_count(const DFrame& F) { return F.chain_split ? F.path_count[4] : F.path_count[0]; }
+__device__ __forceinline__ unsigned int staged_slot(const DFrame& F, unsigned int k) { return F.chain_split ? F.chain_cap - 1u - k : k; }
 
 // the first reflection / refraction ray of a queued path, from the G-buffer (origin already offset along the direction)
 __device__ __forceinline__ void chain_first_ray(const DScene& S, const DFrame& F, size_t i, float3& ro, float3& direction)
@@ -815,6 +839,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain(const __
             origin = prd.origin; direction = prd.direction;
         }
         F.chain_len[slot] = n;
+        if (F.chain_long) F.chain_long[i] = n > 1 ? 1 : 0;
         }
         __syncwarp();
     }
@@ -1013,15 +1038,16 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_warp(con
 // Records live in path_q[0] (by slot) and path_q[1] (continuing paths); path_count[2] counts the latter.  Same arithmetic in the
 // same order as k_chain: every stored colour is bit-identical.
 //   record.a = ray origin (already offset), t of the hit or -1     record.b = direction, u     record.c = v, instance, primitive, mask
-__global__ void __launch_bounds__(VKP_TRAV_BLOCK, 8) k_chain_first(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN_TRACE) k_chain_first(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
     uint32_t* const sstack = s_trav + threadIdx.x;
-    const unsigned int n_paths = F.path_count[0];
+    const unsigned int n_paths = staged_count(F);
     unsigned int n_refl = 0;
     TravCount tc = {0u, 0u, 0u};
     TravCount* const tcp = F.count_trav ? &tc : nullptr;
-    for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_paths; k += gridDim.x * blockDim.x) {
+        const unsigned int slot = staged_slot(F, k);
         const size_t i = (size_t)F.chain_pix[slot];
         float3 ro, direction;
         chain_first_ray(S, F, i, ro, direction);
@@ -1052,17 +1078,18 @@ __device__ __forceinline__ void hit_normal_pos(const DScene& S, float3 rayO, flo
 }
 
 // blockIdx.y = light.  hybridHit.rchit:99-131: a diffuse hit facing a light within its range traces one any-hit ray towards it.
-__global__ void __launch_bounds__(VKP_TRAV_BLOCK, 8) k_chain_shadow0(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN_TRACE) k_chain_shadow0(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
     uint32_t* const sstack = s_trav + threadIdx.x;
-    const unsigned int n_paths = F.path_count[0];
+    const unsigned int n_paths = staged_count(F);
     const int l = (int)blockIdx.y;
     unsigned int n_sec = 0;
     TravCount tc = {0u, 0u, 0u};
     TravCount* const tcp = F.count_trav ? &tc : nullptr;
     const bool advance = F.p.faithful_rng == 0;
-    for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_paths; k += gridDim.x * blockDim.x) {
+        const unsigned int slot = staged_slot(F, k);
         PathItem* rec = F.path_q[0] + slot;
         const float4 a = rec->a;
         if (a.w < 0.0f) continue;                                       // the first ray missed: sky
@@ -1094,13 +1121,14 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, 8) k_chain_shadow0(const __gri
 
 __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_shade0(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
-    const unsigned int n_paths = F.path_count[0];
+    const unsigned int n_paths = staged_count(F);
     const unsigned int n_round = (n_paths + 31u) & ~31u;              // whole warps stay in the loop so that the ballots are convergent
     unsigned int n_sec = 0;
-    for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_round; slot += gridDim.x * blockDim.x) {
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
         bool again = false;
         PathItem item;
-        if (slot < n_paths) {
+        if (k < n_paths) {
+            const unsigned int slot = staged_slot(F, k);
             const PathItem* rec = F.path_q[0] + slot;
             const float4 a = rec->a, b = rec->b, c = rec->c;
             const size_t i = (size_t)F.chain_pix[slot];
@@ -1115,6 +1143,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_shade0(c
             } else shade_miss(S, direction, prd);
             F.chain_buf[(size_t)slot * VKP_CHAIN_MAX] = make_float4(prd.color.x, prd.color.y, prd.color.z, 0.0f);
             again = hit && (prd.scatter > 0.0f) && F.p.max_bounces > 1;
+            if (F.chain_long) F.chain_long[i] = again ? 1 : 0;
             if (!again) F.chain_len[slot] = 1;
             else {
                 item.a = make_float4(prd.origin.x, prd.origin.y, prd.origin.z, __uint_as_float(slot));
@@ -1298,7 +1327,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_RESOLVE) k_resolve(cons
             }
         }
         if (CHAIN == 3 && wants_path) {
-            PathItem* rec = F.path_q[0] + F.chain_slot[i];      // (path_q[1] is the continuation queue of schedule 6)
+            PathItem* rec = F.chain_base + F.chain_slot[i];
             rec->c = make_float4(rayColor.x, rayColor.y, rayColor.z, background ? 1.0f : 0.0f);
             rec->d = background ? make_float4(albedo.x, albedo.y, albedo.z, 0.0f) : make_float4(tail.x, tail.y, tail.z, 0.0f);
         } else if (CHAIN != 1 || !wants_path) {
@@ -1373,10 +1402,11 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK) k_bounce(const __grid_constant
 // bounce order, + ambient tail (or the sky albedo); one thread per path slot
 __global__ void __launch_bounds__(128) k_resolve_paths(const __grid_constant__ DFrame F)
 {
-    const unsigned int n_paths = F.path_count[0];
-    for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
+    const unsigned int n_low = F.path_count[0], n_paths = n_low + (F.chain_split ? F.path_count[4] : 0u);
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_paths; k += gridDim.x * blockDim.x) {
+        const unsigned int slot = k < n_low ? k : F.chain_cap - 1u - (k - n_low);
         const size_t i = (size_t)F.chain_pix[slot];
-        const float4 c0 = F.path_q[0][slot].c, t0 = F.path_q[0][slot].d;
+        const float4 c0 = F.chain_base[slot].c, t0 = F.chain_base[slot].d;
         float3 rayColor = f3(c0.x, c0.y, c0.z);
         const float4* rec = F.chain_buf + (size_t)slot * VKP_CHAIN_MAX;
         const int n = F.chain_len[slot];
@@ -1639,6 +1669,16 @@ __global__ void k_tiles_copy(E* __restrict__ plane, E* __restrict__ packed, int 
     }
 }
 
+// Brings a range into L2 without touching registers or L1 (prefetch.global.L2, one 128-byte line per thread iteration).  The frame
+// kernels are bound by chains of DEPENDENT node fetches -- the longest ray of a kernel sets its floor -- and every one of those that
+// misses L2 costs a round trip to HBM; streaming the 24 MB BVH arena in takes a few microseconds of bandwidth instead.
+__global__ void k_prefetch_l2(const char* __restrict__ p, size_t bytes)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 128u;
+    for (size_t off = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128u; off < bytes; off += stride)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+}
+
 __global__ void k_l2_flush(uint4* buf, size_t n)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1775,7 +1815,7 @@ cudaError_t launch_resolve(const FrameLaunch& L, int* launches)
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
-    if (L.frame.p.wavefront == 5 || L.frame.p.wavefront == 6) {
+    if (L.frame.p.wavefront >= 5) {
         k_resolve<3><<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame);     // needs k_chain_scan only; launch_resolve_paths follows the chain
         if (launches) *launches += 1;
         return cudaGetLastError();
@@ -1802,11 +1842,23 @@ cudaError_t launch_resolve_paths(const FrameLaunch& L)
     k_resolve_paths<<<frame_grid(L).x / 4u + 1u, 128, 0, L.stream>>>(L.frame);
     return cudaGetLastError();
 }
+// schedule 7, second half: the staged kernels over the paths predicted to end after one bounce, on their own stream beside k_chain
+cudaError_t launch_chain_staged(const FrameLaunch& L, cudaStream_t stream)
+{
+    const unsigned int px_blocks = frame_grid(L).x;
+    const unsigned int g1 = px_blocks / 4u + 1u, g2 = px_blocks / 16u + 1u;
+    k_chain_first<<<g1, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    if (L.scene.n_lights > 0) k_chain_shadow0<<<dim3(g1, (unsigned)L.scene.n_lights), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    k_chain_shade0<<<g1, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    k_chain_rest<<<g2, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t after_scan, uint32_t tag, unsigned int cont_cap)
 {
     // path_count[0] = number of paths, [1] = head of the queue the persistent warps of mode 3 pull from
     // [2] = number of paths that go on after their first bounce (staged chain, mode 4)
-    cudaError_t e = launch_stage_words(stream, L.frame.path_count, nullptr, 4 * sizeof(unsigned int));
+    cudaError_t e = launch_stage_words(stream, L.frame.path_count, nullptr, 5 * sizeof(unsigned int));
     if (e != cudaSuccess) return e;
     k_chain_scan<<<frame_grid(L), 128, 0, stream>>>(L.scene, L.frame);
     if (after_scan && (e = cudaEventRecord(after_scan, stream)) != cudaSuccess) return e;
@@ -1960,6 +2012,13 @@ cudaError_t launch_sync_wait(cudaStream_t s, const uint32_t* flags, int count, u
 {
     if (count <= 0) return cudaSuccess;
     k_sync_wait<<<1, 64, 0, s>>>(flags, count, value, timeout_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prefetch_l2(cudaStream_t s, const void* p, size_t bytes)
+{
+    if (!p || !bytes) return cudaSuccess;
+    k_prefetch_l2<<<592, 256, 0, s>>>(static_cast<const char*>(p), bytes);
     return cudaGetLastError();
 }
 

@@ -66,6 +66,10 @@ struct vkp_ctx {
     DevBuf position, normal, albedo, motion, material, emissive, hit_ids, final_f32, final_srgb8, shadow, denoised[2];
     int denoised_cur = 0;
     int plane_w = 0, plane_h = 0, plane_lights = 0;
+    DevBuf chain_long;                // one byte per pixel: last frame's path went beyond its first bounce (chain schedule 7)
+    cudaStream_t chain_stream2 = nullptr;
+    cudaEvent_t ev_chain2 = nullptr;
+    bool chain2_in_flight = false;
     DevBuf atrous[2];                 // ping-pong planes of the a-trous shadow filter (vkp_params.denoiser = 1)
     DevBuf counters, io_tmp, io_tmp2, flush, path_q[2], path_count, luts, chain_buf, chain_len, chain_slot, chain_pix;
     cudaStream_t chain_stream = nullptr;
@@ -80,6 +84,8 @@ struct vkp_ctx {
     cudaStream_t order_stream = nullptr;
     cudaEvent_t ev_stage_done[2] = {nullptr, nullptr}, ev_order_done[2] = {nullptr, nullptr};
     int schedule = 1;                 // 0 = hardware block order, 1 = longest first (VKP_SCHEDULE=0|1)
+    int prefetch = 0;                 // VKP_PREFETCH: 1 = stream the BVH arena into L2 at the start of every frame, 2 = vertex / index buffers too
+    cudaEvent_t ev_prefetch = nullptr;
     bool use_seed_plane = true;       // k_gbuffer evaluates TEA once per pixel for the frame's later stages (VKP_SEED_PLANE=0: every stage evaluates it)
     bool chain_in_flight = false;
     // multi-GPU: FINAL_SRGB8 is double-buffered (vkp_set_output_buffer) and may be redirected into rank 0's two buffers over NVLink
@@ -217,6 +223,7 @@ int ensure_planes(vkp_ctx* ctx)
     CK(ctx->path_q[0].ensure(px * sizeof(PathItem))); CK(ctx->path_q[1].ensure(px * sizeof(PathItem)));
     CK(ctx->path_count.ensure(sizeof(unsigned int) * (VKP_MAX_BOUNCES + 2)));
     CK(ctx->chain_buf.ensure(px * sizeof(float4) * VKP_CHAIN_MAX)); CK(ctx->chain_len.ensure(px * sizeof(int))); CK(ctx->chain_slot.ensure(px * sizeof(int))); CK(ctx->chain_pix.ensure(px * sizeof(int)));
+    CK(ctx->chain_long.ensure(px)); CK(cudaMemsetAsync(ctx->chain_long.p, 0, px, ctx->stream));
     ctx->plane_w = W; ctx->plane_h = H; ctx->plane_lights = L;
     // defined initial state: history and accumulation start at zero (blur.comp:73 reads uninitialised memory upstream)
     CK(cudaMemsetAsync(ctx->position.p, 0, px * 8, ctx->stream)); CK(cudaMemsetAsync(ctx->normal.p, 0, px * 8, ctx->stream));
@@ -364,6 +371,10 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.path_count = ctx->path_count.as<unsigned int>();
     F.lut_pow22 = ctx->luts.as<float>(); F.lut_post = ctx->luts.as<uint8_t>() + 1024;
     F.chain_buf = ctx->chain_buf.as<float4>(); F.chain_len = ctx->chain_len.as<int>(); F.chain_slot = ctx->chain_slot.as<int>(); F.chain_pix = ctx->chain_pix.as<int>();
+    F.chain_base = F.p.wavefront == 6 ? F.path_q[0] : F.path_q[1];       // path_q[1] is schedule 6's continuation queue, path_q[0] holds the staged kernels' records
+    F.chain_long = ctx->chain_long.as<uint8_t>();
+    F.chain_split = F.p.wavefront == 7 ? 1 : 0;
+    F.chain_cap = (unsigned int)((size_t)F.p.width * F.p.height);
     const int total = F.tiles_x * F.tiles_y;
     L.n_own_tiles = total > F.rank ? (total - F.rank + F.world - 1) / F.world : 0;
     F.n_cta = L.n_own_tiles * (F.tile_w >> 4) * (F.tile_h >> 3);
@@ -425,7 +436,7 @@ int apply_l2_window(vkp_ctx* ctx)
         attr.accessPolicyWindow.num_bytes = 0;      // disables the window
         attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal; attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
     }
-    cudaStream_t streams[] = {ctx->stream, ctx->own_stream, ctx->chain_stream};
+    cudaStream_t streams[] = {ctx->stream, ctx->own_stream, ctx->chain_stream, ctx->chain_stream2};
     for (cudaStream_t st : streams) if (st) CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
     if (!on && ctx->l2_set_aside) { cudaCtxResetPersistingL2Cache(); }
     return VKP_OK;
@@ -521,8 +532,11 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
     case VKP_STAGE_RESOLVE: {
         int n = 0;
         const bool chain2 = L.frame.p.wavefront >= 2 && L.frame.p.max_bounces <= VKP_CHAIN_MAX;
-        const bool late = chain2 && (L.frame.p.wavefront == 5 || L.frame.p.wavefront == 6);      // the resolve does not wait for the chain: k_resolve_paths merges it afterwards
-        if (chain2 && !ctx->chain_in_flight) { CK(launch_chain(L, ctx->stream, nullptr, ++ctx->chain_tag, chain_cont_cap(ctx))); ctx->last_launches += chain_launches(L); }      // stand-alone stage: serial (clear + scan + chain)
+        const bool late = chain2 && L.frame.p.wavefront >= 5;      // the resolve does not wait for the chain: k_resolve_paths merges it afterwards
+        if (chain2 && !ctx->chain_in_flight) {
+            CK(launch_chain(L, ctx->stream, nullptr, ++ctx->chain_tag, chain_cont_cap(ctx))); ctx->last_launches += chain_launches(L);
+            if (L.frame.p.wavefront == 7) { CK(launch_chain_staged(L, ctx->stream)); ctx->last_launches += L.scene.n_lights > 0 ? 4u : 3u; }
+        }      // stand-alone stage: serial (clear + scan + chain)
         if (chain2 && ctx->chain_in_flight && !late) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0)); ctx->chain_in_flight = false; }
         if (late && ctx->chain_in_flight) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_scan, 0));
         CK(launch_resolve(L, &n));
@@ -592,9 +606,15 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
         const char* cp = getenv("VKP_CHAIN_PRIO");
         cudaStreamCreateWithPriority(&ctx->chain_stream, cudaStreamNonBlocking, (cp && strcmp(cp, "low") == 0) ? lo : hi);
         cudaStreamCreateWithPriority(&ctx->order_stream, cudaStreamNonBlocking, hi);
+        {
+            const char* c2 = getenv("VKP_CHAIN2_PRIO");          // A/B knob: "low" = the staged kernels of schedule 7 at the main stream's priority
+            cudaStreamCreateWithPriority(&ctx->chain_stream2, cudaStreamNonBlocking, (c2 && strcmp(c2, "low") == 0) ? lo : hi);
+        }
+        cudaEventCreateWithFlags(&ctx->ev_chain2, cudaEventDisableTiming);
         for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags(&ctx->ev_stage_done[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_order_done[k], cudaEventDisableTiming); }
         if (const char* e = getenv("VKP_SCHEDULE")) ctx->schedule = atoi(e) != 0;
         if (const char* e = getenv("VKP_SEED_PLANE")) ctx->use_seed_plane = atoi(e) != 0;
+        if (const char* e = getenv("VKP_PREFETCH")) ctx->prefetch = atoi(e);
         cudaEventCreateWithFlags(&ctx->ev_gbuffer, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_scan, cudaEventDisableTiming);
@@ -645,7 +665,7 @@ void vkp_destroy(vkp_ctx* ctx)
     if (ctx->ev_updated) cudaEventDestroy(ctx->ev_updated);
     DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_textures, &ctx->position, &ctx->seed, &ctx->normal, &ctx->albedo, &ctx->motion,
                       &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
-                      &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->chain_pix, &ctx->final_srgb8_alt};
+                      &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->chain_pix, &ctx->chain_long, &ctx->final_srgb8_alt};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->timer0) cudaEventDestroy(ctx->timer0);
@@ -666,6 +686,9 @@ void vkp_destroy(vkp_ctx* ctx)
     if (ctx->ev_gbuffer) cudaEventDestroy(ctx->ev_gbuffer);
     if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
     if (ctx->ev_scan) cudaEventDestroy(ctx->ev_scan);
+    if (ctx->ev_prefetch) cudaEventDestroy(ctx->ev_prefetch);
+    if (ctx->ev_chain2) cudaEventDestroy(ctx->ev_chain2);
+    if (ctx->chain_stream2) cudaStreamDestroy(ctx->chain_stream2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -949,7 +972,7 @@ int vkp_set_params(vkp_ctx* ctx, const vkp_params* p)
     if (p->max_bounces > VKP_MAX_BOUNCES) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: max_bounces > 64");
     if (p->spp < 1 || p->shadow_samples < 1 || p->max_bounces < 0) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: spp / shadow_samples must be >= 1");
     if (p->denoiser < 0 || p->denoiser > 1) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: denoiser is 0 (blur.comp) or 1 (a-trous)");
-    if (p->wavefront < 0 || p->wavefront > 6) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: wavefront (chain schedule) is 0 .. 6");
+    if (p->wavefront < 0 || p->wavefront > 7) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: wavefront (chain schedule) is 0 .. 7");
     ctx->params = *p; ctx->have_params = true;
     return VKP_OK;
 }
@@ -977,6 +1000,18 @@ int vkp_render(vkp_ctx* ctx)
         ctx->copy_pending[b] = false;
     }
     if (!ctx->accumulate_counters) CK(launch_stage_words(ctx->stream, ctx->counters.p, nullptr, 64));
+    if (ctx->prefetch > 0) {
+        // the BVH arena (nodes + leaf triangles of every BLAS) into L2 ahead of the traversals; level 2 adds the vertex and index
+        // buffers the hit shaders read.  On a side stream: the first primary rays do not wait for it.
+        if (!ctx->ev_prefetch) { CK(cudaEventCreateWithFlags(&ctx->ev_prefetch, cudaEventDisableTiming)); }
+        cudaStream_t ps = ctx->order_stream ? ctx->order_stream : ctx->stream;
+        CK(cudaEventRecord(ctx->ev_prefetch, ctx->stream));
+        CK(cudaStreamWaitEvent(ps, ctx->ev_prefetch, 0));
+        CK(launch_prefetch_l2(ps, ctx->bvh_arena.p, ctx->bvh_arena.bytes));
+        ctx->last_launches++;
+        if (ctx->prefetch > 1)
+            for (auto& m : ctx->meshes) { CK(launch_prefetch_l2(ps, m->verts.p, m->verts.bytes)); CK(launch_prefetch_l2(ps, m->idx.p, m->idx.bytes)); ctx->last_launches += 2; }
+    }
     static const int hybrid[] = {VKP_STAGE_GBUFFER, VKP_STAGE_SHADOW, VKP_STAGE_DENOISE, VKP_STAGE_RESOLVE};
     static const int hybrid_fused[] = {VKP_STAGE_GBUFFER, VKP_STAGE_SHADOW, VKP_STAGE_RESOLVE};
     static const int rt[] = {VKP_STAGE_RAYTRACE};
@@ -1002,6 +1037,14 @@ int vkp_render(vkp_ctx* ctx)
                 CK(cudaEventRecord(ctx->ev_chain_t0, ctx->chain_stream));
             }
             CK(launch_chain(L, ctx->chain_stream, ctx->ev_scan, ++ctx->chain_tag, chain_cont_cap(ctx)));
+            if (ctx->params.wavefront == 7) {
+                // the bulk of the paths (predicted to end after one bounce) through the lean staged kernels, beside k_chain's long ones
+                CK(cudaStreamWaitEvent(ctx->chain_stream2, ctx->ev_scan, 0));
+                CK(launch_chain_staged(L, ctx->chain_stream2));
+                CK(cudaEventRecord(ctx->ev_chain2, ctx->chain_stream2));
+                CK(cudaStreamWaitEvent(ctx->chain_stream, ctx->ev_chain2, 0));       // ev_chain below then means: both halves are done
+                ctx->last_launches += L.scene.n_lights > 0 ? 4u : 3u;
+            }
             if (ctx->profiling) { CK(cudaEventRecord(ctx->ev_chain_t1, ctx->chain_stream)); ctx->chain_timed = true; }
             CK(cudaEventRecord(ctx->ev_chain, ctx->chain_stream));
             ctx->chain_in_flight = true;

@@ -176,6 +176,10 @@ struct DFrame {
     int* chain_len;                 // chain mode 2: number of bounces traced per path
     int* chain_slot;                // chain mode 2: per-pixel path slot (written for mirror / glass pixels only)
     int* chain_pix;                 // chain mode 2: pixel index of every path slot (the queue k_chain's warps pull from)
+    PathItem* chain_base;           // schedules 5-7: per path slot, the direct term (c) and the ambient tail (d) k_resolve<3> leaves for k_resolve_paths
+    uint8_t* chain_long;            // per pixel: the path of this pixel went beyond its first bounce in the previous frame (schedule 7's prediction)
+    int chain_split;                // schedule 7: two path lists (see k_chain_scan)
+    unsigned int chain_cap;         // slots in the path arrays (= pixels)
     // longest-first CTA scheduling: cost[v] = SM cycles the slowest warp of virtual block v took in the
     // previous frame, order[b] = the virtual block hardware block b works on (NULL = identity).  [0] k_gbuffer, [1] k_shadow.
     const uint32_t* cta_order[2];

@@ -92,6 +92,7 @@ struct FrameLaunch {
     int n_own_tiles;
 };
 cudaError_t launch_set_carveout(int pct);
+cudaError_t launch_prefetch_l2(cudaStream_t s, const void* p, size_t bytes);
 cudaError_t launch_gbuffer(const FrameLaunch& L);
 cudaError_t launch_shadow(const FrameLaunch& L);
 cudaError_t launch_denoise(const FrameLaunch& L, uint8_t* atrous_a = nullptr, uint8_t* atrous_b = nullptr);
@@ -99,6 +100,7 @@ cudaError_t launch_build_order(cudaStream_t s, uint32_t* cost, uint32_t* order, 
 cudaError_t launch_resolve(const FrameLaunch& L, int* launches);
 cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t after_scan = nullptr, uint32_t tag = 1u, unsigned int cont_cap = 0u);
 cudaError_t launch_resolve_paths(const FrameLaunch& L);
+cudaError_t launch_chain_staged(const FrameLaunch& L, cudaStream_t stream);
 cudaError_t launch_post(const FrameLaunch& L);
 cudaError_t launch_raytrace(const FrameLaunch& L);
 cudaError_t launch_deferred(const FrameLaunch& L);

@@ -298,7 +298,7 @@ public:
     int _maxBounces{8};
     bool _faithfulRng{true};
     bool _reprojectFix{false};          // vkp_params.reproject_fix: false = the reference's blur.comp history fetch, true = the previous frame's pixel
-    int _chainMode{5};                  // vkp_params.wavefront: how the reflection chain is scheduled (0 inline, 1 wavefront, 2 overlapped, 5 overlapped + late merge)
+    int _chainMode{7};                  // vkp_params.wavefront: how the reflection chain is scheduled (include/vkp_types.h; 7 = split by predicted length, overlapped, late merge)
 
     // headless replacement of Window::input_update (window.cpp:40-110): called at the top of every frame of run(), before
     // update(); a script moves the camera there (Camera::processKeyboard / rotate), which resets the accumulation like a key press does
