@@ -203,11 +203,14 @@ def parity_and_cpu_baseline(vk, ctx, scene, name, chain, budget_s):
 def nccl_debug_to_stderr():
     """The driver checks the communicator size from NCCL's own log ("... nranks N ...").  NCCL writes that log to stdout by default,
     where the contract wants exactly one JSON line: NCCL_DEBUG_FILE=/dev/stderr sends every rank's INIT lines to stderr instead
-    (torchrun forwards them).  Nothing is overridden if the caller has set these variables."""
-    os.environ.setdefault("NCCL_DEBUG", "INFO")
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("INFO", "TRACE"):
+    (torchrun forwards them).  A caller's INFO / TRACE setting, subsystem list and log file are kept."""
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):      # unset, or VERSION / WARN (this image presets VERSION): no "nranks" lines
+        os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("RANK", "0") == "0":
+        print("bench.py: NCCL_DEBUG=%s NCCL_DEBUG_SUBSYS=%s NCCL_DEBUG_FILE=%s" % tuple(os.environ.get(k) for k in ("NCCL_DEBUG", "NCCL_DEBUG_SUBSYS", "NCCL_DEBUG_FILE")),
+              file=sys.stderr, flush=True)
 
 
 def load_ncu_measured():
@@ -242,6 +245,8 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and args.impl != "reference":
+        nccl_debug_to_stderr()       # before torch (and with it libnccl) is loaded: NCCL caches its debug settings on first use
     scene_idx, W, H, mode, spp, samples, faithful, desc = WORKLOADS[args.workload]
     peak, peak_src = measured_peak()
 
@@ -273,7 +278,6 @@ def main():
     import torch.distributed as dist
     from vulkanhybridraytracer_b200 import PLANE
     if world > 1:
-        nccl_debug_to_stderr()
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = local if world > 1 else 0

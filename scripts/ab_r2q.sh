@@ -1,4 +1,4 @@
-TAG=r2y; . scripts/ab_r2n.sh
+TAG=r3b; . scripts/ab_r2n.sh
 run7() { name=$1; shift
   env "$@" timeout 200 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-cfg3 --chain 7 > gpurun_out/${TAG}_$name.json 2> gpurun_out/${TAG}_$name.err
   python - <<PY
@@ -9,6 +9,4 @@ for l in open("gpurun_out/${TAG}_$name.json"):
 PY
 }
 run7 c7 A=1
-run7 c7_low2 VKP_CHAIN2_PRIO=low
-run7 c7_ct6 VKP_LIB=$PWD/variants/ct6/libvkp.so
-run7 c7_ct5 VKP_LIB=$PWD/variants/ct5/libvkp.so
+run7 c7_warp VKP_CHAIN_LONG_WARP=1

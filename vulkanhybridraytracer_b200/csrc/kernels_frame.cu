@@ -1018,7 +1018,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_warp(con
             if (!hit || !(prd.scatter > 0.0f)) break;
             origin = prd.origin; direction = prd.direction;
         }
-        if (lane == 0) F.chain_len[slot] = n;
+        if (lane == 0) { F.chain_len[slot] = n; if (F.chain_long) F.chain_long[i] = n > 1 ? 1 : 0; }
     }
     add_counter(F.counters, 2, lane == 0 ? n_refl : 0u);       // the rays are the warp's: count them once
     add_counter(F.counters, 3, lane == 0 ? n_sec : 0u);
@@ -1854,6 +1854,14 @@ cudaError_t launch_chain_staged(const FrameLaunch& L, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+static bool chain_long_by_warp(int world)
+{
+    static int forced = -2;
+    if (forced == -2) { const char* e = getenv("VKP_CHAIN_LONG_WARP"); forced = e ? atoi(e) : -1; }
+    (void)world;
+    return forced > 0;      // measured on 8 GPUs: 0.194 vs 0.205 ms for the chain stream, no gain for the frame -- off unless asked for
+}
+
 cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t after_scan, uint32_t tag, unsigned int cont_cap)
 {
     // path_count[0] = number of paths, [1] = head of the queue the persistent warps of mode 3 pull from
@@ -1879,7 +1887,12 @@ cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t 
         }
         k_chain_q<<<(unsigned)(per_sm6 * n_sm6), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame, tag, cont_cap);
     } else if (L.frame.p.wavefront == 3) k_chain_warp<<<148 * VKP_LB_CHAIN, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
-    else {
+    else if (L.frame.p.wavefront == 7 && chain_long_by_warp(L.frame.world)) {
+        // VKP_CHAIN_LONG_WARP=1 (A/B): one WARP per long path walks every ray cooperatively (warp_trace) -- latency instead of
+        // throughput.  1 GPU: more long paths than resident warps, 2x slower.  8 GPUs (2 k long paths per rank): chain stream 0.194 vs
+        // 0.205 ms, frame unchanged -- there the staged kernels' four dependent tails are the floor.
+        k_chain_warp<<<148 * VKP_LB_CHAIN, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    } else {
         // every queued path gets its own thread in ONE pass (a second pass would double the critical path): the queue length is
         // only known on the device, so the grid covers a quarter of the rank's pixels and the threads beyond the queue leave at once
         const unsigned int px_blocks = frame_grid(L).x;
