@@ -53,7 +53,7 @@ __device__ __forceinline__ unsigned int fast_div(const DFrame& F, unsigned int n
     return F.div_exact ? (unsigned int)(((unsigned long long)n * magic) >> 40) : n / d;
 }
 
-__device__ __forceinline__ Pixel pixel_of_block(const DFrame& F, const unsigned int block)
+__device__ __forceinline__ Pixel pixel_of_block(const DFrame& F, const unsigned int block, const int warp_override = -1)
 {
     const int bpt_x = F.tile_w >> 4, bpt_y = F.tile_h >> 3;
     const int bpt = bpt_x * bpt_y;
@@ -61,7 +61,7 @@ __device__ __forceinline__ Pixel pixel_of_block(const DFrame& F, const unsigned 
     const int tile = F.rank + own_tile * F.world;
     const int ty = (int)fast_div(F, (unsigned int)tile, F.magic_tiles_x, (unsigned int)F.tiles_x), tx = tile - ty * F.tiles_x;
     const int sby = (int)fast_div(F, (unsigned int)sub, F.magic_bpt_x, (unsigned int)bpt_x), sbx = sub - sby * bpt_x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_override >= 0 ? warp_override : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     Pixel p;
     p.x = tx * F.tile_w + sbx * 16 + (warp & 1) * 8 + (lane & 7);
     p.y = ty * F.tile_h + sby * 8 + (warp >> 1) * 4 + (lane >> 3);
@@ -492,18 +492,14 @@ __device__ __forceinline__ LightGeom light_geom(const vkp_light& light, float3 p
 // (latency-bound), 5 (96 registers) when it loops over many soft-shadow samples (issue-bound: cfg5).
 // ONE: the frame traces one sample per light (BASELINE configs[1]): no sample loop, so nothing of the light / G-buffer state
 // stays in registers across the traversal.
-template <int MINB, bool ONE>
-__global__ void __launch_bounds__(VKP_TRAV_BLOCK, MINB) k_shadow(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+template <bool ONE>
+__device__ __forceinline__ void shadow_patch(const DScene& S, const DFrame& F, uint32_t* __restrict__ sstack, const unsigned int vb, const int warp_override,
+                                             unsigned int& nrays, TravCount& tc, TravCount* const tcp, int& l_out, Pixel& px_out)
 {
-    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
-    uint32_t* const sstack = s_trav + threadIdx.x;
-    const long long t_start = clock64();
-    const unsigned int vb = virtual_block(F.cta_order[1]);      // = light * n_cta + pixel block
     const int l = (int)fast_div(F, vb, F.magic_n_cta, (unsigned int)F.n_cta);
-    const Pixel px = pixel_of_block(F, vb - (unsigned int)l * (unsigned int)F.n_cta);
-    unsigned int nrays = 0;
-    TravCount tc = {0u, 0u, 0u};
-    TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
+    const Pixel px = pixel_of_block(F, vb - (unsigned int)l * (unsigned int)F.n_cta, warp_override);
+    l_out = l; px_out = px;
+    (void)tc;
     if (px.valid) {
         const int W = F.p.width, H = F.p.height;
         const size_t i = (size_t)px.y * W + px.x;
@@ -551,9 +547,54 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, MINB) k_shadow(const __grid_co
             F.shadow[l * plane + i] = vkp_unorm8(shadowFactor);
         }
     }
+}
+
+template <int MINB, bool ONE>
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, MINB) k_shadow(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
+    const long long t_start = clock64();
+    const unsigned int vb = virtual_block(F.cta_order[1]);      // = light * n_cta + pixel block
+    unsigned int nrays = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
+    int l; Pixel px;
+    shadow_patch<ONE>(S, F, sstack, vb, -1, nrays, tc, tcp, l, px);
     add_counter(F.counters, 1, nrays);
     if (F.count_trav) add_trav(F.counters, tc, (1u << 28) | ((unsigned)l << 23) | (unsigned)(px.valid ? px.y * F.p.width + px.x : 0));
     record_cost(F.cta_cost[1], vb, t_start);
+}
+
+// The same pass as a PERSISTENT grid (north_star: "persistent-thread ... traversal"; A/B knob VKP_SHADOW_PERSIST = CTAs per SM): a few
+// resident CTAs per SM whose WARPS take the next 8 x 4 pixel patch of the next (light, block) from a counter until none is left, in the
+// longest-first order of the block schedule.  The hardware block scheduler is replaced by one atomic per warp and 32 pixels, and a warp
+// that drew a cheap patch is back for the next one without waiting for the other three warps of its CTA.
+template <int MINB, bool ONE>
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, MINB) k_shadow_persistent(const __grid_constant__ DScene S, const __grid_constant__ DFrame F, unsigned int* __restrict__ next,
+                                                                            const unsigned int n_units)
+{
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
+    const int lane = (int)(threadIdx.x & 31u);
+    unsigned int nrays = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;
+    while (true) {
+        unsigned int u = 0u;
+        if (lane == 0) u = atomicAdd(next, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        const long long t0 = clock64();
+        const unsigned int b = u >> 2;
+        const unsigned int vb = F.cta_order[1] ? __ldg(F.cta_order[1] + b) : b;
+        int l; Pixel px;
+        shadow_patch<ONE>(S, F, sstack, vb, (int)(u & 3u), nrays, tc, tcp, l, px);
+        __syncwarp();
+        record_cost(F.cta_cost[1], vb, t0);
+    }
+    add_counter(F.counters, 1, nrays);
+    if (F.count_trav) add_trav(F.counters, tc, 1u << 28);
 }
 
 // blur.comp:35-82 for one pixel and one light, with runtime W/H/NLIGHTS and an integer motion fetch; returns the new
@@ -1778,10 +1819,30 @@ cudaError_t launch_set_carveout(int pct)
 }
 
 cudaError_t launch_gbuffer(const FrameLaunch& L) { k_gbuffer<<<frame_grid(L), 128, 0, L.stream>>>(L.scene, L.frame); return cudaGetLastError(); }
-cudaError_t launch_shadow(const FrameLaunch& L)
+cudaError_t launch_shadow(const FrameLaunch& L, unsigned int* persist_counter)
 {
     if (L.scene.n_lights == 0) return cudaSuccess;
     dim3 g = frame_grid(L); g.x *= (unsigned)L.scene.n_lights;      // light-major: virtual block = light * n_cta + pixel block
+    // Persistent grid or one CTA per block?  Measured (profiles/r3d_*, r3e_*): with one sample per light (cfg2) the hardware-scheduled grid
+    // wins -- the persistent one fills every SM before the chain's kernels on the other streams get a slot, 0.615 -> 0.66-0.71 ms/frame;
+    // with many samples per light (cfg5: 16 lights x 16 samples, the pass is 99 % of the frame and a thread's work varies 16-fold) the
+    // warp-granular queue wins, 238.8 -> 223.5 ms.  VKP_SHADOW_PERSIST=<CTAs per SM> forces one or the other (0 = never).
+    static int forced = -2, n_sm = 0;
+    if (forced == -2) {
+        const char* e = getenv("VKP_SHADOW_PERSIST"); forced = e ? atoi(e) : -1; if (forced > 16) forced = 16;
+        int dev = 0; cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    const int persist = forced >= 0 ? forced : (L.frame.p.shadow_samples >= 4 ? VKP_LB_SHADOW_MANY : 0);
+    if (persist > 0 && persist_counter && g.x > 0) {
+        cudaError_t e = launch_stage_words(L.stream, persist_counter, nullptr, sizeof(unsigned int));
+        if (e != cudaSuccess) return e;
+        const unsigned int units = g.x * 4u, grid = (unsigned)(persist * n_sm);
+        if (L.frame.p.shadow_samples >= 4) k_shadow_persistent<VKP_LB_SHADOW_MANY, false><<<grid, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame, persist_counter, units);
+        else if (L.frame.p.shadow_samples == 1) k_shadow_persistent<VKP_LB_SHADOW, true><<<grid, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame, persist_counter, units);
+        else k_shadow_persistent<VKP_LB_SHADOW, false><<<grid, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame, persist_counter, units);
+        return cudaGetLastError();
+    }
     if (L.frame.p.shadow_samples >= 4) k_shadow<VKP_LB_SHADOW_MANY, false><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);
     else if (L.frame.p.shadow_samples == 1) k_shadow<VKP_LB_SHADOW, true><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);
     else k_shadow<VKP_LB_SHADOW, false><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);

@@ -86,6 +86,7 @@ struct vkp_ctx {
     int schedule = 1;                 // 0 = hardware block order, 1 = longest first (VKP_SCHEDULE=0|1)
     int prefetch = 0;                 // VKP_PREFETCH: 1 = stream the BVH arena into L2 at the start of every frame, 2 = vertex / index buffers too
     cudaEvent_t ev_prefetch = nullptr;
+    bool shadow_wait_scan = false;
     bool use_seed_plane = true;       // k_gbuffer evaluates TEA once per pixel for the frame's later stages (VKP_SEED_PLANE=0: every stage evaluates it)
     bool chain_in_flight = false;
     // multi-GPU: FINAL_SRGB8 is double-buffered (vkp_set_output_buffer) and may be redirected into rank 0's two buffers over NVLink
@@ -503,7 +504,10 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
         const int k = stage == VKP_STAGE_SHADOW ? 1 : 0;
         if (ctx->order_pending[k]) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_order_done[k], 0)); ctx->order_pending[k] = false; }
         if (k) {
-            CK(launch_shadow(L));
+            // (A/B knob) VKP_SHADOW_WAIT_SCAN=1: k_shadow becomes eligible together with the chain's kernels instead of ~15 us before them,
+            // so that the high-priority chain CTAs are placed first even when k_shadow is a persistent grid that would fill every SM
+            if (ctx->shadow_wait_scan && ctx->chain_in_flight) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_scan, 0));
+            CK(launch_shadow(L, ctx->path_count.as<unsigned int>() + 8));      // [8]: the work counter of the persistent variant (VKP_SHADOW_PERSIST)
         } else CK(launch_gbuffer(L));
         if (L.frame.cta_cost[k]) {       // next frame's order from this frame's costs, beside the rest of the frame
             CK(cudaEventRecord(ctx->ev_stage_done[k], ctx->stream));
@@ -615,6 +619,7 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
         if (const char* e = getenv("VKP_SCHEDULE")) ctx->schedule = atoi(e) != 0;
         if (const char* e = getenv("VKP_SEED_PLANE")) ctx->use_seed_plane = atoi(e) != 0;
         if (const char* e = getenv("VKP_PREFETCH")) ctx->prefetch = atoi(e);
+        if (const char* e = getenv("VKP_SHADOW_WAIT_SCAN")) ctx->shadow_wait_scan = atoi(e) != 0;
         cudaEventCreateWithFlags(&ctx->ev_gbuffer, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_scan, cudaEventDisableTiming);
