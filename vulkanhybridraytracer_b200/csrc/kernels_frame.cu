@@ -1118,7 +1118,32 @@ __device__ __forceinline__ void hit_normal_pos(const DScene& S, float3 rayO, flo
     shadingMode = (int)mat.shadingMetallicRoughness[0];
 }
 
-// blockIdx.y = light.  hybridHit.rchit:99-131: a diffuse hit facing a light within its range traces one any-hit ray towards it.
+// hybridHit.rchit:99-131 for ONE light of ONE hit: a diffuse hit facing a light within its range traces one any-hit ray towards it.
+// seed0 = the path's RNG state when the hit shader starts; with the advancing RNG the sample of light l starts from the state the
+// lights before it leave behind (two LCG steps per light that traces).  Returns "traced and blocked".
+__device__ __forceinline__ bool secondary_blocked(const DScene& S, const DFrame& F, uint32_t* __restrict__ sstack, float3 rayO, float3 rayD, const HitRec& h,
+                                                  int l, uint32_t seed0, unsigned int& n_sec, TravCount* tcp)
+{
+    float3 N, worldPos; int shadingMode;
+    hit_normal_pos(S, rayO, rayD, h, N, worldPos, shadingMode);
+    if (shadingMode != 0) return false;                               // mirror / glass hits trace no shadow rays (hybridHit.rchit:133-183)
+    const vkp_light light = S.lights[l];
+    const LightGeom g = light_geom(light, worldPos, N);
+    if (!(g.NdotL > 0.0f) || !(g.dist < g.maxd)) return false;
+    const bool advance = F.p.faithful_rng == 0;
+    uint32_t seed = seed0;
+    if (advance) {
+        for (int k = 0; k < l; k++) {
+            const LightGeom gk = light_geom(S.lights[k], worldPos, N);
+            if (gk.NdotL > 0.0f && gk.dist < gk.maxd) { seed = 1664525u * seed + 1013904223u; seed = 1664525u * seed + 1013904223u; }
+        }
+    }
+    const float3 dir = sample_disk(light, worldPos, g.L, seed, advance);
+    HitRec sh; n_sec++;
+    return trace_ray<true>(S, sstack, worldPos + dir * 1e-2f, dir, 0.001f, g.dist + 1.0f, sh, nullptr, tcp);
+}
+
+// blockIdx.y = light: one thread per (path, light)
 __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN_TRACE) k_chain_shadow0(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
@@ -1128,7 +1153,6 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN_TRACE) k_chain_sh
     unsigned int n_sec = 0;
     TravCount tc = {0u, 0u, 0u};
     TravCount* const tcp = F.count_trav ? &tc : nullptr;
-    const bool advance = F.p.faithful_rng == 0;
     for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_paths; k += gridDim.x * blockDim.x) {
         const unsigned int slot = staged_slot(F, k);
         PathItem* rec = F.path_q[0] + slot;
@@ -1136,26 +1160,78 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN_TRACE) k_chain_sh
         if (a.w < 0.0f) continue;                                       // the first ray missed: sky
         const float4 b = rec->b, c = rec->c;
         HitRec h; h.t = a.w; h.u = b.w; h.v = c.x; h.inst = __float_as_int(c.y); h.prim = __float_as_int(c.z);
-        float3 N, worldPos; int shadingMode;
-        hit_normal_pos(S, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), h, N, worldPos, shadingMode);
-        if (shadingMode != 0) continue;                                 // mirror / glass hits trace no shadow rays (hybridHit.rchit:133-183)
-        const vkp_light light = S.lights[l];
-        const LightGeom g = light_geom(light, worldPos, N);
-        if (!(g.NdotL > 0.0f) || !(g.dist < g.maxd)) continue;
         const size_t i = (size_t)F.chain_pix[slot];
         const int py = (int)(i / (size_t)F.p.width), pxl = (int)(i - (size_t)py * F.p.width);
-        uint32_t seed = pixel_seed(F, i, pxl, py);
-        if (advance) {
-            for (int k = 0; k < l; k++) {
-                const LightGeom gk = light_geom(S.lights[k], worldPos, N);
-                if (gk.NdotL > 0.0f && gk.dist < gk.maxd) { seed = 1664525u * seed + 1013904223u; seed = 1664525u * seed + 1013904223u; }
-            }
-        }
-        const float3 dir = sample_disk(light, worldPos, g.L, seed, advance);
-        HitRec sh; n_sec++;
-        if (trace_ray<true>(S, sstack, worldPos + dir * 1e-2f, dir, 0.001f, g.dist + 1.0f, sh, nullptr, tcp))
+        if (secondary_blocked(S, F, sstack, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), h, l, pixel_seed(F, i, pxl, py), n_sec, tcp))
             atomicOr(reinterpret_cast<unsigned int*>(&rec->c.w), 1u << l);
     }
+    add_counter(F.counters, 3, n_sec);
+    if (F.count_trav) add_trav(F.counters, tc);
+}
+
+// ---- the long paths of schedule 7, FOUR LANES per path -------------------------------------------------------------------------------
+// A path that goes on for 8 bounces is 8 x (one closest-hit ray + one any-hit ray per light + the hit shader), all dependent: ~230 us for
+// the longest path of the 1080p default frame, whoever else is on the GPU.  The per-light shadow rays of a hit are independent of each
+// other (hybridHit.rchit:99-131), so here a quad of lanes walks one path: all four trace the reflection ray and run the hit shader
+// redundantly (one instruction stream, broadcast loads), and in between lane q traces the shadow ray of light q, q + 4, ...; the quad
+// exchanges the answers with a ballot and the shader takes them as its precomputed mask (shade_hit<PRE>).  Only the few long paths run
+// like this (4 x the threads); every stored colour is bit-identical to k_chain's.  A/B knob VKP_CHAIN_LONG_QUAD=1, off by default.
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_quad(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
+    const unsigned int full = 0xffffffffu;
+    const int lane = (int)(threadIdx.x & 31u), q = lane & 3, quad = lane >> 2;
+    const unsigned int n_paths = F.path_count[0];
+    unsigned int n_refl = 0, n_sec = 0, n_unused = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;
+    while (true) {
+        unsigned int base = 0u;
+        if (lane == 0) base = atomicAdd(&F.path_count[1], 8u);
+        base = __shfl_sync(full, base, 0);
+        if (base >= n_paths) break;
+        const unsigned int slot = base + (unsigned int)quad;
+        bool active = slot < n_paths;
+        size_t i = 0;
+        float3 origin = f3s(0.0f), direction = f3s(0.0f), ro = f3s(0.0f);
+        Payload prd; prd.seed = 0u;
+        int n = 0;
+        if (active) {
+            i = (size_t)F.chain_pix[slot];
+            const int py = (int)(i / (size_t)F.p.width), pxl = (int)(i - (size_t)py * F.p.width);
+            chain_first_ray(S, F, i, ro, direction);
+            prd.seed = pixel_seed(F, i, pxl, py);
+            active = F.p.max_bounces > 0;
+        }
+        while (__any_sync(full, active)) {
+            HitRec h; h.t = -1.0f; h.u = 0.0f; h.v = 0.0f; h.inst = -1; h.prim = -1;
+            bool hit = false;
+            if (active) {
+                if (n > 0) ro = origin + direction * 1e-2f;
+                if (q == 0) n_refl++;
+                hit = trace_ray<false>(S, sstack, ro, direction, 0.001f, 1000.0f, h, nullptr, q == 0 ? tcp : nullptr);
+            }
+            uint32_t pre = 0u;
+            for (int l0 = 0; l0 < S.n_lights; l0 += 4) {
+                const int l = l0 + q;
+                bool blocked = false;
+                if (active && hit && l < S.n_lights) blocked = secondary_blocked(S, F, sstack, ro, direction, h, l, prd.seed, n_sec, tcp);
+                const unsigned int bal = __ballot_sync(full, blocked);
+                pre |= ((bal >> (quad * 4)) & 0xfu) << l0;
+            }
+            if (active) {
+                if (hit) shade_hit<false, 0, true>(S, nullptr, F.p, ro, direction, h, prd, n_unused, nullptr, nullptr, pre); else shade_miss(S, direction, prd);
+                if (q == 0) F.chain_buf[(size_t)slot * VKP_CHAIN_MAX + n] = make_float4(prd.color.x, prd.color.y, prd.color.z, 0.0f);
+                n++;
+                if (!hit || !(prd.scatter > 0.0f) || n >= F.p.max_bounces) {
+                    if (q == 0) { F.chain_len[slot] = n; if (F.chain_long) F.chain_long[i] = n > 1 ? 1 : 0; }
+                    active = false;
+                } else { origin = prd.origin; direction = prd.direction; }
+            }
+        }
+    }
+    add_counter(F.counters, 2, n_refl);
     add_counter(F.counters, 3, n_sec);
     if (F.count_trav) add_trav(F.counters, tc);
 }
@@ -1806,7 +1882,7 @@ cudaError_t launch_set_carveout(int pct)
 {
     if (pct < 0) return cudaSuccess;
     const void* fns[] = {(const void*)k_gbuffer, (const void*)k_shadow<VKP_LB_SHADOW, true>, (const void*)k_shadow<VKP_LB_SHADOW, false>,
-                         (const void*)k_shadow<VKP_LB_SHADOW_MANY, false>, (const void*)k_chain, (const void*)k_chain_q, (const void*)k_chain_scan, (const void*)k_chain_warp,
+                         (const void*)k_shadow<VKP_LB_SHADOW_MANY, false>, (const void*)k_chain, (const void*)k_chain_quad, (const void*)k_chain_q, (const void*)k_chain_scan, (const void*)k_chain_warp,
                          (const void*)k_chain_first, (const void*)k_chain_shadow0, (const void*)k_chain_shade0, (const void*)k_chain_rest,
                          (const void*)k_denoise, (const void*)k_denoise_accumulate4, (const void*)k_resolve<0>, (const void*)k_resolve<1>,
                          (const void*)k_resolve<2>, (const void*)k_resolve<3>, (const void*)k_resolve_paths, (const void*)k_bounce, (const void*)k_build_order,
@@ -1915,6 +1991,13 @@ cudaError_t launch_chain_staged(const FrameLaunch& L, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+static bool chain_long_by_quad()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VKP_CHAIN_LONG_QUAD"); v = e ? (atoi(e) != 0) : 0; }      // measured (profiles/r3g_*): 0.611 -> 0.657 ms/frame on one GPU: four times the 168-register threads take k_shadow's registers, and the chain stream is bound by the staged kernels, not by the long paths
+    return v != 0;
+}
+
 static bool chain_long_by_warp(int world)
 {
     static int forced = -2;
@@ -1948,7 +2031,11 @@ cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t 
         }
         k_chain_q<<<(unsigned)(per_sm6 * n_sm6), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame, tag, cont_cap);
     } else if (L.frame.p.wavefront == 3) k_chain_warp<<<148 * VKP_LB_CHAIN, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
-    else if (L.frame.p.wavefront == 7 && chain_long_by_warp(L.frame.world)) {
+    else if (L.frame.p.wavefront == 7 && chain_long_by_quad()) {
+        static int n_smq = 0;
+        if (!n_smq) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_smq, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_smq <= 0) n_smq = 148; }
+        k_chain_quad<<<(unsigned)(VKP_LB_CHAIN * n_smq), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    } else if (L.frame.p.wavefront == 7 && chain_long_by_warp(L.frame.world)) {
         // VKP_CHAIN_LONG_WARP=1 (A/B): one WARP per long path walks every ray cooperatively (warp_trace) -- latency instead of
         // throughput.  1 GPU: more long paths than resident warps, 2x slower.  8 GPUs (2 k long paths per rank): chain stream 0.194 vs
         // 0.205 ms, frame unchanged -- there the staged kernels' four dependent tails are the floor.
