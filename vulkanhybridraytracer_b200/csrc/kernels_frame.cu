@@ -34,6 +34,9 @@
 #ifndef VKP_CHAIN_CALL
 #define VKP_CHAIN_CALL 0      /* 1: k_chain calls the traversal (trace_ray_call) instead of inlining it */
 #endif
+#ifndef VKP_KEEPW_MANY
+#define VKP_KEEPW_MANY 1      /* many-sample shadow loop and Raytraced mode: trace_ray<.., KEEPW> (vkp_bvh.cuh) */
+#endif
 #ifndef VKP_LB_CHAIN_TRACE
 #define VKP_LB_CHAIN_TRACE 8  /* the lean traversal kernels of the staged chain (k_chain_first, k_chain_shadow0) */
 #endif
@@ -267,7 +270,7 @@ __device__ void shade_hit(const DScene& S, uint32_t* __restrict__ sstack, const 
                             if (advance) for (int r = 0; r < 2 * a; r++) sd = 1664525u * sd + 1013904223u;
                             float3 dir = sample_disk(light, worldPos, L, sd, false);
                             HitRec sh; n_secondary++;
-                            unshadowed = !trace_ray<true>(S, sstack, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, nullptr, tcp);
+                            unshadowed = !trace_ray<true, false, VKP_KEEPW_MANY != 0>(S, sstack, worldPos + dir * 1e-2f, dir, 0.001f, light_distance + 1.0f, sh, nullptr, tcp);
                         }
                         lit += (unsigned)__popc(__ballot_sync(0xffffffffu, unshadowed));
                     }
@@ -537,7 +540,7 @@ __device__ __forceinline__ void shadow_patch(const DScene& S, const DFrame& F, u
                     for (int s = 0; s < shadowSamples; s++) {
                         const float3 dir = sample_disk(light, position, g.L, seed, advance);
                         HitRec h; nrays++;
-                        if (!trace_ray<true>(S, sstack, position + dir * 1e-1f, dir, 0.001f, g.dist + 1.0f, h, nullptr, tcp)) shadowFactor += 1.0f;
+                        if (!trace_ray<true, false, VKP_KEEPW_MANY != 0>(S, sstack, position + dir * 1e-1f, dir, 0.001f, g.dist + 1.0f, h, nullptr, tcp)) shadowFactor += 1.0f;
                     }
                 } else {
                     for (int s = 0; s < shadowSamples; s++) shadowFactor += 1.0f;      // beyond maxDistance: unshadowed (shadowRaygen.rgen:81-83)

@@ -234,7 +234,10 @@ __device__ __noinline__ bool trace_ray_general(const DScene& S, float3 o, float3
 // ---- the fast path ---------------------------------------------------------------------------------------------------------------
 // `sstack` = this thread's column of the CTA's shared-memory stack: sstack[level * VKP_TRAV_BLOCK], VKP_SSTACK levels.
 // STATS: stats[0] = child-pair fetches, stats[1] = triangle tests of this ray (vkp_trace_stats).
-template <bool ANY, bool STATS = false>
+// KEEPW: the world-space slab stays in registers while a BLAS is walked instead of being recomputed (three IEEE reciprocals) when the
+// walk returns to the TLAS -- 12 more live registers against ~30 instructions per instance visit.  Pays in the issue-bound kernels
+// that have registers to spare (many-sample shadows, Raytraced mode), costs in the 64-register latency-bound ones.
+template <bool ANY, bool STATS = false, bool KEEPW = false>
 __device__ __forceinline__ bool trace_ray(const DScene& S, uint32_t* __restrict__ sstack, float3 o, float3 d, float tmin, float tmax, HitRec& best,
                                           uint32_t* stats = nullptr, TravCount* tcount = nullptr)
 {
@@ -259,6 +262,8 @@ __device__ __forceinline__ bool trace_ray(const DScene& S, uint32_t* __restrict_
         VKP_PUSH(VKP_STACK_SENTINEL);
         float3 ro = o, rd = d;
         SlabRay slab = slab_setup(o, d);
+        SlabRay wslab;
+        if (KEEPW) wslab = slab;
         const float4* nodes = S.tlas_nodes2;
         uint32_t cur = S.tlas_root_ref2;
         const float4* tris = nullptr;
@@ -286,7 +291,7 @@ __device__ __forceinline__ bool trace_ray(const DScene& S, uint32_t* __restrict_
             if (cur == VKP_STACK_RETURN) {
                 // back in the TLAS: the world slab is recomputed rather than carried through the BLAS walk in registers
                 inst = -1; ro = o; rd = d;
-                slab = slab_setup(o, d);
+                if (KEEPW) slab = wslab; else slab = slab_setup(o, d);
                 nodes = S.tlas_nodes2;
                 VKP_POP(cur);
                 continue;
