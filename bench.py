@@ -237,7 +237,7 @@ def main():
     ap.add_argument("--no-peer", action="store_true", help="N > 1: composite with pack + NCCL gather + unpack instead of NVLink peer stores")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-identity check of the composite against a 1-GPU render")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the 2-step Raytraced 64 spp x 64 samples block (BASELINE configs[2])")
-    ap.add_argument("--chain", type=int, default=7, choices=[0, 1, 2, 3, 4, 5, 6, 7],
+    ap.add_argument("--chain", type=int, default=7, choices=[0, 1, 2, 3, 4, 5, 6, 7, 8],
                     help="reflection-chain schedule: 0 inline in k_resolve, 1 wavefront queues, 2 k_chain overlapped with the shadow pass, 3 warp per path, 4 staged first bounce, 5 = 2 + the resolve does not wait for the chain, 6 persistent wavefront, 7 = 5 with the paths split by predicted length (default)")
     ap.add_argument("--fuse-denoise", action="store_true", help="run blur.comp inside the resolve kernel instead of as its own pass (A/B)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="wall seconds the parity / cpu_baseline oracle leg may take")
@@ -664,7 +664,7 @@ def main():
                                    "secondary_shadow": int(rays_all[3] // args.steps), "primary_not_counted": int(rays_all[0] // args.steps)},
                 "mrays_s_incl_primary": float(rays_all.sum()) / args.steps / (ms_per_step * 1e-3) / 1e6,
                 "nominal_2P_mrays_s": 2 * P / (ms_per_step * 1e-3) / 1e6,
-                "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise", 3: "k_chain_warp (one warp per queued path, cooperative traversal) on a second stream", 4: "staged chain on a second stream overlapping k_shadow + k_denoise: first bounce as a wavefront (k_chain_first, k_chain_shadow0, k_chain_shade0), continuing paths compacted (k_chain_rest)", 5: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges the chain into the mirror / glass pixels", 6: "k_chain_q: persistent queue-fed grid, one bounce per work item, scattered paths appended to the queue (ballot / prefix compaction), on a second stream overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges it", 7: "paths split by last frame's length: the long ones first in k_chain (persistent, queue-fed), the others through the staged kernels (k_chain_first / _shadow0 / _shade0 / _rest) on a third stream, both overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges them"}[args.chain],
+                "chain_schedule": {0: "inline in k_resolve", 1: "wavefront queues (k_bounce per bounce)", 2: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise", 3: "k_chain_warp (one warp per queued path, cooperative traversal) on a second stream", 4: "staged chain on a second stream overlapping k_shadow + k_denoise: first bounce as a wavefront (k_chain_first, k_chain_shadow0, k_chain_shade0), continuing paths compacted (k_chain_rest)", 5: "k_chain (one thread per queued path) on a second stream overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges the chain into the mirror / glass pixels", 6: "k_chain_q: persistent queue-fed grid, one bounce per work item, scattered paths appended to the queue (ballot / prefix compaction), on a second stream overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges it", 7: "paths split by last frame's length: the long ones first in k_chain (persistent, queue-fed), the others through the staged kernels (k_chain_first / _shadow0 / _shade0 / _rest) on a third stream, both overlapping k_shadow + k_denoise + k_resolve; k_resolve_paths merges them", 8: "as 7 with the first bounce folded into the frame's own kernels: k_gbuffer queues the path pixels (no scan pass), the first reflection rays are the leading blocks of k_shadow's grid, k_chain_shadow0 / _shade0 / _rest follow the shadow pass on a third stream beside k_denoise + k_resolve; k_resolve_paths merges"}[args.chain],
                 "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
                 "parallelism": (f"tiles {TW}x{TH} dealt over {world} GPU(s), replicated BVH, " +
                                 ("resolve kernels store sRGB8 pixels straight into rank 0's image over NVLink peer memory (CUDA IPC) + a device-side flag barrier"

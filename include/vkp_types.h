@@ -91,7 +91,9 @@ typedef struct vkp_params {
                                         6 = as 5 with the chain as a persistent wavefront: one bounce per work item, a queue-fed persistent
                                             grid, scattered paths appended to the queue (ballot / prefix compaction) instead of looping,
                                         7 = as 5 with the paths split by what they did in the previous frame: those that went beyond their first
-                                            bounce start first in k_chain, the others go through the lean staged kernels of 4 on a third stream */
+                                            bounce start first in k_chain, the others go through the lean staged kernels of 4 on a third stream,
+                                        8 = as 7 with the first bounce folded into the frame's own kernels: k_gbuffer queues the path pixels, the first
+                                            reflection rays are the leading blocks of k_shadow's grid, the rest follows the shadow pass */
     int32_t fuse_denoise;            /* vkp_render (Hybrid): run blur.comp inside the resolve kernel instead of as its own pass */
     int32_t reproject_fix;           /* blur.comp:52-53 on a reset frame.  0 (default): the reference's history fetch, pixel + motion.x * (W, H)
                                         (twice the right distance, x component used for both axes).

@@ -44,7 +44,7 @@ def test_cfg2_whole_frames_at_1080p():
     assert cpu["rays"] > 3 * 2_000_000
 
 
-@pytest.mark.parametrize("chain", [0, 1, 2, 3, 4, 6, 7])
+@pytest.mark.parametrize("chain", [0, 1, 2, 3, 4, 6, 7, 8])
 def test_cfg2_other_chain_schedules_at_1080p(chain):
     """The inline, the wavefront, the warp-per-path and the staged schedule of the reflection chain give the same frame at full size (row sample of frame 1)."""
     _, (par, _) = _pair(0, 1920, 1080, vk.MODE_HYBRID, 1, 1, 1, stride=24, chain=chain)

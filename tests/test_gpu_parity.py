@@ -94,7 +94,7 @@ def test_trace_edge_cases(gpu_ctx, small_scene, small_oracle):
     assert got["instance"][0] == -1 and got["instance"][1] == 0 and abs(got["t"][1] - 5.0) < 1e-5 and got["instance"][2] == -1 and got["instance"][3] == -1
 
 
-@pytest.mark.parametrize("w,h,wavefront,fuse", [(320, 184, 0, 1), (250, 130, 0, 0), (320, 184, 1, 1), (250, 130, 1, 0), (320, 184, 2, 0), (250, 130, 2, 1), (320, 184, 4, 0), (250, 130, 4, 1), (320, 184, 5, 0), (250, 130, 5, 1), (320, 184, 6, 0), (250, 130, 6, 1), (320, 184, 7, 0), (250, 130, 7, 1)])
+@pytest.mark.parametrize("w,h,wavefront,fuse", [(320, 184, 0, 1), (250, 130, 0, 0), (320, 184, 1, 1), (250, 130, 1, 0), (320, 184, 2, 0), (250, 130, 2, 1), (320, 184, 4, 0), (250, 130, 4, 1), (320, 184, 5, 0), (250, 130, 5, 1), (320, 184, 6, 0), (250, 130, 6, 1), (320, 184, 7, 0), (250, 130, 7, 1), (320, 184, 8, 0), (250, 130, 8, 1)])
 def test_hybrid_frames_stage_by_stage(gpu_ctx, small_scene, small_oracle, w, h, wavefront, fuse):
     ctx, sc, o = gpu_ctx, small_scene, small_oracle
     cam = sc.camera(w, h)
@@ -121,10 +121,10 @@ def test_hybrid_frames_stage_by_stage(gpu_ctx, small_scene, small_oracle, w, h, 
         # gbuffer, shadow, [denoise], resolve; 1: + one k_bounce per bounce (8), never fused; 2: + queue clear, k_chain_scan, k_chain;
         # 4: + queue clear, k_chain_scan, k_chain_first, k_chain_shadow0, k_chain_shade0, k_chain_rest; 5: as 2 + k_resolve_paths;
         # + the two k_build_order launches of the longest-first schedule (side stream)
-        assert c.kernel_launches == {0: 4, 1: 4 + 8, 2: 7, 4: 10, 5: 8, 6: 8, 7: 12}[wavefront] - (1 if fuse and wavefront != 1 else 0) + 2
+        assert c.kernel_launches == {0: 4, 1: 4 + 8, 2: 7, 4: 10, 5: 8, 6: 8, 7: 12, 8: 9}[wavefront] - (1 if fuse and wavefront != 1 else 0) + 2
 
 
-@pytest.mark.parametrize("wavefront", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("wavefront", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_chain_schedules_with_the_advancing_rng(gpu_ctx, small_scene, small_oracle, wavefront):
     """faithful_rng = 0: every sampleDisk call advances the path's seed, so the secondary shadow ray of light l depends on which of the
     lights before it were sampled (hybridHit.rchit:99-131).  The staged chain (4) replays that per (path, light) thread; all five

@@ -90,7 +90,7 @@ ctx = vk.Context(0); ctx.upload_scene(sc)
 w, h = 256, 144
 cam = sc.camera(w, h); ctx.set_camera(cam)
 hist = None
-for chain in (2, 3, 4, 5, 6, 7, 0):
+for chain in (2, 3, 4, 5, 6, 7, 8, 0):
     ctx.reset_history(); hist = None
     for f in range(2):
         p = vk.make_params(w, h, frame=f, wavefront=chain)
@@ -188,7 +188,7 @@ def test_light_edge_cases_on_the_gpu():
     o = Oracle(sc); o.set_lights(lights)
     ctx = vk.Context(0); ctx.upload_scene(sc); ctx.set_lights(lights)
     cam = sc.camera(W, H); ctx.set_camera(cam)
-    for wavefront in (0, 2, 4, 5, 6, 7):
+    for wavefront in (0, 2, 4, 5, 6, 7, 8):
         p = vk.make_params(W, H, frame=frame, shadow_samples=samples, wavefront=wavefront)
         ctx.set_params(p); ctx.reset_history(); ctx.render()
         ref = o.hybrid_frame(cam, p)

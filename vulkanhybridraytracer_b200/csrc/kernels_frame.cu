@@ -135,6 +135,15 @@ __global__ void __launch_bounds__(256) k_build_order(uint32_t* __restrict__ cost
     }
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_volatile_u32(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
+
 __device__ __forceinline__ void add_counter(unsigned long long* counters, int slot, unsigned int n)
 {
     n = __reduce_add_sync(0xffffffffu, n);      // redux.sync: one instruction instead of five shuffle + add pairs
@@ -376,6 +385,13 @@ __device__ void shade_hit(const DScene& S, uint32_t* __restrict__ sstack, const 
     prd.dist = h.t; prd.direction = direction; prd.scatter = scatter; prd.origin = worldPos;
 }
 
+// (defined with the chain kernels below; schedule 8 calls them from k_gbuffer and k_shadow)
+__device__ __forceinline__ void chain_enqueue(const DFrame& F, size_t i, bool path);
+__device__ __forceinline__ void chain_first_paths(const DScene& S, const DFrame& F, uint32_t* __restrict__ sstack, unsigned int k0, unsigned int stride,
+                                                  unsigned int& n_refl, TravCount* tcp);
+__device__ __forceinline__ void chain_shadow0_paths(const DScene& S, const DFrame& F, uint32_t* __restrict__ sstack, int l, unsigned int k0, unsigned int stride,
+                                                    unsigned int& n_sec, TravCount* tcp, bool wait_ready);
+
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_GBUFFER) k_gbuffer(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
@@ -466,6 +482,18 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_GBUFFER) k_gbuffer(cons
                 F.motion[i] = (uint32_t)vkp_f32_to_f16(mx * 0.5f + 0.5f) | ((uint32_t)vkp_f32_to_f16(my * 0.5f + 0.5f) << 16);
             }
         }
+    }
+    if (F.chain_in_gbuffer) {
+        // schedule 8: the mirror / glass pixels are compacted into the path lists here (no k_chain_scan pass over the frame).  The test is
+        // k_chain_scan's: the material index as the fp16 position plane stores it (0 for a sky pixel), looked up again.
+        bool path = false;
+        size_t pi = 0;
+        if (px.valid) {
+            pi = (size_t)px.y * F.p.width + px.x;
+            const float matIdx = vkp_f16_to_f32((uint16_t)(F.position[pi].y >> 16));
+            path = (int)material_by_float_index(S, matIdx).shadingMetallicRoughness[0] != 0 && F.p.max_bounces > 0;
+        }
+        chain_enqueue(F, pi, path);
     }
     add_counter(F.counters, 0, nrays);
     if (F.count_trav) add_trav(F.counters, tc, (0u << 28) | (unsigned)(px.valid ? px.y * F.p.width + px.x : 0));
@@ -558,10 +586,39 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, MINB) k_shadow(const __grid_co
     __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
     uint32_t* const sstack = s_trav + threadIdx.x;
     const long long t_start = clock64();
-    const unsigned int vb = virtual_block(F.cta_order[1]);      // = light * n_cta + pixel block
     unsigned int nrays = 0;
     TravCount tc = {0u, 0u, 0u};
     TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
+    if (blockIdx.x < F.first_blocks) {
+        // schedule 8: the leading blocks of the grid trace the FIRST reflection / refraction ray of the queued paths (k_chain_first's work)
+        // inside this kernel: the long rays among them start at t = 0 and their tail hides under 48 000 blocks of shadow rays instead
+        // of ending a kernel of its own
+        unsigned int n_refl = 0;
+        chain_first_paths(S, F, sstack, blockIdx.x * blockDim.x + threadIdx.x, F.first_blocks * blockDim.x, n_refl, tcp);
+        add_counter(F.counters, 2, n_refl);
+        if (F.count_trav) add_trav(F.counters, tc);
+        return;
+    }
+    unsigned int hb = blockIdx.x - F.first_blocks;
+    if (F.first_blocks) {
+        // ... and further down the grid, first_blocks x n_lights blocks trace the per-light any-hit rays of those first hits
+        // (k_chain_shadow0's work).  They are dispatched long after the leading blocks, whose records they read -- each carries a tag
+        // written with st.release when it is complete -- so the wait below practically never spins, and it cannot deadlock: a block
+        // only ever waits for blocks dispatched before it.
+        const unsigned int mid = F.first_blocks * (unsigned int)S.n_lights;
+        if (hb >= F.mid_at && hb < F.mid_at + mid) {
+            const unsigned int unit = hb - F.mid_at;
+            const int l = (int)(unit / F.first_blocks);
+            const unsigned int kb = unit - (unsigned int)l * F.first_blocks;
+            unsigned int n_sec = 0;
+            chain_shadow0_paths(S, F, sstack, l, kb * blockDim.x + threadIdx.x, F.first_blocks * blockDim.x, n_sec, tcp, true);
+            add_counter(F.counters, 3, n_sec);
+            if (F.count_trav) add_trav(F.counters, tc);
+            return;
+        }
+        if (hb >= F.mid_at) hb -= mid;
+    }
+    const unsigned int vb = F.cta_order[1] ? __ldg(F.cta_order[1] + hb) : hb;      // = light * n_cta + pixel block
     int l; Pixel px;
     shadow_patch<ONE>(S, F, sstack, vb, -1, nrays, tc, tcp, l, px);
     add_counter(F.counters, 1, nrays);
@@ -779,6 +836,12 @@ __global__ void __launch_bounds__(128) k_chain_scan(const __grid_constant__ DSce
         const float matIdx = vkp_f16_to_f32((uint16_t)(F.position[i].y >> 16));
         path = (int)material_by_float_index(S, matIdx).shadingMetallicRoughness[0] != 0 && F.p.max_bounces > 0;
     }
+    chain_enqueue(F, i, path);
+}
+
+// path compaction: one atomic per warp, slots by ballot + popc prefix.  Every lane of the warp calls it.
+__device__ __forceinline__ void chain_enqueue(const DFrame& F, size_t i, bool path)
+{
     const int lane = threadIdx.x & 31;
     if (F.chain_split) {
         // schedule 7: two path lists in one array.  Paths that went beyond their first bounce in the previous frame (chain_long, one byte
@@ -903,15 +966,6 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain(const __
 // early spin on ld.acquire).  The grid ends when every item ever created has been completed: continuations are reserved before
 // their parent is counted, so completed == created means nothing is in flight.  If the continuation array is full the lane simply
 // goes on with its path itself.  Same arithmetic as k_chain: every stored colour is bit-identical.
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_volatile_u32(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
-
 __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_q(const __grid_constant__ DScene S, const __grid_constant__ DFrame F, const uint32_t tag,
                                                                           const unsigned int cont_cap)
 {
@@ -1082,15 +1136,11 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_warp(con
 // Records live in path_q[0] (by slot) and path_q[1] (continuing paths); path_count[2] counts the latter.  Same arithmetic in the
 // same order as k_chain: every stored colour is bit-identical.
 //   record.a = ray origin (already offset), t of the hit or -1     record.b = direction, u     record.c = v, instance, primitive, mask
-__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN_TRACE) k_chain_first(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+__device__ __forceinline__ void chain_first_paths(const DScene& S, const DFrame& F, uint32_t* __restrict__ sstack, unsigned int k0, unsigned int stride,
+                                                  unsigned int& n_refl, TravCount* tcp)
 {
-    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
-    uint32_t* const sstack = s_trav + threadIdx.x;
     const unsigned int n_paths = staged_count(F);
-    unsigned int n_refl = 0;
-    TravCount tc = {0u, 0u, 0u};
-    TravCount* const tcp = F.count_trav ? &tc : nullptr;
-    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_paths; k += gridDim.x * blockDim.x) {
+    for (unsigned int k = k0; k < n_paths; k += stride) {
         const unsigned int slot = staged_slot(F, k);
         const size_t i = (size_t)F.chain_pix[slot];
         float3 ro, direction;
@@ -1101,7 +1151,18 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN_TRACE) k_chain_fi
         rec->a = make_float4(ro.x, ro.y, ro.z, hit ? h.t : -1.0f);
         rec->b = make_float4(direction.x, direction.y, direction.z, h.u);
         rec->c = make_float4(h.v, __int_as_float(h.inst), __int_as_float(h.prim), __uint_as_float(0u));
+        if (F.first_blocks) st_release_gpu(reinterpret_cast<uint32_t*>(&rec->d.w), F.chain_tag);      // schedule 8: "record complete" for the blocks further down the same grid
     }
+}
+
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN_TRACE) k_chain_first(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
+    unsigned int n_refl = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;
+    chain_first_paths(S, F, sstack, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, n_refl, tcp);
     add_counter(F.counters, 2, n_refl);
     if (F.count_trav) add_trav(F.counters, tc);
 }
@@ -1146,19 +1207,14 @@ __device__ __forceinline__ bool secondary_blocked(const DScene& S, const DFrame&
     return trace_ray<true>(S, sstack, worldPos + dir * 1e-2f, dir, 0.001f, g.dist + 1.0f, sh, nullptr, tcp);
 }
 
-// blockIdx.y = light: one thread per (path, light)
-__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN_TRACE) k_chain_shadow0(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+__device__ __forceinline__ void chain_shadow0_paths(const DScene& S, const DFrame& F, uint32_t* __restrict__ sstack, int l, unsigned int k0, unsigned int stride,
+                                                    unsigned int& n_sec, TravCount* tcp, bool wait_ready)
 {
-    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
-    uint32_t* const sstack = s_trav + threadIdx.x;
     const unsigned int n_paths = staged_count(F);
-    const int l = (int)blockIdx.y;
-    unsigned int n_sec = 0;
-    TravCount tc = {0u, 0u, 0u};
-    TravCount* const tcp = F.count_trav ? &tc : nullptr;
-    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_paths; k += gridDim.x * blockDim.x) {
+    for (unsigned int k = k0; k < n_paths; k += stride) {
         const unsigned int slot = staged_slot(F, k);
         PathItem* rec = F.path_q[0] + slot;
+        if (wait_ready) while (ld_acquire_gpu(reinterpret_cast<const uint32_t*>(&rec->d.w)) != F.chain_tag) __nanosleep(100);
         const float4 a = rec->a;
         if (a.w < 0.0f) continue;                                       // the first ray missed: sky
         const float4 b = rec->b, c = rec->c;
@@ -1168,6 +1224,17 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN_TRACE) k_chain_sh
         if (secondary_blocked(S, F, sstack, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), h, l, pixel_seed(F, i, pxl, py), n_sec, tcp))
             atomicOr(reinterpret_cast<unsigned int*>(&rec->c.w), 1u << l);
     }
+}
+
+// blockIdx.y = light: one thread per (path, light)
+__global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN_TRACE) k_chain_shadow0(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
+{
+    __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
+    uint32_t* const sstack = s_trav + threadIdx.x;
+    unsigned int n_sec = 0;
+    TravCount tc = {0u, 0u, 0u};
+    TravCount* const tcp = F.count_trav ? &tc : nullptr;
+    chain_shadow0_paths(S, F, sstack, (int)blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, n_sec, tcp, false);
     add_counter(F.counters, 3, n_sec);
     if (F.count_trav) add_trav(F.counters, tc);
 }
@@ -1922,9 +1989,36 @@ cudaError_t launch_shadow(const FrameLaunch& L, unsigned int* persist_counter)
         else k_shadow_persistent<VKP_LB_SHADOW, false><<<grid, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame, persist_counter, units);
         return cudaGetLastError();
     }
+    g.x += L.frame.first_blocks * (1u + (unsigned)L.scene.n_lights);   // schedule 8: first-bounce blocks lead the grid, their any-hit blocks sit inside it
     if (L.frame.p.shadow_samples >= 4) k_shadow<VKP_LB_SHADOW_MANY, false><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);
     else if (L.frame.p.shadow_samples == 1) k_shadow<VKP_LB_SHADOW, true><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);
     else k_shadow<VKP_LB_SHADOW, false><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);
+    return cudaGetLastError();
+}
+
+// does launch_shadow run k_shadow as the persistent grid for this frame?  (then schedule 8 cannot fold the first bounces into it)
+bool shadow_is_persistent(const FrameLaunch& L)
+{
+    const char* e = getenv("VKP_SHADOW_PERSIST");
+    const int forced = e ? atoi(e) : -1;
+    return (forced >= 0 ? forced : (L.frame.p.shadow_samples >= 4 ? VKP_LB_SHADOW_MANY : 0)) > 0;
+}
+unsigned int chain_first_blocks(const FrameLaunch& L) { return frame_grid(L).x / 4u + 1u; }
+
+// schedule 8: what follows the shadow pass on the third stream -- the per-light any-hit rays of the first hits, their shading, and
+// the (mispredicted) paths that go on
+cudaError_t launch_chain_after_first(const FrameLaunch& L, cudaStream_t stream)
+{
+    const unsigned int px_blocks = frame_grid(L).x;
+    const unsigned int g1 = px_blocks / 4u + 1u, g2 = px_blocks / 16u + 1u;
+    if (L.scene.n_lights > 0 && !L.frame.first_blocks) k_chain_shadow0<<<dim3(g1, (unsigned)L.scene.n_lights), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    k_chain_shade0<<<g1, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    k_chain_rest<<<g2, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+    return cudaGetLastError();
+}
+cudaError_t launch_chain_first_only(const FrameLaunch& L, cudaStream_t stream)
+{
+    k_chain_first<<<frame_grid(L).x / 4u + 1u, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
     return cudaGetLastError();
 }
 cudaError_t launch_build_order(cudaStream_t s, uint32_t* cost, uint32_t* order, uint32_t n)
@@ -2013,9 +2107,11 @@ cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t 
 {
     // path_count[0] = number of paths, [1] = head of the queue the persistent warps of mode 3 pull from
     // [2] = number of paths that go on after their first bounce (staged chain, mode 4)
-    cudaError_t e = launch_stage_words(stream, L.frame.path_count, nullptr, 5 * sizeof(unsigned int));
-    if (e != cudaSuccess) return e;
-    k_chain_scan<<<frame_grid(L), 128, 0, stream>>>(L.scene, L.frame);
+    cudaError_t e = cudaSuccess;
+    if (!L.frame.chain_in_gbuffer) {          // schedule 8: the counters were cleared before k_gbuffer, which queued the paths itself
+        if ((e = launch_stage_words(stream, L.frame.path_count, nullptr, 5 * sizeof(unsigned int))) != cudaSuccess) return e;
+        k_chain_scan<<<frame_grid(L), 128, 0, stream>>>(L.scene, L.frame);
+    }
     if (after_scan && (e = cudaEventRecord(after_scan, stream)) != cudaSuccess) return e;
     if (L.frame.p.wavefront == 4) {
         // the queue lengths are only known on the device: grids sized for the usual share of path pixels, grid-stride loops beyond it
@@ -2034,11 +2130,11 @@ cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t 
         }
         k_chain_q<<<(unsigned)(per_sm6 * n_sm6), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame, tag, cont_cap);
     } else if (L.frame.p.wavefront == 3) k_chain_warp<<<148 * VKP_LB_CHAIN, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
-    else if (L.frame.p.wavefront == 7 && chain_long_by_quad()) {
+    else if (L.frame.p.wavefront >= 7 && chain_long_by_quad()) {
         static int n_smq = 0;
         if (!n_smq) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_smq, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_smq <= 0) n_smq = 148; }
         k_chain_quad<<<(unsigned)(VKP_LB_CHAIN * n_smq), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
-    } else if (L.frame.p.wavefront == 7 && chain_long_by_warp(L.frame.world)) {
+    } else if (L.frame.p.wavefront >= 7 && chain_long_by_warp(L.frame.world)) {
         // VKP_CHAIN_LONG_WARP=1 (A/B): one WARP per long path walks every ray cooperatively (warp_trace) -- latency instead of
         // throughput.  1 GPU: more long paths than resident warps, 2x slower.  8 GPUs (2 k long paths per rank): chain stream 0.194 vs
         // 0.205 ms, frame unchanged -- there the staged kernels' four dependent tails are the floor.

@@ -68,7 +68,7 @@ struct vkp_ctx {
     int plane_w = 0, plane_h = 0, plane_lights = 0;
     DevBuf chain_long;                // one byte per pixel: last frame's path went beyond its first bounce (chain schedule 7)
     cudaStream_t chain_stream2 = nullptr;
-    cudaEvent_t ev_chain2 = nullptr;
+    cudaEvent_t ev_chain2 = nullptr, ev_shadow = nullptr;
     bool chain2_in_flight = false;
     DevBuf atrous[2];                 // ping-pong planes of the a-trous shadow filter (vkp_params.denoiser = 1)
     DevBuf counters, io_tmp, io_tmp2, flush, path_q[2], path_count, luts, chain_buf, chain_len, chain_slot, chain_pix;
@@ -374,7 +374,8 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.chain_buf = ctx->chain_buf.as<float4>(); F.chain_len = ctx->chain_len.as<int>(); F.chain_slot = ctx->chain_slot.as<int>(); F.chain_pix = ctx->chain_pix.as<int>();
     F.chain_base = F.p.wavefront == 6 ? F.path_q[0] : F.path_q[1];       // path_q[1] is schedule 6's continuation queue, path_q[0] holds the staged kernels' records
     F.chain_long = ctx->chain_long.as<uint8_t>();
-    F.chain_split = F.p.wavefront == 7 ? 1 : 0;
+    F.chain_split = F.p.wavefront >= 7 ? 1 : 0;
+    F.chain_in_gbuffer = 0; F.first_blocks = 0u; F.mid_at = 0u; F.chain_tag = 1u;      // schedule 8 switches them on inside vkp_render
     F.chain_cap = (unsigned int)((size_t)F.p.width * F.p.height);
     const int total = F.tiles_x * F.tiles_y;
     L.n_own_tiles = total > F.rank ? (total - F.rank + F.world - 1) / F.world : 0;
@@ -539,7 +540,7 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
         const bool late = chain2 && L.frame.p.wavefront >= 5;      // the resolve does not wait for the chain: k_resolve_paths merges it afterwards
         if (chain2 && !ctx->chain_in_flight) {
             CK(launch_chain(L, ctx->stream, nullptr, ++ctx->chain_tag, chain_cont_cap(ctx))); ctx->last_launches += chain_launches(L);
-            if (L.frame.p.wavefront == 7) { CK(launch_chain_staged(L, ctx->stream)); ctx->last_launches += L.scene.n_lights > 0 ? 4u : 3u; }
+            if (L.frame.p.wavefront >= 7) { CK(launch_chain_staged(L, ctx->stream)); ctx->last_launches += L.scene.n_lights > 0 ? 4u : 3u; }
         }      // stand-alone stage: serial (clear + scan + chain)
         if (chain2 && ctx->chain_in_flight && !late) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0)); ctx->chain_in_flight = false; }
         if (late && ctx->chain_in_flight) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_scan, 0));
@@ -615,6 +616,7 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
             cudaStreamCreateWithPriority(&ctx->chain_stream2, cudaStreamNonBlocking, (c2 && strcmp(c2, "low") == 0) ? lo : hi);
         }
         cudaEventCreateWithFlags(&ctx->ev_chain2, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_shadow, cudaEventDisableTiming);
         for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags(&ctx->ev_stage_done[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_order_done[k], cudaEventDisableTiming); }
         if (const char* e = getenv("VKP_SCHEDULE")) ctx->schedule = atoi(e) != 0;
         if (const char* e = getenv("VKP_SEED_PLANE")) ctx->use_seed_plane = atoi(e) != 0;
@@ -693,6 +695,7 @@ void vkp_destroy(vkp_ctx* ctx)
     if (ctx->ev_scan) cudaEventDestroy(ctx->ev_scan);
     if (ctx->ev_prefetch) cudaEventDestroy(ctx->ev_prefetch);
     if (ctx->ev_chain2) cudaEventDestroy(ctx->ev_chain2);
+    if (ctx->ev_shadow) cudaEventDestroy(ctx->ev_shadow);
     if (ctx->chain_stream2) cudaStreamDestroy(ctx->chain_stream2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -977,7 +980,7 @@ int vkp_set_params(vkp_ctx* ctx, const vkp_params* p)
     if (p->max_bounces > VKP_MAX_BOUNCES) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: max_bounces > 64");
     if (p->spp < 1 || p->shadow_samples < 1 || p->max_bounces < 0) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: spp / shadow_samples must be >= 1");
     if (p->denoiser < 0 || p->denoiser > 1) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: denoiser is 0 (blur.comp) or 1 (a-trous)");
-    if (p->wavefront < 0 || p->wavefront > 7) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: wavefront (chain schedule) is 0 .. 7");
+    if (p->wavefront < 0 || p->wavefront > 8) return fail(ctx, VKP_ERR_INVALID, "vkp_set_params: wavefront (chain schedule) is 0 .. 8");
     ctx->params = *p; ctx->have_params = true;
     return VKP_OK;
 }
@@ -1029,11 +1032,29 @@ int vkp_render(vkp_ctx* ctx)
     else if (ctx->params.mode == VKP_MODE_DEFERRED) { seq = deferred; n = 2; }
     const bool seeds = ctx->params.mode == VKP_MODE_HYBRID && ctx->use_seed_plane;
     if (seeds) L.frame.seed_w = ctx->seed.as<uint32_t>();
+    const bool chained = ctx->params.mode == VKP_MODE_HYBRID && ctx->params.wavefront >= 2 && ctx->params.max_bounces <= VKP_CHAIN_MAX && L.n_own_tiles > 0;
+    // schedule 8: k_gbuffer queues the path pixels itself, the first reflection rays ride in k_shadow's grid, and what depends on them
+    // (per-light any-hit rays, shading, stragglers) follows the shadow pass on the third stream, beside the filter and the resolve
+    const bool folded = chained && ctx->params.wavefront == 8;
+    if (folded) {
+        CK(launch_stage_words(ctx->stream, ctx->path_count.p, nullptr, 5 * sizeof(unsigned int)));
+        L.frame.chain_in_gbuffer = 1;
+        ctx->last_launches++;
+    }
     for (int i = 0; i < n; i++) {
+        if (folded && seq[i] == VKP_STAGE_SHADOW) {
+            if (shadow_is_persistent(L)) { CK(launch_chain_first_only(L, ctx->stream)); ctx->last_launches++; }      // (the persistent grid has no leading blocks)
+            else {
+                L.frame.first_blocks = chain_first_blocks(L);
+                // two thirds down the shadow blocks: late enough for the leading blocks to be done, early enough for the last third to cover the any-hit tail
+                L.frame.mid_at = (unsigned int)(((unsigned long long)L.frame.n_cta * (unsigned long long)L.scene.n_lights * 2ull) / 3ull);
+                L.frame.chain_tag = ++ctx->chain_tag;
+                if (L.frame.chain_tag == 0u) L.frame.chain_tag = ++ctx->chain_tag;
+            }
+        }
         if ((r = run_one(ctx, L, seq[i])) != VKP_OK) return r;
         if (seq[i] == VKP_STAGE_GBUFFER && seeds) { L.frame.seed_w = nullptr; L.frame.seed_r = ctx->seed.as<uint32_t>(); }
-        if (seq[i] == VKP_STAGE_GBUFFER && ctx->params.mode == VKP_MODE_HYBRID && ctx->params.wavefront >= 2 &&
-            ctx->params.max_bounces <= VKP_CHAIN_MAX && L.n_own_tiles > 0) {
+        if (seq[i] == VKP_STAGE_GBUFFER && chained) {
             // fork: the reflection chain needs only the G-buffer; it overlaps the shadow + denoise passes on its own stream
             CK(cudaEventRecord(ctx->ev_gbuffer, ctx->stream));
             CK(cudaStreamWaitEvent(ctx->chain_stream, ctx->ev_gbuffer, 0));
@@ -1042,6 +1063,7 @@ int vkp_render(vkp_ctx* ctx)
                 CK(cudaEventRecord(ctx->ev_chain_t0, ctx->chain_stream));
             }
             CK(launch_chain(L, ctx->chain_stream, ctx->ev_scan, ++ctx->chain_tag, chain_cont_cap(ctx)));
+            ctx->last_launches += folded ? 1u : chain_launches(L);
             if (ctx->params.wavefront == 7) {
                 // the bulk of the paths (predicted to end after one bounce) through the lean staged kernels, beside k_chain's long ones
                 CK(cudaStreamWaitEvent(ctx->chain_stream2, ctx->ev_scan, 0));
@@ -1050,10 +1072,23 @@ int vkp_render(vkp_ctx* ctx)
                 CK(cudaStreamWaitEvent(ctx->chain_stream, ctx->ev_chain2, 0));       // ev_chain below then means: both halves are done
                 ctx->last_launches += L.scene.n_lights > 0 ? 4u : 3u;
             }
-            if (ctx->profiling) { CK(cudaEventRecord(ctx->ev_chain_t1, ctx->chain_stream)); ctx->chain_timed = true; }
-            CK(cudaEventRecord(ctx->ev_chain, ctx->chain_stream));
+            if (!folded) {
+                if (ctx->profiling) { CK(cudaEventRecord(ctx->ev_chain_t1, ctx->chain_stream)); ctx->chain_timed = true; }
+                CK(cudaEventRecord(ctx->ev_chain, ctx->chain_stream));
+            }
             ctx->chain_in_flight = true;
-            ctx->last_launches += chain_launches(L);
+        }
+        if (seq[i] == VKP_STAGE_SHADOW && folded) {
+            CK(cudaEventRecord(ctx->ev_shadow, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->chain_stream2, ctx->ev_shadow, 0));
+            CK(launch_chain_after_first(L, ctx->chain_stream2));       // (skips k_chain_shadow0 when its work rode in k_shadow's grid)
+            const bool rode = L.frame.first_blocks != 0u;
+            L.frame.first_blocks = 0u;
+            CK(cudaEventRecord(ctx->ev_chain2, ctx->chain_stream2));
+            CK(cudaStreamWaitEvent(ctx->chain_stream, ctx->ev_chain2, 0));
+            if (ctx->profiling) { CK(cudaEventRecord(ctx->ev_chain_t1, ctx->chain_stream)); ctx->chain_timed = true; }
+            CK(cudaEventRecord(ctx->ev_chain, ctx->chain_stream));                   // both halves are done
+            ctx->last_launches += (L.scene.n_lights > 0 && !rode) ? 3u : 2u;
         }
     }
     if ((r = mark_scene_use(ctx)) != VKP_OK) return r;

@@ -180,6 +180,10 @@ struct DFrame {
     uint8_t* chain_long;            // per pixel: the path of this pixel went beyond its first bounce in the previous frame (schedule 7's prediction)
     int chain_split;                // schedule 7: two path lists (see k_chain_scan)
     unsigned int chain_cap;         // slots in the path arrays (= pixels)
+    int chain_in_gbuffer;           // schedule 8: k_gbuffer compacts the path pixels itself (no k_chain_scan)
+    unsigned int first_blocks;      // schedule 8: leading blocks of k_shadow's grid that trace the queued paths' first rays (0 otherwise)
+    unsigned int mid_at;            // schedule 8: first_blocks * n_lights blocks from this shadow-block index on trace the first hits' any-hit rays
+    uint32_t chain_tag;             // schedule 8: "record complete" mark of this frame's first-bounce records (never 0)
     // longest-first CTA scheduling: cost[v] = SM cycles the slowest warp of virtual block v took in the
     // previous frame, order[b] = the virtual block hardware block b works on (NULL = identity).  [0] k_gbuffer, [1] k_shadow.
     const uint32_t* cta_order[2];

@@ -101,6 +101,10 @@ cudaError_t launch_resolve(const FrameLaunch& L, int* launches);
 cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t after_scan = nullptr, uint32_t tag = 1u, unsigned int cont_cap = 0u);
 cudaError_t launch_resolve_paths(const FrameLaunch& L);
 cudaError_t launch_chain_staged(const FrameLaunch& L, cudaStream_t stream);
+cudaError_t launch_chain_after_first(const FrameLaunch& L, cudaStream_t stream);
+cudaError_t launch_chain_first_only(const FrameLaunch& L, cudaStream_t stream);
+bool shadow_is_persistent(const FrameLaunch& L);
+unsigned int chain_first_blocks(const FrameLaunch& L);
 cudaError_t launch_post(const FrameLaunch& L);
 cudaError_t launch_raytrace(const FrameLaunch& L);
 cudaError_t launch_deferred(const FrameLaunch& L);
