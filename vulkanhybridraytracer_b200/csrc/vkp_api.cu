@@ -66,6 +66,7 @@ struct vkp_ctx {
     DevBuf position, normal, albedo, motion, material, emissive, hit_ids, final_f32, final_srgb8, shadow, denoised[2];
     int denoised_cur = 0;
     int plane_w = 0, plane_h = 0, plane_lights = 0;
+    DevBuf shadow_queue, shadow_qstate;   // many-sample shadow pass: compacted (pixel, light) lists and their counters
     DevBuf chain_long;                // one byte per pixel: last frame's path went beyond its first bounce (chain schedule 7)
     cudaStream_t chain_stream2 = nullptr;
     cudaEvent_t ev_chain2 = nullptr, ev_shadow = nullptr;
@@ -508,7 +509,17 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
             // (A/B knob) VKP_SHADOW_WAIT_SCAN=1: k_shadow becomes eligible together with the chain's kernels instead of ~15 us before them,
             // so that the high-priority chain CTAs are placed first even when k_shadow is a persistent grid that would fill every SM
             if (ctx->shadow_wait_scan && ctx->chain_in_flight) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_scan, 0));
-            CK(launch_shadow(L, ctx->path_count.as<unsigned int>() + 8));      // [8]: the work counter of the persistent variant (VKP_SHADOW_PERSIST)
+            {
+                // many-sample frames: the per-light lists of (pixel, light) pairs that trace rays (k_shadow_classify / k_shadow_items); 4 bytes per
+                // pixel and light, only allocated when such a frame is rendered, and only up to 2 GB (beyond that: the uncompacted kernel)
+                uint32_t* sq = nullptr; unsigned int* sqs = nullptr;
+                const size_t need = (size_t)ctx->plane_w * ctx->plane_h * (size_t)L.scene.n_lights * sizeof(uint32_t);
+                if (L.frame.p.shadow_samples >= 4 && need <= ((size_t)2 << 30) && L.scene.n_lights <= 32) {
+                    CK(ctx->shadow_queue.ensure(need)); CK(ctx->shadow_qstate.ensure(64 * sizeof(unsigned int)));
+                    sq = ctx->shadow_queue.as<uint32_t>(); sqs = ctx->shadow_qstate.as<unsigned int>();
+                }
+                CK(launch_shadow(L, ctx->path_count.as<unsigned int>() + 8, sq, sqs));
+            }      // [8]: the work counter of the persistent variant (VKP_SHADOW_PERSIST)
         } else CK(launch_gbuffer(L));
         if (L.frame.cta_cost[k]) {       // next frame's order from this frame's costs, beside the rest of the frame
             CK(cudaEventRecord(ctx->ev_stage_done[k], ctx->stream));
@@ -672,7 +683,7 @@ void vkp_destroy(vkp_ctx* ctx)
     if (ctx->ev_updated) cudaEventDestroy(ctx->ev_updated);
     DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_textures, &ctx->position, &ctx->seed, &ctx->normal, &ctx->albedo, &ctx->motion,
                       &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
-                      &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->chain_pix, &ctx->chain_long, &ctx->final_srgb8_alt};
+                      &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->chain_pix, &ctx->chain_long, &ctx->shadow_queue, &ctx->shadow_qstate, &ctx->final_srgb8_alt};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->timer0) cudaEventDestroy(ctx->timer0);

@@ -94,7 +94,7 @@ struct FrameLaunch {
 cudaError_t launch_set_carveout(int pct);
 cudaError_t launch_prefetch_l2(cudaStream_t s, const void* p, size_t bytes);
 cudaError_t launch_gbuffer(const FrameLaunch& L);
-cudaError_t launch_shadow(const FrameLaunch& L, unsigned int* persist_counter = nullptr);
+cudaError_t launch_shadow(const FrameLaunch& L, unsigned int* persist_counter = nullptr, uint32_t* shadow_queue = nullptr, unsigned int* shadow_qstate = nullptr);
 cudaError_t launch_denoise(const FrameLaunch& L, uint8_t* atrous_a = nullptr, uint8_t* atrous_b = nullptr);
 cudaError_t launch_build_order(cudaStream_t s, uint32_t* cost, uint32_t* order, uint32_t n);
 cudaError_t launch_resolve(const FrameLaunch& L, int* launches);
