@@ -10,7 +10,7 @@ sc = vk.HostScene(0)
 ctx = vk.Context(0); ctx.upload_scene(sc)
 ctx.set_camera(sc.camera(W, H))
 ctx.set_profiling(1)
-for chain, mb in ((7, 8), (8, 8), (8, 1), (8, 0)):
+for chain, mb in ((7, 8),):
     rows = []
     for k in range(24):
         ctx.flush_l2()

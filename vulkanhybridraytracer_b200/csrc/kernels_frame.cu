@@ -40,6 +40,9 @@
 #ifndef VKP_KEEPW_MANY
 #define VKP_KEEPW_MANY 1      /* many-sample shadow loop and Raytraced mode: trace_ray<.., KEEPW> (vkp_bvh.cuh) */
 #endif
+#ifndef VKP_CHAIN_VL_BOUNCES
+#define VKP_CHAIN_VL_BOUNCES 4  /* paths with at least this many bounces last frame go to k_chain_quad (schedules 7 / 8) */
+#endif
 #ifndef VKP_LB_CHAIN_TRACE
 #define VKP_LB_CHAIN_TRACE 8  /* the lean traversal kernels of the staged chain (k_chain_first, k_chain_shadow0) */
 #endif
@@ -1135,7 +1138,7 @@ __device__ __forceinline__ void chain_enqueue(const DFrame& F, size_t i, bool pa
         // schedule 7: two path lists in one array.  Paths that went beyond their first bounce in the previous frame (chain_long, one byte
         // per pixel, written by the chain kernels) are queued from slot 0 upwards for k_chain -- the few long paths start first --
         // the others from the last slot downwards for the staged kernels.  A wrong prediction costs time, never a bit.
-        const bool lng = path && F.chain_long[i] != 0;
+        const bool lng = path && F.chain_long[i] >= 2;
         const bool sht = path && !lng;
         const unsigned ml = __ballot_sync(0xffffffffu, lng), ms = __ballot_sync(0xffffffffu, sht);
         unsigned bl = 0, bs = 0;
@@ -1143,7 +1146,14 @@ __device__ __forceinline__ void chain_enqueue(const DFrame& F, size_t i, bool pa
         if (ms && lane == __ffs(ms) - 1) bs = atomicAdd(&F.path_count[4], (unsigned)__popc(ms));
         if (ml) bl = __shfl_sync(0xffffffffu, bl, __ffs(ml) - 1);
         if (ms) bs = __shfl_sync(0xffffffffu, bs, __ffs(ms) - 1);
-        if (lng) { const unsigned slot = bl + __popc(ml & ((1u << lane) - 1u)); F.chain_slot[i] = (int)slot; F.chain_pix[slot] = (int)i; }
+        if (lng) {
+            const unsigned slot = bl + __popc(ml & ((1u << lane) - 1u)); F.chain_slot[i] = (int)slot; F.chain_pix[slot] = (int)i;
+            // the handful of paths that made >= VKP_CHAIN_VL_BOUNCES bounces last frame set the end of the whole chain (every bounce is
+            // four dependent rays): they get a quad of lanes each (k_chain_quad) and k_chain skips them
+            const bool vl = F.chain_vl_list && F.chain_long[i] >= VKP_CHAIN_VL_BOUNCES;
+            F.chain_kind[slot] = vl ? 1 : 0;
+            if (vl) F.chain_vl_list[atomicAdd(&F.path_count[5], 1u)] = (int)slot;
+        }
         if (sht) { const unsigned slot = F.chain_cap - 1u - (bs + __popc(ms & ((1u << lane) - 1u))); F.chain_slot[i] = (int)slot; F.chain_pix[slot] = (int)i; }
         return;
     }
@@ -1201,7 +1211,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain(const __
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_paths) break;
         const unsigned int slot = base + (unsigned int)lane;
-        if (slot < n_paths) {
+        if (slot < n_paths && !(F.chain_vl_list && F.chain_kind[slot])) {
         const size_t i = (size_t)F.chain_pix[slot];
         const int py = (int)(i / (size_t)F.p.width), pxl = (int)(i - (size_t)py * F.p.width);
         const float4 pos4 = unpack_half4(F.position[i]);
@@ -1234,7 +1244,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain(const __
             origin = prd.origin; direction = prd.direction;
         }
         F.chain_len[slot] = n;
-        if (F.chain_long) F.chain_long[i] = n > 1 ? 1 : 0;
+        if (F.chain_long) F.chain_long[i] = (uint8_t)n;
         }
         __syncwarp();
     }
@@ -1404,7 +1414,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_warp(con
             if (!hit || !(prd.scatter > 0.0f)) break;
             origin = prd.origin; direction = prd.direction;
         }
-        if (lane == 0) { F.chain_len[slot] = n; if (F.chain_long) F.chain_long[i] = n > 1 ? 1 : 0; }
+        if (lane == 0) { F.chain_len[slot] = n; if (F.chain_long) F.chain_long[i] = (uint8_t)n; }
     }
     add_counter(F.counters, 2, lane == 0 ? n_refl : 0u);       // the rays are the warp's: count them once
     add_counter(F.counters, 3, lane == 0 ? n_sec : 0u);
@@ -1540,17 +1550,20 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_quad(con
     uint32_t* const sstack = s_trav + threadIdx.x;
     const unsigned int full = 0xffffffffu;
     const int lane = (int)(threadIdx.x & 31u), q = lane & 3, quad = lane >> 2;
-    const unsigned int n_paths = F.path_count[0];
+    // the very long paths of the split (chain_vl_list, head path_count[6]) -- or, with VKP_CHAIN_LONG_QUAD=1, the whole long list
+    const bool vlist = F.chain_vl_list != nullptr && !F.chain_quad_all;
+    const unsigned int n_paths = vlist ? F.path_count[5] : F.path_count[0];
     unsigned int n_refl = 0, n_sec = 0, n_unused = 0;
     TravCount tc = {0u, 0u, 0u};
     TravCount* const tcp = F.count_trav ? &tc : nullptr;
     while (true) {
         unsigned int base = 0u;
-        if (lane == 0) base = atomicAdd(&F.path_count[1], 8u);
+        if (lane == 0) base = atomicAdd(&F.path_count[vlist ? 6 : 1], 8u);
         base = __shfl_sync(full, base, 0);
         if (base >= n_paths) break;
-        const unsigned int slot = base + (unsigned int)quad;
-        bool active = slot < n_paths;
+        const unsigned int item = base + (unsigned int)quad;
+        bool active = item < n_paths;
+        const unsigned int slot = !active ? 0u : vlist ? (unsigned int)F.chain_vl_list[item] : item;
         size_t i = 0;
         float3 origin = f3s(0.0f), direction = f3s(0.0f), ro = f3s(0.0f);
         Payload prd; prd.seed = 0u;
@@ -1583,7 +1596,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_quad(con
                 if (q == 0) F.chain_buf[(size_t)slot * VKP_CHAIN_MAX + n] = make_float4(prd.color.x, prd.color.y, prd.color.z, 0.0f);
                 n++;
                 if (!hit || !(prd.scatter > 0.0f) || n >= F.p.max_bounces) {
-                    if (q == 0) { F.chain_len[slot] = n; if (F.chain_long) F.chain_long[i] = n > 1 ? 1 : 0; }
+                    if (q == 0) { F.chain_len[slot] = n; if (F.chain_long) F.chain_long[i] = (uint8_t)n; }
                     active = false;
                 } else { origin = prd.origin; direction = prd.direction; }
             }
@@ -1618,7 +1631,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_shade0(c
             } else shade_miss(S, direction, prd);
             F.chain_buf[(size_t)slot * VKP_CHAIN_MAX] = make_float4(prd.color.x, prd.color.y, prd.color.z, 0.0f);
             again = hit && (prd.scatter > 0.0f) && F.p.max_bounces > 1;
-            if (F.chain_long) F.chain_long[i] = again ? 1 : 0;
+            if (F.chain_long) F.chain_long[i] = again ? 2 : 1;          // (k_chain_rest writes the real count of the paths that go on)
             if (!again) F.chain_len[slot] = 1;
             else {
                 item.a = make_float4(prd.origin.x, prd.origin.y, prd.origin.z, __uint_as_float(slot));
@@ -1663,6 +1676,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_CHAIN) k_chain_rest(con
             origin = prd.origin; direction = prd.direction;
         }
         F.chain_len[slot] = n;
+        if (F.chain_long) F.chain_long[(size_t)F.chain_pix[slot]] = (uint8_t)n;
     }
     add_counter(F.counters, 2, n_refl);
     add_counter(F.counters, 3, n_sec);
@@ -1703,6 +1717,13 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_RESOLVE) k_resolve(cons
         float3 material = unorm3(F.material[i]);
         float3 emissive = unorm3(F.emissive[i]);
         const bool background = pos4.w == 0.0f && nrm4.w == 0.0f;
+        if (background && shadingMode == 0 && !F.fused) {
+            // a sky pixel (material 0 diffuse): no light loop, no path -- the pixel ends as its albedo, the sky texel (hybridRaygen.rgen:182-183);
+            // none of the view / irradiance / Fresnel terms below can reach the result (57 % of the 1080p default frame is sky)
+            const float4 outc = make_float4(albedo.x, albedo.y, albedo.z, 1.0f);
+            F.final_f32[i] = outc;
+            F.final_srgb8[i] = post_pixel(F.lut_post, outc);
+        } else {
         const float roughness = material.y, metallic = material.z;
         const float3 F0 = mix3(f3s(0.04f), albedo, metallic);
         const float3 camPosition = f3(F.cam.inv_view[12], F.cam.inv_view[13], F.cam.inv_view[14]);
@@ -1817,6 +1838,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_RESOLVE) k_resolve(cons
             item.b = make_float4(direction.x, direction.y, direction.z, __uint_as_float(prd.seed));
             item.c = make_float4(rayColor.x, rayColor.y, rayColor.z, 0.0f);
             item.d = background ? make_float4(albedo.x, albedo.y, albedo.z, 0.0f) : make_float4(tail.x, tail.y, tail.z, 0.0f);
+        }
         }
     }
     if (CHAIN == 1) path_push(F.path_q[0], &F.path_count[0], wants_path, item);
@@ -2326,6 +2348,13 @@ cudaError_t launch_chain_after_first(const FrameLaunch& L, cudaStream_t stream)
     k_chain_rest<<<g2, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
     return cudaGetLastError();
 }
+// schedules 7 / 8: the very long paths, a quad of lanes each, on their own stream beside k_chain
+cudaError_t launch_chain_very_long(const FrameLaunch& L, cudaStream_t stream)
+{
+    if (!L.frame.chain_vl_list) return cudaSuccess;
+    k_chain_quad<<<296, 32, 0, stream>>>(L.scene, L.frame);          // 8 paths per one-warp CTA: room for 2 368 very long paths in flight
+    return cudaGetLastError();
+}
 cudaError_t launch_chain_first_only(const FrameLaunch& L, cudaStream_t stream)
 {
     k_chain_first<<<frame_grid(L).x / 4u + 1u, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
@@ -2419,7 +2448,7 @@ cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t 
     // [2] = number of paths that go on after their first bounce (staged chain, mode 4)
     cudaError_t e = cudaSuccess;
     if (!L.frame.chain_in_gbuffer) {          // schedule 8: the counters were cleared before k_gbuffer, which queued the paths itself
-        if ((e = launch_stage_words(stream, L.frame.path_count, nullptr, 5 * sizeof(unsigned int))) != cudaSuccess) return e;
+        if ((e = launch_stage_words(stream, L.frame.path_count, nullptr, 7 * sizeof(unsigned int))) != cudaSuccess) return e;
         k_chain_scan<<<frame_grid(L), 128, 0, stream>>>(L.scene, L.frame);
     }
     if (after_scan && (e = cudaEventRecord(after_scan, stream)) != cudaSuccess) return e;
@@ -2440,7 +2469,9 @@ cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t 
         }
         k_chain_q<<<(unsigned)(per_sm6 * n_sm6), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame, tag, cont_cap);
     } else if (L.frame.p.wavefront == 3) k_chain_warp<<<148 * VKP_LB_CHAIN, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
-    else if (L.frame.p.wavefront >= 7 && chain_long_by_quad()) {
+    else if (L.frame.p.wavefront >= 7 && getenv("VKP_TIMING_SKIP_LONG")) {
+        // timing experiments only (the image is then wrong): schedule 7 without its long-path kernel
+    } else if (L.frame.p.wavefront >= 7 && chain_long_by_quad()) {
         static int n_smq = 0;
         if (!n_smq) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_smq, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_smq <= 0) n_smq = 148; }
         k_chain_quad<<<(unsigned)(VKP_LB_CHAIN * n_smq), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
@@ -2464,7 +2495,14 @@ cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t 
             if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
         }
         (void)px_blocks;
-        k_chain<<<(unsigned)(per_sm * n_sm), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
+        // Schedules 7 / 8 hand k_chain only the ~15 k long paths: 470 warps' worth, each alive for hundreds of microseconds.  Registers
+        // are given back per CTA, so a 128-thread CTA with one warp still walking kept 21.5 K registers from k_shadow -- with 444 such
+        // CTAs that was most of the GPU's register file (measured: the long paths cost the frame 0.08 ms).  One-warp CTAs return theirs
+        // as soon as their own 32 paths are done (VKP_CHAIN_BLOCK=128 for the old shape).
+        static int cblock = 0;
+        if (!cblock) { const char* e = getenv("VKP_CHAIN_BLOCK"); cblock = e ? atoi(e) : 32; if (cblock != 32 && cblock != 64 && cblock != 128) cblock = 32; }
+        const int blk = L.frame.p.wavefront >= 7 ? cblock : VKP_TRAV_BLOCK;
+        k_chain<<<(unsigned)(per_sm * n_sm * (VKP_TRAV_BLOCK / blk)), blk, 0, stream>>>(L.scene, L.frame);
     }
     return cudaGetLastError();
 }

@@ -67,6 +67,9 @@ struct vkp_ctx {
     int denoised_cur = 0;
     int plane_w = 0, plane_h = 0, plane_lights = 0;
     DevBuf shadow_queue, shadow_qstate;   // many-sample shadow pass: compacted (pixel, light) lists and their counters
+    DevBuf chain_vl, chain_kind;          // schedules 7 / 8: list of the very long paths' slots, and the per-slot mark k_chain skips them by
+    cudaStream_t chain_stream3 = nullptr;
+    cudaEvent_t ev_chain3 = nullptr;
     DevBuf chain_long;                // one byte per pixel: last frame's path went beyond its first bounce (chain schedule 7)
     cudaStream_t chain_stream2 = nullptr;
     cudaEvent_t ev_chain2 = nullptr, ev_shadow = nullptr;
@@ -77,6 +80,8 @@ struct vkp_ctx {
     cudaEvent_t ev_gbuffer = nullptr, ev_chain = nullptr, ev_scan = nullptr;
     cudaEvent_t ev_chain_t0 = nullptr, ev_chain_t1 = nullptr;     // profiling: the chain on its own stream (vkp_counters.ms_stage[7], ms_tlas = its end in the frame)
     bool chain_timed = false;
+    bool debug_chain_timing = false;  // VKP_DEBUG_CHAIN_TIMING=1: print when the long-path kernel ended (development aid)
+    cudaEvent_t ev_chain_long = nullptr;
     uint32_t chain_tag = 0;           // launch counter: the "written" mark of the continuation items of chain schedule 6 (never 0)
     // longest-first CTA schedule of k_gbuffer [0] and k_shadow [1], rebuilt every frame from the previous frame's per-block cycles
     DevBuf cta_cost[2], cta_order[2];
@@ -226,6 +231,7 @@ int ensure_planes(vkp_ctx* ctx)
     CK(ctx->path_count.ensure(sizeof(unsigned int) * (VKP_MAX_BOUNCES + 2)));
     CK(ctx->chain_buf.ensure(px * sizeof(float4) * VKP_CHAIN_MAX)); CK(ctx->chain_len.ensure(px * sizeof(int))); CK(ctx->chain_slot.ensure(px * sizeof(int))); CK(ctx->chain_pix.ensure(px * sizeof(int)));
     CK(ctx->chain_long.ensure(px)); CK(cudaMemsetAsync(ctx->chain_long.p, 0, px, ctx->stream));
+    CK(ctx->chain_vl.ensure(px * sizeof(int))); CK(ctx->chain_kind.ensure(px)); CK(cudaMemsetAsync(ctx->chain_kind.p, 0, px, ctx->stream));
     ctx->plane_w = W; ctx->plane_h = H; ctx->plane_lights = L;
     // defined initial state: history and accumulation start at zero (blur.comp:73 reads uninitialised memory upstream)
     CK(cudaMemsetAsync(ctx->position.p, 0, px * 8, ctx->stream)); CK(cudaMemsetAsync(ctx->normal.p, 0, px * 8, ctx->stream));
@@ -376,6 +382,13 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.chain_base = F.p.wavefront == 6 ? F.path_q[0] : F.path_q[1];       // path_q[1] is schedule 6's continuation queue, path_q[0] holds the staged kernels' records
     F.chain_long = ctx->chain_long.as<uint8_t>();
     F.chain_split = F.p.wavefront >= 7 ? 1 : 0;
+    {
+        static int vl = -1, quad_all = -1;
+        if (vl < 0) { const char* e = getenv("VKP_CHAIN_VERY_LONG"); vl = e ? (atoi(e) != 0) : 1; const char* q = getenv("VKP_CHAIN_LONG_QUAD"); quad_all = q ? (atoi(q) != 0) : 0; }
+        F.chain_vl_list = (F.chain_split && vl && !quad_all) ? ctx->chain_vl.as<int>() : nullptr;
+        F.chain_kind = ctx->chain_kind.as<uint8_t>();
+        F.chain_quad_all = quad_all;
+    }
     F.chain_in_gbuffer = 0; F.first_blocks = 0u; F.mid_at = 0u; F.chain_tag = 1u;      // schedule 8 switches them on inside vkp_render
     F.chain_cap = (unsigned int)((size_t)F.p.width * F.p.height);
     const int total = F.tiles_x * F.tiles_y;
@@ -439,7 +452,7 @@ int apply_l2_window(vkp_ctx* ctx)
         attr.accessPolicyWindow.num_bytes = 0;      // disables the window
         attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal; attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
     }
-    cudaStream_t streams[] = {ctx->stream, ctx->own_stream, ctx->chain_stream, ctx->chain_stream2};
+    cudaStream_t streams[] = {ctx->stream, ctx->own_stream, ctx->chain_stream, ctx->chain_stream2, ctx->chain_stream3};
     for (cudaStream_t st : streams) if (st) CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
     if (!on && ctx->l2_set_aside) { cudaCtxResetPersistingL2Cache(); }
     return VKP_OK;
@@ -551,6 +564,7 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
         const bool late = chain2 && L.frame.p.wavefront >= 5;      // the resolve does not wait for the chain: k_resolve_paths merges it afterwards
         if (chain2 && !ctx->chain_in_flight) {
             CK(launch_chain(L, ctx->stream, nullptr, ++ctx->chain_tag, chain_cont_cap(ctx))); ctx->last_launches += chain_launches(L);
+            if (L.frame.chain_vl_list) { CK(launch_chain_very_long(L, ctx->stream)); ctx->last_launches++; }
             if (L.frame.p.wavefront >= 7) { CK(launch_chain_staged(L, ctx->stream)); ctx->last_launches += L.scene.n_lights > 0 ? 4u : 3u; }
         }      // stand-alone stage: serial (clear + scan + chain)
         if (chain2 && ctx->chain_in_flight && !late) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0)); ctx->chain_in_flight = false; }
@@ -628,11 +642,14 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
         }
         cudaEventCreateWithFlags(&ctx->ev_chain2, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_shadow, cudaEventDisableTiming);
+        cudaStreamCreateWithPriority(&ctx->chain_stream3, cudaStreamNonBlocking, hi);
+        cudaEventCreateWithFlags(&ctx->ev_chain3, cudaEventDisableTiming);
         for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags(&ctx->ev_stage_done[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_order_done[k], cudaEventDisableTiming); }
         if (const char* e = getenv("VKP_SCHEDULE")) ctx->schedule = atoi(e) != 0;
         if (const char* e = getenv("VKP_SEED_PLANE")) ctx->use_seed_plane = atoi(e) != 0;
         if (const char* e = getenv("VKP_PREFETCH")) ctx->prefetch = atoi(e);
         if (const char* e = getenv("VKP_SHADOW_WAIT_SCAN")) ctx->shadow_wait_scan = atoi(e) != 0;
+        if (const char* e = getenv("VKP_DEBUG_CHAIN_TIMING")) ctx->debug_chain_timing = atoi(e) != 0;
         cudaEventCreateWithFlags(&ctx->ev_gbuffer, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_scan, cudaEventDisableTiming);
@@ -683,7 +700,7 @@ void vkp_destroy(vkp_ctx* ctx)
     if (ctx->ev_updated) cudaEventDestroy(ctx->ev_updated);
     DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_textures, &ctx->position, &ctx->seed, &ctx->normal, &ctx->albedo, &ctx->motion,
                       &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
-                      &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->chain_pix, &ctx->chain_long, &ctx->shadow_queue, &ctx->shadow_qstate, &ctx->final_srgb8_alt};
+                      &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->chain_pix, &ctx->chain_long, &ctx->chain_vl, &ctx->chain_kind, &ctx->shadow_queue, &ctx->shadow_qstate, &ctx->final_srgb8_alt};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->timer0) cudaEventDestroy(ctx->timer0);
@@ -707,6 +724,9 @@ void vkp_destroy(vkp_ctx* ctx)
     if (ctx->ev_prefetch) cudaEventDestroy(ctx->ev_prefetch);
     if (ctx->ev_chain2) cudaEventDestroy(ctx->ev_chain2);
     if (ctx->ev_shadow) cudaEventDestroy(ctx->ev_shadow);
+    if (ctx->ev_chain_long) cudaEventDestroy(ctx->ev_chain_long);
+    if (ctx->ev_chain3) cudaEventDestroy(ctx->ev_chain3);
+    if (ctx->chain_stream3) cudaStreamDestroy(ctx->chain_stream3);
     if (ctx->chain_stream2) cudaStreamDestroy(ctx->chain_stream2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -1048,7 +1068,7 @@ int vkp_render(vkp_ctx* ctx)
     // (per-light any-hit rays, shading, stragglers) follows the shadow pass on the third stream, beside the filter and the resolve
     const bool folded = chained && ctx->params.wavefront == 8;
     if (folded) {
-        CK(launch_stage_words(ctx->stream, ctx->path_count.p, nullptr, 5 * sizeof(unsigned int)));
+        CK(launch_stage_words(ctx->stream, ctx->path_count.p, nullptr, 7 * sizeof(unsigned int)));
         L.frame.chain_in_gbuffer = 1;
         ctx->last_launches++;
     }
@@ -1075,9 +1095,22 @@ int vkp_render(vkp_ctx* ctx)
             }
             CK(launch_chain(L, ctx->chain_stream, ctx->ev_scan, ++ctx->chain_tag, chain_cont_cap(ctx)));
             ctx->last_launches += folded ? 1u : chain_launches(L);
+            if (L.frame.chain_vl_list) {
+                // the very long paths, a quad of lanes each, beside k_chain (which skips them)
+                CK(cudaStreamWaitEvent(ctx->chain_stream3, ctx->ev_scan, 0));
+                CK(launch_chain_very_long(L, ctx->chain_stream3));
+                CK(cudaEventRecord(ctx->ev_chain3, ctx->chain_stream3));
+                CK(cudaStreamWaitEvent(ctx->chain_stream, ctx->ev_chain3, 0));
+                ctx->last_launches++;
+            }
+            if (ctx->profiling && ctx->debug_chain_timing) {
+                if (!ctx->ev_chain_long) CK(cudaEventCreate(&ctx->ev_chain_long));
+                CK(cudaEventRecord(ctx->ev_chain_long, ctx->chain_stream));          // end of the long-path kernel alone (before it waits for the staged half)
+            }
             if (ctx->params.wavefront == 7) {
                 // the bulk of the paths (predicted to end after one bounce) through the lean staged kernels, beside k_chain's long ones
                 CK(cudaStreamWaitEvent(ctx->chain_stream2, ctx->ev_scan, 0));
+                if (!getenv("VKP_TIMING_SKIP_STAGED"))         // timing experiments only (the image is then wrong): which half ends the chain?
                 CK(launch_chain_staged(L, ctx->chain_stream2));
                 CK(cudaEventRecord(ctx->ev_chain2, ctx->chain_stream2));
                 CK(cudaStreamWaitEvent(ctx->chain_stream, ctx->ev_chain2, 0));       // ev_chain below then means: both halves are done
@@ -1359,6 +1392,10 @@ int vkp_get_counters(vkp_ctx* ctx, vkp_counters* out)
             CK(cudaEventSynchronize(ctx->ev_chain_t1));
             CK(cudaEventElapsedTime(&out->ms_stage[7], ctx->ev_chain_t0, ctx->ev_chain_t1));
             CK(cudaEventElapsedTime(&out->ms_tlas, ctx->ev[0], ctx->ev_chain_t1));
+            if (ctx->debug_chain_timing && ctx->ev_chain_long) {
+                float a = 0.f;
+                if (cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev_chain_long) == cudaSuccess) fprintf(stderr, "vkp: long-path kernel ends at %.3f ms, chain stream at %.3f ms\n", a, out->ms_tlas);
+            }
             ctx->chain_timed = false;
         }
     }

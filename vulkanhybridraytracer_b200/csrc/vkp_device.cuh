@@ -179,6 +179,9 @@ struct DFrame {
     PathItem* chain_base;           // schedules 5-7: per path slot, the direct term (c) and the ambient tail (d) k_resolve<3> leaves for k_resolve_paths
     uint8_t* chain_long;            // per pixel: the path of this pixel went beyond its first bounce in the previous frame (schedule 7's prediction)
     int chain_split;                // schedule 7: two path lists (see k_chain_scan)
+    int* chain_vl_list;             // schedules 7 / 8: slots of the paths predicted very long (k_chain_quad's list; NULL = no such split)
+    uint8_t* chain_kind;            // per slot of the long list: 1 = very long (k_chain skips it)
+    int chain_quad_all;             // VKP_CHAIN_LONG_QUAD=1: k_chain_quad walks the whole long list
     unsigned int chain_cap;         // slots in the path arrays (= pixels)
     int chain_in_gbuffer;           // schedule 8: k_gbuffer compacts the path pixels itself (no k_chain_scan)
     unsigned int first_blocks;      // schedule 8: leading blocks of k_shadow's grid that trace the queued paths' first rays (0 otherwise)

@@ -103,6 +103,7 @@ cudaError_t launch_resolve_paths(const FrameLaunch& L);
 cudaError_t launch_chain_staged(const FrameLaunch& L, cudaStream_t stream);
 cudaError_t launch_chain_after_first(const FrameLaunch& L, cudaStream_t stream);
 cudaError_t launch_chain_first_only(const FrameLaunch& L, cudaStream_t stream);
+cudaError_t launch_chain_very_long(const FrameLaunch& L, cudaStream_t stream);
 bool shadow_is_persistent(const FrameLaunch& L);
 unsigned int chain_first_blocks(const FrameLaunch& L);
 cudaError_t launch_post(const FrameLaunch& L);
