@@ -1,3 +1,3 @@
-TAG=r3t; . scripts/ab_r2n.sh
-run vl4 A=1
-run novl VKP_CHAIN_VERY_LONG=0
+TAG=r3w; . scripts/ab_r2n.sh
+run scan_gb A=1
+run scan_sep VKP_SCAN_IN_GBUFFER=0

@@ -586,7 +586,9 @@ __device__ __forceinline__ void shadow_patch(const DScene& S, const DFrame& F, u
     }
 }
 
-template <int MINB, bool ONE>
+// FOLD: the grid also carries the first-bounce blocks of schedule 8 (an instantiation of its own: the extra code paths cost the plain
+// kernel 550 bytes of spills and 0.02 ms when they shared it)
+template <int MINB, bool ONE, bool FOLD = false>
 __global__ void __launch_bounds__(VKP_TRAV_BLOCK, MINB) k_shadow(const __grid_constant__ DScene S, const __grid_constant__ DFrame F)
 {
     __shared__ uint32_t s_trav[VKP_TRAV_SMEM_WORDS];
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, MINB) k_shadow(const __grid_co
     unsigned int nrays = 0;
     TravCount tc = {0u, 0u, 0u};
     TravCount* const tcp = F.count_trav ? &tc : nullptr;      // traversal accounting only on request (vkp_set_profiling(ctx, 2))
-    if (blockIdx.x < F.first_blocks) {
+    if (FOLD && blockIdx.x < F.first_blocks) {
         // schedule 8: the leading blocks of the grid trace the FIRST reflection / refraction ray of the queued paths (k_chain_first's work)
         // inside this kernel: the long rays among them start at t = 0 and their tail hides under 48 000 blocks of shadow rays instead
         // of ending a kernel of its own
@@ -605,8 +607,8 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, MINB) k_shadow(const __grid_co
         if (F.count_trav) add_trav(F.counters, tc);
         return;
     }
-    unsigned int hb = blockIdx.x - F.first_blocks;
-    if (F.first_blocks) {
+    unsigned int hb = FOLD ? blockIdx.x - F.first_blocks : blockIdx.x;
+    if (FOLD && F.first_blocks) {
         // ... and further down the grid, first_blocks x n_lights blocks trace the per-light any-hit rays of those first hits
         // (k_chain_shadow0's work).  They are dispatched long after the leading blocks, whose records they read -- each carries a tag
         // written with st.release when it is complete -- so the wait below practically never spins, and it cannot deadlock: a block
@@ -2262,7 +2264,7 @@ cudaError_t launch_set_carveout(int pct)
 {
     if (pct < 0) return cudaSuccess;
     const void* fns[] = {(const void*)k_gbuffer, (const void*)k_shadow<VKP_LB_SHADOW, true>, (const void*)k_shadow<VKP_LB_SHADOW, false>,
-                         (const void*)k_shadow<VKP_LB_SHADOW_MANY, false>, (const void*)k_chain, (const void*)k_chain_quad, (const void*)k_chain_q, (const void*)k_chain_scan, (const void*)k_chain_warp,
+                         (const void*)k_shadow<VKP_LB_SHADOW_MANY, false>, (const void*)k_shadow<VKP_LB_SHADOW, true, true>, (const void*)k_chain, (const void*)k_chain_quad, (const void*)k_chain_q, (const void*)k_chain_scan, (const void*)k_chain_warp,
                          (const void*)k_chain_first, (const void*)k_chain_shadow0, (const void*)k_chain_shade0, (const void*)k_chain_rest,
                          (const void*)k_denoise, (const void*)k_denoise_accumulate4, (const void*)k_resolve<0>, (const void*)k_resolve<1>,
                          (const void*)k_resolve<2>, (const void*)k_resolve<3>, (const void*)k_resolve_paths, (const void*)k_bounce, (const void*)k_build_order,
@@ -2321,7 +2323,13 @@ cudaError_t launch_shadow(const FrameLaunch& L, unsigned int* persist_counter, u
         else k_shadow_persistent<VKP_LB_SHADOW, false><<<grid, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame, persist_counter, units);
         return cudaGetLastError();
     }
-    g.x += L.frame.first_blocks * (1u + (unsigned)L.scene.n_lights);   // schedule 8: first-bounce blocks lead the grid, their any-hit blocks sit inside it
+    if (L.frame.first_blocks) {
+        g.x += L.frame.first_blocks * (1u + (unsigned)L.scene.n_lights);   // schedule 8: first-bounce blocks lead the grid, their any-hit blocks sit inside it
+        if (L.frame.p.shadow_samples >= 4) k_shadow<VKP_LB_SHADOW_MANY, false, true><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);
+        else if (L.frame.p.shadow_samples == 1) k_shadow<VKP_LB_SHADOW, true, true><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);
+        else k_shadow<VKP_LB_SHADOW, false, true><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);
+        return cudaGetLastError();
+    }
     if (L.frame.p.shadow_samples >= 4) k_shadow<VKP_LB_SHADOW_MANY, false><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);
     else if (L.frame.p.shadow_samples == 1) k_shadow<VKP_LB_SHADOW, true><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);
     else k_shadow<VKP_LB_SHADOW, false><<<g, VKP_TRAV_BLOCK, 0, L.stream>>>(L.scene, L.frame);

@@ -93,6 +93,7 @@ struct vkp_ctx {
     int prefetch = 0;                 // VKP_PREFETCH: 1 = stream the BVH arena into L2 at the start of every frame, 2 = vertex / index buffers too
     cudaEvent_t ev_prefetch = nullptr;
     bool shadow_wait_scan = false;
+    bool scan_in_gbuffer = false;     // schedule 7: path queueing inside k_gbuffer instead of k_chain_scan (VKP_SCAN_IN_GBUFFER=1; measured neutral)
     bool use_seed_plane = true;       // k_gbuffer evaluates TEA once per pixel for the frame's later stages (VKP_SEED_PLANE=0: every stage evaluates it)
     bool chain_in_flight = false;
     // multi-GPU: FINAL_SRGB8 is double-buffered (vkp_set_output_buffer) and may be redirected into rank 0's two buffers over NVLink
@@ -384,8 +385,11 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.chain_split = F.p.wavefront >= 7 ? 1 : 0;
     {
         static int vl = -1, quad_all = -1;
-        if (vl < 0) { const char* e = getenv("VKP_CHAIN_VERY_LONG"); vl = e ? (atoi(e) != 0) : 1; const char* q = getenv("VKP_CHAIN_LONG_QUAD"); quad_all = q ? (atoi(q) != 0) : 0; }
-        F.chain_vl_list = (F.chain_split && vl && !quad_all) ? ctx->chain_vl.as<int>() : nullptr;
+        // -1 = by default only on a tile-sharded frame: there the chain's end is the frame's floor and the quads are worth 5 % (8 GPUs);
+        // on one GPU they end the chain earlier and lengthen the shadow stage by as much
+        if (quad_all < 0) { const char* e = getenv("VKP_CHAIN_VERY_LONG"); vl = e ? (atoi(e) != 0) : -1; const char* q = getenv("VKP_CHAIN_LONG_QUAD"); quad_all = q ? (atoi(q) != 0) : 0; }
+        const bool use_vl = vl >= 0 ? vl != 0 : ctx->world > 1;
+        F.chain_vl_list = (F.chain_split && use_vl && !quad_all) ? ctx->chain_vl.as<int>() : nullptr;
         F.chain_kind = ctx->chain_kind.as<uint8_t>();
         F.chain_quad_all = quad_all;
     }
@@ -650,6 +654,7 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
         if (const char* e = getenv("VKP_PREFETCH")) ctx->prefetch = atoi(e);
         if (const char* e = getenv("VKP_SHADOW_WAIT_SCAN")) ctx->shadow_wait_scan = atoi(e) != 0;
         if (const char* e = getenv("VKP_DEBUG_CHAIN_TIMING")) ctx->debug_chain_timing = atoi(e) != 0;
+        if (const char* e = getenv("VKP_SCAN_IN_GBUFFER")) ctx->scan_in_gbuffer = atoi(e) != 0;
         cudaEventCreateWithFlags(&ctx->ev_gbuffer, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_scan, cudaEventDisableTiming);
@@ -1067,7 +1072,10 @@ int vkp_render(vkp_ctx* ctx)
     // schedule 8: k_gbuffer queues the path pixels itself, the first reflection rays ride in k_shadow's grid, and what depends on them
     // (per-light any-hit rays, shading, stragglers) follows the shadow pass on the third stream, beside the filter and the resolve
     const bool folded = chained && ctx->params.wavefront == 8;
-    if (folded) {
+    // schedules 7 and 8: k_gbuffer queues the path pixels itself (no k_chain_scan pass over the frame on the chain's critical path;
+    // VKP_SCAN_IN_GBUFFER=0 keeps the separate pass for schedule 7)
+    const bool scan_in_gbuffer = folded || (chained && ctx->params.wavefront == 7 && ctx->scan_in_gbuffer);
+    if (scan_in_gbuffer) {
         CK(launch_stage_words(ctx->stream, ctx->path_count.p, nullptr, 7 * sizeof(unsigned int)));
         L.frame.chain_in_gbuffer = 1;
         ctx->last_launches++;
@@ -1094,7 +1102,7 @@ int vkp_render(vkp_ctx* ctx)
                 CK(cudaEventRecord(ctx->ev_chain_t0, ctx->chain_stream));
             }
             CK(launch_chain(L, ctx->chain_stream, ctx->ev_scan, ++ctx->chain_tag, chain_cont_cap(ctx)));
-            ctx->last_launches += folded ? 1u : chain_launches(L);
+            ctx->last_launches += scan_in_gbuffer ? 1u : chain_launches(L);
             if (L.frame.chain_vl_list) {
                 // the very long paths, a quad of lanes each, beside k_chain (which skips them)
                 CK(cudaStreamWaitEvent(ctx->chain_stream3, ctx->ev_scan, 0));
