@@ -1,3 +1,4 @@
-TAG=r3w; . scripts/ab_r2n.sh
-run scan_gb A=1
-run scan_sep VKP_SCAN_IN_GBUFFER=0
+TAG=r3z; . scripts/ab_r2n.sh
+run sky A=1
+run nosky VKP_SKY_CODES=0
+run sky2 A=1

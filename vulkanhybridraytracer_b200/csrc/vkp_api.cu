@@ -92,6 +92,8 @@ struct vkp_ctx {
     int schedule = 1;                 // 0 = hardware block order, 1 = longest first (VKP_SCHEDULE=0|1)
     int prefetch = 0;                 // VKP_PREFETCH: 1 = stream the BVH arena into L2 at the start of every frame, 2 = vertex / index buffers too
     cudaEvent_t ev_prefetch = nullptr;
+    bool use_sky_codes = true;        // VKP_SKY_CODES=0: every sky pixel redoes its light arithmetic in k_shadow
+    DevBuf sky_shadow;
     bool shadow_wait_scan = false;
     bool scan_in_gbuffer = false;     // schedule 7: path queueing inside k_gbuffer instead of k_chain_scan (VKP_SCAN_IN_GBUFFER=1; measured neutral)
     bool use_seed_plane = true;       // k_gbuffer evaluates TEA once per pixel for the frame's later stages (VKP_SEED_PLANE=0: every stage evaluates it)
@@ -369,6 +371,7 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.position = ctx->position.as<uint2>(); F.normal = ctx->normal.as<uint2>(); F.albedo = ctx->albedo.as<uchar4>();
     F.motion = ctx->motion.as<uint32_t>(); F.material = ctx->material.as<uchar4>(); F.emissive = ctx->emissive.as<uchar4>();
     F.hit_ids = ctx->hit_ids.as<int2>(); F.final_f32 = ctx->final_f32.as<float4>();
+    F.sky_shadow_w = nullptr; F.sky_shadow_r = nullptr;
     F.seed_w = nullptr; F.seed_r = nullptr;       // vkp_render (Hybrid) switches the seed plane on for the frame it renders
     F.final_srgb8 = ctx->peer_srgb8[ctx->out_sel] ? reinterpret_cast<uchar4*>(ctx->peer_srgb8[ctx->out_sel])
                                                   : (ctx->out_sel ? ctx->final_srgb8_alt.as<uchar4>() : ctx->final_srgb8.as<uchar4>());
@@ -652,6 +655,7 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
         if (const char* e = getenv("VKP_SCHEDULE")) ctx->schedule = atoi(e) != 0;
         if (const char* e = getenv("VKP_SEED_PLANE")) ctx->use_seed_plane = atoi(e) != 0;
         if (const char* e = getenv("VKP_PREFETCH")) ctx->prefetch = atoi(e);
+        if (const char* e = getenv("VKP_SKY_CODES")) ctx->use_sky_codes = atoi(e) != 0;
         if (const char* e = getenv("VKP_SHADOW_WAIT_SCAN")) ctx->shadow_wait_scan = atoi(e) != 0;
         if (const char* e = getenv("VKP_DEBUG_CHAIN_TIMING")) ctx->debug_chain_timing = atoi(e) != 0;
         if (const char* e = getenv("VKP_SCAN_IN_GBUFFER")) ctx->scan_in_gbuffer = atoi(e) != 0;
@@ -705,7 +709,7 @@ void vkp_destroy(vkp_ctx* ctx)
     if (ctx->ev_updated) cudaEventDestroy(ctx->ev_updated);
     DevBuf* bufs[] = {&ctx->d_materials, &ctx->d_textures, &ctx->position, &ctx->seed, &ctx->normal, &ctx->albedo, &ctx->motion,
                       &ctx->material, &ctx->emissive, &ctx->hit_ids, &ctx->final_f32, &ctx->final_srgb8, &ctx->shadow, &ctx->denoised[0], &ctx->denoised[1],
-                      &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->chain_pix, &ctx->chain_long, &ctx->chain_vl, &ctx->chain_kind, &ctx->shadow_queue, &ctx->shadow_qstate, &ctx->final_srgb8_alt};
+                      &ctx->sync_buf, &ctx->counters, &ctx->io_tmp, &ctx->io_tmp2, &ctx->flush, &ctx->path_q[0], &ctx->path_q[1], &ctx->path_count, &ctx->luts, &ctx->chain_buf, &ctx->chain_len, &ctx->chain_slot, &ctx->chain_pix, &ctx->sky_shadow, &ctx->chain_long, &ctx->chain_vl, &ctx->chain_kind, &ctx->shadow_queue, &ctx->shadow_qstate, &ctx->final_srgb8_alt};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->timer0) cudaEventDestroy(ctx->timer0);
@@ -1068,6 +1072,8 @@ int vkp_render(vkp_ctx* ctx)
     else if (ctx->params.mode == VKP_MODE_DEFERRED) { seq = deferred; n = 2; }
     const bool seeds = ctx->params.mode == VKP_MODE_HYBRID && ctx->use_seed_plane;
     if (seeds) L.frame.seed_w = ctx->seed.as<uint32_t>();
+    const bool sky_codes = ctx->params.mode == VKP_MODE_HYBRID && ctx->use_sky_codes;
+    if (sky_codes) { CK(ctx->sky_shadow.ensure(64 * sizeof(short))); L.frame.sky_shadow_w = ctx->sky_shadow.as<short>(); }
     const bool chained = ctx->params.mode == VKP_MODE_HYBRID && ctx->params.wavefront >= 2 && ctx->params.max_bounces <= VKP_CHAIN_MAX && L.n_own_tiles > 0;
     // schedule 8: k_gbuffer queues the path pixels itself, the first reflection rays ride in k_shadow's grid, and what depends on them
     // (per-light any-hit rays, shading, stragglers) follows the shadow pass on the third stream, beside the filter and the resolve
@@ -1093,6 +1099,7 @@ int vkp_render(vkp_ctx* ctx)
         }
         if ((r = run_one(ctx, L, seq[i])) != VKP_OK) return r;
         if (seq[i] == VKP_STAGE_GBUFFER && seeds) { L.frame.seed_w = nullptr; L.frame.seed_r = ctx->seed.as<uint32_t>(); }
+        if (seq[i] == VKP_STAGE_GBUFFER && sky_codes) { L.frame.sky_shadow_w = nullptr; L.frame.sky_shadow_r = ctx->sky_shadow.as<short>(); }
         if (seq[i] == VKP_STAGE_GBUFFER && chained) {
             // fork: the reflection chain needs only the G-buffer; it overlaps the shadow + denoise passes on its own stream
             CK(cudaEventRecord(ctx->ev_gbuffer, ctx->stream));

@@ -162,6 +162,8 @@ struct DFrame {
     int2* hit_ids;
     uint32_t* seed_w;               // k_gbuffer writes tea(pixel, frame) here (NULL: not wanted) ...
     const uint32_t* seed_r;         // ... and the later stages of the same frame read it (NULL: evaluate TEA; see pixel_seed)
+    short* sky_shadow_w;            // k_gbuffer (block 0) writes, per light, the shadow byte of a sky pixel or -1 if sky pixels trace towards it ...
+    const short* sky_shadow_r;      // ... and k_shadow of the same frame reads it (NULL: every thread does the arithmetic)
     float4* final_f32;
     uchar4* final_srgb8;
     uint8_t* shadow;      // n_lights planes
