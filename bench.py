@@ -114,7 +114,8 @@ def stats_ms(xs):
     xs = np.asarray(xs, dtype=np.float64)
     if xs.size == 0:
         return None
-    return {"min": float(xs.min()), "median": float(np.median(xs)), "max": float(xs.max()), "mean": float(xs.mean()), "n": int(xs.size)}
+    return {"min": float(xs.min()), "median": float(np.median(xs)), "max": float(xs.max()), "mean": float(xs.mean()), "n": int(xs.size),
+            "argmax": int(xs.argmax())}
 
 
 # ------------------------------------------------------------------------------------------------ the CPU oracle, timed ----
@@ -349,6 +350,8 @@ def main():
     trav = np.zeros(3, dtype=np.int64)
     launches = 0
     frame_times = []
+    import gc
+    gc.collect(); gc.disable()          # no collector pause while frames are being queued (at N = 8 the host is only ~1.5x ahead of the device)
     barrier()
     total_ms = 0.0
     if world == 1:
@@ -396,6 +399,7 @@ def main():
             stage_ms += np.array(list(c.ms_stage)) * (args.steps / n_prof)
             frame += 1
     barrier()
+    gc.enable()
     # one extra, untimed frame with traversal accounting on: what the rays actually requested from memory
     ctx.set_profiling(2)
     tr.render(params(frame))
