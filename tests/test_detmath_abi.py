@@ -131,3 +131,18 @@ def test_product_package_never_imports_the_oracle():
                 # comments may name the oracle; nothing may include, import, link or load it
                 assert "liboracle" not in text and "oracle_py" not in text and "oracle/" not in text and "orc_" not in text, os.path.join(dirpath, f)
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), os.path.join(dirpath, f)
+
+
+def test_group_entry_points_validate_their_arguments_without_a_gpu():
+    """vkp_group_* (include/vkp.h "multi-GPU group"): argument errors are reported before any CUDA call, so this runs on the CPU box."""
+    import ctypes as C
+    L = vk.load_vkp()
+    assert L.vkp_group_size(None) == 0
+    assert L.vkp_group_member(None, 0) is None
+    g = C.c_void_p()
+    devs = (C.c_int * 1)(0)
+    assert L.vkp_group_create(C.byref(g), devs, 0, 32, 16) == -1 and not g.value            # VKP_ERR_INVALID: no devices
+    assert L.vkp_group_create(C.byref(g), devs, 65, 32, 16) == -1 and not g.value           # more than 64 ranks
+    assert L.vkp_group_create(None, devs, 1, 32, 16) == -1
+    assert L.vkp_group_render(None) == -1 and L.vkp_group_sync(None) == -1
+    L.vkp_group_destroy(None)                                                               # a no-op, like free(NULL)

@@ -2511,9 +2511,7 @@ cudaError_t launch_chain(const FrameLaunch& L, cudaStream_t stream, cudaEvent_t 
         }
         k_chain_q<<<(unsigned)(per_sm6 * n_sm6), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame, tag, cont_cap);
     } else if (L.frame.p.wavefront == 3) k_chain_warp<<<148 * VKP_LB_CHAIN, VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);
-    else if (L.frame.p.wavefront >= 7 && getenv("VKP_TIMING_SKIP_LONG")) {
-        // timing experiments only (the image is then wrong): schedule 7 without its long-path kernel
-    } else if (L.frame.p.wavefront >= 7 && chain_long_by_quad()) {
+    else if (L.frame.p.wavefront >= 7 && chain_long_by_quad()) {
         static int n_smq = 0;
         if (!n_smq) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_smq, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_smq <= 0) n_smq = 148; }
         k_chain_quad<<<(unsigned)(VKP_LB_CHAIN * n_smq), VKP_TRAV_BLOCK, 0, stream>>>(L.scene, L.frame);

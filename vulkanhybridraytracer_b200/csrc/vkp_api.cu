@@ -1125,7 +1125,6 @@ int vkp_render(vkp_ctx* ctx)
             if (ctx->params.wavefront == 7) {
                 // the bulk of the paths (predicted to end after one bounce) through the lean staged kernels, beside k_chain's long ones
                 CK(cudaStreamWaitEvent(ctx->chain_stream2, ctx->ev_scan, 0));
-                if (!getenv("VKP_TIMING_SKIP_STAGED"))         // timing experiments only (the image is then wrong): which half ends the chain?
                 CK(launch_chain_staged(L, ctx->chain_stream2));
                 CK(cudaEventRecord(ctx->ev_chain2, ctx->chain_stream2));
                 CK(cudaStreamWaitEvent(ctx->chain_stream, ctx->ev_chain2, 0));       // ev_chain below then means: both halves are done
