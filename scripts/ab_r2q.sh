@@ -1,4 +1,5 @@
-TAG=r3z; . scripts/ab_r2n.sh
-run sky A=1
-run nosky VKP_SKY_CODES=0
-run sky2 A=1
+TAG=r4f; . scripts/ab_r2n.sh
+run lb8 A=1
+run lb7 VKP_LIB=$PWD/variants/sh7/libvkp.so
+run lb6 VKP_LIB=$PWD/variants/sh6/libvkp.so
+run lb10 VKP_LIB=$PWD/variants/sh10/libvkp.so
