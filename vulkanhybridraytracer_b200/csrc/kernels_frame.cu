@@ -557,6 +557,26 @@ __global__ void __launch_bounds__(VKP_TRAV_BLOCK, VKP_LB_GBUFFER) k_gbuffer(cons
 // (latency-bound), 5 (96 registers) when it loops over many soft-shadow samples (issue-bound: cfg5).
 // ONE: the frame traces one sample per light (BASELINE configs[1]): no sample loop, so nothing of the light / G-buffer state
 // stays in registers across the traversal.
+// The shadow byte of (pixel i, light l), and -- on accumulation frames (blur.comp:41-48: out = mix(history, in, 1 / (frame + 1)), no
+// neighbourhood) -- the filter's new history byte with it: the thread that has just produced the filter's only fresh input applies
+// the filter, and the frame has one dependent pass less (F.fuse_accumulate; the arithmetic is denoise_pixel's).
+__device__ __forceinline__ void store_shadow(const DFrame& F, int l, size_t plane, size_t i, int x, int y, uint8_t value)
+{
+    F.shadow[l * plane + i] = value;
+    if (F.fuse_accumulate) {
+        const int Wc = F.p.denoise_cover_remainder ? F.p.width : (F.p.width / 16) * 16;
+        const int Hc = F.p.denoise_cover_remainder ? F.p.height : (F.p.height / 16) * 16;
+        const uint8_t hist = F.denoised[l * plane + i];
+        uint8_t out = hist;
+        if (x < Wc && y < Hc) {
+            const float center = unit255(value), old = unit255(hist);
+            const float a = 1.0f / (float)((float)F.p.denoise_frame + 1.0f);
+            out = vkp_unorm8(mix1(old, center, a));
+        }
+        F.denoised_next[l * plane + i] = out;
+    }
+}
+
 template <bool ONE>
 __device__ __forceinline__ void shadow_patch(const DScene& S, const DFrame& F, uint32_t* __restrict__ sstack, const unsigned int vb, const int warp_override,
                                              unsigned int& nrays, TravCount& tc, TravCount* const tcp, int& l_out, Pixel& px_out)
@@ -573,7 +593,7 @@ __device__ __forceinline__ void shadow_patch(const DScene& S, const DFrame& F, u
         if (F.sky_shadow_r && (praw.x | praw.y | nraw.x | nraw.y) == 0u) {
             // a sky pixel (all-zero planes): the per-light answer k_gbuffer's block 0 left, unless sky pixels trace towards this light
             const int code = (int)F.sky_shadow_r[l];
-            if (code >= 0) { F.shadow[l * plane + i] = (uint8_t)code; return; }
+            if (code >= 0) { store_shadow(F, l, plane, i, px.x, px.y, (uint8_t)code); return; }
         }
         float4 pos4 = unpack_half4(praw);
         float4 nrm4 = unpack_half4(nraw);
@@ -581,7 +601,7 @@ __device__ __forceinline__ void shadow_patch(const DScene& S, const DFrame& F, u
         float3 normal = xyz(nrm4) * 2.0f - f3s(1.0f);
         int mode = (int)material_by_float_index(S, pos4.w).shadingMetallicRoughness[0];
         if (mode == 4) {
-            F.shadow[l * plane + i] = 255;
+            store_shadow(F, l, plane, i, px.x, px.y, 255);
         } else {
             float3 N = normalize3(normal);
             const int shadowSamples = F.p.shadow_samples;
@@ -615,7 +635,7 @@ __device__ __forceinline__ void shadow_patch(const DScene& S, const DFrame& F, u
                 }
                 shadowFactor /= (float)shadowSamples;
             }
-            F.shadow[l * plane + i] = vkp_unorm8(shadowFactor);
+            store_shadow(F, l, plane, i, px.x, px.y, vkp_unorm8(shadowFactor));
         }
     }
 }

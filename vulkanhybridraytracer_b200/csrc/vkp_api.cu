@@ -92,6 +92,7 @@ struct vkp_ctx {
     int schedule = 1;                 // 0 = hardware block order, 1 = longest first (VKP_SCHEDULE=0|1)
     int prefetch = 0;                 // VKP_PREFETCH: 1 = stream the BVH arena into L2 at the start of every frame, 2 = vertex / index buffers too
     cudaEvent_t ev_prefetch = nullptr;
+    bool fuse_accumulate = true;      // VKP_FUSE_ACCUMULATE=0: accumulation frames keep their own filter pass (k_denoise_accumulate4)
     bool use_sky_codes = true;        // VKP_SKY_CODES=0: every sky pixel redoes its light arithmetic in k_shadow
     DevBuf sky_shadow;
     bool shadow_wait_scan = false;
@@ -365,7 +366,7 @@ int make_launch(vkp_ctx* ctx, FrameLaunch& L)
     F.tile_w = ctx->tile_w; F.tile_h = ctx->tile_h;
     F.tiles_x = (F.p.width + F.tile_w - 1) / F.tile_w; F.tiles_y = (F.p.height + F.tile_h - 1) / F.tile_h;
     F.rank = ctx->rank; F.world = ctx->world;
-    F.fused = 0;
+    F.fused = 0; F.fuse_accumulate = 0;
     F.count_trav = ctx->count_trav ? 1 : 0;
     F.static_camera = memcmp(F.cam.view, F.cam.prev_view, 64) == 0 && memcmp(F.cam.proj, F.cam.prev_proj, 64) == 0;
     F.position = ctx->position.as<uint2>(); F.normal = ctx->normal.as<uint2>(); F.albedo = ctx->albedo.as<uchar4>();
@@ -552,6 +553,10 @@ int run_one(vkp_ctx* ctx, FrameLaunch& L, int stage)
         break;
     }
     case VKP_STAGE_DENOISE:
+        if (L.frame.fuse_accumulate) {
+            // k_shadow has already written the new history (store_shadow): only the ping-pong flips
+            ctx->last_launches--;          // (run_one counts one launch per stage below)
+        } else
         if (L.frame.p.denoiser == 1) {
             // the a-trous taps reach 8 pixels across tile borders: one GPU only (a tile-sharded frame would need a halo exchange every frame)
             if (L.frame.world > 1) return fail(ctx, VKP_ERR_INVALID, "vkp_params.denoiser = 1 (a-trous) is not available on a tile-sharded frame (world > 1)");
@@ -656,6 +661,7 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
         if (const char* e = getenv("VKP_SEED_PLANE")) ctx->use_seed_plane = atoi(e) != 0;
         if (const char* e = getenv("VKP_PREFETCH")) ctx->prefetch = atoi(e);
         if (const char* e = getenv("VKP_SKY_CODES")) ctx->use_sky_codes = atoi(e) != 0;
+        if (const char* e = getenv("VKP_FUSE_ACCUMULATE")) ctx->fuse_accumulate = atoi(e) != 0;
         if (const char* e = getenv("VKP_SHADOW_WAIT_SCAN")) ctx->shadow_wait_scan = atoi(e) != 0;
         if (const char* e = getenv("VKP_DEBUG_CHAIN_TIMING")) ctx->debug_chain_timing = atoi(e) != 0;
         if (const char* e = getenv("VKP_SCAN_IN_GBUFFER")) ctx->scan_in_gbuffer = atoi(e) != 0;
@@ -1070,6 +1076,10 @@ int vkp_render(vkp_ctx* ctx)
     if (fused) { seq = hybrid_fused; n = 3; L.frame.fused = 1; }
     if (ctx->params.mode == VKP_MODE_RAYTRACING) { seq = rt; n = 1; }
     else if (ctx->params.mode == VKP_MODE_DEFERRED) { seq = deferred; n = 2; }
+    // accumulation frames (denoise_frame > 0): blur.comp is a per-pixel blend, applied by the shadow threads themselves (VKP_FUSE_ACCUMULATE=0: own pass)
+    if (ctx->params.mode == VKP_MODE_HYBRID && !fused && ctx->params.denoiser == 0 && ctx->params.denoise_frame > 0 && ctx->params.shadow_samples < 4 &&
+        ctx->fuse_accumulate && !ctx->lights.empty())
+        L.frame.fuse_accumulate = 1;
     const bool seeds = ctx->params.mode == VKP_MODE_HYBRID && ctx->use_seed_plane;
     if (seeds) L.frame.seed_w = ctx->seed.as<uint32_t>();
     const bool sky_codes = ctx->params.mode == VKP_MODE_HYBRID && ctx->use_sky_codes;

@@ -151,6 +151,7 @@ struct DFrame {
     int tile_w, tile_h, tiles_x, tiles_y, rank, world;
     int count_trav;       // accumulate node fetches / triangle tests / instance entries into counters[4..6]
     int fused;            // k_resolve also runs the shadow filter (vkp_render); 0 when the stages are run one by one
+    int fuse_accumulate;  // accumulation frames inside vkp_render: k_shadow's threads write the filter's new history byte themselves (no filter pass)
     int static_camera;    // prev_view/prev_proj are bit-identical to view/proj: motion vectors are exactly 0
     // planes
     uint2* position;      // 4 x fp16
