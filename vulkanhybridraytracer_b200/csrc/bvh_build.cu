@@ -282,7 +282,9 @@ __global__ void k_emit_triangles(const vkp_vertex* __restrict__ verts, const uin
 // whose union has the smallest surface area, mutual nearest neighbours merge, the cluster list is compacted with a prefix
 // sum, repeat until one cluster is left.  Tree quality is close to a full SAH sweep and far better than the Karras radix
 // tree for long thin triangles (sphere poles) and grazing rays -- which is what sets the frame kernels' tail latency.
-#define PLOC_R 16
+#ifndef PLOC_R
+#define PLOC_R 16                   /* search radius; 8 / 32 / 64 measured: see DESIGN.md section 4c */
+#endif
 #define PLOC_BS 256
 
 __device__ __forceinline__ float half_area(float4 lo, float4 hi)

@@ -140,6 +140,7 @@ struct vkp_ctx {
     DevBuf bvh_arena;
     int l2_persist = -1;          // -1 built-in default, 0 off, 1 on (vkp_set_l2_persistence / VKP_L2_PERSIST)
     size_t l2_set_aside = 0;
+    int blas_leaf_max = 4; // triangles per BLAS leaf (the traversal's leaf loop holds 4; VKP_LEAF_MAX=1..4 is a measurement knob)
     int builder = 1;      // BLAS hierarchy: 0 = Karras LBVH, 1 = PLOC (default; VKP_BLAS_BUILDER=lbvh|ploc or vkp_set_builder)
 };
 
@@ -677,6 +678,7 @@ int vkp_create(vkp_ctx** out, int device_ordinal)
         if ((e = launch_set_carveout(pct)) != cudaSuccess) { vkp_destroy(ctx); return cuda_fail(nullptr, e, "cudaFuncSetAttribute(carveout)"); }
     }
     if (const char* b = getenv("VKP_BLAS_BUILDER")) ctx->builder = (strcmp(b, "lbvh") == 0) ? 0 : 1;
+    if (const char* e = getenv("VKP_LEAF_MAX")) { const int v = atoi(e); if (v >= 1 && v <= 4) ctx->blas_leaf_max = v; }
     if (const char* l = getenv("VKP_L2_PERSIST")) ctx->l2_persist = atoi(l) != 0;
     cudaEventCreate(&ctx->timer0); cudaEventCreate(&ctx->timer1);
     // decode / gamma tables, computed on the device with the contract's own vkp_powf so they are bit-identical to the call
@@ -885,7 +887,7 @@ int vkp_build_blas(vkp_ctx* ctx)
             const uint32_t ntri = b.count / 3u;
             const uint32_t* idx = m.idx.as<uint32_t>() + b.first;
             CK(bvh_triangle_boxes(ctx->stream, m.verts.as<vkp_vertex>(), idx, ntri, ctx->scratch.boxes.as<float>()));
-            CK(bvh_build(ctx->stream, ctx->scratch, ntri, 4, b.bvh, &ctx->build_launches, ctx->builder, &host_syncs, ctx->build_results + k, true));
+            CK(bvh_build(ctx->stream, ctx->scratch, ntri, ctx->blas_leaf_max, b.bvh, &ctx->build_launches, ctx->builder, &host_syncs, ctx->build_results + k, true));
             CK(bvh_emit_triangles(ctx->stream, m.verts.as<vkp_vertex>(), idx, b.bvh));
             ctx->build_launches += 2;      // k_triangle_boxes, k_emit_triangles
             built_tris += ntri;
@@ -900,7 +902,7 @@ int vkp_build_blas(vkp_ctx* ctx)
                 const uint32_t ntri = b.count / 3u;
                 const uint32_t* idx = m.idx.as<uint32_t>() + b.first;
                 CK(bvh_triangle_boxes(ctx->stream, m.verts.as<vkp_vertex>(), idx, ntri, ctx->scratch.boxes.as<float>()));
-                CK(bvh_build(ctx->stream, ctx->scratch, ntri, 4, b.bvh, &ctx->build_launches, ctx->builder, &host_syncs, nullptr, true));
+                CK(bvh_build(ctx->stream, ctx->scratch, ntri, ctx->blas_leaf_max, b.bvh, &ctx->build_launches, ctx->builder, &host_syncs, nullptr, true));
                 CK(bvh_emit_triangles(ctx->stream, m.verts.as<vkp_vertex>(), idx, b.bvh));
                 ctx->bstats_rebuilt++;
             }
