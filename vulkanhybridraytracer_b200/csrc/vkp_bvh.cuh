@@ -32,6 +32,12 @@
 #define VKP_SSTACK 16                /* stack levels kept in shared memory: 16 * 128 * 4 B = 8 KB per CTA */
 #endif
 #define VKP_TRAV_SMEM_WORDS (VKP_SSTACK * VKP_TRAV_BLOCK)
+#ifndef VKP_PF_CLOSEST
+#define VKP_PF_CLOSEST 0             /* 1: closest-hit rays prefetch the far child they push (measured: no gain) */
+#endif
+#ifndef VKP_PF_ANY
+#define VKP_PF_ANY 0                 /* 1: any-hit rays too */
+#endif
 
 struct HitRec {
     float t, u, v;
@@ -281,7 +287,15 @@ __device__ __forceinline__ bool trace_ray(const DScene& S, uint32_t* __restrict_
                 const uint32_t r0 = __float_as_uint(lo0.w), r1 = __float_as_uint(lo1.w);
                 if (h0 && h1) {
                     const bool swap = t1 < t0;
-                    VKP_PUSH(swap ? r0 : r1);
+                    const uint32_t far_ref = swap ? r0 : r1;
+                    VKP_PUSH(far_ref);
+                    // (A/B knob, off: measured slower) the far child is walked after the whole near subtree -- ask for its child pair (or its
+                    // first triangles) now, so that the pop finds it in L1 instead of starting a dependent L2 round trip
+                    if (ANY ? (VKP_PF_ANY != 0) : (VKP_PF_CLOSEST != 0)) {
+                        const float4* pf = (far_ref & VKP_LEAF_BIT) ? (inst >= 0 ? tris + 3u * (size_t)((far_ref & 0x7fffffffu) >> 3) : nullptr)
+                                                                    : nodes + 2u * (size_t)far_ref;
+                        if (pf) asm volatile("prefetch.global.L1 [%0];" :: "l"(pf));
+                    }
                     cur = swap ? r1 : r0;
                 } else if (h0) cur = r0;
                 else if (h1) cur = r1;
