@@ -612,6 +612,11 @@ def main():
     bvh_bytes = 32.0 * (T / 2.0) + 48.0 * T             # ~T/2 nodes of 32 B (<= 4-triangle leaves) + 48 B per leaf-ordered triangle
     plane_bytes = {"k_gbuffer": Pr * 40, "k_shadow": Pr * (16 + L), "k_denoise": Pr * (2 * L + 4 + L), "k_resolve": Pr * (32 + L + 16 + 4),
                    "k_raytrace": Pr * (16 + 16 + 4)}
+    # accumulation frames (every timed frame here): k_shadow's threads read the history byte and write the new one themselves and the filter
+    # pass is not launched (library default; VKP_FUSE_ACCUMULATE=0 or --fuse-denoise keep / move the pass) -- the bytes move with the work
+    if mode == 2 and samples < 4 and not args.fuse_denoise and os.environ.get("VKP_FUSE_ACCUMULATE", "1") != "0":
+        plane_bytes["k_shadow"] += Pr * 2 * L
+        plane_bytes["k_denoise"] = 0.0
     ray_count = {"k_gbuffer": per_frame[0], "k_shadow": per_frame[1], "k_denoise": 0.0, "k_resolve": per_frame[2] + per_frame[3],
                  "k_raytrace": per_frame[2] + per_frame[3]}
     kbytes = {k: plane_bytes[k] + min(ray_count[k] * BR, bvh_bytes if ray_count[k] > 0 else 0.0) for k in plane_bytes}
